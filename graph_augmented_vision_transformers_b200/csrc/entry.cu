@@ -1,0 +1,158 @@
+// entry.cu - the extern "C" surface declared in include/gvit.h: argument validation and routing.
+// bf16 requests go to the tcgen05/TMEM/TMA kernels whenever the shape is in their range and to the
+// fp32-FMA kernels (bf16 storage, fp32 arithmetic) otherwise; fp32 requests always run exact FMA.
+#include "kernels.cuh"
+
+using namespace gvit;
+
+namespace {
+
+inline int check_dtype(int dtype, const char* who) {
+  if (dtype != GVIT_F32 && dtype != GVIT_BF16) return fail(GVIT_ERR_DTYPE, "%s: dtype %d is not GVIT_F32/GVIT_BF16", who, dtype);
+  return GVIT_OK;
+}
+
+inline int check_tokens(const char* who, const void* p, int64_t bs, int64_t rs, int B, int Np, int D, int k) {
+  GVIT_REQUIRE(p != nullptr, GVIT_ERR_SHAPE, "%s: null token pointer", who);
+  GVIT_REQUIRE(B >= 1 && Np >= 1 && D >= 8, GVIT_ERR_SHAPE, "%s: bad sizes B=%d Np=%d D=%d", who, B, Np, D);
+  GVIT_REQUIRE(D % 8 == 0 && D <= 1024, GVIT_ERR_SHAPE, "%s: D=%d must be a multiple of 8 and <= 1024", who, D);
+  GVIT_REQUIRE(k >= 1 && k <= GVIT_MAX_K && k <= Np, GVIT_ERR_SHAPE, "%s: k=%d out of range [1, min(Np=%d, %d)]", who, k, Np, GVIT_MAX_K);
+  GVIT_REQUIRE(rs >= D && rs % 8 == 0 && bs % 8 == 0 && bs >= 0, GVIT_ERR_ALIGN, "%s: strides (%lld, %lld) must be multiples of 8 elements", who, (long long)bs, (long long)rs);
+  GVIT_REQUIRE(aligned16(p), GVIT_ERR_ALIGN, "%s: token pointer must be 16-byte aligned", who);
+  return GVIT_OK;
+}
+
+#define TRY(expr)            \
+  do {                       \
+    int rc__ = (expr);       \
+    if (rc__ != GVIT_OK) return rc__; \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int gvit_knn_fwd(const void* p, int64_t batch_stride, int64_t row_stride, int B, int Np, int D, int k, int dtype,
+                 int32_t* idx, float* vals, float* rnorm, void* stream) {
+  TRY(check_dtype(dtype, "knn_fwd"));
+  TRY(check_tokens("knn_fwd", p, batch_stride, row_stride, B, Np, D, k));
+  GVIT_REQUIRE(idx && vals && rnorm, GVIT_ERR_SHAPE, "knn_fwd: null output");
+  Tokens t{p, batch_stride, row_stride, B, Np, D};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == GVIT_BF16 && knn_tc_supported(Np, D, k)) return knn_fwd_tc(t, k, idx, vals, rnorm, st);
+  return knn_fwd_simt(t, k, dtype, idx, vals, rnorm, st);
+}
+
+int gvit_graph_reverse(const int32_t* idx, int B, int Np, int k, int32_t* rev_ptr, int32_t* rev_src, void* stream) {
+  GVIT_REQUIRE(idx && rev_ptr && rev_src, GVIT_ERR_SHAPE, "graph_reverse: null pointer");
+  GVIT_REQUIRE(B >= 1 && Np >= 1 && k >= 1 && k <= GVIT_MAX_K && k <= Np, GVIT_ERR_SHAPE, "graph_reverse: bad sizes B=%d Np=%d k=%d", B, Np, k);
+  return graph_reverse(idx, B, Np, k, rev_ptr, rev_src, static_cast<cudaStream_t>(stream));
+}
+
+int gvit_knn_bwd(const void* p, int64_t batch_stride, int64_t row_stride, int B, int Np, int D, int k, int dtype,
+                 const int32_t* idx, const float* rnorm, const float* dvals, const int32_t* rev_ptr,
+                 const int32_t* rev_src, void* dp, void* stream) {
+  TRY(check_dtype(dtype, "knn_bwd"));
+  TRY(check_tokens("knn_bwd", p, batch_stride, row_stride, B, Np, D, k));
+  GVIT_REQUIRE(idx && rnorm && dvals && rev_ptr && rev_src && dp, GVIT_ERR_SHAPE, "knn_bwd: null pointer");
+  GVIT_REQUIRE(aligned16(dp), GVIT_ERR_ALIGN, "knn_bwd: dp must be 16-byte aligned");
+  Tokens t{p, batch_stride, row_stride, B, Np, D};
+  return knn_bwd_simt(t, k, dtype, idx, rnorm, dvals, rev_ptr, rev_src, dp, static_cast<cudaStream_t>(stream));
+}
+
+int gvit_agg_gather_fwd(const void* p, int64_t batch_stride, int64_t row_stride, int B, int Np, int D, int k,
+                        int dtype, const int32_t* idx, const float* vals, float* w, void* z, void* stream) {
+  TRY(check_dtype(dtype, "agg_gather_fwd"));
+  TRY(check_tokens("agg_gather_fwd", p, batch_stride, row_stride, B, Np, D, k));
+  GVIT_REQUIRE(idx && vals && w && z, GVIT_ERR_SHAPE, "agg_gather_fwd: null pointer");
+  GVIT_REQUIRE(aligned16(z), GVIT_ERR_ALIGN, "agg_gather_fwd: z must be 16-byte aligned");
+  Tokens t{p, batch_stride, row_stride, B, Np, D};
+  return agg_gather_fwd_simt(t, k, dtype, idx, vals, w, z, static_cast<cudaStream_t>(stream));
+}
+
+int gvit_agg_fwd(const void* h, int B, int Np, int D, int k, int dtype, const int32_t* idx, const float* vals,
+                 const void* Wg, const void* bias, const void* resid, void* out, float* w_save, void* z_save,
+                 void* stream) {
+  TRY(check_dtype(dtype, "agg_fwd"));
+  GVIT_REQUIRE(h && idx && vals && Wg && out, GVIT_ERR_SHAPE, "agg_fwd: null pointer");
+  GVIT_REQUIRE(B >= 1 && Np >= 1 && k >= 1 && k <= GVIT_MAX_K && k <= Np, GVIT_ERR_SHAPE, "agg_fwd: bad sizes B=%d Np=%d k=%d", B, Np, k);
+  GVIT_REQUIRE(dtype == GVIT_BF16, GVIT_ERR_UNSUPPORTED,
+               "agg_fwd: the fused kernel is bf16-only; fp32 composes gvit_agg_gather_fwd with a library GEMM");
+  GVIT_REQUIRE(agg_tc_supported(Np, D, k), GVIT_ERR_UNSUPPORTED, "agg_fwd: shape Np=%d D=%d k=%d outside the fused kernel's range", Np, D, k);
+  GVIT_REQUIRE(aligned16(h) && aligned16(Wg) && aligned16(out) && (!resid || aligned16(resid)) && (!z_save || aligned16(z_save)),
+               GVIT_ERR_ALIGN, "agg_fwd: pointers must be 16-byte aligned");
+  return agg_fwd_tc(h, B, Np, D, k, idx, vals, Wg, bias, resid, out, w_save, z_save, static_cast<cudaStream_t>(stream));
+}
+
+int gvit_agg_bwd(const void* p, int64_t batch_stride, int64_t row_stride, int B, int Np, int D, int k, int dtype,
+                 const int32_t* idx, const float* w, const void* dz, const int32_t* rev_ptr, const int32_t* rev_src,
+                 float* dvals, void* dp, void* stream) {
+  TRY(check_dtype(dtype, "agg_bwd"));
+  TRY(check_tokens("agg_bwd", p, batch_stride, row_stride, B, Np, D, k));
+  GVIT_REQUIRE(idx && w && dz && rev_ptr && rev_src && dvals && dp, GVIT_ERR_SHAPE, "agg_bwd: null pointer");
+  GVIT_REQUIRE(aligned16(dz) && aligned16(dp), GVIT_ERR_ALIGN, "agg_bwd: dz/dp must be 16-byte aligned");
+  Tokens t{p, batch_stride, row_stride, B, Np, D};
+  return agg_bwd_simt(t, k, dtype, idx, w, dz, rev_ptr, rev_src, dvals, dp, static_cast<cudaStream_t>(stream));
+}
+
+int gvit_attn_fwd(const void* qkv, int B, int N, int H, int dh, float scale, int dtype, void* out, float* lse,
+                  void* stream) {
+  TRY(check_dtype(dtype, "attn_fwd"));
+  GVIT_REQUIRE(qkv && out && lse, GVIT_ERR_SHAPE, "attn_fwd: null pointer");
+  GVIT_REQUIRE(B >= 1 && N >= 1 && H >= 1 && B <= 65535 && H <= 65535, GVIT_ERR_SHAPE, "attn_fwd: bad sizes B=%d N=%d H=%d", B, N, H);
+  GVIT_REQUIRE(aligned16(qkv) && aligned16(out), GVIT_ERR_ALIGN, "attn_fwd: qkv/out must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == GVIT_BF16 && attn_fwd_tc_supported(N, dh)) return attn_fwd_tc(qkv, B, N, H, scale, out, lse, st);
+  return attn_fwd_simt(qkv, B, N, H, dh, scale, dtype, out, lse, st);
+}
+
+int gvit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int B, int N, int H, int dh,
+                  float scale, int dtype, float* delta_ws, void* dqkv, void* stream) {
+  TRY(check_dtype(dtype, "attn_bwd"));
+  GVIT_REQUIRE(qkv && out && dout && lse && delta_ws && dqkv, GVIT_ERR_SHAPE, "attn_bwd: null pointer");
+  GVIT_REQUIRE(B >= 1 && N >= 1 && H >= 1 && B <= 65535 && H <= 65535, GVIT_ERR_SHAPE, "attn_bwd: bad sizes B=%d N=%d H=%d", B, N, H);
+  GVIT_REQUIRE(aligned16(qkv) && aligned16(out) && aligned16(dout) && aligned16(dqkv), GVIT_ERR_ALIGN, "attn_bwd: tensors must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == GVIT_BF16 && attn_bwd_tc_supported(N, dh)) return attn_bwd_tc(qkv, out, dout, lse, B, N, H, scale, delta_ws, dqkv, st);
+  return attn_bwd_simt(qkv, out, dout, lse, B, N, H, dh, scale, dtype, delta_ws, dqkv, st);
+}
+
+int gvit_layernorm_fwd(const void* x, const void* gamma, const void* beta, int64_t rows, int D, float eps, int dtype,
+                       void* y, float* mean, float* rstd, void* stream) {
+  TRY(check_dtype(dtype, "layernorm_fwd"));
+  GVIT_REQUIRE(x && gamma && beta && y && mean && rstd, GVIT_ERR_SHAPE, "layernorm_fwd: null pointer");
+  GVIT_REQUIRE(rows >= 1 && D >= 8 && D % 8 == 0 && D <= 1024, GVIT_ERR_SHAPE, "layernorm_fwd: rows=%lld D=%d (D %% 8 == 0, D <= 1024)", (long long)rows, D);
+  GVIT_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta), GVIT_ERR_ALIGN, "layernorm_fwd: 16-byte alignment required");
+  return layernorm_fwd(x, gamma, beta, rows, D, eps, dtype, y, mean, rstd, static_cast<cudaStream_t>(stream));
+}
+
+int gvit_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
+                       int64_t rows, int D, int dtype, void* dx, float* dgamma, float* dbeta, float* partial_ws,
+                       void* stream) {
+  TRY(check_dtype(dtype, "layernorm_bwd"));
+  GVIT_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && partial_ws, GVIT_ERR_SHAPE, "layernorm_bwd: null pointer");
+  GVIT_REQUIRE(rows >= 1 && D >= 8 && D % 8 == 0 && D <= 1024, GVIT_ERR_SHAPE, "layernorm_bwd: rows=%lld D=%d (D %% 8 == 0, D <= 1024)", (long long)rows, D);
+  GVIT_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(gamma), GVIT_ERR_ALIGN, "layernorm_bwd: 16-byte alignment required");
+  return layernorm_bwd(dy, x, gamma, mean, rstd, rows, D, dtype, dx, dgamma, dbeta, partial_ws, static_cast<cudaStream_t>(stream));
+}
+
+int gvit_dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, uint64_t seed, uint64_t offset,
+                              int dtype, void* out, uint8_t* keep_mask, void* stream) {
+  TRY(check_dtype(dtype, "dropout_residual_fwd"));
+  GVIT_REQUIRE(y && out, GVIT_ERR_SHAPE, "dropout_residual_fwd: null pointer");
+  GVIT_REQUIRE(n >= 8 && n % 8 == 0, GVIT_ERR_SHAPE, "dropout_residual_fwd: n=%lld must be a positive multiple of 8", (long long)n);
+  GVIT_REQUIRE(p >= 0.f && p < 1.f, GVIT_ERR_SHAPE, "dropout_residual_fwd: p=%f not in [0,1)", p);
+  GVIT_REQUIRE(p == 0.f || keep_mask, GVIT_ERR_SHAPE, "dropout_residual_fwd: keep_mask required when p > 0");
+  GVIT_REQUIRE(aligned16(y) && aligned16(out) && (!resid || aligned16(resid)) && (!keep_mask || aligned16(keep_mask)), GVIT_ERR_ALIGN, "dropout_residual_fwd: 16-byte alignment required");
+  return dropout_residual_fwd(y, resid, n, p, seed, offset, dtype, out, keep_mask, static_cast<cudaStream_t>(stream));
+}
+
+int gvit_dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, void* dy, void* stream) {
+  TRY(check_dtype(dtype, "dropout_bwd"));
+  GVIT_REQUIRE(dout && keep_mask && dy, GVIT_ERR_SHAPE, "dropout_bwd: null pointer");
+  GVIT_REQUIRE(n >= 8 && n % 8 == 0 && p > 0.f && p < 1.f, GVIT_ERR_SHAPE, "dropout_bwd: n=%lld p=%f", (long long)n, p);
+  GVIT_REQUIRE(aligned16(dout) && aligned16(dy) && aligned16(keep_mask), GVIT_ERR_ALIGN, "dropout_bwd: 16-byte alignment required");
+  return dropout_bwd(dout, keep_mask, n, p, dtype, dy, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

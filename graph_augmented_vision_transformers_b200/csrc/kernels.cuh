@@ -1,0 +1,48 @@
+// kernels.cuh - internal launchers; entry.cu validates arguments and routes to these.
+#pragma once
+#include "common.cuh"
+
+namespace gvit {
+
+struct Tokens {            // strided view of the (B, Np, D) patch tokens inside a (B, 1+Np, D) tensor
+  const void* ptr;
+  int64_t batch_stride, row_stride;   // in elements
+  int B, Np, D;
+};
+
+// ---- exact fp32-FMA kernels (templated on the storage type) : knn_simt.cu, graph_simt.cu, attn_simt.cu
+int knn_fwd_simt(const Tokens& p, int k, int dtype, int32_t* idx, float* vals, float* rnorm, cudaStream_t st);
+int graph_reverse(const int32_t* idx, int B, int Np, int k, int32_t* rev_ptr, int32_t* rev_src, cudaStream_t st);
+int knn_bwd_simt(const Tokens& p, int k, int dtype, const int32_t* idx, const float* rnorm, const float* dvals,
+                 const int32_t* rev_ptr, const int32_t* rev_src, void* dp, cudaStream_t st);
+int agg_gather_fwd_simt(const Tokens& p, int k, int dtype, const int32_t* idx, const float* vals, float* w, void* z,
+                        cudaStream_t st);
+int agg_bwd_simt(const Tokens& p, int k, int dtype, const int32_t* idx, const float* w, const void* dz,
+                 const int32_t* rev_ptr, const int32_t* rev_src, float* dvals, void* dp, cudaStream_t st);
+int attn_fwd_simt(const void* qkv, int B, int N, int H, int dh, float scale, int dtype, void* out, float* lse,
+                  cudaStream_t st);
+int attn_bwd_simt(const void* qkv, const void* out, const void* dout, const float* lse, int B, int N, int H, int dh,
+                  float scale, int dtype, float* delta_ws, void* dqkv, cudaStream_t st);
+
+// ---- tcgen05 / TMEM / TMA kernels (bf16 storage, fp32 accumulate) : knn_tc.cu, agg_tc.cu, attn_tc.cu
+bool knn_tc_supported(int Np, int D, int k);
+int knn_fwd_tc(const Tokens& p, int k, int32_t* idx, float* vals, float* rnorm, cudaStream_t st);
+bool agg_tc_supported(int Np, int D, int k);
+int agg_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, const float* vals, const void* Wg,
+               const void* bias, const void* resid, void* out, float* w_save, void* z_save, cudaStream_t st);
+bool attn_fwd_tc_supported(int N, int dh);
+bool attn_bwd_tc_supported(int N, int dh);
+int attn_fwd_tc(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, cudaStream_t st);
+int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, int B, int N, int H,
+                float scale, float* delta_ws, void* dqkv, cudaStream_t st);
+
+// ---- edges : edges.cu
+int layernorm_fwd(const void* x, const void* gamma, const void* beta, int64_t rows, int D, float eps, int dtype,
+                  void* y, float* mean, float* rstd, cudaStream_t st);
+int layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, int64_t rows,
+                  int D, int dtype, void* dx, float* dgamma, float* dbeta, float* partial_ws, cudaStream_t st);
+int dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, uint64_t seed, uint64_t offset,
+                         int dtype, void* out, uint8_t* keep_mask, cudaStream_t st);
+int dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, void* dy, cudaStream_t st);
+
+}  // namespace gvit

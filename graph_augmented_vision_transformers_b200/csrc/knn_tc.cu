@@ -1,0 +1,169 @@
+// knn_tc.cu - graph construction G1-G3 for bf16 tokens on tcgen05 (north_star:
+// "a tiled similarity GEMM fused with a top-k select that emits the adjacency").
+//
+// One CTA per image (Np <= 256 patch tokens).  The Gram matrix G = P P^T is accumulated in TMEM by
+// tcgen05.mma from TMA-staged 64-feature slabs of the image's tokens: the SAME shared-memory slab is the
+// A operand (its rows [128*mt, 128*mt+128)) and the B operand (all rows), so each token is read from HBM
+// exactly once (Np*D*2 bytes per image) and the Np x Np similarity matrix never leaves the SM.
+// bf16 x bf16 products are exact in fp32 and accumulate in fp32, so G matches an fp32 evaluation of the
+// same bf16 tokens to ~1e-6; the norms come from G's diagonal and S_ij = (G_ij * rn_i) * rn_j.
+// Epilogue: thread <-> similarity row (TMEM lane); it streams its row out of TMEM 32 columns at a time and
+// keeps a sorted top-k in registers with a strict ">" insertion, i.e. descending value, ties -> lowest index.
+//
+// Warp roles: 0-3 epilogue of rows 0-127, 4-7 epilogue of rows 128-255, 8 TMA producer, 9 MMA issuer.
+#include <float.h>
+
+#include "kernels.cuh"
+#include "tc.cuh"
+
+namespace gvit {
+namespace {
+
+using namespace tc;
+
+constexpr int STAGES = 4;
+constexpr int STAGE_BYTES = 256 * 128;   // 256 token rows x 64 bf16
+constexpr int THREADS = 320;
+constexpr int TMEM_COLS = 512;           // two 128 x (<=256) fp32 accumulators
+
+struct __align__(8) Ctrl {
+  float rn[256];
+  uint64_t full[STAGES], empty[STAGES], accum_full;
+  uint32_t tmem_base;
+};
+constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + sizeof(Ctrl);
+
+template <int KT>
+__global__ void __launch_bounds__(THREADS, 1) knn_tc_kernel(const __grid_constant__ CUtensorMap tmap, int Np, int D,
+                                                            int k, int NT, int32_t* __restrict__ idx,
+                                                            float* __restrict__ vals, float* __restrict__ rnorm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* stages = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Ctrl* ctl = reinterpret_cast<Ctrl*>(stages + (size_t)STAGES * STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  const int slabs = D / 64;
+  const int mtiles = Np > 128 ? 2 : 1;
+
+  if (warp == 8 && lane == 0) {
+    prefetch_tmap(&tmap);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
+    mbar_init(&ctl->accum_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc(&ctl->tmem_base, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ctl->tmem_base;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int it = 0; it < slabs; ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&ctl->empty[s], ((it / STAGES) & 1) ^ 1);
+        mbar_expect_tx(&ctl->full[s], (uint32_t)NT * 128u);
+        tma_load_3d(stages + (size_t)s * STAGE_BYTES, &tmap, it * 64, 0, b, &ctl->full[s]);
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, NT, false, false);
+      for (int it = 0; it < slabs; ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&ctl->full[s], (it / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t base = smem_u32(stages + (size_t)s * STAGE_BYTES);
+        for (int mt = 0; mt < mtiles; ++mt)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_ss(tmem + mt * 256, make_sdesc(base + mt * (128 * 128) + kk * 32), make_sdesc(base + kk * 32), idesc,
+                    it > 0 || kk > 0);
+        umma_commit(&ctl->empty[s]);    // slab consumed -> producer may refill it
+      }
+      umma_commit(&ctl->accum_full);    // all MMAs retired -> accumulators readable
+    }
+  } else {
+    const int g = warp >> 2;                              // accumulator tile
+    const int wrow0 = g * 128 + (warp & 3) * 32;          // first similarity row of this warp
+    const int row = wrow0 + lane;
+    const bool active = g < mtiles && wrow0 < Np;         // warp-uniform
+    const uint32_t trow = tmem_lane_base(tmem, warp) + g * 256;
+    float rn_i = 0.f;
+    if (active) {
+      mbar_wait(&ctl->accum_full, 0);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(trow + wrow0, v);                         // the 32x32 block on the diagonal
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) d = (i == lane) ? v[i] : d;
+      rn_i = 1.0f / fmaxf(sqrtf(d), 1e-12f);
+      if (row < Np) { ctl->rn[row] = rn_i; rnorm[(int64_t)b * Np + row] = rn_i; }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");        // the 8 epilogue warps: norms visible
+    if (active) {
+      float tv[KT];
+      int ti[KT];
+#pragma unroll
+      for (int s = 0; s < KT; ++s) { tv[s] = -FLT_MAX; ti[s] = 0x7fffffff; }
+      for (int c0 = 0; c0 < Np; c0 += 32) {
+        float v[32];
+        tmem_ld32(trow + c0, v);
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const int j = c0 + t;
+          if (j < Np) {
+            const float sim = (v[t] * rn_i) * ctl->rn[j];
+            if (sim > tv[KT - 1]) {                       // strict: a later equal column never displaces an earlier one
+              tv[KT - 1] = sim;
+              ti[KT - 1] = j;
+#pragma unroll
+              for (int s = KT - 1; s > 0; --s) {
+                if (tv[s] > tv[s - 1]) {
+                  const float fv = tv[s]; tv[s] = tv[s - 1]; tv[s - 1] = fv;
+                  const int iv = ti[s]; ti[s] = ti[s - 1]; ti[s - 1] = iv;
+                }
+              }
+            }
+          }
+        }
+      }
+      if (row < Np) {
+        const int64_t o = ((int64_t)b * Np + row) * k;
+#pragma unroll
+        for (int s = 0; s < KT; ++s)
+          if (s < k) { idx[o + s] = ti[s]; vals[o + s] = tv[s]; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+template <int KT>
+int launch(const CUtensorMap& tmap, const Tokens& t, int k, int NT, int32_t* idx, float* vals, float* rnorm, cudaStream_t st) {
+  GVIT_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  knn_tc_kernel<KT><<<t.B, THREADS, SMEM_BYTES, st>>>(tmap, t.Np, t.D, k, NT, idx, vals, rnorm);
+  GVIT_CHECK_LAUNCH();
+  return GVIT_OK;
+}
+
+}  // namespace
+
+bool knn_tc_supported(int Np, int D, int k) { return Np >= 16 && Np <= 256 && D >= 64 && D % 64 == 0 && k <= 32; }
+
+int knn_fwd_tc(const Tokens& t, int k, int32_t* idx, float* vals, float* rnorm, cudaStream_t st) {
+  const int NT = (t.Np + 15) & ~15;
+  CUtensorMap tmap;
+  int rc = make_tmap_bf16_3d(&tmap, t.ptr, t.D, t.Np, t.B, t.row_stride, t.batch_stride, NT);
+  if (rc != GVIT_OK) return rc;
+  if (k <= 4) return launch<4>(tmap, t, k, NT, idx, vals, rnorm, st);
+  if (k <= 8) return launch<8>(tmap, t, k, NT, idx, vals, rnorm, st);
+  if (k <= 16) return launch<16>(tmap, t, k, NT, idx, vals, rnorm, st);
+  return launch<32>(tmap, t, k, NT, idx, vals, rnorm, st);
+}
+
+}  // namespace gvit

@@ -1,0 +1,132 @@
+/* gvit.h - C ABI of libgvit.so, the sm_100a implementation of the graph-augmented
+ * ViT hot path (patch-token kNN graph construction, adjacency-weighted
+ * aggregation, multi-head self-attention, and the LayerNorm / residual edges).
+ *
+ * Boundary contract:
+ *   - plain pointers and sizes only; no torch types.  Every pointer is a CUDA
+ *     device pointer owned by the caller (PyTorch's caching allocator on the
+ *     Python side); the library allocates nothing persistent and keeps no
+ *     mutable global state, so calls are re-entrant (PyTorch's autograd worker
+ *     thread calls the *_bwd entry points).
+ *   - `stream` is a cudaStream_t passed as void*; kernels are only ever enqueued
+ *     on it (never on the legacy default stream).
+ *   - return value: 0 = GVIT_OK, otherwise a gvit_status; the message is
+ *     available per thread from gvit_last_error_string().  There is no CPU
+ *     fallback and no alternative backend: unsupported shapes fail loudly.
+ *   - dtype: GVIT_F32 runs exact fp32 FMA kernels (no TF32) - the parity path;
+ *     GVIT_BF16 runs the tcgen05 / TMEM / TMA kernels with fp32 accumulation.
+ *
+ * Each entry point cites the reference interface it replaces, as
+ * /root/reference/<file>:<line>.  The graph stages have no reference symbol
+ * (the reference ships no graph code); they implement SURVEY.md section 9 G0-G6.
+ */
+#ifndef GVIT_H_
+#define GVIT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GVIT_ABI_VERSION 1
+#if defined(__GNUC__)
+#define GVIT_API __attribute__((visibility("default")))
+#else
+#define GVIT_API
+#endif
+
+typedef enum {
+  GVIT_OK = 0,
+  GVIT_ERR_SHAPE = 1,       /* a size is out of the supported range            */
+  GVIT_ERR_ALIGN = 2,       /* a pointer or stride breaks the alignment rules  */
+  GVIT_ERR_DTYPE = 3,       /* dtype is not GVIT_F32 / GVIT_BF16               */
+  GVIT_ERR_CUDA = 4,        /* a CUDA runtime / driver call failed             */
+  GVIT_ERR_UNSUPPORTED = 5  /* valid request this build has no kernel for      */
+} gvit_status;
+
+typedef enum { GVIT_F32 = 0, GVIT_BF16 = 1 } gvit_dtype;
+
+enum { GVIT_MAX_K = 32 };   /* largest neighbour count of the kNN graph */
+
+GVIT_API int gvit_version(void);
+GVIT_API const char* gvit_last_error_string(void);
+
+/* Describes the kernels a request would be routed to (for logs / tests):
+ * writes a short NUL-terminated string such as "knn:tcgen05" into buf. */
+GVIT_API int gvit_describe_path(const char* op, int dtype, int n_tokens, int dim, char* buf, int buf_len);
+
+/* ---- a7: graph construction ---------------------------------------
+ * p      : patch tokens, element (b,i,d) at p[b*batch_stride + i*row_stride + d]; pass
+ *          h + row_stride for a (B,1+Np,D) token tensor so the CLS row (vit.py:207-208) is skipped.
+ * idx    : (B,Np,k) int32, neighbour order = descending similarity, ties -> lowest index.
+ * vals   : (B,Np,k) fp32 cosine similarities of the selected neighbours.
+ * rnorm  : (B,Np) fp32, 1/max(||p_i||,1e-12); saved for gvit_knn_bwd.
+ * Constraints: 1 <= k <= min(Np, GVIT_MAX_K); D % 8 == 0; bf16: Np <= 1024, 16-byte aligned rows. */
+GVIT_API int gvit_knn_fwd(const void* p, int64_t batch_stride, int64_t row_stride, int B, int Np, int D, int k, int dtype,
+                 int32_t* idx, float* vals, float* rnorm, void* stream);
+
+/* Reverse adjacency of idx, per image, in CSR form; deterministic (ascending edge id e = i*k+s).
+ * rev_ptr : (B,Np+1) int32, rev_src : (B,Np*k) int32.  Used by the two backward entry points. */
+GVIT_API int gvit_graph_reverse(const int32_t* idx, int B, int Np, int k, int32_t* rev_ptr, int32_t* rev_src, void* stream);
+
+/* Backward of G1-G3 through the selected similarities (indices are constants):
+ * dp += d vals/d p contracted with dvals.  dp has p's strides and dtype and is ACCUMULATED into
+ * (gvit_agg_bwd writes it first). */
+GVIT_API int gvit_knn_bwd(const void* p, int64_t batch_stride, int64_t row_stride, int B, int Np, int D, int k, int dtype,
+                 const int32_t* idx, const float* rnorm, const float* dvals, const int32_t* rev_ptr,
+                 const int32_t* rev_src, void* dp, void* stream);
+
+/* ---- a8: aggregation ----------------------------------------------
+ * G4+G5 only: w = softmax_k(vals) (fp32, (B,Np,k)); z_i = sum_j w_ij p[idx_ij]  ((B,Np,D) contiguous, dtype). */
+GVIT_API int gvit_agg_gather_fwd(const void* p, int64_t batch_stride, int64_t row_stride, int B, int Np, int D, int k,
+                        int dtype, const int32_t* idx, const float* vals, float* w, void* z, void* stream);
+
+/* Fused G4+G5+G6 + residual: out[b,1+i,:] = resid[b,1+i,:] + (sum_j w_ij p[idx_ij]) Wg^T + bias, with the
+ * aggregated tile kept on chip (shared memory / TMEM) between the two GEMMs; out[b,0,:] = resid[b,0,:]
+ * (CLS row untouched, section 9 G0).  h/resid/out are (B,1+Np,D) contiguous; Wg is (D,D) row-major
+ * (nn.Linear weight: out_features x in_features); bias may be NULL; resid may be NULL (treated as 0).
+ * w_save ((B,Np,k) fp32) and z_save ((B,Np,D) dtype) may be NULL (inference); training saves them.
+ * bf16 only (tcgen05); D % 64 == 0, D <= 1024, Np <= 1024. */
+GVIT_API int gvit_agg_fwd(const void* h, int B, int Np, int D, int k, int dtype, const int32_t* idx, const float* vals,
+                 const void* Wg, const void* bias, const void* resid, void* out, float* w_save, void* z_save,
+                 void* stream);
+
+/* Backward of G4+G5 given dz = dY Wg (the two GEMM gradients dWg, dz are plain library GEMMs on the host
+ * side): dvals (B,Np,k) fp32 and dp (strided like p, WRITTEN, dtype). */
+GVIT_API int gvit_agg_bwd(const void* p, int64_t batch_stride, int64_t row_stride, int B, int Np, int D, int k, int dtype,
+                 const int32_t* idx, const float* w, const void* dz, const int32_t* rev_ptr, const int32_t* rev_src,
+                 float* dvals, void* dp, void* stream);
+
+/* ---- a2: attention core, replaces /root/reference/src/models/vit.py:59-69 -------------------
+ * qkv : the packed projection output of vit.py:59, (B,N,3,H,dh) contiguous - consumed in place, no
+ *       permute; out : (B,N,H*dh) head-major (the layout vit.py:69's transpose+reshape produces);
+ * lse : (B,H,N) fp32 log-sum-exp of the scaled scores, saved for the backward.  dh in {32,64} (fp32),
+ * dh == 64 (bf16).  attn_drop is 0 in every shipped config (vit.py:127) and is not implemented. */
+GVIT_API int gvit_attn_fwd(const void* qkv, int B, int N, int H, int dh, float scale, int dtype, void* out, float* lse,
+                  void* stream);
+/* delta_ws : (B,H,N) fp32 workspace; dqkv : (B,N,3,H,dh) written in full. */
+GVIT_API int gvit_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int B, int N, int H, int dh,
+                  float scale, int dtype, float* delta_ws, void* dqkv, void* stream);
+
+/* ---- a5: LayerNorm + residual edges, replace nn.LayerNorm / "+" at vit.py:103,108,116-119 ----
+ * rows x D, eps as nn.LayerNorm (1e-5); statistics in fp32; mean/rstd (rows) saved for the backward. */
+GVIT_API int gvit_layernorm_fwd(const void* x, const void* gamma, const void* beta, int64_t rows, int D, float eps, int dtype,
+                       void* y, float* mean, float* rstd, void* stream);
+/* dgamma/dbeta are fp32 (D); partial_ws is an fp32 workspace of 2*GVIT_LN_PARTIALS*D floats. */
+enum { GVIT_LN_PARTIALS = 296 };
+GVIT_API int gvit_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
+                       int64_t rows, int D, int dtype, void* dx, float* dgamma, float* dbeta, float* partial_ws,
+                       void* stream);
+/* out = resid + dropout(y, p) with a Philox-4x32-10 keep mask generated from (seed, offset) - the
+ * proj_drop + residual edge of vit.py:71,117.  p == 0 or training == 0 degenerates to an add.
+ * keep_mask: n bytes (0/1), may be NULL when p == 0. */
+GVIT_API int gvit_dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, uint64_t seed, uint64_t offset,
+                              int dtype, void* out, uint8_t* keep_mask, void* stream);
+GVIT_API int gvit_dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, void* dy,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVIT_H_ */
