@@ -1,0 +1,144 @@
+"""Batch-sharded data parallelism: one process per GPU, full weight replica, the only
+collective is one gradient all-reduce (sum -> mean) per step, bucketed in reverse parameter order and
+launched from gradient hooks so it overlaps the rest of the backward pass.  Inference is collective-free.
+
+The reference has no distributed code at all (zero ``torch.distributed`` imports); what must hold is its
+single-process numerics: with equal per-rank batches and ``reduction='mean'`` losses
+(/root/reference/src/training/losses.py:35-53) the averaged gradients equal the single-process gradients
+over the concatenated batch.  ``tests/test_dp_gloo.py`` checks exactly that with world_size 2 on CPU.
+
+``torch.distributed`` (NCCL over NVLink 5 / NVSwitch on the GPU box, gloo on CPU) is the transport.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+__all__ = ["init_from_env", "GradSync", "broadcast_parameters", "shard_batch"]
+
+
+def init_from_env(backend: str | None = None):
+    """Join the process group described by RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT (torchrun's contract).
+
+    Returns (rank, world_size, local_rank).  A single process (no RANK in the environment) is world_size 1
+    and initialises nothing.
+    """
+    if "RANK" not in os.environ or int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        return 0, 1, int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_batch(global_batch: int, rank: int, world: int):
+    """[start, stop) of this rank's slice of a global batch; the batch must divide evenly (mean-loss exactness)."""
+    if global_batch % world:
+        raise ValueError(f"global batch {global_batch} is not divisible by world size {world}")
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+@torch.no_grad()
+def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None):
+    """Make every replica start from rank ``src``'s parameters and buffers."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src, group=group)
+
+
+class GradSync:
+    """Bucketed, backward-overlapped gradient averaging for a replica of ``module``.
+
+    Parameters are grouped, in reverse registration order (the order gradients become ready), into
+    buckets of about ``bucket_mb``.  A post-accumulate-grad hook on each parameter counts down its bucket;
+    when the last gradient of a bucket lands, the bucket is flattened and its all-reduce is issued
+    asynchronously, so it runs on the communicator's stream while autograd keeps going.  ``finish()`` (call
+    it after ``backward()``, before the optimizer) waits for the outstanding collectives and scatters the
+    averaged values back into ``p.grad``.
+
+    With NVSwitch every peer is one hop at full bandwidth, so bucket size trades launch latency against
+    overlap only: ~25-50 MB buckets keep ViT-B's 343 MB of fp32 gradients in about ten collectives.
+    """
+
+    def __init__(self, module: torch.nn.Module, bucket_mb: float = 32.0, group=None, extra_params=()):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        params = [p for p in list(module.parameters()) + list(extra_params) if p.requires_grad]
+        self.buckets: list[list[torch.nn.Parameter]] = []
+        cap = int(bucket_mb * (1 << 20))
+        cur, size = [], 0
+        for p in reversed(params):
+            nbytes = p.numel() * p.element_size()
+            if cur and (size + nbytes > cap or p.dtype != cur[0].dtype or p.device != cur[0].device):
+                self.buckets.append(cur)
+                cur, size = [], 0
+            cur.append(p)
+            size += nbytes
+        if cur:
+            self.buckets.append(cur)
+        self._bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
+        self._pending = [len(b) for b in self.buckets]
+        self._flat: list[torch.Tensor | None] = [None] * len(self.buckets)
+        self._work: list = [None] * len(self.buckets)
+        self._hooks = []
+        self.collectives_issued = 0
+        if self.world > 1:
+            for p in params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    # -- hooks ---------------------------------------------------------------------------------
+    def _on_grad(self, p):
+        i = self._bucket_of[id(p)]
+        self._pending[i] -= 1
+        if self._pending[i] == 0:
+            self._launch(i)
+
+    def _launch(self, i):
+        bucket = self.buckets[i]
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
+        flat = self._flat[i]
+        n = sum(g.numel() for g in grads)
+        if flat is None or flat.numel() != n:
+            flat = self._flat[i] = torch.empty(n, dtype=grads[0].dtype, device=grads[0].device)
+        torch._foreach_copy_(list(flat.split([g.numel() for g in grads])), [g.reshape(-1) for g in grads])
+        self._work[i] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.collectives_issued += 1
+
+    # -- step boundary -------------------------------------------------------------------------
+    @torch.no_grad()
+    def finish(self):
+        """Wait for every bucket, write the mean gradients back, re-arm the hooks for the next backward."""
+        if self.world == 1:
+            return
+        for i, bucket in enumerate(self.buckets):
+            if self._work[i] is None:        # a bucket with parameters that received no gradient this step
+                if self._pending[i] != len(bucket):
+                    self._launch(i)
+                else:
+                    continue
+            self._work[i].wait()
+            flat = self._flat[i].div_(self.world)
+            views = flat.split([p.numel() for p in bucket])
+            for p, v in zip(bucket, views):
+                if p.grad is None:
+                    p.grad = v.view_as(p).clone()
+                else:
+                    p.grad.copy_(v.view_as(p))
+            self._work[i] = None
+        self._pending = [len(b) for b in self.buckets]
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks.clear()

@@ -1,0 +1,231 @@
+"""Drop-in ``nn.Module``s for the reference's ``src/models/vit.py`` hot path, computed by libgvit.
+
+Constructor / ``forward`` signatures, attribute names and state-dict keys are those of the reference
+(SURVEY.md section 8b), so ``scripts/train.py`` / ``scripts/evaluate.py`` build and load these classes
+unchanged through the ``src.models.vit`` shim at the repository root:
+
+* ``Attention``          - /root/reference/src/models/vit.py:39-72
+* ``Mlp``                - vit.py:75-94 (library GEMMs: out of the hot-path scope)
+* ``Block``              - vit.py:97-119, plus the optional graph sub-layer of SURVEY.md section 9
+* ``PatchEmbed``         - vit.py:12-36 (stock Conv2d: out of scope, 0.7 % of the FLOPs)
+* ``VisionTransformer``  - vit.py:122-224, plus keyword-only ``graph_mode / graph_k / graph_every``
+* ``PatchGraphLayer``    - no reference symbol; SURVEY.md section 9 G0-G6
+
+``qkv`` / ``proj`` stay real ``nn.Linear`` sub-modules and the dropouts real ``nn.Dropout`` (Grad-CAM reaches
+into ``block.attn.qkv``, ``.num_heads``, ``.scale`` at /root/reference/src/utils/gradcam.py:252-258 and hooks
+``blocks.11.attn``); the fusion happens underneath ``forward``.
+"""
+from __future__ import annotations
+
+import logging
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+logger = logging.getLogger(__name__)
+
+__all__ = ["Attention", "Mlp", "Block", "DropPath", "PatchEmbed", "PatchGraphLayer", "LayerNorm",
+           "VisionTransformer"]
+
+
+class LayerNorm(nn.LayerNorm):
+    """nn.LayerNorm (same parameters / state-dict keys) evaluated by ``gvit_layernorm_*``."""
+
+    def forward(self, x):
+        if not self.elementwise_affine or len(self.normalized_shape) != 1:
+            raise NotImplementedError("libgvit LayerNorm is affine over the last dimension only")
+        return ops.layer_norm(x, self.weight, self.bias, self.eps)
+
+
+class Attention(nn.Module):
+    def __init__(self, dim, num_heads=8, qkv_bias=False, attn_drop=0., proj_drop=0.):
+        super().__init__()
+        assert dim % num_heads == 0, 'dim should be divisible by num_heads'
+        self.num_heads = num_heads
+        self.scale = (dim // num_heads) ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+
+    def forward(self, x):
+        if self.training and self.attn_drop.p > 0:
+            # 0 in every configuration the reference ships (vit.py:127; scripts/train.py never sets it)
+            raise NotImplementedError("attn_drop > 0 is not implemented by the fused attention kernel")
+        o = ops.attention_core(self.qkv(x), self.num_heads, self.scale)
+        return ops.dropout_add(self.proj(o), None, self.proj_drop.p, self.training)
+
+
+class Mlp(nn.Module):
+    def __init__(self, in_features, hidden_features=None, out_features=None, drop=0.):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = nn.Dropout(drop)
+
+    def forward(self, x):
+        x = self.act(self.fc1(x))
+        x = ops.dropout_add(x, None, self.drop.p, self.training)
+        return ops.dropout_add(self.fc2(x), None, self.drop.p, self.training)
+
+
+class DropPath(nn.Module):
+    """Per-sample stochastic depth (vit.py:227-242); identity in eval mode or for p == 0."""
+
+    def __init__(self, drop_prob=None):
+        super().__init__()
+        self.drop_prob = drop_prob
+
+    def forward(self, x):
+        if not self.training or not self.drop_prob:
+            return x
+        keep = 1.0 - self.drop_prob
+        mask = torch.rand((x.shape[0],) + (1,) * (x.dim() - 1), dtype=x.dtype, device=x.device).add_(keep).floor_()
+        return x.div(keep) * mask
+
+
+class PatchGraphLayer(nn.Module):
+    """kNN / dense patch-token graph sub-layer: forward(h: (B, 1+Np, D)) -> (B, 1+Np, D), CLS row zero.
+
+    h is the already layer-normed token tensor.  ``mode='knn'`` runs the fused libgvit path
+    (similarity + top-k, then softmax-gather-project); ``mode='dense'`` (row-softmax over all Np
+    similarities, BASELINE config 4) is composed from library GEMMs around the libgvit row norms.
+    """
+
+    def __init__(self, dim, k=8, mode="knn"):
+        super().__init__()
+        if mode not in ("knn", "dense"):
+            raise ValueError(f"unknown graph mode {mode!r}")
+        self.k, self.mode = k, mode
+        self.proj = nn.Linear(dim, dim)
+
+    def forward(self, h, resid=None):
+        if self.mode == "knn":
+            return ops.patch_graph(h, self.proj.weight, self.proj.bias, self.k, resid=resid)
+        y = _dense_graph(h, self.proj.weight, self.proj.bias)
+        return y if resid is None else resid + y
+
+
+def _dense_graph(h, weight, bias):
+    """Section 9 with G3 skipped: w = softmax(S) over all patch tokens, z = w p, y = z Wg^T + b."""
+    p = h[:, 1:, :]
+    with torch.autocast("cuda", enabled=False):
+        ph = F.normalize(p.float(), dim=-1)
+        w = torch.softmax(ph @ ph.transpose(-1, -2), dim=-1)
+    z = w.to(p.dtype) @ p
+    y = F.linear(z, weight, bias)
+    return F.pad(y, (0, 0, 1, 0))
+
+
+class Block(nn.Module):
+    def __init__(self, dim, num_heads, mlp_ratio=4., qkv_bias=False, drop=0., attn_drop=0., drop_path=0., *,
+                 graph_mode=None, graph_k=8):
+        super().__init__()
+        self.norm1 = LayerNorm(dim)
+        self.attn = Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, attn_drop=attn_drop, proj_drop=drop)
+        if graph_mode is not None:
+            self.norm_g = LayerNorm(dim)
+            self.graph = PatchGraphLayer(dim, k=graph_k, mode=graph_mode)
+        self.norm2 = LayerNorm(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), drop=drop)
+        self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
+        self.graph_mode = graph_mode
+
+    def forward(self, x):
+        x = x + self.drop_path(self.attn(self.norm1(x)))
+        if self.graph_mode is not None:
+            if isinstance(self.drop_path, nn.Identity):
+                x = self.graph(self.norm_g(x), resid=x)      # residual folded into the kernel epilogue
+            else:
+                x = x + self.drop_path(self.graph(self.norm_g(x)))
+        x = x + self.drop_path(self.mlp(self.norm2(x)))
+        return x
+
+
+class PatchEmbed(nn.Module):
+    def __init__(self, img_size=224, patch_size=16, in_chans=3, embed_dim=768):
+        super().__init__()
+        self.img_size, self.patch_size = (img_size, img_size), (patch_size, patch_size)
+        self.num_patches = (img_size // patch_size) ** 2
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+
+    def forward(self, x):
+        if tuple(x.shape[-2:]) != self.img_size:
+            raise AssertionError(f"Input image size ({x.shape[-2]}*{x.shape[-1]}) doesn't match expected size "
+                                 f"({self.img_size[0]}*{self.img_size[1]})")
+        return self.proj(x).flatten(2).transpose(1, 2)      # (B, Np, D)
+
+
+class VisionTransformer(nn.Module):
+    def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=14, embed_dim=768, depth=12,
+                 num_heads=12, mlp_ratio=4., qkv_bias=True, drop_rate=0., attn_drop_rate=0., drop_path_rate=0., *,
+                 graph_mode=None, graph_k=8, graph_every=1):
+        super().__init__()
+        self.num_classes = num_classes
+        self.num_features = self.embed_dim = embed_dim
+        self.graph_mode, self.graph_k, self.graph_every = graph_mode, graph_k, graph_every
+
+        self.patch_embed = PatchEmbed(img_size=img_size, patch_size=patch_size, in_chans=in_chans,
+                                      embed_dim=embed_dim)
+        num_patches = self.patch_embed.num_patches
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, num_patches + 1, embed_dim))
+        self.pos_drop = nn.Dropout(p=drop_rate)
+
+        dpr = [r.item() for r in torch.linspace(0, drop_path_rate, depth)]
+        self.blocks = nn.ModuleList([
+            Block(embed_dim, num_heads, mlp_ratio, qkv_bias, drop_rate, attn_drop_rate, dpr[i],
+                  graph_mode=graph_mode if (graph_mode is not None and i % graph_every == 0) else None,
+                  graph_k=graph_k)
+            for i in range(depth)])
+        self.norm = LayerNorm(embed_dim)
+        self.head = nn.Linear(embed_dim, num_classes)
+        self.initialize_weights()
+
+    def initialize_weights(self):
+        """Same distributions, in the same RNG order, as vit.py:162-180 (so a seed gives the same weights)."""
+        conv_w = self.patch_embed.proj.weight
+        nn.init.xavier_uniform_(conv_w.data.view(conv_w.shape[0], -1))
+        for t in (self.pos_embed, self.cls_token):
+            nn.init.trunc_normal_(t, std=0.02)
+        self.apply(self._init_weights)
+
+    @staticmethod
+    def _init_weights(m):
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=0.02)
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.ones_(m.weight)
+            nn.init.zeros_(m.bias)
+
+    def load_mae_weights(self, checkpoint_path):
+        """Load MAE pre-training weights: ``ckpt['model']`` minus the ``head``; graph keys stay at init."""
+        try:
+            state = torch.load(checkpoint_path, map_location="cpu")["model"]
+            own = self.state_dict()
+            own.update({k: v for k, v in state.items() if k in own and "head" not in k})
+            msg = self.load_state_dict(own, strict=False)
+            logger.info(f"Loaded MAE pre-trained weights: {msg}")
+        except Exception as e:
+            logger.error(f"Error loading MAE weights: {str(e)}")
+            raise
+
+    def forward_features(self, x):
+        x = self.patch_embed(x)
+        x = torch.cat((self.cls_token.expand(x.shape[0], -1, -1).to(x.dtype), x), dim=1)
+        x = x + self.pos_embed.to(x.dtype)
+        x = ops.dropout_add(x, None, self.pos_drop.p, self.training)
+        for blk in self.blocks:
+            x = blk(x)
+        return self.norm(x[:, 0])        # LayerNorm is per row: same value as vit.py:218-219's norm(x)[:, 0]
+
+    def forward(self, x):
+        return self.head(self.forward_features(x))

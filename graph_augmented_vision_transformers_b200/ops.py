@@ -1,0 +1,353 @@
+"""Host-side operators over the libgvit C ABI (``include/gvit.h``).
+
+Each function here is one stage of the graph-augmented ViT hot path:
+
+* ``attention_core``   - a2, /root/reference/src/models/vit.py:59-69
+* ``layer_norm``       - a5, nn.LayerNorm at vit.py:103,108,154
+* ``dropout_add``      - a5, proj_drop + residual at vit.py:71,117
+* ``knn_graph``        - a7, SURVEY.md section 9 G1-G3 (no reference symbol)
+* ``patch_graph``      - a7+a8 as one differentiable op, section 9 G0-G6 (no reference symbol)
+
+PyTorch is plumbing only: it owns the device memory and the stream, the arithmetic runs in the CUDA
+library.  There is no fallback: a CPU tensor, an unsupported dtype or a missing ``libgvit.so`` raises.
+Under ``torch.autocast`` the ops run in bf16 (fp16 autocast, which the reference trainer uses at
+/root/reference/src/training/trainer.py:101, is also executed in bf16: same 16-bit storage, no loss
+scaling hazards).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import GVIT_BF16, GVIT_F32, GVIT_LN_PARTIALS
+
+__all__ = ["attention_core", "layer_norm", "dropout_add", "knn_graph", "graph_reverse", "patch_graph",
+           "agg_gather", "launch_count", "reset_launch_count"]
+
+# kernels launched through the C ABI since the last reset (bench.py reports it as gpu_launches)
+_LAUNCHES = {"n": 0}
+_KERNELS_PER_CALL = {
+    "gvit_knn_fwd": 1, "gvit_graph_reverse": 1, "gvit_knn_bwd": 1, "gvit_agg_gather_fwd": 1, "gvit_agg_fwd": 1,
+    "gvit_agg_bwd": 2, "gvit_attn_fwd": 1, "gvit_attn_bwd": 1, "gvit_layernorm_fwd": 1, "gvit_layernorm_bwd": 2,
+    "gvit_dropout_residual_fwd": 1, "gvit_dropout_bwd": 1,
+}
+
+
+def launch_count() -> int:
+    return _LAUNCHES["n"]
+
+
+def reset_launch_count() -> None:
+    _LAUNCHES["n"] = 0
+
+
+def _call(name, *args):
+    _lib.call(name, *args)
+    _LAUNCHES["n"] += _KERNELS_PER_CALL.get(name, 1)
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return GVIT_F32
+    if t.dtype == torch.bfloat16:
+        return GVIT_BF16
+    raise TypeError(f"libgvit computes in float32 or bfloat16, got {t.dtype}")
+
+
+def _check_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("libgvit operators run on CUDA tensors only (there is no CPU fallback); "
+                               f"got a tensor on {t.device}")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t, byte_offset=0):
+    return None if t is None else t.data_ptr() + byte_offset
+
+
+def _autocast_dtype(t: torch.Tensor):
+    """bf16 when CUDA autocast is on (any 16-bit autocast dtype is executed as bf16), else the tensor's dtype."""
+    if torch.is_autocast_enabled("cuda"):
+        return torch.bfloat16
+    if t.dtype not in (torch.float32, torch.bfloat16):
+        if t.dtype == torch.float16:
+            return torch.bfloat16
+        raise TypeError(f"unsupported dtype {t.dtype}")
+    return t.dtype
+
+
+# ------------------------------------------------------------------------------------------------
+# a2: attention core
+# ------------------------------------------------------------------------------------------------
+class _AttentionCore(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, num_heads, scale):
+        B, N, C3 = qkv.shape
+        dh = C3 // (3 * num_heads)
+        out = torch.empty((B, N, num_heads * dh), dtype=qkv.dtype, device=qkv.device)
+        lse = torch.empty((B, num_heads, N), dtype=torch.float32, device=qkv.device)
+        _call("gvit_attn_fwd", _ptr(qkv), B, N, num_heads, dh, float(scale), _dtype_code(qkv), _ptr(out), _ptr(lse),
+              _stream())
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.meta = (num_heads, dh, float(scale))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse = ctx.saved_tensors
+        H, dh, scale = ctx.meta
+        B, N, _ = qkv.shape
+        dout = dout.contiguous()
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty_like(lse)
+        _call("gvit_attn_bwd", _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), B, N, H, dh, scale, _dtype_code(qkv),
+              _ptr(delta), _ptr(dqkv), _stream())
+        return dqkv, None, None
+
+
+def attention_core(qkv: torch.Tensor, num_heads: int, scale: float) -> torch.Tensor:
+    """softmax((q k^T) * scale) v on the packed projection output of vit.py:59.
+
+    qkv: (B, N, 3*H*dh) laid out as (B, N, 3, H, dh); returns (B, N, H*dh), head-major - the tensor
+    vit.py:69 produces after its transpose + reshape.  The (B,H,N,N) score tensor is never materialised.
+    """
+    _check_cuda(qkv)
+    if qkv.dim() != 3 or qkv.shape[-1] % (3 * num_heads):
+        raise ValueError(f"qkv must be (B, N, 3*H*dh); got {tuple(qkv.shape)} with H={num_heads}")
+    dt = _autocast_dtype(qkv)
+    with torch.autocast("cuda", enabled=False):
+        return _AttentionCore.apply(qkv.to(dt).contiguous(), int(num_heads), float(scale))
+
+
+# ------------------------------------------------------------------------------------------------
+# a5: LayerNorm, dropout + residual
+# ------------------------------------------------------------------------------------------------
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        D = x.shape[-1]
+        rows = x.numel() // D
+        y = torch.empty_like(x)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        _call("gvit_layernorm_fwd", _ptr(x), _ptr(weight), _ptr(bias), rows, D, float(eps), _dtype_code(x), _ptr(y),
+              _ptr(mean), _ptr(rstd), _stream())
+        ctx.save_for_backward(x, weight, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, rstd = ctx.saved_tensors
+        D = x.shape[-1]
+        rows = x.numel() // D
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dgb = torch.empty((2, D), dtype=torch.float32, device=x.device)
+        ws = torch.empty(2 * GVIT_LN_PARTIALS * D, dtype=torch.float32, device=x.device)
+        _call("gvit_layernorm_bwd", _ptr(dy), _ptr(x), _ptr(weight), _ptr(mean), _ptr(rstd), rows, D, _dtype_code(x),
+              _ptr(dx), _ptr(dgb[0]), _ptr(dgb[1]), _ptr(ws), _stream())
+        return dx, dgb[0].to(weight.dtype), dgb[1].to(weight.dtype), None
+
+
+def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """nn.LayerNorm over the last dimension (affine), statistics in fp32.
+
+    Like ``torch.autocast`` the normalisation keeps the input's dtype (fp32 activations stay fp32).
+    """
+    _check_cuda(x, weight, bias)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.to(torch.bfloat16 if x.dtype == torch.float16 else torch.float32)
+    with torch.autocast("cuda", enabled=False):
+        return _LayerNorm.apply(x.contiguous(), weight.to(x.dtype), bias.to(x.dtype), float(eps))
+
+
+class _DropoutAdd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, resid, p, seed):
+        n = y.numel()
+        out = torch.empty_like(y)
+        mask = torch.empty(n, dtype=torch.uint8, device=y.device) if p > 0 else None
+        _call("gvit_dropout_residual_fwd", _ptr(y), _ptr(resid), n, float(p), int(seed), 0, _dtype_code(y), _ptr(out),
+              _ptr(mask), _stream())
+        ctx.p = p
+        ctx.has_resid = resid is not None
+        if p > 0:
+            ctx.save_for_backward(mask)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dresid = dout if ctx.has_resid else None
+        if ctx.p == 0:
+            return dout, dresid, None, None
+        (mask,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        dy = torch.empty_like(dout)
+        _call("gvit_dropout_bwd", _ptr(dout), _ptr(mask), dout.numel(), float(ctx.p), _dtype_code(dout), _ptr(dy),
+              _stream())
+        return dy, dresid, None, None
+
+
+def dropout_add(y: torch.Tensor, resid: torch.Tensor | None, p: float, training: bool) -> torch.Tensor:
+    """``resid + dropout(y, p)`` in one pass (Philox-4x32-10 keep mask); ``resid`` may be None.
+
+    The seed of each call is drawn from PyTorch's CPU generator, so ``torch.manual_seed`` makes runs
+    reproducible without a device synchronisation.
+    """
+    _check_cuda(y, resid)
+    p = float(p) if training else 0.0
+    if p == 0.0 and resid is None:
+        return y
+    dt = y.dtype if y.dtype in (torch.float32, torch.bfloat16) else torch.bfloat16
+    if resid is not None and resid.dtype != dt:       # mixed residual stream (fp32) / branch (bf16): add in fp32
+        dt = torch.float32 if torch.float32 in (resid.dtype, y.dtype) else dt
+    if y.numel() % 8:
+        raise ValueError("dropout_add needs a multiple of 8 elements")
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
+    with torch.autocast("cuda", enabled=False):
+        return _DropoutAdd.apply(y.to(dt).contiguous(), None if resid is None else resid.to(dt).contiguous(), p, seed)
+
+
+# ------------------------------------------------------------------------------------------------
+# a7: graph construction
+# ------------------------------------------------------------------------------------------------
+def _token_view(h: torch.Tensor):
+    """(pointer offset in bytes, batch stride, row stride, B, Np, D) of the patch tokens h[:, 1:, :]."""
+    B, N, D = h.shape
+    return D * h.element_size(), N * D, D, B, N - 1, D
+
+
+@torch.no_grad()
+def knn_graph(h: torch.Tensor, k: int):
+    """G1-G3 over the patch tokens of h (B, 1+Np, D): returns (idx int32 (B,Np,k), vals fp32, rnorm fp32 (B,Np)).
+
+    Neighbour order: descending cosine similarity, ties to the lowest index.
+    """
+    _check_cuda(h)
+    h = h.contiguous()
+    off, bs, rs, B, Np, D = _token_view(h)
+    idx = torch.empty((B, Np, k), dtype=torch.int32, device=h.device)
+    vals = torch.empty((B, Np, k), dtype=torch.float32, device=h.device)
+    rnorm = torch.empty((B, Np), dtype=torch.float32, device=h.device)
+    _call("gvit_knn_fwd", _ptr(h, off), bs, rs, B, Np, D, int(k), _dtype_code(h), _ptr(idx), _ptr(vals), _ptr(rnorm),
+          _stream())
+    return idx, vals, rnorm
+
+
+@torch.no_grad()
+def graph_reverse(idx: torch.Tensor):
+    """Reverse adjacency (CSR) of idx (B,Np,k): (rev_ptr (B,Np+1), rev_src (B,Np*k)), ascending edge ids."""
+    _check_cuda(idx)
+    B, Np, k = idx.shape
+    rev_ptr = torch.empty((B, Np + 1), dtype=torch.int32, device=idx.device)
+    rev_src = torch.empty((B, Np * k), dtype=torch.int32, device=idx.device)
+    _call("gvit_graph_reverse", _ptr(idx), B, Np, k, _ptr(rev_ptr), _ptr(rev_src), _stream())
+    return rev_ptr, rev_src
+
+
+@torch.no_grad()
+def agg_gather(h: torch.Tensor, idx: torch.Tensor, vals: torch.Tensor):
+    """G4+G5: w = softmax_k(vals), z_i = sum_j w_ij p[idx_ij]; returns (w fp32 (B,Np,k), z (B,Np,D))."""
+    _check_cuda(h, idx, vals)
+    h = h.contiguous()
+    off, bs, rs, B, Np, D = _token_view(h)
+    k = idx.shape[-1]
+    w = torch.empty((B, Np, k), dtype=torch.float32, device=h.device)
+    z = torch.empty((B, Np, D), dtype=h.dtype, device=h.device)
+    _call("gvit_agg_gather_fwd", _ptr(h, off), bs, rs, B, Np, D, k, _dtype_code(h), _ptr(idx), _ptr(vals), _ptr(w),
+          _ptr(z), _stream())
+    return w, z
+
+
+def fused_agg_available(dtype: torch.dtype, Np: int, D: int, k: int) -> bool:
+    if dtype != torch.bfloat16 or k > 16:
+        return False
+    return _lib.describe_path("agg", GVIT_BF16, Np, D).startswith("agg:tcgen05")
+
+
+# ------------------------------------------------------------------------------------------------
+# a7 + a8: the whole graph sub-layer as one differentiable operator
+# ------------------------------------------------------------------------------------------------
+class _PatchGraph(torch.autograd.Function):
+    """y = cat([0, (softmax_k(S_knn) gathered p) Wg^T + b]) [+ resid], SURVEY.md section 9 G0-G6."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, resid, k):
+        off, bs, rs, B, Np, D = _token_view(h)
+        dt = _dtype_code(h)
+        st = _stream()
+        idx = torch.empty((B, Np, k), dtype=torch.int32, device=h.device)
+        vals = torch.empty((B, Np, k), dtype=torch.float32, device=h.device)
+        rnorm = torch.empty((B, Np), dtype=torch.float32, device=h.device)
+        _call("gvit_knn_fwd", _ptr(h, off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(vals), _ptr(rnorm), st)
+        w = torch.empty((B, Np, k), dtype=torch.float32, device=h.device)
+        z = torch.empty((B, Np, D), dtype=h.dtype, device=h.device)
+        if fused_agg_available(h.dtype, Np, D, k):
+            out = torch.empty_like(h)
+            _call("gvit_agg_fwd", _ptr(h), B, Np, D, k, dt, _ptr(idx), _ptr(vals), _ptr(weight), _ptr(bias),
+                  _ptr(resid), _ptr(out), _ptr(w), _ptr(z), st)
+        else:
+            # fp32 parity path: fused gather + softmax kernel, then the projection as a library GEMM
+            _call("gvit_agg_gather_fwd", _ptr(h, off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(vals), _ptr(w),
+                  _ptr(z), st)
+            out = torch.zeros_like(h) if resid is None else resid.clone()
+            out[:, 1:] += F.linear(z, weight, bias)
+        ctx.save_for_backward(h, weight, idx, rnorm, w, z)
+        ctx.k = k
+        ctx.has = (bias is not None, resid is not None)
+        ctx.mark_non_differentiable(idx, vals)
+        return out, idx, vals
+
+    @staticmethod
+    def backward(ctx, dout, _didx, _dvals):
+        h, weight, idx, rnorm, w, z = ctx.saved_tensors
+        k = ctx.k
+        off, bs, rs, B, Np, D = _token_view(h)
+        dt = _dtype_code(h)
+        st = _stream()
+        dout = dout.contiguous()
+        dy = dout[:, 1:, :]
+        dy2 = dy.reshape(B * Np, D)
+        dweight = dy2.t() @ z.view(B * Np, D) if ctx.needs_input_grad[1] else None
+        dbias = dy2.sum(0) if (ctx.has[0] and ctx.needs_input_grad[2]) else None
+        dh = None
+        if ctx.needs_input_grad[0]:
+            dz = (dy2 @ weight).view(B, Np, D)
+            rev_ptr = torch.empty((B, Np + 1), dtype=torch.int32, device=h.device)
+            rev_src = torch.empty((B, Np * k), dtype=torch.int32, device=h.device)
+            _call("gvit_graph_reverse", _ptr(idx), B, Np, k, _ptr(rev_ptr), _ptr(rev_src), st)
+            dvals = torch.empty((B, Np, k), dtype=torch.float32, device=h.device)
+            dh = torch.empty_like(h)
+            dh[:, 0].zero_()
+            _call("gvit_agg_bwd", _ptr(h, off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(w), _ptr(dz), _ptr(rev_ptr),
+                  _ptr(rev_src), _ptr(dvals), _ptr(dh, off), st)
+            _call("gvit_knn_bwd", _ptr(h, off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(rnorm), _ptr(dvals),
+                  _ptr(rev_ptr), _ptr(rev_src), _ptr(dh, off), st)
+        dresid = dout if ctx.has[1] else None
+        return dh, dweight, dbias, dresid, None
+
+
+def patch_graph(h: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, k: int,
+                resid: torch.Tensor | None = None, return_graph: bool = False):
+    """The kNN graph sub-layer on layer-normed tokens h (B, 1+Np, D): returns (B, 1+Np, D).
+
+    The CLS row of the result is zero (or ``resid``'s CLS row when a residual is fused in).
+    ``return_graph=True`` also returns the adjacency (idx int32, vals fp32) that was built.
+    """
+    _check_cuda(h, weight, bias, resid)
+    if h.dim() != 3 or h.shape[1] < 2:
+        raise ValueError(f"h must be (B, 1+Np, D); got {tuple(h.shape)}")
+    dt = _autocast_dtype(h)
+    with torch.autocast("cuda", enabled=False):
+        fuse_resid = resid is not None and resid.dtype == dt
+        out, idx, vals = _PatchGraph.apply(h.to(dt).contiguous(), weight.to(dt).contiguous(),
+                                           None if bias is None else bias.to(dt).contiguous(),
+                                           resid.contiguous() if fuse_resid else None, int(k))
+        if resid is not None and not fuse_resid:
+            out = resid + out
+    return (out, idx, vals) if return_graph else out

@@ -68,7 +68,7 @@ def knn_f64(p: np.ndarray, k: int):
     return idx.astype(np.int32), np.take_along_axis(S, idx, axis=-1), gaps.min(axis=-1)
 
 
-def graph_layer_forward(h, weight, bias, k=8, mode="knn", compute_dtype=None, return_aux=False):
+def graph_layer_forward(h, weight, bias, k=8, mode="knn", compute_dtype=None, return_aux=False, idx_override=None):
     """G0-G6 on an already layer-normed token tensor h (B, 1+Np, D).
 
     compute_dtype: None -> everything fp32.  torch.bfloat16 emulates autocast:
@@ -81,6 +81,9 @@ def graph_layer_forward(h, weight, bias, k=8, mode="knn", compute_dtype=None, re
     cd = compute_dtype or torch.float32
     if mode == "knn":
         idx, vals = knn_select(S, k)                  # G3
+        if idx_override is not None:
+            idx = idx_override.long()
+            vals = S.gather(-1, idx)
         w = torch.softmax(vals, dim=-1)               # G4
         pg = p.to(cd)
         bi = torch.arange(B, device=h.device)[:, None, None]

@@ -1,0 +1,89 @@
+"""a1-a4 - multi-head self-attention, /root/reference/src/models/vit.py:39-72, through gvit_attn_fwd / gvit_attn_bwd."""
+import pytest
+import torch
+
+from conftest import TOL_BF16, TOL_F32, golden, rel_err
+from gpu_util import DEV
+from graph_augmented_vision_transformers_b200 import _lib, modules, ops
+from oracle import vit_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,dim", [("attn_small", 128), ("attn_dh64", 192)])
+def test_fp32_module_matches_reference_fixture(name, dim):
+    g = golden(name)
+    m = modules.Attention(dim, num_heads=int(g["heads"]), qkv_bias=True).eval()
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            p.copy_(torch.from_numpy(g["param." + n]))
+    m.to(DEV)
+    x = torch.from_numpy(g["x"]).to(DEV).requires_grad_(True)
+    out = m(x)
+    out.backward(torch.from_numpy(g["cot"]).to(DEV))
+    assert rel_err(out, g["out"]) < TOL_F32 and rel_err(x.grad, g["dx"]) < TOL_F32
+    for n, p in m.named_parameters():
+        assert rel_err(p.grad, g["grad." + n]) < TOL_F32, n
+
+
+def _core_case(B, N, H, dh, dtype, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    qkv = torch.randn(B, N, 3 * H * dh, generator=g).to(dtype).float()
+    cot = torch.randn(B, N, H * dh, generator=g).to(dtype).float()
+    qd = qkv.to(DEV, dtype).requires_grad_(True)
+    out = ops.attention_core(qd, H, dh ** -0.5)
+    out.backward(cot.to(DEV, dtype))
+    qc = qkv.clone().requires_grad_(True)
+    want = vit_oracle.attention_core(qc, H, dh ** -0.5)
+    want.backward(cot)
+    return out, qd.grad, want, qc.grad
+
+
+@pytest.mark.parametrize("B,N,H,dh", [(2, 197, 12, 64), (1, 577, 16, 64), (2, 37, 4, 32), (1, 1, 2, 64), (3, 128, 2, 64),
+                                      (2, 129, 3, 64)])
+def test_fp32_core_vs_oracle(B, N, H, dh):
+    out, dqkv, want, dwant = _core_case(B, N, H, dh, torch.float32)
+    assert rel_err(out, want) < TOL_F32 and rel_err(dqkv, dwant) < TOL_F32
+
+
+@pytest.mark.parametrize("B,N,H", [(2, 197, 12), (1, 577, 16), (1, 1, 2), (3, 128, 2), (2, 129, 3), (2, 16, 1), (1, 256, 4),
+                                   (1, 257, 2)])
+def test_bf16_core_vs_oracle(B, N, H):
+    assert _lib.describe_path("attn_fwd", _lib.GVIT_BF16, N, 64) == "attn_fwd:tcgen05+tma"
+    out, dqkv, want, dwant = _core_case(B, N, H, 64, torch.bfloat16, seed=N)
+    assert out.dtype == torch.bfloat16
+    assert rel_err(out, want) < TOL_BF16 and rel_err(dqkv, dwant) < TOL_BF16
+
+
+def test_bf16_under_autocast_matches_module_semantics():
+    m = modules.Attention(768, num_heads=12, qkv_bias=True).to(DEV)
+    o = vit_oracle.Attention(768, num_heads=12, qkv_bias=True)
+    o.load_state_dict({k: v.cpu() for k, v in m.state_dict().items()})
+    x = torch.randn(2, 197, 768, generator=torch.Generator().manual_seed(1))
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        got = m(x.to(DEV))
+    assert got.dtype == torch.bfloat16 and rel_err(got, o(x)) < TOL_BF16
+    with torch.autocast("cuda", dtype=torch.float16):             # the reference trainer's autocast dtype
+        got16 = m(x.to(DEV))
+    assert rel_err(got16, o(x)) < TOL_BF16
+
+
+def test_softmax_rows_sum_to_one_at_full_size():
+    """config 2 size: with v == 1 every output is exactly the softmax row sum."""
+    B, N, H = 256, 197, 12
+    qkv = torch.randn(B, N, 3, H, 64, device=DEV, dtype=torch.bfloat16, generator=torch.Generator(device=DEV).manual_seed(0))
+    qkv[:, :, 2] = 1.0
+    out = ops.attention_core(qkv.view(B, N, -1), H, 0.125)
+    assert (out.float() - 1).abs().max() < 1e-2
+    # linearity in v
+    qkv2 = qkv.clone()
+    qkv2[:, :, 2] = 2.0
+    assert (ops.attention_core(qkv2.view(B, N, -1), H, 0.125).float() - 2).abs().max() < 2e-2
+
+
+def test_attn_drop_is_refused_loudly():
+    m = modules.Attention(64, num_heads=1, attn_drop=0.1).to(DEV).train()
+    with pytest.raises(NotImplementedError):
+        m(torch.randn(1, 4, 64, device=DEV))
+    with pytest.raises(_lib.GvitError, match="GVIT_ERR_UNSUPPORTED"):
+        ops.attention_core(torch.randn(1, 4, 3 * 48, device=DEV), 1, 1.0)      # head dim 48

@@ -1,0 +1,135 @@
+"""a7+a8 - the graph sub-layer forward and backward through gvit_knn_fwd, gvit_agg_fwd /
+gvit_agg_gather_fwd, gvit_graph_reverse, gvit_agg_bwd, gvit_knn_bwd, against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import TOL_BF16, TOL_F32, golden, rel_err
+from gpu_util import DEV, check_adjacency, tokens
+from graph_augmented_vision_transformers_b200 import modules, ops
+from oracle import graph_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_device(hc, W, b, k, dtype, cot):
+    h = hc.to(DEV, dtype).requires_grad_(True)
+    Wd = W.to(DEV, dtype).requires_grad_(True)
+    bd = b.to(DEV, dtype).requires_grad_(True)
+    out, idx, vals = ops.patch_graph(h, Wd, bd, k, return_graph=True)
+    out.backward(cot.to(DEV, dtype))
+    return out, idx, vals, h.grad, Wd.grad, bd.grad
+
+
+def _run_oracle(hc, W, b, k, cot, idx, compute_dtype=None):
+    h = hc.clone().requires_grad_(True)
+    Wc = W.clone().requires_grad_(True)
+    bc = b.clone().requires_grad_(True)
+    out = graph_oracle.graph_layer_forward(h, Wc, bc, k, "knn", compute_dtype=compute_dtype,
+                                           idx_override=idx.cpu())
+    out.float().backward(cot)
+    return out.float(), h.grad, Wc.grad, bc.grad
+
+
+@pytest.mark.parametrize("name", ["graph_knn_small", "graph_knn_196"])
+def test_fp32_golden_forward_backward(name):
+    g = golden(name)
+    hc, W, b, cot = (torch.from_numpy(g[n]) for n in ("h", "W", "b", "cot"))
+    out, idx, vals, dh, dW, db = _run_device(hc, W, b, int(g["k"]), torch.float32, cot)
+    sure = check_adjacency(hc, idx, vals, int(g["k"]), noise=1e-6, min_sure=0.97)
+    if sure.all() and np.array_equal(idx.cpu().numpy(), g["idx"]):
+        assert rel_err(out, g["out"]) < TOL_F32
+        assert rel_err(dh, g["dh"]) < TOL_F32 and rel_err(dW, g["dW"]) < TOL_F32 and rel_err(db, g["db"]) < TOL_F32
+    want = _run_oracle(hc, W, b, int(g["k"]), cot, idx)
+    for got, ref, n in zip((out, dh, dW, db), want, ("out", "dh", "dW", "db")):
+        assert rel_err(got, ref) < TOL_F32, n
+    assert float(out[:, 0].abs().max()) == 0.0 and float(dh[:, 0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,Np,D,k", [(2, 196, 768, 8), (1, 50, 72, 5), (2, 300, 128, 16)])
+def test_fp32_forward_backward_vs_oracle(B, Np, D, k):
+    hc, _ = tokens(B, Np, D, seed=11)
+    g = torch.Generator().manual_seed(3)
+    W, b, cot = torch.randn(D, D, generator=g) * 0.05, torch.randn(D, generator=g) * 0.1, torch.randn(B, Np + 1, D, generator=g)
+    out, idx, vals, dh, dW, db = _run_device(hc, W, b, k, torch.float32, cot)
+    check_adjacency(hc, idx, vals, k, noise=2e-6)
+    want = _run_oracle(hc, W, b, k, cot, idx)
+    for got, ref, n in zip((out, dh, dW, db), want, ("out", "dh", "dW", "db")):
+        assert rel_err(got, ref) < TOL_F32, n
+
+
+@pytest.mark.parametrize("B,Np,D,k", [(3, 196, 768, 8), (2, 196, 768, 4), (2, 196, 768, 16), (2, 64, 128, 8),
+                                      (1, 16, 64, 2), (2, 256, 1024, 8), (2, 129, 192, 8), (2, 196, 768, 32),
+                                      (1, 576, 1024, 8)])
+def test_bf16_forward_backward_vs_oracle(B, Np, D, k):
+    """bf16 (tcgen05 kernels where the shape is in range): oracle = autocast semantics, G1-G4 fp32, G5-G6 on bf16."""
+    bf = torch.bfloat16
+    hc, _ = tokens(B, Np, D, seed=21, dtype=bf)
+    g = torch.Generator().manual_seed(4)
+    W = (torch.randn(D, D, generator=g) * 0.05).to(bf).float()
+    b = (torch.randn(D, generator=g) * 0.1).to(bf).float()
+    cot = torch.randn(B, Np + 1, D, generator=g).to(bf).float()
+    out, idx, vals, dh, dW, db = _run_device(hc, W, b, k, bf, cot)
+    assert out.dtype == bf and dh.dtype == bf
+    check_adjacency(hc, idx, vals, k, noise=1e-5)
+    want = _run_oracle(hc, W, b, k, cot, idx, compute_dtype=bf)
+    for got, ref, n in zip((out, dh, dW, db), want, ("out", "dh", "dW", "db")):
+        assert rel_err(got, ref) < TOL_BF16, n
+    assert float(out[:, 0].abs().max()) == 0.0 and float(dh[:, 0].abs().max()) == 0.0
+
+
+def test_bf16_fused_residual_epilogue():
+    bf = torch.bfloat16
+    hc, hd = tokens(2, 196, 768, seed=2, dtype=bf)
+    g = torch.Generator().manual_seed(5)
+    W = (torch.randn(768, 768, generator=g) * 0.05).to(DEV, bf)
+    b = (torch.randn(768, generator=g) * 0.1).to(DEV, bf)
+    x = torch.randn(2, 197, 768, generator=g).to(DEV, bf).requires_grad_(True)
+    plain = ops.patch_graph(hd, W, b, 8)
+    fused = ops.patch_graph(hd, W, b, 8, resid=x)
+    assert rel_err(fused, x.float() + plain.float()) < 1e-2
+    assert torch.equal(fused[:, 0], x[:, 0])                  # CLS row passes through untouched (G0)
+    fused.sum().backward()
+    assert torch.equal(x.grad, torch.ones_like(x))
+    x32 = x.detach().float()                                  # fp32 residual stream under autocast
+    with torch.autocast("cuda", dtype=bf):
+        mixed = ops.patch_graph(hd.float(), W.float(), b.float(), 8, resid=x32)
+    assert mixed.dtype == torch.float32 and rel_err(mixed, x32 + plain.float()) < 1e-6
+
+
+def test_graph_reverse_is_the_transposed_adjacency():
+    _, hd = tokens(3, 196, 64, seed=9)
+    idx, _, _ = ops.knn_graph(hd, 8)
+    rev_ptr, rev_src = ops.graph_reverse(idx)
+    idx, rev_ptr, rev_src = idx.cpu().numpy(), rev_ptr.cpu().numpy(), rev_src.cpu().numpy()
+    for b in range(3):
+        flat = idx[b].reshape(-1)
+        assert rev_ptr[b, 0] == 0 and rev_ptr[b, -1] == flat.size
+        for j in (0, 1, 57, 195):
+            edges = rev_src[b, rev_ptr[b, j]:rev_ptr[b, j + 1]]
+            assert np.array_equal(edges, np.nonzero(flat == j)[0])      # ascending edge ids -> fixed summation order
+
+
+def test_dense_mode_vs_oracle():
+    hc, hd = tokens(2, 100, 64, seed=6)
+    layer = modules.PatchGraphLayer(64, mode="dense").to(DEV)
+    want = graph_oracle.graph_layer_forward(hc, layer.proj.weight.detach().cpu(), layer.proj.bias.detach().cpu(), 0, "dense")
+    assert rel_err(layer(hd), want) < TOL_F32
+
+
+def test_backward_is_deterministic_at_full_size():
+    bf = torch.bfloat16
+    g = torch.Generator(device=DEV).manual_seed(8)
+    h = torch.randn(256, 197, 768, generator=g, device=DEV, dtype=bf)
+    W = torch.randn(768, 768, generator=g, device=DEV, dtype=bf) * 0.05
+    outs = []
+    for _ in range(2):
+        hh = h.clone().requires_grad_(True)
+        o = ops.patch_graph(hh, W, None, 8)
+        o.backward(torch.ones_like(o))
+        outs.append((o.detach(), hh.grad))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])   # no atomics anywhere
+    assert torch.isfinite(outs[0][0].float()).all() and torch.isfinite(outs[0][1].float()).all()
+    # linearity in the projection: scaling Wg scales the output
+    o2 = ops.patch_graph(h, W * 2, None, 8)
+    assert rel_err(o2, 2 * outs[0][0].float()) < 1e-2

@@ -1,0 +1,123 @@
+"""a5/a6 - Block and VisionTransformer (vit.py:97-224) assembled from the libgvit-backed modules, against the
+reference fixtures (fp32) and the oracle graph-ViT (fp32 and bf16 autocast)."""
+import ast
+
+import pytest
+import torch
+
+from conftest import TOL_BF16, TOL_F32, golden, rel_err
+from gpu_util import DEV
+from graph_augmented_vision_transformers_b200 import modules, ops
+from oracle import vit_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32():
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _load(mod, g, prefix="param."):
+    with torch.no_grad():
+        for n, p in mod.named_parameters():
+            p.copy_(torch.from_numpy(g[prefix + n]))
+    return mod.to(DEV)
+
+
+def test_block_matches_reference_fixture():
+    g = golden("block_small")
+    m = _load(modules.Block(128, num_heads=int(g["heads"]), mlp_ratio=float(g["mlp_ratio"]), qkv_bias=True).eval(), g)
+    x = torch.from_numpy(g["x"]).to(DEV).requires_grad_(True)
+    out = m(x)
+    out.backward(torch.from_numpy(g["cot"]).to(DEV))
+    assert rel_err(out, g["out"]) < TOL_F32 and rel_err(x.grad, g["dx"]) < TOL_F32
+    for n, p in m.named_parameters():
+        assert rel_err(p.grad, g["grad." + n]) < TOL_F32, n
+
+
+def test_vit_and_loss_match_reference_fixture():
+    g = golden("vit_small")
+    m = _load(modules.VisionTransformer(**ast.literal_eval(str(g["cfg"]))).eval(), g)
+    logits = m(torch.from_numpy(g["img"]).to(DEV))
+    assert rel_err(logits, g["logits"]) < TOL_F32
+    loss = vit_oracle.multilabel_loss(logits, torch.from_numpy(g["tgt"]).to(DEV), torch.ones(3, device=DEV),
+                                      torch.ones(14, device=DEV))
+    assert abs(float(loss) - float(g["loss"])) < 1e-5
+    loss.backward()
+    for n, p in m.named_parameters():
+        assert rel_err(p.grad, g["grad." + n]) < 2 * TOL_F32, n
+
+
+def test_vit_b16_seed42_logits_match_reference():
+    g = golden("vit_b16_seed42")
+    torch.manual_seed(42)
+    m = modules.VisionTransformer().eval().to(DEV)
+    img = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(1234))
+    with torch.no_grad():
+        assert rel_err(m(img.to(DEV)), g["logits"]) < TOL_F32
+        assert rel_err(m.forward_features(img.to(DEV))[:, :16], g["feats_head"]) < TOL_F32
+
+
+CFG = dict(img_size=64, patch_size=8, embed_dim=128, depth=2, num_heads=2, mlp_ratio=2.0, graph_mode="knn", graph_k=4)
+
+
+def _pair(cfg=CFG, seed=0):
+    torch.manual_seed(seed)
+    o = vit_oracle.VisionTransformer(**cfg).eval()
+    m = modules.VisionTransformer(**cfg).eval()
+    m.load_state_dict(o.state_dict())
+    return o, m.to(DEV)
+
+
+def test_graph_vit_fp32_forward_backward_vs_oracle():
+    o, m = _pair()
+    g = torch.Generator().manual_seed(1)
+    img, tgt = torch.randn(3, 3, 64, 64, generator=g), (torch.rand(3, 14, generator=g) > 0.7).float()
+    lo = vit_oracle.multilabel_loss(o(img), tgt, torch.ones(3), torch.ones(14))
+    logits = m(img.to(DEV))
+    lm = vit_oracle.multilabel_loss(logits, tgt.to(DEV), torch.ones(3, device=DEV), torch.ones(14, device=DEV))
+    assert rel_err(logits, o(img)) < TOL_F32 and abs(float(lo) - float(lm)) < 1e-5
+    lo.backward()
+    lm.backward()
+    for (n, a), b in zip(o.named_parameters(), m.parameters()):
+        assert rel_err(b.grad, a.grad) < 3 * TOL_F32, n
+
+
+def test_graph_every_and_dense_variants_fp32():
+    for extra in (dict(graph_every=2), dict(graph_mode="dense")):
+        o, m = _pair({**CFG, **extra}, seed=3)
+        img = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(2))
+        with torch.no_grad():
+            assert rel_err(m(img.to(DEV)), o(img)) < TOL_F32
+
+
+def test_graph_vit_bf16_autocast_trains():
+    """bf16 autocast fwd+bwd (the bench's precision): close to the fp32 oracle, finite grads for every parameter."""
+    o, m = _pair(seed=5)
+    m.train()
+    g = torch.Generator().manual_seed(1)
+    img, tgt = torch.randn(4, 3, 64, 64, generator=g), (torch.rand(4, 14, generator=g) > 0.7).float()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = m(img.to(DEV))
+    assert rel_err(logits, o(img)) < 5e-2                  # whole-network drift incl. possible near-tie neighbour swaps
+    loss = vit_oracle.multilabel_loss(logits.float(), tgt.to(DEV), torch.ones(3, device=DEV), torch.ones(14, device=DEV))
+    before = ops.launch_count()
+    loss.backward()
+    assert ops.launch_count() > before                     # the backward ran through libgvit kernels
+    for n, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    lo = vit_oracle.multilabel_loss(o(img), tgt, torch.ones(3), torch.ones(14))
+    lo.backward()
+    worst = max(rel_err(b.grad, a.grad) for (n, a), b in zip(o.named_parameters(), m.parameters()) if "graph" not in n)
+    assert worst < 0.15, worst
+
+
+def test_pure_bf16_model_runs():
+    _, m = _pair(seed=6)
+    m.bfloat16()
+    out = m(torch.randn(2, 3, 64, 64, device=DEV, dtype=torch.bfloat16))
+    assert out.dtype == torch.bfloat16 and torch.isfinite(out.float()).all()
