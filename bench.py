@@ -162,7 +162,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # per-kernel roofline (live CUDA-event timing of each libgvit kernel at the bench shape)
 # ------------------------------------------------------------------------------------------------
-def kernel_rooflines(dev, B, peaks, iters=10):
+def kernel_rooflines(dev, B, peaks, iters=10, only=None):
     from graph_augmented_vision_transformers_b200 import ops
     from graph_augmented_vision_transformers_b200.ops import _call, _dtype_code, _ptr, _stream, _token_view
     bf = torch.bfloat16
@@ -206,14 +206,16 @@ def kernel_rooflines(dev, B, peaks, iters=10):
                     3 * tok + B * Np * k * 16, 4.0 * B * Np * k * D, "hbm", 12),
         "knn_bwd": (lambda i: _call("gvit_knn_bwd", _ptr(hs[i % R], off), bs, rs, B, Np, D, k, dt, _ptr(idxs[i % R][0]), _ptr(idxs[i % R][2]), _ptr(dvals), _ptr(rev[i % R][0]), _ptr(rev[i % R][1]), _ptr(out, off), st),
                     3 * tok + B * Np * k * 12, 4.0 * B * Np * k * D, "hbm", 12),
-        "layernorm_fwd": (lambda i: _call("gvit_layernorm_fwd", _ptr(hs[i % R]), _ptr(gam), _ptr(bet), B * N, D, 1e-5, dt, _ptr(out), _ptr(mean), _ptr(rstd), st),
+        "layernorm_fwd": (lambda i: _call("gvit_layernorm_fwd", _ptr(hs[i % R]), _ptr(gam), _ptr(bet), B * N, D, 1e-5, dt, dt, _ptr(out), _ptr(mean), _ptr(rstd), st),
                           2 * B * N * D * e, 0.0, "hbm", 36),
-        "layernorm_bwd": (lambda i: _call("gvit_layernorm_bwd", _ptr(xs[i % R]), _ptr(hs[i % R]), _ptr(gam), _ptr(mean), _ptr(rstd), B * N, D, dt, _ptr(out), _ptr(dgb[0]), _ptr(dgb[1]), _ptr(ws), st),
+        "layernorm_bwd": (lambda i: _call("gvit_layernorm_bwd", _ptr(xs[i % R]), _ptr(hs[i % R]), _ptr(gam), _ptr(mean), _ptr(rstd), B * N, D, dt, dt, _ptr(out), _ptr(dgb[0]), _ptr(dgb[1]), _ptr(ws), st),
                           3 * B * N * D * e, 0.0, "hbm", 36),
     }
-    _call("gvit_layernorm_fwd", _ptr(hs[0]), _ptr(gam), _ptr(bet), B * N, D, 1e-5, dt, _ptr(out), _ptr(mean), _ptr(rstd), st)
+    _call("gvit_layernorm_fwd", _ptr(hs[0]), _ptr(gam), _ptr(bet), B * N, D, 1e-5, dt, dt, _ptr(out), _ptr(mean), _ptr(rstd), st)
     res = {}
     for name, (fn, nbytes, flops, bound, per_step) in cases.items():
+        if only and name not in only:
+            continue
         for i in range(3):
             fn(i)
         torch.cuda.synchronize()

@@ -17,6 +17,10 @@ namespace {
 
 constexpr int TQ = 32, TK = 32, ROWS_PER_WARP = 8;
 
+// feature owned by (lane, t); head dims below 32 leave the upper lanes idle (reads clamped, writes predicated)
+template <int DH> __device__ __forceinline__ int feat(int lane, int t) { return min(lane + 32 * t, DH - 1); }
+template <int DH> __device__ __forceinline__ bool feat_ok(int lane, int t) { return lane + 32 * t < DH; }
+
 template <typename T>
 __device__ __forceinline__ const T* qkv_ptr(const T* qkv, int b, int n, int which, int h, int N, int H, int DH) {
   return qkv + ((((int64_t)b * N + n) * 3 + which) * H + h) * DH;
@@ -38,7 +42,7 @@ __device__ __forceinline__ void load_rows(float (*dst)[LD], const T* base, int64
 template <typename T, int DH>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const T* __restrict__ qkv, int N, int H, float scale,
                                                        T* __restrict__ out, float* __restrict__ lse) {
-  constexpr int DD = DH / 32;
+  constexpr int DD = (DH + 31) / 32;
   __shared__ float Qs[TQ][DH];
   __shared__ float Ks[TK][DH + 1];
   __shared__ float Vs[TK][DH + 1];
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const T* __restrict__ qkv
       for (int kk = 0; kk < TK; ++kk) {
         const float pk = __shfl_sync(0xffffffffu, pr, kk);
 #pragma unroll
-        for (int d = 0; d < DD; ++d) acc[d] = fmaf(pk, Vs[kk][lane + 32 * d], acc[d]);
+        for (int d = 0; d < DD; ++d) acc[d] = fmaf(pk, Vs[kk][feat<DH>(lane, d)], acc[d]);
       }
 #pragma unroll
       for (int d = 0; d < DD; ++d) o[r][d] = acc[d];
@@ -91,7 +95,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const T* __restrict__ qkv
     const float inv = 1.0f / l[r];
     T* dst = out + ((int64_t)b * N + q) * H * DH + h * DH;
 #pragma unroll
-    for (int d = 0; d < DD; ++d) dst[lane + 32 * d] = from_f32<T>(o[r][d] * inv);
+    for (int d = 0; d < DD; ++d)
+      if (feat_ok<DH>(lane, d)) dst[lane + 32 * d] = from_f32<T>(o[r][d] * inv);
     if (lane == 0) lse[((int64_t)b * H + h) * N + q] = m[r] + logf(l[r]);
   }
 }
@@ -102,7 +107,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const T* __restrict__ 
                                                           const T* __restrict__ dout, const float* __restrict__ lse,
                                                           int N, int H, float scale, float* __restrict__ delta,
                                                           T* __restrict__ dqkv) {
-  constexpr int DD = DH / 32;
+  constexpr int DD = (DH + 31) / 32;
   __shared__ float Qs[TQ][DH];
   __shared__ float dOs[TQ][DH];
   __shared__ float Ks[TK][DH + 1];
@@ -122,7 +127,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const T* __restrict__ 
     if (q < N) {
       const T* orow = out + ((int64_t)b * N + q) * os + h * DH;
 #pragma unroll
-      for (int t = 0; t < DD; ++t) d = fmaf(to_f32(orow[lane + 32 * t]), dOs[lr][lane + 32 * t], d);
+      for (int t = 0; t < DD; ++t)
+        if (feat_ok<DH>(lane, t)) d = fmaf(to_f32(orow[lane + 32 * t]), dOs[lr][lane + 32 * t], d);
     }
     d = warp_sum(d);
     del_r[r] = d;
@@ -151,7 +157,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const T* __restrict__ 
       for (int kk = 0; kk < TK; ++kk) {
         const float dk = __shfl_sync(0xffffffffu, ds, kk);
 #pragma unroll
-        for (int t = 0; t < DD; ++t) dq[r][t] = fmaf(dk, Ks[kk][lane + 32 * t], dq[r][t]);
+        for (int t = 0; t < DD; ++t) dq[r][t] = fmaf(dk, Ks[kk][feat<DH>(lane, t)], dq[r][t]);
       }
     }
   }
@@ -161,7 +167,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const T* __restrict__ 
     if (q >= N) continue;
     T* dst = const_cast<T*>(qkv_ptr(dqkv, b, q, 0, h, N, H, DH));
 #pragma unroll
-    for (int t = 0; t < DD; ++t) dst[lane + 32 * t] = from_f32<T>(dq[r][t]);
+    for (int t = 0; t < DD; ++t)
+      if (feat_ok<DH>(lane, t)) dst[lane + 32 * t] = from_f32<T>(dq[r][t]);
   }
 }
 
@@ -171,7 +178,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const T* __restrict__
                                                            const float* __restrict__ lse,
                                                            const float* __restrict__ delta, int N, int H, float scale,
                                                            T* __restrict__ dqkv) {
-  constexpr int DD = DH / 32;
+  constexpr int DD = (DH + 31) / 32;
   __shared__ float Ks[TK][DH];
   __shared__ float Vs[TK][DH];
   __shared__ float Qs[TQ][DH + 1];
@@ -215,8 +222,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const T* __restrict__
         const float pq = __shfl_sync(0xffffffffu, pr, qq), dq = __shfl_sync(0xffffffffu, ds, qq);
 #pragma unroll
         for (int t = 0; t < DD; ++t) {
-          dv[r][t] = fmaf(pq, dOs[qq][lane + 32 * t], dv[r][t]);
-          dk[r][t] = fmaf(dq, Qs[qq][lane + 32 * t], dk[r][t]);
+          dv[r][t] = fmaf(pq, dOs[qq][feat<DH>(lane, t)], dv[r][t]);
+          dk[r][t] = fmaf(dq, Qs[qq][feat<DH>(lane, t)], dk[r][t]);
         }
       }
     }
@@ -229,6 +236,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const T* __restrict__
     T* dvp = const_cast<T*>(qkv_ptr(dqkv, b, kr, 2, h, N, H, DH));
 #pragma unroll
     for (int t = 0; t < DD; ++t) {
+      if (!feat_ok<DH>(lane, t)) continue;
       dkp[lane + 32 * t] = from_f32<T>(dk[r][t]);
       dvp[lane + 32 * t] = from_f32<T>(dv[r][t]);
     }
@@ -266,7 +274,9 @@ int attn_fwd_simt(const void* qkv, int B, int N, int H, int dh, float scale, int
                                          : launch_fwd<bf, 64>(qkv, B, N, H, scale, out, lse, st);
   if (dh == 32) return dtype == GVIT_F32 ? launch_fwd<float, 32>(qkv, B, N, H, scale, out, lse, st)
                                          : launch_fwd<bf, 32>(qkv, B, N, H, scale, out, lse, st);
-  return fail(GVIT_ERR_UNSUPPORTED, "attn_fwd: head dim %d (supported: 32, 64)", dh);
+  if (dh == 16) return dtype == GVIT_F32 ? launch_fwd<float, 16>(qkv, B, N, H, scale, out, lse, st)
+                                         : launch_fwd<bf, 16>(qkv, B, N, H, scale, out, lse, st);
+  return fail(GVIT_ERR_UNSUPPORTED, "attn_fwd: head dim %d (supported: 16, 32, 64)", dh);
 }
 
 int attn_bwd_simt(const void* qkv, const void* out, const void* dout, const float* lse, int B, int N, int H, int dh,
@@ -276,7 +286,9 @@ int attn_bwd_simt(const void* qkv, const void* out, const void* dout, const floa
                                          : launch_bwd<bf, 64>(qkv, out, dout, lse, B, N, H, scale, delta_ws, dqkv, st);
   if (dh == 32) return dtype == GVIT_F32 ? launch_bwd<float, 32>(qkv, out, dout, lse, B, N, H, scale, delta_ws, dqkv, st)
                                          : launch_bwd<bf, 32>(qkv, out, dout, lse, B, N, H, scale, delta_ws, dqkv, st);
-  return fail(GVIT_ERR_UNSUPPORTED, "attn_bwd: head dim %d (supported: 32, 64)", dh);
+  if (dh == 16) return dtype == GVIT_F32 ? launch_bwd<float, 16>(qkv, out, dout, lse, B, N, H, scale, delta_ws, dqkv, st)
+                                         : launch_bwd<bf, 16>(qkv, out, dout, lse, B, N, H, scale, delta_ws, dqkv, st);
+  return fail(GVIT_ERR_UNSUPPORTED, "attn_bwd: head dim %d (supported: 16, 32, 64)", dh);
 }
 
 }  // namespace gvit

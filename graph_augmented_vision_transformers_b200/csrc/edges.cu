@@ -7,20 +7,22 @@
 namespace gvit {
 namespace {
 
-constexpr int MAXC = 4;  // D <= 1024
-
-template <typename T>
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
-                                                     const T* __restrict__ beta, int64_t rows, int D, float eps,
-                                                     T* __restrict__ y, float* __restrict__ mean,
+// A lane owns NC chunks of 8 consecutive features: chunk c covers [c*256 + lane*8, +8).  NC = ceil(D / 256) is a
+// template parameter so the per-thread arrays are exactly as large as the row needs (D <= 1024 -> NC <= 4).
+// Tx is the dtype of x / gamma / beta / dx (the residual stream), Ty the dtype of y / dy (the branch input):
+// under autocast the stream is fp32 and the branch bf16, and the cast is folded into this kernel.
+template <typename Tx, typename Ty, int NC>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const Tx* __restrict__ x, const Tx* __restrict__ gamma,
+                                                     const Tx* __restrict__ beta, int64_t rows, int D, float eps,
+                                                     Ty* __restrict__ y, float* __restrict__ mean,
                                                      float* __restrict__ rstd) {
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  float v[MAXC][8];
+  float v[NC][8];
   float s = 0.f;
 #pragma unroll
-  for (int c = 0; c < MAXC; ++c) {
+  for (int c = 0; c < NC; ++c) {
     const int d0 = lane * 8 + c * 256;
     if (d0 < D) {
       load8(x + row * D + d0, v[c]);
@@ -31,7 +33,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
   const float mu = warp_sum(s) / D;
   float q = 0.f;
 #pragma unroll
-  for (int c = 0; c < MAXC; ++c) {
+  for (int c = 0; c < NC; ++c) {
     const int d0 = lane * 8 + c * 256;
     if (d0 < D) {
 #pragma unroll
@@ -40,7 +42,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
   }
   const float rs = rsqrtf(warp_sum(q) / D + eps);
 #pragma unroll
-  for (int c = 0; c < MAXC; ++c) {
+  for (int c = 0; c < NC; ++c) {
     const int d0 = lane * 8 + c * 256;
     if (d0 < D) {
       float g[8], bt[8], o[8];
@@ -54,51 +56,56 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, co
   if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
 }
 
-// dx for every row; per-CTA partial dgamma/dbeta (fixed row -> CTA assignment: deterministic)
-template <typename T>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
-                                                     const T* __restrict__ gamma, const float* __restrict__ mean,
-                                                     const float* __restrict__ rstd, int64_t rows, int D,
-                                                     T* __restrict__ dx, float* __restrict__ partial) {
+// dx for every row; per-CTA partial dgamma/dbeta (fixed row -> CTA assignment: deterministic, no atomics).
+// x and dy of the row stay in registers between the two reductions and the dx pass; gamma lives in shared memory.
+template <typename Tx, typename Ty, int NC>
+__global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const Ty* __restrict__ dy, const Tx* __restrict__ x,
+                                                        const Tx* __restrict__ gamma, const float* __restrict__ mean,
+                                                        const float* __restrict__ rstd, int64_t rows, int D,
+                                                        Tx* __restrict__ dx, float* __restrict__ partial) {
   __shared__ float red[8][256];
+  __shared__ float gsm[NC * 256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float dg[MAXC][8] = {}, db[MAXC][8] = {}, g[MAXC][8];
-#pragma unroll
-  for (int c = 0; c < MAXC; ++c) {
-    const int d0 = lane * 8 + c * 256;
-    if (d0 < D) load8(gamma + d0, g[c]);
-  }
+  for (int i = threadIdx.x; i < NC * 256; i += 256) gsm[i] = i < D ? to_f32(gamma[i]) : 0.f;
+  __syncthreads();
+  float dg[NC][8] = {}, db[NC][8] = {};
+  const float invD = 1.0f / D;
   for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < rows; row += (int64_t)gridDim.x * 8) {
+    float xv[NC][8], dyv[NC][8];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int d0 = lane * 8 + c * 256;
+      if (d0 < D) { load8(x + row * D + d0, xv[c]); load8(dy + row * D + d0, dyv[c]); }
+    }
     const float mu = mean[row], rs = rstd[row];
-    float xh[MAXC][8], gy[MAXC][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int d0 = lane * 8 + c * 256;
       if (d0 < D) {
-        float xv[8], dyv[8];
-        load8(x + row * D + d0, xv);
-        load8(dy + row * D + d0, dyv);
+        const float4 g0 = *reinterpret_cast<const float4*>(&gsm[d0]), g1 = *reinterpret_cast<const float4*>(&gsm[d0 + 4]);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-          xh[c][t] = (xv[t] - mu) * rs;
-          gy[c][t] = dyv[t] * g[c][t];
-          s1 += gy[c][t];
-          s2 = fmaf(gy[c][t], xh[c][t], s2);
-          dg[c][t] = fmaf(dyv[t], xh[c][t], dg[c][t]);
-          db[c][t] += dyv[t];
+          const float xh = (xv[c][t] - mu) * rs;
+          xv[c][t] = xh;                                   // x is only needed normalised from here on
+          dg[c][t] = fmaf(dyv[c][t], xh, dg[c][t]);
+          db[c][t] += dyv[c][t];
+          dyv[c][t] *= g[t];                               // gy
+          s1 += dyv[c][t];
+          s2 = fmaf(dyv[c][t], xh, s2);
         }
       }
     }
-    s1 = warp_sum(s1) / D;
-    s2 = warp_sum(s2) / D;
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int d0 = lane * 8 + c * 256;
       if (d0 < D) {
         float o[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) o[t] = rs * (gy[c][t] - s1 - xh[c][t] * s2);
+        for (int t = 0; t < 8; ++t) o[t] = rs * (dyv[c][t] - s1 - xv[c][t] * s2);
         store8(dx + row * D + d0, o);
       }
     }
@@ -106,8 +113,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
   // reduce the 8 warps' partials column by column through shared memory, 256 columns at a time
   for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-      if (c * 256 >= D) break;
+    for (int c = 0; c < NC; ++c) {
       __syncthreads();
 #pragma unroll
       for (int t = 0; t < 8; ++t) red[warp][lane * 8 + t] = pass == 0 ? dg[c][t] : db[c][t];
@@ -125,15 +131,15 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
 
 __global__ void ln_bwd_reduce_kernel(const float* __restrict__ partial, int nblk, int D, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= D) return;
-  float a = 0.f, b = 0.f;
-  for (int i = 0; i < nblk; ++i) {
-    a += partial[(int64_t)i * D + col];
-    b += partial[((int64_t)nblk + i) * D + col];
-  }
-  dgamma[col] = a;
-  dbeta[col] = b;
+  // one warp per (column, which): lanes stride over the CTA partials, then a shuffle reduction (fixed order)
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= 2 * D) return;
+  const int which = wid / D, col = wid % D;
+  const float* src = partial + (int64_t)which * nblk * D + col;
+  float a = 0.f;
+  for (int i = lane; i < nblk; i += 32) a += src[(int64_t)i * D];
+  a = warp_sum(a);
+  if (lane == 0) (which == 0 ? dgamma : dbeta)[col] = a;
 }
 
 // ---- Philox-4x32-10 (Salmon et al.), counter = (offset + i/4), key = seed --------------------------
@@ -149,29 +155,36 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) dropout_residual_fwd_kernel(const T* __restrict__ y, const T* __restrict__ resid,
+// 8 keep decisions from ONE Philox block (16 random bits per element): bit j of the result is 1 when element j is
+// kept.  P(keep) = 1 - thresh16 / 65536 with thresh16 = round(p * 65536), i.e. p is honoured to 1.5e-5.
+__device__ __forceinline__ uint32_t keep_bits8(uint64_t seed, uint64_t counter, uint32_t thresh16) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)counter, (uint32_t)(counter >> 32), 0u, 0u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t bits = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bits |= (((w[j >> 1] >> (16 * (j & 1))) & 0xffffu) >= thresh16 ? 1u : 0u) << j;
+  return bits;
+}
+__device__ __forceinline__ uint32_t dropout_thresh16(float p) { return (uint32_t)__float2int_rn(p * 65536.0f); }
+
+// out = resid + dropout(y): y has the branch dtype Ty, resid / out the stream dtype Tx (Tx == Ty when resid is null).
+// The keep mask is stored as one BIT per element (byte i covers elements 8i..8i+7).
+template <typename Tx, typename Ty>
+__global__ void __launch_bounds__(256) dropout_residual_fwd_kernel(const Ty* __restrict__ y, const Tx* __restrict__ resid,
                                                                    int64_t n, float p, uint64_t seed, uint64_t offset,
-                                                                   T* __restrict__ out, uint8_t* __restrict__ mask) {
+                                                                   Tx* __restrict__ out, uint8_t* __restrict__ mask) {
   const float scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  const uint32_t th = dropout_thresh16(p);
   for (int64_t i8 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i8 < n; i8 += (int64_t)gridDim.x * blockDim.x * 8) {
     float a[8], r[8] = {};
     load8(y + i8, a);
     if (resid) load8(resid + i8, r);
     if (p > 0.f) {
-      uint8_t keep[8];
+      const uint32_t bits = keep_bits8(seed, offset + (uint64_t)(i8 >> 3), th);
 #pragma unroll
-      for (int hlf = 0; hlf < 2; ++hlf) {
-        const uint64_t c = offset + (uint64_t)(i8 / 4 + hlf);
-        const uint4 rnd = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
-                                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-        const uint32_t u[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) keep[hlf * 4 + t] = (u[t] >> 8) * (1.0f / 16777216.0f) >= p;
-      }
-#pragma unroll
-      for (int t = 0; t < 8; ++t) a[t] = keep[t] ? a[t] * scale : 0.f;
-      *reinterpret_cast<uint2*>(mask + i8) = *reinterpret_cast<const uint2*>(keep);
+      for (int t = 0; t < 8; ++t) a[t] = (bits >> t) & 1u ? a[t] * scale : 0.f;
+      mask[i8 >> 3] = (uint8_t)bits;
     }
 #pragma unroll
     for (int t = 0; t < 8; ++t) a[t] += r[t];
@@ -179,18 +192,61 @@ __global__ void __launch_bounds__(256) dropout_residual_fwd_kernel(const T* __re
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) dropout_bwd_kernel(const T* __restrict__ dout, const uint8_t* __restrict__ mask,
-                                                          int64_t n, float p, T* __restrict__ dy) {
+template <typename Tx, typename Ty>
+__global__ void __launch_bounds__(256) dropout_bwd_kernel(const Tx* __restrict__ dout, const uint8_t* __restrict__ mask,
+                                                          int64_t n, float p, Ty* __restrict__ dy) {
   const float scale = 1.0f / (1.0f - p);
   for (int64_t i8 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i8 < n; i8 += (int64_t)gridDim.x * blockDim.x * 8) {
     float a[8];
     load8(dout + i8, a);
-    const uint2 raw = *reinterpret_cast<const uint2*>(mask + i8);
-    const uint8_t* keep = reinterpret_cast<const uint8_t*>(&raw);
+    const uint32_t bits = mask[i8 >> 3];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) a[t] = keep[t] ? a[t] * scale : 0.f;
+    for (int t = 0; t < 8; ++t) a[t] = (bits >> t) & 1u ? a[t] * scale : 0.f;
     store8(dy + i8, a);
+  }
+}
+
+// ---- GELU (exact erf form, nn.GELU at vit.py:84) fused with the dropout that follows it (vit.py:92) --------
+__device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float u) {
+  return 0.5f * (1.0f + erff(u * 0.70710678118654752f)) + u * 0.3989422804014327f * __expf(-0.5f * u * u);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gelu_dropout_fwd_kernel(const T* __restrict__ u, int64_t n, float p, uint64_t seed,
+                                                               uint64_t offset, T* __restrict__ out,
+                                                               uint8_t* __restrict__ mask) {
+  const float scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  const uint32_t th = dropout_thresh16(p);
+  for (int64_t i8 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i8 < n; i8 += (int64_t)gridDim.x * blockDim.x * 8) {
+    float a[8];
+    load8(u + i8, a);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) a[t] = gelu_f(a[t]);
+    if (p > 0.f) {
+      const uint32_t bits = keep_bits8(seed, offset + (uint64_t)(i8 >> 3), th);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) a[t] = (bits >> t) & 1u ? a[t] * scale : 0.f;
+      mask[i8 >> 3] = (uint8_t)bits;
+    }
+    store8(out + i8, a);
+  }
+}
+
+// du = dout * keep/(1-p) * gelu'(u); the activation is recomputed from the saved pre-activation
+template <typename T>
+__global__ void __launch_bounds__(256) gelu_dropout_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ u,
+                                                               const uint8_t* __restrict__ mask, int64_t n, float p,
+                                                               T* __restrict__ du) {
+  const float scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  for (int64_t i8 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i8 < n; i8 += (int64_t)gridDim.x * blockDim.x * 8) {
+    float g[8], a[8];
+    load8(dout + i8, g);
+    load8(u + i8, a);
+    const uint32_t bits = p > 0.f ? mask[i8 >> 3] : 0xffu;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) g[t] = (bits >> t) & 1u ? g[t] * scale * gelu_grad_f(a[t]) : 0.f;
+    store8(du + i8, g);
   }
 }
 
@@ -200,64 +256,128 @@ inline int stream_grid(int64_t n8) {
   return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
-}  // namespace
 
-int layernorm_fwd(const void* x, const void* gamma, const void* beta, int64_t rows, int D, float eps, int dtype,
-                  void* y, float* mean, float* rstd, cudaStream_t st) {
-  const int blocks = (int)((rows + 7) / 8);
-  if (dtype == GVIT_F32)
-    ln_fwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), static_cast<const float*>(gamma),
-                                                 static_cast<const float*>(beta), rows, D, eps, static_cast<float*>(y),
-                                                 mean, rstd);
-  else
-    ln_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gamma),
-        static_cast<const __nv_bfloat16*>(beta), rows, D, eps, static_cast<__nv_bfloat16*>(y), mean, rstd);
+template <typename Tx, typename Ty, int NC>
+int ln_fwd_launch(const void* x, const void* gamma, const void* beta, int64_t rows, int D, float eps, void* y, float* mean,
+                  float* rstd, cudaStream_t st) {
+  ln_fwd_kernel<Tx, Ty, NC><<<(int)((rows + 7) / 8), 256, 0, st>>>(static_cast<const Tx*>(x), static_cast<const Tx*>(gamma),
+                                                                  static_cast<const Tx*>(beta), rows, D, eps,
+                                                                  static_cast<Ty*>(y), mean, rstd);
+  GVIT_CHECK_LAUNCH();
+  return GVIT_OK;
+}
+template <typename Tx, typename Ty, int NC>
+int ln_bwd_launch(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, int64_t rows,
+                  int D, void* dx, float* partial, int nblk, cudaStream_t st) {
+  ln_bwd_kernel<Tx, Ty, NC><<<nblk, 256, 0, st>>>(static_cast<const Ty*>(dy), static_cast<const Tx*>(x),
+                                                  static_cast<const Tx*>(gamma), mean, rstd, rows, D,
+                                                  static_cast<Tx*>(dx), partial);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }
 
+#define GVIT_LN_DISPATCH(FN, ...)                                                        \
+  do {                                                                                   \
+    const int nc = (D + 255) / 256;                                                      \
+    if (dtype == GVIT_F32 && y_dtype == GVIT_F32) {                                      \
+      using Tx = float; using Ty = float;                                                \
+      if (nc == 1) return FN<Tx, Ty, 1>(__VA_ARGS__);                                    \
+      if (nc == 2) return FN<Tx, Ty, 2>(__VA_ARGS__);                                    \
+      if (nc == 3) return FN<Tx, Ty, 3>(__VA_ARGS__);                                    \
+      return FN<Tx, Ty, 4>(__VA_ARGS__);                                                 \
+    } else if (dtype == GVIT_F32) {                                                      \
+      using Tx = float; using Ty = __nv_bfloat16;                                        \
+      if (nc == 1) return FN<Tx, Ty, 1>(__VA_ARGS__);                                    \
+      if (nc == 2) return FN<Tx, Ty, 2>(__VA_ARGS__);                                    \
+      if (nc == 3) return FN<Tx, Ty, 3>(__VA_ARGS__);                                    \
+      return FN<Tx, Ty, 4>(__VA_ARGS__);                                                 \
+    } else {                                                                             \
+      using Tx = __nv_bfloat16; using Ty = __nv_bfloat16;                                \
+      if (nc == 1) return FN<Tx, Ty, 1>(__VA_ARGS__);                                    \
+      if (nc == 2) return FN<Tx, Ty, 2>(__VA_ARGS__);                                    \
+      if (nc == 3) return FN<Tx, Ty, 3>(__VA_ARGS__);                                    \
+      return FN<Tx, Ty, 4>(__VA_ARGS__);                                                 \
+    }                                                                                    \
+  } while (0)
+
+}  // namespace
+
+int layernorm_fwd(const void* x, const void* gamma, const void* beta, int64_t rows, int D, float eps, int dtype,
+                  int y_dtype, void* y, float* mean, float* rstd, cudaStream_t st) {
+  GVIT_LN_DISPATCH(ln_fwd_launch, x, gamma, beta, rows, D, eps, y, mean, rstd, st);
+}
+
+static int ln_bwd_main(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
+                       int64_t rows, int D, int dtype, int y_dtype, void* dx, float* partial_ws, int nblk,
+                       cudaStream_t st) {
+  GVIT_LN_DISPATCH(ln_bwd_launch, dy, x, gamma, mean, rstd, rows, D, dx, partial_ws, nblk, st);
+}
+
 int layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, int64_t rows,
-                  int D, int dtype, void* dx, float* dgamma, float* dbeta, float* partial_ws, cudaStream_t st) {
+                  int D, int dtype, int y_dtype, void* dx, float* dgamma, float* dbeta, float* partial_ws,
+                  cudaStream_t st) {
   int nblk = (int)((rows + 7) / 8);
   if (nblk > GVIT_LN_PARTIALS) nblk = GVIT_LN_PARTIALS;
-  if (dtype == GVIT_F32)
-    ln_bwd_kernel<float><<<nblk, 256, 0, st>>>(static_cast<const float*>(dy), static_cast<const float*>(x),
-                                               static_cast<const float*>(gamma), mean, rstd, rows, D,
-                                               static_cast<float*>(dx), partial_ws);
-  else
-    ln_bwd_kernel<__nv_bfloat16><<<nblk, 256, 0, st>>>(
-        static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x),
-        static_cast<const __nv_bfloat16*>(gamma), mean, rstd, rows, D, static_cast<__nv_bfloat16*>(dx), partial_ws);
-  GVIT_CHECK_LAUNCH();
-  ln_bwd_reduce_kernel<<<(D + 255) / 256, 256, 0, st>>>(partial_ws, nblk, D, dgamma, dbeta);
+  int rc = ln_bwd_main(dy, x, gamma, mean, rstd, rows, D, dtype, y_dtype, dx, partial_ws, nblk, st);
+  if (rc != GVIT_OK) return rc;
+  ln_bwd_reduce_kernel<<<(2 * D * 32 + 255) / 256, 256, 0, st>>>(partial_ws, nblk, D, dgamma, dbeta);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }
 
 int dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, uint64_t seed, uint64_t offset,
-                         int dtype, void* out, uint8_t* keep_mask, cudaStream_t st) {
+                         int dtype, int y_dtype, void* out, uint8_t* keep_mask, cudaStream_t st) {
   const int grid = stream_grid(n / 8);
-  if (dtype == GVIT_F32)
-    dropout_residual_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(y),
-                                                             static_cast<const float*>(resid), n, p, seed, offset,
-                                                             static_cast<float*>(out), keep_mask);
+  using bf = __nv_bfloat16;
+  if (dtype == GVIT_F32 && y_dtype == GVIT_F32)
+    dropout_residual_fwd_kernel<float, float><<<grid, 256, 0, st>>>(static_cast<const float*>(y), static_cast<const float*>(resid),
+                                                                    n, p, seed, offset, static_cast<float*>(out), keep_mask);
+  else if (dtype == GVIT_F32)
+    dropout_residual_fwd_kernel<float, bf><<<grid, 256, 0, st>>>(static_cast<const bf*>(y), static_cast<const float*>(resid), n, p,
+                                                                 seed, offset, static_cast<float*>(out), keep_mask);
   else
-    dropout_residual_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
-        static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(resid), n, p, seed, offset,
-        static_cast<__nv_bfloat16*>(out), keep_mask);
+    dropout_residual_fwd_kernel<bf, bf><<<grid, 256, 0, st>>>(static_cast<const bf*>(y), static_cast<const bf*>(resid), n, p, seed,
+                                                              offset, static_cast<bf*>(out), keep_mask);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }
 
-int dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, void* dy, cudaStream_t st) {
+int dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, int y_dtype, void* dy,
+                cudaStream_t st) {
+  const int grid = stream_grid(n / 8);
+  using bf = __nv_bfloat16;
+  if (dtype == GVIT_F32 && y_dtype == GVIT_F32)
+    dropout_bwd_kernel<float, float><<<grid, 256, 0, st>>>(static_cast<const float*>(dout), keep_mask, n, p, static_cast<float*>(dy));
+  else if (dtype == GVIT_F32)
+    dropout_bwd_kernel<float, bf><<<grid, 256, 0, st>>>(static_cast<const float*>(dout), keep_mask, n, p, static_cast<bf*>(dy));
+  else
+    dropout_bwd_kernel<bf, bf><<<grid, 256, 0, st>>>(static_cast<const bf*>(dout), keep_mask, n, p, static_cast<bf*>(dy));
+  GVIT_CHECK_LAUNCH();
+  return GVIT_OK;
+}
+
+int gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t offset, int dtype, void* out,
+                     uint8_t* keep_mask, cudaStream_t st) {
   const int grid = stream_grid(n / 8);
   if (dtype == GVIT_F32)
-    dropout_bwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(dout), keep_mask, n, p,
-                                                    static_cast<float*>(dy));
+    gelu_dropout_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(u), n, p, seed, offset, static_cast<float*>(out), keep_mask);
   else
-    dropout_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dout), keep_mask, n, p,
-                                                            static_cast<__nv_bfloat16*>(dy));
+    gelu_dropout_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(u), n, p, seed, offset,
+                                                                 static_cast<__nv_bfloat16*>(out), keep_mask);
+  GVIT_CHECK_LAUNCH();
+  return GVIT_OK;
+}
+
+int gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, int64_t n, float p, int dtype, void* du,
+                     cudaStream_t st) {
+  const int grid = stream_grid(n / 8);
+  if (dtype == GVIT_F32)
+    gelu_dropout_bwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(dout), static_cast<const float*>(u), keep_mask, n, p,
+                                                         static_cast<float*>(du));
+  else
+    gelu_dropout_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dout),
+                                                                 static_cast<const __nv_bfloat16*>(u), keep_mask, n, p,
+                                                                 static_cast<__nv_bfloat16*>(du));
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }

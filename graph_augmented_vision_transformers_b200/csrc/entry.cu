@@ -117,42 +117,72 @@ int gvit_attn_bwd(const void* qkv, const void* out, const void* dout, const floa
   return attn_bwd_simt(qkv, out, dout, lse, B, N, H, dh, scale, dtype, delta_ws, dqkv, st);
 }
 
+static int check_ln_pair(int dtype, int y_dtype, const char* who) {
+  TRY(check_dtype(dtype, who));
+  TRY(check_dtype(y_dtype, who));
+  GVIT_REQUIRE(y_dtype == dtype || (dtype == GVIT_F32 && y_dtype == GVIT_BF16), GVIT_ERR_DTYPE,
+               "%s: y_dtype must equal dtype, or be GVIT_BF16 over a GVIT_F32 stream", who);
+  return GVIT_OK;
+}
+
 int gvit_layernorm_fwd(const void* x, const void* gamma, const void* beta, int64_t rows, int D, float eps, int dtype,
-                       void* y, float* mean, float* rstd, void* stream) {
-  TRY(check_dtype(dtype, "layernorm_fwd"));
+                       int y_dtype, void* y, float* mean, float* rstd, void* stream) {
+  TRY(check_ln_pair(dtype, y_dtype, "layernorm_fwd"));
   GVIT_REQUIRE(x && gamma && beta && y && mean && rstd, GVIT_ERR_SHAPE, "layernorm_fwd: null pointer");
   GVIT_REQUIRE(rows >= 1 && D >= 8 && D % 8 == 0 && D <= 1024, GVIT_ERR_SHAPE, "layernorm_fwd: rows=%lld D=%d (D %% 8 == 0, D <= 1024)", (long long)rows, D);
   GVIT_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta), GVIT_ERR_ALIGN, "layernorm_fwd: 16-byte alignment required");
-  return layernorm_fwd(x, gamma, beta, rows, D, eps, dtype, y, mean, rstd, static_cast<cudaStream_t>(stream));
+  return layernorm_fwd(x, gamma, beta, rows, D, eps, dtype, y_dtype, y, mean, rstd, static_cast<cudaStream_t>(stream));
 }
 
 int gvit_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
-                       int64_t rows, int D, int dtype, void* dx, float* dgamma, float* dbeta, float* partial_ws,
-                       void* stream) {
-  TRY(check_dtype(dtype, "layernorm_bwd"));
+                       int64_t rows, int D, int dtype, int y_dtype, void* dx, float* dgamma, float* dbeta,
+                       float* partial_ws, void* stream) {
+  TRY(check_ln_pair(dtype, y_dtype, "layernorm_bwd"));
   GVIT_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && partial_ws, GVIT_ERR_SHAPE, "layernorm_bwd: null pointer");
   GVIT_REQUIRE(rows >= 1 && D >= 8 && D % 8 == 0 && D <= 1024, GVIT_ERR_SHAPE, "layernorm_bwd: rows=%lld D=%d (D %% 8 == 0, D <= 1024)", (long long)rows, D);
   GVIT_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(gamma), GVIT_ERR_ALIGN, "layernorm_bwd: 16-byte alignment required");
-  return layernorm_bwd(dy, x, gamma, mean, rstd, rows, D, dtype, dx, dgamma, dbeta, partial_ws, static_cast<cudaStream_t>(stream));
+  return layernorm_bwd(dy, x, gamma, mean, rstd, rows, D, dtype, y_dtype, dx, dgamma, dbeta, partial_ws, static_cast<cudaStream_t>(stream));
 }
 
 int gvit_dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, uint64_t seed, uint64_t offset,
-                              int dtype, void* out, uint8_t* keep_mask, void* stream) {
-  TRY(check_dtype(dtype, "dropout_residual_fwd"));
+                              int dtype, int y_dtype, void* out, uint8_t* keep_mask, void* stream) {
+  TRY(check_ln_pair(dtype, y_dtype, "dropout_residual_fwd"));
   GVIT_REQUIRE(y && out, GVIT_ERR_SHAPE, "dropout_residual_fwd: null pointer");
+  GVIT_REQUIRE(resid || dtype == y_dtype, GVIT_ERR_DTYPE, "dropout_residual_fwd: without a residual, dtype must equal y_dtype");
   GVIT_REQUIRE(n >= 8 && n % 8 == 0, GVIT_ERR_SHAPE, "dropout_residual_fwd: n=%lld must be a positive multiple of 8", (long long)n);
   GVIT_REQUIRE(p >= 0.f && p < 1.f, GVIT_ERR_SHAPE, "dropout_residual_fwd: p=%f not in [0,1)", p);
   GVIT_REQUIRE(p == 0.f || keep_mask, GVIT_ERR_SHAPE, "dropout_residual_fwd: keep_mask required when p > 0");
-  GVIT_REQUIRE(aligned16(y) && aligned16(out) && (!resid || aligned16(resid)) && (!keep_mask || aligned16(keep_mask)), GVIT_ERR_ALIGN, "dropout_residual_fwd: 16-byte alignment required");
-  return dropout_residual_fwd(y, resid, n, p, seed, offset, dtype, out, keep_mask, static_cast<cudaStream_t>(stream));
+  GVIT_REQUIRE(aligned16(y) && aligned16(out) && (!resid || aligned16(resid)), GVIT_ERR_ALIGN, "dropout_residual_fwd: 16-byte alignment required");
+  return dropout_residual_fwd(y, resid, n, p, seed, offset, dtype, y_dtype, out, keep_mask, static_cast<cudaStream_t>(stream));
 }
 
-int gvit_dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, void* dy, void* stream) {
-  TRY(check_dtype(dtype, "dropout_bwd"));
+int gvit_dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, int y_dtype, void* dy,
+                     void* stream) {
+  TRY(check_ln_pair(dtype, y_dtype, "dropout_bwd"));
   GVIT_REQUIRE(dout && keep_mask && dy, GVIT_ERR_SHAPE, "dropout_bwd: null pointer");
   GVIT_REQUIRE(n >= 8 && n % 8 == 0 && p > 0.f && p < 1.f, GVIT_ERR_SHAPE, "dropout_bwd: n=%lld p=%f", (long long)n, p);
-  GVIT_REQUIRE(aligned16(dout) && aligned16(dy) && aligned16(keep_mask), GVIT_ERR_ALIGN, "dropout_bwd: 16-byte alignment required");
-  return dropout_bwd(dout, keep_mask, n, p, dtype, dy, static_cast<cudaStream_t>(stream));
+  GVIT_REQUIRE(aligned16(dout) && aligned16(dy), GVIT_ERR_ALIGN, "dropout_bwd: 16-byte alignment required");
+  return dropout_bwd(dout, keep_mask, n, p, dtype, y_dtype, dy, static_cast<cudaStream_t>(stream));
+}
+
+int gvit_gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t offset, int dtype, void* out,
+                          uint8_t* keep_mask, void* stream) {
+  TRY(check_dtype(dtype, "gelu_dropout_fwd"));
+  GVIT_REQUIRE(u && out, GVIT_ERR_SHAPE, "gelu_dropout_fwd: null pointer");
+  GVIT_REQUIRE(n >= 8 && n % 8 == 0, GVIT_ERR_SHAPE, "gelu_dropout_fwd: n=%lld must be a positive multiple of 8", (long long)n);
+  GVIT_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || keep_mask), GVIT_ERR_SHAPE, "gelu_dropout_fwd: p=%f (keep_mask required when p > 0)", p);
+  GVIT_REQUIRE(aligned16(u) && aligned16(out), GVIT_ERR_ALIGN, "gelu_dropout_fwd: 16-byte alignment required");
+  return gelu_dropout_fwd(u, n, p, seed, offset, dtype, out, keep_mask, static_cast<cudaStream_t>(stream));
+}
+
+int gvit_gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, int64_t n, float p, int dtype,
+                          void* du, void* stream) {
+  TRY(check_dtype(dtype, "gelu_dropout_bwd"));
+  GVIT_REQUIRE(dout && u && du, GVIT_ERR_SHAPE, "gelu_dropout_bwd: null pointer");
+  GVIT_REQUIRE(n >= 8 && n % 8 == 0, GVIT_ERR_SHAPE, "gelu_dropout_bwd: n=%lld must be a positive multiple of 8", (long long)n);
+  GVIT_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || keep_mask), GVIT_ERR_SHAPE, "gelu_dropout_bwd: p=%f (keep_mask required when p > 0)", p);
+  GVIT_REQUIRE(aligned16(dout) && aligned16(u) && aligned16(du), GVIT_ERR_ALIGN, "gelu_dropout_bwd: 16-byte alignment required");
+  return gelu_dropout_bwd(dout, u, keep_mask, n, p, dtype, du, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -38,11 +38,17 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
 
 // ---- edges : edges.cu
 int layernorm_fwd(const void* x, const void* gamma, const void* beta, int64_t rows, int D, float eps, int dtype,
-                  void* y, float* mean, float* rstd, cudaStream_t st);
+                  int y_dtype, void* y, float* mean, float* rstd, cudaStream_t st);
 int layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, int64_t rows,
-                  int D, int dtype, void* dx, float* dgamma, float* dbeta, float* partial_ws, cudaStream_t st);
+                  int D, int dtype, int y_dtype, void* dx, float* dgamma, float* dbeta, float* partial_ws,
+                  cudaStream_t st);
 int dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, uint64_t seed, uint64_t offset,
-                         int dtype, void* out, uint8_t* keep_mask, cudaStream_t st);
-int dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, void* dy, cudaStream_t st);
+                         int dtype, int y_dtype, void* out, uint8_t* keep_mask, cudaStream_t st);
+int dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, int y_dtype, void* dy,
+                cudaStream_t st);
+int gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t offset, int dtype, void* out,
+                     uint8_t* keep_mask, cudaStream_t st);
+int gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, int64_t n, float p, int dtype, void* du,
+                     cudaStream_t st);
 
 }  // namespace gvit

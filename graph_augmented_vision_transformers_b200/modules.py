@@ -51,12 +51,13 @@ class Attention(nn.Module):
         self.proj = nn.Linear(dim, dim)
         self.proj_drop = nn.Dropout(proj_drop)
 
-    def forward(self, x):
+    def forward(self, x, resid=None):
+        """``resid`` (used by Block) folds the residual add of vit.py:117 into the proj_drop kernel."""
         if self.training and self.attn_drop.p > 0:
             # 0 in every configuration the reference ships (vit.py:127; scripts/train.py never sets it)
             raise NotImplementedError("attn_drop > 0 is not implemented by the fused attention kernel")
         o = ops.attention_core(self.qkv(x), self.num_heads, self.scale)
-        return ops.dropout_add(self.proj(o), None, self.proj_drop.p, self.training)
+        return ops.dropout_add(self.proj(o), resid, self.proj_drop.p, self.training)
 
 
 class Mlp(nn.Module):
@@ -69,10 +70,9 @@ class Mlp(nn.Module):
         self.fc2 = nn.Linear(hidden_features, out_features)
         self.drop = nn.Dropout(drop)
 
-    def forward(self, x):
-        x = self.act(self.fc1(x))
-        x = ops.dropout_add(x, None, self.drop.p, self.training)
-        return ops.dropout_add(self.fc2(x), None, self.drop.p, self.training)
+    def forward(self, x, resid=None):
+        x = ops.gelu_dropout(self.fc1(x), self.drop.p, self.training)        # act + drop in one pass
+        return ops.dropout_add(self.fc2(x), resid, self.drop.p, self.training)
 
 
 class DropPath(nn.Module):
@@ -137,15 +137,25 @@ class Block(nn.Module):
         self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
         self.graph_mode = graph_mode
 
+    def _foldable(self):
+        """The residual adds may be folded into the sub-layers' last kernels unless somebody observes the
+        sub-layer outputs through module hooks (Grad-CAM hooks blocks.11.attn, gradcam.py:233-236)."""
+        if not isinstance(self.drop_path, nn.Identity):
+            return False
+        subs = [self.attn, self.mlp] + ([self.graph] if self.graph_mode is not None else [])
+        return not any(m._forward_hooks or m._backward_hooks or m._forward_pre_hooks for m in subs)
+
     def forward(self, x):
+        if self._foldable():
+            # every shipped configuration: the three residual adds are folded into the producing kernels
+            x = self.attn(self.norm1(x), resid=x)
+            if self.graph_mode is not None:
+                x = self.graph(self.norm_g(x), resid=x)
+            return self.mlp(self.norm2(x), resid=x)
         x = x + self.drop_path(self.attn(self.norm1(x)))
         if self.graph_mode is not None:
-            if isinstance(self.drop_path, nn.Identity):
-                x = self.graph(self.norm_g(x), resid=x)      # residual folded into the kernel epilogue
-            else:
-                x = x + self.drop_path(self.graph(self.norm_g(x)))
-        x = x + self.drop_path(self.mlp(self.norm2(x)))
-        return x
+            x = x + self.drop_path(self.graph(self.norm_g(x)))
+        return x + self.drop_path(self.mlp(self.norm2(x)))
 
 
 class PatchEmbed(nn.Module):
@@ -165,8 +175,9 @@ class PatchEmbed(nn.Module):
 class VisionTransformer(nn.Module):
     def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=14, embed_dim=768, depth=12,
                  num_heads=12, mlp_ratio=4., qkv_bias=True, drop_rate=0., attn_drop_rate=0., drop_path_rate=0., *,
-                 graph_mode=None, graph_k=8, graph_every=1):
+                 graph_mode=None, graph_k=8, graph_every=1, fp32_residual=False):
         super().__init__()
+        self.fp32_residual = fp32_residual
         self.num_classes = num_classes
         self.num_features = self.embed_dim = embed_dim
         self.graph_mode, self.graph_k, self.graph_every = graph_mode, graph_k, graph_every
@@ -220,6 +231,11 @@ class VisionTransformer(nn.Module):
 
     def forward_features(self, x):
         x = self.patch_embed(x)
+        # Residual-stream dtype: by default the stream follows the compute dtype (bf16 under autocast - half the
+        # bytes on every LayerNorm / residual edge).  fp32_residual=True keeps torch.autocast's own behaviour,
+        # where cat / add promote the stream to the fp32 of cls_token and pos_embed (vit.py:207-211).
+        if self.fp32_residual:
+            x = x.float()
         x = torch.cat((self.cls_token.expand(x.shape[0], -1, -1).to(x.dtype), x), dim=1)
         x = x + self.pos_embed.to(x.dtype)
         x = ops.dropout_add(x, None, self.pos_drop.p, self.training)

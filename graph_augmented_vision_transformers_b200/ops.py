@@ -5,6 +5,7 @@ Each function here is one stage of the graph-augmented ViT hot path (SURVEY.md s
 * ``attention_core``   - a2, /root/reference/src/models/vit.py:59-69
 * ``layer_norm``       - a5, nn.LayerNorm at vit.py:103,108,154
 * ``dropout_add``      - a5, proj_drop + residual at vit.py:71,117
+* ``gelu_dropout``     - Mlp activation edge, nn.GELU + nn.Dropout at vit.py:84,92
 * ``knn_graph``        - a7, SURVEY.md section 9 G1-G3 (no reference symbol)
 * ``patch_graph``      - a7+a8 as one differentiable op, section 9 G0-G6 (no reference symbol)
 
@@ -22,7 +23,7 @@ import torch.nn.functional as F
 from . import _lib
 from ._lib import GVIT_BF16, GVIT_F32, GVIT_LN_PARTIALS
 
-__all__ = ["attention_core", "layer_norm", "dropout_add", "knn_graph", "graph_reverse", "patch_graph",
+__all__ = ["attention_core", "layer_norm", "dropout_add", "gelu_dropout", "knn_graph", "graph_reverse", "patch_graph",
            "agg_gather", "launch_count", "reset_launch_count"]
 
 # kernels launched through the C ABI since the last reset (bench.py reports it as gpu_launches)
@@ -30,7 +31,7 @@ _LAUNCHES = {"n": 0}
 _KERNELS_PER_CALL = {
     "gvit_knn_fwd": 1, "gvit_graph_reverse": 1, "gvit_knn_bwd": 1, "gvit_agg_gather_fwd": 1, "gvit_agg_fwd": 1,
     "gvit_agg_bwd": 2, "gvit_attn_fwd": 1, "gvit_attn_bwd": 1, "gvit_layernorm_fwd": 1, "gvit_layernorm_bwd": 2,
-    "gvit_dropout_residual_fwd": 1, "gvit_dropout_bwd": 1,
+    "gvit_dropout_residual_fwd": 1, "gvit_dropout_bwd": 1, "gvit_gelu_dropout_fwd": 1, "gvit_gelu_dropout_bwd": 1,
 }
 
 
@@ -125,19 +126,23 @@ def attention_core(qkv: torch.Tensor, num_heads: int, scale: float) -> torch.Ten
 
 
 # ------------------------------------------------------------------------------------------------
-# a5: LayerNorm, dropout + residual
+# a5: LayerNorm, dropout + residual, GELU + dropout
 # ------------------------------------------------------------------------------------------------
+_TORCH_DT = {GVIT_F32: torch.float32, GVIT_BF16: torch.bfloat16}
+
+
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, eps):
+    def forward(ctx, x, weight, bias, eps, y_code):
         D = x.shape[-1]
         rows = x.numel() // D
-        y = torch.empty_like(x)
+        y = torch.empty(x.shape, dtype=_TORCH_DT[y_code], device=x.device)
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
-        _call("gvit_layernorm_fwd", _ptr(x), _ptr(weight), _ptr(bias), rows, D, float(eps), _dtype_code(x), _ptr(y),
-              _ptr(mean), _ptr(rstd), _stream())
+        _call("gvit_layernorm_fwd", _ptr(x), _ptr(weight), _ptr(bias), rows, D, float(eps), _dtype_code(x), y_code,
+              _ptr(y), _ptr(mean), _ptr(rstd), _stream())
         ctx.save_for_backward(x, weight, mean, rstd)
+        ctx.y_code = y_code
         return y
 
     @staticmethod
@@ -150,32 +155,40 @@ class _LayerNorm(torch.autograd.Function):
         dgb = torch.empty((2, D), dtype=torch.float32, device=x.device)
         ws = torch.empty(2 * GVIT_LN_PARTIALS * D, dtype=torch.float32, device=x.device)
         _call("gvit_layernorm_bwd", _ptr(dy), _ptr(x), _ptr(weight), _ptr(mean), _ptr(rstd), rows, D, _dtype_code(x),
-              _ptr(dx), _ptr(dgb[0]), _ptr(dgb[1]), _ptr(ws), _stream())
-        return dx, dgb[0].to(weight.dtype), dgb[1].to(weight.dtype), None
+              ctx.y_code, _ptr(dx), _ptr(dgb[0]), _ptr(dgb[1]), _ptr(ws), _stream())
+        return dx, dgb[0].to(weight.dtype), dgb[1].to(weight.dtype), None, None
 
 
 def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     """nn.LayerNorm over the last dimension (affine), statistics in fp32.
 
-    Like ``torch.autocast`` the normalisation keeps the input's dtype (fp32 activations stay fp32).
+    Outside autocast the output has x's dtype.  Under autocast an fp32 x (fp32 residual stream) yields a bf16
+    output - the cast the consuming Linear / graph / attention op would do anyway, folded into the kernel.
     """
     _check_cuda(x, weight, bias)
     if x.dtype not in (torch.float32, torch.bfloat16):
         x = x.to(torch.bfloat16 if x.dtype == torch.float16 else torch.float32)
+    y_code = GVIT_BF16 if (x.dtype == torch.bfloat16 or torch.is_autocast_enabled("cuda")) else GVIT_F32
     with torch.autocast("cuda", enabled=False):
-        return _LayerNorm.apply(x.contiguous(), weight.to(x.dtype), bias.to(x.dtype), float(eps))
+        return _LayerNorm.apply(x.contiguous(), weight.to(x.dtype), bias.to(x.dtype), float(eps), y_code)
+
+
+def _draw_seed() -> int:
+    # CPU generator: follows torch.manual_seed, costs no device synchronisation
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
 
 
 class _DropoutAdd(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y, resid, p, seed):
         n = y.numel()
-        out = torch.empty_like(y)
-        mask = torch.empty(n, dtype=torch.uint8, device=y.device) if p > 0 else None
-        _call("gvit_dropout_residual_fwd", _ptr(y), _ptr(resid), n, float(p), int(seed), 0, _dtype_code(y), _ptr(out),
-              _ptr(mask), _stream())
+        out = torch.empty_like(y if resid is None else resid)
+        mask = torch.empty(n // 8, dtype=torch.uint8, device=y.device) if p > 0 else None
+        _call("gvit_dropout_residual_fwd", _ptr(y), _ptr(resid), n, float(p), int(seed), 0, _dtype_code(out),
+              _dtype_code(y), _ptr(out), _ptr(mask), _stream())
         ctx.p = p
         ctx.has_resid = resid is not None
+        ctx.y_dtype = y.dtype
         if p > 0:
             ctx.save_for_backward(mask)
         return out
@@ -184,18 +197,19 @@ class _DropoutAdd(torch.autograd.Function):
     def backward(ctx, dout):
         dresid = dout if ctx.has_resid else None
         if ctx.p == 0:
-            return dout, dresid, None, None
+            return dout.to(ctx.y_dtype), dresid, None, None
         (mask,) = ctx.saved_tensors
         dout = dout.contiguous()
-        dy = torch.empty_like(dout)
-        _call("gvit_dropout_bwd", _ptr(dout), _ptr(mask), dout.numel(), float(ctx.p), _dtype_code(dout), _ptr(dy),
-              _stream())
+        dy = torch.empty(dout.shape, dtype=ctx.y_dtype, device=dout.device)
+        _call("gvit_dropout_bwd", _ptr(dout), _ptr(mask), dout.numel(), float(ctx.p), _dtype_code(dout),
+              _dtype_code(dy), _ptr(dy), _stream())
         return dy, dresid, None, None
 
 
 def dropout_add(y: torch.Tensor, resid: torch.Tensor | None, p: float, training: bool) -> torch.Tensor:
-    """``resid + dropout(y, p)`` in one pass (Philox-4x32-10 keep mask); ``resid`` may be None.
+    """``resid + dropout(y, p)`` in one pass (Philox-4x32-10 keep mask, stored as one bit per element).
 
+    ``resid`` may be None (plain dropout).  A bf16 branch ``y`` may be added onto an fp32 stream ``resid``.
     The seed of each call is drawn from PyTorch's CPU generator, so ``torch.manual_seed`` makes runs
     reproducible without a device synchronisation.
     """
@@ -203,14 +217,53 @@ def dropout_add(y: torch.Tensor, resid: torch.Tensor | None, p: float, training:
     p = float(p) if training else 0.0
     if p == 0.0 and resid is None:
         return y
-    dt = y.dtype if y.dtype in (torch.float32, torch.bfloat16) else torch.bfloat16
-    if resid is not None and resid.dtype != dt:       # mixed residual stream (fp32) / branch (bf16): add in fp32
-        dt = torch.float32 if torch.float32 in (resid.dtype, y.dtype) else dt
+    if y.dtype not in (torch.float32, torch.bfloat16):
+        y = y.to(torch.bfloat16)
+    if resid is not None:
+        if resid.dtype not in (torch.float32, torch.bfloat16):
+            resid = resid.to(torch.bfloat16)
+        if resid.dtype == torch.bfloat16 and y.dtype == torch.float32:
+            resid = resid.float()                    # only (stream fp32, branch bf16) is a mixed pairing
     if y.numel() % 8:
         raise ValueError("dropout_add needs a multiple of 8 elements")
-    seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
+    seed = _draw_seed() if p > 0 else 0
     with torch.autocast("cuda", enabled=False):
-        return _DropoutAdd.apply(y.to(dt).contiguous(), None if resid is None else resid.to(dt).contiguous(), p, seed)
+        return _DropoutAdd.apply(y.contiguous(), None if resid is None else resid.contiguous(), p, seed)
+
+
+class _GeluDropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, p, seed):
+        n = u.numel()
+        out = torch.empty_like(u)
+        mask = torch.empty(n // 8, dtype=torch.uint8, device=u.device) if p > 0 else None
+        _call("gvit_gelu_dropout_fwd", _ptr(u), n, float(p), int(seed), 0, _dtype_code(u), _ptr(out), _ptr(mask),
+              _stream())
+        ctx.p = p
+        ctx.save_for_backward(u, mask)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        u, mask = ctx.saved_tensors
+        dout = dout.contiguous()
+        du = torch.empty_like(u)
+        _call("gvit_gelu_dropout_bwd", _ptr(dout), _ptr(u), _ptr(mask), u.numel(), float(ctx.p), _dtype_code(u),
+              _ptr(du), _stream())
+        return du, None, None
+
+
+def gelu_dropout(u: torch.Tensor, p: float, training: bool) -> torch.Tensor:
+    """``dropout(gelu(u), p)`` with the exact-erf GELU of nn.GELU (vit.py:84,92) in one pass; the backward
+    recomputes GELU' from u instead of keeping the activation."""
+    _check_cuda(u)
+    p = float(p) if training else 0.0
+    dt = _autocast_dtype(u)
+    if u.numel() % 8:
+        raise ValueError("gelu_dropout needs a multiple of 8 elements")
+    seed = _draw_seed() if p > 0 else 0
+    with torch.autocast("cuda", enabled=False):
+        return _GeluDropout.apply(u.to(dt).contiguous(), p, seed)
 
 
 # ------------------------------------------------------------------------------------------------

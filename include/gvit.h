@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GVIT_ABI_VERSION 1
+#define GVIT_ABI_VERSION 2
 #if defined(__GNUC__)
 #define GVIT_API __attribute__((visibility("default")))
 #else
@@ -101,7 +101,7 @@ GVIT_API int gvit_agg_bwd(const void* p, int64_t batch_stride, int64_t row_strid
 /* ---- a2: attention core, replaces /root/reference/src/models/vit.py:59-69 -------------------
  * qkv : the packed projection output of vit.py:59, (B,N,3,H,dh) contiguous - consumed in place, no
  *       permute; out : (B,N,H*dh) head-major (the layout vit.py:69's transpose+reshape produces);
- * lse : (B,H,N) fp32 log-sum-exp of the scaled scores, saved for the backward.  dh in {32,64} (fp32),
+ * lse : (B,H,N) fp32 log-sum-exp of the scaled scores, saved for the backward.  dh in {16,32,64} (fp32 arithmetic),
  * dh == 64 (bf16).  attn_drop is 0 in every shipped config (vit.py:127) and is not implemented. */
 GVIT_API int gvit_attn_fwd(const void* qkv, int B, int N, int H, int dh, float scale, int dtype, void* out, float* lse,
                   void* stream);
@@ -110,21 +110,35 @@ GVIT_API int gvit_attn_bwd(const void* qkv, const void* out, const void* dout, c
                   float scale, int dtype, float* delta_ws, void* dqkv, void* stream);
 
 /* ---- a5: LayerNorm + residual edges, replace nn.LayerNorm / "+" at vit.py:103,108,116-119 ----
- * rows x D, eps as nn.LayerNorm (1e-5); statistics in fp32; mean/rstd (rows) saved for the backward. */
+ * rows x D, eps as nn.LayerNorm (1e-5); statistics in fp32; mean/rstd (rows) saved for the backward.
+ * dtype is the type of x / gamma / beta (and dx / the residual stream); y_dtype the type of y (and dy): equal to
+ * dtype, or GVIT_BF16 with dtype GVIT_F32 - the fp32-stream / bf16-branch pairing of autocast, with the cast
+ * folded into the kernel. */
 GVIT_API int gvit_layernorm_fwd(const void* x, const void* gamma, const void* beta, int64_t rows, int D, float eps, int dtype,
-                       void* y, float* mean, float* rstd, void* stream);
+                       int y_dtype, void* y, float* mean, float* rstd, void* stream);
 /* dgamma/dbeta are fp32 (D); partial_ws is an fp32 workspace of 2*GVIT_LN_PARTIALS*D floats. */
 enum { GVIT_LN_PARTIALS = 296 };
 GVIT_API int gvit_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
-                       int64_t rows, int D, int dtype, void* dx, float* dgamma, float* dbeta, float* partial_ws,
-                       void* stream);
-/* out = resid + dropout(y, p) with a Philox-4x32-10 keep mask generated from (seed, offset) - the
- * proj_drop + residual edge of vit.py:71,117.  p == 0 or training == 0 degenerates to an add.
- * keep_mask: n bytes (0/1), may be NULL when p == 0. */
+                       int64_t rows, int D, int dtype, int y_dtype, void* dx, float* dgamma, float* dbeta,
+                       float* partial_ws, void* stream);
+/* out = resid + dropout(y, p) with a Philox-4x32-10 keep mask generated from (seed, offset) - the proj_drop +
+ * residual edge of vit.py:71,117 (also pos_drop, vit.py:212, with resid NULL).  p == 0 degenerates to an add.
+ * dtype: type of resid / out (the residual stream); y_dtype: type of y (the branch) - same pairing rule as LayerNorm;
+ * with resid NULL both must be equal.  keep_mask: n/8 bytes, ONE BIT per element (bit j of byte i = element 8i+j),
+ * may be NULL when p == 0.  n % 8 == 0. */
 GVIT_API int gvit_dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, uint64_t seed, uint64_t offset,
-                              int dtype, void* out, uint8_t* keep_mask, void* stream);
-GVIT_API int gvit_dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, void* dy,
+                              int dtype, int y_dtype, void* out, uint8_t* keep_mask, void* stream);
+/* dy = dout * keep / (1 - p);  dout has `dtype`, dy has `y_dtype`. */
+GVIT_API int gvit_dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, int y_dtype, void* dy,
                      void* stream);
+
+/* ---- Mlp activation edge: out = dropout(GELU(u), p), exact-erf GELU - nn.GELU + nn.Dropout at vit.py:84,92 in one
+ * pass; the backward recomputes GELU' from the saved pre-activation u (no activation tensor is kept).
+ * keep_mask as above (may be NULL when p == 0). */
+GVIT_API int gvit_gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t offset, int dtype, void* out,
+                          uint8_t* keep_mask, void* stream);
+GVIT_API int gvit_gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, int64_t n, float p, int dtype,
+                          void* du, void* stream);
 
 #ifdef __cplusplus
 }

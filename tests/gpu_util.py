@@ -16,13 +16,15 @@ def tokens(B, Np, D, seed=0, dtype=torch.float32):
     return h.float(), h.to(DEV)
 
 
-def check_adjacency(h_cpu, idx_dev, vals_dev, k, noise, min_sure=0.9):
+def check_adjacency(h_cpu, idx_dev, vals_dev, k, noise, min_sure=None):
     """idx must equal the float64 oracle's on every row whose decision margin exceeds the arithmetic noise;
     on the remaining rows the selected similarities must still agree (two near-equal neighbours may swap)."""
     idx64, vals64, margin = graph_oracle.knn_f64(h_cpu[:, 1:].numpy(), k)
     idx = idx_dev.cpu().numpy()
     vals = vals_dev.cpu().numpy()
     sure = margin > noise
+    if min_sure is None:                      # k+1 gaps per row can each fall inside the noise band
+        min_sure = 0.9 if k <= 16 else 0.7
     assert sure.mean() >= min_sure, f"only {sure.mean():.3f} of the rows are decidable"
     bad = (idx[sure] != idx64[sure]).any(-1)
     assert not bad.any(), f"{bad.sum()} decidable rows differ, e.g. {idx[sure][bad][:2]} vs {idx64[sure][bad][:2]}"

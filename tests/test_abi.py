@@ -16,7 +16,8 @@ def test_header_declares_the_expected_surface():
     names = [n for n, _ in DECLS]
     for must in ("gvit_knn_fwd", "gvit_knn_bwd", "gvit_graph_reverse", "gvit_agg_fwd", "gvit_agg_gather_fwd",
                  "gvit_agg_bwd", "gvit_attn_fwd", "gvit_attn_bwd", "gvit_layernorm_fwd", "gvit_layernorm_bwd",
-                 "gvit_dropout_residual_fwd", "gvit_dropout_bwd", "gvit_version", "gvit_last_error_string"):
+                 "gvit_dropout_residual_fwd", "gvit_dropout_bwd", "gvit_gelu_dropout_fwd", "gvit_gelu_dropout_bwd",
+                 "gvit_version", "gvit_last_error_string"):
         assert must in names
     assert len(names) == len(set(names))
 
@@ -50,7 +51,9 @@ def test_validation_errors_are_loud_and_need_no_gpu():
     with pytest.raises(_lib.GvitError, match="GVIT_ERR_SHAPE"):
         _lib.call("gvit_knn_fwd", 16, 64, 64, 1, 4, 64, 9, _lib.GVIT_F32, 16, 16, 16, None)     # k > Np
     with pytest.raises(_lib.GvitError, match="GVIT_ERR_ALIGN"):
-        _lib.call("gvit_layernorm_fwd", 8, 16, 16, 1, 64, 1e-5, _lib.GVIT_F32, 16, 16, 16, None)
+        _lib.call("gvit_layernorm_fwd", 8, 16, 16, 1, 64, 1e-5, _lib.GVIT_F32, _lib.GVIT_F32, 16, 16, 16, None)
+    with pytest.raises(_lib.GvitError, match="GVIT_ERR_DTYPE"):            # bf16 stream with an fp32 branch is not a pairing
+        _lib.call("gvit_layernorm_fwd", 16, 16, 16, 1, 64, 1e-5, _lib.GVIT_BF16, _lib.GVIT_F32, 16, 16, 16, None)
     with pytest.raises(_lib.GvitError, match="GVIT_ERR_UNSUPPORTED"):
         _lib.call("gvit_agg_fwd", 16, 1, 16, 64, 4, _lib.GVIT_F32, 16, 16, 16, None, None, 16, None, None, None)
 

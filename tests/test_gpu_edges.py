@@ -36,11 +36,11 @@ def test_dropout_add():
     torch.manual_seed(0)
     xr = x.clone().requires_grad_(True)
     y = ops.dropout_add(xr, r, 0.1, training=True)
-    kept = (y != r)
-    assert abs(float(kept.float().mean()) - 0.9) < 2e-3                      # Bernoulli(0.9) keep mask
-    assert rel_err(y[kept], (x / 0.9 + r)[kept]) < 1e-6
     y.backward(torch.ones_like(y))
-    assert torch.equal(xr.grad != 0, kept) and rel_err(xr.grad[kept], torch.full_like(xr.grad[kept], 1 / 0.9)) < 1e-6
+    kept = xr.grad != 0                                                        # the keep mask, seen through the gradient
+    assert abs(float(kept.float().mean()) - 0.9) < 2e-3                        # Bernoulli(0.9)
+    assert rel_err(xr.grad[kept], torch.full_like(xr.grad[kept], 1 / 0.9)) < 1e-6
+    assert rel_err(y[kept], (x / 0.9 + r)[kept]) < 1e-6 and torch.equal(y[~kept], r[~kept])
     torch.manual_seed(0)
     assert torch.equal(ops.dropout_add(x, r, 0.1, training=True), y)          # reproducible under manual_seed
     assert not torch.equal(ops.dropout_add(x, r, 0.1, training=True), y)      # and fresh on the next call
@@ -48,3 +48,46 @@ def test_dropout_add():
     assert abs(float(m.mean()) - 0.5) < 2e-3 and abs(float((m[:, 1:] * m[:, :-1]).mean()) - 0.25) < 2e-3
     yb = ops.dropout_add(x.bfloat16(), r, 0.0, training=True)                 # bf16 branch onto an fp32 stream
     assert yb.dtype == torch.float32 and rel_err(yb, x.bfloat16().float() + r) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gelu_dropout(dtype):
+    g = torch.Generator().manual_seed(0)
+    u = (torch.randn(64, 197, 3072, generator=g) * 1.5).to(dtype).float()
+    cot = torch.randn(64, 197, 3072, generator=g).to(dtype).float()
+    tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
+    ud = u.to(DEV, dtype).requires_grad_(True)
+    out = ops.gelu_dropout(ud, 0.1, training=False)                          # eval: exact-erf GELU only
+    out.backward(cot.to(DEV, dtype))
+    uc = u.clone().requires_grad_(True)
+    F.gelu(uc).backward(cot)
+    assert rel_err(out, F.gelu(u)) < tol and rel_err(ud.grad, uc.grad) < tol
+    torch.manual_seed(1)
+    ud.grad = None
+    out = ops.gelu_dropout(ud, 0.1, training=True)
+    out.backward(cot.to(DEV, dtype))
+    kept = (ud.grad != 0) | (cot.to(DEV) == 0) | (uc.grad.to(DEV) == 0)
+    frac = float((ud.grad != 0).float().mean())
+    assert abs(frac - 0.9) < 5e-3
+    assert rel_err((out.float() * kept)[kept], (F.gelu(u).to(DEV) / 0.9)[kept]) < tol
+    assert rel_err(ud.grad.float()[kept], (uc.grad.to(DEV) / 0.9)[kept]) < tol
+    assert float(out[~kept].abs().max()) == 0.0
+
+
+def test_layernorm_fp32_stream_bf16_branch_under_autocast():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2 * 197, 768, generator=g) * 2
+    w, b = 1 + 0.2 * torch.randn(768, generator=g), 0.1 * torch.randn(768, generator=g)
+    cot = torch.randn(2 * 197, 768, generator=g).bfloat16().float()
+    xd, wd, bd = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = ops.layer_norm(xd, wd, bd)
+    assert y.dtype == torch.bfloat16                                          # the cast is folded into the kernel
+    y.backward(cot.to(DEV, torch.bfloat16))
+    assert xd.grad.dtype == torch.float32
+    xc, wc, bc = (t.clone().requires_grad_(True) for t in (x, w, b))
+    F.layer_norm(xc, (768,), wc, bc).backward(cot)
+    assert rel_err(y, F.layer_norm(x, (768,), w, b)) < TOL_BF16
+    assert rel_err(xd.grad, xc.grad) < TOL_F32 * 10 and rel_err(wd.grad, wc.grad) < TOL_F32 * 10
+    y32 = ops.layer_norm(xd, wd, bd)                                           # no autocast: fp32 in, fp32 out
+    assert y32.dtype == torch.float32 and rel_err(y32, F.layer_norm(x, (768,), w, b)) < TOL_F32

@@ -121,3 +121,29 @@ def test_pure_bf16_model_runs():
     m.bfloat16()
     out = m(torch.randn(2, 3, 64, 64, device=DEV, dtype=torch.bfloat16))
     assert out.dtype == torch.bfloat16 and torch.isfinite(out.float()).all()
+
+
+def test_fp32_residual_stream_option_and_hook_safe_folding():
+    o, m = _pair(seed=7)
+    img = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(3))
+    m.fp32_residual = True
+    with torch.autocast("cuda", dtype=torch.bfloat16), torch.no_grad():
+        a = m(img.to(DEV))
+    m.fp32_residual = False
+    with torch.autocast("cuda", dtype=torch.bfloat16), torch.no_grad():
+        b = m(img.to(DEV))
+    assert rel_err(a, o(img)) < 3e-2 and rel_err(b, o(img)) < 5e-2
+    # a forward hook on blocks.1.attn (what Grad-CAM installs) must observe the attention output, not x + attention
+    seen = {}
+    h = m.blocks[1].attn.register_forward_hook(lambda mod, inp, out: seen.setdefault("out", out.detach()))
+    with torch.no_grad():
+        hooked = m(img.to(DEV))
+    h.remove()
+    with torch.no_grad():
+        plain = m(img.to(DEV))
+    assert rel_err(hooked, plain) < 1e-5
+    ref = {}
+    ho = o.blocks[1].attn.register_forward_hook(lambda mod, inp, out: ref.setdefault("out", out.detach()))
+    o(img)
+    ho.remove()
+    assert rel_err(seen["out"], ref["out"]) < TOL_F32
