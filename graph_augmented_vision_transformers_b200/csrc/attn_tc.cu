@@ -207,6 +207,175 @@ __global__ void __launch_bounds__(THREADS, 2) attn_fwd_tc_kernel(const __grid_co
 }
 
 // =================================================================================================
+// forward, N <= 256 keys (ViT-B/16 at 224: N = 197): persistent and pipelined.
+//
+// One CTA per SM loops over (image, head) work items.  An item is the whole attention problem of one head: all its
+// keys fit ONE tcgen05.mma N extent (NT = ceil16(N) <= 256), so there is no online-softmax rescaling - the score
+// row is complete after a single S = Q K^T.  Per item:
+//   TMA producer (warp 8)  : Q, K, V tiles of the NEXT item into the other shared-memory stage (2 x 96 KB stages)
+//   MMA issuer   (warp 9)  : S_g = Q_g K^T  (g = 0,1: query rows [128g, 128g+128)) -> TMEM region g (256 columns);
+//                            O_g = P_g V with P_g read straight from TMEM (tcgen05.mma A-from-TMEM) -> region g
+//   softmax WG g (warps 4g..4g+3, thread <-> query row = TMEM lane): row max, p = exp2(..), row sum; P_g is written
+//                            back IN PLACE over S_g as packed bf16 (tcgen05.st) - it never touches shared memory;
+//                            then O_g / l -> bf16 -> the (dead) Q_g tile of the stage -> one TMA tile store.
+// TMEM region g (256 of the 512 columns): S_g at [0, NT) -> P_g at [0, NT/2), O_g at [128, 192).
+// Regions, stages and warpgroups are decoupled by mbarriers, so S of item i+1 overlaps the epilogue of item i.
+// =================================================================================================
+constexpr int F2_THREADS = 320;
+constexpr int F2_STAGE_BYTES = 6 * TILE_BYTES;     // Q[256][64] | K[256][64] | V[256][64]
+struct __align__(8) F2Ctrl {
+  uint64_t full[2], empty[2], s_full[2], p_full[2], o_full[2], t_free[2];
+  uint32_t tmem_base;
+};
+constexpr size_t F2_SMEM = 1024 + 2 * F2_STAGE_BYTES + sizeof(F2Ctrl);
+
+__global__ void __launch_bounds__(F2_THREADS, 1) attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tm_qkv,
+                                                                     const __grid_constant__ CUtensorMap tm_out, int N,
+                                                                     int H, int items, float scale,
+                                                                     float* __restrict__ lse) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  F2Ctrl* ctl = reinterpret_cast<F2Ctrl*>(sm + 2 * F2_STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int MT = (N + 127) >> 7;                 // 128-row query tiles (1 or 2) == 128-row key/value tiles
+  const int NT = (N + 15) & ~15;                 // key extent of the MMAs
+
+  if (warp == 8 && lane == 0) {
+    prefetch_tmap(&tm_qkv);
+    prefetch_tmap(&tm_out);
+    for (int s = 0; s < 2; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], MT); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&ctl->s_full[g], 1);
+      mbar_init(&ctl->p_full[g], 128);
+      mbar_init(&ctl->o_full[g], 1);
+      mbar_init(&ctl->t_free[g], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc(&ctl->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ctl->tmem_base;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      int it = 0;
+      for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+        const int s = it & 1, b = w / H, h = w - b * H;
+        mbar_wait(&ctl->empty[s], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&ctl->full[s], (uint32_t)(3 * MT * TILE_BYTES));
+        uint8_t* st = sm + s * F2_STAGE_BYTES;
+        for (int j = 0; j < MT; ++j) {
+          tma_load_3d(st + j * TILE_BYTES, &tm_qkv, h * 64, j * 128, b, &ctl->full[s]);
+          tma_load_3d(st + (2 + j) * TILE_BYTES, &tm_qkv, (H + h) * 64, j * 128, b, &ctl->full[s]);
+          tma_load_3d(st + (4 + j) * TILE_BYTES, &tm_qkv, (2 * H + h) * 64, j * 128, b, &ctl->full[s]);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(128, NT, false, false);
+      const uint32_t idesc_o = make_idesc(128, 64, false, true);
+      int it = 0;
+      for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+        const int s = it & 1;
+        const uint32_t aQ = smem_u32(sm + s * F2_STAGE_BYTES), aK = aQ + 2 * TILE_BYTES, aV = aQ + 4 * TILE_BYTES;
+        mbar_wait(&ctl->full[s], (it >> 1) & 1);
+        for (int g = 0; g < MT; ++g) {
+          mbar_wait(&ctl->t_free[g], (it & 1) ^ 1);          // region g drained by the previous item's epilogue
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_ss(tmem + g * 256, make_sdesc(aQ + g * TILE_BYTES + kk * 32), make_sdesc(aK + kk * 32), idesc_s, kk > 0);
+          umma_commit(&ctl->s_full[g]);
+        }
+        for (int g = 0; g < MT; ++g) {
+          mbar_wait(&ctl->p_full[g], it & 1);                // P_g is in TMEM, S_g fully consumed
+          tc_fence_after();
+          for (int ks = 0; ks < NT / 16; ++ks)
+            umma_ts(tmem + g * 256 + 128, tmem + g * 256 + ks * 8, make_sdesc(aV + ks * 2048), idesc_o, ks > 0);
+          umma_commit(&ctl->o_full[g]);
+        }
+      }
+    }
+  } else {
+    const int g = warp >> 2;
+    if (g < MT) {
+      const int r = (warp & 3) * 32 + lane;                  // row inside the tile == TMEM lane
+      const uint32_t tR = tmem_lane_base(tmem + g * 256, warp);
+      const float sl2 = scale * LOG2E;
+      int it = 0;
+      for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+        const int s = it & 1, b = w / H, h = w - b * H;
+        mbar_wait(&ctl->s_full[g], it & 1);
+        tc_fence_after();
+        float mx = -3.0e38f;
+        for (int c0 = 0; c0 < NT; c0 += 32) {
+          float v[32];
+          tmem_ld32(tR + c0, v);
+#pragma unroll
+          for (int t = 0; t < 32; ++t) mx = (c0 + t < N) ? fmaxf(mx, v[t]) : mx;
+        }
+        const float msc = mx * sl2;
+        float l = 0.f;
+        for (int c0 = 0; c0 < NT; c0 += 32) {
+          float v[32];
+          tmem_ld32(tR + c0, v);
+          uint32_t pk[16];
+#pragma unroll
+          for (int t = 0; t < 32; t += 2) {
+            const float p0 = (c0 + t < N) ? ex2(fmaf(v[t], sl2, -msc)) : 0.f;
+            const float p1 = (c0 + t + 1 < N) ? ex2(fmaf(v[t + 1], sl2, -msc)) : 0.f;
+            l += p0 + p1;
+            pk[t >> 1] = pack_bf16(p0, p1);
+          }
+          tmem_st16(tR + (c0 >> 1), pk);                     // in place: columns [c0/2, c0/2+16) were read already
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&ctl->p_full[g]);
+
+        mbar_wait(&ctl->o_full[g], it & 1);
+        tc_fence_after();
+        const float inv = 1.0f / l;
+        uint8_t* so = sm + s * F2_STAGE_BYTES + g * TILE_BYTES;   // the Q_g tile: dead once S_g has been issued
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          float v[32];
+          tmem_ld32(tR + 128 + hlf * 32, v);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o4;
+            o4.x = pack_bf16(v[8 * q + 0] * inv, v[8 * q + 1] * inv);
+            o4.y = pack_bf16(v[8 * q + 2] * inv, v[8 * q + 3] * inv);
+            o4.z = pack_bf16(v[8 * q + 4] * inv, v[8 * q + 5] * inv);
+            o4.w = pack_bf16(v[8 * q + 6] * inv, v[8 * q + 7] * inv);
+            *reinterpret_cast<uint4*>(so + swz128(r, hlf * 32 + 8 * q)) = o4;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&ctl->t_free[g]);                        // TMEM region g may be overwritten by the next S_g
+        const int q = g * 128 + r;
+        if (q < N) lse[((int64_t)b * H + h) * N + q] = (msc + log2f(l)) * LN2;
+        fence_async_smem();                                  // generic-proxy tile writes -> visible to the TMA store
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        if ((warp & 3) == 0 && lane == 0) {
+          tma_store_3d(&tm_out, so, h * 64, g * 128, b);     // rows >= N are clipped by the TMA unit
+          tma_store_commit();
+          tma_store_wait_read();
+          mbar_arrive(&ctl->empty[s]);                       // stage s (Q/K/V and the O staging) may be refilled
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem, 512);
+}
+
+// =================================================================================================
 // backward (N <= 256)
 // =================================================================================================
 struct __align__(8) BwdCtrl {
@@ -214,8 +383,8 @@ struct __align__(8) BwdCtrl {
   uint64_t qdo_full, kv_full, kv_empty, s_full, p_full, mma_done;
   uint32_t tmem_base;
 };
-// Q[2], dO[2], K, V tiles + P^T, dS^T, dS (each [128][128] = 2 blocks)
-constexpr size_t BWD_SMEM = 1024 + 12 * TILE_BYTES + sizeof(BwdCtrl);
+// Q[2], dO[2], K, V tiles + P^T, dS^T (each [128][128] = 2 blocks)
+constexpr size_t BWD_SMEM = 1024 + 10 * TILE_BYTES + sizeof(BwdCtrl);
 
 __global__ void __launch_bounds__(THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,
                                                                  const __grid_constant__ CUtensorMap tm_do, int N,
@@ -232,9 +401,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_bwd_tc_kernel(const __grid_co
   uint8_t* sK = sm + 4 * TILE_BYTES;
   uint8_t* sV = sm + 5 * TILE_BYTES;
   uint8_t* sPT = sm + 6 * TILE_BYTES;      // [keys][q]   K-major A of dV
-  uint8_t* sdST = sm + 8 * TILE_BYTES;     // [keys][q]   K-major A of dK
-  uint8_t* sdS = sm + 10 * TILE_BYTES;     // [q][keys]   K-major A of dQ
-  BwdCtrl* ctl = reinterpret_cast<BwdCtrl*>(sm + 12 * TILE_BYTES);
+  uint8_t* sdST = sm + 8 * TILE_BYTES;     // [keys][q]   K-major A of dK and MN-major A of dQ
+  BwdCtrl* ctl = reinterpret_cast<BwdCtrl*>(sm + 10 * TILE_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, b = blockIdx.y;
@@ -275,7 +443,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_bwd_tc_kernel(const __grid_co
   } else if (warp == 5) {
     if (lane == 0) {
       const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV);
-      const uint32_t aPT = smem_u32(sPT), adST = smem_u32(sdST), adS = smem_u32(sdS);
+      const uint32_t aPT = smem_u32(sPT), adST = smem_u32(sdST);
       mbar_wait(&ctl->qdo_full, 0);
       int it = 0;
       for (int kt = 0; kt < T; ++kt) {
@@ -301,9 +469,12 @@ __global__ void __launch_bounds__(THREADS, 1) attn_bwd_tc_kernel(const __grid_co
             umma_ss(tdV, make_sdesc(aPT + aoff), make_sdesc(adO + boff), idesc_mn, qt > 0 || ks > 0);
             umma_ss(tdK, make_sdesc(adST + aoff), make_sdesc(aQ + boff), idesc_mn, qt > 0 || ks > 0);
           }
+          // dQ += dS K with dS = (dS^T)^T: the [keys][queries] tile is read as an MN-major A operand (M = queries
+          // contiguous, two 64-query atoms LBO = one tile apart), so dS is never transposed through shared memory
+          const uint32_t idesc_tt = make_idesc(128, 64, true, true);
           for (int ks = 0; ks < nk / 16; ++ks)     // K = keys of this tile
-            umma_ss(tdQ + qt * 64, make_sdesc(adS + (ks >> 2) * TILE_BYTES + (ks & 3) * 32), make_sdesc(aK + ks * 2048),
-                    idesc_mn, kt > 0 || ks > 0);
+            umma_ss(tdQ + qt * 64, make_sdesc_lbo(adST + ks * 2048, TILE_BYTES), make_sdesc(aK + ks * 2048), idesc_tt,
+                    kt > 0 || ks > 0);
           umma_commit(&ctl->mma_done);
           if (qt == T - 1) umma_commit(&ctl->kv_empty);
         }
@@ -355,13 +526,6 @@ __global__ void __launch_bounds__(THREADS, 1) attn_bwd_tc_kernel(const __grid_co
           }
           store_row32(sPT, t, c0, s);
           store_row32(sdST, t, c0, dp);
-          // dS[q][key]: transposed scatter, one bf16 per (row q, column t)
-          uint8_t* blk = sdS + (t >> 6) * TILE_BYTES;
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int ql = c0 + e;
-            *reinterpret_cast<__nv_bfloat16*>(blk + swz128(ql, t & 63) + (t & 7) * 2) = __float2bfloat16_rn(dp[e]);
-          }
         }
         fence_async_smem();
         tc_fence_before();
@@ -402,6 +566,17 @@ int attn_fwd_tc(const void* qkv, int B, int N, int H, float scale, void* out, fl
   CUtensorMap tm;
   int rc = make_tmap_bf16_3d(&tm, qkv, (uint64_t)3 * H * 64, N, B, (uint64_t)3 * H * 64, (uint64_t)N * 3 * H * 64, 128);
   if (rc != GVIT_OK) return rc;
+  if (N <= 256) {                                            // whole head per work item, persistent CTAs
+    CUtensorMap tm_out;
+    rc = make_tmap_bf16_3d(&tm_out, out, (uint64_t)H * 64, N, B, (uint64_t)H * 64, (uint64_t)N * H * 64, 128);
+    if (rc != GVIT_OK) return rc;
+    GVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F2_SMEM));
+    const int items = B * H;
+    const int grid = items < num_sms() ? items : num_sms();
+    attn_fwd_tc2_kernel<<<grid, F2_THREADS, F2_SMEM, st>>>(tm, tm_out, N, H, items, scale, lse);
+    GVIT_CHECK_LAUNCH();
+    return GVIT_OK;
+  }
   GVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));
   dim3 grid((N + 127) / 128, H, B);
   attn_fwd_tc_kernel<<<grid, THREADS, FWD_SMEM, st>>>(tm, N, H, scale, static_cast<__nv_bfloat16*>(out), lse);

@@ -77,6 +77,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, int
       : "memory");
 }
 
+// shared memory -> global tile store (rows outside the tensor are clipped by the TMA unit)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the committed stores have finished READING shared memory (the buffer may be reused)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // ---- tcgen05: TMEM allocation (one full warp executes these) ----
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols) : "memory");
@@ -138,6 +148,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// ---- tcgen05.st : 16 consecutive 32-bit columns of this thread's lane (used to hand bf16x2-packed operands to a
+// tcgen05.mma that reads A from tensor memory) ----
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t tmem_lane_base(uint32_t taddr, int warp) { return taddr + (static_cast<uint32_t>((warp & 3) * 32) << 16); }
 
 // ---- descriptors ----
@@ -154,6 +174,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major,
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
   constexpr uint64_t SBO = 1024 >> 4, LBO = 1;
   return static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4) | (LBO << 16) | (SBO << 32) | (1ull << 46) | (2ull << 61);
+}
+// same, for an MN-major operand that spans several 64-element atoms along M/N: lbo_bytes = distance between them
+__device__ __forceinline__ uint64_t make_sdesc_lbo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  constexpr uint64_t SBO = 1024 >> 4;
+  return static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) | (SBO << 32) |
+         (1ull << 46) | (2ull << 61);
 }
 // byte offset of element (row, col) inside a swizzled [rows][64 bf16] tile (col multiple of 8 -> 16-byte chunk)
 __device__ __forceinline__ uint32_t swz128(int row, int col) {
