@@ -298,9 +298,9 @@ def run_ours(args):
         return float(ms) / steps
 
     # ---- device-resident throughput -----------------------------------------------------------
-    for _ in range(args.warmup):
+    sampler = ClockSampler(local) if rank == 0 else None   # started before the warm-up: nvidia-smi takes ~0.5 s to
+    for _ in range(args.warmup):                            # emit its first sample; idle samples are filtered by power
         train_step(img_dev, tgt_dev)
-    sampler = ClockSampler(local) if rank == 0 else None
     ops.reset_launch_count()
     ms_step = timed(lambda i: train_step(img_dev, tgt_dev), args.steps)
     launches = ops.launch_count()

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(THREADS, 1) agg_tc_kernel(const __grid_constan
   uint8_t* sStage = sm + A_BYTES;
   Ctrl* ctl = reinterpret_cast<Ctrl*>(sStage + 2 * STAGE_BYTES);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role id
   const int mt = blockIdx.x, nchunk = blockIdx.y, b = blockIdx.z;
   const int n0 = nchunk * P.NC;
   const int slabs = P.D / 64;
@@ -92,10 +92,10 @@ __global__ void __launch_bounds__(THREADS, 1) agg_tc_kernel(const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = ctl->tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one()) {   // ONE elected thread runs the whole role loop (see tc.cuh)
       for (int s = 0; s < slabs; ++s) {
         const int st = s & 1;
         mbar_wait(&ctl->empty[st], ((s >> 1) & 1) ^ 1);
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(THREADS, 1) agg_tc_kernel(const __grid_constan
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    if (elect_one()) {   // ONE elected thread runs the whole role loop (see tc.cuh)
       const uint32_t idesc_z = make_idesc(128, 64, false, true);       // A~ K-major, token slab MN-major
       const uint32_t idesc_w = make_idesc(128, P.NH, false, false);    // Z from TMEM, W slab K-major
       const uint32_t aA = smem_u32(sA);

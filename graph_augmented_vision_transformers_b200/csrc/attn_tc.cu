@@ -65,6 +65,18 @@ __device__ __forceinline__ void store_out64(__nv_bfloat16* dst, const float (&o)
   }
 }
 
+__device__ __forceinline__ void store_out32(__nv_bfloat16* dst, const float (&o)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 w;
+    w.x = pack_bf16(o[8 * q + 0], o[8 * q + 1]);
+    w.y = pack_bf16(o[8 * q + 2], o[8 * q + 3]);
+    w.z = pack_bf16(o[8 * q + 4], o[8 * q + 5]);
+    w.w = pack_bf16(o[8 * q + 6], o[8 * q + 7]);
+    *reinterpret_cast<uint4*>(dst + 8 * q) = w;
+  }
+}
+
 // =================================================================================================
 // forward
 // =================================================================================================
@@ -85,7 +97,7 @@ __global__ void __launch_bounds__(THREADS, 2) attn_fwd_tc_kernel(const __grid_co
   uint8_t* sP = sm + 5 * TILE_BYTES;      // [128 rows][128 keys] as two 64-key blocks
   FwdCtrl* ctl = reinterpret_cast<FwdCtrl*>(sm + 7 * TILE_BYTES);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role id
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int nblk = (N + 127) / 128;
 
@@ -102,11 +114,11 @@ __global__ void __launch_bounds__(THREADS, 2) attn_fwd_tc_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = ctl->tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
   const uint32_t tS = tmem, tO = tmem + 128;
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one()) {   // ONE elected thread runs the whole role loop (see tc.cuh)
       mbar_expect_tx(&ctl->q_full, TILE_BYTES);
       tma_load_3d(sQ, &tm_qkv, h * 64, q0, b, &ctl->q_full);
       for (int j = 0; j < nblk; ++j) {
@@ -118,7 +130,7 @@ __global__ void __launch_bounds__(THREADS, 2) attn_fwd_tc_kernel(const __grid_co
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    if (elect_one()) {   // ONE elected thread runs the whole role loop (see tc.cuh)
       const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
       auto issue_s = [&](int j) {
         const int s = j & 1;
@@ -237,7 +249,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) attn_fwd_tc2_kernel(const __gri
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   F2Ctrl* ctl = reinterpret_cast<F2Ctrl*>(sm + 2 * F2_STAGE_BYTES);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role id
   const int MT = (N + 127) >> 7;                 // 128-row query tiles (1 or 2) == 128-row key/value tiles
   const int NT = (N + 15) & ~15;                 // key extent of the MMAs
 
@@ -257,10 +269,10 @@ __global__ void __launch_bounds__(F2_THREADS, 1) attn_fwd_tc2_kernel(const __gri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = ctl->tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
 
   if (warp == 8) {
-    if (lane == 0) {
+    if (elect_one()) {   // ONE elected thread runs the whole role loop (see tc.cuh)
       int it = 0;
       for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
         const int s = it & 1, b = w / H, h = w - b * H;
@@ -275,7 +287,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) attn_fwd_tc2_kernel(const __gri
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
+    if (elect_one()) {   // ONE elected thread runs the whole role loop (see tc.cuh)
       const uint32_t idesc_s = make_idesc(128, NT, false, false);
       const uint32_t idesc_o = make_idesc(128, 64, false, true);
       int it = 0;
@@ -376,188 +388,313 @@ __global__ void __launch_bounds__(F2_THREADS, 1) attn_fwd_tc2_kernel(const __gri
 }
 
 // =================================================================================================
-// backward (N <= 256)
+// backward (N <= 256): persistent, key-major, pipelined over 64-query sub-tiles.
+//
+// One CTA per SM loops over (image, head) items; all of a head's Q, K, V, dO tiles (<= 8 x 16 KB) are resident.
+// For key tile kt and query tile qt the 128 x 128 score block is processed as TWO 64-query sub-tiles g = 0,1, each
+// owned by one softmax warpgroup (warps 4g..4g+3, thread <-> key row = TMEM lane) and one 64-column TMEM sub-buffer:
+//   MMA1(g) : S^T_g = K Q_g^T,  dP^T_g = V dO_g^T                     (tcgen05.mma, M = keys, N = <=64 queries)
+//   WG g    : P^T_g = exp2(S^T_g c - lse), dS^T_g = P^T_g (dP^T_g - delta) scale  -> bf16 staging tiles in smem
+//   MMA2(g) : dV += P^T_g dO_g,  dK += dS^T_g Q_g                      (accumulate in TMEM across all query tiles)
+//   dQ[qt] += dS K  once per (kt, qt): the [keys][128 queries] staging pair is read as an MN-major A operand.
+// MMA1 of the NEXT (kt, qt) is issued into sub-buffer g as soon as WG g has drained it, so the tensor pipe, the two
+// warpgroups and the epilogue stores overlap instead of taking turns (v1 ran them strictly in sequence: 470 us).
+// TMEM: S^T [0,128) | dP^T [128,256) | dV [256,320) | dK [320,384) | dQ [384,512).
+// Warp roles: 0-3 WG0, 4-7 WG1, 8 TMA producer, 9 MMA issuer (+ TMEM allocation).
 // =================================================================================================
-struct __align__(8) BwdCtrl {
-  float lse2[256], delta[256];
-  uint64_t qdo_full, kv_full, kv_empty, s_full, p_full, mma_done;
+constexpr int B2_THREADS = 320;
+struct __align__(16) BwdCtrl {
+  float lse2[2][256], delta[2][256];            // double-buffered by item parity
+  uint64_t kv_full[2], q_full[2], in_empty, s_full[2], p_full[2], st_free, dvk_free, dq_free;
   uint32_t tmem_base;
 };
-// Q[2], dO[2], K, V tiles + P^T, dS^T (each [128][128] = 2 blocks)
-constexpr size_t BWD_SMEM = 1024 + 10 * TILE_BYTES + sizeof(BwdCtrl);
+// Q[2], dO[2], K[2], V[2] tiles + P^T staging (2 sub-tiles) + dS^T staging (2 sub-tiles)
+constexpr size_t BWD_SMEM = 1024 + 12 * TILE_BYTES + sizeof(BwdCtrl);
 
-__global__ void __launch_bounds__(THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,
-                                                                 const __grid_constant__ CUtensorMap tm_do, int N,
-                                                                 int H, float scale,
-                                                                 const __nv_bfloat16* __restrict__ out,
-                                                                 const __nv_bfloat16* __restrict__ dout,
-                                                                 const float* __restrict__ lse,
-                                                                 float* __restrict__ delta_ws,
-                                                                 __nv_bfloat16* __restrict__ dqkv) {
+// two 32-column TMEM reads of this thread's lane, one wait
+__device__ __forceinline__ void tmem_ld32x2(uint32_t ta, uint32_t tb, float (&a)[32], float (&b)[32]) {
+  uint32_t r[64];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%64];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,"
+      "%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%65];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+        "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+        "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
+        "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
+        "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(ta), "r"(tb)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[32 + i]); }
+}
+
+// width (multiple of 16) of 64-query sub-tile g of a query tile with nq (multiple of 16) padded queries; an
+// all-padding second sub-tile still runs, 16 wide, so that every (kt, qt) step has the same barrier traffic
+__device__ __forceinline__ int sub_width(int nq, int g) { return g == 0 ? min(64, nq) : max(16, nq - 64); }
+
+__global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,
+                                                                    const __grid_constant__ CUtensorMap tm_do, int N,
+                                                                    int H, int items, float scale,
+                                                                    const __nv_bfloat16* __restrict__ out,
+                                                                    const __nv_bfloat16* __restrict__ dout,
+                                                                    const float* __restrict__ lse,
+                                                                    __nv_bfloat16* __restrict__ dqkv) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = sm;                        // 2 tiles
   uint8_t* sdO = sm + 2 * TILE_BYTES;      // 2 tiles
-  uint8_t* sK = sm + 4 * TILE_BYTES;
-  uint8_t* sV = sm + 5 * TILE_BYTES;
-  uint8_t* sPT = sm + 6 * TILE_BYTES;      // [keys][q]   K-major A of dV
-  uint8_t* sdST = sm + 8 * TILE_BYTES;     // [keys][q]   K-major A of dK and MN-major A of dQ
-  BwdCtrl* ctl = reinterpret_cast<BwdCtrl*>(sm + 10 * TILE_BYTES);
+  uint8_t* sK = sm + 4 * TILE_BYTES;       // 2 tiles
+  uint8_t* sV = sm + 6 * TILE_BYTES;       // 2 tiles
+  uint8_t* sPT = sm + 8 * TILE_BYTES;      // sub-tile g at + g*TILE_BYTES: [128 keys][64 queries], K-major A of dV
+  uint8_t* sdST = sm + 10 * TILE_BYTES;    // same shape: K-major A of dK; both sub-tiles = MN-major A of dQ
+  BwdCtrl* ctl = reinterpret_cast<BwdCtrl*>(sm + 12 * TILE_BYTES);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role id
   const int T = (N + 127) / 128;           // tiles along queries == tiles along keys (1 or 2)
+  GVIT_TRACE_DECL
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     prefetch_tmap(&tm_qkv);
     prefetch_tmap(&tm_do);
-    mbar_init(&ctl->qdo_full, 1);
-    mbar_init(&ctl->kv_full, 1);
-    mbar_init(&ctl->kv_empty, 1);
-    mbar_init(&ctl->s_full, 1);
-    mbar_init(&ctl->p_full, 128);
-    mbar_init(&ctl->mma_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctl->kv_full[i], 1);
+      mbar_init(&ctl->q_full[i], 1);
+      mbar_init(&ctl->s_full[i], 1);
+      mbar_init(&ctl->p_full[i], 128);
+    }
+    mbar_init(&ctl->in_empty, 1);
+    mbar_init(&ctl->st_free, 1);
+    mbar_init(&ctl->dvk_free, 256);
+    mbar_init(&ctl->dq_free, 256);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc(&ctl->tmem_base, 512);
+  if (warp == 9) tmem_alloc(&ctl->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = ctl->tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
   const uint32_t tST = tmem, tdPT = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
 
-  if (warp == 4) {
-    if (lane == 0) {
-      mbar_expect_tx(&ctl->qdo_full, 2 * T * TILE_BYTES);
-      for (int t = 0; t < T; ++t) {
-        tma_load_3d(sQ + t * TILE_BYTES, &tm_qkv, h * 64, t * 128, b, &ctl->qdo_full);
-        tma_load_3d(sdO + t * TILE_BYTES, &tm_do, h * 64, t * 128, b, &ctl->qdo_full);
-      }
-      for (int kt = 0; kt < T; ++kt) {
-        mbar_wait(&ctl->kv_empty, (kt & 1) ^ 1);
-        mbar_expect_tx(&ctl->kv_full, 2 * TILE_BYTES);
-        tma_load_3d(sK, &tm_qkv, (H + h) * 64, kt * 128, b, &ctl->kv_full);
-        tma_load_3d(sV, &tm_qkv, (2 * H + h) * 64, kt * 128, b, &ctl->kv_full);
+  if (warp == 8) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {   // ONE elected thread runs the whole role loop (see tc.cuh)
+      int ic = 0;
+      for (int w = blockIdx.x; w < items; w += gridDim.x, ++ic) {
+        const int b = w / H, h = w - b * H;
+        if (ic > 0) mbar_wait(&ctl->in_empty, (ic - 1) & 1);   // every MMA of the previous item has retired
+        GVIT_TR(1);
+        for (int t = 0; t < T; ++t) {
+          mbar_expect_tx(&ctl->kv_full[t], 2 * TILE_BYTES);
+          mbar_expect_tx(&ctl->q_full[t], 2 * TILE_BYTES);
+        }
+        tma_load_3d(sK, &tm_qkv, (H + h) * 64, 0, b, &ctl->kv_full[0]);
+        tma_load_3d(sV, &tm_qkv, (2 * H + h) * 64, 0, b, &ctl->kv_full[0]);
+        for (int t = 0; t < T; ++t) {
+          tma_load_3d(sQ + t * TILE_BYTES, &tm_qkv, h * 64, t * 128, b, &ctl->q_full[t]);
+          tma_load_3d(sdO + t * TILE_BYTES, &tm_do, h * 64, t * 128, b, &ctl->q_full[t]);
+        }
+        if (T > 1) {
+          tma_load_3d(sK + TILE_BYTES, &tm_qkv, (H + h) * 64, 128, b, &ctl->kv_full[1]);
+          tma_load_3d(sV + TILE_BYTES, &tm_qkv, (2 * H + h) * 64, 128, b, &ctl->kv_full[1]);
+        }
       }
     }
-  } else if (warp == 5) {
-    if (lane == 0) {
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {   // ONE elected thread runs the whole role loop (see tc.cuh)
       const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV);
       const uint32_t aPT = smem_u32(sPT), adST = smem_u32(sdST);
-      mbar_wait(&ctl->qdo_full, 0);
-      int it = 0;
-      for (int kt = 0; kt < T; ++kt) {
-        const int nk = (min(128, N - kt * 128) + 15) & ~15;
-        mbar_wait(&ctl->kv_full, kt & 1);
-        for (int qt = 0; qt < T; ++qt, ++it) {
-          const int nq = (min(128, N - qt * 128) + 15) & ~15;
-          tc_fence_after();
-          // S^T = K Q^T, dP^T = V dO^T   (M = keys, N = queries, K = head dim)
-          const uint32_t idesc_s = make_idesc(128, nq, false, false);
+      const uint32_t idesc_mn = make_idesc(128, 64, false, true);    // A K-major (staging), B MN-major (dO / Q rows)
+      const uint32_t idesc_tt = make_idesc(128, 64, true, true);     // A MN-major (dS), B MN-major (K rows)
+      int ic = 0, itc = 0, kc = 0;                                   // items, (kt,qt) steps, key tiles done so far
+      // S^T_g = K_kt Q_{qt,g}^T and dP^T_g = V_kt dO_{qt,g}^T into TMEM sub-buffer g
+      auto issue_mma1 = [&](int kt, int qt, int g) {
+        const int nq = (min(128, N - qt * 128) + 15) & ~15;
+        const uint32_t idesc = make_idesc(128, sub_width(nq, g), false, false);
+        const uint32_t boff = qt * TILE_BYTES + g * 8192;            // query rows [64g, 64g+64) of the tile
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_ss(tST, make_sdesc(aK + kk * 32), make_sdesc(aQ + qt * TILE_BYTES + kk * 32), idesc_s, kk > 0);
+        for (int kk = 0; kk < 4; ++kk)
+          umma_ss(tST + g * 64, make_sdesc(aK + kt * TILE_BYTES + kk * 32), make_sdesc(aQ + boff + kk * 32), idesc, kk > 0);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_ss(tdPT, make_sdesc(aV + kk * 32), make_sdesc(adO + qt * TILE_BYTES + kk * 32), idesc_s, kk > 0);
-          umma_commit(&ctl->s_full);
-          mbar_wait(&ctl->p_full, it & 1);   // P^T, dS^T, dS staged in smem
-          tc_fence_after();
-          const uint32_t idesc_mn = make_idesc(128, 64, false, true);
-          for (int ks = 0; ks < nq / 16; ++ks) {   // K = queries of this tile
-            const uint32_t aoff = (ks >> 2) * TILE_BYTES + (ks & 3) * 32, boff = qt * TILE_BYTES + ks * 2048;
-            umma_ss(tdV, make_sdesc(aPT + aoff), make_sdesc(adO + boff), idesc_mn, qt > 0 || ks > 0);
-            umma_ss(tdK, make_sdesc(adST + aoff), make_sdesc(aQ + boff), idesc_mn, qt > 0 || ks > 0);
+        for (int kk = 0; kk < 4; ++kk)
+          umma_ss(tdPT + g * 64, make_sdesc(aV + kt * TILE_BYTES + kk * 32), make_sdesc(adO + boff + kk * 32), idesc, kk > 0);
+        umma_commit(&ctl->s_full[g]);
+      };
+      for (int w = blockIdx.x; w < items; w += gridDim.x, ++ic) {
+        const int par = ic & 1;
+        mbar_wait(&ctl->kv_full[0], par);
+        mbar_wait(&ctl->q_full[0], par);
+        tc_fence_after();
+        GVIT_TR(2);
+        // the TMEM sub-buffers were drained when p_full of the previous step completed (waited below)
+        issue_mma1(0, 0, 0);
+        issue_mma1(0, 0, 1);
+        for (int kt = 0; kt < T; ++kt) {
+          const int nk = (min(128, N - kt * 128) + 15) & ~15;
+          for (int qt = 0; qt < T; ++qt, ++itc) {
+            const int nq = (min(128, N - qt * 128) + 15) & ~15;
+            const bool last = (kt == T - 1 && qt == T - 1);
+            const int nkt = (qt == T - 1) ? kt + 1 : kt, nqt = (qt == T - 1) ? 0 : qt + 1;
+            for (int g = 0; g < 2; ++g) {
+              mbar_wait(&ctl->p_full[g], itc & 1);       // staging g written, TMEM sub-buffer g drained
+              tc_fence_after();
+              GVIT_TR(3 + g);
+              if (!last) {
+                if (g == 0) {
+                  if (nqt == 0) mbar_wait(&ctl->kv_full[nkt], par);   // first use of the next key tile
+                  else if (kt == 0) mbar_wait(&ctl->q_full[nqt], par); // first use of the next query tile
+                  tc_fence_after();
+                }
+                issue_mma1(nkt, nqt, g);                  // next scores overlap this step's dV / dK / dQ
+              }
+              if (g == 0 && qt == 0 && kc > 0) {          // dV / dK are about to be overwritten: epilogue has read them
+                mbar_wait(&ctl->dvk_free, (kc - 1) & 1);
+                tc_fence_after();
+              }
+              const int wg = sub_width(nq, g);
+              for (int ks = 0; ks < wg / 16; ++ks) {      // K = queries of the sub-tile
+                const uint32_t aoff = g * TILE_BYTES + ks * 32, boff = qt * TILE_BYTES + g * 8192 + ks * 2048;
+                const bool acc = qt > 0 || g > 0 || ks > 0;
+                umma_ss(tdV, make_sdesc(aPT + aoff), make_sdesc(adO + boff), idesc_mn, acc);
+                umma_ss(tdK, make_sdesc(adST + aoff), make_sdesc(aQ + boff), idesc_mn, acc);
+              }
+            }
+            if (kt == 0 && qt == 0 && ic > 0) {           // dQ is about to be overwritten: previous item stored it
+              mbar_wait(&ctl->dq_free, (ic - 1) & 1);
+              tc_fence_after();
+            }
+            for (int ks = 0; ks < nk / 16; ++ks)          // dQ[qt] += dS K_kt, K = keys of this tile
+              umma_ss(tdQ + qt * 64, make_sdesc_lbo(adST + ks * 2048, TILE_BYTES), make_sdesc(aK + kt * TILE_BYTES + ks * 2048),
+                      idesc_tt, kt > 0 || ks > 0);
+            umma_commit(&ctl->st_free);                   // staging consumed; accumulators of this step final
+            GVIT_TR(5);
+            if (qt == T - 1) ++kc;
           }
-          // dQ += dS K with dS = (dS^T)^T: the [keys][queries] tile is read as an MN-major A operand (M = queries
-          // contiguous, two 64-query atoms LBO = one tile apart), so dS is never transposed through shared memory
-          const uint32_t idesc_tt = make_idesc(128, 64, true, true);
-          for (int ks = 0; ks < nk / 16; ++ks)     // K = keys of this tile
-            umma_ss(tdQ + qt * 64, make_sdesc_lbo(adST + ks * 2048, TILE_BYTES), make_sdesc(aK + ks * 2048), idesc_tt,
-                    kt > 0 || ks > 0);
-          umma_commit(&ctl->mma_done);
-          if (qt == T - 1) umma_commit(&ctl->kv_empty);
         }
+        umma_commit(&ctl->in_empty);                      // Q / dO / K / V tiles may be refilled
       }
     }
   } else {
-    const int t = warp * 32 + lane;              // key row of the tile (S^T lanes) / query row (dQ lanes)
+    // ------------------------------------------------------------------ softmax / epilogue warpgroups
+    const int g = warp >> 2;                              // warpgroup == sub-tile == TMEM sub-buffer
+    const int t = (warp & 3) * 32 + lane;                 // key row of the tile == TMEM lane
+    const int tid = g * 128 + t;                          // 0..255
     const float sl2 = scale * LOG2E;
-    // prologue: delta = rowsum(dO * O), lse in log2 units
-    for (int q = t; q < 256; q += 128) {
-      float d = 0.f, l2 = 0.f;
-      if (q < N) {
-        const __nv_bfloat16* orow = out + (((int64_t)b * N + q) * H + h) * 64;
-        const __nv_bfloat16* drow = dout + (((int64_t)b * N + q) * H + h) * 64;
+    const uint32_t lST = tmem_lane_base(tST + g * 64, warp), ldPT = tmem_lane_base(tdPT + g * 64, warp);
+    uint8_t* pt_g = sPT + g * TILE_BYTES;
+    uint8_t* dst_g = sdST + g * TILE_BYTES;
+    int ic = 0, itc = 0;
+    for (int w = blockIdx.x; w < items; w += gridDim.x, ++ic) {
+      const int b = w / H, h = w - b * H;
+      const int par = ic & 1;
+      {  // delta = rowsum(dO * O) and lse in log2 units for query row `tid`
+        float d = 0.f, l2 = 0.f;
+        if (tid < N) {
+          const __nv_bfloat16* orow = out + (((int64_t)b * N + tid) * H + h) * 64;
+          const __nv_bfloat16* drow = dout + (((int64_t)b * N + tid) * H + h) * 64;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float a[8], g[8];
-          load8(orow + 8 * c, a);
-          load8(drow + 8 * c, g);
+          for (int c = 0; c < 8; ++c) {
+            float a[8], gg[8];
+            load8(orow + 8 * c, a);
+            load8(drow + 8 * c, gg);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) d = fmaf(a[e], g[e], d);
-        }
-        l2 = lse[((int64_t)b * H + h) * N + q] * LOG2E;
-        delta_ws[((int64_t)b * H + h) * N + q] = d;
-      }
-      ctl->delta[q] = d;
-      ctl->lse2[q] = l2;
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    const uint32_t lST = tmem_lane_base(tST, warp), ldPT = tmem_lane_base(tdPT, warp);
-    int it = 0;
-    for (int kt = 0; kt < T; ++kt) {
-      const int key = kt * 128 + t;
-      const bool kvalid = key < N;
-      for (int qt = 0; qt < T; ++qt, ++it) {
-        const int nq = (min(128, N - qt * 128) + 15) & ~15;
-        mbar_wait(&ctl->s_full, it & 1);
-        tc_fence_after();
-        for (int c0 = 0; c0 < nq; c0 += 32) {
-          float s[32], dp[32];
-          tmem_ld32(lST + c0, s);
-          tmem_ld32(ldPT + c0, dp);
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int q = qt * 128 + c0 + e;
-            const float p = (kvalid && q < N) ? ex2(fmaf(s[e], sl2, -ctl->lse2[q])) : 0.f;
-            s[e] = p;
-            dp[e] = p * (dp[e] - ctl->delta[q]) * scale;
+            for (int e = 0; e < 8; ++e) d = fmaf(a[e], gg[e], d);
           }
-          store_row32(sPT, t, c0, s);
-          store_row32(sdST, t, c0, dp);
+          l2 = lse[((int64_t)b * H + h) * N + tid] * LOG2E;
         }
-        fence_async_smem();
-        tc_fence_before();
-        mbar_arrive(&ctl->p_full);
-        mbar_wait(&ctl->mma_done, it & 1);       // P^T/dS^T/dS consumed; dV, dK, dQ updated
-        tc_fence_after();
-        if (qt == T - 1) {
-          float v[64];
-          tmem_ld32(tmem_lane_base(tdV, warp), *reinterpret_cast<float(*)[32]>(&v[0]));
-          tmem_ld32(tmem_lane_base(tdV, warp) + 32, *reinterpret_cast<float(*)[32]>(&v[32]));
-          if (kvalid) store_out64(dqkv + ((((int64_t)b * N + key) * 3 + 2) * H + h) * 64, v, 1.0f);
-          tmem_ld32(tmem_lane_base(tdK, warp), *reinterpret_cast<float(*)[32]>(&v[0]));
-          tmem_ld32(tmem_lane_base(tdK, warp) + 32, *reinterpret_cast<float(*)[32]>(&v[32]));
-          if (kvalid) store_out64(dqkv + ((((int64_t)b * N + key) * 3 + 1) * H + h) * 64, v, 1.0f);
-          tc_fence_before();                      // order these reads before the next tile's MMAs (via p_full)
+        ctl->delta[par][tid] = d;
+        ctl->lse2[par][tid] = l2;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      GVIT_TR(10);
+      for (int kt = 0; kt < T; ++kt) {
+        const int key = kt * 128 + t;
+        const bool kvalid = key < N;
+        for (int qt = 0; qt < T; ++qt, ++itc) {
+          const int nq = (min(128, N - qt * 128) + 15) & ~15;
+          const int wg = sub_width(nq, g);
+          const int q0 = qt * 128 + g * 64;
+          mbar_wait(&ctl->s_full[g], itc & 1);
+          tc_fence_after();
+          GVIT_TR(11);
+          for (int c0 = 0; c0 < wg; c0 += 32) {
+            float s[32], dp[32];
+            tmem_ld32x2(lST + c0, ldPT + c0, s, dp);
+            GVIT_TR(12);
+#pragma unroll
+            for (int e4 = 0; e4 < 32; e4 += 4) {
+              const float4 l4 = *reinterpret_cast<const float4*>(&ctl->lse2[par][q0 + c0 + e4]);
+              const float4 d4 = *reinterpret_cast<const float4*>(&ctl->delta[par][q0 + c0 + e4]);
+              const float ll[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int e = e4 + u;
+                const float p = (kvalid && q0 + c0 + e < N) ? ex2(fmaf(s[e], sl2, -ll[u])) : 0.f;
+                s[e] = p;
+                dp[e] = p * (dp[e] - dd[u]) * scale;
+              }
+            }
+            GVIT_TR(13);
+            if (c0 == 0 && itc > 0) mbar_wait(&ctl->st_free, (itc - 1) & 1);   // staging of the previous step consumed
+            GVIT_TR(14);
+            store_row32(pt_g, t, c0, s);
+            store_row32(dst_g, t, c0, dp);
+          }
+          fence_async_smem();
+          tc_fence_before();
+          mbar_arrive(&ctl->p_full[g]);
+          GVIT_TR(15);
+          if (qt == T - 1) {                              // key tile finished: dV (WG0) / dK (WG1) -> HBM
+            mbar_wait(&ctl->st_free, itc & 1);
+            tc_fence_after();
+            GVIT_TR(16);
+            float v0[32], v1[32];
+            const uint32_t ta = tmem_lane_base(g == 0 ? tdV : tdK, warp);
+            tmem_ld32x2(ta, ta + 32, v0, v1);
+            tc_fence_before();
+            mbar_arrive(&ctl->dvk_free);
+            if (kvalid) {
+              __nv_bfloat16* dst = dqkv + ((((int64_t)b * N + key) * 3 + (g == 0 ? 2 : 1)) * H + h) * 64;
+              store_out32(dst, v0);
+              store_out32(dst + 32, v1);
+            }
+          }
         }
       }
-    }
-    for (int qt = 0; qt < T; ++qt) {
-      float v[64];
-      tmem_ld32(tmem_lane_base(tdQ, warp) + qt * 64, *reinterpret_cast<float(*)[32]>(&v[0]));
-      tmem_ld32(tmem_lane_base(tdQ, warp) + qt * 64 + 32, *reinterpret_cast<float(*)[32]>(&v[32]));
-      const int q = qt * 128 + t;
-      if (q < N) store_out64(dqkv + ((((int64_t)b * N + q) * 3 + 0) * H + h) * 64, v, 1.0f);
+      {  // dQ: warpgroup g stores query tile g (every thread arrives so that the barrier count is fixed)
+        float v0[32], v1[32];
+        const int q = g * 128 + t;
+        if (g < T) {
+          const uint32_t ta = tmem_lane_base(tdQ + g * 64, warp);
+          tmem_ld32x2(ta, ta + 32, v0, v1);
+        }
+        tc_fence_before();
+        mbar_arrive(&ctl->dq_free);
+        GVIT_TR(17);
+        if (g < T && q < N) {
+          __nv_bfloat16* dst = dqkv + ((((int64_t)b * N + q) * 3 + 0) * H + h) * 64;
+          store_out32(dst, v0);
+          store_out32(dst + 32, v1);
+        }
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, 512);
+  if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace
+
+GVIT_TRACE_SETTER(gvit_debug_set_trace_attn)
 
 bool attn_fwd_tc_supported(int N, int dh) { return dh == 64 && N >= 1; }
 bool attn_bwd_tc_supported(int N, int dh) { return dh == 64 && N >= 1 && N <= 256; }
@@ -592,10 +729,13 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
   rc = make_tmap_bf16_3d(&tm_do, dout, (uint64_t)H * 64, N, B, (uint64_t)H * 64, (uint64_t)N * H * 64, 128);
   if (rc != GVIT_OK) return rc;
   GVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
-  dim3 grid(H, B);
-  attn_bwd_tc_kernel<<<grid, THREADS, BWD_SMEM, st>>>(tm_qkv, tm_do, N, H, scale, static_cast<const __nv_bfloat16*>(out),
-                                                      static_cast<const __nv_bfloat16*>(dout), lse, delta_ws,
-                                                      static_cast<__nv_bfloat16*>(dqkv));
+  const int items = B * H;
+  const int grid = items < num_sms() ? items : num_sms();
+  (void)delta_ws;                                            // only the fp32-FMA path needs the global delta workspace
+  attn_bwd_tc_kernel<<<grid, B2_THREADS, BWD_SMEM, st>>>(tm_qkv, tm_do, N, H, items, scale,
+                                                         static_cast<const __nv_bfloat16*>(out),
+                                                         static_cast<const __nv_bfloat16*>(dout), lse,
+                                                         static_cast<__nv_bfloat16*>(dqkv));
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }

@@ -207,10 +207,34 @@ __global__ void __launch_bounds__(256) dropout_bwd_kernel(const Tx* __restrict__
 }
 
 // ---- GELU (exact erf form, nn.GELU at vit.py:84) fused with the dropout that follows it (vit.py:92) --------
-__device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_grad_f(float u) {
-  return 0.5f * (1.0f + erff(u * 0.70710678118654752f)) + u * 0.3989422804014327f * __expf(-0.5f * u * u);
-}
+// Exact form (erff) for fp32 storage - the parity path.  For bf16 storage (8-bit mantissa) the normal CDF comes from
+// Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, one MUFU.EX2 + one MUFU.RCP + 7 FMA, branch-free): erff's two-branch
+// polynomial made these kernels ALU-bound at 2.7x their HBM time.  The exp(-u^2/2) factor is shared with GELU'.
+template <bool EXACT> struct Gelu;
+template <> struct Gelu<true> {
+  static __device__ __forceinline__ float fwd(float u) { return 0.5f * u * (1.0f + erff(u * 0.70710678118654752f)); }
+  static __device__ __forceinline__ float grad(float u) {
+    return 0.5f * (1.0f + erff(u * 0.70710678118654752f)) + u * 0.3989422804014327f * __expf(-0.5f * u * u);
+  }
+};
+template <> struct Gelu<false> {
+  // returns Phi(u) and e = exp(-u^2/2)
+  static __device__ __forceinline__ float cdf(float u, float& e) {
+    const float ax = fabsf(u) * 0.70710678118654752f;
+    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    e = __expf(-0.5f * u * u);
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float half_q = 0.5f * poly * t * e;          // 0.5 * erfc(|u|/sqrt2)
+    return u >= 0.f ? 1.0f - half_q : half_q;
+  }
+  static __device__ __forceinline__ float fwd(float u) { float e; return u * cdf(u, e); }
+  static __device__ __forceinline__ float grad(float u) { float e; const float c = cdf(u, e); return fmaf(u * 0.3989422804014327f, e, c); }
+};
+template <typename T> struct GeluFor { using type = Gelu<true>; };
+template <> struct GeluFor<__nv_bfloat16> { using type = Gelu<false>; };
 
 template <typename T>
 __global__ void __launch_bounds__(256) gelu_dropout_fwd_kernel(const T* __restrict__ u, int64_t n, float p, uint64_t seed,
@@ -222,7 +246,7 @@ __global__ void __launch_bounds__(256) gelu_dropout_fwd_kernel(const T* __restri
     float a[8];
     load8(u + i8, a);
 #pragma unroll
-    for (int t = 0; t < 8; ++t) a[t] = gelu_f(a[t]);
+    for (int t = 0; t < 8; ++t) a[t] = GeluFor<T>::type::fwd(a[t]);
     if (p > 0.f) {
       const uint32_t bits = keep_bits8(seed, offset + (uint64_t)(i8 >> 3), th);
 #pragma unroll
@@ -245,7 +269,7 @@ __global__ void __launch_bounds__(256) gelu_dropout_bwd_kernel(const T* __restri
     load8(u + i8, a);
     const uint32_t bits = p > 0.f ? mask[i8 >> 3] : 0xffu;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) g[t] = (bits >> t) & 1u ? g[t] * scale * gelu_grad_f(a[t]) : 0.f;
+    for (int t = 0; t < 8; ++t) g[t] = (bits >> t) & 1u ? g[t] * scale * GeluFor<T>::type::grad(a[t]) : 0.f;
     store8(du + i8, g);
   }
 }

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(THREADS, 1) knn_tc_kernel(const __grid_constan
   uint8_t* stages = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Ctrl* ctl = reinterpret_cast<Ctrl*>(stages + (size_t)STAGES * STAGE_BYTES);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role id
   const int b = blockIdx.x;
   const int slabs = D / 64;
   const int mtiles = Np > 128 ? 2 : 1;
@@ -56,10 +56,10 @@ __global__ void __launch_bounds__(THREADS, 1) knn_tc_kernel(const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = ctl->tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
 
   if (warp == 8) {
-    if (lane == 0) {
+    if (elect_one()) {   // ONE elected thread runs the whole role loop (see tc.cuh)
       for (int it = 0; it < slabs; ++it) {
         const int s = it % STAGES;
         mbar_wait(&ctl->empty[s], ((it / STAGES) & 1) ^ 1);
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(THREADS, 1) knn_tc_kernel(const __grid_constan
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
+    if (elect_one()) {   // ONE elected thread runs the whole role loop (see tc.cuh)
       const uint32_t idesc = make_idesc(128, NT, false, false);
       for (int it = 0; it < slabs; ++it) {
         const int s = it % STAGES;

@@ -33,8 +33,18 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// NOTE on single-thread roles (TMA producer, MMA issuer): enter them with
+//     const int warp = __shfl_sync(~0u, threadIdx.x >> 5, 0);  if (warp == ROLE) { if (elect_one()) { ...loop... } }
+// i.e. a warp-uniform role test followed by ONE elect.sync around the whole loop.  Measured on B200 (tools/mma_bench.cu):
+// a tight single-thread issue loop costs N/2+10 cycles per tcgen05.mma with A in TMEM and N/2+41 with A in shared
+// memory; an `if (lane == 0)` role made the compiler wrap every UTCHMMA in an ELECT/R2UR.BROADCAST/BRA.U.ANY waterfall
+// (~125 cycles per MMA), and an elect per MMA still costs ~96.
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// single arrival issued by one elected lane of a converged warp
+__device__ __forceinline__ void mbar_arrive_elect(uint64_t* bar) {
+  if (elect_one()) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -185,6 +195,39 @@ __device__ __forceinline__ uint64_t make_sdesc_lbo(uint32_t smem_addr, uint32_t 
 __device__ __forceinline__ uint32_t swz128(int row, int col) {
   return static_cast<uint32_t>(row) * 128u + ((((static_cast<uint32_t>(col) >> 3) ^ (static_cast<uint32_t>(row) & 7u)) << 4));
 }
+
+// ---- optional event trace (builds with -DGVIT_TRACE only; see tools/trace_kernel.py) ----
+// CTA 0 records (warp, event id, clock64) tuples into a global buffer set by gvit_debug_set_trace(); used to see
+// where the warp-specialised pipelines wait.  Compiled out of the product library.
+#ifdef GVIT_TRACE
+static __device__ unsigned long long* g_trace_buf = nullptr;
+static __device__ unsigned int g_trace_cap = 0;      // entries per warp region (16 regions)
+// no atomics: every traced warp owns a region of the buffer and a cursor in a register, so an event costs one
+// CS2R + one fire-and-forget store
+__device__ __forceinline__ void trace_event(int id, unsigned int& cursor) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0 && g_trace_buf != nullptr &&
+      cursor < g_trace_cap) {
+    const unsigned int warp = threadIdx.x >> 5;
+    g_trace_buf[(warp & 15) * g_trace_cap + cursor] =
+        (static_cast<unsigned long long>((warp << 8) | (id & 0xff)) << 44) |
+        (static_cast<unsigned long long>(clock64()) & 0xFFFFFFFFFFFULL);
+    ++cursor;
+  }
+}
+#define GVIT_TRACE_DECL unsigned int gvit_trc = 0;
+#define GVIT_TR(id) ::gvit::tc::trace_event(id, gvit_trc)
+#define GVIT_TRACE_SETTER(NAME)                                                                   \
+  extern "C" GVIT_API int NAME(void* buf, unsigned int cap) {                                      \
+    unsigned long long* b = static_cast<unsigned long long*>(buf);                                 \
+    if (cudaMemcpyToSymbol(::gvit::tc::g_trace_buf, &b, sizeof(b)) != cudaSuccess) return 4;       \
+    if (cudaMemcpyToSymbol(::gvit::tc::g_trace_cap, &cap, sizeof(cap)) != cudaSuccess) return 4;   \
+    return 0;                                                                                      \
+  }
+#else
+#define GVIT_TR(id) ((void)0)
+#define GVIT_TRACE_DECL
+#define GVIT_TRACE_SETTER(NAME)
+#endif
 
 }  // namespace tc
 

@@ -47,7 +47,8 @@ def test_fp32_core_vs_oracle(B, N, H, dh):
 
 
 @pytest.mark.parametrize("B,N,H", [(2, 197, 12), (1, 577, 16), (1, 1, 2), (3, 128, 2), (2, 129, 3), (2, 16, 1), (1, 256, 4),
-                                   (1, 257, 2)])
+                                   (1, 257, 2), (31, 197, 12), (40, 65, 8), (27, 150, 6)])   # last three: > 148 (image, head)
+                                                                                             # items -> persistent CTAs loop
 def test_bf16_core_vs_oracle(B, N, H):
     assert _lib.describe_path("attn_fwd", _lib.GVIT_BF16, N, 64) == "attn_fwd:tcgen05+tma"
     out, dqkv, want, dwant = _core_case(B, N, H, 64, torch.bfloat16, seed=N)
