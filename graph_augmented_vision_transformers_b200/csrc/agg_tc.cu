@@ -64,8 +64,9 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 template <int KT>
 __global__ void __launch_bounds__(THREADS, 1) agg_tc_kernel(const __grid_constant__ CUtensorMap tm_tok,
                                                             const __grid_constant__ CUtensorMap tm_w, const Params P) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // no static __shared__ in these kernels: base is 1024-aligned
+  uint8_t* sm = smem_raw;   // NOT rounded through an integer: that made every access a generic LD/ST instead of LDS/STS
+  if ((smem_u32(sm) & 1023u) != 0) __trap();
   uint8_t* sA = sm;
   uint8_t* sStage = sm + A_BYTES;
   Ctrl* ctl = reinterpret_cast<Ctrl*>(sStage + 2 * STAGE_BYTES);

@@ -65,15 +65,33 @@ __device__ __forceinline__ void store_out64(__nv_bfloat16* dst, const float (&o)
   }
 }
 
-__device__ __forceinline__ void store_out32(__nv_bfloat16* dst, const float (&o)[32]) {
+__device__ __forceinline__ void store_out32(__nv_bfloat16* dst, const float (&o)[32], float mul) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     uint4 w;
-    w.x = pack_bf16(o[8 * q + 0], o[8 * q + 1]);
-    w.y = pack_bf16(o[8 * q + 2], o[8 * q + 3]);
-    w.z = pack_bf16(o[8 * q + 4], o[8 * q + 5]);
-    w.w = pack_bf16(o[8 * q + 6], o[8 * q + 7]);
+    w.x = pack_bf16(o[8 * q + 0] * mul, o[8 * q + 1] * mul);
+    w.y = pack_bf16(o[8 * q + 2] * mul, o[8 * q + 3] * mul);
+    w.z = pack_bf16(o[8 * q + 4] * mul, o[8 * q + 5] * mul);
+    w.w = pack_bf16(o[8 * q + 6] * mul, o[8 * q + 7] * mul);
     *reinterpret_cast<uint4*>(dst + 8 * q) = w;
+  }
+}
+
+// 64 fp32 -> bf16 into row `row` of a swizzled [128][64] staging tile (the layout a SWIZZLE_128B TMA store reads)
+__device__ __forceinline__ void stage_out64(uint8_t* tile, int row, const float (&a)[32], const float (&b)[32], float mul) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 w;
+    w.x = pack_bf16(a[8 * q + 0] * mul, a[8 * q + 1] * mul);
+    w.y = pack_bf16(a[8 * q + 2] * mul, a[8 * q + 3] * mul);
+    w.z = pack_bf16(a[8 * q + 4] * mul, a[8 * q + 5] * mul);
+    w.w = pack_bf16(a[8 * q + 6] * mul, a[8 * q + 7] * mul);
+    *reinterpret_cast<uint4*>(tile + swz128(row, 8 * q)) = w;
+    w.x = pack_bf16(b[8 * q + 0] * mul, b[8 * q + 1] * mul);
+    w.y = pack_bf16(b[8 * q + 2] * mul, b[8 * q + 3] * mul);
+    w.z = pack_bf16(b[8 * q + 4] * mul, b[8 * q + 5] * mul);
+    w.w = pack_bf16(b[8 * q + 6] * mul, b[8 * q + 7] * mul);
+    *reinterpret_cast<uint4*>(tile + swz128(row, 32 + 8 * q)) = w;
   }
 }
 
@@ -89,8 +107,9 @@ constexpr size_t FWD_SMEM = 1024 + 7 * TILE_BYTES + sizeof(FwdCtrl);   // Q, K x
 __global__ void __launch_bounds__(THREADS, 2) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int N,
                                                                  int H, float scale, __nv_bfloat16* __restrict__ out,
                                                                  float* __restrict__ lse) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // no static __shared__ in these kernels: base is 1024-aligned
+  uint8_t* sm = smem_raw;   // NOT rounded through an integer: that made every access a generic LD/ST instead of LDS/STS
+  if ((smem_u32(sm) & 1023u) != 0) __trap();
   uint8_t* sQ = sm;
   uint8_t* sK = sm + TILE_BYTES;          // 2 stages
   uint8_t* sV = sm + 3 * TILE_BYTES;      // 2 stages
@@ -245,8 +264,9 @@ __global__ void __launch_bounds__(F2_THREADS, 1) attn_fwd_tc2_kernel(const __gri
                                                                      const __grid_constant__ CUtensorMap tm_out, int N,
                                                                      int H, int items, float scale,
                                                                      float* __restrict__ lse) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // no static __shared__ in these kernels: base is 1024-aligned
+  uint8_t* sm = smem_raw;   // NOT rounded through an integer: that made every access a generic LD/ST instead of LDS/STS
+  if ((smem_u32(sm) & 1023u) != 0) __trap();
   F2Ctrl* ctl = reinterpret_cast<F2Ctrl*>(sm + 2 * F2_STAGE_BYTES);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role id
@@ -436,19 +456,76 @@ __device__ __forceinline__ void tmem_ld32x2(uint32_t ta, uint32_t tb, float (&a)
   for (int i = 0; i < 32; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[32 + i]); }
 }
 
+__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&a)[16], float (&b)[16]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(ta), "r"(tb)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[16 + i]); }
+}
+
+// P^T = exp2(S^T c - lse), dS^T = P^T (dP^T - delta) for W (16 or 32) consecutive queries of this thread's key row,
+// written as bf16 into the two staging tiles.  No masks: lse2 is +inf for padded queries (p = 0 exactly), and padded
+// KEY rows only feed accumulator rows that are never stored (dV, dK) or multiply zero-filled K rows (dQ).  The
+// softmax scale is applied to dK / dQ when they are stored.
+template <int W>
+__device__ __forceinline__ void bwd_chunk(float (&s)[W], float (&dp)[W], const float* lse2, const float* delta,
+                                          float sl2, uint8_t* pt_tile, uint8_t* dst_tile, int row, int c0) {
+  // written in phases over the whole chunk (all exponent arguments, then all MUFU.EX2, then dS) so that W
+  // independent transcendental ops are in flight: with two warps per scheduler the loop is latency-, not rate-bound
+#pragma unroll
+  for (int q4 = 0; q4 < W; q4 += 4) {
+    const float4 l = *reinterpret_cast<const float4*>(lse2 + q4);
+    s[q4 + 0] = fmaf(s[q4 + 0], sl2, -l.x);
+    s[q4 + 1] = fmaf(s[q4 + 1], sl2, -l.y);
+    s[q4 + 2] = fmaf(s[q4 + 2], sl2, -l.z);
+    s[q4 + 3] = fmaf(s[q4 + 3], sl2, -l.w);
+  }
+#pragma unroll
+  for (int e = 0; e < W; ++e) s[e] = ex2(s[e]);
+#pragma unroll
+  for (int q4 = 0; q4 < W; q4 += 4) {
+    const float4 d = *reinterpret_cast<const float4*>(delta + q4);
+    dp[q4 + 0] = s[q4 + 0] * (dp[q4 + 0] - d.x);
+    dp[q4 + 1] = s[q4 + 1] * (dp[q4 + 1] - d.y);
+    dp[q4 + 2] = s[q4 + 2] * (dp[q4 + 2] - d.z);
+    dp[q4 + 3] = s[q4 + 3] * (dp[q4 + 3] - d.w);
+  }
+#pragma unroll
+  for (int q8 = 0; q8 < W; q8 += 8) {
+    uint4 wp, wd;
+    wp.x = pack_bf16(s[q8 + 0], s[q8 + 1]); wp.y = pack_bf16(s[q8 + 2], s[q8 + 3]);
+    wp.z = pack_bf16(s[q8 + 4], s[q8 + 5]); wp.w = pack_bf16(s[q8 + 6], s[q8 + 7]);
+    wd.x = pack_bf16(dp[q8 + 0], dp[q8 + 1]); wd.y = pack_bf16(dp[q8 + 2], dp[q8 + 3]);
+    wd.z = pack_bf16(dp[q8 + 4], dp[q8 + 5]); wd.w = pack_bf16(dp[q8 + 6], dp[q8 + 7]);
+    const uint32_t off = swz128(row, c0 + q8);
+    *reinterpret_cast<uint4*>(pt_tile + off) = wp;
+    *reinterpret_cast<uint4*>(dst_tile + off) = wd;
+  }
+}
+
 // width (multiple of 16) of 64-query sub-tile g of a query tile with nq (multiple of 16) padded queries; an
 // all-padding second sub-tile still runs, 16 wide, so that every (kt, qt) step has the same barrier traffic
 __device__ __forceinline__ int sub_width(int nq, int g) { return g == 0 ? min(64, nq) : max(16, nq - 64); }
 
 __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,
-                                                                    const __grid_constant__ CUtensorMap tm_do, int N,
+                                                                    const __grid_constant__ CUtensorMap tm_do,
+                                                                    const __grid_constant__ CUtensorMap tm_dqkv, int N,
                                                                     int H, int items, float scale,
                                                                     const __nv_bfloat16* __restrict__ out,
                                                                     const __nv_bfloat16* __restrict__ dout,
-                                                                    const float* __restrict__ lse,
-                                                                    __nv_bfloat16* __restrict__ dqkv) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+                                                                    const float* __restrict__ lse) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // no static __shared__ in these kernels: base is 1024-aligned
+  uint8_t* sm = smem_raw;   // NOT rounded through an integer: that made every access a generic LD/ST instead of LDS/STS
+  if ((smem_u32(sm) & 1023u) != 0) __trap();
   uint8_t* sQ = sm;                        // 2 tiles
   uint8_t* sdO = sm + 2 * TILE_BYTES;      // 2 tiles
   uint8_t* sK = sm + 4 * TILE_BYTES;       // 2 tiles
@@ -464,6 +541,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tm_qkv);
     prefetch_tmap(&tm_do);
+    prefetch_tmap(&tm_dqkv);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl->kv_full[i], 1);
       mbar_init(&ctl->q_full[i], 1);
@@ -595,23 +673,43 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
     for (int w = blockIdx.x; w < items; w += gridDim.x, ++ic) {
       const int b = w / H, h = w - b * H;
       const int par = ic & 1;
-      {  // delta = rowsum(dO * O) and lse in log2 units for query row `tid`
-        float d = 0.f, l2 = 0.f;
-        if (tid < N) {
-          const __nv_bfloat16* orow = out + (((int64_t)b * N + tid) * H + h) * 64;
-          const __nv_bfloat16* drow = dout + (((int64_t)b * N + tid) * H + h) * 64;
+      {  // delta = rowsum(dO * O): 8 lanes share one 128-byte row (coalesced; a row per thread made every load touch 32
+         // lines and cost ~9000 cycles per item), warp w owns rows [32w, 32w+32); lse in log2 units for row `tid`
+        const int wid = g * 4 + (warp & 3), sub = lane >> 3, ch = lane & 7;
+        const int64_t rstride = (int64_t)H * 64;
+        const __nv_bfloat16* obase = out + ((int64_t)b * N * H + h) * 64 + ch * 8;
+        const __nv_bfloat16* dbase = dout + ((int64_t)b * N * H + h) * 64 + ch * 8;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float a[8], gg[8];
-            load8(orow + 8 * c, a);
-            load8(drow + 8 * c, gg);
+        for (int half = 0; half < 2; ++half) {
+          uint4 ov[4], dv[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) d = fmaf(a[e], gg[e], d);
+          for (int i = 0; i < 4; ++i) {
+            const int row = wid * 32 + (half * 4 + i) * 4 + sub;
+            ov[i] = dv[i] = make_uint4(0, 0, 0, 0);
+            if (row < N) {
+              ov[i] = *reinterpret_cast<const uint4*>(obase + row * rstride);
+              dv[i] = *reinterpret_cast<const uint4*>(dbase + row * rstride);
+            }
           }
-          l2 = lse[((int64_t)b * H + h) * N + tid] * LOG2E;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162* oa = reinterpret_cast<const __nv_bfloat162*>(&ov[i]);
+            const __nv_bfloat162* da = reinterpret_cast<const __nv_bfloat162*>(&dv[i]);
+            float d = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 x = __bfloat1622float2(oa[e]), y = __bfloat1622float2(da[e]);
+              d = fmaf(x.x, y.x, d);
+              d = fmaf(x.y, y.y, d);
+            }
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            d += __shfl_xor_sync(0xffffffffu, d, 4);
+            if (ch == 0) ctl->delta[par][wid * 32 + (half * 4 + i) * 4 + sub] = d;
+          }
         }
-        ctl->delta[par][tid] = d;
-        ctl->lse2[par][tid] = l2;
+        // +inf for padded queries: exp2(x - inf) = 0 masks them without a select
+        ctl->lse2[par][tid] = tid < N ? lse[((int64_t)b * H + h) * N + tid] * LOG2E : __int_as_float(0x7f800000);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       GVIT_TR(10);
@@ -626,27 +724,22 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
           tc_fence_after();
           GVIT_TR(11);
           for (int c0 = 0; c0 < wg; c0 += 32) {
-            float s[32], dp[32];
-            tmem_ld32x2(lST + c0, ldPT + c0, s, dp);
-            GVIT_TR(12);
-#pragma unroll
-            for (int e4 = 0; e4 < 32; e4 += 4) {
-              const float4 l4 = *reinterpret_cast<const float4*>(&ctl->lse2[par][q0 + c0 + e4]);
-              const float4 d4 = *reinterpret_cast<const float4*>(&ctl->delta[par][q0 + c0 + e4]);
-              const float ll[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int e = e4 + u;
-                const float p = (kvalid && q0 + c0 + e < N) ? ex2(fmaf(s[e], sl2, -ll[u])) : 0.f;
-                s[e] = p;
-                dp[e] = p * (dp[e] - dd[u]) * scale;
-              }
+            const float* l2p = &ctl->lse2[par][q0 + c0];
+            const float* dlp = &ctl->delta[par][q0 + c0];
+            if (wg - c0 >= 32) {
+              float s[32], dp[32];
+              tmem_ld32x2(lST + c0, ldPT + c0, s, dp);
+              GVIT_TR(12);
+              if (c0 == 0 && itc > 0) mbar_wait(&ctl->st_free, (itc - 1) & 1);   // staging of the previous step consumed
+              GVIT_TR(14);
+              bwd_chunk<32>(s, dp, l2p, dlp, sl2, pt_g, dst_g, t, c0);
+            } else {                                      // 16-column tail: never touch stale TMEM columns
+              float s[16], dp[16];
+              tmem_ld16x2(lST + c0, ldPT + c0, s, dp);
+              if (c0 == 0 && itc > 0) mbar_wait(&ctl->st_free, (itc - 1) & 1);
+              bwd_chunk<16>(s, dp, l2p, dlp, sl2, pt_g, dst_g, t, c0);
             }
             GVIT_TR(13);
-            if (c0 == 0 && itc > 0) mbar_wait(&ctl->st_free, (itc - 1) & 1);   // staging of the previous step consumed
-            GVIT_TR(14);
-            store_row32(pt_g, t, c0, s);
-            store_row32(dst_g, t, c0, dp);
           }
           fence_async_smem();
           tc_fence_before();
@@ -661,17 +754,22 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
             tmem_ld32x2(ta, ta + 32, v0, v1);
             tc_fence_before();
             mbar_arrive(&ctl->dvk_free);
-            if (kvalid) {
-              __nv_bfloat16* dst = dqkv + ((((int64_t)b * N + key) * 3 + (g == 0 ? 2 : 1)) * H + h) * 64;
-              store_out32(dst, v0);
-              store_out32(dst + 32, v1);
+            // bf16 rows -> this warpgroup's P^T staging tile (every MMA that read it has retired) -> ONE TMA tile store
+            // (a 128-byte row per thread made each STG touch 32 lines: ~4000 cycles per key tile)
+            stage_out64(pt_g, t, v0, v1, g == 0 ? 1.0f : scale);      // dS was formed without the softmax scale
+            fence_async_smem();
+            asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+            if (t == 0) {
+              tma_store_3d(&tm_dqkv, pt_g, ((g == 0 ? 2 : 1) * H + h) * 64, kt * 128, b);   // rows >= N are clipped
+              tma_store_commit();
+              tma_store_wait_read();
             }
+            asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");   // staging tile reusable
           }
         }
       }
       {  // dQ: warpgroup g stores query tile g (every thread arrives so that the barrier count is fixed)
         float v0[32], v1[32];
-        const int q = g * 128 + t;
         if (g < T) {
           const uint32_t ta = tmem_lane_base(tdQ + g * 64, warp);
           tmem_ld32x2(ta, ta + 32, v0, v1);
@@ -679,10 +777,16 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
         tc_fence_before();
         mbar_arrive(&ctl->dq_free);
         GVIT_TR(17);
-        if (g < T && q < N) {
-          __nv_bfloat16* dst = dqkv + ((((int64_t)b * N + q) * 3 + 0) * H + h) * 64;
-          store_out32(dst, v0);
-          store_out32(dst + 32, v1);
+        if (g < T) {
+          stage_out64(pt_g, t, v0, v1, scale);
+          fence_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+          if (t == 0) {
+            tma_store_3d(&tm_dqkv, pt_g, h * 64, g * 128, b);
+            tma_store_commit();
+            tma_store_wait_read();
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
         }
       }
     }
@@ -728,14 +832,16 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
   if (rc != GVIT_OK) return rc;
   rc = make_tmap_bf16_3d(&tm_do, dout, (uint64_t)H * 64, N, B, (uint64_t)H * 64, (uint64_t)N * H * 64, 128);
   if (rc != GVIT_OK) return rc;
+  CUtensorMap tm_dqkv;
+  rc = make_tmap_bf16_3d(&tm_dqkv, dqkv, (uint64_t)3 * H * 64, N, B, (uint64_t)3 * H * 64, (uint64_t)N * 3 * H * 64, 128);
+  if (rc != GVIT_OK) return rc;
   GVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
   const int items = B * H;
   const int grid = items < num_sms() ? items : num_sms();
   (void)delta_ws;                                            // only the fp32-FMA path needs the global delta workspace
-  attn_bwd_tc_kernel<<<grid, B2_THREADS, BWD_SMEM, st>>>(tm_qkv, tm_do, N, H, items, scale,
+  attn_bwd_tc_kernel<<<grid, B2_THREADS, BWD_SMEM, st>>>(tm_qkv, tm_do, tm_dqkv, N, H, items, scale,
                                                          static_cast<const __nv_bfloat16*>(out),
-                                                         static_cast<const __nv_bfloat16*>(dout), lse,
-                                                         static_cast<__nv_bfloat16*>(dqkv));
+                                                         static_cast<const __nv_bfloat16*>(dout), lse);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }

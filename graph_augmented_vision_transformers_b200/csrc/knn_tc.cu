@@ -37,8 +37,9 @@ template <int KT>
 __global__ void __launch_bounds__(THREADS, 1) knn_tc_kernel(const __grid_constant__ CUtensorMap tmap, int Np, int D,
                                                             int k, int NT, int32_t* __restrict__ idx,
                                                             float* __restrict__ vals, float* __restrict__ rnorm) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* stages = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // no static __shared__ in these kernels: base is 1024-aligned
+  uint8_t* stages = smem_raw;   // NOT rounded through an integer: that made every access a generic LD/ST instead of LDS/STS
+  if ((smem_u32(stages) & 1023u) != 0) __trap();
   Ctrl* ctl = reinterpret_cast<Ctrl*>(stages + (size_t)STAGES * STAGE_BYTES);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role id
