@@ -56,28 +56,78 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const Tx* __restrict__ x, c
   if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
 }
 
+// ---- per-warp bulk-copy row pipeline (cp.async.bulk + mbarrier) for the LayerNorm backward ----------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok)
+    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}"
+                 : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
 // dx for every row; per-CTA partial dgamma/dbeta (fixed row -> CTA assignment: deterministic, no atomics).
-// x and dy of the row stay in registers between the two reductions and the dx pass; gamma lives in shared memory.
+// Each warp owns a private ring of `slots` shared-memory row slots filled by cp.async.bulk (x row + dy row per slot,
+// one mbarrier per slot): the rows of the next `slots` iterations are always in flight without costing registers.
+// v1 (rows loaded straight into registers, one row in flight per warp, 16 warps/SM) reached 46 % of HBM.
 template <typename Tx, typename Ty, int NC>
 __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const Ty* __restrict__ dy, const Tx* __restrict__ x,
                                                         const Tx* __restrict__ gamma, const float* __restrict__ mean,
-                                                        const float* __restrict__ rstd, int64_t rows, int D,
+                                                        const float* __restrict__ rstd, int64_t rows, int D, int slots,
                                                         Tx* __restrict__ dx, float* __restrict__ partial) {
+  extern __shared__ __align__(128) uint8_t ring[];
   __shared__ float red[8][256];
   __shared__ float gsm[NC * 256];
+  __shared__ __align__(8) uint64_t bars[8][4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t xbytes = D * sizeof(Tx), ybytes = D * sizeof(Ty);
+  const uint32_t xpad = (xbytes + 127u) & ~127u, slot_bytes = xpad + ((ybytes + 127u) & ~127u);
+  uint8_t* wring = ring + (size_t)warp * slots * slot_bytes;
   for (int i = threadIdx.x; i < NC * 256; i += 256) gsm[i] = i < D ? to_f32(gamma[i]) : 0.f;
+  if (lane == 0) {
+    for (int s = 0; s < slots; ++s) bar_init(&bars[warp][s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * 8;
+  const int64_t row0 = (int64_t)blockIdx.x * 8 + warp;
+  auto issue = [&](int64_t r, int s) {      // lane 0 only
+    bar_expect_tx(&bars[warp][s], xbytes + ybytes);
+    bulk_copy_g2s(wring + (size_t)s * slot_bytes, x + r * D, xbytes, &bars[warp][s]);
+    bulk_copy_g2s(wring + (size_t)s * slot_bytes + xpad, dy + r * D, ybytes, &bars[warp][s]);
+  };
+  if (lane == 0)
+    for (int s = 0; s < slots; ++s)
+      if (row0 + s * stride < rows) issue(row0 + s * stride, s);
   float dg[NC][8] = {}, db[NC][8] = {};
   const float invD = 1.0f / D;
-  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < rows; row += (int64_t)gridDim.x * 8) {
+  float mu_n = 0.f, rs_n = 0.f;
+  if (row0 < rows) { mu_n = mean[row0]; rs_n = rstd[row0]; }
+  int it = 0;
+  for (int64_t row = row0; row < rows; row += stride, ++it) {
+    const int s = it % slots;
+    const float mu = mu_n, rs = rs_n;
+    if (row + stride < rows) { mu_n = mean[row + stride]; rs_n = rstd[row + stride]; }
+    bar_wait(&bars[warp][s], (it / slots) & 1);
+    const Tx* xs = reinterpret_cast<const Tx*>(wring + (size_t)s * slot_bytes);
+    const Ty* ys = reinterpret_cast<const Ty*>(wring + (size_t)s * slot_bytes + xpad);
     float xv[NC][8], dyv[NC][8];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const int d0 = lane * 8 + c * 256;
-      if (d0 < D) { load8(x + row * D + d0, xv[c]); load8(dy + row * D + d0, dyv[c]); }
+      if (d0 < D) { load8(xs + d0, xv[c]); load8(ys + d0, dyv[c]); }
     }
-    const float mu = mean[row], rs = rstd[row];
+    __syncwarp();                                           // every lane has its copy: the slot may be refilled
+    if (lane == 0 && row + (int64_t)slots * stride < rows) issue(row + (int64_t)slots * stride, s);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -120,10 +170,10 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const Ty* __restrict__ d
       __syncthreads();
       const int col = c * 256 + threadIdx.x;
       if (col < D) {
-        float s = 0.f;
+        float sacc = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-        partial[((int64_t)pass * gridDim.x + blockIdx.x) * D + col] = s;
+        for (int w = 0; w < 8; ++w) sacc += red[w][threadIdx.x];
+        partial[((int64_t)pass * gridDim.x + blockIdx.x) * D + col] = sacc;
       }
     }
   }
@@ -293,9 +343,15 @@ int ln_fwd_launch(const void* x, const void* gamma, const void* beta, int64_t ro
 template <typename Tx, typename Ty, int NC>
 int ln_bwd_launch(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, int64_t rows,
                   int D, void* dx, float* partial, int nblk, cudaStream_t st) {
-  ln_bwd_kernel<Tx, Ty, NC><<<nblk, 256, 0, st>>>(static_cast<const Ty*>(dy), static_cast<const Tx*>(x),
-                                                  static_cast<const Tx*>(gamma), mean, rstd, rows, D,
-                                                  static_cast<Tx*>(dx), partial);
+  // ring: 8 warps x slots x (x row + dy row); aim for two CTAs per SM (<= ~100 KB of dynamic shared memory each)
+  const size_t slot_bytes = (((size_t)D * sizeof(Tx) + 127) & ~size_t(127)) + (((size_t)D * sizeof(Ty) + 127) & ~size_t(127));
+  int slots = (int)((100 * 1024) / (8 * slot_bytes));
+  slots = slots > 4 ? 4 : (slots < 2 ? 2 : slots);
+  const size_t smem = 8 * slots * slot_bytes;
+  auto kern = ln_bwd_kernel<Tx, Ty, NC>;
+  GVIT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<nblk, 256, smem, st>>>(static_cast<const Ty*>(dy), static_cast<const Tx*>(x), static_cast<const Tx*>(gamma), mean,
+                                rstd, rows, D, slots, static_cast<Tx*>(dx), partial);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }
