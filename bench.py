@@ -206,6 +206,8 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
                     3 * tok + B * Np * k * 16, 4.0 * B * Np * k * D, "hbm", 12),
         "knn_bwd": (lambda i: _call("gvit_knn_bwd", _ptr(hs[i % R], off), bs, rs, B, Np, D, k, dt, _ptr(idxs[i % R][0]), _ptr(idxs[i % R][2]), _ptr(dvals), _ptr(rev[i % R][0]), _ptr(rev[i % R][1]), _ptr(out, off), st),
                     3 * tok + B * Np * k * 12, 4.0 * B * Np * k * D, "hbm", 12),
+        "graph_bwd": (lambda i: _call("gvit_graph_bwd", _ptr(hs[i % R], off), bs, rs, B, Np, D, k, dt, _ptr(idxs[i % R][0]), _ptr(idxs[i % R][1]), _ptr(w), _ptr(idxs[i % R][2]), _ptr(xs[i % R], off), _ptr(dvals), _ptr(out, off), st),
+                      3 * tok + B * Np * k * 20, 6.0 * B * Np * Np * D, "hbm", 12),
         "layernorm_fwd": (lambda i: _call("gvit_layernorm_fwd", _ptr(hs[i % R]), _ptr(gam), _ptr(bet), B * N, D, 1e-5, dt, dt, _ptr(out), _ptr(mean), _ptr(rstd), st),
                           2 * B * N * D * e, 0.0, "hbm", 36),
         "layernorm_bwd": (lambda i: _call("gvit_layernorm_bwd", _ptr(xs[i % R]), _ptr(hs[i % R]), _ptr(gam), _ptr(mean), _ptr(rstd), B * N, D, dt, dt, _ptr(out), _ptr(dgb[0]), _ptr(dgb[1]), _ptr(ws), st),

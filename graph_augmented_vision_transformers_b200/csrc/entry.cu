@@ -95,6 +95,20 @@ int gvit_agg_bwd(const void* p, int64_t batch_stride, int64_t row_stride, int B,
   return agg_bwd_simt(t, k, dtype, idx, w, dz, rev_ptr, rev_src, dvals, dp, static_cast<cudaStream_t>(stream));
 }
 
+int gvit_graph_bwd(const void* p, int64_t batch_stride, int64_t row_stride, int B, int Np, int D, int k, int dtype,
+                   const int32_t* idx, const float* vals, const float* w, const float* rnorm, const void* dz,
+                   float* dvals, void* dp, void* stream) {
+  TRY(check_dtype(dtype, "graph_bwd"));
+  TRY(check_tokens("graph_bwd", p, batch_stride, row_stride, B, Np, D, k));
+  GVIT_REQUIRE(idx && vals && w && rnorm && dz && dvals && dp, GVIT_ERR_SHAPE, "graph_bwd: null pointer");
+  GVIT_REQUIRE(aligned16(dz) && aligned16(dp), GVIT_ERR_ALIGN, "graph_bwd: dz/dp must be 16-byte aligned");
+  GVIT_REQUIRE(dtype == GVIT_BF16 && graph_bwd_tc_supported(Np, D, k), GVIT_ERR_UNSUPPORTED,
+               "graph_bwd: the fused backward is bf16-only with Np=%d D=%d k=%d in range; compose gvit_graph_reverse, "
+               "gvit_agg_bwd and gvit_knn_bwd instead", Np, D, k);
+  Tokens t{p, batch_stride, row_stride, B, Np, D};
+  return graph_bwd_tc(t, k, idx, vals, w, rnorm, dz, dvals, dp, static_cast<cudaStream_t>(stream));
+}
+
 int gvit_attn_fwd(const void* qkv, int B, int N, int H, int dh, float scale, int dtype, void* out, float* lse,
                   void* stream) {
   TRY(check_dtype(dtype, "attn_fwd"));

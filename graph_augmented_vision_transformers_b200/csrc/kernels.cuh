@@ -30,6 +30,9 @@ int knn_fwd_tc(const Tokens& p, int k, int32_t* idx, float* vals, float* rnorm, 
 bool agg_tc_supported(int Np, int D, int k);
 int agg_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, const float* vals, const void* Wg,
                const void* bias, const void* resid, void* out, float* w_save, void* z_save, cudaStream_t st);
+bool graph_bwd_tc_supported(int Np, int D, int k);
+int graph_bwd_tc(const Tokens& p, int k, const int32_t* idx, const float* vals, const float* w, const float* rnorm,
+                 const void* dz, float* dvals, void* dp, cudaStream_t st);
 bool attn_fwd_tc_supported(int N, int dh);
 bool attn_bwd_tc_supported(int N, int dh);
 int attn_fwd_tc(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, cudaStream_t st);

@@ -30,7 +30,7 @@ __all__ = ["attention_core", "layer_norm", "dropout_add", "gelu_dropout", "knn_g
 _LAUNCHES = {"n": 0}
 _KERNELS_PER_CALL = {
     "gvit_knn_fwd": 1, "gvit_graph_reverse": 1, "gvit_knn_bwd": 1, "gvit_agg_gather_fwd": 1, "gvit_agg_fwd": 1,
-    "gvit_agg_bwd": 2, "gvit_attn_fwd": 1, "gvit_attn_bwd": 1, "gvit_layernorm_fwd": 1, "gvit_layernorm_bwd": 2,
+    "gvit_agg_bwd": 2, "gvit_graph_bwd": 2, "gvit_attn_fwd": 1, "gvit_attn_bwd": 1, "gvit_layernorm_fwd": 1, "gvit_layernorm_bwd": 2,
     "gvit_dropout_residual_fwd": 1, "gvit_dropout_bwd": 1, "gvit_gelu_dropout_fwd": 1, "gvit_gelu_dropout_bwd": 1,
 }
 
@@ -323,6 +323,12 @@ def fused_agg_available(dtype: torch.dtype, Np: int, D: int, k: int) -> bool:
     return _lib.describe_path("agg", GVIT_BF16, Np, D).startswith("agg:tcgen05")
 
 
+def fused_graph_bwd_available(dtype: torch.dtype, Np: int, D: int, k: int) -> bool:
+    if dtype != torch.bfloat16 or k > 16:
+        return False
+    return _lib.describe_path("graph_bwd", GVIT_BF16, Np, D).startswith("graph_bwd:tcgen05")
+
+
 # ------------------------------------------------------------------------------------------------
 # a7 + a8: the whole graph sub-layer as one differentiable operator
 # ------------------------------------------------------------------------------------------------
@@ -350,7 +356,7 @@ class _PatchGraph(torch.autograd.Function):
                   _ptr(z), st)
             out = torch.zeros_like(h) if resid is None else resid.clone()
             out[:, 1:] += F.linear(z, weight, bias)
-        ctx.save_for_backward(h, weight, idx, rnorm, w, z)
+        ctx.save_for_backward(h, weight, idx, rnorm, w, z, vals)
         ctx.k = k
         ctx.has = (bias is not None, resid is not None)
         ctx.mark_non_differentiable(idx, vals)
@@ -358,7 +364,7 @@ class _PatchGraph(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _didx, _dvals):
-        h, weight, idx, rnorm, w, z = ctx.saved_tensors
+        h, weight, idx, rnorm, w, z, vals = ctx.saved_tensors
         k = ctx.k
         off, bs, rs, B, Np, D = _token_view(h)
         dt = _dtype_code(h)
@@ -371,12 +377,17 @@ class _PatchGraph(torch.autograd.Function):
         dh = None
         if ctx.needs_input_grad[0]:
             dz = (dy2 @ weight).view(B, Np, D)
-            rev_ptr = torch.empty((B, Np + 1), dtype=torch.int32, device=h.device)
-            rev_src = torch.empty((B, Np * k), dtype=torch.int32, device=h.device)
-            _call("gvit_graph_reverse", _ptr(idx), B, Np, k, _ptr(rev_ptr), _ptr(rev_src), st)
             dvals = torch.empty((B, Np, k), dtype=torch.float32, device=h.device)
             dh = torch.empty_like(h)
             dh[:, 0].zero_()
+            if fused_graph_bwd_available(h.dtype, Np, D, k):
+                # bf16: both sparse stages as two per-image tensor-core GEMMs, no reverse adjacency
+                _call("gvit_graph_bwd", _ptr(h, off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(vals), _ptr(w),
+                      _ptr(rnorm), _ptr(dz), _ptr(dvals), _ptr(dh, off), st)
+                return dh, dweight, dbias, (dout if ctx.has[1] else None), None
+            rev_ptr = torch.empty((B, Np + 1), dtype=torch.int32, device=h.device)
+            rev_src = torch.empty((B, Np * k), dtype=torch.int32, device=h.device)
+            _call("gvit_graph_reverse", _ptr(idx), B, Np, k, _ptr(rev_ptr), _ptr(rev_src), st)
             _call("gvit_agg_bwd", _ptr(h, off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(w), _ptr(dz), _ptr(rev_ptr),
                   _ptr(rev_src), _ptr(dvals), _ptr(dh, off), st)
             _call("gvit_knn_bwd", _ptr(h, off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(rnorm), _ptr(dvals),

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GVIT_ABI_VERSION 2
+#define GVIT_ABI_VERSION 3
 #if defined(__GNUC__)
 #define GVIT_API __attribute__((visibility("default")))
 #else
@@ -97,6 +97,16 @@ GVIT_API int gvit_agg_fwd(const void* h, int B, int Np, int D, int k, int dtype,
 GVIT_API int gvit_agg_bwd(const void* p, int64_t batch_stride, int64_t row_stride, int B, int Np, int D, int k, int dtype,
                  const int32_t* idx, const float* w, const void* dz, const int32_t* rev_ptr, const int32_t* rev_src,
                  float* dvals, void* dp, void* stream);
+
+/* Fused backward of G1-G5 for bf16 on the tensor cores (no reverse adjacency needed): given dz = dY Wg it writes
+ * dvals (B,Np,k) fp32 - the gradient w.r.t. the selected similarities - and dp (strided like p, WRITTEN in full):
+ * dp = A~^T dz  +  the gradient through the cosine similarities and the L2 normalisation.  `vals` are the saved
+ * similarities of gvit_knn_fwd, `w` the saved softmax weights, `rnorm` the saved reciprocal norms.
+ * bf16 only; returns GVIT_ERR_UNSUPPORTED outside the kernel's range (use gvit_graph_reverse + gvit_agg_bwd +
+ * gvit_knn_bwd there, which also serve fp32).  gvit_describe_path("graph_bwd", ...) tells which applies. */
+GVIT_API int gvit_graph_bwd(const void* p, int64_t batch_stride, int64_t row_stride, int B, int Np, int D, int k, int dtype,
+                   const int32_t* idx, const float* vals, const float* w, const float* rnorm, const void* dz,
+                   float* dvals, void* dp, void* stream);
 
 /* ---- a2: attention core, replaces /root/reference/src/models/vit.py:59-69 -------------------
  * qkv : the packed projection output of vit.py:59, (B,N,3,H,dh) contiguous - consumed in place, no

@@ -133,3 +133,33 @@ def test_backward_is_deterministic_at_full_size():
     # linearity in the projection: scaling Wg scales the output
     o2 = ops.patch_graph(h, W * 2, None, 8)
     assert rel_err(o2, 2 * outs[0][0].float()) < 1e-2
+
+
+@pytest.mark.parametrize("B,Np,D,k", [(3, 196, 768, 8), (2, 144, 256, 4), (5, 64, 128, 16), (2, 129, 192, 8), (1, 16, 64, 2)])
+def test_bf16_fused_backward_matches_gather_backward(B, Np, D, k):
+    """gvit_graph_bwd (two per-image tensor-core GEMMs) against gvit_graph_reverse + gvit_agg_bwd + gvit_knn_bwd
+    (reverse-CSR gathers) on the same saved tensors: same algebra, only bf16 rounding of the coefficients differs."""
+    from graph_augmented_vision_transformers_b200.ops import _call, _dtype_code, _ptr, _stream, _token_view
+    bf = torch.bfloat16
+    _, hd = tokens(B, Np, D, seed=31, dtype=bf)
+    assert ops.fused_graph_bwd_available(bf, Np, D, k)
+    idx, vals, rnorm = ops.knn_graph(hd, k)
+    w, _ = ops.agg_gather(hd, idx, vals)
+    g = torch.Generator(device=DEV).manual_seed(7)
+    dz = torch.randn(B, Np, D, generator=g, device=DEV).to(bf)
+    off, bs, rs, _, _, _ = _token_view(hd)
+    dt, st = _dtype_code(hd), _stream()
+    rev_ptr, rev_src = ops.graph_reverse(idx)
+    dvals_ref = torch.empty(B, Np, k, device=DEV)
+    dh_ref = torch.zeros_like(hd)
+    _call("gvit_agg_bwd", _ptr(hd, off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(w), _ptr(dz), _ptr(rev_ptr), _ptr(rev_src),
+          _ptr(dvals_ref), _ptr(dh_ref, off), st)
+    _call("gvit_knn_bwd", _ptr(hd, off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(rnorm), _ptr(dvals_ref), _ptr(rev_ptr),
+          _ptr(rev_src), _ptr(dh_ref, off), st)
+    dvals = torch.empty(B, Np, k, device=DEV)
+    dh = torch.zeros_like(hd)
+    _call("gvit_graph_bwd", _ptr(hd, off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(vals), _ptr(w), _ptr(rnorm), _ptr(dz),
+          _ptr(dvals), _ptr(dh, off), st)
+    assert rel_err(dvals, dvals_ref) < 1e-4
+    assert rel_err(dh, dh_ref.float()) < 1e-2
+    assert float(dh[:, 0].abs().max()) == 0.0
