@@ -152,11 +152,13 @@ class _LayerNorm(torch.autograd.Function):
         rows = x.numel() // D
         dy = dy.contiguous()
         dx = torch.empty_like(x)
-        dgb = torch.empty((2, D), dtype=torch.float32, device=x.device)
+        # two separate tensors: AccumulateGrad steals a whole tensor but has to clone a view
+        dgamma = torch.empty(D, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(D, dtype=torch.float32, device=x.device)
         ws = torch.empty(2 * GVIT_LN_PARTIALS * D, dtype=torch.float32, device=x.device)
         _call("gvit_layernorm_bwd", _ptr(dy), _ptr(x), _ptr(weight), _ptr(mean), _ptr(rstd), rows, D, _dtype_code(x),
-              ctx.y_code, _ptr(dx), _ptr(dgb[0]), _ptr(dgb[1]), _ptr(ws), _stream())
-        return dx, dgb[0].to(weight.dtype), dgb[1].to(weight.dtype), None, None
+              ctx.y_code, _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(ws), _stream())
+        return dx, dgamma.to(weight.dtype), dbeta.to(weight.dtype), None, None
 
 
 def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
