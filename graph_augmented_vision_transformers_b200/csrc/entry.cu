@@ -78,9 +78,12 @@ int gvit_agg_fwd(const void* h, int B, int Np, int D, int k, int dtype, const in
   GVIT_REQUIRE(B >= 1 && Np >= 1 && k >= 1 && k <= GVIT_MAX_K && k <= Np, GVIT_ERR_SHAPE, "agg_fwd: bad sizes B=%d Np=%d k=%d", B, Np, k);
   GVIT_REQUIRE(dtype == GVIT_BF16, GVIT_ERR_UNSUPPORTED,
                "agg_fwd: the fused kernel is bf16-only; fp32 composes gvit_agg_gather_fwd with a library GEMM");
-  GVIT_REQUIRE(agg_tc_supported(Np, D, k), GVIT_ERR_UNSUPPORTED, "agg_fwd: shape Np=%d D=%d k=%d outside the fused kernel's range", Np, D, k);
+  GVIT_REQUIRE(agg3_tc_supported(Np, D, k) || agg_tc_supported(Np, D, k), GVIT_ERR_UNSUPPORTED,
+               "agg_fwd: shape Np=%d D=%d k=%d outside the fused kernels' range", Np, D, k);
   GVIT_REQUIRE(aligned16(h) && aligned16(Wg) && aligned16(out) && (!resid || aligned16(resid)) && (!z_save || aligned16(z_save)),
                GVIT_ERR_ALIGN, "agg_fwd: pointers must be 16-byte aligned");
+  if (agg3_tc_supported(Np, D, k))
+    return agg3_fwd_tc(h, B, Np, D, k, idx, vals, Wg, bias, resid, out, w_save, z_save, static_cast<cudaStream_t>(stream));
   return agg_fwd_tc(h, B, Np, D, k, idx, vals, Wg, bias, resid, out, w_save, z_save, static_cast<cudaStream_t>(stream));
 }
 

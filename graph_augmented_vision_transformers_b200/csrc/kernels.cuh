@@ -27,7 +27,10 @@ int attn_bwd_simt(const void* qkv, const void* out, const void* dout, const floa
 // ---- tcgen05 / TMEM / TMA kernels (bf16 storage, fp32 accumulate) : knn_tc.cu, agg_tc.cu, attn_tc.cu
 bool knn_tc_supported(int Np, int D, int k);
 int knn_fwd_tc(const Tokens& p, int k, int32_t* idx, float* vals, float* rnorm, cudaStream_t st);
-bool agg_tc_supported(int Np, int D, int k);
+bool agg_tc_supported(int Np, int D, int k);    // v2 kernel (agg_tc.cu): D up to 1024
+bool agg3_tc_supported(int Np, int D, int k);   // v3 kernel (agg3_tc.cu): whole Z tile resident in TMEM, D <= 768
+int agg3_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, const float* vals, const void* Wg,
+                const void* bias, const void* resid, void* out, float* w_save, void* z_save, cudaStream_t st);
 int agg_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, const float* vals, const void* Wg,
                const void* bias, const void* resid, void* out, float* w_save, void* z_save, cudaStream_t st);
 bool graph_bwd_tc_supported(int Np, int D, int k);
