@@ -18,8 +18,9 @@
 //
 // TMEM (512 columns): Z bf16 [0, D/2) | Z fp32 staging: step t even -> [64t, 64t+128) (in place), odd -> [384, 512)
 //                     | OUT chunk buffers [384, 448), [448, 512) (projection phase).
-// Shared memory: A~ (4 x 16 KB) | ring of 4 x 32 KB slots (token slabs, then W pieces) | 4 x 8 KB per-warp staging.
-// Warp roles: 0-3 row warps (thread <-> token row = TMEM lane), 4 TMA producer, 5 MMA issuer (+ TMEM allocation).
+// Shared memory: A~ (4 x 16 KB) | ring of 4 x 32 KB slots (token slabs, then W pieces) | 8 x 4 KB per-warp staging.
+// Warp roles: 0-3 row warpgroup 0, 4-7 row warpgroup 1 (thread <-> token row = TMEM lane; warpgroup g owns the Z steps
+// and output chunks of parity g, i.e. one of the two TMEM staging / OUT buffers), 8 TMA producer, 9 MMA issuer.
 #include <float.h>
 
 #include "kernels.cuh"
@@ -30,19 +31,20 @@ namespace {
 
 using namespace tc;
 
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;
 constexpr int TILE = 128 * 128;             // [128 rows][64 bf16]
 constexpr int A_BYTES = 4 * TILE;           // A~ [128][256] as four 64-column blocks
 constexpr int SLOT = 32 * 1024;             // ring slot: one token slab [<=256][64] or one W piece [64][<=256]
 constexpr int NSLOT = 4;
-constexpr int WSTAGE = 8 * 1024;            // per-warp staging for coalesced global access
+constexpr int WSTAGE = 4 * 1024;            // per-warp staging ([32 rows][128 B]) for coalesced global access
 constexpr int T_OUT = 384;                  // first OUT chunk buffer / odd Z staging
 
 struct __align__(8) Ctrl {
   uint64_t full[NSLOT], empty[NSLOT], a_ready, zs_full[2], conv_done[2], out_full[2], out_free[2];
   uint32_t tmem_base;
+  __align__(16) __nv_bfloat16 bias[768];
 };
-constexpr size_t SMEM_BYTES = A_BYTES + NSLOT * SLOT + 4 * WSTAGE + sizeof(Ctrl);
+constexpr size_t SMEM_BYTES = A_BYTES + NSLOT * SLOT + 8 * WSTAGE + sizeof(Ctrl);
 
 struct Params {
   int Np, D, k, NT;
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_consta
   if ((smem_u32(sA) & 1023u) != 0) __trap();
   uint8_t* sRing = sA + A_BYTES;
   uint8_t* sStg = sRing + NSLOT * SLOT;
-  Ctrl* ctl = reinterpret_cast<Ctrl*>(sStg + 4 * WSTAGE);
+  Ctrl* ctl = reinterpret_cast<Ctrl*>(sStg + 8 * WSTAGE);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int mt = blockIdx.x, b = blockIdx.y;
@@ -78,8 +80,9 @@ __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_consta
   const int nslab = D / 64;                 // 64-feature token slabs == 64-feature output chunks
   const int nstep = (D + 127) / 128;        // Z steps of (up to) 128 features
   const int npiece = (D + 255) / 256;       // W pieces of (up to) 256 reduction columns per output chunk
+  GVIT_TRACE_DECL
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     prefetch_tmap(&tm_tok);
     prefetch_tmap(&tm_w);
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
@@ -92,13 +95,13 @@ __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_consta
     mbar_init(&ctl->a_ready, 128);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc(&ctl->tmem_base, 512);
+  if (warp == 9) tmem_alloc(&ctl->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int c = 0;                                                       // ring fill counter
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_consta
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       const uint32_t aA = smem_u32(sA), aR = smem_u32(sRing);
@@ -132,6 +135,7 @@ __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_consta
         const uint32_t stg = (t & 1) ? T_OUT : 64 * t;
         if (t >= 2) mbar_wait(&ctl->conv_done[t & 1], ((t - 2) >> 1) & 1);   // staging (odd) / neighbours converted
         const int sl0 = c % NSLOT;
+        GVIT_TR(1);
         mbar_wait(&ctl->full[sl0], (c / NSLOT) & 1);
         if (width == 128) mbar_wait(&ctl->full[sl0 + 1], ((c + 1) / NSLOT) & 1);   // slabs 2t, 2t+1: slots (0,1) or (2,3)
         tc_fence_after();
@@ -141,6 +145,7 @@ __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_consta
           umma_ss(tmem + stg, make_sdesc(aA + (ks >> 2) * TILE + (ks & 3) * 32),
                   width == 128 ? make_sdesc_lbo(aTok + ks * 2048, SLOT) : make_sdesc(aTok + ks * 2048), idesc_z, ks > 0);
         umma_commit(&ctl->zs_full[t & 1]);
+        GVIT_TR(2);
         umma_commit(&ctl->empty[sl0]);
         if (width == 128) umma_commit(&ctl->empty[sl0 + 1]);
         c += width == 128 ? 2 : 1;
@@ -149,15 +154,18 @@ __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_consta
       if (nstep >= 2) mbar_wait(&ctl->conv_done[(nstep - 2) & 1], ((nstep - 2) >> 1) & 1);
       mbar_wait(&ctl->conv_done[(nstep - 1) & 1], ((nstep - 1) >> 1) & 1);
       tc_fence_after();
+      GVIT_TR(3);
       for (int n = 0; n < nslab; ++n) {                                // ---- projection
         const int buf = n & 1;
         mbar_wait(&ctl->out_free[buf], ((n >> 1) & 1) ^ 1);
         tc_fence_after();
+        GVIT_TR(4);
         for (int p = 0; p < npiece; ++p, ++c) {
           const int sl = c % NSLOT;
           const int nbox = min(4, (D - p * 256) / 64);
           mbar_wait(&ctl->full[sl], (c / NSLOT) & 1);
           tc_fence_after();
+          GVIT_TR(5);
           const uint32_t aW = aR + sl * SLOT;
           for (int j = 0; j < nbox; ++j)
 #pragma unroll
@@ -167,113 +175,137 @@ __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_consta
           umma_commit(&ctl->empty[sl]);
         }
         umma_commit(&ctl->out_full[buf]);
+        GVIT_TR(6);
       }
     }
   } else {
-    // ------------------------------------------------------------------ row warps
-    const int row = threadIdx.x;                                       // 0..127 == TMEM lane
+    // ------------------------------------------------------------------ row warpgroups
+    const int g = warp >> 2;                                           // warpgroup: parity of the steps / chunks it owns
+    const int row = threadIdx.x & 127;                                 // == TMEM lane
     const int rowg = mt * 128 + row;
     const bool valid = rowg < P.Np;
-    uint8_t* stg = sStg + warp * WSTAGE;                               // this warp's private staging (8 KB)
-    const int wrow0 = mt * 128 + warp * 32;                            // first token row of this warp
-    // ---- G4 + adjacency tile: zero A~, then scatter this row's k softmax weights (bf16) at its neighbour columns
+    uint8_t* stg = sStg + warp * WSTAGE;                               // this warp's private staging (4 KB)
+    const int wrow0 = mt * 128 + (warp & 3) * 32;                      // first token row of this warp
+    // ---- G4 + adjacency tile: zero A~, then scatter each row's k softmax weights (bf16) at its neighbour columns
     {
       const uint4 z4 = make_uint4(0, 0, 0, 0);
-      for (int i = threadIdx.x; i < A_BYTES / 16; i += 128) reinterpret_cast<uint4*>(sA)[i] = z4;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (valid) {
-        float w[KT];
-        int nb[KT];
-        float mx = -FLT_MAX, sum = 0.f;
-        const int64_t o = ((int64_t)b * P.Np + rowg) * P.k;
+      for (int i = threadIdx.x; i < A_BYTES / 16; i += 256) reinterpret_cast<uint4*>(sA)[i] = z4;
+      for (int i = threadIdx.x; i < 768 / 8; i += 256)
+        reinterpret_cast<uint4*>(ctl->bias)[i] = (P.bias && i < D / 8) ? reinterpret_cast<const uint4*>(P.bias)[i] : z4;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (g == 0) {
+        if (valid) {
+          float w[KT];
+          int nb[KT];
+          float mx = -FLT_MAX, sum = 0.f;
+          const int64_t o = ((int64_t)b * P.Np + rowg) * P.k;
 #pragma unroll
-        for (int j = 0; j < KT; ++j) {
-          const bool on = j < P.k;
-          nb[j] = on ? P.idx[o + j] : 0;
-          w[j] = on ? P.vals[o + j] : -FLT_MAX;
-          mx = fmaxf(mx, w[j]);
-        }
+          for (int j = 0; j < KT; ++j) {
+            const bool on = j < P.k;
+            nb[j] = on ? P.idx[o + j] : 0;
+            w[j] = on ? P.vals[o + j] : -FLT_MAX;
+            mx = fmaxf(mx, w[j]);
+          }
 #pragma unroll
-        for (int j = 0; j < KT; ++j) { w[j] = j < P.k ? expf(w[j] - mx) : 0.f; sum += w[j]; }
-        const float inv = 1.0f / sum;
+          for (int j = 0; j < KT; ++j) { w[j] = j < P.k ? expf(w[j] - mx) : 0.f; sum += w[j]; }
+          const float inv = 1.0f / sum;
 #pragma unroll
-        for (int j = 0; j < KT; ++j) {
-          if (j < P.k) {
-            const float wj = w[j] * inv;
-            if (P.w_save) P.w_save[o + j] = wj;
-            const int cidx = nb[j];
-            *reinterpret_cast<__nv_bfloat16*>(sA + (cidx >> 6) * TILE + swz128(row, cidx & 63) + (cidx & 7) * 2) = __float2bfloat16_rn(wj);
+          for (int j = 0; j < KT; ++j) {
+            if (j < P.k) {
+              const float wj = w[j] * inv;
+              if (P.w_save) P.w_save[o + j] = wj;
+              const int cidx = nb[j];
+              *reinterpret_cast<__nv_bfloat16*>(sA + (cidx >> 6) * TILE + swz128(row, cidx & 63) + (cidx & 7) * 2) = __float2bfloat16_rn(wj);
+            }
           }
         }
+        fence_async_smem();
+        mbar_arrive(&ctl->a_ready);
+        GVIT_TR(10);
+      } else if (mt == 0 && row < D / 8) {
+        // CLS row: out[b,0,:] = resid[b,0,:] (the graph leaves CLS untouched, section 9 G0)
+        const int64_t o = (int64_t)b * (P.Np + 1) * D + row * 8;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (P.resid) v = *reinterpret_cast<const uint4*>(P.resid + o);
+        *reinterpret_cast<uint4*>(P.out + o) = v;
       }
-      fence_async_smem();
-      mbar_arrive(&ctl->a_ready);
     }
-    // CLS row: out[b,0,:] = resid[b,0,:] (the graph leaves CLS untouched, section 9 G0)
-    if (mt == 0 && threadIdx.x < D / 8) {
-      const int64_t o = (int64_t)b * (P.Np + 1) * D + threadIdx.x * 8;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (P.resid) v = *reinterpret_cast<const uint4*>(P.resid + o);
-      *reinterpret_cast<uint4*>(P.out + o) = v;
-    }
-    // ---- Z phase: fp32 staging -> packed bf16 at TMEM columns [64t, 64t + width/2); optional copy out for the backward
+    const int ch8 = lane & 7, r8 = lane >> 3;                           // coalesced pattern: 8 lanes per 128-byte row segment
+    // residual rows of this warp for output chunk n, coalesced (lane -> rows r8 + 4i, 16-byte chunk ch8)
+    auto load_resid = [&](int n, uint4 (&rr)[8]) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r8 + 4 * i;
+        rr[i] = make_uint4(0, 0, 0, 0);
+        if (P.resid && n < nslab && wrow0 + r < P.Np)
+          rr[i] = *reinterpret_cast<const uint4*>(P.resid + ((int64_t)b * (P.Np + 1) + 1 + wrow0 + r) * D + n * 64 + ch8 * 8);
+      }
+    };
+    uint4 rnext[8];
+    load_resid(g, rnext);                                              // first chunk of this warpgroup: in flight during Z
+    // ---- Z phase (steps of parity g): fp32 staging -> packed bf16 at TMEM columns [64t, 64t + width/2);
+    //      optional copy out for the backward, 64 features at a time through the warp staging
     const uint32_t tl = tmem_lane_base(tmem, warp);
-    for (int t = 0; t < nstep; ++t) {
+    for (int t = g; t < nstep; t += 2) {
       const int width = min(128, D - t * 128);
       const uint32_t src = tl + ((t & 1) ? T_OUT : 64 * t), dst = tl + 64 * t;
       mbar_wait(&ctl->zs_full[t & 1], (t >> 1) & 1);
+      // an odd step's bf16 destination is the upper half of the previous (even) step's in-place staging, which the
+      // OTHER warpgroup converts: wait until it has read it
+      if (t & 1) mbar_wait(&ctl->conv_done[0], ((t - 1) >> 1) & 1);
       tc_fence_after();
-      for (int c0 = 0; c0 < width; c0 += 32) {
-        float v[32];
-        tmem_ld32(src + c0, v);
-        uint32_t pk[16];
+      GVIT_TR(11);
+      for (int h0 = 0; h0 < width; h0 += 64) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) pk[e] = pack2(v[2 * e], v[2 * e + 1]);
-        tmem_st16(dst + (c0 >> 1), pk);                               // in place for even t: columns already read
-        if (P.z_save) {                                                // row-major copy into the warp staging
+        for (int cc = 0; cc < 64; cc += 32) {
+          const int c0 = h0 + cc;
+          float v[32];
+          tmem_ld32(src + c0, v);
+          uint32_t pk[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int ch = (c0 >> 3) + q;                              // 16-byte chunk of the (up to 256-byte) row
-            *reinterpret_cast<uint4*>(stg + lane * 256 + ((ch ^ (lane & 15)) << 4)) =
-                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          for (int e = 0; e < 16; ++e) pk[e] = pack2(v[2 * e], v[2 * e + 1]);
+          tmem_st16(dst + (c0 >> 1), pk);                             // in place for even t: columns already read
+          if (P.z_save) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((((cc >> 3) + q) ^ (lane & 7)) << 4)) =
+                  make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
           }
         }
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&ctl->conv_done[t & 1]);
-      if (P.z_save) {                                                  // coalesced: a warp instruction covers whole rows
-        __syncwarp();
-        const int cpr = width / 8;                                     // 16-byte chunks per row: 16 or 8
-        const int rpi = 32 / cpr;                                      // rows per warp instruction: 2 or 4
-        const int ch = lane % cpr, r0 = lane / cpr;
-        for (int r = r0; r < 32; r += rpi) {
-          if (wrow0 + r < P.Np) {
-            const uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 256 + ((ch ^ (r & 15)) << 4));
-            *reinterpret_cast<uint4*>(P.z_save + ((int64_t)b * P.Np + wrow0 + r) * D + t * 128 + ch * 8) = v4;
-          }
+        if (h0 + 64 >= width) {                                        // whole step converted: release it to the MMA warp
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&ctl->conv_done[t & 1]);
+          GVIT_TR(12);
         }
-        __syncwarp();
+        if (P.z_save) {                                                // coalesced: 4 whole 128-byte row segments per instr
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = r8 + 4 * i;
+            if (wrow0 + r < P.Np) {
+              const uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4));
+              *reinterpret_cast<uint4*>(P.z_save + ((int64_t)b * P.Np + wrow0 + r) * D + t * 128 + h0 + ch8 * 8) = v4;
+            }
+          }
+          __syncwarp();
+        }
       }
     }
-    // ---- projection epilogue per 64-feature chunk: + bias + residual, bf16, coalesced through the warp staging
-    for (int n = 0; n < nslab; ++n) {
+    // ---- projection epilogue (chunks of parity g): + bias + residual, bf16, coalesced through the warp staging
+    for (int n = g; n < nslab; n += 2) {
       const int buf = n & 1;
-      // residual rows of this warp -> staging (coalesced: 8 lanes per 128-byte row segment)
-      {
-        const int ch = lane & 7, r0 = lane >> 3;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r0 + 4 * i;
-          uint4 v4 = make_uint4(0, 0, 0, 0);
-          if (P.resid && wrow0 + r < P.Np)
-            v4 = *reinterpret_cast<const uint4*>(P.resid + ((int64_t)b * (P.Np + 1) + 1 + wrow0 + r) * D + n * 64 + ch * 8);
-          *reinterpret_cast<uint4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4)) = v4;
-        }
+      for (int i = 0; i < 8; ++i) {
+        const int r = r8 + 4 * i;
+        *reinterpret_cast<uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4)) = rnext[i];
       }
+      load_resid(n + 2, rnext);                                        // next chunk of this warpgroup: in flight meanwhile
       __syncwarp();
+      GVIT_TR(13);
       mbar_wait(&ctl->out_full[buf], (n >> 1) & 1);
       tc_fence_after();
+      GVIT_TR(14);
       float v0[32], v1[32];
       tmem_ld32(tl + T_OUT + buf * 64, v0);
       tmem_ld32(tl + T_OUT + buf * 64 + 32, v1);
@@ -283,8 +315,7 @@ __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_consta
       for (int q = 0; q < 8; ++q) {
         const uint32_t off = lane * 128 + ((q ^ (lane & 7)) << 4);
         const uint4 r4 = *reinterpret_cast<const uint4*>(stg + off);
-        uint4 b4 = make_uint4(0, 0, 0, 0);
-        if (P.bias) b4 = *reinterpret_cast<const uint4*>(P.bias + n * 64 + q * 8);
+        const uint4 b4 = *reinterpret_cast<const uint4*>(&ctl->bias[n * 64 + q * 8]);
         const float* vv = q < 4 ? &v0[8 * q] : &v1[8 * (q - 4)];
         const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
         uint32_t oo[4];
@@ -294,15 +325,12 @@ __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_consta
         *reinterpret_cast<uint4*>(stg + off) = make_uint4(oo[0], oo[1], oo[2], oo[3]);
       }
       __syncwarp();
-      {
-        const int ch = lane & 7, r0 = lane >> 3;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r0 + 4 * i;
-          if (wrow0 + r < P.Np) {
-            const uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4));
-            *reinterpret_cast<uint4*>(P.out + ((int64_t)b * (P.Np + 1) + 1 + wrow0 + r) * D + n * 64 + ch * 8) = v4;
-          }
+      for (int i = 0; i < 8; ++i) {
+        const int r = r8 + 4 * i;
+        if (wrow0 + r < P.Np) {
+          const uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4));
+          *reinterpret_cast<uint4*>(P.out + ((int64_t)b * (P.Np + 1) + 1 + wrow0 + r) * D + n * 64 + ch8 * 8) = v4;
         }
       }
       __syncwarp();
@@ -310,7 +338,7 @@ __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, 512);
+  if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
 template <int KT>
@@ -323,6 +351,8 @@ int launch(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const Params& P, 
 }
 
 }  // namespace
+
+GVIT_TRACE_SETTER(gvit_debug_set_trace_agg)
 
 bool agg3_tc_supported(int Np, int D, int k) {
   return Np >= 16 && Np <= 256 && D >= 64 && D % 64 == 0 && D <= 768 && k <= 16;
