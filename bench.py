@@ -194,7 +194,7 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
         # name: (launch fn(i), algorithmic bytes, flops, bound, launches per training step)
         "knn_fwd": (lambda i: _call("gvit_knn_fwd", _ptr(hs[i % R], off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(vals), _ptr(rnorm), st),
                     tok + B * Np * k * 8, 2.0 * B * Np * Np * D, "hbm", 12),
-        "agg_fwd": (lambda i: _call("gvit_agg_fwd", _ptr(hs[i % R]), B, Np, D, k, dt, _ptr(idxs[i % R][0]), _ptr(idxs[i % R][1]), _ptr(W), _ptr(bias), _ptr(xs[i % R]), _ptr(out), _ptr(w), _ptr(z), st),
+        "agg_fwd": (lambda i: _call("gvit_agg_fwd", _ptr(hs[i % R]), B, Np, D, k, dt, _ptr(idxs[i % R][0]), _ptr(idxs[i % R][1]), _ptr(W), _ptr(bias), _ptr(xs[i % R]), _ptr(out), _ptr(w), _ptr(z), Np * D, st),
                     3 * tok + B * Np * k * 8, 2.0 * B * Np * D * (k + D), "tensor", 12),
         "attn_fwd": (lambda i: _call("gvit_attn_fwd", _ptr(qkvs[i % 2]), B, N, H, 64, 0.125, dt, _ptr(ao), _ptr(lse), st),
                      4 * B * N * D * e + 4 * B * H * N, 4.0 * B * N * N * D, "hbm", 12),
@@ -206,11 +206,11 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
                     3 * tok + B * Np * k * 16, 4.0 * B * Np * k * D, "hbm", 12),
         "knn_bwd": (lambda i: _call("gvit_knn_bwd", _ptr(hs[i % R], off), bs, rs, B, Np, D, k, dt, _ptr(idxs[i % R][0]), _ptr(idxs[i % R][2]), _ptr(dvals), _ptr(rev[i % R][0]), _ptr(rev[i % R][1]), _ptr(out, off), st),
                     3 * tok + B * Np * k * 12, 4.0 * B * Np * k * D, "hbm", 12),
-        "graph_bwd": (lambda i: _call("gvit_graph_bwd", _ptr(hs[i % R], off), bs, rs, B, Np, D, k, dt, _ptr(idxs[i % R][0]), _ptr(idxs[i % R][1]), _ptr(w), _ptr(idxs[i % R][2]), _ptr(xs[i % R], off), _ptr(dvals), _ptr(out, off), st),
+        "graph_bwd": (lambda i: _call("gvit_graph_bwd", _ptr(hs[i % R], off), bs, rs, B, Np, D, k, dt, _ptr(idxs[i % R][0]), _ptr(idxs[i % R][1]), _ptr(w), _ptr(idxs[i % R][2]), _ptr(xs[i % R], off), bs, _ptr(dvals), _ptr(out, off), st),
                       3 * tok + B * Np * k * 20, 6.0 * B * Np * Np * D, "hbm", 12),
         "layernorm_fwd": (lambda i: _call("gvit_layernorm_fwd", _ptr(hs[i % R]), _ptr(gam), _ptr(bet), B * N, D, 1e-5, dt, dt, _ptr(out), _ptr(mean), _ptr(rstd), st),
                           2 * B * N * D * e, 0.0, "hbm", 36),
-        "layernorm_bwd": (lambda i: _call("gvit_layernorm_bwd", _ptr(xs[i % R]), _ptr(hs[i % R]), _ptr(gam), _ptr(mean), _ptr(rstd), B * N, D, dt, dt, _ptr(out), _ptr(dgb[0]), _ptr(dgb[1]), _ptr(ws), st),
+        "layernorm_bwd": (lambda i: _call("gvit_layernorm_bwd", _ptr(xs[i % R]), _ptr(hs[i % R]), _ptr(gam), _ptr(mean), _ptr(rstd), B * N, D, dt, dt, None, _ptr(out), _ptr(dgb[0]), _ptr(dgb[1]), _ptr(ws), st),
                           3 * B * N * D * e, 0.0, "hbm", 36),
     }
     _call("gvit_layernorm_fwd", _ptr(hs[0]), _ptr(gam), _ptr(bet), B * N, D, 1e-5, dt, dt, _ptr(out), _ptr(mean), _ptr(rstd), st)

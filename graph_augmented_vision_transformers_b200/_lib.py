@@ -17,7 +17,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "gvit.h")
 GVIT_F32, GVIT_BF16 = 0, 1
 GVIT_MAX_K = 32
 GVIT_LN_PARTIALS = 296
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 STATUS_NAMES = {0: "GVIT_OK", 1: "GVIT_ERR_SHAPE", 2: "GVIT_ERR_ALIGN", 3: "GVIT_ERR_DTYPE", 4: "GVIT_ERR_CUDA",
                 5: "GVIT_ERR_UNSUPPORTED"}
@@ -46,13 +46,13 @@ SIGNATURES = {
     "gvit_graph_reverse": [_vp, _i, _i, _i, _vp, _vp, _vp],
     "gvit_knn_bwd": [_vp, _i64, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "gvit_agg_gather_fwd": [_vp, _i64, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
-    "gvit_agg_fwd": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "gvit_agg_fwd": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "gvit_agg_bwd": [_vp, _i64, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "gvit_graph_bwd": [_vp, _i64, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "gvit_graph_bwd": [_vp, _i64, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     "gvit_attn_fwd": [_vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp],
     "gvit_attn_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp],
     "gvit_layernorm_fwd": [_vp, _vp, _vp, _i64, _i, _f, _i, _i, _vp, _vp, _vp, _vp],
-    "gvit_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "gvit_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "gvit_dropout_residual_fwd": [_vp, _vp, _i64, _f, _u64, _u64, _i, _i, _vp, _vp, _vp],
     "gvit_dropout_bwd": [_vp, _vp, _i64, _f, _i, _i, _vp, _vp],
     "gvit_gelu_dropout_fwd": [_vp, _i64, _f, _u64, _u64, _i, _vp, _vp, _vp],

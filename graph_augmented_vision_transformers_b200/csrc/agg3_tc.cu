@@ -55,6 +55,7 @@ struct Params {
   __nv_bfloat16* out;
   float* w_save;
   __nv_bfloat16* z_save;
+  int64_t zbs;                              // batch stride of z_save in elements (rows are D apart)
 };
 
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_consta
             const int r = r8 + 4 * i;
             if (wrow0 + r < P.Np) {
               const uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4));
-              *reinterpret_cast<uint4*>(P.z_save + ((int64_t)b * P.Np + wrow0 + r) * D + t * 128 + h0 + ch8 * 8) = v4;
+              *reinterpret_cast<uint4*>(P.z_save + (int64_t)b * P.zbs + (int64_t)(wrow0 + r) * D + t * 128 + h0 + ch8 * 8) = v4;
             }
           }
           __syncwarp();
@@ -359,7 +360,8 @@ bool agg3_tc_supported(int Np, int D, int k) {
 }
 
 int agg3_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, const float* vals, const void* Wg,
-                const void* bias, const void* resid, void* out, float* w_save, void* z_save, cudaStream_t st) {
+                const void* bias, const void* resid, void* out, float* w_save, void* z_save, int64_t z_batch_stride,
+                cudaStream_t st) {
   Params P;
   P.Np = Np; P.D = D; P.k = k;
   P.NT = (Np + 15) & ~15;
@@ -370,6 +372,7 @@ int agg3_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, 
   P.out = static_cast<__nv_bfloat16*>(out);
   P.w_save = w_save;
   P.z_save = static_cast<__nv_bfloat16*>(z_save);
+  P.zbs = z_batch_stride;
 
   CUtensorMap tm_tok, tm_w;
   const __nv_bfloat16* tok = static_cast<const __nv_bfloat16*>(h) + D;   // skip the CLS row (section 9, G0)

@@ -54,6 +54,7 @@ struct Params {
   __nv_bfloat16* out;
   float* w_save;
   __nv_bfloat16* z_save;
+  int64_t zbs;                             // batch stride of z_save in elements (rows are D apart)
 };
 
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(THREADS, 1) agg_tc_kernel(const __grid_constan
       tmem_st16(tZ + st * 64, pk0);
       tmem_st16(tZ + st * 64 + 16, pk1);
       if (P.z_save && nchunk == 0 && valid) {
-        uint4* dst = reinterpret_cast<uint4*>(P.z_save + ((int64_t)b * P.Np + rowg) * P.D + s * 64);
+        uint4* dst = reinterpret_cast<uint4*>(P.z_save + (int64_t)b * P.zbs + (int64_t)rowg * P.D + s * 64);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           dst[q] = make_uint4(pk0[4 * q], pk0[4 * q + 1], pk0[4 * q + 2], pk0[4 * q + 3]);
@@ -266,7 +267,8 @@ bool agg_tc_supported(int Np, int D, int k) {
 }
 
 int agg_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, const float* vals, const void* Wg,
-               const void* bias, const void* resid, void* out, float* w_save, void* z_save, cudaStream_t st) {
+               const void* bias, const void* resid, void* out, float* w_save, void* z_save, int64_t z_batch_stride,
+               cudaStream_t st) {
   Params P;
   P.Np = Np; P.D = D; P.k = k;
   P.NT = (Np + 15) & ~15;
@@ -278,6 +280,7 @@ int agg_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, c
   P.out = static_cast<__nv_bfloat16*>(out);
   P.w_save = w_save;
   P.z_save = static_cast<__nv_bfloat16*>(z_save);
+  P.zbs = z_batch_stride;
 
   CUtensorMap tm_tok, tm_w;
   const __nv_bfloat16* tok = static_cast<const __nv_bfloat16*>(h) + D;   // skip the CLS row (section 9, G0)

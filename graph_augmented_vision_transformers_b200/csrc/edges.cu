@@ -83,14 +83,16 @@ template <typename Tx, typename Ty, int NC>
 __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const Ty* __restrict__ dy, const Tx* __restrict__ x,
                                                         const Tx* __restrict__ gamma, const float* __restrict__ mean,
                                                         const float* __restrict__ rstd, int64_t rows, int D, int slots,
-                                                        Tx* __restrict__ dx, float* __restrict__ partial) {
+                                                        const Tx* __restrict__ dx_add, Tx* __restrict__ dx,
+                                                        float* __restrict__ partial) {
   extern __shared__ __align__(128) uint8_t ring[];
   __shared__ float red[8][256];
   __shared__ float gsm[NC * 256];
   __shared__ __align__(8) uint64_t bars[8][4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t xbytes = D * sizeof(Tx), ybytes = D * sizeof(Ty);
-  const uint32_t xpad = (xbytes + 127u) & ~127u, slot_bytes = xpad + ((ybytes + 127u) & ~127u);
+  const uint32_t xpad = (xbytes + 127u) & ~127u, ypad = (ybytes + 127u) & ~127u;
+  const uint32_t slot_bytes = xpad + ypad + (dx_add ? xpad : 0u);     // optional third stream: gradient to add to dx
   uint8_t* wring = ring + (size_t)warp * slots * slot_bytes;
   for (int i = threadIdx.x; i < NC * 256; i += 256) gsm[i] = i < D ? to_f32(gamma[i]) : 0.f;
   if (lane == 0) {
@@ -101,9 +103,10 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const Ty* __restrict__ d
   const int64_t stride = (int64_t)gridDim.x * 8;
   const int64_t row0 = (int64_t)blockIdx.x * 8 + warp;
   auto issue = [&](int64_t r, int s) {      // lane 0 only
-    bar_expect_tx(&bars[warp][s], xbytes + ybytes);
+    bar_expect_tx(&bars[warp][s], xbytes + ybytes + (dx_add ? xbytes : 0u));
     bulk_copy_g2s(wring + (size_t)s * slot_bytes, x + r * D, xbytes, &bars[warp][s]);
     bulk_copy_g2s(wring + (size_t)s * slot_bytes + xpad, dy + r * D, ybytes, &bars[warp][s]);
+    if (dx_add) bulk_copy_g2s(wring + (size_t)s * slot_bytes + xpad + ypad, dx_add + r * D, xbytes, &bars[warp][s]);
   };
   if (lane == 0)
     for (int s = 0; s < slots; ++s)
@@ -120,11 +123,20 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const Ty* __restrict__ d
     bar_wait(&bars[warp][s], (it / slots) & 1);
     const Tx* xs = reinterpret_cast<const Tx*>(wring + (size_t)s * slot_bytes);
     const Ty* ys = reinterpret_cast<const Ty*>(wring + (size_t)s * slot_bytes + xpad);
+    const Tx* as = reinterpret_cast<const Tx*>(wring + (size_t)s * slot_bytes + xpad + ypad);
     float xv[NC][8], dyv[NC][8];
+    uint4 addv[NC][sizeof(Tx) / 2];                         // the add stream stays packed until the dx store
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const int d0 = lane * 8 + c * 256;
-      if (d0 < D) { load8(xs + d0, xv[c]); load8(ys + d0, dyv[c]); }
+      if (d0 < D) {
+        load8(xs + d0, xv[c]);
+        load8(ys + d0, dyv[c]);
+        if (dx_add) {
+#pragma unroll
+          for (int u = 0; u < (int)(sizeof(Tx) / 2); ++u) addv[c][u] = reinterpret_cast<const uint4*>(as + d0)[u];
+        }
+      }
     }
     __syncwarp();                                           // every lane has its copy: the slot may be refilled
     if (lane == 0 && row + (int64_t)slots * stride < rows) issue(row + (int64_t)slots * stride, s);
@@ -156,6 +168,12 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const Ty* __restrict__ d
         float o[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) o[t] = rs * (dyv[c][t] - s1 - xv[c][t] * s2);
+        if (dx_add) {
+          float a[8];
+          load8(reinterpret_cast<const Tx*>(&addv[c][0]), a);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) o[t] += a[t];
+        }
         store8(dx + row * D + d0, o);
       }
     }
@@ -268,17 +286,19 @@ template <> struct Gelu<true> {
   }
 };
 template <> struct Gelu<false> {
-  // returns Phi(u) and e = exp(-u^2/2)
+  // returns Phi(u) and e = exp(-u^2/2); MUFU.RCP / MUFU.EX2 approximations (1 ulp-ish, far below bf16 resolution):
+  // __frcp_rn compiled to a subroutine call with a divergent slow path
   static __device__ __forceinline__ float cdf(float u, float& e) {
-    const float ax = fabsf(u) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-    e = __expf(-0.5f * u * u);
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float half_q = 0.5f * poly * t * e;          // 0.5 * erfc(|u|/sqrt2)
-    return u >= 0.f ? 1.0f - half_q : half_q;
+    float t, ee;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752f, fabsf(u), 1.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ee) : "f"(u * (u * -0.72134752044448170f)));   // exp(-u^2/2)
+    e = ee;
+    float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);    // coefficients pre-multiplied by 0.5
+    poly = fmaf(poly, t, 0.5f * 1.421413741f);
+    poly = fmaf(poly, t, 0.5f * -0.284496736f);
+    poly = fmaf(poly, t, 0.5f * 0.254829592f);
+    const float half_q = poly * t * ee;                // 0.5 * erfc(|u|/sqrt2)
+    return 0.5f + copysignf(0.5f - half_q, u);         // u >= 0: 1 - half_q, u < 0: half_q
   }
   static __device__ __forceinline__ float fwd(float u) { float e; return u * cdf(u, e); }
   static __device__ __forceinline__ float grad(float u) { float e; const float c = cdf(u, e); return fmaf(u * 0.3989422804014327f, e, c); }
@@ -342,16 +362,17 @@ int ln_fwd_launch(const void* x, const void* gamma, const void* beta, int64_t ro
 }
 template <typename Tx, typename Ty, int NC>
 int ln_bwd_launch(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, int64_t rows,
-                  int D, void* dx, float* partial, int nblk, cudaStream_t st) {
-  // ring: 8 warps x slots x (x row + dy row); aim for two CTAs per SM (<= ~100 KB of dynamic shared memory each)
-  const size_t slot_bytes = (((size_t)D * sizeof(Tx) + 127) & ~size_t(127)) + (((size_t)D * sizeof(Ty) + 127) & ~size_t(127));
+                  int D, const void* dx_add, void* dx, float* partial, int nblk, cudaStream_t st) {
+  // ring: 8 warps x slots x (x row + dy row [+ add row]); aim for two CTAs per SM (<= ~100 KB of dynamic smem each)
+  const size_t xpad = ((size_t)D * sizeof(Tx) + 127) & ~size_t(127);
+  const size_t slot_bytes = xpad + (((size_t)D * sizeof(Ty) + 127) & ~size_t(127)) + (dx_add ? xpad : 0);
   int slots = (int)((100 * 1024) / (8 * slot_bytes));
   slots = slots > 4 ? 4 : (slots < 2 ? 2 : slots);
   const size_t smem = 8 * slots * slot_bytes;
   auto kern = ln_bwd_kernel<Tx, Ty, NC>;
   GVIT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<nblk, 256, smem, st>>>(static_cast<const Ty*>(dy), static_cast<const Tx*>(x), static_cast<const Tx*>(gamma), mean,
-                                rstd, rows, D, slots, static_cast<Tx*>(dx), partial);
+                                rstd, rows, D, slots, static_cast<const Tx*>(dx_add), static_cast<Tx*>(dx), partial);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }
@@ -388,17 +409,17 @@ int layernorm_fwd(const void* x, const void* gamma, const void* beta, int64_t ro
 }
 
 static int ln_bwd_main(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
-                       int64_t rows, int D, int dtype, int y_dtype, void* dx, float* partial_ws, int nblk,
-                       cudaStream_t st) {
-  GVIT_LN_DISPATCH(ln_bwd_launch, dy, x, gamma, mean, rstd, rows, D, dx, partial_ws, nblk, st);
+                       int64_t rows, int D, int dtype, int y_dtype, const void* dx_add, void* dx, float* partial_ws,
+                       int nblk, cudaStream_t st) {
+  GVIT_LN_DISPATCH(ln_bwd_launch, dy, x, gamma, mean, rstd, rows, D, dx_add, dx, partial_ws, nblk, st);
 }
 
 int layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, int64_t rows,
-                  int D, int dtype, int y_dtype, void* dx, float* dgamma, float* dbeta, float* partial_ws,
-                  cudaStream_t st) {
+                  int D, int dtype, int y_dtype, const void* dx_add, void* dx, float* dgamma, float* dbeta,
+                  float* partial_ws, cudaStream_t st) {
   int nblk = (int)((rows + 7) / 8);
   if (nblk > GVIT_LN_PARTIALS) nblk = GVIT_LN_PARTIALS;
-  int rc = ln_bwd_main(dy, x, gamma, mean, rstd, rows, D, dtype, y_dtype, dx, partial_ws, nblk, st);
+  int rc = ln_bwd_main(dy, x, gamma, mean, rstd, rows, D, dtype, y_dtype, dx_add, dx, partial_ws, nblk, st);
   if (rc != GVIT_OK) return rc;
   ln_bwd_reduce_kernel<<<(2 * D * 32 + 255) / 256, 256, 0, st>>>(partial_ws, nblk, D, dgamma, dbeta);
   GVIT_CHECK_LAUNCH();

@@ -72,7 +72,7 @@ int gvit_agg_gather_fwd(const void* p, int64_t batch_stride, int64_t row_stride,
 
 int gvit_agg_fwd(const void* h, int B, int Np, int D, int k, int dtype, const int32_t* idx, const float* vals,
                  const void* Wg, const void* bias, const void* resid, void* out, float* w_save, void* z_save,
-                 void* stream) {
+                 int64_t z_batch_stride, void* stream) {
   TRY(check_dtype(dtype, "agg_fwd"));
   GVIT_REQUIRE(h && idx && vals && Wg && out, GVIT_ERR_SHAPE, "agg_fwd: null pointer");
   GVIT_REQUIRE(B >= 1 && Np >= 1 && k >= 1 && k <= GVIT_MAX_K && k <= Np, GVIT_ERR_SHAPE, "agg_fwd: bad sizes B=%d Np=%d k=%d", B, Np, k);
@@ -82,9 +82,12 @@ int gvit_agg_fwd(const void* h, int B, int Np, int D, int k, int dtype, const in
                "agg_fwd: shape Np=%d D=%d k=%d outside the fused kernels' range", Np, D, k);
   GVIT_REQUIRE(aligned16(h) && aligned16(Wg) && aligned16(out) && (!resid || aligned16(resid)) && (!z_save || aligned16(z_save)),
                GVIT_ERR_ALIGN, "agg_fwd: pointers must be 16-byte aligned");
+  GVIT_REQUIRE(!z_save || (z_batch_stride >= (int64_t)Np * D && z_batch_stride % 8 == 0), GVIT_ERR_ALIGN,
+               "agg_fwd: z_batch_stride=%lld must be >= Np*D and a multiple of 8", (long long)z_batch_stride);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (agg3_tc_supported(Np, D, k))
-    return agg3_fwd_tc(h, B, Np, D, k, idx, vals, Wg, bias, resid, out, w_save, z_save, static_cast<cudaStream_t>(stream));
-  return agg_fwd_tc(h, B, Np, D, k, idx, vals, Wg, bias, resid, out, w_save, z_save, static_cast<cudaStream_t>(stream));
+    return agg3_fwd_tc(h, B, Np, D, k, idx, vals, Wg, bias, resid, out, w_save, z_save, z_batch_stride, st);
+  return agg_fwd_tc(h, B, Np, D, k, idx, vals, Wg, bias, resid, out, w_save, z_save, z_batch_stride, st);
 }
 
 int gvit_agg_bwd(const void* p, int64_t batch_stride, int64_t row_stride, int B, int Np, int D, int k, int dtype,
@@ -100,16 +103,17 @@ int gvit_agg_bwd(const void* p, int64_t batch_stride, int64_t row_stride, int B,
 
 int gvit_graph_bwd(const void* p, int64_t batch_stride, int64_t row_stride, int B, int Np, int D, int k, int dtype,
                    const int32_t* idx, const float* vals, const float* w, const float* rnorm, const void* dz,
-                   float* dvals, void* dp, void* stream) {
+                   int64_t dz_batch_stride, float* dvals, void* dp, void* stream) {
   TRY(check_dtype(dtype, "graph_bwd"));
   TRY(check_tokens("graph_bwd", p, batch_stride, row_stride, B, Np, D, k));
   GVIT_REQUIRE(idx && vals && w && rnorm && dz && dvals && dp, GVIT_ERR_SHAPE, "graph_bwd: null pointer");
-  GVIT_REQUIRE(aligned16(dz) && aligned16(dp), GVIT_ERR_ALIGN, "graph_bwd: dz/dp must be 16-byte aligned");
+  GVIT_REQUIRE(aligned16(dz) && aligned16(dp) && dz_batch_stride >= (int64_t)Np * D && dz_batch_stride % 8 == 0, GVIT_ERR_ALIGN,
+               "graph_bwd: dz/dp must be 16-byte aligned, dz_batch_stride >= Np*D and a multiple of 8");
   GVIT_REQUIRE(dtype == GVIT_BF16 && graph_bwd_tc_supported(Np, D, k), GVIT_ERR_UNSUPPORTED,
                "graph_bwd: the fused backward is bf16-only with Np=%d D=%d k=%d in range; compose gvit_graph_reverse, "
                "gvit_agg_bwd and gvit_knn_bwd instead", Np, D, k);
   Tokens t{p, batch_stride, row_stride, B, Np, D};
-  return graph_bwd_tc(t, k, idx, vals, w, rnorm, dz, dvals, dp, static_cast<cudaStream_t>(stream));
+  return graph_bwd_tc(t, k, idx, vals, w, rnorm, dz, dz_batch_stride, dvals, dp, static_cast<cudaStream_t>(stream));
 }
 
 int gvit_attn_fwd(const void* qkv, int B, int N, int H, int dh, float scale, int dtype, void* out, float* lse,
@@ -152,13 +156,15 @@ int gvit_layernorm_fwd(const void* x, const void* gamma, const void* beta, int64
 }
 
 int gvit_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
-                       int64_t rows, int D, int dtype, int y_dtype, void* dx, float* dgamma, float* dbeta,
-                       float* partial_ws, void* stream) {
+                       int64_t rows, int D, int dtype, int y_dtype, const void* dx_add, void* dx, float* dgamma,
+                       float* dbeta, float* partial_ws, void* stream) {
   TRY(check_ln_pair(dtype, y_dtype, "layernorm_bwd"));
   GVIT_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && partial_ws, GVIT_ERR_SHAPE, "layernorm_bwd: null pointer");
   GVIT_REQUIRE(rows >= 1 && D >= 8 && D % 8 == 0 && D <= 1024, GVIT_ERR_SHAPE, "layernorm_bwd: rows=%lld D=%d (D %% 8 == 0, D <= 1024)", (long long)rows, D);
-  GVIT_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(gamma), GVIT_ERR_ALIGN, "layernorm_bwd: 16-byte alignment required");
-  return layernorm_bwd(dy, x, gamma, mean, rstd, rows, D, dtype, y_dtype, dx, dgamma, dbeta, partial_ws, static_cast<cudaStream_t>(stream));
+  GVIT_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(gamma) && (!dx_add || aligned16(dx_add)), GVIT_ERR_ALIGN,
+               "layernorm_bwd: 16-byte alignment required");
+  return layernorm_bwd(dy, x, gamma, mean, rstd, rows, D, dtype, y_dtype, dx_add, dx, dgamma, dbeta, partial_ws,
+                       static_cast<cudaStream_t>(stream));
 }
 
 int gvit_dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, uint64_t seed, uint64_t offset,

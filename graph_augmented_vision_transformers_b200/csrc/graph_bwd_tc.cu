@@ -360,11 +360,11 @@ bool graph_bwd_tc_supported(int Np, int D, int k) {
 }
 
 int graph_bwd_tc(const Tokens& t, int k, const int32_t* idx, const float* vals, const float* w, const float* rnorm,
-                 const void* dz, float* dvals, void* dp, cudaStream_t st) {
+                 const void* dz, int64_t dz_batch_stride, float* dvals, void* dp, cudaStream_t st) {
   const int NT = (t.Np + 15) & ~15;
   GVIT_REQUIRE(t.B <= 65535, GVIT_ERR_SHAPE, "graph_bwd: batch %d exceeds the grid limit 65535", t.B);
   CUtensorMap tm_dz, tm_p, tm_dp;
-  int rc = make_tmap_bf16_3d(&tm_dz, dz, t.D, t.Np, t.B, t.D, (uint64_t)t.Np * t.D, NT);
+  int rc = make_tmap_bf16_3d(&tm_dz, dz, t.D, t.Np, t.B, t.D, (uint64_t)dz_batch_stride, NT);
   if (rc != GVIT_OK) return rc;
   rc = make_tmap_bf16_3d(&tm_p, t.ptr, t.D, t.Np, t.B, t.row_stride, t.batch_stride, NT);
   if (rc != GVIT_OK) return rc;

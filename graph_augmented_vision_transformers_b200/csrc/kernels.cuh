@@ -30,12 +30,14 @@ int knn_fwd_tc(const Tokens& p, int k, int32_t* idx, float* vals, float* rnorm, 
 bool agg_tc_supported(int Np, int D, int k);    // v2 kernel (agg_tc.cu): D up to 1024
 bool agg3_tc_supported(int Np, int D, int k);   // v3 kernel (agg3_tc.cu): whole Z tile resident in TMEM, D <= 768
 int agg3_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, const float* vals, const void* Wg,
-                const void* bias, const void* resid, void* out, float* w_save, void* z_save, cudaStream_t st);
+                const void* bias, const void* resid, void* out, float* w_save, void* z_save, int64_t z_batch_stride,
+                cudaStream_t st);
 int agg_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, const float* vals, const void* Wg,
-               const void* bias, const void* resid, void* out, float* w_save, void* z_save, cudaStream_t st);
+               const void* bias, const void* resid, void* out, float* w_save, void* z_save, int64_t z_batch_stride,
+               cudaStream_t st);
 bool graph_bwd_tc_supported(int Np, int D, int k);
 int graph_bwd_tc(const Tokens& p, int k, const int32_t* idx, const float* vals, const float* w, const float* rnorm,
-                 const void* dz, float* dvals, void* dp, cudaStream_t st);
+                 const void* dz, int64_t dz_batch_stride, float* dvals, void* dp, cudaStream_t st);
 bool attn_fwd_tc_supported(int N, int dh);
 bool attn_bwd_tc_supported(int N, int dh);
 int attn_fwd_tc(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, cudaStream_t st);
@@ -46,8 +48,8 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
 int layernorm_fwd(const void* x, const void* gamma, const void* beta, int64_t rows, int D, float eps, int dtype,
                   int y_dtype, void* y, float* mean, float* rstd, cudaStream_t st);
 int layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, int64_t rows,
-                  int D, int dtype, int y_dtype, void* dx, float* dgamma, float* dbeta, float* partial_ws,
-                  cudaStream_t st);
+                  int D, int dtype, int y_dtype, const void* dx_add, void* dx, float* dgamma, float* dbeta,
+                  float* partial_ws, cudaStream_t st);
 int dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, uint64_t seed, uint64_t offset,
                          int dtype, int y_dtype, void* out, uint8_t* keep_mask, cudaStream_t st);
 int dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, int y_dtype, void* dy,

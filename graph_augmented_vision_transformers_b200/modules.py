@@ -39,6 +39,12 @@ class LayerNorm(nn.LayerNorm):
             raise NotImplementedError("libgvit LayerNorm is affine over the last dimension only")
         return ops.layer_norm(x, self.weight, self.bias, self.eps)
 
+    def forward_with_residual(self, x):
+        """``(x, LN(x))`` for ``x + f(LN(x))``: use the returned x in the residual add (see ``ops.pre_norm``)."""
+        if not self.elementwise_affine or len(self.normalized_shape) != 1:
+            raise NotImplementedError("libgvit LayerNorm is affine over the last dimension only")
+        return ops.pre_norm(x, self.weight, self.bias, self.eps)
+
 
 class Attention(nn.Module):
     def __init__(self, dim, num_heads=8, qkv_bias=False, attn_drop=0., proj_drop=0.):
@@ -142,12 +148,22 @@ class Block(nn.Module):
         sub-layer outputs through module hooks (Grad-CAM hooks blocks.11.attn, gradcam.py:233-236)."""
         if not isinstance(self.drop_path, nn.Identity):
             return False
-        subs = [self.attn, self.mlp] + ([self.graph] if self.graph_mode is not None else [])
+        subs = [self.attn, self.mlp, self.norm1, self.norm2] + ([self.graph, self.norm_g] if self.graph_mode is not None else [])
         return not any(m._forward_hooks or m._backward_hooks or m._forward_pre_hooks for m in subs)
 
     def forward(self, x):
         if self._foldable():
             # every shipped configuration: the three residual adds are folded into the producing kernels
+            if torch.is_grad_enabled() and x.requires_grad:
+                # training: (x, LN(x)) leave through one autograd node, so the residual-path gradient is added inside
+                # the LayerNorm backward kernel instead of by a separate add
+                x, y = self.norm1.forward_with_residual(x)
+                x = self.attn(y, resid=x)
+                if self.graph_mode is not None:
+                    x, y = self.norm_g.forward_with_residual(x)
+                    x = self.graph(y, resid=x)
+                x, y = self.norm2.forward_with_residual(x)
+                return self.mlp(y, resid=x)
             x = self.attn(self.norm1(x), resid=x)
             if self.graph_mode is not None:
                 x = self.graph(self.norm_g(x), resid=x)

@@ -23,7 +23,7 @@ import torch.nn.functional as F
 from . import _lib
 from ._lib import GVIT_BF16, GVIT_F32, GVIT_LN_PARTIALS
 
-__all__ = ["attention_core", "layer_norm", "dropout_add", "gelu_dropout", "knn_graph", "graph_reverse", "patch_graph",
+__all__ = ["attention_core", "layer_norm", "pre_norm", "dropout_add", "gelu_dropout", "knn_graph", "graph_reverse", "patch_graph",
            "agg_gather", "launch_count", "reset_launch_count"]
 
 # kernels launched through the C ABI since the last reset (bench.py reports it as gpu_launches)
@@ -147,18 +147,43 @@ class _LayerNorm(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, mean, rstd = ctx.saved_tensors
-        D = x.shape[-1]
-        rows = x.numel() // D
-        dy = dy.contiguous()
-        dx = torch.empty_like(x)
-        # two separate tensors: AccumulateGrad steals a whole tensor but has to clone a view
-        dgamma = torch.empty(D, dtype=torch.float32, device=x.device)
-        dbeta = torch.empty(D, dtype=torch.float32, device=x.device)
-        ws = torch.empty(2 * GVIT_LN_PARTIALS * D, dtype=torch.float32, device=x.device)
-        _call("gvit_layernorm_bwd", _ptr(dy), _ptr(x), _ptr(weight), _ptr(mean), _ptr(rstd), rows, D, _dtype_code(x),
-              ctx.y_code, _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(ws), _stream())
-        return dx, dgamma.to(weight.dtype), dbeta.to(weight.dtype), None, None
+        dx, dgamma, dbeta = _layer_norm_backward(ctx, dy, None)
+        return dx, dgamma, dbeta, None, None
+
+
+def _layer_norm_backward(ctx, dy, dx_add):
+    x, weight, mean, rstd = ctx.saved_tensors
+    D = x.shape[-1]
+    rows = x.numel() // D
+    dy = dy.contiguous()
+    dx = torch.empty_like(x)
+    if dx_add is not None:
+        dx_add = dx_add.to(x.dtype).contiguous()
+    # two separate tensors: AccumulateGrad steals a whole tensor but has to clone a view
+    dgamma = torch.empty(D, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(D, dtype=torch.float32, device=x.device)
+    ws = torch.empty(2 * GVIT_LN_PARTIALS * D, dtype=torch.float32, device=x.device)
+    _call("gvit_layernorm_bwd", _ptr(dy), _ptr(x), _ptr(weight), _ptr(mean), _ptr(rstd), rows, D, _dtype_code(x),
+          ctx.y_code, _ptr(dx_add), _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(ws), _stream())
+    return dx, dgamma.to(weight.dtype), dbeta.to(weight.dtype)
+
+
+class _PreNorm(torch.autograd.Function):
+    """(x, LayerNorm(x)): the first output is x itself, handed to the residual add of the sub-layer.  Because both
+    uses of x leave through ONE node, its backward receives the residual-path gradient together with dy and the
+    LayerNorm backward kernel adds it to dx in the same pass (autograd would otherwise launch a separate add)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, y_code):
+        y = _LayerNorm.forward(ctx, x, weight, bias, eps, y_code)
+        return x.view_as(x), y
+
+    @staticmethod
+    def backward(ctx, dres, dy):
+        if dy is None:                      # the branch was unused: only the residual path carries gradient
+            return dres, None, None, None, None
+        dx, dgamma, dbeta = _layer_norm_backward(ctx, dy, dres)
+        return dx, dgamma, dbeta, None, None
 
 
 def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
@@ -173,6 +198,18 @@ def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: f
     y_code = GVIT_BF16 if (x.dtype == torch.bfloat16 or torch.is_autocast_enabled("cuda")) else GVIT_F32
     with torch.autocast("cuda", enabled=False):
         return _LayerNorm.apply(x.contiguous(), weight.to(x.dtype), bias.to(x.dtype), float(eps), y_code)
+
+
+def pre_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5):
+    """``(x, layer_norm(x))`` for a pre-norm residual sub-layer ``x + f(LN(x))`` (vit.py:117-118): use the returned x
+    for the residual add.  Same values as ``layer_norm``; the backward folds the residual-path gradient into the
+    LayerNorm backward kernel."""
+    _check_cuda(x, weight, bias)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.to(torch.bfloat16 if x.dtype == torch.float16 else torch.float32)
+    y_code = GVIT_BF16 if (x.dtype == torch.bfloat16 or torch.is_autocast_enabled("cuda")) else GVIT_F32
+    with torch.autocast("cuda", enabled=False):
+        return _PreNorm.apply(x.contiguous(), weight.to(x.dtype), bias.to(x.dtype), float(eps), y_code)
 
 
 def _draw_seed() -> int:
@@ -347,12 +384,17 @@ class _PatchGraph(torch.autograd.Function):
         rnorm = torch.empty((B, Np), dtype=torch.float32, device=h.device)
         _call("gvit_knn_fwd", _ptr(h, off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(vals), _ptr(rnorm), st)
         w = torch.empty((B, Np, k), dtype=torch.float32, device=h.device)
-        z = torch.empty((B, Np, D), dtype=h.dtype, device=h.device)
         if fused_agg_available(h.dtype, Np, D, k):
             out = torch.empty_like(h)
+            # z is laid out like h (zero CLS row) so that the weight / input gradients are plain GEMMs over all
+            # B*(1+Np) rows of dout - slicing the CLS row off would cost a copy of dout per layer
+            zf = torch.empty_like(h)
+            zf[:, 0].zero_()
             _call("gvit_agg_fwd", _ptr(h), B, Np, D, k, dt, _ptr(idx), _ptr(vals), _ptr(weight), _ptr(bias),
-                  _ptr(resid), _ptr(out), _ptr(w), _ptr(z), st)
+                  _ptr(resid), _ptr(out), _ptr(w), _ptr(zf, off), bs, st)
+            z = zf
         else:
+            z = torch.empty((B, Np, D), dtype=h.dtype, device=h.device)
             # fp32 parity path: fused gather + softmax kernel, then the projection as a library GEMM
             _call("gvit_agg_gather_fwd", _ptr(h, off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(vals), _ptr(w),
                   _ptr(z), st)
@@ -372,6 +414,24 @@ class _PatchGraph(torch.autograd.Function):
         dt = _dtype_code(h)
         st = _stream()
         dout = dout.contiguous()
+        dresid = dout if ctx.has[1] else None
+        if z.shape[1] == Np + 1 and fused_graph_bwd_available(h.dtype, Np, D, k):
+            # bf16: z / dz laid out like h; GEMMs over all rows (the CLS row of z is zero, the CLS row of dz is unused),
+            # then both sparse stages as two per-image tensor-core GEMMs (no reverse adjacency)
+            d2 = dout.view(B * (Np + 1), D)
+            dweight = d2.t() @ z.view(B * (Np + 1), D) if ctx.needs_input_grad[1] else None
+            dbias = (d2.sum(0) - dout[:, 0].sum(0)) if (ctx.has[0] and ctx.needs_input_grad[2]) else None
+            dh = None
+            if ctx.needs_input_grad[0]:
+                dz = d2 @ weight                                   # (B*(1+Np), D)
+                dvals = torch.empty((B, Np, k), dtype=torch.float32, device=h.device)
+                dh = torch.empty_like(h)
+                dh[:, 0].zero_()
+                _call("gvit_graph_bwd", _ptr(h, off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(vals), _ptr(w),
+                      _ptr(rnorm), _ptr(dz, off), bs, _ptr(dvals), _ptr(dh, off), st)
+            return dh, dweight, dbias, dresid, None
+        if z.shape[1] == Np + 1:
+            z = z[:, 1:].contiguous()
         dy = dout[:, 1:, :]
         dy2 = dy.reshape(B * Np, D)
         dweight = dy2.t() @ z.view(B * Np, D) if ctx.needs_input_grad[1] else None
@@ -382,11 +442,6 @@ class _PatchGraph(torch.autograd.Function):
             dvals = torch.empty((B, Np, k), dtype=torch.float32, device=h.device)
             dh = torch.empty_like(h)
             dh[:, 0].zero_()
-            if fused_graph_bwd_available(h.dtype, Np, D, k):
-                # bf16: both sparse stages as two per-image tensor-core GEMMs, no reverse adjacency
-                _call("gvit_graph_bwd", _ptr(h, off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(vals), _ptr(w),
-                      _ptr(rnorm), _ptr(dz), _ptr(dvals), _ptr(dh, off), st)
-                return dh, dweight, dbias, (dout if ctx.has[1] else None), None
             rev_ptr = torch.empty((B, Np + 1), dtype=torch.int32, device=h.device)
             rev_src = torch.empty((B, Np * k), dtype=torch.int32, device=h.device)
             _call("gvit_graph_reverse", _ptr(idx), B, Np, k, _ptr(rev_ptr), _ptr(rev_src), st)
@@ -394,7 +449,6 @@ class _PatchGraph(torch.autograd.Function):
                   _ptr(rev_src), _ptr(dvals), _ptr(dh, off), st)
             _call("gvit_knn_bwd", _ptr(h, off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(rnorm), _ptr(dvals),
                   _ptr(rev_ptr), _ptr(rev_src), _ptr(dh, off), st)
-        dresid = dout if ctx.has[1] else None
         return dh, dweight, dbias, dresid, None
 
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GVIT_ABI_VERSION 3
+#define GVIT_ABI_VERSION 4
 #if defined(__GNUC__)
 #define GVIT_API __attribute__((visibility("default")))
 #else
@@ -86,11 +86,13 @@ GVIT_API int gvit_agg_gather_fwd(const void* p, int64_t batch_stride, int64_t ro
  * aggregated tile kept on chip (shared memory / TMEM) between the two GEMMs; out[b,0,:] = resid[b,0,:]
  * (CLS row untouched, section 9 G0).  h/resid/out are (B,1+Np,D) contiguous; Wg is (D,D) row-major
  * (nn.Linear weight: out_features x in_features); bias may be NULL; resid may be NULL (treated as 0).
- * w_save ((B,Np,k) fp32) and z_save ((B,Np,D) dtype) may be NULL (inference); training saves them.
+ * w_save ((B,Np,k) fp32) and z_save may be NULL (inference); training saves them.  z_save holds the aggregated
+ * tokens z = A~ p: row i of image b at z_save[b*z_batch_stride + i*D] - pass z_full + D with stride (1+Np)*D to lay it
+ * out like h (CLS row left to the caller), which lets the weight gradient run over all (B*(1+Np)) rows without a copy.
  * bf16 only (tcgen05); D % 64 == 0, D <= 1024, Np <= 1024. */
 GVIT_API int gvit_agg_fwd(const void* h, int B, int Np, int D, int k, int dtype, const int32_t* idx, const float* vals,
                  const void* Wg, const void* bias, const void* resid, void* out, float* w_save, void* z_save,
-                 void* stream);
+                 int64_t z_batch_stride, void* stream);
 
 /* Backward of G4+G5 given dz = dY Wg (the two GEMM gradients dWg, dz are plain library GEMMs on the host
  * side): dvals (B,Np,k) fp32 and dp (strided like p, WRITTEN, dtype). */
@@ -101,12 +103,13 @@ GVIT_API int gvit_agg_bwd(const void* p, int64_t batch_stride, int64_t row_strid
 /* Fused backward of G1-G5 for bf16 on the tensor cores (no reverse adjacency needed): given dz = dY Wg it writes
  * dvals (B,Np,k) fp32 - the gradient w.r.t. the selected similarities - and dp (strided like p, WRITTEN in full):
  * dp = A~^T dz  +  the gradient through the cosine similarities and the L2 normalisation.  `vals` are the saved
- * similarities of gvit_knn_fwd, `w` the saved softmax weights, `rnorm` the saved reciprocal norms.
+ * similarities of gvit_knn_fwd, `w` the saved softmax weights, `rnorm` the saved reciprocal norms; dz row i of image b
+ * is at dz[b*dz_batch_stride + i*D].
  * bf16 only; returns GVIT_ERR_UNSUPPORTED outside the kernel's range (use gvit_graph_reverse + gvit_agg_bwd +
  * gvit_knn_bwd there, which also serve fp32).  gvit_describe_path("graph_bwd", ...) tells which applies. */
 GVIT_API int gvit_graph_bwd(const void* p, int64_t batch_stride, int64_t row_stride, int B, int Np, int D, int k, int dtype,
                    const int32_t* idx, const float* vals, const float* w, const float* rnorm, const void* dz,
-                   float* dvals, void* dp, void* stream);
+                   int64_t dz_batch_stride, float* dvals, void* dp, void* stream);
 
 /* ---- a2: attention core, replaces /root/reference/src/models/vit.py:59-69 -------------------
  * qkv : the packed projection output of vit.py:59, (B,N,3,H,dh) contiguous - consumed in place, no
@@ -126,11 +129,13 @@ GVIT_API int gvit_attn_bwd(const void* qkv, const void* out, const void* dout, c
  * folded into the kernel. */
 GVIT_API int gvit_layernorm_fwd(const void* x, const void* gamma, const void* beta, int64_t rows, int D, float eps, int dtype,
                        int y_dtype, void* y, float* mean, float* rstd, void* stream);
-/* dgamma/dbeta are fp32 (D); partial_ws is an fp32 workspace of 2*GVIT_LN_PARTIALS*D floats. */
+/* dgamma/dbeta are fp32 (D); partial_ws is an fp32 workspace of 2*GVIT_LN_PARTIALS*D floats.  dx_add (nullable, type
+ * of dx) is added to dx: the gradient that reaches x through the residual path of vit.py:117-118, folded into this
+ * pass instead of a separate add kernel. */
 enum { GVIT_LN_PARTIALS = 296 };
 GVIT_API int gvit_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
-                       int64_t rows, int D, int dtype, int y_dtype, void* dx, float* dgamma, float* dbeta,
-                       float* partial_ws, void* stream);
+                       int64_t rows, int D, int dtype, int y_dtype, const void* dx_add, void* dx, float* dgamma,
+                       float* dbeta, float* partial_ws, void* stream);
 /* out = resid + dropout(y, p) with a Philox-4x32-10 keep mask generated from (seed, offset) - the proj_drop +
  * residual edge of vit.py:71,117 (also pos_drop, vit.py:212, with resid NULL).  p == 0 degenerates to an add.
  * dtype: type of resid / out (the residual stream); y_dtype: type of y (the branch) - same pairing rule as LayerNorm;

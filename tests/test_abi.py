@@ -15,7 +15,7 @@ DECLS = re.findall(r"GVIT_API\s+[\w\s\*]+?\b(gvit_\w+)\s*\(([^;]*?)\)\s*;", HEAD
 def test_header_declares_the_expected_surface():
     names = [n for n, _ in DECLS]
     for must in ("gvit_knn_fwd", "gvit_knn_bwd", "gvit_graph_reverse", "gvit_agg_fwd", "gvit_agg_gather_fwd",
-                 "gvit_agg_bwd", "gvit_attn_fwd", "gvit_attn_bwd", "gvit_layernorm_fwd", "gvit_layernorm_bwd",
+                 "gvit_agg_bwd", "gvit_graph_bwd", "gvit_attn_fwd", "gvit_attn_bwd", "gvit_layernorm_fwd", "gvit_layernorm_bwd",
                  "gvit_dropout_residual_fwd", "gvit_dropout_bwd", "gvit_gelu_dropout_fwd", "gvit_gelu_dropout_bwd",
                  "gvit_version", "gvit_last_error_string"):
         assert must in names
@@ -55,7 +55,9 @@ def test_validation_errors_are_loud_and_need_no_gpu():
     with pytest.raises(_lib.GvitError, match="GVIT_ERR_DTYPE"):            # bf16 stream with an fp32 branch is not a pairing
         _lib.call("gvit_layernorm_fwd", 16, 16, 16, 1, 64, 1e-5, _lib.GVIT_BF16, _lib.GVIT_F32, 16, 16, 16, None)
     with pytest.raises(_lib.GvitError, match="GVIT_ERR_UNSUPPORTED"):
-        _lib.call("gvit_agg_fwd", 16, 1, 16, 64, 4, _lib.GVIT_F32, 16, 16, 16, None, None, 16, None, None, None)
+        _lib.call("gvit_agg_fwd", 16, 1, 16, 64, 4, _lib.GVIT_F32, 16, 16, 16, None, None, 16, None, None, 0, None)
+    with pytest.raises(_lib.GvitError, match="GVIT_ERR_UNSUPPORTED"):      # the fused graph backward is bf16-only
+        _lib.call("gvit_graph_bwd", 16, 1024, 64, 1, 16, 64, 4, _lib.GVIT_F32, 16, 16, 16, 16, 16, 1024, 16, 16, None)
 
 
 def test_describe_path_routes_bf16_to_tcgen05():
@@ -63,3 +65,5 @@ def test_describe_path_routes_bf16_to_tcgen05():
     assert _lib.describe_path("knn", _lib.GVIT_F32, 196, 768) == "knn:fp32-fma"
     assert _lib.describe_path("agg", _lib.GVIT_BF16, 196, 768) == "agg:tcgen05+tma"
     assert _lib.describe_path("attn_fwd", _lib.GVIT_BF16, 197, 64) == "attn_fwd:tcgen05+tma"
+    assert _lib.describe_path("graph_bwd", _lib.GVIT_BF16, 196, 768) == "graph_bwd:tcgen05+tma"
+    assert _lib.describe_path("graph_bwd", _lib.GVIT_BF16, 576, 1024) == "graph_bwd:reverse-csr+gather"

@@ -159,7 +159,7 @@ def test_bf16_fused_backward_matches_gather_backward(B, Np, D, k):
     dvals = torch.empty(B, Np, k, device=DEV)
     dh = torch.zeros_like(hd)
     _call("gvit_graph_bwd", _ptr(hd, off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(vals), _ptr(w), _ptr(rnorm), _ptr(dz),
-          _ptr(dvals), _ptr(dh, off), st)
+          Np * D, _ptr(dvals), _ptr(dh, off), st)
     assert rel_err(dvals, dvals_ref) < 1e-4
     assert rel_err(dh, dh_ref.float()) < 1e-2
     assert float(dh[:, 0].abs().max()) == 0.0
