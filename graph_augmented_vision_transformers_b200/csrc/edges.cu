@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const Ty* __restrict__ d
                                                         const Tx* __restrict__ dx_add, Tx* __restrict__ dx,
                                                         float* __restrict__ partial) {
   extern __shared__ __align__(128) uint8_t ring[];
-  __shared__ float red[8][256];
+  float (*red)[256] = reinterpret_cast<float (*)[256]>(ring);   // the ring is dead when the final reduction runs
   __shared__ float gsm[NC * 256];
   __shared__ __align__(8) uint64_t bars[8][4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -125,21 +125,18 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const Ty* __restrict__ d
     const Ty* ys = reinterpret_cast<const Ty*>(wring + (size_t)s * slot_bytes + xpad);
     const Tx* as = reinterpret_cast<const Tx*>(wring + (size_t)s * slot_bytes + xpad + ypad);
     float xv[NC][8], dyv[NC][8];
-    uint4 addv[NC][sizeof(Tx) / 2];                         // the add stream stays packed until the dx store
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const int d0 = lane * 8 + c * 256;
       if (d0 < D) {
         load8(xs + d0, xv[c]);
         load8(ys + d0, dyv[c]);
-        if (dx_add) {
-#pragma unroll
-          for (int u = 0; u < (int)(sizeof(Tx) / 2); ++u) addv[c][u] = reinterpret_cast<const uint4*>(as + d0)[u];
-        }
       }
     }
-    __syncwarp();                                           // every lane has its copy: the slot may be refilled
-    if (lane == 0 && row + (int64_t)slots * stride < rows) issue(row + (int64_t)slots * stride, s);
+    if (!dx_add) {                                          // x / dy live in registers now: refill the slot at once
+      __syncwarp();
+      if (lane == 0 && row + (int64_t)slots * stride < rows) issue(row + (int64_t)slots * stride, s);
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -168,16 +165,21 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const Ty* __restrict__ d
         float o[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) o[t] = rs * (dyv[c][t] - s1 - xv[c][t] * s2);
-        if (dx_add) {
+        if (dx_add) {                                       // read from the slot: no registers held across the row
           float a[8];
-          load8(reinterpret_cast<const Tx*>(&addv[c][0]), a);
+          load8(as + d0, a);
 #pragma unroll
           for (int t = 0; t < 8; ++t) o[t] += a[t];
         }
         store8(dx + row * D + d0, o);
       }
     }
+    if (dx_add) {                                           // the add row was read from the slot just above
+      __syncwarp();
+      if (lane == 0 && row + (int64_t)slots * stride < rows) issue(row + (int64_t)slots * stride, s);
+    }
   }
+  __syncthreads();                                          // all warps out of the ring before it is reused below
   // reduce the 8 warps' partials column by column through shared memory, 256 columns at a time
   for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
@@ -366,9 +368,10 @@ int ln_bwd_launch(const void* dy, const void* x, const void* gamma, const float*
   // ring: 8 warps x slots x (x row + dy row [+ add row]); aim for two CTAs per SM (<= ~100 KB of dynamic smem each)
   const size_t xpad = ((size_t)D * sizeof(Tx) + 127) & ~size_t(127);
   const size_t slot_bytes = xpad + (((size_t)D * sizeof(Ty) + 127) & ~size_t(127)) + (dx_add ? xpad : 0);
-  int slots = (int)((100 * 1024) / (8 * slot_bytes));
+  int slots = (int)((109 * 1024) / (8 * slot_bytes));
   slots = slots > 4 ? 4 : (slots < 2 ? 2 : slots);
-  const size_t smem = 8 * slots * slot_bytes;
+  size_t smem = 8 * slots * slot_bytes;
+  if (smem < 8 * 256 * sizeof(float)) smem = 8 * 256 * sizeof(float);   // also hosts the final 8 x 256 reduction buffer
   auto kern = ln_bwd_kernel<Tx, Ty, NC>;
   GVIT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<nblk, 256, smem, st>>>(static_cast<const Ty*>(dy), static_cast<const Tx*>(x), static_cast<const Tx*>(gamma), mean,
