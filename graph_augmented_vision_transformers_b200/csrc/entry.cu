@@ -167,6 +167,14 @@ int gvit_layernorm_bwd(const void* dy, const void* x, const void* gamma, const f
                        static_cast<cudaStream_t>(stream));
 }
 
+int gvit_colsum(const void* x, int64_t rows, int D, int dtype, float* out, float* partial_ws, void* stream) {
+  TRY(check_dtype(dtype, "colsum"));
+  GVIT_REQUIRE(x && out && partial_ws, GVIT_ERR_SHAPE, "colsum: null pointer");
+  GVIT_REQUIRE(rows >= 1 && D >= 8 && D % 8 == 0, GVIT_ERR_SHAPE, "colsum: rows=%lld D=%d (D %% 8 == 0)", (long long)rows, D);
+  GVIT_REQUIRE(aligned16(x), GVIT_ERR_ALIGN, "colsum: x must be 16-byte aligned");
+  return colsum(x, rows, D, dtype, out, partial_ws, static_cast<cudaStream_t>(stream));
+}
+
 int gvit_dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, uint64_t seed, uint64_t offset,
                               int dtype, int y_dtype, void* out, uint8_t* keep_mask, void* stream) {
   TRY(check_ln_pair(dtype, y_dtype, "dropout_residual_fwd"));

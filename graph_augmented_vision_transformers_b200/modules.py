@@ -46,6 +46,13 @@ class LayerNorm(nn.LayerNorm):
         return ops.pre_norm(x, self.weight, self.bias, self.eps)
 
 
+def _linear(mod: nn.Linear, x):
+    """mod(x) through ops.linear (libgvit bias gradient) unless somebody hooked the Linear module itself."""
+    if mod._forward_hooks or mod._forward_pre_hooks or mod._backward_hooks or mod._backward_pre_hooks:
+        return mod(x)
+    return ops.linear(x, mod.weight, mod.bias)
+
+
 class Attention(nn.Module):
     def __init__(self, dim, num_heads=8, qkv_bias=False, attn_drop=0., proj_drop=0.):
         super().__init__()
@@ -62,8 +69,8 @@ class Attention(nn.Module):
         if self.training and self.attn_drop.p > 0:
             # 0 in every configuration the reference ships (vit.py:127; scripts/train.py never sets it)
             raise NotImplementedError("attn_drop > 0 is not implemented by the fused attention kernel")
-        o = ops.attention_core(self.qkv(x), self.num_heads, self.scale)
-        return ops.dropout_add(self.proj(o), resid, self.proj_drop.p, self.training)
+        o = ops.attention_core(_linear(self.qkv, x), self.num_heads, self.scale)
+        return ops.dropout_add(_linear(self.proj, o), resid, self.proj_drop.p, self.training)
 
 
 class Mlp(nn.Module):
@@ -77,8 +84,8 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x, resid=None):
-        x = ops.gelu_dropout(self.fc1(x), self.drop.p, self.training)        # act + drop in one pass
-        return ops.dropout_add(self.fc2(x), resid, self.drop.p, self.training)
+        x = ops.gelu_dropout(_linear(self.fc1, x), self.drop.p, self.training)        # act + drop in one pass
+        return ops.dropout_add(_linear(self.fc2, x), resid, self.drop.p, self.training)
 
 
 class DropPath(nn.Module):

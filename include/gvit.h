@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GVIT_ABI_VERSION 4
+#define GVIT_ABI_VERSION 5
 #if defined(__GNUC__)
 #define GVIT_API __attribute__((visibility("default")))
 #else
@@ -136,6 +136,11 @@ enum { GVIT_LN_PARTIALS = 296 };
 GVIT_API int gvit_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
                        int64_t rows, int D, int dtype, int y_dtype, const void* dx_add, void* dx, float* dgamma,
                        float* dbeta, float* partial_ws, void* stream);
+/* Column sums out[c] = sum_r x[r*D + c] (fp32 result): the bias gradient of the nn.Linear layers of the block
+ * (vit.py:50,52,83,85) from the gradient of their output.  partial_ws: GVIT_COLSUM_CHUNKS * D floats.  Deterministic. */
+enum { GVIT_COLSUM_CHUNKS = 1024 };
+GVIT_API int gvit_colsum(const void* x, int64_t rows, int D, int dtype, float* out, float* partial_ws, void* stream);
+
 /* out = resid + dropout(y, p) with a Philox-4x32-10 keep mask generated from (seed, offset) - the proj_drop +
  * residual edge of vit.py:71,117 (also pos_drop, vit.py:212, with resid NULL).  p == 0 degenerates to an add.
  * dtype: type of resid / out (the residual stream); y_dtype: type of y (the branch) - same pairing rule as LayerNorm;

@@ -16,7 +16,7 @@ def test_header_declares_the_expected_surface():
     names = [n for n, _ in DECLS]
     for must in ("gvit_knn_fwd", "gvit_knn_bwd", "gvit_graph_reverse", "gvit_agg_fwd", "gvit_agg_gather_fwd",
                  "gvit_agg_bwd", "gvit_graph_bwd", "gvit_attn_fwd", "gvit_attn_bwd", "gvit_layernorm_fwd", "gvit_layernorm_bwd",
-                 "gvit_dropout_residual_fwd", "gvit_dropout_bwd", "gvit_gelu_dropout_fwd", "gvit_gelu_dropout_bwd",
+                 "gvit_colsum", "gvit_dropout_residual_fwd", "gvit_dropout_bwd", "gvit_gelu_dropout_fwd", "gvit_gelu_dropout_bwd",
                  "gvit_version", "gvit_last_error_string"):
         assert must in names
     assert len(names) == len(set(names))

@@ -94,3 +94,31 @@ def test_layernorm_fp32_stream_bf16_branch_under_autocast():
     assert rel_err(xd.grad, xc.grad) < TOL_F32 * 10 and rel_err(wd.grad, wc.grad) < TOL_F32 * 10
     y32 = ops.layer_norm(xd, wd, bd)                                           # no autocast: fp32 in, fp32 out
     assert y32.dtype == torch.float32 and rel_err(y32, F.layer_norm(x, (768,), w, b)) < TOL_F32
+
+
+@pytest.mark.parametrize("rows,D,dtype", [(50432, 768, torch.bfloat16), (1000, 3072, torch.bfloat16), (7, 8, torch.float32),
+                                           (12345, 2304, torch.bfloat16), (300, 72, torch.float32)])
+def test_colsum_matches_fp64_sum(rows, D, dtype):
+    g = torch.Generator(device=DEV).manual_seed(rows)
+    x = torch.randn(rows, D, generator=g, device=DEV).to(dtype)
+    got = ops.colsum(x)
+    want = x.double().sum(0)
+    assert got.dtype == torch.float32
+    assert float((got.double() - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max())) + 1e-3
+    assert torch.equal(got, ops.colsum(x))                  # fixed reduction order
+
+
+def test_linear_matches_torch_linear_forward_and_backward():
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.randn(4, 197, 256, generator=g, device=DEV, requires_grad=True)
+    w = (torch.randn(512, 256, generator=g, device=DEV) * 0.05).requires_grad_(True)
+    b = torch.randn(512, generator=g, device=DEV, requires_grad=True)
+    cot = torch.randn(4, 197, 512, generator=g, device=DEV)
+    y = ops.linear(x, w, b)
+    y.backward(cot)
+    got = (y.detach(), x.grad.clone(), w.grad.clone(), b.grad.clone())
+    x.grad = w.grad = b.grad = None
+    y2 = torch.nn.functional.linear(x, w, b)
+    y2.backward(cot)
+    for a, r in zip(got, (y2.detach(), x.grad, w.grad, b.grad)):
+        assert rel_err(a, r) < 1e-5
