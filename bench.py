@@ -217,7 +217,7 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
                           3 * B * N * D * e, 0.0, "hbm", 1),
         "gelu_dropout_fwd": (lambda i: _call("gvit_gelu_dropout_fwd", _ptr(u4[i % 2]), B * N * 4 * D, 0.1, 1234, 0, dt, _ptr(o4), _ptr(m4), st),
                              2 * B * N * 4 * D * e + B * N * 4 * D // 8, 0.0, "hbm", 12),
-        "gelu_dropout_bwd": (lambda i: _call("gvit_gelu_dropout_bwd", _ptr(u4[(i + 1) % 2]), _ptr(u4[i % 2]), _ptr(m4), B * N * 4 * D, 0.1, dt, _ptr(o4), st),
+        "gelu_dropout_bwd": (lambda i: _call("gvit_gelu_dropout_bwd", _ptr(u4[(i + 1) % 2]), _ptr(u4[i % 2]), _ptr(m4), B * N * 4 * D, 0.1, dt, _ptr(o4), 4 * D, _ptr(cs_out), _ptr(cs_ws), st),
                              3 * B * N * 4 * D * e + B * N * 4 * D // 8, 0.0, "hbm", 12),
         "colsum_3072": (lambda i: _call("gvit_colsum", _ptr(u4[i % 2]), B * N, 4 * D, dt, _ptr(cs_out), _ptr(cs_ws), st),
                         B * N * 4 * D * e, 0.0, "hbm", 12),

@@ -427,6 +427,75 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int nchun
   out[c] = s;
 }
 
+// ---- backward edges fused with the bias gradient of the Linear that produced their input -----------------------------
+// dy = dropout_bwd(dout) [* gelu'(u)] is exactly the tensor whose column sums are that Linear's bias gradient
+// (vit.py:70-71, 90-93), so the same pass accumulates them: same 2-D mapping as colsum_partial_kernel
+// (block = 32 column groups x 8 row lanes, grid = column blocks x row chunks), four rows in flight per thread.
+template <typename Tx, typename Ty, bool GELU>
+__global__ void __launch_bounds__(256) edge_bwd_colsum_kernel(const Tx* __restrict__ dout, const Ty* __restrict__ u,
+                                                              const uint8_t* __restrict__ mask, int64_t rows, int D,
+                                                              int rows_per_chunk, float p, Ty* __restrict__ dy,
+                                                              float* __restrict__ partial) {
+  __shared__ float red[8][256 + 8];
+  const float scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + cx) * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+  const int64_t r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
+  float acc[8] = {};
+  if (col < D) {
+    for (int64_t r = r0 + ry; r < r1; r += 32) {
+      float g[4][8], a[4][8];
+      uint32_t bits[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t rr = r + 8 * i;
+        bits[i] = 0xffu;
+        if (rr < r1) {
+          const int64_t o = rr * D + col;
+          load8(dout + o, g[i]);
+          if (GELU) load8(u + o, a[i]);
+          if (p > 0.f) bits[i] = mask[o >> 3];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t rr = r + 8 * i;
+        if (rr < r1) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            float v = (bits[i] >> t) & 1u ? g[i][t] * scale : 0.f;
+            if (GELU) v *= GeluFor<Ty>::type::grad(a[i][t]);
+            v = to_f32(from_f32<Ty>(v));                   // the bias gradient sums the values as stored
+            g[i][t] = v;
+            acc[t] += v;
+          }
+          store8(dy + rr * D + col, g[i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) red[ry][cx * 8 + t] = acc[t];
+  __syncthreads();
+  const int cc = blockIdx.x * 256 + threadIdx.x;
+  if (cc < D) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w][threadIdx.x];
+    partial[(int64_t)blockIdx.y * D + cc] = sum;
+  }
+}
+
+inline void colsum_grid(int64_t rows, int D, int per_sm, int* colblocks, int* nchunks, int* rpc) {
+  *colblocks = (D + 255) / 256;
+  int n = (per_sm * num_sms() + *colblocks - 1) / *colblocks;
+  if (n > GVIT_COLSUM_CHUNKS) n = GVIT_COLSUM_CHUNKS;
+  if ((int64_t)n * 32 > rows) n = (int)((rows + 31) / 32);
+  *rpc = (int)((rows + n - 1) / n);
+  *nchunks = (int)((rows + *rpc - 1) / *rpc);
+}
+
 inline int stream_grid(int64_t n8) {
   const int64_t blocks = (n8 + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 8;
@@ -546,9 +615,25 @@ int dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, u
 }
 
 int dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, int y_dtype, void* dy,
-                cudaStream_t st) {
-  const int grid = stream_grid(n / 8);
+                int D, float* colsum_out, float* partial_ws, cudaStream_t st) {
   using bf = __nv_bfloat16;
+  if (colsum_out) {
+    int cb, nch, rpc;
+    const int64_t rows = n / D;
+    colsum_grid(rows, D, 8, &cb, &nch, &rpc);
+    dim3 g2(cb, nch);
+    if (dtype == GVIT_F32 && y_dtype == GVIT_F32)
+      edge_bwd_colsum_kernel<float, float, false><<<g2, 256, 0, st>>>(static_cast<const float*>(dout), nullptr, keep_mask, rows, D, rpc, p, static_cast<float*>(dy), partial_ws);
+    else if (dtype == GVIT_F32)
+      edge_bwd_colsum_kernel<float, bf, false><<<g2, 256, 0, st>>>(static_cast<const float*>(dout), nullptr, keep_mask, rows, D, rpc, p, static_cast<bf*>(dy), partial_ws);
+    else
+      edge_bwd_colsum_kernel<bf, bf, false><<<g2, 256, 0, st>>>(static_cast<const bf*>(dout), nullptr, keep_mask, rows, D, rpc, p, static_cast<bf*>(dy), partial_ws);
+    GVIT_CHECK_LAUNCH();
+    colsum_final_kernel<<<(D + 255) / 256, 256, 0, st>>>(partial_ws, nch, D, colsum_out);
+    GVIT_CHECK_LAUNCH();
+    return GVIT_OK;
+  }
+  const int grid = stream_grid(n / 8);
   if (dtype == GVIT_F32 && y_dtype == GVIT_F32)
     dropout_bwd_kernel<float, float><<<grid, 256, 0, st>>>(static_cast<const float*>(dout), keep_mask, n, p, static_cast<float*>(dy));
   else if (dtype == GVIT_F32)
@@ -572,7 +657,22 @@ int gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t 
 }
 
 int gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, int64_t n, float p, int dtype, void* du,
-                     cudaStream_t st) {
+                     int D, float* colsum_out, float* partial_ws, cudaStream_t st) {
+  if (colsum_out) {
+    using bf = __nv_bfloat16;
+    int cb, nch, rpc;
+    const int64_t rows = n / D;
+    colsum_grid(rows, D, 8, &cb, &nch, &rpc);
+    dim3 g2(cb, nch);
+    if (dtype == GVIT_F32)
+      edge_bwd_colsum_kernel<float, float, true><<<g2, 256, 0, st>>>(static_cast<const float*>(dout), static_cast<const float*>(u), keep_mask, rows, D, rpc, p, static_cast<float*>(du), partial_ws);
+    else
+      edge_bwd_colsum_kernel<bf, bf, true><<<g2, 256, 0, st>>>(static_cast<const bf*>(dout), static_cast<const bf*>(u), keep_mask, rows, D, rpc, p, static_cast<bf*>(du), partial_ws);
+    GVIT_CHECK_LAUNCH();
+    colsum_final_kernel<<<(D + 255) / 256, 256, 0, st>>>(partial_ws, nch, D, colsum_out);
+    GVIT_CHECK_LAUNCH();
+    return GVIT_OK;
+  }
   const int grid = stream_grid(n / 8);
   if (dtype == GVIT_F32)
     gelu_dropout_bwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(dout), static_cast<const float*>(u), keep_mask, n, p,

@@ -187,13 +187,21 @@ int gvit_dropout_residual_fwd(const void* y, const void* resid, int64_t n, float
   return dropout_residual_fwd(y, resid, n, p, seed, offset, dtype, y_dtype, out, keep_mask, static_cast<cudaStream_t>(stream));
 }
 
+static int check_colsum_args(const char* who, int64_t n, int D, const float* colsum_out, const float* partial_ws) {
+  if (!colsum_out) return GVIT_OK;
+  GVIT_REQUIRE(partial_ws != nullptr, GVIT_ERR_SHAPE, "%s: colsum_out needs partial_ws", who);
+  GVIT_REQUIRE(D >= 8 && D % 8 == 0 && n % D == 0, GVIT_ERR_SHAPE, "%s: D=%d must be a multiple of 8 dividing n=%lld", who, D, (long long)n);
+  return GVIT_OK;
+}
+
 int gvit_dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, int y_dtype, void* dy,
-                     void* stream) {
+                     int D, float* colsum_out, float* partial_ws, void* stream) {
   TRY(check_ln_pair(dtype, y_dtype, "dropout_bwd"));
-  GVIT_REQUIRE(dout && keep_mask && dy, GVIT_ERR_SHAPE, "dropout_bwd: null pointer");
-  GVIT_REQUIRE(n >= 8 && n % 8 == 0 && p > 0.f && p < 1.f, GVIT_ERR_SHAPE, "dropout_bwd: n=%lld p=%f", (long long)n, p);
+  GVIT_REQUIRE(dout && dy && (keep_mask || (colsum_out && p == 0.f)), GVIT_ERR_SHAPE, "dropout_bwd: null pointer");
+  GVIT_REQUIRE(n >= 8 && n % 8 == 0 && p >= 0.f && p < 1.f && (p > 0.f || colsum_out), GVIT_ERR_SHAPE, "dropout_bwd: n=%lld p=%f", (long long)n, p);
   GVIT_REQUIRE(aligned16(dout) && aligned16(dy), GVIT_ERR_ALIGN, "dropout_bwd: 16-byte alignment required");
-  return dropout_bwd(dout, keep_mask, n, p, dtype, y_dtype, dy, static_cast<cudaStream_t>(stream));
+  TRY(check_colsum_args("dropout_bwd", n, D, colsum_out, partial_ws));
+  return dropout_bwd(dout, keep_mask, n, p, dtype, y_dtype, dy, D, colsum_out, partial_ws, static_cast<cudaStream_t>(stream));
 }
 
 int gvit_gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t offset, int dtype, void* out,
@@ -207,13 +215,14 @@ int gvit_gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint
 }
 
 int gvit_gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, int64_t n, float p, int dtype,
-                          void* du, void* stream) {
+                          void* du, int D, float* colsum_out, float* partial_ws, void* stream) {
   TRY(check_dtype(dtype, "gelu_dropout_bwd"));
   GVIT_REQUIRE(dout && u && du, GVIT_ERR_SHAPE, "gelu_dropout_bwd: null pointer");
   GVIT_REQUIRE(n >= 8 && n % 8 == 0, GVIT_ERR_SHAPE, "gelu_dropout_bwd: n=%lld must be a positive multiple of 8", (long long)n);
   GVIT_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || keep_mask), GVIT_ERR_SHAPE, "gelu_dropout_bwd: p=%f (keep_mask required when p > 0)", p);
   GVIT_REQUIRE(aligned16(dout) && aligned16(u) && aligned16(du), GVIT_ERR_ALIGN, "gelu_dropout_bwd: 16-byte alignment required");
-  return gelu_dropout_bwd(dout, u, keep_mask, n, p, dtype, du, static_cast<cudaStream_t>(stream));
+  TRY(check_colsum_args("gelu_dropout_bwd", n, D, colsum_out, partial_ws));
+  return gelu_dropout_bwd(dout, u, keep_mask, n, p, dtype, du, D, colsum_out, partial_ws, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -54,10 +54,10 @@ int colsum(const void* x, int64_t rows, int D, int dtype, float* out, float* par
 int dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, uint64_t seed, uint64_t offset,
                          int dtype, int y_dtype, void* out, uint8_t* keep_mask, cudaStream_t st);
 int dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, int y_dtype, void* dy,
-                cudaStream_t st);
+                int D, float* colsum_out, float* partial_ws, cudaStream_t st);
 int gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t offset, int dtype, void* out,
                      uint8_t* keep_mask, cudaStream_t st);
 int gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, int64_t n, float p, int dtype, void* du,
-                     cudaStream_t st);
+                     int D, float* colsum_out, float* partial_ws, cudaStream_t st);
 
 }  // namespace gvit

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(THREADS, 1) knn_tc_kernel(const __grid_constan
   const int b = blockIdx.x;
   const int slabs = D / 64;
   const int mtiles = Np > 128 ? 2 : 1;
+  GVIT_TRACE_DECL
 
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tmap);
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(THREADS, 1) knn_tc_kernel(const __grid_constan
         const int s = it % STAGES;
         mbar_wait(&ctl->full[s], (it / STAGES) & 1);
         tc_fence_after();
+        GVIT_TR(1);
         const uint32_t base = smem_u32(stages + (size_t)s * STAGE_BYTES);
         for (int mt = 0; mt < mtiles; ++mt)
 #pragma unroll
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(THREADS, 1) knn_tc_kernel(const __grid_constan
         umma_commit(&ctl->empty[s]);    // slab consumed -> producer may refill it
       }
       umma_commit(&ctl->accum_full);    // all MMAs retired -> accumulators readable
+      GVIT_TR(2);
     }
   } else {
     const int g = warp >> 2;                              // accumulator tile
@@ -93,8 +96,10 @@ __global__ void __launch_bounds__(THREADS, 1) knn_tc_kernel(const __grid_constan
     const uint32_t trow = tmem_lane_base(tmem, warp) + g * 256;
     float rn_i = 0.f;
     if (active) {
+      GVIT_TR(10);
       mbar_wait(&ctl->accum_full, 0);
       tc_fence_after();
+      GVIT_TR(11);
       float v[32];
       tmem_ld32(trow + wrow0, v);                         // the 32x32 block on the diagonal
       float d = 0.f;
@@ -104,6 +109,7 @@ __global__ void __launch_bounds__(THREADS, 1) knn_tc_kernel(const __grid_constan
       if (row < Np) { ctl->rn[row] = rn_i; rnorm[(int64_t)b * Np + row] = rn_i; }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");        // the 8 epilogue warps: norms visible
+    GVIT_TR(12);
     if (active) {
       float tv[KT];
       int ti[KT];
@@ -113,24 +119,35 @@ __global__ void __launch_bounds__(THREADS, 1) knn_tc_kernel(const __grid_constan
         float v[32];
         tmem_ld32(trow + c0, v);
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const int j = c0 + t;
-          if (j < Np) {
-            const float sim = (v[t] * rn_i) * ctl->rn[j];
-            if (sim > tv[KT - 1]) {                       // strict: a later equal column never displaces an earlier one
-              tv[KT - 1] = sim;
-              ti[KT - 1] = j;
+        for (int t4 = 0; t4 < 32; t4 += 4) {
+          const float4 rn4 = *reinterpret_cast<const float4*>(&ctl->rn[c0 + t4]);
+          const float rnv[4] = {rn4.x, rn4.y, rn4.z, rn4.w};
 #pragma unroll
-              for (int s = KT - 1; s > 0; --s) {
-                if (tv[s] > tv[s - 1]) {
-                  const float fv = tv[s]; tv[s] = tv[s - 1]; tv[s - 1] = fv;
-                  const int iv = ti[s]; ti[s] = ti[s - 1]; ti[s - 1] = iv;
-                }
-              }
+          for (int u = 0; u < 4; ++u) {
+            const int j = c0 + t4 + u;
+            // columns >= Np can never be selected (-FLT_MAX never beats the initial entries under a strict ">")
+            float x = j < Np ? (v[t4 + u] * rn_i) * rnv[u] : -FLT_MAX;
+            int xi = j;
+            // branch-free insertion into the sorted list: the new element enters at the first entry it strictly beats
+            // (equal similarities keep ascending index order: ties -> lowest index) and everything below shifts down
+            // by one.  The data-dependent "if (sim > tv[k-1]) bubble up" of v1 diverged on almost every column of a
+            // warp: 55k cycles per image.
+            bool ins = false;
+#pragma unroll
+            for (int s = 0; s < KT; ++s) {
+              const bool gt = ins || x > tv[s];
+              ins = gt;
+              const float nv = gt ? x : tv[s];
+              const int ni = gt ? xi : ti[s];
+              x = gt ? tv[s] : x;
+              xi = gt ? ti[s] : xi;
+              tv[s] = nv;
+              ti[s] = ni;
             }
           }
         }
       }
+      GVIT_TR(13);
       if (row < Np) {
         const int64_t o = ((int64_t)b * Np + row) * k;
 #pragma unroll
@@ -153,6 +170,8 @@ int launch(const CUtensorMap& tmap, const Tokens& t, int k, int NT, int32_t* idx
 }
 
 }  // namespace
+
+GVIT_TRACE_SETTER(gvit_debug_set_trace_knn)
 
 bool knn_tc_supported(int Np, int D, int k) { return Np >= 16 && Np <= 256 && D >= 64 && D % 64 == 0 && k <= 32; }
 

@@ -46,9 +46,13 @@ class LayerNorm(nn.LayerNorm):
         return ops.pre_norm(x, self.weight, self.bias, self.eps)
 
 
+def _hooked(mod: nn.Module) -> bool:
+    return bool(mod._forward_hooks or mod._forward_pre_hooks or mod._backward_hooks or mod._backward_pre_hooks)
+
+
 def _linear(mod: nn.Linear, x):
     """mod(x) through ops.linear (libgvit bias gradient) unless somebody hooked the Linear module itself."""
-    if mod._forward_hooks or mod._forward_pre_hooks or mod._backward_hooks or mod._backward_pre_hooks:
+    if _hooked(mod):
         return mod(x)
     return ops.linear(x, mod.weight, mod.bias)
 
@@ -70,7 +74,10 @@ class Attention(nn.Module):
             # 0 in every configuration the reference ships (vit.py:127; scripts/train.py never sets it)
             raise NotImplementedError("attn_drop > 0 is not implemented by the fused attention kernel")
         o = ops.attention_core(_linear(self.qkv, x), self.num_heads, self.scale)
-        return ops.dropout_add(_linear(self.proj, o), resid, self.proj_drop.p, self.training)
+        if _hooked(self.proj) or _hooked(self.proj_drop):
+            return ops.dropout_add(self.proj(o), resid, self.proj_drop.p, self.training)
+        # proj + proj_drop + residual as one node: the dropout backward pass also yields proj's bias gradient
+        return ops.linear_dropout_add(o, self.proj.weight, self.proj.bias, resid, self.proj_drop.p, self.training)
 
 
 class Mlp(nn.Module):
@@ -84,8 +91,12 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x, resid=None):
-        x = ops.gelu_dropout(_linear(self.fc1, x), self.drop.p, self.training)        # act + drop in one pass
-        return ops.dropout_add(_linear(self.fc2, x), resid, self.drop.p, self.training)
+        if _hooked(self.fc1) or _hooked(self.fc2) or _hooked(self.act) or _hooked(self.drop):
+            x = ops.gelu_dropout(self.fc1(x), self.drop.p, self.training)
+            return ops.dropout_add(self.fc2(x), resid, self.drop.p, self.training)
+        # fc1 + GELU + drop, then fc2 + drop + residual: each Linear's bias gradient comes out of the edge's backward pass
+        x = ops.linear_gelu_dropout(x, self.fc1.weight, self.fc1.bias, self.drop.p, self.training)
+        return ops.linear_dropout_add(x, self.fc2.weight, self.fc2.bias, resid, self.drop.p, self.training)
 
 
 class DropPath(nn.Module):

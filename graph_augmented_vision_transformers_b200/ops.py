@@ -23,7 +23,7 @@ import torch.nn.functional as F
 from . import _lib
 from ._lib import GVIT_BF16, GVIT_COLSUM_CHUNKS, GVIT_F32, GVIT_LN_PARTIALS
 
-__all__ = ["attention_core", "layer_norm", "pre_norm", "linear", "colsum", "dropout_add", "gelu_dropout", "knn_graph", "graph_reverse", "patch_graph",
+__all__ = ["attention_core", "layer_norm", "pre_norm", "linear", "colsum", "linear_dropout_add", "linear_gelu_dropout", "dropout_add", "gelu_dropout", "knn_graph", "graph_reverse", "patch_graph",
            "agg_gather", "launch_count", "reset_launch_count"]
 
 # kernels launched through the C ABI since the last reset (bench.py reports it as gpu_launches)
@@ -287,7 +287,7 @@ class _DropoutAdd(torch.autograd.Function):
         dout = dout.contiguous()
         dy = torch.empty(dout.shape, dtype=ctx.y_dtype, device=dout.device)
         _call("gvit_dropout_bwd", _ptr(dout), _ptr(mask), dout.numel(), float(ctx.p), _dtype_code(dout),
-              _dtype_code(dy), _ptr(dy), _stream())
+              _dtype_code(dy), _ptr(dy), 0, None, None, _stream())
         return dy, dresid, None, None
 
 
@@ -334,7 +334,7 @@ class _GeluDropout(torch.autograd.Function):
         dout = dout.contiguous()
         du = torch.empty_like(u)
         _call("gvit_gelu_dropout_bwd", _ptr(dout), _ptr(u), _ptr(mask), u.numel(), float(ctx.p), _dtype_code(u),
-              _ptr(du), _stream())
+              _ptr(du), 0, None, None, _stream())
         return du, None, None
 
 
@@ -349,6 +349,110 @@ def gelu_dropout(u: torch.Tensor, p: float, training: bool) -> torch.Tensor:
     seed = _draw_seed() if p > 0 else 0
     with torch.autocast("cuda", enabled=False):
         return _GeluDropout.apply(u.to(dt).contiguous(), p, seed)
+
+
+# ------------------------------------------------------------------------------------------------
+# Linear + edge, as one autograd node each: the edge's backward kernel also yields the Linear's bias gradient
+# ------------------------------------------------------------------------------------------------
+def _linear_grads(ctx_needs, x, weight, dy2):
+    dx = (dy2 @ weight).view(x.shape) if ctx_needs[0] else None
+    dw = dy2.t() @ x.reshape(-1, x.shape[-1]) if ctx_needs[1] else None
+    return dx, dw
+
+
+class _LinearDropoutAdd(torch.autograd.Function):
+    """out = resid + dropout(x W^T + b, p)  (proj + proj_drop + residual, vit.py:70-71,117; fc2 + drop + residual,
+    vit.py:93-94,118).  Backward: ONE pass over dout applies the keep mask and accumulates the column sums that are
+    the bias gradient; the two GEMM gradients are library GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, resid, p, seed):
+        y = F.linear(x, weight, bias)
+        n = y.numel()
+        out = torch.empty_like(y if resid is None else resid)
+        mask = torch.empty(n // 8, dtype=torch.uint8, device=y.device) if p > 0 else None
+        _call("gvit_dropout_residual_fwd", _ptr(y), _ptr(resid), n, float(p), int(seed), 0, _dtype_code(out),
+              _dtype_code(y), _ptr(out), _ptr(mask), _stream())
+        ctx.save_for_backward(x, weight, mask)
+        ctx.p, ctx.has_bias, ctx.has_resid, ctx.y_dtype = p, bias is not None, resid is not None, y.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, mask = ctx.saved_tensors
+        dout = dout.contiguous()
+        Dn = dout.shape[-1]
+        dy = torch.empty(dout.shape, dtype=ctx.y_dtype, device=dout.device)
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
+        db = torch.empty(Dn, dtype=torch.float32, device=dout.device) if want_db else None
+        ws = torch.empty(GVIT_COLSUM_CHUNKS * Dn, dtype=torch.float32, device=dout.device) if want_db else None
+        if ctx.p > 0 or want_db:
+            _call("gvit_dropout_bwd", _ptr(dout), _ptr(mask), dout.numel(), float(ctx.p), _dtype_code(dout),
+                  _dtype_code(dy), _ptr(dy), Dn, _ptr(db), _ptr(ws), _stream())
+        else:
+            dy = dout.to(ctx.y_dtype)
+        dx, dw = _linear_grads(ctx.needs_input_grad, x, weight, dy.view(-1, Dn))
+        return dx, dw, (db.to(ctx.y_dtype) if want_db else None), (dout if ctx.has_resid else None), None, None
+
+
+class _LinearGeluDropout(torch.autograd.Function):
+    """out = dropout(gelu(x W^T + b), p)  (fc1 + GELU + drop, vit.py:90-92); the pre-activation is saved, GELU' is
+    recomputed, and the backward pass over dout also accumulates fc1's bias gradient."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, p, seed):
+        u = F.linear(x, weight, bias)
+        n = u.numel()
+        out = torch.empty_like(u)
+        mask = torch.empty(n // 8, dtype=torch.uint8, device=u.device) if p > 0 else None
+        _call("gvit_gelu_dropout_fwd", _ptr(u), n, float(p), int(seed), 0, _dtype_code(u), _ptr(out), _ptr(mask), _stream())
+        ctx.save_for_backward(x, weight, u, mask)
+        ctx.p, ctx.has_bias = p, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, u, mask = ctx.saved_tensors
+        dout = dout.contiguous()
+        Dn = u.shape[-1]
+        du = torch.empty_like(u)
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
+        db = torch.empty(Dn, dtype=torch.float32, device=u.device) if want_db else None
+        ws = torch.empty(GVIT_COLSUM_CHUNKS * Dn, dtype=torch.float32, device=u.device) if want_db else None
+        _call("gvit_gelu_dropout_bwd", _ptr(dout), _ptr(u), _ptr(mask), u.numel(), float(ctx.p), _dtype_code(u),
+              _ptr(du), Dn, _ptr(db), _ptr(ws), _stream())
+        dx, dw = _linear_grads(ctx.needs_input_grad, x, weight, du.view(-1, Dn))
+        return dx, dw, (db.to(u.dtype) if want_db else None), None, None
+
+
+def linear_dropout_add(x, weight, bias, resid, p: float, training: bool):
+    """``resid + dropout(linear(x, weight, bias), p)`` as one autograd node (``resid`` may be None)."""
+    _check_cuda(x, weight, bias, resid)
+    p = float(p) if training else 0.0
+    dt = _autocast_dtype(x)
+    if resid is not None:
+        if resid.dtype not in (torch.float32, torch.bfloat16):
+            resid = resid.to(torch.bfloat16)
+        if resid.dtype == torch.bfloat16 and dt == torch.float32:
+            resid = resid.float()
+    if weight.shape[0] % 8:
+        return dropout_add(linear(x, weight, bias), resid, p, training)
+    seed = _draw_seed() if p > 0 else 0
+    with torch.autocast("cuda", enabled=False):
+        return _LinearDropoutAdd.apply(x.to(dt), weight.to(dt), None if bias is None else bias.to(dt),
+                                       None if resid is None else resid.contiguous(), p, seed)
+
+
+def linear_gelu_dropout(x, weight, bias, p: float, training: bool):
+    """``dropout(gelu(linear(x, weight, bias)), p)`` as one autograd node."""
+    _check_cuda(x, weight, bias)
+    p = float(p) if training else 0.0
+    dt = _autocast_dtype(x)
+    if weight.shape[0] % 8:
+        return gelu_dropout(linear(x, weight, bias), p, training)
+    seed = _draw_seed() if p > 0 else 0
+    with torch.autocast("cuda", enabled=False):
+        return _LinearGeluDropout.apply(x.to(dt), weight.to(dt), None if bias is None else bias.to(dt), p, seed)
 
 
 # ------------------------------------------------------------------------------------------------

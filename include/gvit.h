@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GVIT_ABI_VERSION 5
+#define GVIT_ABI_VERSION 6
 #if defined(__GNUC__)
 #define GVIT_API __attribute__((visibility("default")))
 #else
@@ -148,17 +148,21 @@ GVIT_API int gvit_colsum(const void* x, int64_t rows, int D, int dtype, float* o
  * may be NULL when p == 0.  n % 8 == 0. */
 GVIT_API int gvit_dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, uint64_t seed, uint64_t offset,
                               int dtype, int y_dtype, void* out, uint8_t* keep_mask, void* stream);
-/* dy = dout * keep / (1 - p);  dout has `dtype`, dy has `y_dtype`. */
+/* dy = dout * keep / (1 - p);  dout has `dtype`, dy has `y_dtype`.
+ * With colsum_out != NULL the same pass also writes colsum_out[c] = sum_r dy[r*D + c] (fp32, D values; the tensor is
+ * read as n/D rows of D) - the bias gradient of the Linear whose output was dropped out (vit.py:70-71, 93-94);
+ * partial_ws then holds GVIT_COLSUM_CHUNKS * D floats, and p == 0 (keep_mask NULL) is allowed: a cast + column sum. */
 GVIT_API int gvit_dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, int y_dtype, void* dy,
-                     void* stream);
+                     int D, float* colsum_out, float* partial_ws, void* stream);
 
 /* ---- Mlp activation edge: out = dropout(GELU(u), p), exact-erf GELU - nn.GELU + nn.Dropout at vit.py:84,92 in one
  * pass; the backward recomputes GELU' from the saved pre-activation u (no activation tensor is kept).
  * keep_mask as above (may be NULL when p == 0). */
 GVIT_API int gvit_gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t offset, int dtype, void* out,
                           uint8_t* keep_mask, void* stream);
+/* colsum_out / partial_ws / D as for gvit_dropout_bwd: the bias gradient of fc1 (vit.py:90) in the same pass. */
 GVIT_API int gvit_gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, int64_t n, float p, int dtype,
-                          void* du, void* stream);
+                          void* du, int D, float* colsum_out, float* partial_ws, void* stream);
 
 #ifdef __cplusplus
 }

@@ -122,3 +122,33 @@ def test_linear_matches_torch_linear_forward_and_backward():
     y2.backward(cot)
     for a, r in zip(got, (y2.detach(), x.grad, w.grad, b.grad)):
         assert rel_err(a, r) < 1e-5
+
+
+@pytest.mark.parametrize("dtype,p", [(torch.float32, 0.0), (torch.float32, 0.3), (torch.bfloat16, 0.1)])
+def test_fused_linear_edges_match_the_unfused_composition(dtype, p):
+    """linear_gelu_dropout / linear_dropout_add (bias gradient from the edge's backward pass) against
+    linear -> gelu_dropout / dropout_add with the same seeds."""
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x0 = torch.randn(3, 197, 128, generator=g, device=DEV).to(dtype)
+    r0 = torch.randn(3, 197, 128, generator=g, device=DEV).to(dtype)
+    w1 = (torch.randn(256, 128, generator=g, device=DEV) * 0.1).to(dtype)
+    b1 = torch.randn(256, generator=g, device=DEV).to(dtype)
+    w2 = (torch.randn(128, 256, generator=g, device=DEV) * 0.1).to(dtype)
+    b2 = torch.randn(128, generator=g, device=DEV).to(dtype)
+    cot = torch.randn(3, 197, 128, generator=g, device=DEV).to(dtype)
+    outs = []
+    for fused in (True, False):
+        leaves = [t.clone().requires_grad_(True) for t in (x0, r0, w1, b1, w2, b2)]
+        x, r, W1, B1, W2, B2 = leaves
+        torch.manual_seed(99)                                  # same dropout seeds in both variants
+        if fused:
+            h = ops.linear_gelu_dropout(x, W1, B1, p, True)
+            y = ops.linear_dropout_add(h, W2, B2, r, p, True)
+        else:
+            h = ops.gelu_dropout(ops.linear(x, W1, B1), p, True)
+            y = ops.dropout_add(ops.linear(h, W2, B2), r, p, True)
+        y.backward(cot)
+        outs.append([y.detach()] + [t.grad for t in leaves])
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    for a, b in zip(*outs):
+        assert rel_err(a, b) < tol
