@@ -419,12 +419,23 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
     partial[(int64_t)blockIdx.y * D + c] = sum;
   }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int nchunks, int D, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= D) return;
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int nchunks, int D,
+                                                           float* __restrict__ out) {
+  // 32 columns x 8 chunk lanes per CTA; fixed summation order (lane-strided, then lanes 0..7)
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float s = 0.f;
-  for (int i = 0; i < nchunks; ++i) s += partial[(int64_t)i * D + c];
-  out[c] = s;
+  if (c < D)
+    for (int i = ly; i < nchunks; i += 8) s += partial[(int64_t)i * D + c];
+  red[ly][cx] = s;
+  __syncthreads();
+  if (ly == 0 && c < D) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][cx];
+    out[c] = t;
+  }
 }
 
 // ---- backward edges fused with the bias gradient of the Linear that produced their input -----------------------------
@@ -432,7 +443,7 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int nchun
 // (vit.py:70-71, 90-93), so the same pass accumulates them: same 2-D mapping as colsum_partial_kernel
 // (block = 32 column groups x 8 row lanes, grid = column blocks x row chunks), four rows in flight per thread.
 template <typename Tx, typename Ty, bool GELU>
-__global__ void __launch_bounds__(256) edge_bwd_colsum_kernel(const Tx* __restrict__ dout, const Ty* __restrict__ u,
+__global__ void __launch_bounds__(256, GELU ? 3 : 2) edge_bwd_colsum_kernel(const Tx* __restrict__ dout, const Ty* __restrict__ u,
                                                               const uint8_t* __restrict__ mask, int64_t rows, int D,
                                                               int rows_per_chunk, float p, Ty* __restrict__ dy,
                                                               float* __restrict__ partial) {
@@ -444,11 +455,12 @@ __global__ void __launch_bounds__(256) edge_bwd_colsum_kernel(const Tx* __restri
   const int64_t r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
   float acc[8] = {};
   if (col < D) {
-    for (int64_t r = r0 + ry; r < r1; r += 32) {
-      float g[4][8], a[4][8];
-      uint32_t bits[4];
+    constexpr int RF = GELU ? 2 : 4;                        // rows in flight per thread (GELU': keep 24 warps / SM)
+    for (int64_t r = r0 + ry; r < r1; r += 8 * RF) {
+      float g[RF][8], a[RF][8];
+      uint32_t bits[RF];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < RF; ++i) {
         const int64_t rr = r + 8 * i;
         bits[i] = 0xffu;
         if (rr < r1) {
@@ -459,7 +471,7 @@ __global__ void __launch_bounds__(256) edge_bwd_colsum_kernel(const Tx* __restri
         }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < RF; ++i) {
         const int64_t rr = r + 8 * i;
         if (rr < r1) {
 #pragma unroll
@@ -592,7 +604,7 @@ int colsum(const void* x, int64_t rows, int D, int dtype, float* out, float* par
   else
     colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), rows, D, rpc, partial_ws);
   GVIT_CHECK_LAUNCH();
-  colsum_final_kernel<<<(D + 255) / 256, 256, 0, st>>>(partial_ws, nchunks, D, out);
+  colsum_final_kernel<<<(D + 31) / 32, 256, 0, st>>>(partial_ws, nchunks, D, out);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }
@@ -620,7 +632,7 @@ int dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, 
   if (colsum_out) {
     int cb, nch, rpc;
     const int64_t rows = n / D;
-    colsum_grid(rows, D, 8, &cb, &nch, &rpc);
+    colsum_grid(rows, D, 6, &cb, &nch, &rpc);
     dim3 g2(cb, nch);
     if (dtype == GVIT_F32 && y_dtype == GVIT_F32)
       edge_bwd_colsum_kernel<float, float, false><<<g2, 256, 0, st>>>(static_cast<const float*>(dout), nullptr, keep_mask, rows, D, rpc, p, static_cast<float*>(dy), partial_ws);
@@ -629,7 +641,7 @@ int dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, 
     else
       edge_bwd_colsum_kernel<bf, bf, false><<<g2, 256, 0, st>>>(static_cast<const bf*>(dout), nullptr, keep_mask, rows, D, rpc, p, static_cast<bf*>(dy), partial_ws);
     GVIT_CHECK_LAUNCH();
-    colsum_final_kernel<<<(D + 255) / 256, 256, 0, st>>>(partial_ws, nch, D, colsum_out);
+    colsum_final_kernel<<<(D + 31) / 32, 256, 0, st>>>(partial_ws, nch, D, colsum_out);
     GVIT_CHECK_LAUNCH();
     return GVIT_OK;
   }
@@ -662,14 +674,14 @@ int gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, 
     using bf = __nv_bfloat16;
     int cb, nch, rpc;
     const int64_t rows = n / D;
-    colsum_grid(rows, D, 8, &cb, &nch, &rpc);
+    colsum_grid(rows, D, 6, &cb, &nch, &rpc);
     dim3 g2(cb, nch);
     if (dtype == GVIT_F32)
       edge_bwd_colsum_kernel<float, float, true><<<g2, 256, 0, st>>>(static_cast<const float*>(dout), static_cast<const float*>(u), keep_mask, rows, D, rpc, p, static_cast<float*>(du), partial_ws);
     else
       edge_bwd_colsum_kernel<bf, bf, true><<<g2, 256, 0, st>>>(static_cast<const bf*>(dout), static_cast<const bf*>(u), keep_mask, rows, D, rpc, p, static_cast<bf*>(du), partial_ws);
     GVIT_CHECK_LAUNCH();
-    colsum_final_kernel<<<(D + 255) / 256, 256, 0, st>>>(partial_ws, nch, D, colsum_out);
+    colsum_final_kernel<<<(D + 31) / 32, 256, 0, st>>>(partial_ws, nch, D, colsum_out);
     GVIT_CHECK_LAUNCH();
     return GVIT_OK;
   }

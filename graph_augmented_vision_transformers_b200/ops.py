@@ -147,7 +147,8 @@ class _Linear(torch.autograd.Function):
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        return F.linear(x, weight, bias)
+        ctx.bias_dtype = bias.dtype if bias is not None else None
+        return F.linear(x, weight, None if bias is None else bias.to(x.dtype))
 
     @staticmethod
     def backward(ctx, dy):
@@ -159,7 +160,7 @@ class _Linear(torch.autograd.Function):
         dw = dy2.t() @ x.reshape(-1, x.shape[-1]) if ctx.needs_input_grad[1] else None
         db = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = colsum(dy2).to(dy.dtype) if dy2.shape[1] % 8 == 0 else dy2.sum(0)
+            db = (colsum(dy2) if dy2.shape[1] % 8 == 0 else dy2.float().sum(0)).to(ctx.bias_dtype)
         return dx, dw, db
 
 
@@ -168,7 +169,7 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> 
     _check_cuda(x, weight, bias)
     dt = _autocast_dtype(x)
     with torch.autocast("cuda", enabled=False):
-        return _Linear.apply(x.to(dt), weight.to(dt), None if bias is None else bias.to(dt))
+        return _Linear.apply(x.to(dt), weight.to(dt), bias)      # the bias parameter itself: its gradient comes back fp32
 
 
 # ------------------------------------------------------------------------------------------------
@@ -367,7 +368,8 @@ class _LinearDropoutAdd(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, resid, p, seed):
-        y = F.linear(x, weight, bias)
+        ctx.bias_dtype = bias.dtype if bias is not None else None
+        y = F.linear(x, weight, None if bias is None else bias.to(x.dtype))
         n = y.numel()
         out = torch.empty_like(y if resid is None else resid)
         mask = torch.empty(n // 8, dtype=torch.uint8, device=y.device) if p > 0 else None
@@ -392,7 +394,7 @@ class _LinearDropoutAdd(torch.autograd.Function):
         else:
             dy = dout.to(ctx.y_dtype)
         dx, dw = _linear_grads(ctx.needs_input_grad, x, weight, dy.view(-1, Dn))
-        return dx, dw, (db.to(ctx.y_dtype) if want_db else None), (dout if ctx.has_resid else None), None, None
+        return dx, dw, (db.to(ctx.bias_dtype) if want_db else None), (dout if ctx.has_resid else None), None, None
 
 
 class _LinearGeluDropout(torch.autograd.Function):
@@ -401,7 +403,8 @@ class _LinearGeluDropout(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, p, seed):
-        u = F.linear(x, weight, bias)
+        ctx.bias_dtype = bias.dtype if bias is not None else None
+        u = F.linear(x, weight, None if bias is None else bias.to(x.dtype))
         n = u.numel()
         out = torch.empty_like(u)
         mask = torch.empty(n // 8, dtype=torch.uint8, device=u.device) if p > 0 else None
@@ -422,7 +425,7 @@ class _LinearGeluDropout(torch.autograd.Function):
         _call("gvit_gelu_dropout_bwd", _ptr(dout), _ptr(u), _ptr(mask), u.numel(), float(ctx.p), _dtype_code(u),
               _ptr(du), Dn, _ptr(db), _ptr(ws), _stream())
         dx, dw = _linear_grads(ctx.needs_input_grad, x, weight, du.view(-1, Dn))
-        return dx, dw, (db.to(u.dtype) if want_db else None), None, None
+        return dx, dw, (db.to(ctx.bias_dtype) if want_db else None), None, None
 
 
 def linear_dropout_add(x, weight, bias, resid, p: float, training: bool):
@@ -439,8 +442,7 @@ def linear_dropout_add(x, weight, bias, resid, p: float, training: bool):
         return dropout_add(linear(x, weight, bias), resid, p, training)
     seed = _draw_seed() if p > 0 else 0
     with torch.autocast("cuda", enabled=False):
-        return _LinearDropoutAdd.apply(x.to(dt), weight.to(dt), None if bias is None else bias.to(dt),
-                                       None if resid is None else resid.contiguous(), p, seed)
+        return _LinearDropoutAdd.apply(x.to(dt), weight.to(dt), bias, None if resid is None else resid.contiguous(), p, seed)
 
 
 def linear_gelu_dropout(x, weight, bias, p: float, training: bool):
@@ -452,7 +454,7 @@ def linear_gelu_dropout(x, weight, bias, p: float, training: bool):
         return gelu_dropout(linear(x, weight, bias), p, training)
     seed = _draw_seed() if p > 0 else 0
     with torch.autocast("cuda", enabled=False):
-        return _LinearGeluDropout.apply(x.to(dt), weight.to(dt), None if bias is None else bias.to(dt), p, seed)
+        return _LinearGeluDropout.apply(x.to(dt), weight.to(dt), bias, p, seed)
 
 
 # ------------------------------------------------------------------------------------------------
