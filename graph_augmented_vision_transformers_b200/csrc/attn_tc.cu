@@ -36,6 +36,19 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// exp2 on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max relative error
+// 7.5e-5 - far below the bf16 resolution of the probabilities it feeds).  The softmax loops are MUFU-bound
+// (one MUFU.EX2 per score, 4 lanes/clk/SMSP), so every fourth exponential is evaluated this way to balance the pipes.
+// x <= 0 is expected; x < -125 is clamped (result ~2^-125 instead of 0 / denormal).
+__device__ __forceinline__ float ex2_emul(float x) {
+  x = fmaxf(x, -125.0f);
+  const float xr = x + 12582912.0f;                 // 1.5 * 2^23: round to nearest integer in the low mantissa bits
+  const float f = x - (xr - 12582912.0f);           // in [-0.5, 0.5]
+  float p = fmaf(0.05517164617776871f, f, 0.2426111251115799f);
+  p = fmaf(p, f, 0.6932609677314758f);
+  p = fmaf(p, f, 0.9999280571937561f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -272,6 +285,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) attn_fwd_tc2_kernel(const __gri
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role id
   const int MT = (N + 127) >> 7;                 // 128-row query tiles (1 or 2) == 128-row key/value tiles
   const int NT = (N + 15) & ~15;                 // key extent of the MMAs
+  GVIT_TRACE_DECL
 
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tm_qkv);
@@ -315,6 +329,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) attn_fwd_tc2_kernel(const __gri
         const int s = it & 1;
         const uint32_t aQ = smem_u32(sm + s * F2_STAGE_BYTES), aK = aQ + 2 * TILE_BYTES, aV = aQ + 4 * TILE_BYTES;
         mbar_wait(&ctl->full[s], (it >> 1) & 1);
+        GVIT_TR(1);
         for (int g = 0; g < MT; ++g) {
           mbar_wait(&ctl->t_free[g], (it & 1) ^ 1);          // region g drained by the previous item's epilogue
           tc_fence_after();
@@ -329,6 +344,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) attn_fwd_tc2_kernel(const __gri
           for (int ks = 0; ks < NT / 16; ++ks)
             umma_ts(tmem + g * 256 + 128, tmem + g * 256 + ks * 8, make_sdesc(aV + ks * 2048), idesc_o, ks > 0);
           umma_commit(&ctl->o_full[g]);
+          GVIT_TR(2);
         }
       }
     }
@@ -341,14 +357,21 @@ __global__ void __launch_bounds__(F2_THREADS, 1) attn_fwd_tc2_kernel(const __gri
       int it = 0;
       for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
         const int s = it & 1, b = w / H, h = w - b * H;
+        GVIT_TR(10);
         mbar_wait(&ctl->s_full[g], it & 1);
         tc_fence_after();
+        GVIT_TR(11);
         float mx = -3.0e38f;
         for (int c0 = 0; c0 < NT; c0 += 32) {
           float v[32];
           tmem_ld32(tR + c0, v);
+          if (c0 + 32 <= N) {
 #pragma unroll
-          for (int t = 0; t < 32; ++t) mx = (c0 + t < N) ? fmaxf(mx, v[t]) : mx;
+            for (int t = 0; t < 32; ++t) mx = fmaxf(mx, v[t]);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) mx = (c0 + t < N) ? fmaxf(mx, v[t]) : mx;
+          }
         }
         const float msc = mx * sl2;
         float l = 0.f;
@@ -356,21 +379,36 @@ __global__ void __launch_bounds__(F2_THREADS, 1) attn_fwd_tc2_kernel(const __gri
           float v[32];
           tmem_ld32(tR + c0, v);
           uint32_t pk[16];
+          if (c0 + 32 <= N) {                                // full chunk: no masks, every 4th exp2 off the MUFU pipe
 #pragma unroll
-          for (int t = 0; t < 32; t += 2) {
-            const float p0 = (c0 + t < N) ? ex2(fmaf(v[t], sl2, -msc)) : 0.f;
-            const float p1 = (c0 + t + 1 < N) ? ex2(fmaf(v[t + 1], sl2, -msc)) : 0.f;
-            l += p0 + p1;
-            pk[t >> 1] = pack_bf16(p0, p1);
+            for (int t = 0; t < 32; t += 4) {
+              const float p0 = ex2(fmaf(v[t], sl2, -msc));
+              const float p1 = ex2(fmaf(v[t + 1], sl2, -msc));
+              const float p2 = ex2(fmaf(v[t + 2], sl2, -msc));
+              const float p3 = ex2_emul(fmaf(v[t + 3], sl2, -msc));
+              l += (p0 + p1) + (p2 + p3);
+              pk[t >> 1] = pack_bf16(p0, p1);
+              pk[(t >> 1) + 1] = pack_bf16(p2, p3);
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 32; t += 2) {
+              const float p0 = (c0 + t < N) ? ex2(fmaf(v[t], sl2, -msc)) : 0.f;
+              const float p1 = (c0 + t + 1 < N) ? ex2(fmaf(v[t + 1], sl2, -msc)) : 0.f;
+              l += p0 + p1;
+              pk[t >> 1] = pack_bf16(p0, p1);
+            }
           }
           tmem_st16(tR + (c0 >> 1), pk);                     // in place: columns [c0/2, c0/2+16) were read already
         }
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&ctl->p_full[g]);
+        GVIT_TR(12);
 
         mbar_wait(&ctl->o_full[g], it & 1);
         tc_fence_after();
+        GVIT_TR(13);
         const float inv = 1.0f / l;
         uint8_t* so = sm + s * F2_STAGE_BYTES + g * TILE_BYTES;   // the Q_g tile: dead once S_g has been issued
 #pragma unroll
@@ -388,7 +426,8 @@ __global__ void __launch_bounds__(F2_THREADS, 1) attn_fwd_tc2_kernel(const __gri
           }
         }
         tc_fence_before();
-        mbar_arrive(&ctl->t_free[g]);                        // TMEM region g may be overwritten by the next S_g
+        mbar_arrive(&ctl->t_free[g]);
+        GVIT_TR(14);                        // TMEM region g may be overwritten by the next S_g
         const int q = g * 128 + r;
         if (q < N) lse[((int64_t)b * H + h) * N + q] = (msc + log2f(l)) * LN2;
         fence_async_smem();                                  // generic-proxy tile writes -> visible to the TMA store
@@ -420,12 +459,12 @@ __global__ void __launch_bounds__(F2_THREADS, 1) attn_fwd_tc2_kernel(const __gri
 // MMA1 of the NEXT (kt, qt) is issued into sub-buffer g as soon as WG g has drained it, so the tensor pipe, the two
 // warpgroups and the epilogue stores overlap instead of taking turns (v1 ran them strictly in sequence: 470 us).
 // TMEM: S^T [0,128) | dP^T [128,256) | dV [256,320) | dK [320,384) | dQ [384,512).
-// Warp roles: 0-3 WG0, 4-7 WG1, 8 TMA producer, 9 MMA issuer (+ TMEM allocation).
+// Warp roles: 0-3 WG0, 4-7 WG1, 8 TMA producer, 9 MMA issuer (+ TMEM allocation), 10-11 delta / lse helpers.
 // =================================================================================================
-constexpr int B2_THREADS = 320;
+constexpr int B2_THREADS = 384;   // 8 warpgroup warps + TMA + MMA + 2 helper warps
 struct __align__(16) BwdCtrl {
   float lse2[2][256], delta[2][256];            // double-buffered by item parity
-  uint64_t kv_full[2], q_full[2], in_empty, s_full[2], p_full[2], st_free, dvk_free, dq_free;
+  uint64_t kv_full[2], q_full[2], in_empty, s_full[2], p_full[2], st_free, dvk_free, dq_free, delta_ready[2];
   uint32_t tmem_base;
 };
 // Q[2], dO[2], K[2], V[2] tiles + P^T staging (2 sub-tiles) + dS^T staging (2 sub-tiles)
@@ -490,7 +529,7 @@ __device__ __forceinline__ void bwd_chunk(float (&s)[W], float (&dp)[W], const f
     s[q4 + 3] = fmaf(s[q4 + 3], sl2, -l.w);
   }
 #pragma unroll
-  for (int e = 0; e < W; ++e) s[e] = ex2(s[e]);
+  for (int e = 0; e < W; ++e) s[e] = (e & 3) == 3 ? ex2_emul(s[e]) : ex2(s[e]);   // balance the MUFU and FMA pipes
 #pragma unroll
   for (int q4 = 0; q4 < W; q4 += 4) {
     const float4 d = *reinterpret_cast<const float4*>(delta + q4);
@@ -518,7 +557,8 @@ __device__ __forceinline__ int sub_width(int nq, int g) { return g == 0 ? min(64
 
 __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv,
                                                                     const __grid_constant__ CUtensorMap tm_do,
-                                                                    const __grid_constant__ CUtensorMap tm_dqkv, int N,
+                                                                    const __grid_constant__ CUtensorMap tm_dqkv,
+                                                                    const __grid_constant__ CUtensorMap tm_o, int N,
                                                                     int H, int items, float scale,
                                                                     const __nv_bfloat16* __restrict__ out,
                                                                     const __nv_bfloat16* __restrict__ dout,
@@ -552,6 +592,8 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
     mbar_init(&ctl->st_free, 1);
     mbar_init(&ctl->dvk_free, 256);
     mbar_init(&ctl->dq_free, 256);
+    mbar_init(&ctl->delta_ready[0], 2);
+    mbar_init(&ctl->delta_ready[1], 2);
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc(&ctl->tmem_base, 512);
@@ -582,6 +624,20 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
         if (T > 1) {
           tma_load_3d(sK + TILE_BYTES, &tm_qkv, (H + h) * 64, 128, b, &ctl->kv_full[1]);
           tma_load_3d(sV + TILE_BYTES, &tm_qkv, (2 * H + h) * 64, 128, b, &ctl->kv_full[1]);
+        }
+        // the NEXT item's tiles (and its O rows for the delta prologue) into L2 now: there is no shared memory to
+        // double-buffer 128 KB of inputs, and all CTAs start their loads together, so an un-prefetched item start
+        // waited ~5000 cycles on DRAM with the tensor pipe idle
+        const int wn = w + gridDim.x;
+        if (wn < items) {
+          const int bn = wn / H, hn = wn - bn * H;
+          for (int t = 0; t < T; ++t) {
+            tma_prefetch_3d(&tm_qkv, (H + hn) * 64, t * 128, bn);
+            tma_prefetch_3d(&tm_qkv, (2 * H + hn) * 64, t * 128, bn);
+            tma_prefetch_3d(&tm_qkv, hn * 64, t * 128, bn);
+            tma_prefetch_3d(&tm_do, hn * 64, t * 128, bn);
+            tma_prefetch_3d(&tm_o, hn * 64, t * 128, bn);
+          }
         }
       }
     }
@@ -660,6 +716,57 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
         umma_commit(&ctl->in_empty);                      // Q / dO / K / V tiles may be refilled
       }
     }
+  } else if (warp >= 10) {
+    // ------------------------------------------------------------------ helper warps: delta / lse ONE ITEM AHEAD
+    // delta = rowsum(dO * O) and lse in log2 units for the next item, into the item-parity double buffer, while the
+    // warpgroups are busy with the current item (as a warpgroup prologue it cost ~5000 idle cycles per item).
+    // 8 lanes share one 128-byte row (coalesced); helper h owns query rows [128h, 128h+128).
+    const int hw = warp - 10, sub = lane >> 3, ch = lane & 7;
+    const int64_t rstride = (int64_t)H * 64;
+    int ic = 0;
+    for (int w = blockIdx.x; w < items; w += gridDim.x, ++ic) {
+      const int b = w / H, h = w - b * H;
+      const int par = ic & 1;
+      if (ic >= 2) mbar_wait(&ctl->dq_free, (ic - 2) & 1);  // the warpgroups are done reading this buffer (item ic-2)
+      const __nv_bfloat16* obase = out + ((int64_t)b * N * H + h) * 64 + ch * 8;
+      const __nv_bfloat16* dbase = dout + ((int64_t)b * N * H + h) * 64 + ch * 8;
+      for (int rb = 0; rb < 4; ++rb) {
+        uint4 ov[8], dv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = hw * 128 + rb * 32 + i * 4 + sub;
+          ov[i] = dv[i] = make_uint4(0, 0, 0, 0);
+          if (row < N) {
+            ov[i] = *reinterpret_cast<const uint4*>(obase + row * rstride);
+            dv[i] = *reinterpret_cast<const uint4*>(dbase + row * rstride);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __nv_bfloat162* oa = reinterpret_cast<const __nv_bfloat162*>(&ov[i]);
+          const __nv_bfloat162* da = reinterpret_cast<const __nv_bfloat162*>(&dv[i]);
+          float d = 0.f;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 x = __bfloat1622float2(oa[e]), y = __bfloat1622float2(da[e]);
+            d = fmaf(x.x, y.x, d);
+            d = fmaf(x.y, y.y, d);
+          }
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          d += __shfl_xor_sync(0xffffffffu, d, 2);
+          d += __shfl_xor_sync(0xffffffffu, d, 4);
+          if (ch == 0) ctl->delta[par][hw * 128 + rb * 32 + i * 4 + sub] = d;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = hw * 128 + j * 32 + lane;
+        // +inf for padded queries: exp2(x - inf) = 0 masks them without a select
+        ctl->lse2[par][q] = q < N ? lse[((int64_t)b * H + h) * N + q] * LOG2E : __int_as_float(0x7f800000);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->delta_ready[par]);
+    }
   } else {
     // ------------------------------------------------------------------ softmax / epilogue warpgroups
     const int g = warp >> 2;                              // warpgroup == sub-tile == TMEM sub-buffer
@@ -673,45 +780,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
     for (int w = blockIdx.x; w < items; w += gridDim.x, ++ic) {
       const int b = w / H, h = w - b * H;
       const int par = ic & 1;
-      {  // delta = rowsum(dO * O): 8 lanes share one 128-byte row (coalesced; a row per thread made every load touch 32
-         // lines and cost ~9000 cycles per item), warp w owns rows [32w, 32w+32); lse in log2 units for row `tid`
-        const int wid = g * 4 + (warp & 3), sub = lane >> 3, ch = lane & 7;
-        const int64_t rstride = (int64_t)H * 64;
-        const __nv_bfloat16* obase = out + ((int64_t)b * N * H + h) * 64 + ch * 8;
-        const __nv_bfloat16* dbase = dout + ((int64_t)b * N * H + h) * 64 + ch * 8;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint4 ov[4], dv[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = wid * 32 + (half * 4 + i) * 4 + sub;
-            ov[i] = dv[i] = make_uint4(0, 0, 0, 0);
-            if (row < N) {
-              ov[i] = *reinterpret_cast<const uint4*>(obase + row * rstride);
-              dv[i] = *reinterpret_cast<const uint4*>(dbase + row * rstride);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const __nv_bfloat162* oa = reinterpret_cast<const __nv_bfloat162*>(&ov[i]);
-            const __nv_bfloat162* da = reinterpret_cast<const __nv_bfloat162*>(&dv[i]);
-            float d = 0.f;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 x = __bfloat1622float2(oa[e]), y = __bfloat1622float2(da[e]);
-              d = fmaf(x.x, y.x, d);
-              d = fmaf(x.y, y.y, d);
-            }
-            d += __shfl_xor_sync(0xffffffffu, d, 1);
-            d += __shfl_xor_sync(0xffffffffu, d, 2);
-            d += __shfl_xor_sync(0xffffffffu, d, 4);
-            if (ch == 0) ctl->delta[par][wid * 32 + (half * 4 + i) * 4 + sub] = d;
-          }
-        }
-        // +inf for padded queries: exp2(x - inf) = 0 masks them without a select
-        ctl->lse2[par][tid] = tid < N ? lse[((int64_t)b * H + h) * N + tid] * LOG2E : __int_as_float(0x7f800000);
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(&ctl->delta_ready[par], (ic >> 1) & 1);     // delta / lse of this item: written by the helper warps
       GVIT_TR(10);
       for (int kt = 0; kt < T; ++kt) {
         const int key = kt * 128 + t;
@@ -832,14 +901,16 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
   if (rc != GVIT_OK) return rc;
   rc = make_tmap_bf16_3d(&tm_do, dout, (uint64_t)H * 64, N, B, (uint64_t)H * 64, (uint64_t)N * H * 64, 128);
   if (rc != GVIT_OK) return rc;
-  CUtensorMap tm_dqkv;
+  CUtensorMap tm_dqkv, tm_o;
+  rc = make_tmap_bf16_3d(&tm_o, out, (uint64_t)H * 64, N, B, (uint64_t)H * 64, (uint64_t)N * H * 64, 128);
+  if (rc != GVIT_OK) return rc;
   rc = make_tmap_bf16_3d(&tm_dqkv, dqkv, (uint64_t)3 * H * 64, N, B, (uint64_t)3 * H * 64, (uint64_t)N * 3 * H * 64, 128);
   if (rc != GVIT_OK) return rc;
   GVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
   const int items = B * H;
   const int grid = items < num_sms() ? items : num_sms();
   (void)delta_ws;                                            // only the fp32-FMA path needs the global delta workspace
-  attn_bwd_tc_kernel<<<grid, B2_THREADS, BWD_SMEM, st>>>(tm_qkv, tm_do, tm_dqkv, N, H, items, scale,
+  attn_bwd_tc_kernel<<<grid, B2_THREADS, BWD_SMEM, st>>>(tm_qkv, tm_do, tm_dqkv, tm_o, N, H, items, scale,
                                                          static_cast<const __nv_bfloat16*>(out),
                                                          static_cast<const __nv_bfloat16*>(dout), lse);
   GVIT_CHECK_LAUNCH();

@@ -87,6 +87,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, int
       : "memory");
 }
 
+// tile -> L2 only (no shared-memory destination, no barrier): warms L2 for a later tma_load of the same box
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 // shared memory -> global tile store (rows outside the tensor are clipped by the TMA unit)
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
