@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) graph_dp_tc_kernel(const __grid_
   const int j0 = mt * 128;
   const int slabs = P.D / 64;
   const int NT = P.NT;
+  GVIT_TRACE_DECL
 
   if (warp == 4 && lane == 0) {
     prefetch_tmap(&tm_dz);
@@ -234,14 +235,18 @@ __global__ void __launch_bounds__(B_THREADS, 1) graph_dp_tc_kernel(const __grid_
       tc_fence_after();
       for (int s = 0; s < slabs; ++s) {
         const int st = s & 1;
+        GVIT_TR(1);
         mbar_wait(&ctl->full[st], (s >> 1) & 1);
+        GVIT_TR(2);
         mbar_wait(&ctl->out_free[st], ((s >> 1) & 1) ^ 1);          // accumulator buffer drained by the epilogue
         tc_fence_after();
+        GVIT_TR(3);
         const uint32_t aS = smem_u32(sStage + (size_t)st * P.stage_bytes);
         for (int kk = 0; kk < 2 * NT / 16; ++kk)                    // K = [Np rows of dZ | Np rows of P]
           umma_ss(tmem + st * 64, make_sdesc(aA + (kk >> 2) * TILE + (kk & 3) * 32), make_sdesc(aS + kk * 2048), idesc,
                   kk > 0);
         umma_commit(&ctl->out_full[st]);
+        GVIT_TR(4);
       }
     }
   } else {
@@ -254,39 +259,85 @@ __global__ void __launch_bounds__(B_THREADS, 1) graph_dp_tc_kernel(const __grid_
     const float* v_b = P.vals + (int64_t)b * E;
     const float* ds_b = P.dvals + (int64_t)b * E;
     // ---- coefficient tile ----------------------------------------------------------------------------------------
+    // Every global load of the build is issued up front (edge ids of the whole image, then the payload of the edges
+    // that land in this tile): two memory latencies in total.  v1 chased one latency per edge (17k cycles per CTA).
     {
+      constexpr int EPT = 16;                                       // edges per thread: 128 * 16 = 2048 per pass
+      // t_j in 64-bit fixed point as two native 32-bit shared atomics (lo with carry-out into hi): the sum is the same
+      // for every arrival order, and there is no 64-bit CAS loop (ATOMS.CAST.SPIN) under contention
+      auto tfix_add = [&](int j, long long v) {
+        unsigned int* cell = reinterpret_cast<unsigned int*>(&ctl->tfix[j]);
+        const unsigned int lo = static_cast<unsigned int>(static_cast<unsigned long long>(v));
+        const unsigned int hi = static_cast<unsigned int>(static_cast<unsigned long long>(v) >> 32);
+        const unsigned int old = atomicAdd(cell, lo);
+        atomicAdd(cell + 1, hi + ((old + lo) < old ? 1u : 0u));
+      };
+      int ii1[8];
+      float ds1[8], vv1[8];
+      const int kk1 = min(P.k, 8);
+      if (valid) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = jg * P.k + min(u, P.k - 1);
+          ii1[u] = idx_b[e];
+          ds1[u] = ds_b[e];
+          vv1[u] = v_b[e];
+        }
+      }
+      int jj[EPT];
+#pragma unroll
+      for (int u = 0; u < EPT; ++u) {
+        const int e = u * 128 + tid;
+        jj[u] = e < E ? idx_b[e] - j0 : -1;
+      }
       const uint4 z4 = make_uint4(0, 0, 0, 0);
       for (int i = tid; i < P.nblk * TILE / 16; i += 128) reinterpret_cast<uint4*>(sA)[i] = z4;
       for (int i = tid; i < 256; i += 128) ctl->rn[i] = i < P.Np ? P.rnorm[(int64_t)b * P.Np + i] : 0.f;
       ctl->tfix[tid] = 0;
+      float ww[EPT], dsv[EPT], vv[EPT];
+#pragma unroll
+      for (int u = 0; u < EPT; ++u) {
+        const int e = u * 128 + tid;
+        if (jj[u] >= 0 && jj[u] < 128) { ww[u] = w_b[e]; dsv[u] = ds_b[e]; vv[u] = v_b[e]; }
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      GVIT_TR(10);
       // phase 1: the row's own k entries of dS (forward edges j -> i)
       if (valid) {
         const float rnj = ctl->rn[jg];
         long long tacc = 0;
-        for (int s = 0; s < P.k; ++s) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (u < kk1) {
+            *a2_cell(sA, tid, NT + ii1[u]) = __float2bfloat16_rn(rnj * ctl->rn[ii1[u]] * ds1[u]);
+            tacc += __float2ll_rn(ds1[u] * vv1[u] * FIX_SCALE);
+          }
+        }
+        for (int s = 8; s < P.k; ++s) {                             // k > 8: the remaining own entries, one by one
           const int e = jg * P.k + s;
           const int i = idx_b[e];
           const float ds = ds_b[e];
           *a2_cell(sA, tid, NT + i) = __float2bfloat16_rn(rnj * ctl->rn[i] * ds);
           tacc += __float2ll_rn(ds * v_b[e] * FIX_SCALE);
         }
-        atomicAdd(reinterpret_cast<unsigned long long*>(&ctl->tfix[tid]), static_cast<unsigned long long>(tacc));
+        tfix_add(tid, tacc);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       // phase 2: every edge i -> j of the image that lands in this tile: A~^T[j,i] = w_e and M3[j,i] += rn_j rn_i dS_e.
       // (j,i) pairs are unique over the edges (a row's k neighbours are distinct), so the 16-bit updates do not race.
-      for (int e = tid; e < E; e += 128) {
+      auto apply_edge = [&](int e, int j, float we, float ds, float v) {
+        const int i = e / P.k;
+        *a2_cell(sA, j, i) = __float2bfloat16_rn(we);
+        __nv_bfloat16* c = a2_cell(sA, j, NT + i);
+        *c = __float2bfloat16_rn(__bfloat162float(*c) + ctl->rn[j0 + j] * ctl->rn[i] * ds);
+        tfix_add(j, __float2ll_rn(ds * v * FIX_SCALE));
+      };
+#pragma unroll
+      for (int u = 0; u < EPT; ++u)
+        if (jj[u] >= 0 && jj[u] < 128) apply_edge(u * 128 + tid, jj[u], ww[u], dsv[u], vv[u]);
+      for (int e = EPT * 128 + tid; e < E; e += 128) {              // images with more than 2048 edges
         const int j = idx_b[e] - j0;
-        if (j >= 0 && j < 128) {
-          const int i = e / P.k;
-          *a2_cell(sA, j, i) = __float2bfloat16_rn(w_b[e]);
-          const float ds = ds_b[e];
-          __nv_bfloat16* c = a2_cell(sA, j, NT + i);
-          *c = __float2bfloat16_rn(__bfloat162float(*c) + ctl->rn[j0 + j] * ctl->rn[i] * ds);
-          atomicAdd(reinterpret_cast<unsigned long long*>(&ctl->tfix[j]),
-                    static_cast<unsigned long long>(__float2ll_rn(ds * v_b[e] * FIX_SCALE)));
-        }
+        if (j >= 0 && j < 128) apply_edge(e, j, w_b[e], ds_b[e], v_b[e]);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       // phase 3: the radial term on the diagonal
@@ -298,13 +349,16 @@ __global__ void __launch_bounds__(B_THREADS, 1) graph_dp_tc_kernel(const __grid_
       }
       fence_async_smem();
       mbar_arrive(&ctl->a_ready);
+      GVIT_TR(11);
     }
     // ---- per slab: accumulator -> bf16 -> the (consumed) stage -> TMA tile store ------------------------------------
     const uint32_t tO = tmem_lane_base(tmem, warp);
     for (int s = 0; s < slabs; ++s) {
       const int st = s & 1;
+      GVIT_TR(12);
       mbar_wait(&ctl->out_full[st], (s >> 1) & 1);
       tc_fence_after();
+      GVIT_TR(13);
       float v0[32], v1[32];
       tmem_ld32(tO + st * 64, v0);
       tmem_ld32(tO + st * 64 + 32, v1);
@@ -329,6 +383,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) graph_dp_tc_kernel(const __grid_
         tma_store_wait_read();
         mbar_arrive(&ctl->empty[st]);                            // the producer may refill this stage
       }
+      GVIT_TR(14);
     }
   }
   tc_fence_before();
@@ -352,6 +407,8 @@ inline size_t b_smem(int NT, int* nblk, int* stage_bytes) {
 }
 
 }  // namespace
+
+GVIT_TRACE_SETTER(gvit_debug_set_trace_graph_bwd)
 
 bool graph_bwd_tc_supported(int Np, int D, int k) {
   int nblk, sb;
