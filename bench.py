@@ -204,11 +204,11 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
         "attn_bwd": (lambda i: _call("gvit_attn_bwd", _ptr(qkvs[i % 2]), _ptr(ao), _ptr(xs[i % R]), _ptr(lse), B, N, H, 64, 0.125, dt, _ptr(delta), _ptr(dqkv), st),
                      8 * B * N * D * e + 8 * B * H * N, 10.0 * B * N * N * D, "hbm", 12),
         "graph_reverse": (lambda i: _call("gvit_graph_reverse", _ptr(idxs[i % R][0]), B, Np, k, _ptr(rev[0][0]), _ptr(rev[0][1]), st),
-                          B * (Np * k * 8 + (Np + 1) * 4), 0.0, "hbm", 12),
+                          B * (Np * k * 8 + (Np + 1) * 4), 0.0, "hbm", 0),      # fp32 / large-shape path only
         "agg_bwd": (lambda i: _call("gvit_agg_bwd", _ptr(hs[i % R], off), bs, rs, B, Np, D, k, dt, _ptr(idxs[i % R][0]), _ptr(w), _ptr(xs[i % R], off), _ptr(rev[i % R][0]), _ptr(rev[i % R][1]), _ptr(dvals), _ptr(out, off), st),
-                    3 * tok + B * Np * k * 16, 4.0 * B * Np * k * D, "hbm", 12),
+                    3 * tok + B * Np * k * 16, 4.0 * B * Np * k * D, "hbm", 0),             # fp32 / large-shape path only
         "knn_bwd": (lambda i: _call("gvit_knn_bwd", _ptr(hs[i % R], off), bs, rs, B, Np, D, k, dt, _ptr(idxs[i % R][0]), _ptr(idxs[i % R][2]), _ptr(dvals), _ptr(rev[i % R][0]), _ptr(rev[i % R][1]), _ptr(out, off), st),
-                    3 * tok + B * Np * k * 12, 4.0 * B * Np * k * D, "hbm", 12),
+                    3 * tok + B * Np * k * 12, 4.0 * B * Np * k * D, "hbm", 0),             # fp32 / large-shape path only
         "graph_bwd": (lambda i: _call("gvit_graph_bwd", _ptr(hs[i % R], off), bs, rs, B, Np, D, k, dt, _ptr(idxs[i % R][0]), _ptr(idxs[i % R][1]), _ptr(w), _ptr(idxs[i % R][2]), _ptr(xs[i % R], off), bs, _ptr(dvals), _ptr(out, off), st),
                       3 * tok + B * Np * k * 20, 6.0 * B * Np * Np * D, "hbm", 12),
         "layernorm_fwd": (lambda i: _call("gvit_layernorm_fwd", _ptr(hs[i % R]), _ptr(gam), _ptr(bet), B * N, D, 1e-5, dt, dt, _ptr(out), _ptr(mean), _ptr(rstd), st),
