@@ -3,6 +3,7 @@
 // One warp per token row, 16-byte loads/stores, fp32 statistics, no shared-memory staging
 // (each element is touched once).
 #include "kernels.cuh"
+#include "philox.cuh"
 
 namespace gvit {
 namespace {
@@ -212,32 +213,6 @@ __global__ void ln_bwd_reduce_kernel(const float* __restrict__ partial, int nblk
   a = warp_sum(a);
   if (lane == 0) (which == 0 ? dgamma : dbeta)[col] = a;
 }
-
-// ---- Philox-4x32-10 (Salmon et al.), counter = (offset + i/4), key = seed --------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += 0x9E3779B9u;
-    key.y += 0xBB67AE85u;
-  }
-  return ctr;
-}
-
-// 8 keep decisions from ONE Philox block (16 random bits per element): bit j of the result is 1 when element j is
-// kept.  P(keep) = 1 - thresh16 / 65536 with thresh16 = round(p * 65536), i.e. p is honoured to 1.5e-5.
-__device__ __forceinline__ uint32_t keep_bits8(uint64_t seed, uint64_t counter, uint32_t thresh16) {
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)counter, (uint32_t)(counter >> 32), 0u, 0u),
-                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-  uint32_t bits = 0;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) bits |= (((w[j >> 1] >> (16 * (j & 1))) & 0xffffu) >= thresh16 ? 1u : 0u) << j;
-  return bits;
-}
-__device__ __forceinline__ uint32_t dropout_thresh16(float p) { return (uint32_t)__float2int_rn(p * 65536.0f); }
 
 // out = resid + dropout(y): y has the branch dtype Ty, resid / out the stream dtype Tx (Tx == Ty when resid is null).
 // The keep mask is stored as one BIT per element (byte i covers elements 8i..8i+7).

@@ -225,4 +225,28 @@ int gvit_gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_m
   return gelu_dropout_bwd(dout, u, keep_mask, n, p, dtype, du, D, colsum_out, partial_ws, static_cast<cudaStream_t>(stream));
 }
 
+int gvit_patchify(const void* img, int B, int C, int H, int W, int P, int in_dtype, int out_dtype, void* out, void* stream) {
+  TRY(check_dtype(in_dtype, "patchify"));
+  TRY(check_dtype(out_dtype, "patchify"));
+  GVIT_REQUIRE(img && out, GVIT_ERR_SHAPE, "patchify: null pointer");
+  GVIT_REQUIRE(in_dtype == out_dtype || in_dtype == GVIT_F32, GVIT_ERR_DTYPE, "patchify: a bf16 image cannot produce fp32 patches");
+  GVIT_REQUIRE(B >= 1 && C >= 1 && P >= 8 && P % 8 == 0 && H >= P && W >= P && H % P == 0 && W % P == 0, GVIT_ERR_SHAPE,
+               "patchify: bad sizes B=%d C=%d H=%d W=%d P=%d (P %% 8 == 0, H and W multiples of P)", B, C, H, W, P);
+  GVIT_REQUIRE(aligned16(img) && aligned16(out), GVIT_ERR_ALIGN, "patchify: 16-byte alignment required");
+  return patchify(img, B, C, H, W, P, in_dtype, out_dtype, out, static_cast<cudaStream_t>(stream));
+}
+
+int gvit_embed_assemble(const void* y, const void* bias, const void* cls, const void* pos, int B, int N, int D, float p,
+                        uint64_t seed, uint64_t offset, int dtype, int param_dtype, void* out, uint8_t* keep_mask, void* stream) {
+  TRY(check_dtype(dtype, "embed_assemble"));
+  TRY(check_dtype(param_dtype, "embed_assemble"));
+  GVIT_REQUIRE(y && cls && pos && out, GVIT_ERR_SHAPE, "embed_assemble: null pointer");
+  GVIT_REQUIRE(param_dtype == dtype || param_dtype == GVIT_F32, GVIT_ERR_DTYPE, "embed_assemble: parameters must be fp32 or the token dtype");
+  GVIT_REQUIRE(B >= 1 && N >= 2 && D >= 8 && D % 8 == 0, GVIT_ERR_SHAPE, "embed_assemble: bad sizes B=%d N=%d D=%d", B, N, D);
+  GVIT_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || keep_mask), GVIT_ERR_SHAPE, "embed_assemble: p=%f (keep_mask required when p > 0)", p);
+  GVIT_REQUIRE(aligned16(y) && aligned16(out) && aligned16(cls) && aligned16(pos) && (!bias || aligned16(bias)), GVIT_ERR_ALIGN,
+               "embed_assemble: 16-byte alignment required");
+  return embed_assemble(y, bias, cls, pos, B, N, D, p, seed, offset, dtype, param_dtype, out, keep_mask, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

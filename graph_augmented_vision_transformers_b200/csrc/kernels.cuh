@@ -60,4 +60,10 @@ int gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t 
 int gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, int64_t n, float p, int dtype, void* du,
                      int D, float* colsum_out, float* partial_ws, cudaStream_t st);
 
+
+// ---- token prologue : embed.cu
+int patchify(const void* img, int B, int C, int H, int W, int P, int in_dtype, int out_dtype, void* out, cudaStream_t st);
+int embed_assemble(const void* y, const void* bias, const void* cls, const void* pos, int B, int N, int D, float p,
+                   uint64_t seed, uint64_t offset, int dtype, int param_dtype, void* out, uint8_t* keep_mask, cudaStream_t st);
+
 }  // namespace gvit

@@ -203,6 +203,11 @@ class PatchEmbed(nn.Module):
         if tuple(x.shape[-2:]) != self.img_size:
             raise AssertionError(f"Input image size ({x.shape[-2]}*{x.shape[-1]}) doesn't match expected size "
                                  f"({self.img_size[0]}*{self.img_size[1]})")
+        if x.is_cuda and not _hooked(self.proj) and ops.patch_embed_supported(x, self.proj.weight):
+            # kernel == stride: a GEMM over the re-ordered image (gvit_patchify), no im2col, no NCHW<->NHWC passes
+            zeros = torch.zeros(1, self.num_patches + 1, self.proj.out_channels, dtype=self.proj.weight.dtype, device=x.device)
+            t = ops.patch_embed_tokens(x, self.proj.weight, self.proj.bias, zeros[:, :1], zeros, 0.0, False)
+            return t[:, 1:]
         return self.proj(x).flatten(2).transpose(1, 2)      # (B, Np, D)
 
 
@@ -263,7 +268,22 @@ class VisionTransformer(nn.Module):
             logger.error(f"Error loading MAE weights: {str(e)}")
             raise
 
+    def _prologue_fusable(self, x):
+        pe = self.patch_embed
+        return (x.is_cuda and not self.fp32_residual and not _hooked(pe) and not _hooked(pe.proj) and not _hooked(self.pos_drop)
+                and tuple(x.shape[-2:]) == pe.img_size and ops.patch_embed_supported(x, pe.proj.weight))
+
     def forward_features(self, x):
+        if x.is_cuda and torch.is_autocast_enabled("cuda"):
+            # one multi-tensor cast of the fp32 master parameters per step instead of one `.to()` per use
+            ops.refresh_shadows(self._parameters_for_shadow(), torch.bfloat16)
+        if self._prologue_fusable(x):
+            # vit.py:203-212 in three launches: patchify, projection GEMM, (bias + CLS + pos_embed + pos_drop)
+            x = ops.patch_embed_tokens(x, self.patch_embed.proj.weight, self.patch_embed.proj.bias, self.cls_token,
+                                       self.pos_embed, self.pos_drop.p, self.training)
+            for blk in self.blocks:
+                x = blk(x)
+            return self.norm(x[:, 0])
         x = self.patch_embed(x)
         # Residual-stream dtype: by default the stream follows the compute dtype (bf16 under autocast - half the
         # bytes on every LayerNorm / residual edge).  fp32_residual=True keeps torch.autocast's own behaviour,
@@ -276,6 +296,9 @@ class VisionTransformer(nn.Module):
         for blk in self.blocks:
             x = blk(x)
         return self.norm(x[:, 0])        # LayerNorm is per row: same value as vit.py:218-219's norm(x)[:, 0]
+
+    def _parameters_for_shadow(self):
+        return [p for n, p in self.named_parameters() if not n.startswith("head.")]
 
     def forward(self, x):
         return self.head(self.forward_features(x))

@@ -24,7 +24,7 @@ from . import _lib
 from ._lib import GVIT_BF16, GVIT_COLSUM_CHUNKS, GVIT_F32, GVIT_LN_PARTIALS
 
 __all__ = ["attention_core", "layer_norm", "pre_norm", "linear", "colsum", "linear_dropout_add", "linear_gelu_dropout", "dropout_add", "gelu_dropout", "knn_graph", "graph_reverse", "patch_graph",
-           "agg_gather", "launch_count", "reset_launch_count"]
+           "agg_gather", "patch_embed_tokens", "refresh_shadows", "launch_count", "reset_launch_count"]
 
 # kernels launched through the C ABI since the last reset (bench.py reports it as gpu_launches)
 _LAUNCHES = {"n": 0}
@@ -32,6 +32,7 @@ _KERNELS_PER_CALL = {
     "gvit_knn_fwd": 1, "gvit_graph_reverse": 1, "gvit_knn_bwd": 1, "gvit_agg_gather_fwd": 1, "gvit_agg_fwd": 1,
     "gvit_agg_bwd": 2, "gvit_graph_bwd": 2, "gvit_attn_fwd": 1, "gvit_attn_bwd": 1, "gvit_layernorm_fwd": 1, "gvit_layernorm_bwd": 2,
     "gvit_colsum": 2, "gvit_dropout_residual_fwd": 1, "gvit_dropout_bwd": 1, "gvit_gelu_dropout_fwd": 1, "gvit_gelu_dropout_bwd": 1,
+    "gvit_patchify": 1, "gvit_embed_assemble": 1,
 }
 
 
@@ -80,6 +81,76 @@ def _autocast_dtype(t: torch.Tensor):
             return torch.bfloat16
         raise TypeError(f"unsupported dtype {t.dtype}")
     return t.dtype
+
+
+# ------------------------------------------------------------------------------------------------
+# Parameter shadows: the 16-bit copies of the fp32 master parameters that autocast would make one `.to()` at a time
+# (335 cast kernels per forward of ViT-B + graph) are made by ONE multi-tensor copy per step, and the operators below
+# take the MASTER parameter as their autograd input: their backward returns fp32 gradients directly (the weight-gradient
+# GEMM accumulates and writes fp32), so there is no 16-bit gradient and no cast on the way back either.
+# ------------------------------------------------------------------------------------------------
+_SHADOWS: dict = {}          # id(param) -> (weakref(param), version, data_ptr, shadow tensor)
+
+
+def refresh_shadows(params, dtype: torch.dtype) -> None:
+    """Bring the `dtype` shadows of `params` up to date with one multi-tensor copy (stale or missing ones only)."""
+    import weakref
+    src, dst = [], []
+    for prm in params:
+        if prm is None or prm.dtype == dtype or not prm.is_cuda:
+            continue
+        e = _SHADOWS.get(id(prm))
+        if e is not None and e[0]() is prm and e[3].dtype == dtype and e[3].shape == prm.shape:
+            if e[1] == prm._version and e[2] == prm.data_ptr():
+                continue
+            sh = e[3]
+        else:
+            sh = torch.empty_like(prm, dtype=dtype, memory_format=torch.contiguous_format)
+        _SHADOWS[id(prm)] = (weakref.ref(prm, lambda _r, k=id(prm): _SHADOWS.pop(k, None)), prm._version, prm.data_ptr(), sh)
+        src.append(prm.detach())
+        dst.append(sh)
+    if src:
+        with torch.no_grad():
+            torch._foreach_copy_(dst, src)
+
+
+def _shadow(prm, dtype: torch.dtype):
+    """`prm` in the compute dtype, without an autograd edge: the parameter itself, its fresh shadow, or a one-off cast."""
+    if prm is None:
+        return None
+    t = prm.detach()
+    if t.dtype == dtype:
+        return t if t.is_contiguous() else t.contiguous()
+    e = _SHADOWS.get(id(prm))
+    if e is not None and e[0]() is prm and e[1] == prm._version and e[2] == prm.data_ptr() and e[3].dtype == dtype:
+        return e[3]
+    return t.to(dtype).contiguous()
+
+
+def _wgrad(dy2: torch.Tensor, x2: torch.Tensor, master_dtype: torch.dtype) -> torch.Tensor:
+    """dW = dy2^T x2 in the MASTER parameter's dtype: an fp32 master over 16-bit operands gets the GEMM's fp32
+    accumulator written out as is (no bf16 rounding of the gradient, no cast kernel afterwards)."""
+    if master_dtype == torch.float32 and dy2.dtype != torch.float32:
+        return torch.mm(dy2.t(), x2, out_dtype=torch.float32)
+    return (dy2.t() @ x2).to(master_dtype)
+
+
+def _colsum_ws(rows: int, D: int, device) -> torch.Tensor:
+    """Workspace of gvit_colsum / the *_bwd column sums: (row chunks the launcher will use) x D floats."""
+    cb = (D + 255) // 256
+    n = min(GVIT_COLSUM_CHUNKS, (6 * _sm_count(device) + cb - 1) // cb + 1, max(1, (rows + 31) // 32) + 1)
+    return torch.empty(n * D, dtype=torch.float32, device=device)
+
+
+_SMS: dict = {}
+
+
+def _sm_count(device) -> int:
+    i = torch.device(device).index
+    i = torch.cuda.current_device() if i is None else i
+    if i not in _SMS:
+        _SMS[i] = torch.cuda.get_device_properties(i).multi_processor_count
+    return _SMS[i]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -134,7 +205,7 @@ def colsum(x2: torch.Tensor) -> torch.Tensor:
     _check_cuda(x2)
     rows, D = x2.shape
     out = torch.empty(D, dtype=torch.float32, device=x2.device)
-    ws = torch.empty(GVIT_COLSUM_CHUNKS * D, dtype=torch.float32, device=x2.device)
+    ws = _colsum_ws(rows, D, x2.device)
     _call("gvit_colsum", _ptr(x2), rows, D, _dtype_code(x2), _ptr(out), _ptr(ws), _stream())
     return out
 
@@ -145,10 +216,12 @@ class _Linear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight)
+        w = _shadow(weight, x.dtype)
+        ctx.save_for_backward(x, w)
         ctx.has_bias = bias is not None
         ctx.bias_dtype = bias.dtype if bias is not None else None
-        return F.linear(x, weight, None if bias is None else bias.to(x.dtype))
+        ctx.w_dtype = weight.dtype
+        return F.linear(x, w, _shadow(bias, x.dtype))
 
     @staticmethod
     def backward(ctx, dy):
@@ -157,7 +230,7 @@ class _Linear(torch.autograd.Function):
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
         dx = (dy2 @ weight).view(x.shape) if ctx.needs_input_grad[0] else None
-        dw = dy2.t() @ x.reshape(-1, x.shape[-1]) if ctx.needs_input_grad[1] else None
+        dw = _wgrad(dy2, x.reshape(-1, x.shape[-1]), ctx.w_dtype) if ctx.needs_input_grad[1] else None
         db = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = (colsum(dy2) if dy2.shape[1] % 8 == 0 else dy2.float().sum(0)).to(ctx.bias_dtype)
@@ -169,7 +242,7 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> 
     _check_cuda(x, weight, bias)
     dt = _autocast_dtype(x)
     with torch.autocast("cuda", enabled=False):
-        return _Linear.apply(x.to(dt), weight.to(dt), bias)      # the bias parameter itself: its gradient comes back fp32
+        return _Linear.apply(x.to(dt), weight, bias)      # the master parameters themselves: their gradients come back in their dtype
 
 
 # ------------------------------------------------------------------------------------------------
@@ -186,6 +259,8 @@ class _LayerNorm(torch.autograd.Function):
         y = torch.empty(x.shape, dtype=_TORCH_DT[y_code], device=x.device)
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        ctx.w_dtype = weight.dtype
+        weight, bias = _shadow(weight, x.dtype), _shadow(bias, x.dtype)
         _call("gvit_layernorm_fwd", _ptr(x), _ptr(weight), _ptr(bias), rows, D, float(eps), _dtype_code(x), y_code,
               _ptr(y), _ptr(mean), _ptr(rstd), _stream())
         ctx.save_for_backward(x, weight, mean, rstd)
@@ -212,7 +287,7 @@ def _layer_norm_backward(ctx, dy, dx_add):
     ws = torch.empty(2 * GVIT_LN_PARTIALS * D, dtype=torch.float32, device=x.device)
     _call("gvit_layernorm_bwd", _ptr(dy), _ptr(x), _ptr(weight), _ptr(mean), _ptr(rstd), rows, D, _dtype_code(x),
           ctx.y_code, _ptr(dx_add), _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(ws), _stream())
-    return dx, dgamma.to(weight.dtype), dbeta.to(weight.dtype)
+    return dx, dgamma.to(ctx.w_dtype), dbeta.to(ctx.w_dtype)
 
 
 class _PreNorm(torch.autograd.Function):
@@ -244,7 +319,7 @@ def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: f
         x = x.to(torch.bfloat16 if x.dtype == torch.float16 else torch.float32)
     y_code = GVIT_BF16 if (x.dtype == torch.bfloat16 or torch.is_autocast_enabled("cuda")) else GVIT_F32
     with torch.autocast("cuda", enabled=False):
-        return _LayerNorm.apply(x.contiguous(), weight.to(x.dtype), bias.to(x.dtype), float(eps), y_code)
+        return _LayerNorm.apply(x.contiguous(), weight, bias, float(eps), y_code)
 
 
 def pre_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5):
@@ -256,7 +331,7 @@ def pre_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: flo
         x = x.to(torch.bfloat16 if x.dtype == torch.float16 else torch.float32)
     y_code = GVIT_BF16 if (x.dtype == torch.bfloat16 or torch.is_autocast_enabled("cuda")) else GVIT_F32
     with torch.autocast("cuda", enabled=False):
-        return _PreNorm.apply(x.contiguous(), weight.to(x.dtype), bias.to(x.dtype), float(eps), y_code)
+        return _PreNorm.apply(x.contiguous(), weight, bias, float(eps), y_code)
 
 
 def _draw_seed() -> int:
@@ -355,9 +430,9 @@ def gelu_dropout(u: torch.Tensor, p: float, training: bool) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # Linear + edge, as one autograd node each: the edge's backward kernel also yields the Linear's bias gradient
 # ------------------------------------------------------------------------------------------------
-def _linear_grads(ctx_needs, x, weight, dy2):
+def _linear_grads(ctx_needs, x, weight, dy2, w_dtype):
     dx = (dy2 @ weight).view(x.shape) if ctx_needs[0] else None
-    dw = dy2.t() @ x.reshape(-1, x.shape[-1]) if ctx_needs[1] else None
+    dw = _wgrad(dy2, x.reshape(-1, x.shape[-1]), w_dtype) if ctx_needs[1] else None
     return dx, dw
 
 
@@ -369,7 +444,9 @@ class _LinearDropoutAdd(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, resid, p, seed):
         ctx.bias_dtype = bias.dtype if bias is not None else None
-        y = F.linear(x, weight, None if bias is None else bias.to(x.dtype))
+        ctx.w_dtype = weight.dtype
+        weight = _shadow(weight, x.dtype)
+        y = F.linear(x, weight, _shadow(bias, x.dtype))
         n = y.numel()
         out = torch.empty_like(y if resid is None else resid)
         mask = torch.empty(n // 8, dtype=torch.uint8, device=y.device) if p > 0 else None
@@ -387,13 +464,13 @@ class _LinearDropoutAdd(torch.autograd.Function):
         dy = torch.empty(dout.shape, dtype=ctx.y_dtype, device=dout.device)
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
         db = torch.empty(Dn, dtype=torch.float32, device=dout.device) if want_db else None
-        ws = torch.empty(GVIT_COLSUM_CHUNKS * Dn, dtype=torch.float32, device=dout.device) if want_db else None
+        ws = _colsum_ws(dout.numel() // Dn, Dn, dout.device) if want_db else None
         if ctx.p > 0 or want_db:
             _call("gvit_dropout_bwd", _ptr(dout), _ptr(mask), dout.numel(), float(ctx.p), _dtype_code(dout),
                   _dtype_code(dy), _ptr(dy), Dn, _ptr(db), _ptr(ws), _stream())
         else:
             dy = dout.to(ctx.y_dtype)
-        dx, dw = _linear_grads(ctx.needs_input_grad, x, weight, dy.view(-1, Dn))
+        dx, dw = _linear_grads(ctx.needs_input_grad, x, weight, dy.view(-1, Dn), ctx.w_dtype)
         return dx, dw, (db.to(ctx.bias_dtype) if want_db else None), (dout if ctx.has_resid else None), None, None
 
 
@@ -404,7 +481,9 @@ class _LinearGeluDropout(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, p, seed):
         ctx.bias_dtype = bias.dtype if bias is not None else None
-        u = F.linear(x, weight, None if bias is None else bias.to(x.dtype))
+        ctx.w_dtype = weight.dtype
+        weight = _shadow(weight, x.dtype)
+        u = F.linear(x, weight, _shadow(bias, x.dtype))
         n = u.numel()
         out = torch.empty_like(u)
         mask = torch.empty(n // 8, dtype=torch.uint8, device=u.device) if p > 0 else None
@@ -421,10 +500,10 @@ class _LinearGeluDropout(torch.autograd.Function):
         du = torch.empty_like(u)
         want_db = ctx.has_bias and ctx.needs_input_grad[2]
         db = torch.empty(Dn, dtype=torch.float32, device=u.device) if want_db else None
-        ws = torch.empty(GVIT_COLSUM_CHUNKS * Dn, dtype=torch.float32, device=u.device) if want_db else None
+        ws = _colsum_ws(u.numel() // Dn, Dn, u.device) if want_db else None
         _call("gvit_gelu_dropout_bwd", _ptr(dout), _ptr(u), _ptr(mask), u.numel(), float(ctx.p), _dtype_code(u),
               _ptr(du), Dn, _ptr(db), _ptr(ws), _stream())
-        dx, dw = _linear_grads(ctx.needs_input_grad, x, weight, du.view(-1, Dn))
+        dx, dw = _linear_grads(ctx.needs_input_grad, x, weight, du.view(-1, Dn), ctx.w_dtype)
         return dx, dw, (db.to(ctx.bias_dtype) if want_db else None), None, None
 
 
@@ -442,7 +521,7 @@ def linear_dropout_add(x, weight, bias, resid, p: float, training: bool):
         return dropout_add(linear(x, weight, bias), resid, p, training)
     seed = _draw_seed() if p > 0 else 0
     with torch.autocast("cuda", enabled=False):
-        return _LinearDropoutAdd.apply(x.to(dt), weight.to(dt), bias, None if resid is None else resid.contiguous(), p, seed)
+        return _LinearDropoutAdd.apply(x.to(dt), weight, bias, None if resid is None else resid.contiguous(), p, seed)
 
 
 def linear_gelu_dropout(x, weight, bias, p: float, training: bool):
@@ -454,7 +533,81 @@ def linear_gelu_dropout(x, weight, bias, p: float, training: bool):
         return gelu_dropout(linear(x, weight, bias), p, training)
     seed = _draw_seed() if p > 0 else 0
     with torch.autocast("cuda", enabled=False):
-        return _LinearGeluDropout.apply(x.to(dt), weight.to(dt), bias, p, seed)
+        return _LinearGeluDropout.apply(x.to(dt), weight, bias, p, seed)
+
+
+# ------------------------------------------------------------------------------------------------
+# f4: token prologue - PatchEmbed + CLS + pos_embed + pos_drop (vit.py:25-36, 207-212)
+# ------------------------------------------------------------------------------------------------
+class _PatchEmbedTokens(torch.autograd.Function):
+    """tokens = dropout(cat([cls, conv(img).flatten(2).T + b]) + pos): gvit_patchify, ONE library GEMM over all
+    B*(1+Np) rows (the CLS slot of the patch matrix is zero), gvit_embed_assemble.  The image gets no gradient."""
+
+    @staticmethod
+    def forward(ctx, img, conv_w, conv_b, cls, pos, p, seed, dt):
+        B, C, H, W = img.shape
+        D, P = conv_w.shape[0], conv_w.shape[-1]
+        N, K = (H // P) * (W // P) + 1, C * P * P
+        st = _stream()
+        patches = torch.empty((B, N, K), dtype=dt, device=img.device)
+        _call("gvit_patchify", _ptr(img), B, C, H, W, P, _dtype_code(img), _dtype_code(patches), _ptr(patches), st)
+        y = F.linear(patches.view(B * N, K), _shadow(conv_w, dt).view(D, K))
+        prm = [cls, pos] + ([conv_b] if conv_b is not None else [])
+        if all(t.dtype == torch.float32 for t in prm) or all(t.dtype == dt for t in prm):
+            pd = prm[0].dtype
+        else:
+            pd = dt
+        b_, c_, p_ = _shadow(conv_b, pd), _shadow(cls, pd), _shadow(pos, pd)
+        out = torch.empty((B, N, D), dtype=dt, device=img.device)
+        mask = torch.empty(B * N * D // 8, dtype=torch.uint8, device=img.device) if p > 0 else None
+        _call("gvit_embed_assemble", _ptr(y), _ptr(b_), _ptr(c_), _ptr(p_), B, N, D, float(p), int(seed), 0,
+              _dtype_code(out), GVIT_F32 if pd == torch.float32 else GVIT_BF16, _ptr(out), _ptr(mask), st)
+        ctx.save_for_backward(patches, mask)
+        ctx.p = p
+        ctx.meta = (conv_w.shape, conv_w.dtype, None if conv_b is None else conv_b.dtype, cls.dtype, pos.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        patches, mask = ctx.saved_tensors
+        w_shape, w_dt, b_dt, cls_dt, pos_dt = ctx.meta
+        B, N, K = patches.shape
+        D = dout.shape[-1]
+        dout = dout.contiguous()
+        if ctx.p > 0:
+            d = torch.empty_like(dout)
+            _call("gvit_dropout_bwd", _ptr(dout), _ptr(mask), dout.numel(), float(ctx.p), _dtype_code(dout),
+                  _dtype_code(d), _ptr(d), 0, None, None, _stream())
+        else:
+            d = dout
+        dsum = colsum(d.view(B, N * D)).view(N, D)              # fp32 sum over the batch: d pos_embed
+        dpos = dsum.view(1, N, D).to(pos_dt) if ctx.needs_input_grad[4] else None
+        dcls = dsum[0].view(1, 1, D).to(cls_dt) if ctx.needs_input_grad[3] else None
+        dbias = dsum[1:].sum(0).to(b_dt) if (b_dt is not None and ctx.needs_input_grad[2]) else None
+        dw = _wgrad(d.view(B * N, D), patches.view(B * N, K), w_dt).view(w_shape) if ctx.needs_input_grad[1] else None
+        return None, dw, dbias, dcls, dpos, None, None, None
+
+
+def patch_embed_supported(img: torch.Tensor, conv_w: torch.Tensor) -> bool:
+    P = conv_w.shape[-1]
+    return (img.dim() == 4 and conv_w.dim() == 4 and conv_w.shape[-2] == P and P % 8 == 0 and img.shape[1] == conv_w.shape[1]
+            and img.shape[-1] % P == 0 and img.shape[-2] % P == 0 and conv_w.shape[0] % 8 == 0)
+
+
+def patch_embed_tokens(img, conv_w, conv_b, cls_token, pos_embed, p: float, training: bool):
+    """The (B, 1+Np, D) token tensor of vit.py:203-212 from the image: patch projection (Conv2d with kernel == stride,
+    vit.py:22,34), CLS token, position embedding and pos_drop.  Runs in bf16 under autocast, else in fp32."""
+    _check_cuda(img, conv_w, conv_b, cls_token, pos_embed)
+    if not patch_embed_supported(img, conv_w):
+        raise ValueError(f"patch_embed_tokens needs a square patch size that is a multiple of 8 dividing the image; got image "
+                         f"{tuple(img.shape)} and weight {tuple(conv_w.shape)}")
+    p = float(p) if training else 0.0
+    dt = torch.bfloat16 if torch.is_autocast_enabled("cuda") else _autocast_dtype(conv_w)
+    if img.dtype not in (torch.float32, torch.bfloat16) or (img.dtype == torch.bfloat16 and dt == torch.float32):
+        img = img.float()
+    seed = _draw_seed() if p > 0 else 0
+    with torch.autocast("cuda", enabled=False):
+        return _PatchEmbedTokens.apply(img.contiguous(), conv_w, conv_b, cls_token, pos_embed, p, seed, dt)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -528,6 +681,9 @@ class _PatchGraph(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, h, weight, bias, resid, k):
+        ctx.w_dtype = weight.dtype
+        ctx.b_dtype = bias.dtype if bias is not None else None
+        weight, bias = _shadow(weight, h.dtype), _shadow(bias, h.dtype)
         off, bs, rs, B, Np, D = _token_view(h)
         dt = _dtype_code(h)
         st = _stream()
@@ -571,8 +727,8 @@ class _PatchGraph(torch.autograd.Function):
             # bf16: z / dz laid out like h; GEMMs over all rows (the CLS row of z is zero, the CLS row of dz is unused),
             # then both sparse stages as two per-image tensor-core GEMMs (no reverse adjacency)
             d2 = dout.view(B * (Np + 1), D)
-            dweight = d2.t() @ z.view(B * (Np + 1), D) if ctx.needs_input_grad[1] else None
-            dbias = ((colsum(d2) - dout[:, 0].float().sum(0)).to(dout.dtype)
+            dweight = _wgrad(d2, z.view(B * (Np + 1), D), ctx.w_dtype) if ctx.needs_input_grad[1] else None
+            dbias = ((colsum(d2) - dout[:, 0].float().sum(0)).to(ctx.b_dtype)
                      if (ctx.has[0] and ctx.needs_input_grad[2]) else None)
             dh = None
             if ctx.needs_input_grad[0]:
@@ -587,8 +743,8 @@ class _PatchGraph(torch.autograd.Function):
             z = z[:, 1:].contiguous()
         dy = dout[:, 1:, :]
         dy2 = dy.reshape(B * Np, D)
-        dweight = dy2.t() @ z.view(B * Np, D) if ctx.needs_input_grad[1] else None
-        dbias = dy2.sum(0) if (ctx.has[0] and ctx.needs_input_grad[2]) else None
+        dweight = _wgrad(dy2, z.view(B * Np, D), ctx.w_dtype) if ctx.needs_input_grad[1] else None
+        dbias = dy2.float().sum(0).to(ctx.b_dtype) if (ctx.has[0] and ctx.needs_input_grad[2]) else None
         dh = None
         if ctx.needs_input_grad[0]:
             dz = (dy2 @ weight).view(B, Np, D)
@@ -618,8 +774,7 @@ def patch_graph(h: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None
     dt = _autocast_dtype(h)
     with torch.autocast("cuda", enabled=False):
         fuse_resid = resid is not None and resid.dtype == dt
-        out, idx, vals = _PatchGraph.apply(h.to(dt).contiguous(), weight.to(dt).contiguous(),
-                                           None if bias is None else bias.to(dt).contiguous(),
+        out, idx, vals = _PatchGraph.apply(h.to(dt).contiguous(), weight, bias,
                                            resid.contiguous() if fuse_resid else None, int(k))
         if resid is not None and not fuse_resid:
             out = resid + out

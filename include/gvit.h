@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GVIT_ABI_VERSION 6
+#define GVIT_ABI_VERSION 7
 #if defined(__GNUC__)
 #define GVIT_API __attribute__((visibility("default")))
 #else
@@ -163,6 +163,21 @@ GVIT_API int gvit_gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t s
 /* colsum_out / partial_ws / D as for gvit_dropout_bwd: the bias gradient of fc1 (vit.py:90) in the same pass. */
 GVIT_API int gvit_gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, int64_t n, float p, int dtype,
                           void* du, int D, float* colsum_out, float* partial_ws, void* stream);
+
+/* ---- f4: token prologue, replaces PatchEmbed (/root/reference/src/models/vit.py:25-36) and the CLS / pos_embed /
+ * pos_drop lines vit.py:207-212.  A kernel == stride convolution is a GEMM over non-overlapping patches:
+ * gvit_patchify re-orders the image (B,C,H,W) into the patch matrix, laid out like the token tensor: out is
+ * (B, 1+Np, C*P*P) with row 0 of every image ZERO (the CLS slot) and row 1+py*(W/P)+px holding patch (py,px) in
+ * (c,i,j) feature order - the order of Conv2d's weight.view(D, C*P*P).  The projection (and its weight gradient) is then
+ * a plain GEMM over all B*(1+Np) rows.  in_dtype: image dtype; out_dtype: patch dtype (the fp32 -> bf16 cast of
+ * autocast is folded in).  P % 8 == 0. */
+GVIT_API int gvit_patchify(const void* img, int B, int C, int H, int W, int P, int in_dtype, int out_dtype, void* out, void* stream);
+/* out[b,0,:] = cls + pos[0];  out[b,n,:] = y[b,n,:] + bias + pos[n] for n >= 1 (row 0 of y is ignored);  then
+ * dropout(p) with the keep-mask convention of gvit_dropout_residual_fwd (mask index = element index / 8).  y / out:
+ * (B,N,D) of `dtype`; bias (D, nullable), cls (D), pos (N,D) of `param_dtype` (GVIT_F32 master parameters may feed a
+ * bf16 stream).  The backward is gvit_dropout_bwd followed by gvit_colsum over the batch. */
+GVIT_API int gvit_embed_assemble(const void* y, const void* bias, const void* cls, const void* pos, int B, int N, int D, float p,
+                        uint64_t seed, uint64_t offset, int dtype, int param_dtype, void* out, uint8_t* keep_mask, void* stream);
 
 #ifdef __cplusplus
 }

@@ -152,3 +152,81 @@ def test_fused_linear_edges_match_the_unfused_composition(dtype, p):
     tol = 1e-5 if dtype == torch.float32 else 2e-2
     for a, b in zip(*outs):
         assert rel_err(a, b) < tol
+
+
+def _prologue_reference(img, w, b, cls, pos):
+    """vit.py:34-36, 207-211 on the CPU in fp32."""
+    y = F.conv2d(img, w, b, stride=w.shape[-1]).flatten(2).transpose(1, 2)
+    return torch.cat((cls.expand(img.shape[0], -1, -1), y), dim=1) + pos
+
+
+@pytest.mark.parametrize("B,C,S,P,D", [(3, 3, 224, 16, 768), (2, 3, 64, 8, 128), (1, 1, 48, 16, 64), (2, 3, 384, 16, 1024)])
+@pytest.mark.parametrize("mode", ["fp32", "autocast"])
+def test_patch_embed_tokens_forward_backward(B, C, S, P, D, mode):
+    """f4 - PatchEmbed + CLS + pos_embed (vit.py:25-36, 207-211) as patchify + GEMM + assemble, against Conv2d."""
+    g = torch.Generator().manual_seed(S + D)
+    N = (S // P) ** 2 + 1
+    img = torch.randn(B, C, S, S, generator=g)
+    w = torch.randn(D, C, P, P, generator=g) * 0.05
+    b, cls, pos = torch.randn(D, generator=g) * 0.1, torch.randn(1, 1, D, generator=g) * 0.1, torch.randn(1, N, D, generator=g) * 0.1
+    cot = torch.randn(B, N, D, generator=g)
+    ref_p = [t.clone().requires_grad_(True) for t in (w, b, cls, pos)]
+    ref = _prologue_reference(img, *ref_p)
+    ref.backward(cot)
+    dev_p = [t.to(DEV).requires_grad_(True) for t in (w, b, cls, pos)]
+    if mode == "autocast":
+        ops.refresh_shadows(dev_p, torch.bfloat16)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = ops.patch_embed_tokens(img.to(DEV), *dev_p, 0.1, training=False)
+        assert out.dtype == torch.bfloat16
+        out.backward(cot.to(DEV, torch.bfloat16))
+        tol = TOL_BF16
+    else:
+        out = ops.patch_embed_tokens(img.to(DEV), *dev_p, 0.1, training=False)
+        out.backward(cot.to(DEV))
+        tol = TOL_F32
+    assert rel_err(out, ref) < tol
+    for d, r, name in zip(dev_p, ref_p, ("weight", "bias", "cls", "pos")):
+        assert d.grad.dtype == torch.float32 and rel_err(d.grad, r.grad) < tol, name
+
+
+def test_patch_embed_tokens_dropout_and_errors():
+    g = torch.Generator().manual_seed(5)
+    img, w = torch.randn(4, 3, 64, 64, generator=g).to(DEV), (torch.randn(128, 3, 16, 16, generator=g) * 0.05).to(DEV)
+    b, cls, pos = torch.zeros(128, device=DEV), torch.zeros(1, 1, 128, device=DEV), torch.zeros(1, 17, 128, device=DEV)
+    pos.requires_grad_(True)
+    clean = ops.patch_embed_tokens(img, w, b, cls, pos, 0.25, training=False)
+    torch.manual_seed(3)
+    y = ops.patch_embed_tokens(img, w, b, cls, pos, 0.25, training=True)
+    y.backward(torch.ones_like(y))
+    kept = y != 0
+    assert abs(float(kept[:, 1:].float().mean()) - 0.75) < 2e-2
+    assert rel_err(y[kept], clean[kept] / 0.75) < 1e-6
+    # d pos = sum over the batch of keep / (1 - p)
+    assert rel_err(pos.grad[0, 1:], kept[:, 1:].float().sum(0) / 0.75) < 1e-6
+    torch.manual_seed(3)
+    assert torch.equal(ops.patch_embed_tokens(img, w, b, cls, pos, 0.25, training=True), y)
+    with pytest.raises(ValueError):
+        ops.patch_embed_tokens(img, w[:, :, :12, :12].contiguous(), b, cls, pos, 0.0, False)     # 12 is not a multiple of 8
+    with pytest.raises(RuntimeError):
+        ops.patch_embed_tokens(img.cpu(), w, b, cls, pos, 0.0, False)
+
+
+def test_parameter_shadows_follow_the_master():
+    w = torch.nn.Parameter(torch.randn(64, 64, device=DEV))
+    x = torch.randn(8, 64, device=DEV, dtype=torch.bfloat16)
+    ops.refresh_shadows([w], torch.bfloat16)
+    s0 = ops._shadow(w, torch.bfloat16)
+    assert s0.dtype == torch.bfloat16 and torch.equal(s0, w.detach().bfloat16())
+    assert ops._shadow(w, torch.bfloat16) is s0                        # fresh: reused, no cast
+    with torch.no_grad():
+        w.add_(1.0)                                                    # an optimizer step bumps the version
+    s1 = ops._shadow(w, torch.bfloat16)
+    assert s1 is not s0 and torch.equal(s1, w.detach().bfloat16())     # stale shadow is never served
+    ops.refresh_shadows([w], torch.bfloat16)
+    assert ops._shadow(w, torch.bfloat16) is s0 and torch.equal(s0, w.detach().bfloat16())    # refreshed in place
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = ops.linear(x, w, None)
+    y.sum().backward()
+    assert w.grad.dtype == torch.float32
+    assert rel_err(w.grad, (torch.ones(8, 64, device=DEV).t() @ x.float())) < 1e-6          # fp32 accumulator written out unrounded
