@@ -215,7 +215,7 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
                           2 * B * N * D * e, 0.0, "hbm", 36),
         "layernorm_bwd": (lambda i: _call("gvit_layernorm_bwd", _ptr(xs[i % R]), _ptr(hs[i % R]), _ptr(gam), _ptr(mean), _ptr(rstd), B * N, D, dt, dt, None, _ptr(out), _ptr(dgb[0]), _ptr(dgb[1]), _ptr(ws), st),
                           3 * B * N * D * e, 0.0, "hbm", 1),
-        "gelu_dropout_fwd": (lambda i: _call("gvit_gelu_dropout_fwd", _ptr(u4[i % 2]), B * N * 4 * D, 0.1, 1234, 0, dt, _ptr(o4), _ptr(m4), st),
+        "gelu_dropout_fwd": (lambda i: _call("gvit_gelu_dropout_fwd", _ptr(u4[i % 2]), B * N * 4 * D, 0.1, 1234, 0, None, dt, _ptr(o4), _ptr(m4), st),
                              2 * B * N * 4 * D * e + B * N * 4 * D // 8, 0.0, "hbm", 12),
         "gelu_dropout_bwd": (lambda i: _call("gvit_gelu_dropout_bwd", _ptr(u4[(i + 1) % 2]), _ptr(u4[i % 2]), _ptr(m4), B * N * 4 * D, 0.1, dt, _ptr(o4), 4 * D, _ptr(cs_out), _ptr(cs_ws), st),
                              3 * B * N * 4 * D * e + B * N * 4 * D // 8, 0.0, "hbm", 12),
@@ -255,6 +255,7 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
 def run_ours(args):
     from graph_augmented_vision_transformers_b200 import _lib, dp, modules, ops
     from graph_augmented_vision_transformers_b200.losses import DynamicWeightedLoss
+    from graph_augmented_vision_transformers_b200.step import CapturedTrainStep
     import torch.distributed as dist
 
     if not torch.cuda.is_available():
@@ -276,14 +277,14 @@ def run_ours(args):
     dp.broadcast_parameters(crit)
     sync = dp.GradSync(model, bucket_mb=32.0, extra_params=list(crit.parameters()))
     opt = torch.optim.AdamW([{"params": model.parameters()}, {"params": crit.parameters(), "lr": 1e-5}], lr=1e-4,
-                            weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, fused=True)
+                            weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, fused=True, capturable=True)
     all_params = list(model.parameters()) + list(crit.parameters())
 
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     img_dev = torch.randn(B, 3, 224, 224, device=dev, generator=gen)
     tgt_dev = (torch.rand(B, 14, device=dev, generator=gen) > 0.9).float()
 
-    def train_step(img, tgt):
+    def eager_step(img, tgt):
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             logits = model(img)
@@ -293,6 +294,25 @@ def run_ours(args):
         torch.nn.utils.clip_grad_norm_(all_params, 1.0, foreach=True)
         opt.step()
         return loss
+
+    # The step is captured once into a CUDA graph and replayed (step.CapturedTrainStep): ~800 launches per step leave
+    # the host as the bottleneck when issued eagerly.  --eager keeps the Python-issued step.
+    captured, step_mode, per_step_launches = None, "eager", None
+    if not args.eager:
+        try:
+            ops.reset_launch_count()
+            captured = CapturedTrainStep(model, crit, opt, max_norm=1.0, clip_params=all_params,
+                                         grad_sync=sync if world > 1 else None, warmup=3).capture(img_dev, tgt_dev)
+            per_step_launches = ops.launch_count() // 4      # 3 eager warm-up bodies + the captured one
+            step_mode = "cuda-graph"
+        except Exception as e:                               # noqa: BLE001 - report and keep measuring eagerly
+            sys.stderr.write(f"bench.py: CUDA-graph capture failed ({type(e).__name__}: {e}); running the eager step\n")
+            captured = None
+            ops.set_rng_offset_tensor(None)
+            torch.cuda.synchronize()
+
+    def train_step(img, tgt):
+        return captured(img, tgt) if captured is not None else eager_step(img, tgt)
 
     def barrier():
         if world > 1:
@@ -318,7 +338,7 @@ def run_ours(args):
         train_step(img_dev, tgt_dev)
     ops.reset_launch_count()
     ms_step = timed(lambda i: train_step(img_dev, tgt_dev), args.steps)
-    launches = ops.launch_count()
+    launches = ops.launch_count() if captured is None else per_step_launches * args.steps
     clocks = sampler.stop() if sampler else None
 
     # ---- end to end: every step's batch comes from pinned host memory; loss is read back ---------
@@ -382,6 +402,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "BASELINE configs[1]: ViT-B/16 + kNN graph block (196 patch tokens, k=8, every block), "
                                        "full training step (fwd, loss, bwd, grad sync, clip, AdamW), bf16 autocast, 224x224",
+                           "step_issue": step_mode + (" (whole step replayed from one captured graph; dropout counters advance on the device)" if captured is not None else ""),
                            "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
                            "l2": "no flush needed: one step streams >20 GB of activations (126 MB L2); kernel micro-timings rotate >L2 input sets"},
                 "model_tflops": value * FLOPS_PER_IMAGE / 1e12,
@@ -394,7 +415,7 @@ def run_ours(args):
                             for n, d in (kernels or {}).items()},
                 "paths": {op: _lib.describe_path(op, _lib.GVIT_BF16, 196 if op in ("knn", "agg") else 197, 768 if op in ("knn", "agg") else 64)
                           for op in ("knn", "agg", "attn_fwd", "attn_bwd")},
-                "collectives_per_step": sync.collectives_issued // max(1, (args.steps * 2 + args.warmup + 2)) if world > 1 else 0,
+                "collectives_per_step": len(sync.buckets) if world > 1 else 0,
                 "last_loss": losses[-1] if losses else None}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -417,6 +438,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="issue the step from Python instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                                     # timing rule: at least 3 warm-up steps

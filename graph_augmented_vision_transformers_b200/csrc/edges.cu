@@ -219,7 +219,9 @@ __global__ void ln_bwd_reduce_kernel(const float* __restrict__ partial, int nblk
 template <typename Tx, typename Ty>
 __global__ void __launch_bounds__(256) dropout_residual_fwd_kernel(const Ty* __restrict__ y, const Tx* __restrict__ resid,
                                                                    int64_t n, float p, uint64_t seed, uint64_t offset,
+                                                                   const uint64_t* __restrict__ offset_dev,
                                                                    Tx* __restrict__ out, uint8_t* __restrict__ mask) {
+  if (offset_dev) offset += __ldg(offset_dev);
   const float scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
   const uint32_t th = dropout_thresh16(p);
   for (int64_t i8 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i8 < n; i8 += (int64_t)gridDim.x * blockDim.x * 8) {
@@ -288,8 +290,9 @@ template <> struct GeluFor<__nv_bfloat16> { using type = Gelu<false>; };
 // (GELU + Philox), so one 16-byte load in flight per thread left the memory pipe idle while the math ran.
 template <typename T>
 __global__ void __launch_bounds__(256) gelu_dropout_fwd_kernel(const T* __restrict__ u, int64_t n, float p, uint64_t seed,
-                                                               uint64_t offset, T* __restrict__ out,
-                                                               uint8_t* __restrict__ mask) {
+                                                               uint64_t offset, const uint64_t* __restrict__ offset_dev,
+                                                               T* __restrict__ out, uint8_t* __restrict__ mask) {
+  if (offset_dev) offset += __ldg(offset_dev);
   const float scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
   const uint32_t th = dropout_thresh16(p);
   const int64_t step = (int64_t)gridDim.x * blockDim.x * 8;
@@ -585,18 +588,18 @@ int colsum(const void* x, int64_t rows, int D, int dtype, float* out, float* par
 }
 
 int dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, uint64_t seed, uint64_t offset,
-                         int dtype, int y_dtype, void* out, uint8_t* keep_mask, cudaStream_t st) {
+                         const uint64_t* offset_dev, int dtype, int y_dtype, void* out, uint8_t* keep_mask, cudaStream_t st) {
   const int grid = stream_grid(n / 8);
   using bf = __nv_bfloat16;
   if (dtype == GVIT_F32 && y_dtype == GVIT_F32)
     dropout_residual_fwd_kernel<float, float><<<grid, 256, 0, st>>>(static_cast<const float*>(y), static_cast<const float*>(resid),
-                                                                    n, p, seed, offset, static_cast<float*>(out), keep_mask);
+                                                                    n, p, seed, offset, offset_dev, static_cast<float*>(out), keep_mask);
   else if (dtype == GVIT_F32)
     dropout_residual_fwd_kernel<float, bf><<<grid, 256, 0, st>>>(static_cast<const bf*>(y), static_cast<const float*>(resid), n, p,
-                                                                 seed, offset, static_cast<float*>(out), keep_mask);
+                                                                 seed, offset, offset_dev, static_cast<float*>(out), keep_mask);
   else
     dropout_residual_fwd_kernel<bf, bf><<<grid, 256, 0, st>>>(static_cast<const bf*>(y), static_cast<const bf*>(resid), n, p, seed,
-                                                              offset, static_cast<bf*>(out), keep_mask);
+                                                              offset, offset_dev, static_cast<bf*>(out), keep_mask);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }
@@ -631,13 +634,13 @@ int dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, 
   return GVIT_OK;
 }
 
-int gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t offset, int dtype, void* out,
-                     uint8_t* keep_mask, cudaStream_t st) {
+int gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype,
+                     void* out, uint8_t* keep_mask, cudaStream_t st) {
   const int grid = stream_grid(n / 8);
   if (dtype == GVIT_F32)
-    gelu_dropout_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(u), n, p, seed, offset, static_cast<float*>(out), keep_mask);
+    gelu_dropout_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(u), n, p, seed, offset, offset_dev, static_cast<float*>(out), keep_mask);
   else
-    gelu_dropout_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(u), n, p, seed, offset,
+    gelu_dropout_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(u), n, p, seed, offset, offset_dev,
                                                                  static_cast<__nv_bfloat16*>(out), keep_mask);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;

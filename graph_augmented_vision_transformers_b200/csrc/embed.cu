@@ -48,8 +48,10 @@ __global__ void __launch_bounds__(256) patchify_kernel(const Tin* __restrict__ i
 template <typename T, typename Tp>
 __global__ void __launch_bounds__(256) embed_assemble_kernel(const T* __restrict__ y, const Tp* __restrict__ bias,
                                                              const Tp* __restrict__ cls, const Tp* __restrict__ pos, int B, int N,
-                                                             int D, float p, uint64_t seed, uint64_t offset, T* __restrict__ out,
+                                                             int D, float p, uint64_t seed, uint64_t offset,
+                                                             const uint64_t* __restrict__ offset_dev, T* __restrict__ out,
                                                              uint8_t* __restrict__ mask) {
+  if (offset_dev) offset += __ldg(offset_dev);
   const float scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
   const uint32_t th = dropout_thresh16(p);
   const int d8 = D / 8;
@@ -104,18 +106,19 @@ int patchify(const void* img, int B, int C, int H, int W, int P, int in_dtype, i
 }
 
 int embed_assemble(const void* y, const void* bias, const void* cls, const void* pos, int B, int N, int D, float p,
-                   uint64_t seed, uint64_t offset, int dtype, int param_dtype, void* out, uint8_t* keep_mask, cudaStream_t st) {
+                   uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, int param_dtype, void* out, uint8_t* keep_mask,
+                   cudaStream_t st) {
   using bf = __nv_bfloat16;
   const int grid = grid_for((int64_t)B * N * (D / 8));
   if (dtype == GVIT_F32)
     embed_assemble_kernel<float, float><<<grid, 256, 0, st>>>(static_cast<const float*>(y), static_cast<const float*>(bias), static_cast<const float*>(cls),
-                                                              static_cast<const float*>(pos), B, N, D, p, seed, offset, static_cast<float*>(out), keep_mask);
+                                                              static_cast<const float*>(pos), B, N, D, p, seed, offset, offset_dev, static_cast<float*>(out), keep_mask);
   else if (param_dtype == GVIT_F32)
     embed_assemble_kernel<bf, float><<<grid, 256, 0, st>>>(static_cast<const bf*>(y), static_cast<const float*>(bias), static_cast<const float*>(cls),
-                                                           static_cast<const float*>(pos), B, N, D, p, seed, offset, static_cast<bf*>(out), keep_mask);
+                                                           static_cast<const float*>(pos), B, N, D, p, seed, offset, offset_dev, static_cast<bf*>(out), keep_mask);
   else
     embed_assemble_kernel<bf, bf><<<grid, 256, 0, st>>>(static_cast<const bf*>(y), static_cast<const bf*>(bias), static_cast<const bf*>(cls),
-                                                        static_cast<const bf*>(pos), B, N, D, p, seed, offset, static_cast<bf*>(out), keep_mask);
+                                                        static_cast<const bf*>(pos), B, N, D, p, seed, offset, offset_dev, static_cast<bf*>(out), keep_mask);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }

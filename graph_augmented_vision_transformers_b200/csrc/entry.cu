@@ -176,7 +176,7 @@ int gvit_colsum(const void* x, int64_t rows, int D, int dtype, float* out, float
 }
 
 int gvit_dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, uint64_t seed, uint64_t offset,
-                              int dtype, int y_dtype, void* out, uint8_t* keep_mask, void* stream) {
+                              const uint64_t* offset_dev, int dtype, int y_dtype, void* out, uint8_t* keep_mask, void* stream) {
   TRY(check_ln_pair(dtype, y_dtype, "dropout_residual_fwd"));
   GVIT_REQUIRE(y && out, GVIT_ERR_SHAPE, "dropout_residual_fwd: null pointer");
   GVIT_REQUIRE(resid || dtype == y_dtype, GVIT_ERR_DTYPE, "dropout_residual_fwd: without a residual, dtype must equal y_dtype");
@@ -184,7 +184,7 @@ int gvit_dropout_residual_fwd(const void* y, const void* resid, int64_t n, float
   GVIT_REQUIRE(p >= 0.f && p < 1.f, GVIT_ERR_SHAPE, "dropout_residual_fwd: p=%f not in [0,1)", p);
   GVIT_REQUIRE(p == 0.f || keep_mask, GVIT_ERR_SHAPE, "dropout_residual_fwd: keep_mask required when p > 0");
   GVIT_REQUIRE(aligned16(y) && aligned16(out) && (!resid || aligned16(resid)), GVIT_ERR_ALIGN, "dropout_residual_fwd: 16-byte alignment required");
-  return dropout_residual_fwd(y, resid, n, p, seed, offset, dtype, y_dtype, out, keep_mask, static_cast<cudaStream_t>(stream));
+  return dropout_residual_fwd(y, resid, n, p, seed, offset, offset_dev, dtype, y_dtype, out, keep_mask, static_cast<cudaStream_t>(stream));
 }
 
 static int check_colsum_args(const char* who, int64_t n, int D, const float* colsum_out, const float* partial_ws) {
@@ -204,14 +204,14 @@ int gvit_dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, floa
   return dropout_bwd(dout, keep_mask, n, p, dtype, y_dtype, dy, D, colsum_out, partial_ws, static_cast<cudaStream_t>(stream));
 }
 
-int gvit_gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t offset, int dtype, void* out,
-                          uint8_t* keep_mask, void* stream) {
+int gvit_gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype,
+                          void* out, uint8_t* keep_mask, void* stream) {
   TRY(check_dtype(dtype, "gelu_dropout_fwd"));
   GVIT_REQUIRE(u && out, GVIT_ERR_SHAPE, "gelu_dropout_fwd: null pointer");
   GVIT_REQUIRE(n >= 8 && n % 8 == 0, GVIT_ERR_SHAPE, "gelu_dropout_fwd: n=%lld must be a positive multiple of 8", (long long)n);
   GVIT_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || keep_mask), GVIT_ERR_SHAPE, "gelu_dropout_fwd: p=%f (keep_mask required when p > 0)", p);
   GVIT_REQUIRE(aligned16(u) && aligned16(out), GVIT_ERR_ALIGN, "gelu_dropout_fwd: 16-byte alignment required");
-  return gelu_dropout_fwd(u, n, p, seed, offset, dtype, out, keep_mask, static_cast<cudaStream_t>(stream));
+  return gelu_dropout_fwd(u, n, p, seed, offset, offset_dev, dtype, out, keep_mask, static_cast<cudaStream_t>(stream));
 }
 
 int gvit_gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, int64_t n, float p, int dtype,
@@ -237,7 +237,8 @@ int gvit_patchify(const void* img, int B, int C, int H, int W, int P, int in_dty
 }
 
 int gvit_embed_assemble(const void* y, const void* bias, const void* cls, const void* pos, int B, int N, int D, float p,
-                        uint64_t seed, uint64_t offset, int dtype, int param_dtype, void* out, uint8_t* keep_mask, void* stream) {
+                        uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, int param_dtype, void* out,
+                        uint8_t* keep_mask, void* stream) {
   TRY(check_dtype(dtype, "embed_assemble"));
   TRY(check_dtype(param_dtype, "embed_assemble"));
   GVIT_REQUIRE(y && cls && pos && out, GVIT_ERR_SHAPE, "embed_assemble: null pointer");
@@ -246,7 +247,7 @@ int gvit_embed_assemble(const void* y, const void* bias, const void* cls, const 
   GVIT_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || keep_mask), GVIT_ERR_SHAPE, "embed_assemble: p=%f (keep_mask required when p > 0)", p);
   GVIT_REQUIRE(aligned16(y) && aligned16(out) && aligned16(cls) && aligned16(pos) && (!bias || aligned16(bias)), GVIT_ERR_ALIGN,
                "embed_assemble: 16-byte alignment required");
-  return embed_assemble(y, bias, cls, pos, B, N, D, p, seed, offset, dtype, param_dtype, out, keep_mask, static_cast<cudaStream_t>(stream));
+  return embed_assemble(y, bias, cls, pos, B, N, D, p, seed, offset, offset_dev, dtype, param_dtype, out, keep_mask, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

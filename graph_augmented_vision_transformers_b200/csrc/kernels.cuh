@@ -52,11 +52,11 @@ int layernorm_bwd(const void* dy, const void* x, const void* gamma, const float*
                   float* partial_ws, cudaStream_t st);
 int colsum(const void* x, int64_t rows, int D, int dtype, float* out, float* partial_ws, cudaStream_t st);
 int dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, uint64_t seed, uint64_t offset,
-                         int dtype, int y_dtype, void* out, uint8_t* keep_mask, cudaStream_t st);
+                         const uint64_t* offset_dev, int dtype, int y_dtype, void* out, uint8_t* keep_mask, cudaStream_t st);
 int dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, int y_dtype, void* dy,
                 int D, float* colsum_out, float* partial_ws, cudaStream_t st);
-int gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t offset, int dtype, void* out,
-                     uint8_t* keep_mask, cudaStream_t st);
+int gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype,
+                     void* out, uint8_t* keep_mask, cudaStream_t st);
 int gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, int64_t n, float p, int dtype, void* du,
                      int D, float* colsum_out, float* partial_ws, cudaStream_t st);
 
@@ -64,6 +64,7 @@ int gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, 
 // ---- token prologue : embed.cu
 int patchify(const void* img, int B, int C, int H, int W, int P, int in_dtype, int out_dtype, void* out, cudaStream_t st);
 int embed_assemble(const void* y, const void* bias, const void* cls, const void* pos, int B, int N, int D, float p,
-                   uint64_t seed, uint64_t offset, int dtype, int param_dtype, void* out, uint8_t* keep_mask, cudaStream_t st);
+                   uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, int param_dtype, void* out, uint8_t* keep_mask,
+                   cudaStream_t st);
 
 }  // namespace gvit

@@ -24,7 +24,7 @@ from . import _lib
 from ._lib import GVIT_BF16, GVIT_COLSUM_CHUNKS, GVIT_F32, GVIT_LN_PARTIALS
 
 __all__ = ["attention_core", "layer_norm", "pre_norm", "linear", "colsum", "linear_dropout_add", "linear_gelu_dropout", "dropout_add", "gelu_dropout", "knn_graph", "graph_reverse", "patch_graph",
-           "agg_gather", "patch_embed_tokens", "refresh_shadows", "launch_count", "reset_launch_count"]
+           "agg_gather", "patch_embed_tokens", "refresh_shadows", "invalidate_shadows", "set_rng_offset_tensor", "launch_count", "reset_launch_count"]
 
 # kernels launched through the C ABI since the last reset (bench.py reports it as gpu_launches)
 _LAUNCHES = {"n": 0}
@@ -89,7 +89,15 @@ def _autocast_dtype(t: torch.Tensor):
 # take the MASTER parameter as their autograd input: their backward returns fp32 gradients directly (the weight-gradient
 # GEMM accumulates and writes fp32), so there is no 16-bit gradient and no cast on the way back either.
 # ------------------------------------------------------------------------------------------------
-_SHADOWS: dict = {}          # id(param) -> (weakref(param), version, data_ptr, shadow tensor)
+_SHADOWS: dict = {}          # id(param) -> (weakref(param), version, data_ptr, shadow tensor, epoch)
+_SHADOW_EPOCH = {"n": 0}
+
+
+def invalidate_shadows() -> None:
+    """Declare every shadow stale.  Needed when parameters change without their `_version` moving: a CUDA-graph replay
+    of an optimizer step updates the masters on the device without executing any Python."""
+    _SHADOW_EPOCH["n"] += 1
+
 
 
 def refresh_shadows(params, dtype: torch.dtype) -> None:
@@ -101,12 +109,13 @@ def refresh_shadows(params, dtype: torch.dtype) -> None:
             continue
         e = _SHADOWS.get(id(prm))
         if e is not None and e[0]() is prm and e[3].dtype == dtype and e[3].shape == prm.shape:
-            if e[1] == prm._version and e[2] == prm.data_ptr():
+            if e[1] == prm._version and e[2] == prm.data_ptr() and e[4] == _SHADOW_EPOCH["n"]:
                 continue
             sh = e[3]
         else:
             sh = torch.empty_like(prm, dtype=dtype, memory_format=torch.contiguous_format)
-        _SHADOWS[id(prm)] = (weakref.ref(prm, lambda _r, k=id(prm): _SHADOWS.pop(k, None)), prm._version, prm.data_ptr(), sh)
+        _SHADOWS[id(prm)] = (weakref.ref(prm, lambda _r, k=id(prm): _SHADOWS.pop(k, None)), prm._version, prm.data_ptr(), sh,
+                             _SHADOW_EPOCH["n"])
         src.append(prm.detach())
         dst.append(sh)
     if src:
@@ -122,7 +131,8 @@ def _shadow(prm, dtype: torch.dtype):
     if t.dtype == dtype:
         return t if t.is_contiguous() else t.contiguous()
     e = _SHADOWS.get(id(prm))
-    if e is not None and e[0]() is prm and e[1] == prm._version and e[2] == prm.data_ptr() and e[3].dtype == dtype:
+    if (e is not None and e[0]() is prm and e[1] == prm._version and e[2] == prm.data_ptr() and e[3].dtype == dtype
+            and e[4] == _SHADOW_EPOCH["n"]):
         return e[3]
     return t.to(dtype).contiguous()
 
@@ -334,6 +344,24 @@ def pre_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: flo
         return _PreNorm.apply(x.contiguous(), weight, bias, float(eps), y_code)
 
 
+# Device-resident Philox offset for CUDA-graph capture: a captured launch bakes its host arguments (seed, offset)
+# in, so graph replays would repeat the dropout masks.  While an offset tensor is installed every dropout kernel adds
+# the uint64 it holds to its counter; the captured step advances it on the device (see step.CapturedTrainStep).
+_RNG_OFFSET = {"t": None}
+
+
+def set_rng_offset_tensor(t: torch.Tensor | None) -> None:
+    """Install (or remove, with None) a 1-element int64 CUDA tensor whose value is added to every dropout counter."""
+    if t is not None and (t.dtype != torch.int64 or t.numel() != 1 or not t.is_cuda):
+        raise ValueError("the rng offset must be a 1-element int64 CUDA tensor")
+    _RNG_OFFSET["t"] = t
+
+
+def _rng_offset_ptr():
+    t = _RNG_OFFSET["t"]
+    return None if t is None else t.data_ptr()
+
+
 def _draw_seed() -> int:
     # CPU generator: follows torch.manual_seed, costs no device synchronisation
     return int(torch.randint(0, 2 ** 62, (1,)).item())
@@ -345,7 +373,7 @@ class _DropoutAdd(torch.autograd.Function):
         n = y.numel()
         out = torch.empty_like(y if resid is None else resid)
         mask = torch.empty(n // 8, dtype=torch.uint8, device=y.device) if p > 0 else None
-        _call("gvit_dropout_residual_fwd", _ptr(y), _ptr(resid), n, float(p), int(seed), 0, _dtype_code(out),
+        _call("gvit_dropout_residual_fwd", _ptr(y), _ptr(resid), n, float(p), int(seed), 0, _rng_offset_ptr(), _dtype_code(out),
               _dtype_code(y), _ptr(out), _ptr(mask), _stream())
         ctx.p = p
         ctx.has_resid = resid is not None
@@ -398,7 +426,7 @@ class _GeluDropout(torch.autograd.Function):
         n = u.numel()
         out = torch.empty_like(u)
         mask = torch.empty(n // 8, dtype=torch.uint8, device=u.device) if p > 0 else None
-        _call("gvit_gelu_dropout_fwd", _ptr(u), n, float(p), int(seed), 0, _dtype_code(u), _ptr(out), _ptr(mask),
+        _call("gvit_gelu_dropout_fwd", _ptr(u), n, float(p), int(seed), 0, _rng_offset_ptr(), _dtype_code(u), _ptr(out), _ptr(mask),
               _stream())
         ctx.p = p
         ctx.save_for_backward(u, mask)
@@ -450,7 +478,7 @@ class _LinearDropoutAdd(torch.autograd.Function):
         n = y.numel()
         out = torch.empty_like(y if resid is None else resid)
         mask = torch.empty(n // 8, dtype=torch.uint8, device=y.device) if p > 0 else None
-        _call("gvit_dropout_residual_fwd", _ptr(y), _ptr(resid), n, float(p), int(seed), 0, _dtype_code(out),
+        _call("gvit_dropout_residual_fwd", _ptr(y), _ptr(resid), n, float(p), int(seed), 0, _rng_offset_ptr(), _dtype_code(out),
               _dtype_code(y), _ptr(out), _ptr(mask), _stream())
         ctx.save_for_backward(x, weight, mask)
         ctx.p, ctx.has_bias, ctx.has_resid, ctx.y_dtype = p, bias is not None, resid is not None, y.dtype
@@ -487,7 +515,7 @@ class _LinearGeluDropout(torch.autograd.Function):
         n = u.numel()
         out = torch.empty_like(u)
         mask = torch.empty(n // 8, dtype=torch.uint8, device=u.device) if p > 0 else None
-        _call("gvit_gelu_dropout_fwd", _ptr(u), n, float(p), int(seed), 0, _dtype_code(u), _ptr(out), _ptr(mask), _stream())
+        _call("gvit_gelu_dropout_fwd", _ptr(u), n, float(p), int(seed), 0, _rng_offset_ptr(), _dtype_code(u), _ptr(out), _ptr(mask), _stream())
         ctx.save_for_backward(x, weight, u, mask)
         ctx.p, ctx.has_bias = p, bias is not None
         return out
@@ -561,7 +589,7 @@ class _PatchEmbedTokens(torch.autograd.Function):
         out = torch.empty((B, N, D), dtype=dt, device=img.device)
         mask = torch.empty(B * N * D // 8, dtype=torch.uint8, device=img.device) if p > 0 else None
         _call("gvit_embed_assemble", _ptr(y), _ptr(b_), _ptr(c_), _ptr(p_), B, N, D, float(p), int(seed), 0,
-              _dtype_code(out), GVIT_F32 if pd == torch.float32 else GVIT_BF16, _ptr(out), _ptr(mask), st)
+              _rng_offset_ptr(), _dtype_code(out), GVIT_F32 if pd == torch.float32 else GVIT_BF16, _ptr(out), _ptr(mask), st)
         ctx.save_for_backward(patches, mask)
         ctx.p = p
         ctx.meta = (conv_w.shape, conv_w.dtype, None if conv_b is None else conv_b.dtype, cls.dtype, pos.dtype)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GVIT_ABI_VERSION 7
+#define GVIT_ABI_VERSION 8
 #if defined(__GNUC__)
 #define GVIT_API __attribute__((visibility("default")))
 #else
@@ -145,9 +145,11 @@ GVIT_API int gvit_colsum(const void* x, int64_t rows, int D, int dtype, float* o
  * residual edge of vit.py:71,117 (also pos_drop, vit.py:212, with resid NULL).  p == 0 degenerates to an add.
  * dtype: type of resid / out (the residual stream); y_dtype: type of y (the branch) - same pairing rule as LayerNorm;
  * with resid NULL both must be equal.  keep_mask: n/8 bytes, ONE BIT per element (bit j of byte i = element 8i+j),
- * may be NULL when p == 0.  n % 8 == 0. */
+ * may be NULL when p == 0.  n % 8 == 0.
+ * offset_dev (nullable): a device uint64 that is ADDED to `offset` when the kernel runs - a captured CUDA graph bakes
+ * `seed` and `offset` into the launch, so the host advances *offset_dev (by >= 2^40) between replays to get fresh masks. */
 GVIT_API int gvit_dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, uint64_t seed, uint64_t offset,
-                              int dtype, int y_dtype, void* out, uint8_t* keep_mask, void* stream);
+                              const uint64_t* offset_dev, int dtype, int y_dtype, void* out, uint8_t* keep_mask, void* stream);
 /* dy = dout * keep / (1 - p);  dout has `dtype`, dy has `y_dtype`.
  * With colsum_out != NULL the same pass also writes colsum_out[c] = sum_r dy[r*D + c] (fp32, D values; the tensor is
  * read as n/D rows of D) - the bias gradient of the Linear whose output was dropped out (vit.py:70-71, 93-94);
@@ -158,8 +160,8 @@ GVIT_API int gvit_dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_
 /* ---- Mlp activation edge: out = dropout(GELU(u), p), exact-erf GELU - nn.GELU + nn.Dropout at vit.py:84,92 in one
  * pass; the backward recomputes GELU' from the saved pre-activation u (no activation tensor is kept).
  * keep_mask as above (may be NULL when p == 0). */
-GVIT_API int gvit_gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t offset, int dtype, void* out,
-                          uint8_t* keep_mask, void* stream);
+GVIT_API int gvit_gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                          int dtype, void* out, uint8_t* keep_mask, void* stream);
 /* colsum_out / partial_ws / D as for gvit_dropout_bwd: the bias gradient of fc1 (vit.py:90) in the same pass. */
 GVIT_API int gvit_gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, int64_t n, float p, int dtype,
                           void* du, int D, float* colsum_out, float* partial_ws, void* stream);
@@ -177,7 +179,8 @@ GVIT_API int gvit_patchify(const void* img, int B, int C, int H, int W, int P, i
  * (B,N,D) of `dtype`; bias (D, nullable), cls (D), pos (N,D) of `param_dtype` (GVIT_F32 master parameters may feed a
  * bf16 stream).  The backward is gvit_dropout_bwd followed by gvit_colsum over the batch. */
 GVIT_API int gvit_embed_assemble(const void* y, const void* bias, const void* cls, const void* pos, int B, int N, int D, float p,
-                        uint64_t seed, uint64_t offset, int dtype, int param_dtype, void* out, uint8_t* keep_mask, void* stream);
+                        uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, int param_dtype, void* out,
+                        uint8_t* keep_mask, void* stream);
 
 #ifdef __cplusplus
 }

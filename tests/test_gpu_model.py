@@ -147,3 +147,76 @@ def test_fp32_residual_stream_option_and_hook_safe_folding():
     o(img)
     ho.remove()
     assert rel_err(seen["out"], ref["out"]) < TOL_F32
+
+
+def _train_setup(drop, seed=0):
+    from graph_augmented_vision_transformers_b200.losses import DynamicWeightedLoss
+    torch.manual_seed(seed)
+    cfg = dict(CFG, drop_rate=drop)
+    m = modules.VisionTransformer(**cfg).to(DEV).train()
+    crit = DynamicWeightedLoss(14).to(DEV)
+    params = list(m.parameters()) + list(crit.parameters())
+    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=0.05, fused=True, capturable=True)
+    return m, crit, opt, params
+
+
+def test_captured_train_step_matches_the_eager_step():
+    """f2 - trainer.py:96-120 as one CUDA graph: without dropout the replayed steps follow the eager trajectory."""
+    from graph_augmented_vision_transformers_b200.step import CapturedTrainStep
+    g = torch.Generator().manual_seed(2)
+    batches = [(torch.randn(4, 3, 64, 64, generator=g).to(DEV), (torch.rand(4, 14, generator=g) > 0.7).float().to(DEV))
+               for _ in range(4)]
+    m0, c0, o0, p0 = _train_setup(0.0)
+    eager = []
+    # eager reference: 3 warm-up steps on batch 0 (what capture() does), then the 4 batches
+    for img, tgt in [batches[0]] * 3 + batches:
+        o0.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = m0(img)
+        loss, _ = c0(logits, tgt)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(p0, 1.0, foreach=True)
+        o0.step()
+        eager.append(float(loss))
+    m1, c1, o1, p1 = _train_setup(0.0)
+    step = CapturedTrainStep(m1, c1, o1, max_norm=1.0, clip_params=p1, warmup=3)
+    try:
+        got = [float(step(img, tgt)) for img, tgt in batches]
+        assert step.replays == 4
+        for a, b in zip(got, eager[3:]):
+            assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (got, eager[3:])
+        for (n, a), b in zip(m1.named_parameters(), m0.parameters()):
+            assert rel_err(a, b) < 2e-2, n
+        # an eager evaluation after the replays must see the CURRENT weights (shadows are invalidated by every replay)
+        m0.eval(), m1.eval()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            assert rel_err(m1(batches[0][0]), m0(batches[0][0])) < TOL_BF16
+    finally:
+        step.release()
+
+
+def test_captured_step_draws_fresh_dropout_masks_on_every_replay():
+    x = torch.ones(1 << 16, device=DEV)
+    off = torch.zeros(1, dtype=torch.int64, device=DEV)
+    ops.set_rng_offset_tensor(off)
+    try:
+        torch.manual_seed(0)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ops.dropout_add(x, None, 0.5, True)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            off.add_(1 << 40)
+            y = ops.dropout_add(x, None, 0.5, True)
+        masks = []
+        for _ in range(3):
+            graph.replay()
+            masks.append((y != 0).clone())
+        assert not torch.equal(masks[0], masks[1]) and not torch.equal(masks[1], masks[2])
+        for mk in masks:
+            assert abs(float(mk.float().mean()) - 0.5) < 1e-2
+        assert abs(float((masks[0] & masks[1]).float().mean()) - 0.25) < 1e-2      # independent across replays
+    finally:
+        ops.set_rng_offset_tensor(None)
