@@ -453,21 +453,26 @@ __global__ void __launch_bounds__(F2_THREADS, 1) attn_fwd_tc2_kernel(const __gri
 // For key tile kt and query tile qt the 128 x 128 score block is processed as TWO 64-query sub-tiles g = 0,1, each
 // owned by one softmax warpgroup (warps 4g..4g+3, thread <-> key row = TMEM lane) and one 64-column TMEM sub-buffer:
 //   MMA1(g) : S^T_g = K Q_g^T,  dP^T_g = V dO_g^T                     (tcgen05.mma, M = keys, N = <=64 queries)
-//   WG g    : P^T_g = exp2(S^T_g c - lse), dS^T_g = P^T_g (dP^T_g - delta) scale  -> bf16 staging tiles in smem
-//   MMA2(g) : dV += P^T_g dO_g,  dK += dS^T_g Q_g                      (accumulate in TMEM across all query tiles)
-//   dQ[qt] += dS K  once per (kt, qt): the [keys][128 queries] staging pair is read as an MN-major A operand.
-// MMA1 of the NEXT (kt, qt) is issued into sub-buffer g as soon as WG g has drained it, so the tensor pipe, the two
-// warpgroups and the epilogue stores overlap instead of taking turns (v1 ran them strictly in sequence: 470 us).
+//   WG g    : P^T_g = exp2(S^T_g c - lse), dS^T_g = P^T_g (dP^T_g - delta)   -> bf16, written back IN PLACE into the
+//             TMEM columns they were computed from (two bf16 per 32-bit column); dS^T_g also into an smem staging tile
+//   MMA2(g) : dV += P^T_g dO_g,  dK += dS^T_g Q_g     (A operand read from TMEM, accumulate across all query tiles)
+//   dQ[qt] += dS K  once per (kt, qt): the [keys][128 queries] dS^T staging pair is read as an MN-major A operand.
+// Every MMA here is 128 x 64 x 16, which reads 6 KB of operands from shared memory per 32 tensor-pipe cycles - more than
+// the 128 B/clk the SM delivers - so shared-memory bandwidth, not the tensor pipe, paces the kernel: taking the A
+// operands of dV and dK from TMEM (and not staging P at all) removes 30 % of that traffic.
+// MMA1 of the NEXT (kt, qt) is issued into sub-buffer g right behind MMA2(g) (the pipe executes in order, so the
+// in-place operands are consumed first), so the tensor pipe, the two warpgroups and the epilogue stores overlap
+// instead of taking turns (v1 ran them strictly in sequence: 470 us).
 // TMEM: S^T [0,128) | dP^T [128,256) | dV [256,320) | dK [320,384) | dQ [384,512).
 // Warp roles: 0-3 WG0, 4-7 WG1, 8 TMA producer, 9 MMA issuer (+ TMEM allocation), 10-11 delta / lse helpers.
 // =================================================================================================
 constexpr int B2_THREADS = 384;   // 8 warpgroup warps + TMA + MMA + 2 helper warps
 struct __align__(16) BwdCtrl {
   float lse2[2][256], delta[2][256];            // double-buffered by item parity
-  uint64_t kv_full[2], q_full[2], in_empty, s_full[2], p_full[2], st_free, dvk_free, dq_free, delta_ready[2];
+  uint64_t kv_full[2], q_full[2], kv_empty[2], q_empty[2], s_full[2], p_full[2], st_free, dvk_free, dq_free, delta_ready[2];
   uint32_t tmem_base;
 };
-// Q[2], dO[2], K[2], V[2] tiles + P^T staging (2 sub-tiles) + dS^T staging (2 sub-tiles)
+// Q[2], dO[2], K[2], V[2] tiles + output staging (one tile per warpgroup) + dS^T staging (2 sub-tiles)
 constexpr size_t BWD_SMEM = 1024 + 12 * TILE_BYTES + sizeof(BwdCtrl);
 
 // two 32-column TMEM reads of this thread's lane, one wait
@@ -517,7 +522,7 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&a)
 // softmax scale is applied to dK / dQ when they are stored.
 template <int W>
 __device__ __forceinline__ void bwd_chunk(float (&s)[W], float (&dp)[W], const float* lse2, const float* delta,
-                                          float sl2, uint8_t* pt_tile, uint8_t* dst_tile, int row, int c0) {
+                                          float sl2, uint32_t tP, uint32_t tdS, uint8_t* dst_tile, int row, int c0) {
   // written in phases over the whole chunk (all exponent arguments, then all MUFU.EX2, then dS) so that W
   // independent transcendental ops are in flight: with two warps per scheduler the loop is latency-, not rate-bound
 #pragma unroll
@@ -538,17 +543,23 @@ __device__ __forceinline__ void bwd_chunk(float (&s)[W], float (&dp)[W], const f
     dp[q4 + 2] = s[q4 + 2] * (dp[q4 + 2] - d.z);
     dp[q4 + 3] = s[q4 + 3] * (dp[q4 + 3] - d.w);
   }
+  uint32_t pk[W / 2], dk[W / 2];
 #pragma unroll
-  for (int q8 = 0; q8 < W; q8 += 8) {
-    uint4 wp, wd;
-    wp.x = pack_bf16(s[q8 + 0], s[q8 + 1]); wp.y = pack_bf16(s[q8 + 2], s[q8 + 3]);
-    wp.z = pack_bf16(s[q8 + 4], s[q8 + 5]); wp.w = pack_bf16(s[q8 + 6], s[q8 + 7]);
-    wd.x = pack_bf16(dp[q8 + 0], dp[q8 + 1]); wd.y = pack_bf16(dp[q8 + 2], dp[q8 + 3]);
-    wd.z = pack_bf16(dp[q8 + 4], dp[q8 + 5]); wd.w = pack_bf16(dp[q8 + 6], dp[q8 + 7]);
-    const uint32_t off = swz128(row, c0 + q8);
-    *reinterpret_cast<uint4*>(pt_tile + off) = wp;
-    *reinterpret_cast<uint4*>(dst_tile + off) = wd;
+  for (int e = 0; e < W; e += 2) {
+    pk[e >> 1] = pack_bf16(s[e], s[e + 1]);
+    dk[e >> 1] = pack_bf16(dp[e], dp[e + 1]);
   }
+  // in place: the 32-bit columns [c0/2, c0/2 + W/2) of both regions were read by this or an earlier chunk
+  if constexpr (W == 32) {
+    tmem_st16(tP + (c0 >> 1), pk);
+    tmem_st16(tdS + (c0 >> 1), dk);
+  } else {
+    tmem_st8(tP + (c0 >> 1), pk);
+    tmem_st8(tdS + (c0 >> 1), dk);
+  }
+#pragma unroll
+  for (int q8 = 0; q8 < W; q8 += 8)
+    *reinterpret_cast<uint4*>(dst_tile + swz128(row, c0 + q8)) = make_uint4(dk[q8 / 2], dk[q8 / 2 + 1], dk[q8 / 2 + 2], dk[q8 / 2 + 3]);
 }
 
 // width (multiple of 16) of 64-query sub-tile g of a query tile with nq (multiple of 16) padded queries; an
@@ -570,8 +581,8 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
   uint8_t* sdO = sm + 2 * TILE_BYTES;      // 2 tiles
   uint8_t* sK = sm + 4 * TILE_BYTES;       // 2 tiles
   uint8_t* sV = sm + 6 * TILE_BYTES;       // 2 tiles
-  uint8_t* sPT = sm + 8 * TILE_BYTES;      // sub-tile g at + g*TILE_BYTES: [128 keys][64 queries], K-major A of dV
-  uint8_t* sdST = sm + 10 * TILE_BYTES;    // same shape: K-major A of dK; both sub-tiles = MN-major A of dQ
+  uint8_t* sOut = sm + 8 * TILE_BYTES;     // warpgroup g's output staging tile at + g*TILE_BYTES (dV / dK / dQ -> TMA store)
+  uint8_t* sdST = sm + 10 * TILE_BYTES;    // sub-tile g at + g*TILE_BYTES: [128 keys][64 queries]; the pair = MN-major A of dQ
   BwdCtrl* ctl = reinterpret_cast<BwdCtrl*>(sm + 12 * TILE_BYTES);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role id
@@ -588,7 +599,10 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
       mbar_init(&ctl->s_full[i], 1);
       mbar_init(&ctl->p_full[i], 128);
     }
-    mbar_init(&ctl->in_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctl->kv_empty[i], 1);
+      mbar_init(&ctl->q_empty[i], 1);
+    }
     mbar_init(&ctl->st_free, 1);
     mbar_init(&ctl->dvk_free, 256);
     mbar_init(&ctl->dq_free, 256);
@@ -609,19 +623,24 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
       int ic = 0;
       for (int w = blockIdx.x; w < items; w += gridDim.x, ++ic) {
         const int b = w / H, h = w - b * H;
-        if (ic > 0) mbar_wait(&ctl->in_empty, (ic - 1) & 1);   // every MMA of the previous item has retired
+        const uint32_t prev = (ic - 1) & 1;
+        // Each tile pair is refilled as soon as the LAST MMA of the previous item that reads it has retired (per-slot
+        // empty barriers, in the order the slots are released), so the inputs of the next item's first steps land while
+        // the current item is still computing: with one barrier for all eight tiles every item began with ~5000 idle cycles.
+        if (ic > 0) mbar_wait(&ctl->kv_empty[0], prev);        // released after step (kt = 0, qt = T-1)
         GVIT_TR(1);
-        for (int t = 0; t < T; ++t) {
-          mbar_expect_tx(&ctl->kv_full[t], 2 * TILE_BYTES);
-          mbar_expect_tx(&ctl->q_full[t], 2 * TILE_BYTES);
-        }
+        mbar_expect_tx(&ctl->kv_full[0], 2 * TILE_BYTES);
         tma_load_3d(sK, &tm_qkv, (H + h) * 64, 0, b, &ctl->kv_full[0]);
         tma_load_3d(sV, &tm_qkv, (2 * H + h) * 64, 0, b, &ctl->kv_full[0]);
         for (int t = 0; t < T; ++t) {
+          if (ic > 0) mbar_wait(&ctl->q_empty[t], prev);       // released after step (kt = T-1, qt = t)
+          mbar_expect_tx(&ctl->q_full[t], 2 * TILE_BYTES);
           tma_load_3d(sQ + t * TILE_BYTES, &tm_qkv, h * 64, t * 128, b, &ctl->q_full[t]);
           tma_load_3d(sdO + t * TILE_BYTES, &tm_do, h * 64, t * 128, b, &ctl->q_full[t]);
         }
         if (T > 1) {
+          if (ic > 0) mbar_wait(&ctl->kv_empty[1], prev);      // released after the last step
+          mbar_expect_tx(&ctl->kv_full[1], 2 * TILE_BYTES);
           tma_load_3d(sK + TILE_BYTES, &tm_qkv, (H + h) * 64, 128, b, &ctl->kv_full[1]);
           tma_load_3d(sV + TILE_BYTES, &tm_qkv, (2 * H + h) * 64, 128, b, &ctl->kv_full[1]);
         }
@@ -645,7 +664,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {   // ONE elected thread runs the whole role loop (see tc.cuh)
       const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV);
-      const uint32_t aPT = smem_u32(sPT), adST = smem_u32(sdST);
+      const uint32_t adST = smem_u32(sdST);
       const uint32_t idesc_mn = make_idesc(128, 64, false, true);    // A K-major (staging), B MN-major (dO / Q rows)
       const uint32_t idesc_tt = make_idesc(128, 64, true, true);     // A MN-major (dS), B MN-major (K rows)
       int ic = 0, itc = 0, kc = 0;                                   // items, (kt,qt) steps, key tiles done so far
@@ -678,27 +697,27 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
             const bool last = (kt == T - 1 && qt == T - 1);
             const int nkt = (qt == T - 1) ? kt + 1 : kt, nqt = (qt == T - 1) ? 0 : qt + 1;
             for (int g = 0; g < 2; ++g) {
-              mbar_wait(&ctl->p_full[g], itc & 1);       // staging g written, TMEM sub-buffer g drained
+              mbar_wait(&ctl->p_full[g], itc & 1);       // P^T_g / dS^T_g are in TMEM (and dS^T_g staged)
               tc_fence_after();
               GVIT_TR(3 + g);
-              if (!last) {
-                if (g == 0) {
-                  if (nqt == 0) mbar_wait(&ctl->kv_full[nkt], par);   // first use of the next key tile
-                  else if (kt == 0) mbar_wait(&ctl->q_full[nqt], par); // first use of the next query tile
-                  tc_fence_after();
-                }
-                issue_mma1(nkt, nqt, g);                  // next scores overlap this step's dV / dK / dQ
-              }
               if (g == 0 && qt == 0 && kc > 0) {          // dV / dK are about to be overwritten: epilogue has read them
                 mbar_wait(&ctl->dvk_free, (kc - 1) & 1);
                 tc_fence_after();
               }
               const int wg = sub_width(nq, g);
-              for (int ks = 0; ks < wg / 16; ++ks) {      // K = queries of the sub-tile
-                const uint32_t aoff = g * TILE_BYTES + ks * 32, boff = qt * TILE_BYTES + g * 8192 + ks * 2048;
+              for (int ks = 0; ks < wg / 16; ++ks) {      // K = queries of the sub-tile; A = 8 packed TMEM columns per slice
+                const uint32_t boff = qt * TILE_BYTES + g * 8192 + ks * 2048;
                 const bool acc = qt > 0 || g > 0 || ks > 0;
-                umma_ss(tdV, make_sdesc(aPT + aoff), make_sdesc(adO + boff), idesc_mn, acc);
-                umma_ss(tdK, make_sdesc(adST + aoff), make_sdesc(aQ + boff), idesc_mn, acc);
+                umma_ts(tdV, tST + g * 64 + ks * 8, make_sdesc(adO + boff), idesc_mn, acc);
+                umma_ts(tdK, tdPT + g * 64 + ks * 8, make_sdesc(aQ + boff), idesc_mn, acc);
+              }
+              if (!last) {                                // behind MMA2(g) in the (in-order) pipe: it overwrites its A operands
+                if (g == 0) {
+                  if (nqt == 0) mbar_wait(&ctl->kv_full[nkt], par);   // first use of the next key tile
+                  else if (kt == 0) mbar_wait(&ctl->q_full[nqt], par); // first use of the next query tile
+                  tc_fence_after();
+                }
+                issue_mma1(nkt, nqt, g);                  // next scores overlap this step's dQ and the other sub-tile
               }
             }
             if (kt == 0 && qt == 0 && ic > 0) {           // dQ is about to be overwritten: previous item stored it
@@ -709,11 +728,12 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
               umma_ss(tdQ + qt * 64, make_sdesc_lbo(adST + ks * 2048, TILE_BYTES), make_sdesc(aK + kt * TILE_BYTES + ks * 2048),
                       idesc_tt, kt > 0 || ks > 0);
             umma_commit(&ctl->st_free);                   // staging consumed; accumulators of this step final
+            if (qt == T - 1) umma_commit(&ctl->kv_empty[kt]);   // K / V tile kt: no later MMA of this item reads it
+            if (kt == T - 1) umma_commit(&ctl->q_empty[qt]);    // Q / dO tile qt: likewise
             GVIT_TR(5);
             if (qt == T - 1) ++kc;
           }
         }
-        umma_commit(&ctl->in_empty);                      // Q / dO / K / V tiles may be refilled
       }
     }
   } else if (warp >= 10) {
@@ -774,8 +794,9 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
     const int tid = g * 128 + t;                          // 0..255
     const float sl2 = scale * LOG2E;
     const uint32_t lST = tmem_lane_base(tST + g * 64, warp), ldPT = tmem_lane_base(tdPT + g * 64, warp);
-    uint8_t* pt_g = sPT + g * TILE_BYTES;
+    uint8_t* out_g = sOut + g * TILE_BYTES;
     uint8_t* dst_g = sdST + g * TILE_BYTES;
+    bool store_pending = false;                           // thread 0 of the warpgroup: a TMA store may still read out_g
     int ic = 0, itc = 0;
     for (int w = blockIdx.x; w < items; w += gridDim.x, ++ic) {
       const int b = w / H, h = w - b * H;
@@ -801,15 +822,16 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
               GVIT_TR(12);
               if (c0 == 0 && itc > 0) mbar_wait(&ctl->st_free, (itc - 1) & 1);   // staging of the previous step consumed
               GVIT_TR(14);
-              bwd_chunk<32>(s, dp, l2p, dlp, sl2, pt_g, dst_g, t, c0);
+              bwd_chunk<32>(s, dp, l2p, dlp, sl2, lST, ldPT, dst_g, t, c0);
             } else {                                      // 16-column tail: never touch stale TMEM columns
               float s[16], dp[16];
               tmem_ld16x2(lST + c0, ldPT + c0, s, dp);
               if (c0 == 0 && itc > 0) mbar_wait(&ctl->st_free, (itc - 1) & 1);
-              bwd_chunk<16>(s, dp, l2p, dlp, sl2, pt_g, dst_g, t, c0);
+              bwd_chunk<16>(s, dp, l2p, dlp, sl2, lST, ldPT, dst_g, t, c0);
             }
             GVIT_TR(13);
           }
+          tmem_st_wait();
           fence_async_smem();
           tc_fence_before();
           mbar_arrive(&ctl->p_full[g]);
@@ -823,17 +845,19 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
             tmem_ld32x2(ta, ta + 32, v0, v1);
             tc_fence_before();
             mbar_arrive(&ctl->dvk_free);
-            // bf16 rows -> this warpgroup's P^T staging tile (every MMA that read it has retired) -> ONE TMA tile store
-            // (a 128-byte row per thread made each STG touch 32 lines: ~4000 cycles per key tile)
-            stage_out64(pt_g, t, v0, v1, g == 0 ? 1.0f : scale);      // dS was formed without the softmax scale
+            // bf16 rows -> this warpgroup's output staging tile -> ONE TMA tile store (a 128-byte row per thread made each
+            // STG touch 32 lines: ~4000 cycles per key tile).  The tile is private to the epilogues, so the wait for the
+            // PREVIOUS store to have read it sits here, long after that store was issued, instead of behind the store.
+            if (t == 0 && store_pending) tma_store_wait_read();
+            asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+            stage_out64(out_g, t, v0, v1, g == 0 ? 1.0f : scale);     // dS was formed without the softmax scale
             fence_async_smem();
             asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
             if (t == 0) {
-              tma_store_3d(&tm_dqkv, pt_g, ((g == 0 ? 2 : 1) * H + h) * 64, kt * 128, b);   // rows >= N are clipped
+              tma_store_3d(&tm_dqkv, out_g, ((g == 0 ? 2 : 1) * H + h) * 64, kt * 128, b);   // rows >= N are clipped
               tma_store_commit();
-              tma_store_wait_read();
+              store_pending = true;
             }
-            asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");   // staging tile reusable
           }
         }
       }
@@ -847,19 +871,21 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
         mbar_arrive(&ctl->dq_free);
         GVIT_TR(17);
         if (g < T) {
-          stage_out64(pt_g, t, v0, v1, scale);
+          if (t == 0 && store_pending) tma_store_wait_read();
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+          stage_out64(out_g, t, v0, v1, scale);
           fence_async_smem();
           asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
           if (t == 0) {
-            tma_store_3d(&tm_dqkv, pt_g, h * 64, g * 128, b);
+            tma_store_3d(&tm_dqkv, out_g, h * 64, g * 128, b);
             tma_store_commit();
-            tma_store_wait_read();
+            store_pending = true;
           }
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
         }
       }
     }
   }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // outstanding TMA stores of this thread (no-op for most)
   tc_fence_before();
   __syncthreads();
   if (warp == 9) tmem_dealloc(tmem, 512);
