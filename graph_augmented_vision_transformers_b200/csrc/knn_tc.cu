@@ -7,11 +7,18 @@
 // exactly once (Np*D*2 bytes per image) and the Np x Np similarity matrix never leaves the SM.
 // bf16 x bf16 products are exact in fp32 and accumulate in fp32, so G matches an fp32 evaluation of the
 // same bf16 tokens to ~1e-6; the norms come from G's diagonal and S_ij = (G_ij * rn_i) * rn_j.
-// Epilogue: thread <-> similarity row (TMEM lane); it streams its row out of TMEM 32 columns at a time and
-// keeps a sorted top-k in registers with a strict ">" insertion, i.e. descending value, ties -> lowest index.
+// Epilogue: thread <-> similarity row (TMEM lane); it streams its row out of TMEM 32 columns at a time and keeps a
+// sorted top-k of 32-bit KEYS in registers: key = fixed-point similarity (24 bits: round(s * 2^22) + 2^22, s in [-1, 1])
+// above (255 - column) in the low byte.  Keys are distinct, larger key == larger similarity or, at equal similarity,
+// lower column, so inserting a candidate into the sorted list is one max/min pair per slot (2 integer instructions; the
+// fp32 (value, index) insertion needed a compare, a predicate-or and four selects per slot and made the top-k 70 % of
+// the kernel).  The 2^-22 quantum (2.4e-7) is below the ~1e-6 accumulation-order noise of the bf16 Gram matrix; the
+// emitted similarities are the de-quantised keys.
 //
 // Warp roles: 0-3 epilogue of rows 0-127, 4-7 epilogue of rows 128-255, 8 TMA producer, 9 MMA issuer.
 #include <float.h>
+
+#include <type_traits>
 
 #include "kernels.cuh"
 #include "tc.cuh"
@@ -25,6 +32,9 @@ constexpr int STAGES = 4;
 constexpr int STAGE_BYTES = 256 * 128;   // 256 token rows x 64 bf16
 constexpr int THREADS = 320;
 constexpr int TMEM_COLS = 512;           // two 128 x (<=256) fp32 accumulators
+// similarities are quantised to round(s * KEY_SCALE) for the top-k keys: 2^22 - 8 leaves room for |s| up to 1 + 1.9e-6
+// (rounding can push a cosine that far past 1) inside the 23-bit window of the float -> integer trick
+constexpr float KEY_SCALE = 4194296.0f;
 
 struct __align__(8) Ctrl {
   float rn[256];
@@ -111,48 +121,49 @@ __global__ void __launch_bounds__(THREADS, 1) knn_tc_kernel(const __grid_constan
     asm volatile("bar.sync 1, 256;" ::: "memory");        // the 8 epilogue warps: norms visible
     GVIT_TR(12);
     if (active) {
-      float tv[KT];
-      int ti[KT];
+      uint32_t key[KT];
 #pragma unroll
-      for (int s = 0; s < KT; ++s) { tv[s] = -FLT_MAX; ti[s] = 0x7fffffff; }
-      for (int c0 = 0; c0 < Np; c0 += 32) {
+      for (int s = 0; s < KT; ++s) key[s] = 0u;             // below every real key
+      const float ci = rn_i * KEY_SCALE;                    // fixed-point scale folded into the row factor
+      // one 32-column block of this thread's similarity row; MASK only for the block that straddles Np
+      auto block = [&](int c0, auto mask_tag) {
+        constexpr bool MASK = decltype(mask_tag)::value;
         float v[32];
         tmem_ld32(trow + c0, v);
+        const uint32_t cbase = 255u - (uint32_t)c0;
 #pragma unroll
         for (int t4 = 0; t4 < 32; t4 += 4) {
           const float4 rn4 = *reinterpret_cast<const float4*>(&ctl->rn[c0 + t4]);
           const float rnv[4] = {rn4.x, rn4.y, rn4.z, rn4.w};
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int j = c0 + t4 + u;
-            // columns >= Np can never be selected (-FLT_MAX never beats the initial entries under a strict ">")
-            float x = j < Np ? (v[t4 + u] * rn_i) * rnv[u] : -FLT_MAX;
-            int xi = j;
-            // branch-free insertion into the sorted list: the new element enters at the first entry it strictly beats
-            // (equal similarities keep ascending index order: ties -> lowest index) and everything below shifts down
-            // by one.  The data-dependent "if (sim > tv[k-1]) bubble up" of v1 diverged on almost every column of a
-            // warp: 55k cycles per image.
-            bool ins = false;
+            // round(s * KEY_SCALE) lands in the low mantissa bits of (x + 1.5 * 2^23); the << 8 drops the exponent byte
+            // and leaves 2^22 + round(s * KEY_SCALE) in bits 8..31
+            const float x = fmaf(v[t4 + u] * ci, rnv[u], 12582912.0f);
+            uint32_t kx = (__float_as_uint(x) << 8) + (cbase - (uint32_t)(t4 + u));
+            if (MASK && c0 + t4 + u >= Np) kx = 0u;         // columns >= Np can never be selected
+            // sorted insertion: the candidate sinks through the list, every slot keeps the larger key
 #pragma unroll
             for (int s = 0; s < KT; ++s) {
-              const bool gt = ins || x > tv[s];
-              ins = gt;
-              const float nv = gt ? x : tv[s];
-              const int ni = gt ? xi : ti[s];
-              x = gt ? tv[s] : x;
-              xi = gt ? ti[s] : xi;
-              tv[s] = nv;
-              ti[s] = ni;
+              const uint32_t hi = max(key[s], kx);
+              kx = min(key[s], kx);
+              key[s] = hi;
             }
           }
         }
-      }
+      };
+      int c0 = 0;
+      for (; c0 + 32 <= Np; c0 += 32) block(c0, std::false_type{});
+      if (c0 < Np) block(c0, std::true_type{});
       GVIT_TR(13);
       if (row < Np) {
         const int64_t o = ((int64_t)b * Np + row) * k;
 #pragma unroll
         for (int s = 0; s < KT; ++s)
-          if (s < k) { idx[o + s] = ti[s]; vals[o + s] = tv[s]; }
+          if (s < k) {
+            idx[o + s] = 255 - (int)(key[s] & 0xffu);
+            vals[o + s] = (float)((int)(key[s] >> 8) - 4194304) * (1.0f / KEY_SCALE);
+          }
       }
     }
   }

@@ -396,7 +396,7 @@ class _DropoutAdd(torch.autograd.Function):
 
 
 def dropout_add(y: torch.Tensor, resid: torch.Tensor | None, p: float, training: bool) -> torch.Tensor:
-    """``resid + dropout(y, p)`` in one pass (Philox-4x32-10 keep mask, stored as one bit per element).
+    """``resid + dropout(y, p)`` in one pass (Philox-4x32-7 keep mask, stored as one bit per element).
 
     ``resid`` may be None (plain dropout).  A bf16 branch ``y`` may be added onto an fp32 stream ``resid``.
     The seed of each call is drawn from PyTorch's CPU generator, so ``torch.manual_seed`` makes runs

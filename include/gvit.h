@@ -141,7 +141,7 @@ GVIT_API int gvit_layernorm_bwd(const void* dy, const void* x, const void* gamma
 enum { GVIT_COLSUM_CHUNKS = 1024 };
 GVIT_API int gvit_colsum(const void* x, int64_t rows, int D, int dtype, float* out, float* partial_ws, void* stream);
 
-/* out = resid + dropout(y, p) with a Philox-4x32-10 keep mask generated from (seed, offset) - the proj_drop +
+/* out = resid + dropout(y, p) with a Philox-4x32-7 keep mask generated from (seed, offset) - the proj_drop +
  * residual edge of vit.py:71,117 (also pos_drop, vit.py:212, with resid NULL).  p == 0 degenerates to an add.
  * dtype: type of resid / out (the residual stream); y_dtype: type of y (the branch) - same pairing rule as LayerNorm;
  * with resid NULL both must be equal.  keep_mask: n/8 bytes, ONE BIT per element (bit j of byte i = element 8i+j),
