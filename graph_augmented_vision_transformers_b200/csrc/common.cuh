@@ -81,4 +81,16 @@ inline int num_sms() {
   return n;
 }
 
+// Launch a grid-stride streaming kernel (256 threads, one 8-element group per thread and trip) as exactly ONE wave:
+// grid = min(blocks needed, SMs x resident CTAs of THIS kernel).  A fixed "8 CTAs per SM" guess put a 40-register kernel
+// (6 resident CTAs) at 1.33 waves: the last third of the CTAs ran alone at a third of the occupancy.
+template <typename... KArgs, typename... Args>
+inline void stream_launch(void (*kernel)(KArgs...), int64_t groups, cudaStream_t st, Args... args) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+  const int64_t blocks = (groups + 255) / 256, cap = (int64_t)num_sms() * per_sm;
+  const int grid = (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+  kernel<<<grid, 256, 0, st>>>(args...);
+}
+
 }  // namespace gvit

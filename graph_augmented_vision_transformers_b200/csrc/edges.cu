@@ -126,48 +126,45 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const Ty* __restrict__ d
     const Tx* xs = reinterpret_cast<const Tx*>(wring + (size_t)s * slot_bytes);
     const Ty* ys = reinterpret_cast<const Ty*>(wring + (size_t)s * slot_bytes + xpad);
     const Tx* as = reinterpret_cast<const Tx*>(wring + (size_t)s * slot_bytes + xpad + ypad);
-    float xv[NC][8], dyv[NC][8];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int d0 = lane * 8 + c * 256;
-      if (d0 < D) {
-        load8(xs + d0, xv[c]);
-        load8(ys + d0, dyv[c]);
-      }
-    }
-    if (!dx_add) {                                          // x / dy live in registers now: refill the slot at once
-      __syncwarp();
-      if (lane == 0 && row + (int64_t)slots * stride < rows) issue(row + (int64_t)slots * stride, s);
-    }
+    // Two passes over the row IN THE SLOT (shared memory), nothing but the 2 x NC x 8 column accumulators lives across
+    // them: holding the normalised row and gy in registers through the two warp reductions put the kernel at 128
+    // registers with local-memory spills on its hottest instructions (10 % of all stall samples on one STL).
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const int d0 = lane * 8 + c * 256;
       if (d0 < D) {
+        float xv[8], dyv[8];
+        load8(xs + d0, xv);
+        load8(ys + d0, dyv);
         const float4 g0 = *reinterpret_cast<const float4*>(&gsm[d0]), g1 = *reinterpret_cast<const float4*>(&gsm[d0 + 4]);
         const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-          const float xh = (xv[c][t] - mu) * rs;
-          xv[c][t] = xh;                                   // x is only needed normalised from here on
-          dg[c][t] = fmaf(dyv[c][t], xh, dg[c][t]);
-          db[c][t] += dyv[c][t];
-          dyv[c][t] *= g[t];                               // gy
-          s1 += dyv[c][t];
-          s2 = fmaf(dyv[c][t], xh, s2);
+          const float xh = (xv[t] - mu) * rs;
+          dg[c][t] = fmaf(dyv[t], xh, dg[c][t]);
+          db[c][t] += dyv[t];
+          const float gy = dyv[t] * g[t];
+          s1 += gy;
+          s2 = fmaf(gy, xh, s2);
         }
       }
     }
     s1 = warp_sum(s1) * invD;
     s2 = warp_sum(s2) * invD;
+    asm volatile("" ::: "memory");                           // pass 2 re-reads the slot instead of keeping pass 1's values
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const int d0 = lane * 8 + c * 256;
       if (d0 < D) {
-        float o[8];
+        float xv[8], dyv[8], o[8];
+        load8(xs + d0, xv);
+        load8(ys + d0, dyv);
+        const float4 g0 = *reinterpret_cast<const float4*>(&gsm[d0]), g1 = *reinterpret_cast<const float4*>(&gsm[d0 + 4]);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-        for (int t = 0; t < 8; ++t) o[t] = rs * (dyv[c][t] - s1 - xv[c][t] * s2);
-        if (dx_add) {                                       // read from the slot: no registers held across the row
+        for (int t = 0; t < 8; ++t) o[t] = rs * (dyv[t] * g[t] - s1 - ((xv[t] - mu) * rs) * s2);
+        if (dx_add) {
           float a[8];
           load8(as + d0, a);
 #pragma unroll
@@ -176,10 +173,8 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const Ty* __restrict__ d
         store8(dx + row * D + d0, o);
       }
     }
-    if (dx_add) {                                           // the add row was read from the slot just above
-      __syncwarp();
-      if (lane == 0 && row + (int64_t)slots * stride < rows) issue(row + (int64_t)slots * stride, s);
-    }
+    __syncwarp();                                            // every lane is done with the slot: refill it
+    if (lane == 0 && row + (int64_t)slots * stride < rows) issue(row + (int64_t)slots * stride, s);
   }
   __syncthreads();                                          // all warps out of the ring before it is reused below
   // reduce the 8 warps' partials column by column through shared memory, 256 columns at a time
@@ -483,7 +478,7 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
 // (vit.py:70-71, 90-93), so the same pass accumulates them: same 2-D mapping as colsum_partial_kernel
 // (block = 32 column groups x 8 row lanes, grid = column blocks x row chunks), four rows in flight per thread.
 template <typename Tx, typename Ty, bool GELU>
-__global__ void __launch_bounds__(256, GELU ? 3 : 2) edge_bwd_colsum_kernel(const Tx* __restrict__ dout, const Ty* __restrict__ u,
+__global__ void __launch_bounds__(256, GELU ? 4 : 2) edge_bwd_colsum_kernel(const Tx* __restrict__ dout, const Ty* __restrict__ u,
                                                               const uint8_t* __restrict__ mask, int64_t rows, int D,
                                                               int rows_per_chunk, float p, Ty* __restrict__ dy,
                                                               float* __restrict__ partial) {
@@ -495,7 +490,10 @@ __global__ void __launch_bounds__(256, GELU ? 3 : 2) edge_bwd_colsum_kernel(cons
   const int64_t r1 = r0 + rows_per_chunk < rows ? r0 + rows_per_chunk : rows;
   float acc[8] = {};
   if (col < D) {
-    constexpr int RF = GELU ? 2 : 4;                        // rows in flight per thread (GELU': keep 24 warps / SM)
+    // rows in flight per thread.  GELU': ONE, at 32 warps / SM (<= 64 registers) - measured 184 us against 224 us for
+    // two rows at 24 warps and 267 us for three (A/B on B200, B = 256): the GELU' arithmetic needs warps to hide behind
+    // more than it needs bytes in flight per warp.
+    constexpr int RF = GELU ? 1 : 4;
     for (int64_t r = r0 + ry; r < r1; r += 8 * RF) {
       float g[RF][8], a[RF][8];
       uint32_t bits[RF];
@@ -656,16 +654,16 @@ int colsum(const void* x, int64_t rows, int D, int dtype, float* out, float* par
 
 int dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, uint64_t seed, uint64_t offset,
                          const uint64_t* offset_dev, int dtype, int y_dtype, void* out, uint8_t* keep_mask, cudaStream_t st) {
-  const int grid = stream_grid(n / 8);
+  const int64_t n8 = n / 8;
   using bf = __nv_bfloat16;
   if (dtype == GVIT_F32 && y_dtype == GVIT_F32)
-    dropout_residual_fwd_kernel<float, float><<<grid, 256, 0, st>>>(static_cast<const float*>(y), static_cast<const float*>(resid),
+    stream_launch(dropout_residual_fwd_kernel<float, float>, n8, st, static_cast<const float*>(y), static_cast<const float*>(resid),
                                                                     n, p, seed, offset, offset_dev, static_cast<float*>(out), keep_mask);
   else if (dtype == GVIT_F32)
-    dropout_residual_fwd_kernel<float, bf><<<grid, 256, 0, st>>>(static_cast<const bf*>(y), static_cast<const float*>(resid), n, p,
+    stream_launch(dropout_residual_fwd_kernel<float, bf>, n8, st, static_cast<const bf*>(y), static_cast<const float*>(resid), n, p,
                                                                  seed, offset, offset_dev, static_cast<float*>(out), keep_mask);
   else
-    dropout_residual_fwd_kernel<bf, bf><<<grid, 256, 0, st>>>(static_cast<const bf*>(y), static_cast<const bf*>(resid), n, p, seed,
+    stream_launch(dropout_residual_fwd_kernel<bf, bf>, n8, st, static_cast<const bf*>(y), static_cast<const bf*>(resid), n, p, seed,
                                                               offset, offset_dev, static_cast<bf*>(out), keep_mask);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
@@ -690,24 +688,24 @@ int dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, 
     GVIT_CHECK_LAUNCH();
     return GVIT_OK;
   }
-  const int grid = stream_grid(n / 8);
+  const int64_t n8 = n / 8;
   if (dtype == GVIT_F32 && y_dtype == GVIT_F32)
-    dropout_bwd_kernel<float, float><<<grid, 256, 0, st>>>(static_cast<const float*>(dout), keep_mask, n, p, static_cast<float*>(dy));
+    stream_launch(dropout_bwd_kernel<float, float>, n8, st, static_cast<const float*>(dout), keep_mask, n, p, static_cast<float*>(dy));
   else if (dtype == GVIT_F32)
-    dropout_bwd_kernel<float, bf><<<grid, 256, 0, st>>>(static_cast<const float*>(dout), keep_mask, n, p, static_cast<bf*>(dy));
+    stream_launch(dropout_bwd_kernel<float, bf>, n8, st, static_cast<const float*>(dout), keep_mask, n, p, static_cast<bf*>(dy));
   else
-    dropout_bwd_kernel<bf, bf><<<grid, 256, 0, st>>>(static_cast<const bf*>(dout), keep_mask, n, p, static_cast<bf*>(dy));
+    stream_launch(dropout_bwd_kernel<bf, bf>, n8, st, static_cast<const bf*>(dout), keep_mask, n, p, static_cast<bf*>(dy));
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }
 
 int gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype,
                      void* out, uint8_t* keep_mask, cudaStream_t st) {
-  const int grid = stream_grid(n / 8);
+  const int64_t n8 = n / 8;
   if (dtype == GVIT_F32)
-    gelu_dropout_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(u), n, p, seed, offset, offset_dev, static_cast<float*>(out), keep_mask);
+    stream_launch(gelu_dropout_fwd_kernel<float>, n8, st, static_cast<const float*>(u), n, p, seed, offset, offset_dev, static_cast<float*>(out), keep_mask);
   else
-    gelu_dropout_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(u), n, p, seed, offset, offset_dev,
+    stream_launch(gelu_dropout_fwd_kernel<__nv_bfloat16>, n8, st, static_cast<const __nv_bfloat16*>(u), n, p, seed, offset, offset_dev,
                                                                  static_cast<__nv_bfloat16*>(out), keep_mask);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
@@ -719,7 +717,7 @@ int gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, 
     using bf = __nv_bfloat16;
     int cb, nch, rpc;
     const int64_t rows = n / D;
-    colsum_grid(rows, D, 6, &cb, &nch, &rpc);
+    colsum_grid(rows, D, 12, &cb, &nch, &rpc);               // 3 waves of 4 resident CTAs: measured best of 3..48
     dim3 g2(cb, nch);
     if (dtype == GVIT_F32)
       edge_bwd_colsum_kernel<float, float, true><<<g2, 256, 0, st>>>(static_cast<const float*>(dout), static_cast<const float*>(u), keep_mask, rows, D, rpc, p, static_cast<float*>(du), partial_ws);
@@ -730,12 +728,12 @@ int gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, 
     GVIT_CHECK_LAUNCH();
     return GVIT_OK;
   }
-  const int grid = stream_grid(n / 8);
+  const int64_t n8 = n / 8;
   if (dtype == GVIT_F32)
-    gelu_dropout_bwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(dout), static_cast<const float*>(u), keep_mask, n, p,
+    stream_launch(gelu_dropout_bwd_kernel<float>, n8, st, static_cast<const float*>(dout), static_cast<const float*>(u), keep_mask, n, p,
                                                          static_cast<float*>(du));
   else
-    gelu_dropout_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dout),
+    stream_launch(gelu_dropout_bwd_kernel<__nv_bfloat16>, n8, st, static_cast<const __nv_bfloat16*>(dout),
                                                                  static_cast<const __nv_bfloat16*>(u), keep_mask, n, p,
                                                                  static_cast<__nv_bfloat16*>(du));
   GVIT_CHECK_LAUNCH();

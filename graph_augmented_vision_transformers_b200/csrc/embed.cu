@@ -94,13 +94,13 @@ inline int grid_for(int64_t items) {
 
 int patchify(const void* img, int B, int C, int H, int W, int P, int in_dtype, int out_dtype, void* out, cudaStream_t st) {
   using bf = __nv_bfloat16;
-  const int grid = grid_for((int64_t)B * C * H * (W / 8));
+  const int64_t n8 = (int64_t)B * C * H * (W / 8);
   if (in_dtype == GVIT_F32 && out_dtype == GVIT_F32)
-    patchify_kernel<float, float><<<grid, 256, 0, st>>>(static_cast<const float*>(img), B, C, H, W, P, static_cast<float*>(out));
+    stream_launch(patchify_kernel<float, float>, n8, st, static_cast<const float*>(img), B, C, H, W, P, static_cast<float*>(out));
   else if (in_dtype == GVIT_F32)
-    patchify_kernel<float, bf><<<grid, 256, 0, st>>>(static_cast<const float*>(img), B, C, H, W, P, static_cast<bf*>(out));
+    stream_launch(patchify_kernel<float, bf>, n8, st, static_cast<const float*>(img), B, C, H, W, P, static_cast<bf*>(out));
   else
-    patchify_kernel<bf, bf><<<grid, 256, 0, st>>>(static_cast<const bf*>(img), B, C, H, W, P, static_cast<bf*>(out));
+    stream_launch(patchify_kernel<bf, bf>, n8, st, static_cast<const bf*>(img), B, C, H, W, P, static_cast<bf*>(out));
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }
@@ -109,15 +109,15 @@ int embed_assemble(const void* y, const void* bias, const void* cls, const void*
                    uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, int param_dtype, void* out, uint8_t* keep_mask,
                    cudaStream_t st) {
   using bf = __nv_bfloat16;
-  const int grid = grid_for((int64_t)B * N * (D / 8));
+  const int64_t n8 = (int64_t)B * N * (D / 8);
   if (dtype == GVIT_F32)
-    embed_assemble_kernel<float, float><<<grid, 256, 0, st>>>(static_cast<const float*>(y), static_cast<const float*>(bias), static_cast<const float*>(cls),
+    stream_launch(embed_assemble_kernel<float, float>, n8, st, static_cast<const float*>(y), static_cast<const float*>(bias), static_cast<const float*>(cls),
                                                               static_cast<const float*>(pos), B, N, D, p, seed, offset, offset_dev, static_cast<float*>(out), keep_mask);
   else if (param_dtype == GVIT_F32)
-    embed_assemble_kernel<bf, float><<<grid, 256, 0, st>>>(static_cast<const bf*>(y), static_cast<const float*>(bias), static_cast<const float*>(cls),
+    stream_launch(embed_assemble_kernel<bf, float>, n8, st, static_cast<const bf*>(y), static_cast<const float*>(bias), static_cast<const float*>(cls),
                                                            static_cast<const float*>(pos), B, N, D, p, seed, offset, offset_dev, static_cast<bf*>(out), keep_mask);
   else
-    embed_assemble_kernel<bf, bf><<<grid, 256, 0, st>>>(static_cast<const bf*>(y), static_cast<const bf*>(bias), static_cast<const bf*>(cls),
+    stream_launch(embed_assemble_kernel<bf, bf>, n8, st, static_cast<const bf*>(y), static_cast<const bf*>(bias), static_cast<const bf*>(cls),
                                                         static_cast<const bf*>(pos), B, N, D, p, seed, offset, offset_dev, static_cast<bf*>(out), keep_mask);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;

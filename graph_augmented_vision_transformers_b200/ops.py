@@ -146,9 +146,10 @@ def _wgrad(dy2: torch.Tensor, x2: torch.Tensor, master_dtype: torch.dtype) -> to
 
 
 def _colsum_ws(rows: int, D: int, device) -> torch.Tensor:
-    """Workspace of gvit_colsum / the *_bwd column sums: (row chunks the launcher will use) x D floats."""
+    """Workspace of gvit_colsum / the *_bwd column sums: an upper bound of the row chunks the launchers use (at most 12
+    per SM and column block, never more than GVIT_COLSUM_CHUNKS or rows / 32) x D floats."""
     cb = (D + 255) // 256
-    n = min(GVIT_COLSUM_CHUNKS, (6 * _sm_count(device) + cb - 1) // cb + 1, max(1, (rows + 31) // 32) + 1)
+    n = min(GVIT_COLSUM_CHUNKS, (12 * _sm_count(device) + cb - 1) // cb + 1, max(1, (rows + 31) // 32) + 1)
     return torch.empty(n * D, dtype=torch.float32, device=device)
 
 
