@@ -419,7 +419,16 @@ def run_ours(args):
                 "last_loss": losses[-1] if losses else None}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: destroying the process group (or the interpreter's own teardown) while a captured
+        # CUDA graph still holds NCCL kernels hung both ranks at exit (measured at N = 2).  Everything is flushed and every
+        # rank has passed the barrier, so a hard exit loses nothing.
+        if captured is not None:
+            captured.release()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def _reserve_stdout():
