@@ -112,7 +112,9 @@ class CapturedTrainStep:
         return self.loss
 
     def release(self):
-        """Drop the graph and its memory pool; dropout goes back to host-drawn seeds."""
+        """Drop the graph and its memory pool; dropout goes back to host-drawn seeds.  With a ``grad_sync`` the graph
+        holds NCCL kernels: release it (and synchronize) BEFORE ``torch.distributed.destroy_process_group()`` - tearing
+        the communicator down under a live graph hung both ranks in testing."""
         self.graph = None
         self.loss = None
         ops.set_rng_offset_tensor(None)

@@ -17,7 +17,7 @@ def test_header_declares_the_expected_surface():
     for must in ("gvit_knn_fwd", "gvit_knn_bwd", "gvit_graph_reverse", "gvit_agg_fwd", "gvit_agg_gather_fwd",
                  "gvit_agg_bwd", "gvit_graph_bwd", "gvit_attn_fwd", "gvit_attn_bwd", "gvit_layernorm_fwd", "gvit_layernorm_bwd",
                  "gvit_colsum", "gvit_dropout_residual_fwd", "gvit_dropout_bwd", "gvit_gelu_dropout_fwd", "gvit_gelu_dropout_bwd",
-                 "gvit_version", "gvit_last_error_string"):
+                 "gvit_patchify", "gvit_embed_assemble", "gvit_version", "gvit_last_error_string"):
         assert must in names
     assert len(names) == len(set(names))
 
@@ -56,6 +56,12 @@ def test_validation_errors_are_loud_and_need_no_gpu():
         _lib.call("gvit_layernorm_fwd", 16, 16, 16, 1, 64, 1e-5, _lib.GVIT_BF16, _lib.GVIT_F32, 16, 16, 16, None)
     with pytest.raises(_lib.GvitError, match="GVIT_ERR_UNSUPPORTED"):
         _lib.call("gvit_agg_fwd", 16, 1, 16, 64, 4, _lib.GVIT_F32, 16, 16, 16, None, None, 16, None, None, 0, None)
+    with pytest.raises(_lib.GvitError, match="GVIT_ERR_SHAPE"):            # patch size must be a multiple of 8
+        _lib.call("gvit_patchify", 16, 1, 3, 224, 224, 14, _lib.GVIT_F32, _lib.GVIT_BF16, 16, None)
+    with pytest.raises(_lib.GvitError, match="GVIT_ERR_DTYPE"):            # a bf16 image cannot produce fp32 patches
+        _lib.call("gvit_patchify", 16, 1, 3, 224, 224, 16, _lib.GVIT_BF16, _lib.GVIT_F32, 16, None)
+    with pytest.raises(_lib.GvitError, match="GVIT_ERR_SHAPE"):            # dropout without a keep-mask buffer
+        _lib.call("gvit_embed_assemble", 16, 16, 16, 16, 1, 197, 768, 0.1, 1, 0, None, _lib.GVIT_BF16, _lib.GVIT_F32, 16, None, None)
     with pytest.raises(_lib.GvitError, match="GVIT_ERR_UNSUPPORTED"):      # the fused graph backward is bf16-only
         _lib.call("gvit_graph_bwd", 16, 1024, 64, 1, 16, 64, 4, _lib.GVIT_F32, 16, 16, 16, 16, 16, 1024, 16, 16, None)
 

@@ -108,3 +108,61 @@ def test_loss_matches_reference_fixture():
     assert abs(float(loss) - float(g["loss"])) < 1e-6
     for n in ("wbce", "focal", "asl"):
         assert abs(float(parts[n]) - float(g[n])) < 1e-6, n
+
+
+def test_ops_refuse_cpu_tensors_for_the_new_rows():
+    """f2 / f4 host logic: no CPU fallback behind the token prologue, loud errors for unsupported patch sizes."""
+    import torch
+    from graph_augmented_vision_transformers_b200 import ops
+    img, w = torch.randn(1, 3, 32, 32), torch.randn(64, 3, 16, 16)
+    z = torch.zeros(1, 5, 64)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.patch_embed_tokens(img, w, None, z[:, :1], z, 0.0, False)
+    assert ops.patch_embed_supported(img, w)
+    assert not ops.patch_embed_supported(img, torch.randn(64, 3, 12, 12))          # 12 is not a multiple of 8
+    assert not ops.patch_embed_supported(torch.randn(1, 3, 40, 40), w)             # 40 is not a multiple of 16
+
+
+def test_shadow_cache_ignores_cpu_parameters_and_follows_epochs():
+    import torch
+    from graph_augmented_vision_transformers_b200 import ops
+    p = torch.nn.Parameter(torch.randn(4, 4))
+    ops.refresh_shadows([p, None], torch.bfloat16)                                  # CPU parameters are skipped, not cast
+    assert id(p) not in ops._SHADOWS
+    s = ops._shadow(p, torch.bfloat16)                                              # one-off cast, no autograd edge
+    assert s.dtype == torch.bfloat16 and not s.requires_grad and torch.equal(s, p.detach().bfloat16())
+    assert ops._shadow(p, torch.float32).data_ptr() == p.data_ptr()                 # same dtype: the parameter itself
+    e0 = ops._SHADOW_EPOCH["n"]
+    ops.invalidate_shadows()
+    assert ops._SHADOW_EPOCH["n"] == e0 + 1
+
+
+def test_captured_step_requires_a_capturable_optimizer():
+    import torch
+    from graph_augmented_vision_transformers_b200.step import CapturedTrainStep
+    m = torch.nn.Linear(4, 4)
+    with pytest.raises(ValueError, match="capturable"):
+        CapturedTrainStep(m, torch.nn.MSELoss(), torch.optim.AdamW(m.parameters()))
+    with pytest.raises(ValueError, match="int64"):
+        from graph_augmented_vision_transformers_b200 import ops
+        ops.set_rng_offset_tensor(torch.zeros(1))
+
+
+def test_colsum_workspace_covers_the_launchers_chunking():
+    """ops._colsum_ws must be an upper bound of the row chunks the C launchers use (<= 12 per SM and column block)."""
+    from graph_augmented_vision_transformers_b200 import ops
+    import torch
+
+    def chunks(rows, D, per_sm, sms=148):                                           # colsum_grid() of edges.cu
+        cb = (D + 255) // 256
+        n = min((per_sm * sms + cb - 1) // cb, 1024)
+        if n * 32 > rows:
+            n = (rows + 31) // 32
+        rpc = (rows + n - 1) // n
+        return (rows + rpc - 1) // rpc
+
+    for rows, D in [(256 * 197, 3072), (256 * 197, 768), (256, 197 * 768), (2, 64), (50432, 2304)]:
+        cb = (D + 255) // 256
+        bound = min(1024, (12 * 148 + cb - 1) // cb + 1, max(1, (rows + 31) // 32) + 1)
+        for per_sm in (6, 12):
+            assert chunks(rows, D, per_sm) <= bound, (rows, D, per_sm)
