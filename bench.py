@@ -173,6 +173,8 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
     xs = [torch.randn(B, N, D, device=dev, dtype=bf, generator=g) for _ in range(R)]
     qkvs = [torch.randn(B, N, 3 * D, device=dev, dtype=bf, generator=g) for _ in range(2)]
     W = torch.randn(D, D, device=dev, dtype=bf, generator=g) * 0.03
+    W1 = torch.randn(4 * D, D, device=dev, dtype=bf, generator=g) * 0.03
+    b1 = torch.zeros(4 * D, device=dev, dtype=bf)
     bias = torch.zeros(D, device=dev, dtype=bf)
     gam, bet = torch.ones(D, device=dev, dtype=bf), torch.zeros(D, device=dev, dtype=bf)
     idx, vals, rnorm = ops.knn_graph(hs[0], k)
@@ -215,8 +217,10 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
                           2 * B * N * D * e, 0.0, "hbm", 36),
         "layernorm_bwd": (lambda i: _call("gvit_layernorm_bwd", _ptr(xs[i % R]), _ptr(hs[i % R]), _ptr(gam), _ptr(mean), _ptr(rstd), B * N, D, dt, dt, None, _ptr(out), _ptr(dgb[0]), _ptr(dgb[1]), _ptr(ws), st),
                           3 * B * N * D * e, 0.0, "hbm", 1),
+        "fc1_fused": (lambda i: _call("gvit_linear_gelu_dropout_fwd", _ptr(hs[i % R]), _ptr(W1), _ptr(b1), B * N, 4 * D, D, 0.1, 1234, 0, None, dt, _ptr(u4[i % 2]), _ptr(o4), _ptr(m4), st),
+                      B * N * D * e + 4 * D * D * e + 2 * B * N * 4 * D * e + B * N * 4 * D // 8, 2.0 * B * N * D * 4 * D, "tensor", 12),
         "gelu_dropout_fwd": (lambda i: _call("gvit_gelu_dropout_fwd", _ptr(u4[i % 2]), B * N * 4 * D, 0.1, 1234, 0, None, dt, _ptr(o4), _ptr(m4), st),
-                             2 * B * N * 4 * D * e + B * N * 4 * D // 8, 0.0, "hbm", 12),
+                             2 * B * N * 4 * D * e + B * N * 4 * D // 8, 0.0, "hbm", 0),      # folded into fc1_fused for bf16
         "gelu_dropout_bwd": (lambda i: _call("gvit_gelu_dropout_bwd", _ptr(u4[(i + 1) % 2]), _ptr(u4[i % 2]), _ptr(m4), B * N * 4 * D, 0.1, dt, _ptr(o4), 4 * D, _ptr(cs_out), _ptr(cs_ws), st),
                              3 * B * N * 4 * D * e + B * N * 4 * D // 8, 0.0, "hbm", 12),
         "colsum_3072": (lambda i: _call("gvit_colsum", _ptr(u4[i % 2]), B * N, 4 * D, dt, _ptr(cs_out), _ptr(cs_ws), st),

@@ -41,6 +41,7 @@ int gvit_describe_path(const char* op, int dtype, int n_tokens, int dim, char* b
   else if (!strcmp(op, "graph_bwd")) path = (bf16 && gvit::graph_bwd_tc_supported(n_tokens, dim, 8)) ? "graph_bwd:tcgen05+tma" : "graph_bwd:reverse-csr+gather";
   else if (!strcmp(op, "attn_fwd")) path = (bf16 && gvit::attn_fwd_tc_supported(n_tokens, dim)) ? "attn_fwd:tcgen05+tma" : "attn_fwd:fp32-fma";
   else if (!strcmp(op, "attn_bwd")) path = (bf16 && gvit::attn_bwd_tc_supported(n_tokens, dim)) ? "attn_bwd:tcgen05+tma" : "attn_bwd:fp32-fma";
+  else if (!strcmp(op, "fc1")) path = (bf16 && gvit::fc1_tc_supported(1, n_tokens, dim)) ? "fc1:tcgen05+tma fused bias+gelu+dropout" : "fc1:library-gemm+edge";
   else if (!strcmp(op, "layernorm") || !strcmp(op, "dropout_residual")) path = "edge:vectorised";
   snprintf(buf, buf_len, "%s", path);
   return GVIT_OK;

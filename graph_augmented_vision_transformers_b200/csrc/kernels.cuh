@@ -61,6 +61,11 @@ int gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, 
                      int D, float* colsum_out, float* partial_ws, cudaStream_t st);
 
 
+// ---- fused fc1 : mlp_tc.cu
+bool fc1_tc_supported(int64_t M, int N, int K);
+int fc1_gelu_dropout_fwd_tc(const void* x, const void* w, const void* bias, int64_t M, int N, int K, float p, uint64_t seed,
+                            uint64_t offset, const uint64_t* offset_dev, void* u, void* out, uint8_t* mask, cudaStream_t st);
+
 // ---- token prologue : embed.cu
 int patchify(const void* img, int B, int C, int H, int W, int P, int in_dtype, int out_dtype, void* out, cudaStream_t st);
 int embed_assemble(const void* y, const void* bias, const void* cls, const void* pos, int B, int N, int D, float p,

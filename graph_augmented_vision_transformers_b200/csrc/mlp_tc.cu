@@ -1,0 +1,256 @@
+// mlp_tc.cu - fc1 of the Mlp with its whole epilogue in one kernel:
+//
+//     u   = x W^T + b                         (vit.py:90, nn.Linear)            -> saved for the backward, bf16
+//     out = dropout(gelu(u), p)               (vit.py:91-92, nn.GELU, nn.Dropout) -> bf16 + 1-bit keep mask
+//
+// As a library GEMM plus the gvit_gelu_dropout_fwd pass this is 173 us + 163 us at B = 256 (M = 50432, N = 3072,
+// K = 768): the elementwise pass is issue-bound ALU work (GELU + Philox) over 640 MB.  Here that ALU work runs in the
+// epilogue warps of a persistent tcgen05 GEMM, under the tensor pipe's shadow: the accumulator tile (128 x 256 fp32) is
+// double-buffered in TMEM, so the MMAs of tile i+1 overlap bias + GELU + dropout + the two stores of tile i, and the
+// pre-activation never makes the extra HBM round trip.
+//
+// Tiles: BM x BN x BK = 128 x 256 x 64, both operands K-major ([rows][64 bf16] 128B-swizzled TMA boxes), 4-stage ring
+// (48 KB per stage).  One tcgen05.mma is 128 x 256 x 16: 12 KB of shared-memory operands per 128 tensor cycles.
+// Tile order: consecutive tile ids share the x row block (the 12 column tiles of one row block run on neighbouring
+// CTAs at the same time, so x is read from HBM once and from L2 eleven times); W (4.7 MB) stays L2-resident.
+// Measured on B200: the main loop alone runs at 1.07 PF/s - the L2 -> SM operand traffic of un-clustered 128 x 256
+// tiles (96 B/clk/SM at full tensor rate, ~43 B/clk/SM available chip-wide) is its bound - and the epilogue is ~30
+// instructions per element, so SIXTEEN epilogue warps (4 per scheduler) are needed to keep it off the critical path:
+// with eight, the kernel ran at the speed of GEMM + separate elementwise pass.
+// Clusters of two CTAs work on the two row blocks (2i, 2i+1) of the same column tile: each CTA fetches HALF of the W tile
+// and TMA-multicasts it to both, so the L2 -> SM traffic per tile drops from 48 to 32 KB per stage (a ring slot is
+// refilled once BOTH CTAs have released it: the MMA warps commit to the empty barrier of both CTAs).
+// Warp roles: 0-15 epilogue (warpgroup g = warp / 4 owns accumulator columns [64g, 64g + 64), thread <-> row = TMEM lane),
+// 16 TMA producer, 17 MMA issuer.
+#include "gelu.cuh"
+#include "kernels.cuh"
+#include "philox.cuh"
+#include "tc.cuh"
+
+namespace gvit {
+namespace {
+
+using namespace tc;
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int EPI_WARPS = 16;
+constexpr int WSTAGE = 2 * 1024;            // per-warp staging ([32 rows][64 B]) for coalesced global stores
+constexpr int THREADS = (EPI_WARPS + 2) * 32;
+
+struct __align__(8) Ctrl {
+  uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_free[2];
+  uint32_t tmem_base;
+};
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_WARPS * WSTAGE + sizeof(Ctrl);
+
+struct Params {
+  int64_t M;
+  int N, K;
+  float p;
+  uint64_t seed, offset;
+  const uint64_t* offset_dev;
+  const __nv_bfloat16* bias;
+  __nv_bfloat16* u;
+  __nv_bfloat16* out;
+  uint8_t* mask;
+};
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) fc1_gelu_dropout_tc_kernel(const __grid_constant__ CUtensorMap tm_x,
+                                                                         const __grid_constant__ CUtensorMap tm_w,
+                                                                         const Params P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* ring = smem_raw;
+  if ((smem_u32(ring) & 1023u) != 0) __trap();
+  uint8_t* sStg = ring + (size_t)STAGES * STAGE_BYTES;
+  Ctrl* ctl = reinterpret_cast<Ctrl*>(sStg + EPI_WARPS * WSTAGE);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int nM = (int)((P.M + BM - 1) / BM), nN = P.N / BN, nK = P.K / BK;
+  const int rank = (int)cluster_ctarank();                 // 0 / 1: which row block of the pair, which half of W to fetch
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const int npairs = ((nM + 1) >> 1) * nN;                 // (row-block pair, column tile); an odd last row block pairs with
+                                                           // an empty one (TMA zero-fills, the stores are row-guarded)
+
+  if (warp == EPI_WARPS && lane == 0) {
+    prefetch_tmap(&tm_x);
+    prefetch_tmap(&tm_w);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 2); }   // empty: both CTAs' MMA warps
+    for (int s = 0; s < 2; ++s) { mbar_init(&ctl->acc_full[s], 1); mbar_init(&ctl->acc_free[s], EPI_WARPS * 32); }
+    fence_mbar_init();
+  }
+  if (warp == EPI_WARPS + 1) tmem_alloc(&ctl->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                      // the peer's barriers exist before anything is multicast to it
+  tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
+
+  if (warp == EPI_WARPS) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int it = 0;
+      for (int pr = cid; pr < npairs; pr += ncl) {
+        const int mp = pr / nN, n = pr - mp * nN, m = 2 * mp + rank;
+        for (int kb = 0; kb < nK; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&ctl->empty[s], ((it / STAGES) & 1) ^ 1);            // released by BOTH CTAs of the cluster
+          mbar_expect_tx(&ctl->full[s], (uint32_t)STAGE_BYTES);          // own x tile + own W half + the peer's W half
+          tma_load_3d(ring + (size_t)s * STAGE_BYTES, &tm_x, kb * BK, m * BM, 0, &ctl->full[s]);             // rows >= M: zeros
+          tma_load_3d_mc(ring + (size_t)s * STAGE_BYTES + A_BYTES + rank * (B_BYTES / 2), &tm_w, kb * BK, n * BN + rank * (BN / 2), 0,
+                         &ctl->full[s], (uint16_t)0b11);
+        }
+      }
+    }
+  } else if (warp == EPI_WARPS + 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(BM, BN, false, false);
+      const uint32_t aR = smem_u32(ring);
+      int it = 0, tc = 0;
+      for (int pr = cid; pr < npairs; pr += ncl, ++tc) {
+        const int buf = tc & 1;
+        if (tc >= 2) {                              // the epilogue has drained this accumulator buffer (use tc/2 - 1)
+          mbar_wait(&ctl->acc_free[buf], ((tc >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        for (int kb = 0; kb < nK; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&ctl->full[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t aA = aR + s * STAGE_BYTES, aB = aA + A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_ss(tmem + buf * BN, make_sdesc(aA + kk * 32), make_sdesc(aB + kk * 32), idesc, kb > 0 || kk > 0);
+          umma_commit_mc(&ctl->empty[s], (uint16_t)0b11);             // slot s of BOTH CTAs is written by the next refill
+        }
+        umma_commit(&ctl->acc_full[buf]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int g = warp >> 2;                                           // accumulator column quarter
+    uint8_t* stg = sStg + warp * WSTAGE;
+    const uint32_t tl = tmem_lane_base(tmem, warp) + g * 64;
+    const int ch4 = lane & 3, r4 = lane >> 2;                          // coalesced pattern: 4 lanes per 64-byte row segment
+    const float scale = P.p > 0.f ? 1.0f / (1.0f - P.p) : 1.0f;
+    const uint32_t th = dropout_thresh16(P.p);
+    const uint64_t off = P.offset + (P.offset_dev ? __ldg(P.offset_dev) : 0ull);
+    // staging tile [32 rows][64 B]: 16-byte chunk q of row r lives at chunk q ^ ((r >> 1) & 3) - conflict-free for the
+    // row-per-lane writes and for the 4-lanes-per-row reads
+    auto stage = [&](const uint32_t (&w)[16]) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    };
+    // this warp's 32 staged rows x 32 columns -> global, eight 64-byte row segments per instruction
+    auto flush = [&](__nv_bfloat16* dst, int64_t row0, int col0) {
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r4 + 8 * i;
+        if (row0 + r < P.M) {
+          const uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 64 + ((ch4 ^ ((r >> 1) & 3)) << 4));
+          *reinterpret_cast<uint4*>(dst + (row0 + r) * P.N + col0 + ch4 * 8) = v4;
+        }
+      }
+      __syncwarp();
+    };
+    int tc = 0;
+    for (int pr = cid; pr < npairs; pr += ncl, ++tc) {
+      const int mp = pr / nN, n = pr - mp * nN, m = 2 * mp + rank;
+      const int buf = tc & 1;
+      const int64_t wrow0 = (int64_t)m * BM + (warp & 3) * 32;         // first row of this warp
+      const int64_t row = wrow0 + lane;
+      mbar_wait(&ctl->acc_full[buf], (tc >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {                                    // 32 columns at a time
+        const int col0 = n * BN + g * 64 + h * 32;
+        // bias of these 32 columns as fp32 in the (idle) staging area: every lane then reads it with broadcast LDS.128
+        float* sbias = reinterpret_cast<float*>(stg);
+        if (lane < 8) {
+          float4 bf4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (P.bias) {
+            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(P.bias + col0 + lane * 4));
+            bf4 = make_float4(bf_lo(raw.x), bf_hi(raw.x), bf_lo(raw.y), bf_hi(raw.y));
+          }
+          *reinterpret_cast<float4*>(sbias + lane * 4) = bf4;
+        }
+        float v[32];
+        tmem_ld32(tl + buf * BN + h * 32, v);
+        if (h == 1) {                                                  // this thread's accumulator row has been read
+          tc_fence_before();
+          mbar_arrive(&ctl->acc_free[buf]);
+        }
+        __syncwarp();
+        uint32_t upk[16];                                              // u as stored: 32 bf16
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 bq = *reinterpret_cast<const float4*>(sbias + q4 * 4);
+          upk[2 * q4] = pack2(v[4 * q4] + bq.x, v[4 * q4 + 1] + bq.y);
+          upk[2 * q4 + 1] = pack2(v[4 * q4 + 2] + bq.z, v[4 * q4 + 3] + bq.w);
+        }
+        __syncwarp();                                                  // bias reads done: the staging area takes u now
+        stage(upk);
+        flush(P.u, wrow0, col0);                                       // pre-activation tile
+        uint32_t keep = 0xffffffffu;
+        const uint64_t ctr0 = off + (uint64_t)((row * P.N + col0) >> 3);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                                  // 8 columns per step
+          float a[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { a[2 * e] = bf_lo(upk[4 * q + e]); a[2 * e + 1] = bf_hi(upk[4 * q + e]); }
+          Gelu<false>::fwd8(a, scale);                                 // GELU of the stored value, dropout scale folded in
+          if (P.p > 0.f) {
+            const uint32_t bits = keep_bits8(P.seed, ctr0 + q, th);    // same counters as gvit_gelu_dropout_fwd
+#pragma unroll
+            for (int t = 0; t < 8; ++t) a[t] = (bits >> t) & 1u ? a[t] : 0.f;
+            keep = (keep & ~(0xffu << (8 * q))) | (bits << (8 * q));
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) upk[4 * q + e] = pack2(a[2 * e], a[2 * e + 1]);
+        }
+        stage(upk);
+        flush(P.out, wrow0, col0);                                     // activation tile
+        if (P.p > 0.f && row < P.M) *reinterpret_cast<uint32_t*>(P.mask + ((row * P.N + col0) >> 3)) = keep;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                      // no CTA leaves while its peer may still multicast into it
+  if (warp == EPI_WARPS + 1) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+bool fc1_tc_supported(int64_t M, int N, int K) { return M >= 1 && N >= BN && N % BN == 0 && K >= BK && K % BK == 0; }
+
+int fc1_gelu_dropout_fwd_tc(const void* x, const void* w, const void* bias, int64_t M, int N, int K, float p, uint64_t seed,
+                            uint64_t offset, const uint64_t* offset_dev, void* u, void* out, uint8_t* mask, cudaStream_t st) {
+  CUtensorMap tm_x, tm_w;
+  int rc = make_tmap_bf16_3d(&tm_x, x, (uint64_t)K, (uint64_t)M, 1, (uint64_t)K, (uint64_t)M * K, BM);
+  if (rc != GVIT_OK) return rc;
+  rc = make_tmap_bf16_3d(&tm_w, w, (uint64_t)K, (uint64_t)N, 1, (uint64_t)K, (uint64_t)N * K, BN / 2);   // one CTA's half tile
+  if (rc != GVIT_OK) return rc;
+  Params P{M, N, K, p, seed, offset, offset_dev, static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(u),
+           static_cast<__nv_bfloat16*>(out), mask};
+  GVIT_CHECK_CUDA(cudaFuncSetAttribute(fc1_gelu_dropout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  const int64_t npairs = (((M + BM - 1) / BM + 1) / 2) * (N / BN);
+  const int64_t want = 2 * npairs, cap = num_sms() & ~1;
+  const int grid = (int)(want < cap ? want : cap);                  // whole clusters of two CTAs
+  fc1_gelu_dropout_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tm_x, tm_w, P);
+  GVIT_CHECK_LAUNCH();
+  return GVIT_OK;
+}
+
+}  // namespace gvit

@@ -32,7 +32,7 @@ _KERNELS_PER_CALL = {
     "gvit_knn_fwd": 1, "gvit_graph_reverse": 1, "gvit_knn_bwd": 1, "gvit_agg_gather_fwd": 1, "gvit_agg_fwd": 1,
     "gvit_agg_bwd": 2, "gvit_graph_bwd": 2, "gvit_attn_fwd": 1, "gvit_attn_bwd": 1, "gvit_layernorm_fwd": 1, "gvit_layernorm_bwd": 2,
     "gvit_colsum": 2, "gvit_dropout_residual_fwd": 1, "gvit_dropout_bwd": 1, "gvit_gelu_dropout_fwd": 1, "gvit_gelu_dropout_bwd": 1,
-    "gvit_patchify": 1, "gvit_embed_assemble": 1,
+    "gvit_patchify": 1, "gvit_embed_assemble": 1, "gvit_linear_gelu_dropout_fwd": 1,
 }
 
 
@@ -512,11 +512,21 @@ class _LinearGeluDropout(torch.autograd.Function):
         ctx.bias_dtype = bias.dtype if bias is not None else None
         ctx.w_dtype = weight.dtype
         weight = _shadow(weight, x.dtype)
-        u = F.linear(x, weight, _shadow(bias, x.dtype))
-        n = u.numel()
-        out = torch.empty_like(u)
-        mask = torch.empty(n // 8, dtype=torch.uint8, device=u.device) if p > 0 else None
-        _call("gvit_gelu_dropout_fwd", _ptr(u), n, float(p), int(seed), 0, _rng_offset_ptr(), _dtype_code(u), _ptr(out), _ptr(mask), _stream())
+        N, K = weight.shape
+        if x.dtype == torch.bfloat16 and fused_fc1_available(N, K) and x.is_contiguous():
+            # one persistent tcgen05 GEMM: bias + GELU + dropout + both stores run in its epilogue warps
+            M = x.numel() // K
+            u = torch.empty(x.shape[:-1] + (N,), dtype=x.dtype, device=x.device)
+            out = torch.empty_like(u)
+            mask = torch.empty(M * N // 8, dtype=torch.uint8, device=x.device) if p > 0 else None
+            _call("gvit_linear_gelu_dropout_fwd", _ptr(x), _ptr(weight), _ptr(_shadow(bias, x.dtype)), M, N, K, float(p),
+                  int(seed), 0, _rng_offset_ptr(), GVIT_BF16, _ptr(u), _ptr(out), _ptr(mask), _stream())
+        else:
+            u = F.linear(x, weight, _shadow(bias, x.dtype))
+            n = u.numel()
+            out = torch.empty_like(u)
+            mask = torch.empty(n // 8, dtype=torch.uint8, device=u.device) if p > 0 else None
+            _call("gvit_gelu_dropout_fwd", _ptr(u), n, float(p), int(seed), 0, _rng_offset_ptr(), _dtype_code(u), _ptr(out), _ptr(mask), _stream())
         ctx.save_for_backward(x, weight, u, mask)
         ctx.p, ctx.has_bias = p, bias is not None
         return out
@@ -688,6 +698,13 @@ def agg_gather(h: torch.Tensor, idx: torch.Tensor, vals: torch.Tensor):
     _call("gvit_agg_gather_fwd", _ptr(h, off), bs, rs, B, Np, D, k, _dtype_code(h), _ptr(idx), _ptr(vals), _ptr(w),
           _ptr(z), _stream())
     return w, z
+
+
+_FC1_ENABLED = {"on": True}
+
+
+def fused_fc1_available(N: int, K: int) -> bool:
+    return _FC1_ENABLED["on"] and _lib.describe_path("fc1", GVIT_BF16, N, K).startswith("fc1:tcgen05")
 
 
 def fused_agg_available(dtype: torch.dtype, Np: int, D: int, k: int) -> bool:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GVIT_ABI_VERSION 8
+#define GVIT_ABI_VERSION 9
 #if defined(__GNUC__)
 #define GVIT_API __attribute__((visibility("default")))
 #else
@@ -165,6 +165,16 @@ GVIT_API int gvit_gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t s
 /* colsum_out / partial_ws / D as for gvit_dropout_bwd: the bias gradient of fc1 (vit.py:90) in the same pass. */
 GVIT_API int gvit_gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, int64_t n, float p, int dtype,
                           void* du, int D, float* colsum_out, float* partial_ws, void* stream);
+
+/* ---- f1: fc1 of the Mlp with its epilogue fused (vit.py:90-92): u = x W^T + bias (saved pre-activation), out =
+ * dropout(gelu(u), p) with the keep-mask convention above - ONE persistent tcgen05 GEMM whose epilogue warps do
+ * bias + GELU + Philox + both stores under the tensor pipe's shadow (accumulators double-buffered in TMEM).
+ * x (M,K) and w (N,K) row-major bf16 (w is nn.Linear's weight), bias (N) bf16 or NULL, u / out (M,N) bf16,
+ * keep_mask M*N/8 bytes (8-byte aligned; NULL when p == 0).  bf16 only, N % 256 == 0, K % 64 == 0: other shapes return
+ * GVIT_ERR_UNSUPPORTED (compose a library GEMM with gvit_gelu_dropout_fwd); gvit_describe_path("fc1", dtype, N, K) tells. */
+GVIT_API int gvit_linear_gelu_dropout_fwd(const void* x, const void* w, const void* bias, int64_t M, int N, int K, float p, uint64_t seed,
+                                 uint64_t offset, const uint64_t* offset_dev, int dtype, void* u, void* out, uint8_t* keep_mask,
+                                 void* stream);
 
 /* ---- f4: token prologue, replaces PatchEmbed (/root/reference/src/models/vit.py:25-36) and the CLS / pos_embed /
  * pos_drop lines vit.py:207-212.  A kernel == stride convolution is a GEMM over non-overlapping patches:

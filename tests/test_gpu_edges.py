@@ -230,3 +230,46 @@ def test_parameter_shadows_follow_the_master():
     y.sum().backward()
     assert w.grad.dtype == torch.float32
     assert rel_err(w.grad, (torch.ones(8, 64, device=DEV).t() @ x.float())) < 1e-6          # fp32 accumulator written out unrounded
+
+
+@pytest.mark.parametrize("M,N,K", [(4 * 197, 3072, 768), (130, 256, 64), (1, 512, 128), (50432, 3072, 768)])
+def test_fused_fc1_gemm_epilogue(M, N, K):
+    """f1 - fc1 + bias + GELU + dropout as ONE tcgen05 GEMM (gvit_linear_gelu_dropout_fwd) against a float64 GEMM of the
+    same bf16 operands; the saved pre-activation, the keep mask and the backward through it."""
+    assert ops.fused_fc1_available(N, K)
+    g = torch.Generator(device=DEV).manual_seed(M + N)
+    x = torch.randn(M, K, generator=g, device=DEV).bfloat16()
+    w = (torch.randn(N, K, generator=g, device=DEV) * K ** -0.5).bfloat16()
+    b = torch.randn(N, generator=g, device=DEV).bfloat16()
+    rows = torch.randperm(M, generator=torch.Generator().manual_seed(1))[:256].to(DEV)        # sample rows for the fp64 check
+    u_ref = (x[rows].double() @ w.double().t() + b.double()).bfloat16()
+    want = torch.nn.functional.gelu(u_ref.double())
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    out = ops.linear_gelu_dropout(xr, wr, br, 0.0, True)
+    assert out.shape == (M, N) and out.dtype == torch.bfloat16
+    # u is rounded to bf16 before the GELU (as the unfused path stores it): one bf16 ulp of u may flip
+    assert rel_err(out[rows], want) < TOL_BF16
+    assert float((out[rows].detach().double() - want).abs().mean() / want.abs().mean()) < 2e-3
+    torch.manual_seed(7)
+    outp = ops.linear_gelu_dropout(xr, wr, br, 0.25, True)
+    kept = outp != 0
+    dead = out == 0                                             # exact zeros of the GELU itself (u = -0 ... underflow)
+    assert abs(float(kept[~dead].float().mean()) - 0.75) < max(5e-3, 4.0 * (0.1875 / max(1, int((~dead).sum()))) ** 0.5)
+    assert rel_err(outp[kept].float(), (out.float() / 0.75)[kept]) < 1e-2
+    torch.manual_seed(7)
+    assert torch.equal(ops.linear_gelu_dropout(xr, wr, br, 0.25, True), outp)                # reproducible
+    if M <= 1024:
+        cot = torch.randn(M, N, generator=g, device=DEV).bfloat16()
+        outp.backward(cot)
+        ops._FC1_ENABLED["on"] = False                          # the unfused composition with the same seed
+        try:
+            x2, w2, b2 = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+            torch.manual_seed(7)
+            ref = ops.linear_gelu_dropout(x2, w2, b2, 0.25, True)
+            ref.backward(cot)
+        finally:
+            ops._FC1_ENABLED["on"] = True
+        assert (ref != 0).eq(kept).all()                        # same Philox counters -> same keep mask
+        assert rel_err(outp, ref) < TOL_BF16
+        for a, r in ((xr.grad, x2.grad), (wr.grad, w2.grad), (br.grad, b2.grad)):
+            assert rel_err(a, r) < TOL_BF16

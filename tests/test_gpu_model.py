@@ -220,3 +220,34 @@ def test_captured_step_draws_fresh_dropout_masks_on_every_replay():
         assert abs(float((masks[0] & masks[1]).float().mean()) - 0.25) < 1e-2      # independent across replays
     finally:
         ops.set_rng_offset_tensor(None)
+
+
+@pytest.mark.parametrize("k,every", [(4, 1), (16, 1), (8, 4)])
+def test_config5_inference_sweep_point_vs_oracle(k, every):
+    """BASELINE config 5 (inference: eval, no_grad, bf16, k in {4,8,16}, graph layers in every block vs every 4th) at
+    ViT-B/16 width with 4 blocks: against the CPU oracle, and batch-size independence of the result."""
+    cfg = dict(img_size=224, patch_size=16, embed_dim=768, depth=4, num_heads=12, graph_mode="knn", graph_k=k, graph_every=every)
+    o, m = _pair(cfg, seed=k + every)
+    img = torch.randn(3, 3, 224, 224, generator=torch.Generator().manual_seed(k))
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        got = m(img.to(DEV))
+        assert rel_err(got, o(img)) < 5e-2                 # whole-network bf16 drift (incl. near-tie neighbour swaps)
+        big = torch.randn(64, 3, 224, 224, generator=torch.Generator(device=DEV).manual_seed(1), device=DEV)
+        whole, parts = m(big), torch.cat([m(big[:32]), m(big[32:])])
+    assert torch.equal(whole, parts)                       # images are independent: no batch-size dependent kernel path
+    assert sum(hasattr(b, "graph") for b in m.blocks) == (4 if every == 1 else 1)
+
+
+def test_config4_vit_l_384_dense_shapes_run():
+    """BASELINE config 4 shapes (ViT-L/16 @ 384: 576 patch tokens, D = 1024, H = 16, dense adjacency), 2 blocks: the
+    577-token attention runs on the tcgen05 forward, LayerNorm at D = 1024, finite gradients for every parameter."""
+    cfg = dict(img_size=384, patch_size=16, embed_dim=1024, depth=2, num_heads=16, graph_mode="dense")
+    o, m = _pair(cfg, seed=9)
+    m.train()
+    img = torch.randn(2, 3, 384, 384, generator=torch.Generator().manual_seed(4))
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = m(img.to(DEV))
+    assert rel_err(logits, o(img)) < 5e-2
+    logits.float().square().mean().backward()
+    for n, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
