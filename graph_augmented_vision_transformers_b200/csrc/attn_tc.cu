@@ -19,6 +19,7 @@
 // Warp roles: 0-3 softmax / epilogue, 4 TMA producer, 5 MMA issuer (+ TMEM allocation).
 #include <float.h>
 
+#include "gelu.cuh"
 #include "kernels.cuh"
 #include "tc.cuh"
 
@@ -517,7 +518,7 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&a)
 }
 
 // P^T = exp2(S^T c - lse), dS^T = P^T (dP^T - delta) for W (16 or 32) consecutive queries of this thread's key row,
-// written as bf16 into the two staging tiles.  No masks: lse2 is +inf for padded queries (p = 0 exactly), and padded
+// written as bf16 into the two staging tiles.  No masks: the (negated) lse2 is -inf for padded queries (p = 0 exactly), and padded
 // KEY rows only feed accumulator rows that are never stored (dV, dK) or multiply zero-filled K rows (dQ).  The
 // softmax scale is applied to dK / dQ when they are stored.
 template <int W>
@@ -525,23 +526,22 @@ __device__ __forceinline__ void bwd_chunk(float (&s)[W], float (&dp)[W], const f
                                           float sl2, uint32_t tP, uint32_t tdS, uint8_t* dst_tile, int row, int c0) {
   // written in phases over the whole chunk (all exponent arguments, then all MUFU.EX2, then dS) so that W
   // independent transcendental ops are in flight: with two warps per scheduler the loop is latency-, not rate-bound
+  // lse2[] and delta[] hold the NEGATED values (the helper warps write them that way), so both affine steps are one packed
+  // fp32x2 instruction per two queries (FFMA2 / FADD2 / FMUL2): the loop is issue-bound, and these are a third of it
+  const f32x2 sl22 = pk2(sl2, sl2);
 #pragma unroll
   for (int q4 = 0; q4 < W; q4 += 4) {
-    const float4 l = *reinterpret_cast<const float4*>(lse2 + q4);
-    s[q4 + 0] = fmaf(s[q4 + 0], sl2, -l.x);
-    s[q4 + 1] = fmaf(s[q4 + 1], sl2, -l.y);
-    s[q4 + 2] = fmaf(s[q4 + 2], sl2, -l.z);
-    s[q4 + 3] = fmaf(s[q4 + 3], sl2, -l.w);
+    const ulonglong2 l = *reinterpret_cast<const ulonglong2*>(lse2 + q4);
+    up2(fma2(pk2(s[q4 + 0], s[q4 + 1]), sl22, f32x2{l.x}), s[q4 + 0], s[q4 + 1]);
+    up2(fma2(pk2(s[q4 + 2], s[q4 + 3]), sl22, f32x2{l.y}), s[q4 + 2], s[q4 + 3]);
   }
 #pragma unroll
   for (int e = 0; e < W; ++e) s[e] = (e & 3) == 3 ? ex2_emul(s[e]) : ex2(s[e]);   // balance the MUFU and FMA pipes
 #pragma unroll
   for (int q4 = 0; q4 < W; q4 += 4) {
-    const float4 d = *reinterpret_cast<const float4*>(delta + q4);
-    dp[q4 + 0] = s[q4 + 0] * (dp[q4 + 0] - d.x);
-    dp[q4 + 1] = s[q4 + 1] * (dp[q4 + 1] - d.y);
-    dp[q4 + 2] = s[q4 + 2] * (dp[q4 + 2] - d.z);
-    dp[q4 + 3] = s[q4 + 3] * (dp[q4 + 3] - d.w);
+    const ulonglong2 d = *reinterpret_cast<const ulonglong2*>(delta + q4);
+    up2(mul2(pk2(s[q4 + 0], s[q4 + 1]), add2(pk2(dp[q4 + 0], dp[q4 + 1]), f32x2{d.x})), dp[q4 + 0], dp[q4 + 1]);
+    up2(mul2(pk2(s[q4 + 2], s[q4 + 3]), add2(pk2(dp[q4 + 2], dp[q4 + 3]), f32x2{d.y})), dp[q4 + 2], dp[q4 + 3]);
   }
   uint32_t pk[W / 2], dk[W / 2];
 #pragma unroll
@@ -775,14 +775,14 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
           d += __shfl_xor_sync(0xffffffffu, d, 1);
           d += __shfl_xor_sync(0xffffffffu, d, 2);
           d += __shfl_xor_sync(0xffffffffu, d, 4);
-          if (ch == 0) ctl->delta[par][hw * 128 + rb * 32 + i * 4 + sub] = d;
+          if (ch == 0) ctl->delta[par][hw * 128 + rb * 32 + i * 4 + sub] = -d;     // negated: see bwd_chunk
         }
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int q = hw * 128 + j * 32 + lane;
-        // +inf for padded queries: exp2(x - inf) = 0 masks them without a select
-        ctl->lse2[par][q] = q < N ? lse[((int64_t)b * H + h) * N + q] * LOG2E : __int_as_float(0x7f800000);
+        // negated (see bwd_chunk); -inf for padded queries: exp2(x - inf) = 0 masks them without a select
+        ctl->lse2[par][q] = q < N ? -lse[((int64_t)b * H + h) * N + q] * LOG2E : __int_as_float(0xff800000);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->delta_ready[par]);
