@@ -242,7 +242,7 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
         for i, (a, b) in enumerate(evs):
             a.record(); fn(i); b.record()
         torch.cuda.synchronize()
-        ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+        ms = statistics.median(a.elapsed_time(b) for a, b in evs)
         gbs, tfs = nbytes / ms / 1e6, flops / ms / 1e9
         if bound == "hbm":
             ach, peak, unit = gbs, peaks["hbm"], "GB/s"
