@@ -55,7 +55,8 @@ struct Params {
   __nv_bfloat16* u;
   __nv_bfloat16* out;
   uint8_t* mask;
-};
+  uint32_t rk[2 * GVIT_PHILOX_ROUNDS];        // Philox round keys, precomputed on the host: constant-bank operands, no
+};                                            // per-call key schedule in the epilogue
 
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
@@ -143,6 +144,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) fc1_gelu
     const int ch4 = lane & 3, r4 = lane >> 2;                          // coalesced pattern: 4 lanes per 64-byte row segment
     const float scale = P.p > 0.f ? 1.0f / (1.0f - P.p) : 1.0f;
     const uint32_t th = dropout_thresh16(P.p);
+    // Philox-4x32 with the host-made round keys
+    auto philox = [&](uint32_t c0, uint32_t c1) -> uint4 {
+      uint4 ctr = make_uint4(c0, c1, 0u, 0u);
+#pragma unroll
+      for (int r = 0; r < GVIT_PHILOX_ROUNDS; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ P.rk[2 * r], lo1, hi0 ^ ctr.w ^ P.rk[2 * r + 1], lo0);
+      }
+      return ctr;
+    };
     const uint64_t off = P.offset + (P.offset_dev ? __ldg(P.offset_dev) : 0ull);
     // staging tile [32 rows][64 B]: 16-byte chunk q of row r lives at chunk q ^ ((r >> 1) & 3) - conflict-free for the
     // row-per-lane writes and for the 4-lanes-per-row reads
@@ -195,27 +207,51 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) fc1_gelu
         uint32_t upk[16];                                              // u as stored: 32 bf16
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
-          const float4 bq = *reinterpret_cast<const float4*>(sbias + q4 * 4);
-          upk[2 * q4] = pack2(v[4 * q4] + bq.x, v[4 * q4 + 1] + bq.y);
-          upk[2 * q4 + 1] = pack2(v[4 * q4 + 2] + bq.z, v[4 * q4 + 3] + bq.w);
+          const ulonglong2 bq = *reinterpret_cast<const ulonglong2*>(sbias + q4 * 4);    // two packed fp32 pairs
+          float x0, x1, x2, x3;
+          up2(add2(pk2(v[4 * q4], v[4 * q4 + 1]), f32x2{bq.x}), x0, x1);
+          up2(add2(pk2(v[4 * q4 + 2], v[4 * q4 + 3]), f32x2{bq.y}), x2, x3);
+          upk[2 * q4] = pack2(x0, x1);
+          upk[2 * q4 + 1] = pack2(x2, x3);
         }
         __syncwarp();                                                  // bias reads done: the staging area takes u now
         stage(upk);
         flush(P.u, wrow0, col0);                                       // pre-activation tile
+        // Keep decisions for these 32 columns, BIT-SLICED: 16 Philox words w[15..0], bit j of w[i] = bit i of element j's
+        // 16-bit uniform number r_j; keep_j = (r_j >= th) comes out of a serial comparator over the 16 bit planes (1-2
+        // LOP3 per plane for all 32 elements at once) instead of 32 extract / compare / select / merge sequences, and the
+        // result IS the keep-mask word of these columns.  (Same distribution, different bit assignment than
+        // gvit_gelu_dropout_fwd: the two paths draw different - equally valid - masks from the same seed.)
         uint32_t keep = 0xffffffffu;
-        const uint64_t ctr0 = off + (uint64_t)((row * P.N + col0) >> 3);
+        if (P.p > 0.f) {
+          const uint64_t ctr0 = off + (uint64_t)((row * P.N + col0) >> 3);           // 4 consecutive counters per 32 columns
+          uint32_t gt = 0u, eq = 0xffffffffu;
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const uint64_t ctr = ctr0 + c4;
+            const uint4 r = philox((uint32_t)ctr, (uint32_t)(ctr >> 32));
+            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int plane = 15 - (4 * c4 + i);                     // most significant plane first
+              if ((th >> plane) & 1u) {                                // warp-uniform (th is a kernel argument)
+                eq &= w[i];                                            // r bit 0 under a th bit 1: r < th, leaves eq
+              } else {
+                gt |= eq & w[i];                                       // r bit 1 over a th bit 0: r > th
+                eq &= ~w[i];
+              }
+            }
+          }
+          keep = gt | eq;                                              // r >= th
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {                                  // 8 columns per step
           float a[8];
 #pragma unroll
           for (int e = 0; e < 4; ++e) { a[2 * e] = bf_lo(upk[4 * q + e]); a[2 * e + 1] = bf_hi(upk[4 * q + e]); }
           Gelu<false>::fwd8(a, scale);                                 // GELU of the stored value, dropout scale folded in
-          if (P.p > 0.f) {
-            const uint32_t bits = keep_bits8(P.seed, ctr0 + q, th);    // same counters as gvit_gelu_dropout_fwd
 #pragma unroll
-            for (int t = 0; t < 8; ++t) a[t] = (bits >> t) & 1u ? a[t] : 0.f;
-            keep = (keep & ~(0xffu << (8 * q))) | (bits << (8 * q));
-          }
+          for (int t = 0; t < 8; ++t) a[t] = (keep >> (8 * q + t)) & 1u ? a[t] : 0.f;
 #pragma unroll
           for (int e = 0; e < 4; ++e) upk[4 * q + e] = pack2(a[2 * e], a[2 * e + 1]);
         }
@@ -243,7 +279,11 @@ int fc1_gelu_dropout_fwd_tc(const void* x, const void* w, const void* bias, int6
   rc = make_tmap_bf16_3d(&tm_w, w, (uint64_t)K, (uint64_t)N, 1, (uint64_t)K, (uint64_t)N * K, BN / 2);   // one CTA's half tile
   if (rc != GVIT_OK) return rc;
   Params P{M, N, K, p, seed, offset, offset_dev, static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(u),
-           static_cast<__nv_bfloat16*>(out), mask};
+           static_cast<__nv_bfloat16*>(out), mask, {}};
+  for (int r = 0; r < GVIT_PHILOX_ROUNDS; ++r) {
+    P.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+    P.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+  }
   GVIT_CHECK_CUDA(cudaFuncSetAttribute(fc1_gelu_dropout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   const int64_t npairs = (((M + BM - 1) / BM + 1) / 2) * (N / BN);
   const int64_t want = 2 * npairs, cap = num_sms() & ~1;
