@@ -218,14 +218,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) fc1_gelu
         stage(upk);
         flush(P.u, wrow0, col0);                                       // pre-activation tile
         // Keep decisions for these 32 columns, BIT-SLICED: 16 Philox words w[15..0], bit j of w[i] = bit i of element j's
-        // 16-bit uniform number r_j; keep_j = (r_j >= th) comes out of a serial comparator over the 16 bit planes (1-2
+        // 16-bit uniform number r_j; keep_j = (r_j >= th) comes out of a serial comparator over the 16 bit planes (one
         // LOP3 per plane for all 32 elements at once) instead of 32 extract / compare / select / merge sequences, and the
         // result IS the keep-mask word of these columns.  (Same distribution, different bit assignment than
         // gvit_gelu_dropout_fwd: the two paths draw different - equally valid - masks from the same seed.)
         uint32_t keep = 0xffffffffu;
         if (P.p > 0.f) {
           const uint64_t ctr0 = off + (uint64_t)((row * P.N + col0) >> 3);           // 4 consecutive counters per 32 columns
-          uint32_t gt = 0u, eq = 0xffffffffu;
+          // borrow chain of r - th, least significant plane first: b' = t ? (~r | b) : (~r & b), which is ONE three-input
+          // LOP3 per plane on (r, b, T) with T = the th bit spread to all 32 bits (uniform, hoisted): no borrow out = keep
+          uint32_t bor = 0u;
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
             const uint64_t ctr = ctr0 + c4;
@@ -233,16 +235,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) fc1_gelu
             const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int plane = 15 - (4 * c4 + i);                     // most significant plane first
-              if ((th >> plane) & 1u) {                                // warp-uniform (th is a kernel argument)
-                eq &= w[i];                                            // r bit 0 under a th bit 1: r < th, leaves eq
-              } else {
-                gt |= eq & w[i];                                       // r bit 1 over a th bit 0: r > th
-                eq &= ~w[i];
-              }
+              const uint32_t T = 0u - ((th >> (4 * c4 + i)) & 1u);
+              bor = (~w[i] & bor) | (T & (~w[i] | bor));
             }
           }
-          keep = gt | eq;                                              // r >= th
+          keep = ~bor;                                                 // r >= th
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {                                  // 8 columns per step
