@@ -458,11 +458,6 @@ inline void colsum_grid(int64_t rows, int D, int per_sm, int* colblocks, int* nc
   *nchunks = (int)((rows + *rpc - 1) / *rpc);
 }
 
-inline int stream_grid(int64_t n8) {
-  const int64_t blocks = (n8 + 255) / 256;
-  const int64_t cap = (int64_t)num_sms() * 8;
-  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
-}
 
 
 template <typename Tx, typename Ty, int NC>

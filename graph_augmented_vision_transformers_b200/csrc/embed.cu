@@ -85,10 +85,6 @@ __global__ void __launch_bounds__(256) embed_assemble_kernel(const T* __restrict
   }
 }
 
-inline int grid_for(int64_t items) {
-  const int64_t blocks = (items + 255) / 256, cap = (int64_t)num_sms() * 8;
-  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
-}
 
 }  // namespace
 
