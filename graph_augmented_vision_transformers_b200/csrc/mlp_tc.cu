@@ -17,9 +17,9 @@
 // tiles (96 B/clk/SM at full tensor rate, ~43 B/clk/SM available chip-wide) is its bound - and the epilogue is ~30
 // instructions per element, so SIXTEEN epilogue warps (4 per scheduler) are needed to keep it off the critical path:
 // with eight, the kernel ran at the speed of GEMM + separate elementwise pass.
-// Clusters of two CTAs work on the two row blocks (2i, 2i+1) of the same column tile: each CTA fetches HALF of the W tile
-// and TMA-multicasts it to both, so the L2 -> SM traffic per tile drops from 48 to 32 KB per stage (a ring slot is
-// refilled once BOTH CTAs have released it: the MMA warps commit to the empty barrier of both CTAs).
+// Clusters of CL = 2 CTAs work on consecutive row blocks of the same column tile: each CTA fetches 1/CL of the W tile
+// and TMA-multicasts it to the whole cluster, so the L2 -> SM traffic drops from 48 to 32 KB per stage (a ring slot is
+// refilled once EVERY CTA has released it: the MMA warps commit to the empty barrier of all CTAs of the cluster).
 // Warp roles: 0-15 epilogue (warpgroup g = warp / 4 owns accumulator columns [64g, 64g + 64), thread <-> row = TMEM lane),
 // 16 TMA producer, 17 MMA issuer.
 #include "gelu.cuh"
@@ -35,6 +35,10 @@ using namespace tc;
 constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+// CTAs per cluster: CL row blocks share one W tile (each fetches 1/CL of it).  Measured: 2 -> 275 us; 4 -> 490 us, because
+// only ~34 four-CTA clusters are co-resident on the 148 SMs (GPC granularity), so a 37-cluster persistent grid ran in two
+// waves.  The grid is sized from cudaOccupancyMaxActiveClusters for that reason.
+constexpr int CL = 2;
 constexpr int EPI_WARPS = 16;
 constexpr int WSTAGE = 2 * 1024;            // per-warp staging ([32 rows][64 B]) for coalesced global stores
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
@@ -65,7 +69,7 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) fc1_gelu_dropout_tc_kernel(const __grid_constant__ CUtensorMap tm_x,
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gelu_dropout_tc_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                          const __grid_constant__ CUtensorMap tm_w,
                                                                          const Params P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -76,15 +80,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) fc1_gelu
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int nM = (int)((P.M + BM - 1) / BM), nN = P.N / BN, nK = P.K / BK;
-  const int rank = (int)cluster_ctarank();                 // 0 / 1: which row block of the pair, which half of W to fetch
-  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
-  const int npairs = ((nM + 1) >> 1) * nN;                 // (row-block pair, column tile); an odd last row block pairs with
-                                                           // an empty one (TMA zero-fills, the stores are row-guarded)
+  const int rank = (int)cluster_ctarank();                 // which row block of the group, which slice of W to fetch
+  const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
+  const int npairs = ((nM + CL - 1) / CL) * nN;            // (group of CL row blocks, column tile); row blocks past the end
+                                                           // are empty (TMA zero-fills, the stores are row-guarded)
 
   if (warp == EPI_WARPS && lane == 0) {
     prefetch_tmap(&tm_x);
     prefetch_tmap(&tm_w);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 2); }   // empty: both CTAs' MMA warps
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], CL); }   // empty: every CTA's MMA warp
     for (int s = 0; s < 2; ++s) { mbar_init(&ctl->acc_full[s], 1); mbar_init(&ctl->acc_free[s], EPI_WARPS * 32); }
     fence_mbar_init();
   }
@@ -100,14 +104,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) fc1_gelu
     if (elect_one()) {
       int it = 0;
       for (int pr = cid; pr < npairs; pr += ncl) {
-        const int mp = pr / nN, n = pr - mp * nN, m = 2 * mp + rank;
+        const int mp = pr / nN, n = pr - mp * nN, m = CL * mp + rank;
         for (int kb = 0; kb < nK; ++kb, ++it) {
           const int s = it % STAGES;
-          mbar_wait(&ctl->empty[s], ((it / STAGES) & 1) ^ 1);            // released by BOTH CTAs of the cluster
-          mbar_expect_tx(&ctl->full[s], (uint32_t)STAGE_BYTES);          // own x tile + own W half + the peer's W half
+          mbar_wait(&ctl->empty[s], ((it / STAGES) & 1) ^ 1);            // released by EVERY CTA of the cluster
+          mbar_expect_tx(&ctl->full[s], (uint32_t)STAGE_BYTES);          // own x tile + own W slice + the peers' W slices
           tma_load_3d(ring + (size_t)s * STAGE_BYTES, &tm_x, kb * BK, m * BM, 0, &ctl->full[s]);             // rows >= M: zeros
-          tma_load_3d_mc(ring + (size_t)s * STAGE_BYTES + A_BYTES + rank * (B_BYTES / 2), &tm_w, kb * BK, n * BN + rank * (BN / 2), 0,
-                         &ctl->full[s], (uint16_t)0b11);
+          tma_load_3d_mc(ring + (size_t)s * STAGE_BYTES + A_BYTES + rank * (B_BYTES / CL), &tm_w, kb * BK, n * BN + rank * (BN / CL), 0,
+                         &ctl->full[s], (uint16_t)((1u << CL) - 1));
         }
       }
     }
@@ -131,7 +135,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) fc1_gelu
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             umma_ss(tmem + buf * BN, make_sdesc(aA + kk * 32), make_sdesc(aB + kk * 32), idesc, kb > 0 || kk > 0);
-          umma_commit_mc(&ctl->empty[s], (uint16_t)0b11);             // slot s of BOTH CTAs is written by the next refill
+          umma_commit_mc(&ctl->empty[s], (uint16_t)((1u << CL) - 1));  // slot s of EVERY CTA is written by the next refill
         }
         umma_commit(&ctl->acc_full[buf]);
       }
@@ -178,7 +182,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) fc1_gelu
     };
     int tc = 0;
     for (int pr = cid; pr < npairs; pr += ncl, ++tc) {
-      const int mp = pr / nN, n = pr - mp * nN, m = 2 * mp + rank;
+      const int mp = pr / nN, n = pr - mp * nN, m = CL * mp + rank;
       const int buf = tc & 1;
       const int64_t wrow0 = (int64_t)m * BM + (warp & 3) * 32;         // first row of this warp
       const int64_t row = wrow0 + lane;
@@ -273,7 +277,7 @@ int fc1_gelu_dropout_fwd_tc(const void* x, const void* w, const void* bias, int6
   CUtensorMap tm_x, tm_w;
   int rc = make_tmap_bf16_3d(&tm_x, x, (uint64_t)K, (uint64_t)M, 1, (uint64_t)K, (uint64_t)M * K, BM);
   if (rc != GVIT_OK) return rc;
-  rc = make_tmap_bf16_3d(&tm_w, w, (uint64_t)K, (uint64_t)N, 1, (uint64_t)K, (uint64_t)N * K, BN / 2);   // one CTA's half tile
+  rc = make_tmap_bf16_3d(&tm_w, w, (uint64_t)K, (uint64_t)N, 1, (uint64_t)K, (uint64_t)N * K, BN / CL);   // one CTA's slice of the tile
   if (rc != GVIT_OK) return rc;
   Params P{M, N, K, p, seed, offset, offset_dev, static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(u),
            static_cast<__nv_bfloat16*>(out), mask, {}};
@@ -282,9 +286,25 @@ int fc1_gelu_dropout_fwd_tc(const void* x, const void* w, const void* bias, int6
     P.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
   }
   GVIT_CHECK_CUDA(cudaFuncSetAttribute(fc1_gelu_dropout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  const int64_t npairs = (((M + BM - 1) / BM + 1) / 2) * (N / BN);
-  const int64_t want = 2 * npairs, cap = num_sms() & ~1;
-  const int grid = (int)(want < cap ? want : cap);                  // whole clusters of two CTAs
+  const int64_t ngroups = (((M + BM - 1) / BM + CL - 1) / CL) * (N / BN);
+  int max_clusters = 0;
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((num_sms() / CL) * CL);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = CL; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, fc1_gelu_dropout_tc_kernel, &cfg) != cudaSuccess || max_clusters < 1) {
+      (void)cudaGetLastError();
+      max_clusters = num_sms() / CL;
+    }
+  }
+  const int64_t want = CL * ngroups, cap = (int64_t)CL * max_clusters;
+  const int grid = (int)(want < cap ? want : cap);                  // whole, co-resident clusters: a persistent grid
   fc1_gelu_dropout_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tm_x, tm_w, P);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
