@@ -465,12 +465,16 @@ __global__ void __launch_bounds__(F2_THREADS, 1) attn_fwd_tc2_kernel(const __gri
 // in-place operands are consumed first), so the tensor pipe, the two warpgroups and the epilogue stores overlap
 // instead of taking turns (v1 ran them strictly in sequence: 470 us).
 // TMEM: S^T [0,128) | dP^T [128,256) | dV [256,320) | dK [320,384) | dQ [384,512).
-// Warp roles: 0-3 WG0, 4-7 WG1, 8 TMA producer, 9 MMA issuer (+ TMEM allocation), 10-11 delta / lse helpers.
+// The dV / dK / dQ epilogues (wait for the step's MMAs, TMEM -> bf16 -> staging tile -> TMA store) belong to a warpgroup of
+// their own: on the softmax warpgroups they were a third of every item's critical path (three ~2000-cycle epilogues plus
+// the waits for the accumulators to become final), with the tensor pipe idle behind them.
+// Warp roles: 0-3 WG0, 4-7 WG1, 8 TMA producer, 9 MMA issuer (+ TMEM allocation), 10-11 delta / lse helpers,
+// 12-15 epilogue warpgroup (thread <-> accumulator row = TMEM lane).
 // =================================================================================================
-constexpr int B2_THREADS = 384;   // 8 warpgroup warps + TMA + MMA + 2 helper warps
+constexpr int B2_THREADS = 512;   // 8 softmax warps + TMA + MMA + 2 delta helpers + 4 epilogue warps
 struct __align__(16) BwdCtrl {
   float lse2[2][256], delta[2][256];            // double-buffered by item parity
-  uint64_t kv_full[2], q_full[2], kv_empty[2], q_empty[2], s_full[2], p_full[2], st_free, dvk_free, dq_free, delta_ready[2];
+  uint64_t kv_full[2], q_full[2], kv_empty[2], q_empty[2], s_full[2], p_full[2], st_free, dvk_free, dq_free, delta_ready[2], wg_done;
   uint32_t tmem_base;
 };
 // Q[2], dO[2], K[2], V[2] tiles + output staging (one tile per warpgroup) + dS^T staging (2 sub-tiles)
@@ -604,8 +608,9 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
       mbar_init(&ctl->q_empty[i], 1);
     }
     mbar_init(&ctl->st_free, 1);
-    mbar_init(&ctl->dvk_free, 256);
-    mbar_init(&ctl->dq_free, 256);
+    mbar_init(&ctl->dvk_free, 128);
+    mbar_init(&ctl->dq_free, 128);
+    mbar_init(&ctl->wg_done, 256);
     mbar_init(&ctl->delta_ready[0], 2);
     mbar_init(&ctl->delta_ready[1], 2);
     fence_mbar_init();
@@ -736,6 +741,68 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
         }
       }
     }
+  } else if (warp >= 12) {
+    // ------------------------------------------------------------------ epilogue warpgroup
+    const int t = (warp & 3) * 32 + lane;                 // accumulator row == TMEM lane
+    uint8_t* tile0 = sOut;                                // dV, then dQ tile 0
+    uint8_t* tile1 = sOut + TILE_BYTES;                   // dK, then dQ tile 1
+    bool store_pending = false;                           // thread 0: TMA stores may still be reading the staging tiles
+    // wait until the previous stores have read the staging tiles, let every thread see it
+    auto tiles_reusable = [&]() {
+      if (t == 0 && store_pending) tma_store_wait_read();
+      asm volatile("bar.sync 4, 128;" ::: "memory");
+    };
+    auto tiles_written = [&]() {
+      fence_async_smem();
+      asm volatile("bar.sync 4, 128;" ::: "memory");
+    };
+    int ic = 0;
+    for (int w = blockIdx.x; w < items; w += gridDim.x, ++ic) {
+      const int b = w / H, h = w - b * H;
+      for (int kt = 0; kt < T; ++kt) {
+        // every step's phase is waited in order (a parity wait may only name the current or the preceding phase); the
+        // last one, step (kt, T-1), completes key tile kt
+        for (int qt = 0; qt < T; ++qt) mbar_wait(&ctl->st_free, (ic * T * T + kt * T + qt) & 1);
+        tc_fence_after();
+        GVIT_TR(16);
+        float v0[32], v1[32];
+        tiles_reusable();
+        tmem_ld32x2(tmem_lane_base(tdV, warp), tmem_lane_base(tdV, warp) + 32, v0, v1);
+        stage_out64(tile0, t, v0, v1, 1.0f);
+        tmem_ld32x2(tmem_lane_base(tdK, warp), tmem_lane_base(tdK, warp) + 32, v0, v1);
+        tc_fence_before();
+        mbar_arrive(&ctl->dvk_free);                      // both accumulators are in registers / staged
+        stage_out64(tile1, t, v0, v1, scale);             // dS was formed without the softmax scale
+        tiles_written();
+        if (t == 0) {
+          tma_store_3d(&tm_dqkv, tile0, (2 * H + h) * 64, kt * 128, b);   // dV; rows >= N are clipped
+          tma_store_3d(&tm_dqkv, tile1, (H + h) * 64, kt * 128, b);       // dK
+          tma_store_commit();
+          store_pending = true;
+        }
+      }
+      // dQ (final with the same step as the last key tile)
+      {
+        float v0[32], v1[32];
+        tiles_reusable();
+        tmem_ld32x2(tmem_lane_base(tdQ, warp), tmem_lane_base(tdQ, warp) + 32, v0, v1);
+        stage_out64(tile0, t, v0, v1, scale);
+        if (T > 1) {
+          tmem_ld32x2(tmem_lane_base(tdQ + 64, warp), tmem_lane_base(tdQ + 64, warp) + 32, v0, v1);
+          stage_out64(tile1, t, v0, v1, scale);
+        }
+        tc_fence_before();
+        mbar_arrive(&ctl->dq_free);
+        GVIT_TR(17);
+        tiles_written();
+        if (t == 0) {
+          tma_store_3d(&tm_dqkv, tile0, h * 64, 0, b);
+          if (T > 1) tma_store_3d(&tm_dqkv, tile1, h * 64, 128, b);
+          tma_store_commit();
+          store_pending = true;
+        }
+      }
+    }
   } else if (warp >= 10) {
     // ------------------------------------------------------------------ helper warps: delta / lse ONE ITEM AHEAD
     // delta = rowsum(dO * O) and lse in log2 units for the next item, into the item-parity double buffer, while the
@@ -747,7 +814,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
     for (int w = blockIdx.x; w < items; w += gridDim.x, ++ic) {
       const int b = w / H, h = w - b * H;
       const int par = ic & 1;
-      if (ic >= 2) mbar_wait(&ctl->dq_free, (ic - 2) & 1);  // the warpgroups are done reading this buffer (item ic-2)
+      if (ic >= 2) mbar_wait(&ctl->wg_done, (ic - 2) & 1);  // the warpgroups are done reading this buffer (item ic-2)
       const __nv_bfloat16* obase = out + ((int64_t)b * N * H + h) * 64 + ch * 8;
       const __nv_bfloat16* dbase = dout + ((int64_t)b * N * H + h) * 64 + ch * 8;
       for (int rb = 0; rb < 4; ++rb) {
@@ -788,18 +855,15 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
       if (lane == 0) mbar_arrive(&ctl->delta_ready[par]);
     }
   } else {
-    // ------------------------------------------------------------------ softmax / epilogue warpgroups
+    // ------------------------------------------------------------------ softmax warpgroups
     const int g = warp >> 2;                              // warpgroup == sub-tile == TMEM sub-buffer
     const int t = (warp & 3) * 32 + lane;                 // key row of the tile == TMEM lane
     const int tid = g * 128 + t;                          // 0..255
     const float sl2 = scale * LOG2E;
     const uint32_t lST = tmem_lane_base(tST + g * 64, warp), ldPT = tmem_lane_base(tdPT + g * 64, warp);
-    uint8_t* out_g = sOut + g * TILE_BYTES;
     uint8_t* dst_g = sdST + g * TILE_BYTES;
-    bool store_pending = false;                           // thread 0 of the warpgroup: a TMA store may still read out_g
     int ic = 0, itc = 0;
     for (int w = blockIdx.x; w < items; w += gridDim.x, ++ic) {
-      const int b = w / H, h = w - b * H;
       const int par = ic & 1;
       mbar_wait(&ctl->delta_ready[par], (ic >> 1) & 1);     // delta / lse of this item: written by the helper warps
       GVIT_TR(10);
@@ -836,53 +900,9 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
           tc_fence_before();
           mbar_arrive(&ctl->p_full[g]);
           GVIT_TR(15);
-          if (qt == T - 1) {                              // key tile finished: dV (WG0) / dK (WG1) -> HBM
-            mbar_wait(&ctl->st_free, itc & 1);
-            tc_fence_after();
-            GVIT_TR(16);
-            float v0[32], v1[32];
-            const uint32_t ta = tmem_lane_base(g == 0 ? tdV : tdK, warp);
-            tmem_ld32x2(ta, ta + 32, v0, v1);
-            tc_fence_before();
-            mbar_arrive(&ctl->dvk_free);
-            // bf16 rows -> this warpgroup's output staging tile -> ONE TMA tile store (a 128-byte row per thread made each
-            // STG touch 32 lines: ~4000 cycles per key tile).  The tile is private to the epilogues, so the wait for the
-            // PREVIOUS store to have read it sits here, long after that store was issued, instead of behind the store.
-            if (t == 0 && store_pending) tma_store_wait_read();
-            asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
-            stage_out64(out_g, t, v0, v1, g == 0 ? 1.0f : scale);     // dS was formed without the softmax scale
-            fence_async_smem();
-            asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
-            if (t == 0) {
-              tma_store_3d(&tm_dqkv, out_g, ((g == 0 ? 2 : 1) * H + h) * 64, kt * 128, b);   // rows >= N are clipped
-              tma_store_commit();
-              store_pending = true;
-            }
-          }
         }
       }
-      {  // dQ: warpgroup g stores query tile g (every thread arrives so that the barrier count is fixed)
-        float v0[32], v1[32];
-        if (g < T) {
-          const uint32_t ta = tmem_lane_base(tdQ + g * 64, warp);
-          tmem_ld32x2(ta, ta + 32, v0, v1);
-        }
-        tc_fence_before();
-        mbar_arrive(&ctl->dq_free);
-        GVIT_TR(17);
-        if (g < T) {
-          if (t == 0 && store_pending) tma_store_wait_read();
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
-          stage_out64(out_g, t, v0, v1, scale);
-          fence_async_smem();
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
-          if (t == 0) {
-            tma_store_3d(&tm_dqkv, out_g, h * 64, g * 128, b);
-            tma_store_commit();
-            store_pending = true;
-          }
-        }
-      }
+      mbar_arrive(&ctl->wg_done);                         // lse2 / delta of this item are no longer read
     }
   }
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // outstanding TMA stores of this thread (no-op for most)
