@@ -189,6 +189,7 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
     dgb = torch.empty(2, D, device=dev); ws = torch.empty(2 * 296 * D, device=dev)
     u4 = [torch.randn(B, N, 4 * D, device=dev, dtype=bf, generator=g) for _ in range(2)]
     o4 = torch.empty_like(u4[0]); m4 = torch.empty(B * N * 4 * D // 8, dtype=torch.uint8, device=dev)
+    m1 = torch.empty(B * N * D // 8, dtype=torch.uint8, device=dev)
     cs_out = torch.empty(4 * D, device=dev); cs_ws = torch.empty(1024 * 4 * D, device=dev)
     st = _stream()
     dt = _dtype_code(hs[0])
@@ -219,6 +220,8 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
                           3 * B * N * D * e, 0.0, "hbm", 1),
         "fc1_fused": (lambda i: _call("gvit_linear_gelu_dropout_fwd", _ptr(hs[i % R]), _ptr(W1), _ptr(b1), B * N, 4 * D, D, 0.1, 1234, 0, None, dt, _ptr(u4[i % 2]), _ptr(o4), _ptr(m4), st),
                       B * N * D * e + 4 * D * D * e + 2 * B * N * 4 * D * e + B * N * 4 * D // 8, 2.0 * B * N * D * 4 * D, "tensor", 12),
+        "proj_fused": (lambda i: _call("gvit_linear_dropout_residual_fwd", _ptr(hs[i % R]), _ptr(W), _ptr(bias), _ptr(xs[i % R]), B * N, D, D, 0.1, 1234, 0, None, dt, _ptr(out), _ptr(m1), st),
+                       3 * B * N * D * e + D * D * e + B * N * D // 8, 2.0 * B * N * D * D, "hbm", 12),
         "gelu_dropout_fwd": (lambda i: _call("gvit_gelu_dropout_fwd", _ptr(u4[i % 2]), B * N * 4 * D, 0.1, 1234, 0, None, dt, _ptr(o4), _ptr(m4), st),
                              2 * B * N * 4 * D * e + B * N * 4 * D // 8, 0.0, "hbm", 0),      # folded into fc1_fused for bf16
         "gelu_dropout_bwd": (lambda i: _call("gvit_gelu_dropout_bwd", _ptr(u4[(i + 1) % 2]), _ptr(u4[i % 2]), _ptr(m4), B * N * 4 * D, 0.1, dt, _ptr(o4), 4 * D, _ptr(cs_out), _ptr(cs_ws), st),

@@ -240,6 +240,21 @@ int gvit_linear_gelu_dropout_fwd(const void* x, const void* w, const void* bias,
   return fc1_gelu_dropout_fwd_tc(x, w, bias, M, N, K, p, seed, offset, offset_dev, u, out, keep_mask, static_cast<cudaStream_t>(stream));
 }
 
+int gvit_linear_dropout_residual_fwd(const void* x, const void* w, const void* bias, const void* resid, int64_t M, int N, int K, float p,
+                                     uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, void* out,
+                                     uint8_t* keep_mask, void* stream) {
+  TRY(check_dtype(dtype, "linear_dropout_residual_fwd"));
+  GVIT_REQUIRE(x && w && resid && out, GVIT_ERR_SHAPE, "linear_dropout_residual_fwd: null pointer");
+  GVIT_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || keep_mask), GVIT_ERR_SHAPE, "linear_dropout_residual_fwd: p=%f (keep_mask required when p > 0)", p);
+  GVIT_REQUIRE(dtype == GVIT_BF16 && fc1_tc_supported(M, N, K), GVIT_ERR_UNSUPPORTED,
+               "linear_dropout_residual_fwd: the fused kernel is bf16-only with N %% 256 == 0 and K %% 64 == 0 (M=%lld N=%d K=%d); "
+               "compose a library GEMM with gvit_dropout_residual_fwd instead", (long long)M, N, K);
+  GVIT_REQUIRE(aligned16(x) && aligned16(w) && aligned16(resid) && aligned16(out) && (!bias || aligned16(bias)) &&
+               (!keep_mask || (reinterpret_cast<uintptr_t>(keep_mask) & 3u) == 0), GVIT_ERR_ALIGN,
+               "linear_dropout_residual_fwd: tensors must be 16-byte aligned (keep_mask 4-byte)");
+  return linear_dropout_residual_fwd_tc(x, w, bias, resid, M, N, K, p, seed, offset, offset_dev, out, keep_mask, static_cast<cudaStream_t>(stream));
+}
+
 int gvit_patchify(const void* img, int B, int C, int H, int W, int P, int in_dtype, int out_dtype, void* out, void* stream) {
   TRY(check_dtype(in_dtype, "patchify"));
   TRY(check_dtype(out_dtype, "patchify"));

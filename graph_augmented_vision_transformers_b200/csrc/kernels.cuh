@@ -66,6 +66,9 @@ bool fc1_tc_supported(int64_t M, int N, int K);
 int fc1_gelu_dropout_fwd_tc(const void* x, const void* w, const void* bias, int64_t M, int N, int K, float p, uint64_t seed,
                             uint64_t offset, const uint64_t* offset_dev, void* u, void* out, uint8_t* mask, cudaStream_t st);
 
+int linear_dropout_residual_fwd_tc(const void* x, const void* w, const void* bias, const void* resid, int64_t M, int N, int K, float p,
+                                   uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* out, uint8_t* mask, cudaStream_t st);
+
 // ---- token prologue : embed.cu
 int patchify(const void* img, int B, int C, int H, int W, int P, int in_dtype, int out_dtype, void* out, cudaStream_t st);
 int embed_assemble(const void* y, const void* bias, const void* cls, const void* pos, int B, int N, int D, float p,

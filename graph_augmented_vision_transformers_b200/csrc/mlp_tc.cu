@@ -1,7 +1,12 @@
-// mlp_tc.cu - fc1 of the Mlp with its whole epilogue in one kernel:
+// mlp_tc.cu - Linear layers of the block with their whole epilogue in one kernel:
 //
+//   MODE 0, fc1 of the Mlp:
 //     u   = x W^T + b                         (vit.py:90, nn.Linear)            -> saved for the backward, bf16
 //     out = dropout(gelu(u), p)               (vit.py:91-92, nn.GELU, nn.Dropout) -> bf16 + 1-bit keep mask
+//   MODE 1, attention output projection:
+//     out = resid + dropout(x W^T + b, p)     (vit.py:70-71 proj + proj_drop, residual add of vit.py:117)
+//
+// (The text below describes MODE 0; MODE 1 shares the main loop and swaps the epilogue.)
 //
 // As a library GEMM plus the gvit_gelu_dropout_fwd pass this is 173 us + 163 us at B = 256 (M = 50432, N = 3072,
 // K = 768): the elementwise pass is issue-bound ALU work (GELU + Philox) over 640 MB.  Here that ALU work runs in the
@@ -56,7 +61,7 @@ struct Params {
   uint64_t seed, offset;
   const uint64_t* offset_dev;
   const __nv_bfloat16* bias;
-  __nv_bfloat16* u;
+  __nv_bfloat16* u;                           // MODE 0: pre-activation output.  MODE 1: the RESIDUAL input (read only)
   __nv_bfloat16* out;
   uint8_t* mask;
   uint32_t rk[2 * GVIT_PHILOX_ROUNDS];        // Philox round keys, precomputed on the host: constant-bank operands, no
@@ -69,6 +74,7 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
+template <int MODE>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gelu_dropout_tc_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                          const __grid_constant__ CUtensorMap tm_w,
                                                                          const Params P) {
@@ -218,9 +224,28 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
           upk[2 * q4] = pack2(x0, x1);
           upk[2 * q4 + 1] = pack2(x2, x3);
         }
-        __syncwarp();                                                  // bias reads done: the staging area takes u now
-        stage(upk);
-        flush(P.u, wrow0, col0);                                       // pre-activation tile
+        __syncwarp();                                                  // bias reads done: the staging area is free again
+        uint32_t rres[16];                                             // MODE 1: this row's 32 residual values (bf16 pairs)
+        if constexpr (MODE == 0) {
+          stage(upk);
+          flush(P.u, wrow0, col0);                                     // pre-activation tile
+        } else {
+          // residual tile: coalesced global -> staging (the store pattern in reverse), then every lane reads its row
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = r4 + 8 * i;
+            uint4 v4 = make_uint4(0, 0, 0, 0);
+            if (wrow0 + r < P.M) v4 = *reinterpret_cast<const uint4*>(P.u + (wrow0 + r) * P.N + col0 + ch4 * 8);
+            *reinterpret_cast<uint4*>(stg + r * 64 + ((ch4 ^ ((r >> 1) & 3)) << 4)) = v4;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 v4 = *reinterpret_cast<const uint4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4));
+            rres[4 * q] = v4.x; rres[4 * q + 1] = v4.y; rres[4 * q + 2] = v4.z; rres[4 * q + 3] = v4.w;
+          }
+          __syncwarp();
+        }
         // Keep decisions for these 32 columns, BIT-SLICED: 16 Philox words w[15..0], bit j of w[i] = bit i of element j's
         // 16-bit uniform number r_j; keep_j = (r_j >= th) comes out of a serial comparator over the 16 bit planes (one
         // LOP3 per plane for all 32 elements at once) instead of 32 extract / compare / select / merge sequences, and the
@@ -250,9 +275,18 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
           float a[8];
 #pragma unroll
           for (int e = 0; e < 4; ++e) { a[2 * e] = bf_lo(upk[4 * q + e]); a[2 * e + 1] = bf_hi(upk[4 * q + e]); }
-          Gelu<false>::fwd8(a, scale);                                 // GELU of the stored value, dropout scale folded in
+          if constexpr (MODE == 0) {
+            Gelu<false>::fwd8(a, scale);                               // GELU of the stored value, dropout scale folded in
 #pragma unroll
-          for (int t = 0; t < 8; ++t) a[t] = (keep >> (8 * q + t)) & 1u ? a[t] : 0.f;
+            for (int t = 0; t < 8; ++t) a[t] = (keep >> (8 * q + t)) & 1u ? a[t] : 0.f;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {                              // resid + keep * scale * y (y as a bf16 GEMM would store it)
+              const uint32_t rr = rres[4 * q + e];
+              a[2 * e] = bf_lo(rr) + ((keep >> (8 * q + 2 * e)) & 1u ? a[2 * e] * scale : 0.f);
+              a[2 * e + 1] = bf_hi(rr) + ((keep >> (8 * q + 2 * e + 1)) & 1u ? a[2 * e + 1] * scale : 0.f);
+            }
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) upk[4 * q + e] = pack2(a[2 * e], a[2 * e + 1]);
         }
@@ -272,20 +306,22 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
 
 bool fc1_tc_supported(int64_t M, int N, int K) { return M >= 1 && N >= BN && N % BN == 0 && K >= BK && K % BK == 0; }
 
-int fc1_gelu_dropout_fwd_tc(const void* x, const void* w, const void* bias, int64_t M, int N, int K, float p, uint64_t seed,
-                            uint64_t offset, const uint64_t* offset_dev, void* u, void* out, uint8_t* mask, cudaStream_t st) {
+template <int MODE>
+static int fused_linear_launch(const void* x, const void* w, const void* bias, int64_t M, int N, int K, float p, uint64_t seed,
+                               uint64_t offset, const uint64_t* offset_dev, void* u_or_resid, void* out, uint8_t* mask,
+                               cudaStream_t st) {
   CUtensorMap tm_x, tm_w;
   int rc = make_tmap_bf16_3d(&tm_x, x, (uint64_t)K, (uint64_t)M, 1, (uint64_t)K, (uint64_t)M * K, BM);
   if (rc != GVIT_OK) return rc;
   rc = make_tmap_bf16_3d(&tm_w, w, (uint64_t)K, (uint64_t)N, 1, (uint64_t)K, (uint64_t)N * K, BN / CL);   // one CTA's slice of the tile
   if (rc != GVIT_OK) return rc;
-  Params P{M, N, K, p, seed, offset, offset_dev, static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(u),
+  Params P{M, N, K, p, seed, offset, offset_dev, static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(u_or_resid),
            static_cast<__nv_bfloat16*>(out), mask, {}};
   for (int r = 0; r < GVIT_PHILOX_ROUNDS; ++r) {
     P.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
     P.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
   }
-  GVIT_CHECK_CUDA(cudaFuncSetAttribute(fc1_gelu_dropout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  GVIT_CHECK_CUDA(cudaFuncSetAttribute(fc1_gelu_dropout_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   const int64_t ngroups = (((M + BM - 1) / BM + CL - 1) / CL) * (N / BN);
   int max_clusters = 0;
   {
@@ -298,16 +334,26 @@ int fc1_gelu_dropout_fwd_tc(const void* x, const void* w, const void* bias, int6
     attr.val.clusterDim.x = CL; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, fc1_gelu_dropout_tc_kernel, &cfg) != cudaSuccess || max_clusters < 1) {
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, fc1_gelu_dropout_tc_kernel<MODE>, &cfg) != cudaSuccess || max_clusters < 1) {
       (void)cudaGetLastError();
       max_clusters = num_sms() / CL;
     }
   }
   const int64_t want = CL * ngroups, cap = (int64_t)CL * max_clusters;
   const int grid = (int)(want < cap ? want : cap);                  // whole, co-resident clusters: a persistent grid
-  fc1_gelu_dropout_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tm_x, tm_w, P);
+  fc1_gelu_dropout_tc_kernel<MODE><<<grid, THREADS, SMEM_BYTES, st>>>(tm_x, tm_w, P);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
+}
+
+int fc1_gelu_dropout_fwd_tc(const void* x, const void* w, const void* bias, int64_t M, int N, int K, float p, uint64_t seed,
+                            uint64_t offset, const uint64_t* offset_dev, void* u, void* out, uint8_t* mask, cudaStream_t st) {
+  return fused_linear_launch<0>(x, w, bias, M, N, K, p, seed, offset, offset_dev, u, out, mask, st);
+}
+
+int linear_dropout_residual_fwd_tc(const void* x, const void* w, const void* bias, const void* resid, int64_t M, int N, int K, float p,
+                                   uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* out, uint8_t* mask, cudaStream_t st) {
+  return fused_linear_launch<1>(x, w, bias, M, N, K, p, seed, offset, offset_dev, const_cast<void*>(resid), out, mask, st);
 }
 
 }  // namespace gvit

@@ -32,7 +32,7 @@ _KERNELS_PER_CALL = {
     "gvit_knn_fwd": 1, "gvit_graph_reverse": 1, "gvit_knn_bwd": 1, "gvit_agg_gather_fwd": 1, "gvit_agg_fwd": 1,
     "gvit_agg_bwd": 2, "gvit_graph_bwd": 2, "gvit_attn_fwd": 1, "gvit_attn_bwd": 1, "gvit_layernorm_fwd": 1, "gvit_layernorm_bwd": 2,
     "gvit_colsum": 2, "gvit_dropout_residual_fwd": 1, "gvit_dropout_bwd": 1, "gvit_gelu_dropout_fwd": 1, "gvit_gelu_dropout_bwd": 1,
-    "gvit_patchify": 1, "gvit_embed_assemble": 1, "gvit_linear_gelu_dropout_fwd": 1,
+    "gvit_patchify": 1, "gvit_embed_assemble": 1, "gvit_linear_gelu_dropout_fwd": 1, "gvit_linear_dropout_residual_fwd": 1,
 }
 
 
@@ -475,14 +475,26 @@ class _LinearDropoutAdd(torch.autograd.Function):
         ctx.bias_dtype = bias.dtype if bias is not None else None
         ctx.w_dtype = weight.dtype
         weight = _shadow(weight, x.dtype)
-        y = F.linear(x, weight, _shadow(bias, x.dtype))
-        n = y.numel()
-        out = torch.empty_like(y if resid is None else resid)
-        mask = torch.empty(n // 8, dtype=torch.uint8, device=y.device) if p > 0 else None
-        _call("gvit_dropout_residual_fwd", _ptr(y), _ptr(resid), n, float(p), int(seed), 0, _rng_offset_ptr(), _dtype_code(out),
-              _dtype_code(y), _ptr(out), _ptr(mask), _stream())
+        N, K = weight.shape
+        if (x.dtype == torch.bfloat16 and resid is not None and resid.dtype == torch.bfloat16 and K <= _FUSED_RESID_MAX_K
+                and fused_fc1_available(N, K) and x.is_contiguous()):
+            # proj + proj_drop + residual add as ONE tcgen05 GEMM (its main loop is L2-bound, so only while K is small)
+            M = x.numel() // K
+            out = torch.empty_like(resid)
+            mask = torch.empty(M * N // 8, dtype=torch.uint8, device=x.device) if p > 0 else None
+            _call("gvit_linear_dropout_residual_fwd", _ptr(x), _ptr(weight), _ptr(_shadow(bias, x.dtype)), _ptr(resid), M, N, K,
+                  float(p), int(seed), 0, _rng_offset_ptr(), GVIT_BF16, _ptr(out), _ptr(mask), _stream())
+            y_dtype = x.dtype
+        else:
+            y = F.linear(x, weight, _shadow(bias, x.dtype))
+            n = y.numel()
+            out = torch.empty_like(y if resid is None else resid)
+            mask = torch.empty(n // 8, dtype=torch.uint8, device=y.device) if p > 0 else None
+            _call("gvit_dropout_residual_fwd", _ptr(y), _ptr(resid), n, float(p), int(seed), 0, _rng_offset_ptr(), _dtype_code(out),
+                  _dtype_code(y), _ptr(out), _ptr(mask), _stream())
+            y_dtype = y.dtype
         ctx.save_for_backward(x, weight, mask)
-        ctx.p, ctx.has_bias, ctx.has_resid, ctx.y_dtype = p, bias is not None, resid is not None, y.dtype
+        ctx.p, ctx.has_bias, ctx.has_resid, ctx.y_dtype = p, bias is not None, resid is not None, y_dtype
         return out
 
     @staticmethod
@@ -701,6 +713,7 @@ def agg_gather(h: torch.Tensor, idx: torch.Tensor, vals: torch.Tensor):
 
 
 _FC1_ENABLED = {"on": True}
+_FUSED_RESID_MAX_K = 1024        # Linear + dropout + residual goes through the fused GEMM up to this reduction length
 
 
 def fused_fc1_available(N: int, K: int) -> bool:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GVIT_ABI_VERSION 9
+#define GVIT_ABI_VERSION 10
 #if defined(__GNUC__)
 #define GVIT_API __attribute__((visibility("default")))
 #else
@@ -175,6 +175,14 @@ GVIT_API int gvit_gelu_dropout_bwd(const void* dout, const void* u, const uint8_
 GVIT_API int gvit_linear_gelu_dropout_fwd(const void* x, const void* w, const void* bias, int64_t M, int N, int K, float p, uint64_t seed,
                                  uint64_t offset, const uint64_t* offset_dev, int dtype, void* u, void* out, uint8_t* keep_mask,
                                  void* stream);
+
+/* Same GEMM with the other epilogue of the block: out = resid + dropout(x W^T + bias, p) - proj + proj_drop + the residual
+ * add of vit.py:70-71,117 (and fc2 + drop + residual, vit.py:93-94,118) in one kernel.  resid / out (M,N) bf16; same
+ * shape limits and keep-mask convention (4-byte aligned).  Worth it while K is small (the main loop is L2-bound at
+ * ~1.07 PF/s): the host side uses it for K <= 1024. */
+GVIT_API int gvit_linear_dropout_residual_fwd(const void* x, const void* w, const void* bias, const void* resid, int64_t M, int N, int K, float p,
+                                     uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, void* out,
+                                     uint8_t* keep_mask, void* stream);
 
 /* ---- f4: token prologue, replaces PatchEmbed (/root/reference/src/models/vit.py:25-36) and the CLS / pos_embed /
  * pos_drop lines vit.py:207-212.  A kernel == stride convolution is a GEMM over non-overlapping patches:

@@ -283,3 +283,42 @@ def test_fused_fc1_gemm_epilogue(M, N, K):
             x3, w3, b3 = x.float().requires_grad_(True), w.float().requires_grad_(True), b.float().requires_grad_(True)
             (torch.nn.functional.gelu(x3 @ w3.t() + b3) * mk).backward(cot.float())
             assert rel_err(xg, x3.grad) < TOL_BF16 and rel_err(wg, w3.grad) < TOL_BF16 and rel_err(bg, b3.grad) < TOL_BF16
+
+
+@pytest.mark.parametrize("M,N,K", [(4 * 197, 768, 768), (130, 256, 64), (50432, 768, 768)])
+def test_fused_proj_gemm_epilogue(M, N, K):
+    """f1 - proj + proj_drop + residual add as ONE tcgen05 GEMM (gvit_linear_dropout_residual_fwd) against a float64 GEMM
+    of the same bf16 operands; keep mask statistics; the backward through the kernel's own mask."""
+    assert ops.fused_fc1_available(N, K) and K <= ops._FUSED_RESID_MAX_K
+    g = torch.Generator(device=DEV).manual_seed(M + N + 1)
+    x = torch.randn(M, K, generator=g, device=DEV).bfloat16()
+    w = (torch.randn(N, K, generator=g, device=DEV) * K ** -0.5).bfloat16()
+    b = torch.randn(N, generator=g, device=DEV).bfloat16()
+    r = torch.randn(M, N, generator=g, device=DEV).bfloat16()
+    rows = torch.randperm(M, generator=torch.Generator().manual_seed(1))[:256].to(DEV)
+    y_ref = (x[rows].double() @ w.double().t() + b.double()).bfloat16().double()
+    before = ops.launch_count()
+    out0 = ops.linear_dropout_add(x, w, b, r, 0.0, True)
+    assert ops.launch_count() == before + 1                    # one kernel: no separate GEMM + edge pass
+    assert rel_err(out0[rows], r[rows].double() + y_ref) < TOL_BF16
+    xr, wr, br, rr = (t.clone().requires_grad_(True) for t in (x, w, b, r))
+    torch.manual_seed(11)
+    out = ops.linear_dropout_add(xr, wr, br, rr, 0.25, True)
+    y_all = (out0.float() - r.float())                        # x W^T + b as the kernel computed it (up to bf16 rounding of out0)
+    kept = (out.float() - r.float()).abs() > 0.5 * y_all.abs() / 0.75
+    live = y_all.abs() > 0.05                                  # keep decisions are only visible where y is not ~0
+    assert abs(float(kept[live].float().mean()) - 0.75) < max(5e-3, 4.0 * (0.1875 / max(1, int(live.sum()))) ** 0.5)
+    torch.manual_seed(11)
+    assert torch.equal(ops.linear_dropout_add(xr, wr, br, rr, 0.25, True), out)             # reproducible
+    if M <= 1024:
+        # backward through the kernel's OWN mask: with a zero residual the mask is readable from the output (out = keep * y / (1-p))
+        cot = torch.randn(M, N, generator=g, device=DEV).bfloat16()
+        xz, wz, bz, rz = (t.clone().requires_grad_(True) for t in (x, w, b, torch.zeros_like(r)))
+        torch.manual_seed(12)
+        oz = ops.linear_dropout_add(xz, wz, bz, rz, 0.25, True)
+        oz.backward(cot)
+        mask = (oz != 0).float()
+        x3, w3, b3, r3 = (t.float().requires_grad_(True) for t in (x, w, b, torch.zeros_like(r)))
+        (r3 + (x3 @ w3.t() + b3) * mask / 0.75).backward(cot.float())
+        assert rel_err(rz.grad, r3.grad) < TOL_BF16 and rel_err(xz.grad, x3.grad) < TOL_BF16
+        assert rel_err(wz.grad, w3.grad) < TOL_BF16 and rel_err(bz.grad, b3.grad) < TOL_BF16
