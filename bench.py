@@ -162,6 +162,11 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # per-kernel roofline (live CUDA-event timing of each libgvit kernel at the bench shape)
 # ------------------------------------------------------------------------------------------------
+def _lib_rows(M):
+    from graph_augmented_vision_transformers_b200 import _lib
+    return _lib.load().gvit_linear_gelu_dropout_bwd_ws_rows(M)
+
+
 def kernel_rooflines(dev, B, peaks, iters=10, only=None):
     from graph_augmented_vision_transformers_b200 import ops
     from graph_augmented_vision_transformers_b200.ops import _call, _dtype_code, _ptr, _stream, _token_view
@@ -175,6 +180,7 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
     W = torch.randn(D, D, device=dev, dtype=bf, generator=g) * 0.03
     W1 = torch.randn(4 * D, D, device=dev, dtype=bf, generator=g) * 0.03
     b1 = torch.zeros(4 * D, device=dev, dtype=bf)
+    W2 = torch.randn(D, 4 * D, device=dev, dtype=bf, generator=g) * 0.03
     bias = torch.zeros(D, device=dev, dtype=bf)
     gam, bet = torch.ones(D, device=dev, dtype=bf), torch.zeros(D, device=dev, dtype=bf)
     idx, vals, rnorm = ops.knn_graph(hs[0], k)
@@ -190,6 +196,7 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
     u4 = [torch.randn(B, N, 4 * D, device=dev, dtype=bf, generator=g) for _ in range(2)]
     o4 = torch.empty_like(u4[0]); m4 = torch.empty(B * N * 4 * D // 8, dtype=torch.uint8, device=dev)
     m1 = torch.empty(B * N * D // 8, dtype=torch.uint8, device=dev)
+    part4 = torch.empty(_lib_rows(B * N) * 4 * D, device=dev)
     cs_out = torch.empty(4 * D, device=dev); cs_ws = torch.empty(1024 * 4 * D, device=dev)
     st = _stream()
     dt = _dtype_code(hs[0])
@@ -222,10 +229,12 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
                       B * N * D * e + 4 * D * D * e + 2 * B * N * 4 * D * e + B * N * 4 * D // 8, 2.0 * B * N * D * 4 * D, "tensor", 12),
         "proj_fused": (lambda i: _call("gvit_linear_dropout_residual_fwd", _ptr(hs[i % R]), _ptr(W), _ptr(bias), _ptr(xs[i % R]), B * N, D, D, 0.1, 1234, 0, None, dt, _ptr(out), _ptr(m1), st),
                        3 * B * N * D * e + D * D * e + B * N * D // 8, 2.0 * B * N * D * D, "hbm", 12),
+        "fc2_bwd_fused": (lambda i: _call("gvit_linear_gelu_dropout_bwd", _ptr(hs[i % R]), _ptr(W2), _ptr(u4[i % 2]), _ptr(m4), B * N, 4 * D, D, 0.1, dt, _ptr(o4), _ptr(cs_out), _ptr(part4), st),
+                          B * N * D * e + 4 * D * D * e + 2 * B * N * 4 * D * e + B * N * 4 * D // 8, 2.0 * B * N * D * 4 * D, "tensor", 12),
         "gelu_dropout_fwd": (lambda i: _call("gvit_gelu_dropout_fwd", _ptr(u4[i % 2]), B * N * 4 * D, 0.1, 1234, 0, None, dt, _ptr(o4), _ptr(m4), st),
                              2 * B * N * 4 * D * e + B * N * 4 * D // 8, 0.0, "hbm", 0),      # folded into fc1_fused for bf16
         "gelu_dropout_bwd": (lambda i: _call("gvit_gelu_dropout_bwd", _ptr(u4[(i + 1) % 2]), _ptr(u4[i % 2]), _ptr(m4), B * N * 4 * D, 0.1, dt, _ptr(o4), 4 * D, _ptr(cs_out), _ptr(cs_ws), st),
-                             3 * B * N * 4 * D * e + B * N * 4 * D // 8, 0.0, "hbm", 12),
+                             3 * B * N * 4 * D * e + B * N * 4 * D // 8, 0.0, "hbm", 0),      # folded into fc2_bwd_fused for bf16
         "colsum_3072": (lambda i: _call("gvit_colsum", _ptr(u4[i % 2]), B * N, 4 * D, dt, _ptr(cs_out), _ptr(cs_ws), st),
                         B * N * 4 * D * e, 0.0, "hbm", 12),
         "colsum_768": (lambda i: _call("gvit_colsum", _ptr(hs[i % R]), B * N, D, dt, _ptr(cs_out), _ptr(cs_ws), st),

@@ -255,6 +255,22 @@ int gvit_linear_dropout_residual_fwd(const void* x, const void* w, const void* b
   return linear_dropout_residual_fwd_tc(x, w, bias, resid, M, N, K, p, seed, offset, offset_dev, out, keep_mask, static_cast<cudaStream_t>(stream));
 }
 
+int64_t gvit_linear_gelu_dropout_bwd_ws_rows(int64_t M) { return fc2_bwd_partial_rows(M); }
+
+int gvit_linear_gelu_dropout_bwd(const void* dout, const void* w2, const void* u, const uint8_t* keep_mask, int64_t M, int N, int K,
+                                 float p, int dtype, void* du, float* colsum_out, float* partial_ws, void* stream) {
+  TRY(check_dtype(dtype, "linear_gelu_dropout_bwd"));
+  GVIT_REQUIRE(dout && w2 && u && du && colsum_out && partial_ws, GVIT_ERR_SHAPE, "linear_gelu_dropout_bwd: null pointer");
+  GVIT_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || keep_mask), GVIT_ERR_SHAPE, "linear_gelu_dropout_bwd: p=%f (keep_mask required when p > 0)", p);
+  GVIT_REQUIRE(dtype == GVIT_BF16 && fc1_tc_supported(M, N, K), GVIT_ERR_UNSUPPORTED,
+               "linear_gelu_dropout_bwd: the fused kernel is bf16-only with N %% 256 == 0 and K %% 64 == 0 (M=%lld N=%d K=%d); "
+               "compose a library GEMM with gvit_gelu_dropout_bwd instead", (long long)M, N, K);
+  GVIT_REQUIRE(aligned16(dout) && aligned16(w2) && aligned16(u) && aligned16(du) && aligned16(partial_ws) &&
+               (!keep_mask || (reinterpret_cast<uintptr_t>(keep_mask) & 3u) == 0), GVIT_ERR_ALIGN,
+               "linear_gelu_dropout_bwd: tensors must be 16-byte aligned (keep_mask 4-byte)");
+  return linear_gelu_dropout_bwd_tc(dout, w2, u, keep_mask, M, N, K, p, du, colsum_out, partial_ws, static_cast<cudaStream_t>(stream));
+}
+
 int gvit_patchify(const void* img, int B, int C, int H, int W, int P, int in_dtype, int out_dtype, void* out, void* stream) {
   TRY(check_dtype(in_dtype, "patchify"));
   TRY(check_dtype(out_dtype, "patchify"));

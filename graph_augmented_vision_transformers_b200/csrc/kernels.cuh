@@ -69,6 +69,10 @@ int fc1_gelu_dropout_fwd_tc(const void* x, const void* w, const void* bias, int6
 int linear_dropout_residual_fwd_tc(const void* x, const void* w, const void* bias, const void* resid, int64_t M, int N, int K, float p,
                                    uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* out, uint8_t* mask, cudaStream_t st);
 
+int64_t fc2_bwd_partial_rows(int64_t M);
+int linear_gelu_dropout_bwd_tc(const void* dout, const void* w2, const void* u, const uint8_t* mask, int64_t M, int N, int K, float p,
+                               void* du, float* colsum_out, float* partial_ws, cudaStream_t st);
+
 // ---- token prologue : embed.cu
 int patchify(const void* img, int B, int C, int H, int W, int P, int in_dtype, int out_dtype, void* out, cudaStream_t st);
 int embed_assemble(const void* y, const void* bias, const void* cls, const void* pos, int B, int N, int D, float p,

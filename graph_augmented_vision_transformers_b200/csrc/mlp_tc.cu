@@ -6,7 +6,12 @@
 //   MODE 1, attention output projection:
 //     out = resid + dropout(x W^T + b, p)     (vit.py:70-71 proj + proj_drop, residual add of vit.py:117)
 //
-// (The text below describes MODE 0; MODE 1 shares the main loop and swaps the epilogue.)
+//   MODE 2, backward of fc2 -> (drop, GELU): the input gradient of fc2 fused with the backward of vit.py:91-92:
+//     du  = (dout W2) * keep / (1 - p) * gelu'(u)     and per-tile column sums of du (fc1's bias gradient, summed by a
+//     second tiny kernel in a fixed order).  Here the B operand is W2 itself ((out, in) row-major = [K][N] with N
+//     contiguous): MN-major, four [64 k][64 n] atoms per stage.
+//
+// (The text below describes MODE 0; the other modes share the main loop and swap the epilogue.)
 //
 // As a library GEMM plus the gvit_gelu_dropout_fwd pass this is 173 us + 163 us at B = 256 (M = 50432, N = 3072,
 // K = 768): the elementwise pass is issue-bound ALU work (GELU + Philox) over 640 MB.  Here that ALU work runs in the
@@ -61,9 +66,11 @@ struct Params {
   uint64_t seed, offset;
   const uint64_t* offset_dev;
   const __nv_bfloat16* bias;
-  __nv_bfloat16* u;                           // MODE 0: pre-activation output.  MODE 1: the RESIDUAL input (read only)
+  __nv_bfloat16* u;                           // MODE 0: pre-activation output.  MODE 1: the RESIDUAL input (read only).
+                                              // MODE 2: the saved pre-activation (read only); mask is read only too
   __nv_bfloat16* out;
   uint8_t* mask;
+  float* partial;                             // MODE 2: (ceil(M/128) * 4, N) fp32 column partial sums of du
   uint32_t rk[2 * GVIT_PHILOX_ROUNDS];        // Philox round keys, precomputed on the host: constant-bank operands, no
 };                                            // per-call key schedule in the epilogue
 
@@ -116,15 +123,24 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
           mbar_wait(&ctl->empty[s], ((it / STAGES) & 1) ^ 1);            // released by EVERY CTA of the cluster
           mbar_expect_tx(&ctl->full[s], (uint32_t)STAGE_BYTES);          // own x tile + own W slice + the peers' W slices
           tma_load_3d(ring + (size_t)s * STAGE_BYTES, &tm_x, kb * BK, m * BM, 0, &ctl->full[s]);             // rows >= M: zeros
-          tma_load_3d_mc(ring + (size_t)s * STAGE_BYTES + A_BYTES + rank * (B_BYTES / CL), &tm_w, kb * BK, n * BN + rank * (BN / CL), 0,
-                         &ctl->full[s], (uint16_t)((1u << CL) - 1));
+          if constexpr (MODE != 2) {                                     // W (N, K): K-major, one box of BN / CL rows
+            tma_load_3d_mc(ring + (size_t)s * STAGE_BYTES + A_BYTES + rank * (B_BYTES / CL), &tm_w, kb * BK, n * BN + rank * (BN / CL), 0,
+                           &ctl->full[s], (uint16_t)((1u << CL) - 1));
+          } else {                                                       // W2 (K, N): MN-major, [64 k][64 n] atoms of 8 KB
+#pragma unroll
+            for (int j = 0; j < 4 / CL; ++j) {
+              const int atom = rank * (4 / CL) + j;
+              tma_load_3d_mc(ring + (size_t)s * STAGE_BYTES + A_BYTES + atom * 8192, &tm_w, n * BN + atom * 64, kb * BK, 0, &ctl->full[s],
+                             (uint16_t)((1u << CL) - 1));
+            }
+          }
         }
       }
     }
   } else if (warp == EPI_WARPS + 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      const uint32_t idesc = make_idesc(BM, BN, false, false);
+      const uint32_t idesc = make_idesc(BM, BN, false, MODE == 2);
       const uint32_t aR = smem_u32(ring);
       int it = 0, tc = 0;
       for (int pr = cid; pr < npairs; pr += ncl, ++tc) {
@@ -140,7 +156,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
           const uint32_t aA = aR + s * STAGE_BYTES, aB = aA + A_BYTES;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_ss(tmem + buf * BN, make_sdesc(aA + kk * 32), make_sdesc(aB + kk * 32), idesc, kb > 0 || kk > 0);
+            umma_ss(tmem + buf * BN, make_sdesc(aA + kk * 32),
+                    MODE == 2 ? make_sdesc_lbo(aB + kk * 2048, 8192) : make_sdesc(aB + kk * 32), idesc, kb > 0 || kk > 0);
           umma_commit_mc(&ctl->empty[s], (uint16_t)((1u << CL) - 1));  // slot s of EVERY CTA is written by the next refill
         }
         umma_commit(&ctl->acc_full[buf]);
@@ -199,7 +216,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
         const int col0 = n * BN + g * 64 + h * 32;
         // bias of these 32 columns as fp32 in the (idle) staging area: every lane then reads it with broadcast LDS.128
         float* sbias = reinterpret_cast<float*>(stg);
-        if (lane < 8) {
+        if (MODE != 2 && lane < 8) {
           float4 bf4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (P.bias) {
             const uint2 raw = __ldg(reinterpret_cast<const uint2*>(P.bias + col0 + lane * 4));
@@ -214,6 +231,61 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
           mbar_arrive(&ctl->acc_free[buf]);
         }
         __syncwarp();
+        if constexpr (MODE == 2) {
+          // ---- du = dh * keep / (1 - p) * gelu'(u); column sums of du over this warp's 32 rows
+          uint32_t uu[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {                                // u tile: coalesced global -> staging -> own row
+            const int r = r4 + 8 * i;
+            uint4 v4 = make_uint4(0, 0, 0, 0);
+            if (wrow0 + r < P.M) v4 = *reinterpret_cast<const uint4*>(P.u + (wrow0 + r) * P.N + col0 + ch4 * 8);
+            *reinterpret_cast<uint4*>(stg + r * 64 + ((ch4 ^ ((r >> 1) & 3)) << 4)) = v4;
+          }
+          uint32_t keep = 0xffffffffu;
+          if (P.p > 0.f && row < P.M) keep = *reinterpret_cast<const uint32_t*>(P.mask + ((row * P.N + col0) >> 3));
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 v4 = *reinterpret_cast<const uint4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4));
+            uu[4 * q] = v4.x; uu[4 * q + 1] = v4.y; uu[4 * q + 2] = v4.z; uu[4 * q + 3] = v4.w;
+          }
+          __syncwarp();
+          uint32_t dpk[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float gq[8], uq[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              uq[2 * e] = bf_lo(uu[4 * q + e]); uq[2 * e + 1] = bf_hi(uu[4 * q + e]);
+              gq[2 * e] = v[8 * q + 2 * e]; gq[2 * e + 1] = v[8 * q + 2 * e + 1];
+            }
+            Gelu<false>::grad8(gq, uq, scale);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) gq[t] = (keep >> (8 * q + t)) & 1u ? gq[t] : 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dpk[4 * q + e] = pack2(gq[2 * e], gq[2 * e + 1]);
+          }
+          stage(dpk);
+          __syncwarp();
+          // column sums of the STAGED (bf16, as stored) tile: lane = (row half, column pair); two halves joined by one shuffle
+          {
+            const int cp = lane & 15, rh = lane >> 4;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int r = rh * 16 + i;
+              const uint32_t w2 = *reinterpret_cast<const uint32_t*>(stg + r * 64 + (((cp >> 2) ^ ((r >> 1) & 3)) << 4) + (cp & 3) * 4);
+              s0 += bf_lo(w2);
+              s1 += bf_hi(w2);
+            }
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            if (lane < 16)
+              *reinterpret_cast<float2*>(P.partial + ((int64_t)m * 4 + (warp & 3)) * P.N + col0 + 2 * cp) = make_float2(s0, s1);
+          }
+          flush(P.out, wrow0, col0);                                   // du tile (flush syncs the warp before and after)
+          continue;
+        }
         uint32_t upk[16];                                              // u as stored: 32 bf16
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
@@ -302,6 +374,24 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
   if (warp == EPI_WARPS + 1) tmem_dealloc(tmem, 512);
 }
 
+// out[c] = sum over the partial rows, fixed order (32 columns x 8 row lanes per CTA, then lanes 0..7): deterministic
+__global__ void __launch_bounds__(256) partial_colsum_kernel(const float* __restrict__ partial, int nrows, int N, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float sacc = 0.f;
+  if (c < N)
+    for (int i = ly; i < nrows; i += 8) sacc += partial[(int64_t)i * N + c];
+  red[ly][cx] = sacc;
+  __syncthreads();
+  if (ly == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][cx];
+    out[c] = t;
+  }
+}
+
 }  // namespace
 
 bool fc1_tc_supported(int64_t M, int N, int K) { return M >= 1 && N >= BN && N % BN == 0 && K >= BK && K % BK == 0; }
@@ -309,14 +399,17 @@ bool fc1_tc_supported(int64_t M, int N, int K) { return M >= 1 && N >= BN && N %
 template <int MODE>
 static int fused_linear_launch(const void* x, const void* w, const void* bias, int64_t M, int N, int K, float p, uint64_t seed,
                                uint64_t offset, const uint64_t* offset_dev, void* u_or_resid, void* out, uint8_t* mask,
-                               cudaStream_t st) {
+                               cudaStream_t st, float* partial = nullptr) {
   CUtensorMap tm_x, tm_w;
   int rc = make_tmap_bf16_3d(&tm_x, x, (uint64_t)K, (uint64_t)M, 1, (uint64_t)K, (uint64_t)M * K, BM);
   if (rc != GVIT_OK) return rc;
-  rc = make_tmap_bf16_3d(&tm_w, w, (uint64_t)K, (uint64_t)N, 1, (uint64_t)K, (uint64_t)N * K, BN / CL);   // one CTA's slice of the tile
+  if (MODE != 2)
+    rc = make_tmap_bf16_3d(&tm_w, w, (uint64_t)K, (uint64_t)N, 1, (uint64_t)K, (uint64_t)N * K, BN / CL);   // one CTA's slice of the tile
+  else
+    rc = make_tmap_bf16_3d(&tm_w, w, (uint64_t)N, (uint64_t)K, 1, (uint64_t)N, (uint64_t)N * K, 64);        // W2 (K, N): [64 k][64 n] atoms
   if (rc != GVIT_OK) return rc;
   Params P{M, N, K, p, seed, offset, offset_dev, static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(u_or_resid),
-           static_cast<__nv_bfloat16*>(out), mask, {}};
+           static_cast<__nv_bfloat16*>(out), mask, partial, {}};
   for (int r = 0; r < GVIT_PHILOX_ROUNDS; ++r) {
     P.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
     P.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
@@ -354,6 +447,19 @@ int fc1_gelu_dropout_fwd_tc(const void* x, const void* w, const void* bias, int6
 int linear_dropout_residual_fwd_tc(const void* x, const void* w, const void* bias, const void* resid, int64_t M, int N, int K, float p,
                                    uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* out, uint8_t* mask, cudaStream_t st) {
   return fused_linear_launch<1>(x, w, bias, M, N, K, p, seed, offset, offset_dev, const_cast<void*>(resid), out, mask, st);
+}
+
+// rows of the column-partial workspace of linear_gelu_dropout_bwd_tc: one per (row block incl. cluster padding, lane quarter)
+int64_t fc2_bwd_partial_rows(int64_t M) { return (((M + BM - 1) / BM + CL - 1) / CL) * CL * 4; }
+
+int linear_gelu_dropout_bwd_tc(const void* dout, const void* w2, const void* u, const uint8_t* mask, int64_t M, int N, int K, float p,
+                               void* du, float* colsum_out, float* partial_ws, cudaStream_t st) {
+  int rc = fused_linear_launch<2>(dout, w2, nullptr, M, N, K, p, 0, 0, nullptr, const_cast<void*>(u), du, const_cast<uint8_t*>(mask), st,
+                                  partial_ws);
+  if (rc != GVIT_OK) return rc;
+  partial_colsum_kernel<<<(N + 31) / 32, 256, 0, st>>>(partial_ws, (int)fc2_bwd_partial_rows(M), N, colsum_out);
+  GVIT_CHECK_LAUNCH();
+  return GVIT_OK;
 }
 
 }  // namespace gvit

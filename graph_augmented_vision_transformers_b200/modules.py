@@ -94,6 +94,9 @@ class Mlp(nn.Module):
         if _hooked(self.fc1) or _hooked(self.fc2) or _hooked(self.act) or _hooked(self.drop):
             x = ops.gelu_dropout(self.fc1(x), self.drop.p, self.training)
             return ops.dropout_add(self.fc2(x), resid, self.drop.p, self.training)
+        if ops.mlp_fused_available(x, self.fc1.weight, self.fc2.weight, resid):
+            # bf16: the whole branch as one autograd node - fused fc1 GEMM forward, fused fc2-dgrad + GELU' GEMM backward
+            return ops.mlp_fused(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, resid, self.drop.p, self.training)
         # fc1 + GELU + drop, then fc2 + drop + residual: each Linear's bias gradient comes out of the edge's backward pass
         x = ops.linear_gelu_dropout(x, self.fc1.weight, self.fc1.bias, self.drop.p, self.training)
         return ops.linear_dropout_add(x, self.fc2.weight, self.fc2.bias, resid, self.drop.p, self.training)

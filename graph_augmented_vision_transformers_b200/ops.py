@@ -24,7 +24,7 @@ from . import _lib
 from ._lib import GVIT_BF16, GVIT_COLSUM_CHUNKS, GVIT_F32, GVIT_LN_PARTIALS
 
 __all__ = ["attention_core", "layer_norm", "pre_norm", "linear", "colsum", "linear_dropout_add", "linear_gelu_dropout", "dropout_add", "gelu_dropout", "knn_graph", "graph_reverse", "patch_graph",
-           "agg_gather", "patch_embed_tokens", "refresh_shadows", "invalidate_shadows", "set_rng_offset_tensor", "launch_count", "reset_launch_count"]
+           "agg_gather", "mlp_fused", "patch_embed_tokens", "refresh_shadows", "invalidate_shadows", "set_rng_offset_tensor", "launch_count", "reset_launch_count"]
 
 # kernels launched through the C ABI since the last reset (bench.py reports it as gpu_launches)
 _LAUNCHES = {"n": 0}
@@ -32,7 +32,7 @@ _KERNELS_PER_CALL = {
     "gvit_knn_fwd": 1, "gvit_graph_reverse": 1, "gvit_knn_bwd": 1, "gvit_agg_gather_fwd": 1, "gvit_agg_fwd": 1,
     "gvit_agg_bwd": 2, "gvit_graph_bwd": 2, "gvit_attn_fwd": 1, "gvit_attn_bwd": 1, "gvit_layernorm_fwd": 1, "gvit_layernorm_bwd": 2,
     "gvit_colsum": 2, "gvit_dropout_residual_fwd": 1, "gvit_dropout_bwd": 1, "gvit_gelu_dropout_fwd": 1, "gvit_gelu_dropout_bwd": 1,
-    "gvit_patchify": 1, "gvit_embed_assemble": 1, "gvit_linear_gelu_dropout_fwd": 1, "gvit_linear_dropout_residual_fwd": 1,
+    "gvit_patchify": 1, "gvit_embed_assemble": 1, "gvit_linear_gelu_dropout_fwd": 1, "gvit_linear_dropout_residual_fwd": 1, "gvit_linear_gelu_dropout_bwd": 2,
 }
 
 
@@ -556,6 +556,92 @@ class _LinearGeluDropout(torch.autograd.Function):
               _ptr(du), Dn, _ptr(db), _ptr(ws), _stream())
         dx, dw = _linear_grads(ctx.needs_input_grad, x, weight, du.view(-1, Dn), ctx.w_dtype)
         return dx, dw, (db.to(ctx.bias_dtype) if want_db else None), None, None
+
+
+class _MlpFused(torch.autograd.Function):
+    """out = resid + dropout(fc2(dropout(gelu(fc1(x)))))  - the whole Mlp branch of vit.py:88-94,118 as one autograd node, so
+    that the backward can run fc2's input-gradient GEMM fused with the GELU / dropout backward and fc1's bias gradient
+    (gvit_linear_gelu_dropout_bwd): the (M, 4D) gradient of the hidden activation never makes an HBM round trip.
+    Forward: fused fc1 GEMM (gvit_linear_gelu_dropout_fwd), library fc2 GEMM, gvit_dropout_residual_fwd."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, resid, p, seed1, seed2):
+        ctx.dtypes = (w1.dtype, None if b1 is None else b1.dtype, w2.dtype, None if b2 is None else b2.dtype)
+        w1s, w2s = _shadow(w1, x.dtype), _shadow(w2, x.dtype)
+        Nh, K = w1s.shape
+        M = x.numel() // K
+        st = _stream()
+        u = torch.empty(x.shape[:-1] + (Nh,), dtype=x.dtype, device=x.device)
+        h = torch.empty_like(u)
+        mask1 = torch.empty(M * Nh // 8, dtype=torch.uint8, device=x.device) if p > 0 else None
+        _call("gvit_linear_gelu_dropout_fwd", _ptr(x), _ptr(w1s), _ptr(_shadow(b1, x.dtype)), M, Nh, K, float(p), int(seed1), 0,
+              _rng_offset_ptr(), GVIT_BF16, _ptr(u), _ptr(h), _ptr(mask1), st)
+        y = F.linear(h, w2s, _shadow(b2, x.dtype))
+        n = y.numel()
+        out = torch.empty_like(y if resid is None else resid)
+        mask2 = torch.empty(n // 8, dtype=torch.uint8, device=x.device) if p > 0 else None
+        _call("gvit_dropout_residual_fwd", _ptr(y), _ptr(resid), n, float(p), int(seed2), 0, _rng_offset_ptr(), _dtype_code(out),
+              _dtype_code(y), _ptr(out), _ptr(mask2), st)
+        ctx.save_for_backward(x, w1s, w2s, u, h, mask1, mask2)
+        ctx.p, ctx.has_resid, ctx.y_dtype = p, resid is not None, y.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w1s, w2s, u, h, mask1, mask2 = ctx.saved_tensors
+        w1_dt, b1_dt, w2_dt, b2_dt = ctx.dtypes
+        Nh, K = w1s.shape
+        D2 = w2s.shape[0]
+        M = x.numel() // K
+        st = _stream()
+        dout = dout.contiguous()
+        # fc2: dropout backward + bias gradient in one pass, weight gradient as a library GEMM
+        dy = torch.empty(dout.shape, dtype=ctx.y_dtype, device=dout.device)
+        db2 = torch.empty(D2, dtype=torch.float32, device=dout.device) if b2_dt is not None else None
+        ws2 = _colsum_ws(M, D2, dout.device) if db2 is not None else None
+        if ctx.p > 0 or db2 is not None:
+            _call("gvit_dropout_bwd", _ptr(dout), _ptr(mask2), dout.numel(), float(ctx.p), _dtype_code(dout), _dtype_code(dy),
+                  _ptr(dy), D2, _ptr(db2), _ptr(ws2), st)
+        else:
+            dy = dout.to(ctx.y_dtype)
+        dy2 = dy.view(M, D2)
+        dw2 = _wgrad(dy2, h.view(M, Nh), w2_dt) if ctx.needs_input_grad[3] else None
+        # fc2 input gradient + GELU' + keep mask + fc1 bias gradient: ONE tcgen05 GEMM, W2 read as stored (MN-major B)
+        du = torch.empty_like(u)
+        db1 = torch.empty(Nh, dtype=torch.float32, device=dout.device)
+        rows = _lib.load().gvit_linear_gelu_dropout_bwd_ws_rows(M)
+        part = torch.empty(rows * Nh, dtype=torch.float32, device=dout.device)
+        _call("gvit_linear_gelu_dropout_bwd", _ptr(dy2), _ptr(w2s), _ptr(u), _ptr(mask1), M, Nh, D2, float(ctx.p), GVIT_BF16,
+              _ptr(du), _ptr(db1), _ptr(part), st)
+        du2 = du.view(M, Nh)
+        dx = (du2 @ w1s).view(x.shape) if ctx.needs_input_grad[0] else None
+        dw1 = _wgrad(du2, x.reshape(M, K), w1_dt) if ctx.needs_input_grad[1] else None
+        return (dx, dw1, (db1.to(b1_dt) if b1_dt is not None and ctx.needs_input_grad[2] else None), dw2,
+                (db2.to(b2_dt) if db2 is not None and ctx.needs_input_grad[4] else None),
+                (dout if ctx.has_resid else None), None, None, None)
+
+
+import os as _os
+
+_MLP_FUSED = {"on": _os.environ.get("GVIT_MLP_FUSED", "1") != "0"}      # GVIT_MLP_FUSED=0: two-op composition (A/B switch)
+
+
+def mlp_fused_available(x, w1, w2, resid) -> bool:
+    """True when the whole-Mlp node applies: bf16 compute, hidden width a multiple of 256, widths multiples of 64."""
+    dt = _autocast_dtype(x)
+    return (_MLP_FUSED["on"] and dt == torch.bfloat16 and x.is_cuda and w1.dim() == 2 and w2.dim() == 2
+            and w2.shape[1] == w1.shape[0] and w2.shape[0] % 8 == 0 and (resid is None or resid.dtype == torch.bfloat16)
+            and fused_fc1_available(w1.shape[0], w1.shape[1]) and fused_fc1_available(w1.shape[0], w2.shape[0]))
+
+
+def mlp_fused(x, w1, b1, w2, b2, resid, p: float, training: bool):
+    """``resid + dropout(linear(dropout(gelu(linear(x, w1, b1))), w2, b2))`` as one autograd node (see _MlpFused)."""
+    _check_cuda(x, w1, b1, w2, b2, resid)
+    p = float(p) if training else 0.0
+    seed1, seed2 = (_draw_seed(), _draw_seed()) if p > 0 else (0, 0)
+    with torch.autocast("cuda", enabled=False):
+        return _MlpFused.apply(x.to(torch.bfloat16).contiguous(), w1, b1, w2, b2,
+                               None if resid is None else resid.contiguous(), p, seed1, seed2)
 
 
 def linear_dropout_add(x, weight, bias, resid, p: float, training: bool):

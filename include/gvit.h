@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GVIT_ABI_VERSION 10
+#define GVIT_ABI_VERSION 11
 #if defined(__GNUC__)
 #define GVIT_API __attribute__((visibility("default")))
 #else
@@ -183,6 +183,15 @@ GVIT_API int gvit_linear_gelu_dropout_fwd(const void* x, const void* w, const vo
 GVIT_API int gvit_linear_dropout_residual_fwd(const void* x, const void* w, const void* bias, const void* resid, int64_t M, int N, int K, float p,
                                      uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, void* out,
                                      uint8_t* keep_mask, void* stream);
+
+/* Backward counterpart for the Mlp: the input gradient of fc2 fused with the backward of drop + GELU (vit.py:91-93):
+ *   du = (dout W2) * keep / (1 - p) * gelu'(u),   colsum_out[n] = sum_rows du[:, n]   (fc1's bias gradient, fp32, deterministic)
+ * dout (M,K) is the gradient of fc2's output after its own dropout backward, w2 (K,N) is fc2.weight as stored ((out, in)
+ * row-major: no transpose copy), u (M,N) the saved pre-activation, keep_mask as written by the forward, du (M,N) bf16.
+ * partial_ws: gvit_linear_gelu_dropout_bwd_ws_rows(M) * N floats.  bf16 only, N % 256 == 0, K % 64 == 0. */
+GVIT_API int64_t gvit_linear_gelu_dropout_bwd_ws_rows(int64_t M);
+GVIT_API int gvit_linear_gelu_dropout_bwd(const void* dout, const void* w2, const void* u, const uint8_t* keep_mask, int64_t M, int N, int K,
+                                 float p, int dtype, void* du, float* colsum_out, float* partial_ws, void* stream);
 
 /* ---- f4: token prologue, replaces PatchEmbed (/root/reference/src/models/vit.py:25-36) and the CLS / pos_embed /
  * pos_drop lines vit.py:207-212.  A kernel == stride convolution is a GEMM over non-overlapping patches:

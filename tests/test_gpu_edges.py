@@ -322,3 +322,74 @@ def test_fused_proj_gemm_epilogue(M, N, K):
         (r3 + (x3 @ w3.t() + b3) * mask / 0.75).backward(cot.float())
         assert rel_err(rz.grad, r3.grad) < TOL_BF16 and rel_err(xz.grad, x3.grad) < TOL_BF16
         assert rel_err(wz.grad, w3.grad) < TOL_BF16 and rel_err(bz.grad, b3.grad) < TOL_BF16
+
+
+@pytest.mark.parametrize("M,N,K,p", [(4 * 197, 3072, 768, 0.1), (130, 256, 64, 0.25), (300, 512, 128, 0.0), (50432, 3072, 768, 0.1)])
+def test_fused_fc2_dgrad_gelu_backward_kernel(M, N, K, p):
+    """f1 - gvit_linear_gelu_dropout_bwd (fc2 input-gradient GEMM + keep mask + GELU' + fc1 bias gradient in one kernel, W2
+    read as stored) against the unfused pair: library GEMM, then gvit_gelu_dropout_bwd with the SAME mask bytes."""
+    from graph_augmented_vision_transformers_b200 import _lib
+    from graph_augmented_vision_transformers_b200.ops import _call, _ptr, _stream, GVIT_BF16, _colsum_ws
+    g = torch.Generator(device=DEV).manual_seed(M + N + 3)
+    dy = torch.randn(M, K, generator=g, device=DEV).bfloat16()                 # gradient of fc2's output
+    w2 = (torch.randn(K, N, generator=g, device=DEV) * K ** -0.5).bfloat16()   # fc2.weight: (out = K here, in = N)
+    u = (torch.randn(M, N, generator=g, device=DEV) * 1.5).bfloat16()
+    mask = torch.randint(0, 256, (M * N // 8,), generator=g, device=DEV, dtype=torch.uint8) if p > 0 else None
+    du = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    db = torch.empty(N, device=DEV)
+    rows = _lib.load().gvit_linear_gelu_dropout_bwd_ws_rows(M)
+    part = torch.empty(rows * N, device=DEV)
+    _call("gvit_linear_gelu_dropout_bwd", _ptr(dy), _ptr(w2), _ptr(u), _ptr(mask), M, N, K, float(p), GVIT_BF16, _ptr(du), _ptr(db),
+          _ptr(part), _stream())
+    dh = dy @ w2                                                               # (M, N) bf16, what the unfused path stores
+    du_ref = torch.empty_like(du)
+    db_ref = torch.empty(N, device=DEV)
+    ws = _colsum_ws(M, N, DEV)
+    _call("gvit_gelu_dropout_bwd", _ptr(dh), _ptr(u), _ptr(mask), M * N, float(p), GVIT_BF16, _ptr(du_ref), N, _ptr(db_ref), _ptr(ws),
+          _stream())
+    assert rel_err(du, du_ref) < TOL_BF16                                      # dh is not rounded to bf16 on the fused path
+    assert float((du.float() - du_ref.float()).abs().mean() / du_ref.float().abs().mean()) < 4e-3
+    assert ((du == 0) == (du_ref == 0)).float().mean() > 0.999                 # same mask applied
+    assert rel_err(db, du.float().sum(0)) < 1e-4                               # the bias gradient sums the values as stored
+    assert rel_err(db, db_ref) < TOL_BF16
+    db2 = torch.empty(N, device=DEV)
+    _call("gvit_linear_gelu_dropout_bwd", _ptr(dy), _ptr(w2), _ptr(u), _ptr(mask), M, N, K, float(p), GVIT_BF16, _ptr(du_ref), _ptr(db2),
+          _ptr(part), _stream())
+    assert torch.equal(db, db2) and torch.equal(du, du_ref)                    # deterministic
+
+
+@pytest.mark.parametrize("p", [0.0, 0.2])
+def test_mlp_fused_node_matches_the_two_op_composition(p):
+    """The whole-Mlp autograd node (fused fc1 forward, fused fc2-dgrad backward) against linear_gelu_dropout +
+    linear_dropout_add on the library GEMMs; with dropout the two draw different masks, so p > 0 compares statistics."""
+    g = torch.Generator(device=DEV).manual_seed(9)
+    x0 = torch.randn(3, 197, 128, generator=g, device=DEV).bfloat16()
+    r0 = torch.randn(3, 197, 128, generator=g, device=DEV).bfloat16()
+    w1 = (torch.randn(512, 128, generator=g, device=DEV) * 0.1).bfloat16()
+    b1 = (torch.randn(512, generator=g, device=DEV) * 0.1).bfloat16()
+    w2 = (torch.randn(128, 512, generator=g, device=DEV) * 0.05).bfloat16()
+    b2 = (torch.randn(128, generator=g, device=DEV) * 0.1).bfloat16()
+    cot = torch.randn(3, 197, 128, generator=g, device=DEV).bfloat16()
+    assert ops.mlp_fused_available(x0, w1, w2, r0)
+    outs = []
+    for fused in (True, False):
+        leaves = [t.clone().requires_grad_(True) for t in (x0, w1, b1, w2, b2, r0)]
+        x, W1, B1, W2, B2, r = leaves
+        torch.manual_seed(4)
+        if fused:
+            y = ops.mlp_fused(x, W1, B1, W2, B2, r, p, True)
+        else:
+            ops._FC1_ENABLED["on"] = False
+            try:
+                y = ops.linear_dropout_add(ops.linear_gelu_dropout(x, W1, B1, p, True), W2, B2, r, p, True)
+            finally:
+                ops._FC1_ENABLED["on"] = True
+        y.backward(cot)
+        outs.append([y.detach()] + [t.grad for t in leaves])
+    if p == 0.0:
+        for a, b in zip(*outs):
+            assert rel_err(a, b) < TOL_BF16
+    else:
+        for a, b in zip(*outs):                               # different masks: same scale of every quantity
+            assert torch.isfinite(a.float()).all() and 0.8 < float(a.float().norm() / b.float().norm()) < 1.25
+        assert torch.equal(outs[0][6], cot)                   # d resid is the incoming gradient itself
