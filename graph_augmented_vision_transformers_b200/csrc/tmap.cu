@@ -28,6 +28,16 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64
                       uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows) {
   EncodeTiledFn enc = resolve_encode();
   GVIT_REQUIRE(enc != nullptr, GVIT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  // The driver call needs a current context on THIS thread.  PyTorch's autograd worker thread has none until its first
+  // runtime call that touches the device - if a libgvit backward is the first thing it runs, the encode failed with
+  // CUDA_ERROR_INVALID_CONTEXT (201).  cudaSetDevice binds the primary context (once per thread).
+  static thread_local bool bound = false;
+  if (!bound) {
+    int dev = 0;
+    GVIT_CHECK_CUDA(cudaGetDevice(&dev));
+    GVIT_CHECK_CUDA(cudaSetDevice(dev));          // CUDA 12: initialises and binds the primary context; not a stream operation
+    bound = true;
+  }
   GVIT_REQUIRE(box_rows >= 1 && box_rows <= 256, GVIT_ERR_SHAPE, "TMA box rows %u out of range", box_rows);
   GVIT_REQUIRE(inner % 64 == 0, GVIT_ERR_SHAPE, "TMA inner extent %llu is not a multiple of 64", (unsigned long long)inner);
   GVIT_REQUIRE((row_stride_elems * 2) % 16 == 0 && (batch_stride_elems * 2) % 16 == 0 && aligned16(base), GVIT_ERR_ALIGN,

@@ -88,3 +88,30 @@ def test_attn_drop_is_refused_loudly():
         m(torch.randn(1, 4, 64, device=DEV))
     with pytest.raises(_lib.GvitError, match="GVIT_ERR_UNSUPPORTED"):
         ops.attention_core(torch.randn(1, 4, 3 * 48, device=DEV), 1, 1.0)      # head dim 48
+
+
+@pytest.mark.parametrize("N,boost_from,boost", [(197, 100, 60.0), (197, 33, 25.0), (256, 200, 200.0), (150, 64, 8.0)])
+def test_bf16_large_logits_late_keys(N, boost_from, boost):
+    """Softmax range stress: keys from `boost_from` on are scaled so that the row maxima sit far (tens to hundreds of nats)
+    above the scores of the first keys, in some heads and not in others; forward, saved log-sum-exp (through the
+    backward) against the fp32 oracle."""
+    B, H = 2, 3
+    g = torch.Generator().manual_seed(N + int(boost))
+    qkv = torch.randn(B, N, 3, H, 64, generator=g)
+    qkv[:, boost_from:, 1] *= boost                              # later keys: logits of up to +-(4 * boost) nats
+    qkv[0, :, 0, 0] *= 0.01                                      # one head with tiny queries: its rows never re-base
+    qkv = qkv.bfloat16().float().reshape(B, N, 3 * H * 64)
+    out = ops.attention_core(qkv.to(DEV).bfloat16(), H, 0.125)
+    q, k, v = qkv.view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    want = (torch.softmax((q @ k.transpose(-1, -2)) * 0.125, dim=-1) @ v).transpose(1, 2).reshape(B, N, H * 64)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, want) < TOL_BF16
+    # the saved log-sum-exp must be the true one (the backward recomputes P from it): check through the gradient
+    x = qkv.to(DEV).bfloat16().requires_grad_(True)
+    o = ops.attention_core(x, H, 0.125)
+    cot = torch.randn(B, N, H * 64, generator=g).bfloat16()
+    o.backward(cot.to(DEV))
+    xr = qkv.clone().requires_grad_(True)
+    qr, kr, vr = xr.view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    (torch.softmax((qr @ kr.transpose(-1, -2)) * 0.125, dim=-1) @ vr).transpose(1, 2).reshape(B, N, H * 64).backward(cot.float())
+    assert rel_err(x.grad, xr.grad) < 2 * TOL_BF16              # near-one-hot rows: bf16 P / dS rounding on huge logits
