@@ -166,3 +166,25 @@ def test_colsum_workspace_covers_the_launchers_chunking():
         bound = min(1024, (12 * 148 + cb - 1) // cb + 1, max(1, (rows + 31) // 32) + 1)
         for per_sm in (6, 12):
             assert chunks(rows, D, per_sm) <= bound, (rows, D, per_sm)
+
+
+def test_product_path_never_touches_the_oracle_or_the_reference_tree():
+    """The oracle is test infrastructure: nothing under the package, src/ or the C sources may import it or read
+    /root/reference; bench.py may (cpu_baseline / --impl reference legs only) and must not import it at module level."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    offenders = []
+    for base in ("graph_augmented_vision_transformers_b200", "src", "include"):
+        for dp, _, files in os.walk(os.path.join(root, base)):
+            for f in files:
+                if not f.endswith((".py", ".cu", ".cuh", ".h")):
+                    continue
+                text = open(os.path.join(dp, f), errors="ignore").read()
+                code = "\n".join(ln for ln in text.splitlines() if not ln.lstrip().startswith(("#", "//", "*", "/*")))
+                if re.search(r"^\s*(from|import)\s+oracle\b", code, flags=re.M) or re.search(r"open\([^)]*/root/reference", code):
+                    offenders.append(os.path.join(dp, f))
+    assert not offenders, offenders
+    bench = open(os.path.join(root, "bench.py")).read()
+    top_level = [ln for ln in bench.splitlines() if re.match(r"(from|import)\s+oracle\b", ln)]
+    assert not top_level, "bench.py must import the oracle only inside its cpu_baseline / reference legs"
