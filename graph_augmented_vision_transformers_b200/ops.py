@@ -8,6 +8,10 @@ Each function here is one stage of the graph-augmented ViT hot path (SURVEY.md s
 * ``gelu_dropout``     - Mlp activation edge, nn.GELU + nn.Dropout at vit.py:84,92
 * ``knn_graph``        - a7, SURVEY.md section 9 G1-G3 (no reference symbol)
 * ``patch_graph``      - a7+a8 as one differentiable op, section 9 G0-G6 (no reference symbol)
+* ``linear`` / ``linear_gelu_dropout`` / ``linear_dropout_add`` / ``mlp_fused`` - f1, the nn.Linear layers of the block
+  (vit.py:50,52,83-94) with their edges: fused tcgen05 GEMMs for fc1, the attention projection and fc2's input gradient,
+  library GEMMs elsewhere; parameter shadows (one multi-tensor cast per step) and fp32 weight gradients
+* ``patch_embed_tokens`` - f4, PatchEmbed + CLS + pos_embed + pos_drop (vit.py:25-36, 207-212)
 
 PyTorch is plumbing only: it owns the device memory and the stream, the arithmetic runs in the CUDA
 library.  There is no fallback: a CPU tensor, an unsupported dtype or a missing ``libgvit.so`` raises.
@@ -16,6 +20,8 @@ Under ``torch.autocast`` the ops run in bf16 (fp16 autocast, which the reference
 scaling hazards).
 """
 from __future__ import annotations
+
+import os
 
 import torch
 import torch.nn.functional as F
@@ -621,9 +627,7 @@ class _MlpFused(torch.autograd.Function):
                 (dout if ctx.has_resid else None), None, None, None)
 
 
-import os as _os
-
-_MLP_FUSED = {"on": _os.environ.get("GVIT_MLP_FUSED", "1") != "0"}      # GVIT_MLP_FUSED=0: two-op composition (A/B switch)
+_MLP_FUSED = {"on": os.environ.get("GVIT_MLP_FUSED", "1") != "0"}      # GVIT_MLP_FUSED=0: two-op composition (A/B switch)
 
 
 def mlp_fused_available(x, w1, w2, resid) -> bool:
