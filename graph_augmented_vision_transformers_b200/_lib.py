@@ -7,6 +7,7 @@ the user to build it (``make`` or ``python -c 'import __graft_entry__ as g; g.bu
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 import threading
 
@@ -104,7 +105,9 @@ def call(name, *args):
         raise GvitError(name, rc, msg.decode() if msg else "")
 
 
+@functools.lru_cache(maxsize=None)
 def describe_path(op: str, dtype: int, n_tokens: int, dim: int) -> str:
+    """Which kernels a request routes to (a pure function of its arguments: cached, the operators ask on every call)."""
     buf = C.create_string_buffer(64)
     call("gvit_describe_path", op.encode(), dtype, n_tokens, dim, buf, 64)
     return buf.value.decode()
