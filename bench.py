@@ -207,7 +207,7 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
         # name: (launch fn(i), algorithmic bytes, flops, bound, launches per training step)
         "knn_fwd": (lambda i: _call("gvit_knn_fwd", _ptr(hs[i % R], off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(vals), _ptr(rnorm), st),
                     tok + B * Np * k * 8, 2.0 * B * Np * Np * D, "hbm", 12),
-        "agg_fwd": (lambda i: _call("gvit_agg_fwd", _ptr(hs[i % R]), B, Np, D, k, dt, _ptr(idxs[i % R][0]), _ptr(idxs[i % R][1]), _ptr(W), _ptr(bias), _ptr(xs[i % R]), _ptr(out), _ptr(w), _ptr(z), Np * D, st),
+        "agg_fwd": (lambda i: _call("gvit_agg_fwd", _ptr(hs[i % R]), B, Np, D, k, dt, _ptr(idxs[i % R][0]), _ptr(idxs[i % R][1]), _ptr(W), _ptr(bias), _ptr(xs[i % R]), dt, _ptr(out), _ptr(w), _ptr(z), Np * D, st),
                     3 * tok + B * Np * k * 8, 2.0 * B * Np * D * (k + D), "tensor", 12),
         "attn_fwd": (lambda i: _call("gvit_attn_fwd", _ptr(qkvs[i % 2]), B, N, H, 64, 0.125, dt, _ptr(ao), _ptr(lse), st),
                      4 * B * N * D * e + 4 * B * H * N, 4.0 * B * N * N * D, "hbm", 12),
@@ -227,7 +227,7 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
                           3 * B * N * D * e, 0.0, "hbm", 1),
         "fc1_fused": (lambda i: _call("gvit_linear_gelu_dropout_fwd", _ptr(hs[i % R]), _ptr(W1), _ptr(b1), B * N, 4 * D, D, 0.1, 1234, 0, None, dt, _ptr(u4[i % 2]), _ptr(o4), _ptr(m4), st),
                       B * N * D * e + 4 * D * D * e + 2 * B * N * 4 * D * e + B * N * 4 * D // 8, 2.0 * B * N * D * 4 * D, "tensor", 12),
-        "proj_fused": (lambda i: _call("gvit_linear_dropout_residual_fwd", _ptr(hs[i % R]), _ptr(W), _ptr(bias), _ptr(xs[i % R]), B * N, D, D, 0.1, 1234, 0, None, dt, _ptr(out), _ptr(m1), st),
+        "proj_fused": (lambda i: _call("gvit_linear_dropout_residual_fwd", _ptr(hs[i % R]), _ptr(W), _ptr(bias), _ptr(xs[i % R]), B * N, D, D, 0.1, 1234, 0, None, dt, dt, _ptr(out), _ptr(m1), st),
                        3 * B * N * D * e + D * D * e + B * N * D // 8, 2.0 * B * N * D * D, "hbm", 12),
         "fc2_bwd_fused": (lambda i: _call("gvit_linear_gelu_dropout_bwd", _ptr(hs[i % R]), _ptr(W2), _ptr(u4[i % 2]), _ptr(m4), B * N, 4 * D, D, 0.1, dt, _ptr(o4), _ptr(cs_out), _ptr(part4), st),
                           B * N * D * e + 4 * D * D * e + 2 * B * N * 4 * D * e + B * N * 4 * D // 8, 2.0 * B * N * D * 4 * D, "tensor", 12),

@@ -51,8 +51,8 @@ struct Params {
   const int32_t* idx;
   const float* vals;
   const __nv_bfloat16* bias;
-  const __nv_bfloat16* resid;
-  __nv_bfloat16* out;
+  const void* resid;                        // bf16, or fp32 when the kernel is instantiated with RES32 (fp32 residual stream)
+  void* out;                                // same type as resid
   float* w_save;
   __nv_bfloat16* z_save;
   int64_t zbs;                              // batch stride of z_save in elements (rows are D apart)
@@ -65,7 +65,9 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
-template <int KT>
+// RES32: resid / out are fp32 - the residual stream torch.autocast keeps in fp32 (vit.py:117-118 add onto an fp32 x); the
+// branch value (projection + bias) is rounded to bf16 first, exactly what `x + graph(norm_g(x))` computes under autocast.
+template <int KT, bool RES32>
 __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_constant__ CUtensorMap tm_tok,
                                                              const __grid_constant__ CUtensorMap tm_w, const Params P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -223,26 +225,37 @@ __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_consta
         fence_async_smem();
         mbar_arrive(&ctl->a_ready);
         GVIT_TR(10);
-      } else if (mt == 0 && row < D / 8) {
-        // CLS row: out[b,0,:] = resid[b,0,:] (the graph leaves CLS untouched, section 9 G0)
-        const int64_t o = (int64_t)b * (P.Np + 1) * D + row * 8;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (P.resid) v = *reinterpret_cast<const uint4*>(P.resid + o);
-        *reinterpret_cast<uint4*>(P.out + o) = v;
+      } else if (mt == 0) {
+        // CLS row: out[b,0,:] = resid[b,0,:] (the graph leaves CLS untouched, section 9 G0), 16 bytes per thread and trip
+        constexpr int EPV = RES32 ? 4 : 8;                               // elements per 16-byte vector
+        constexpr int ESZ = RES32 ? 4 : 2;
+        for (int c = row; c < D / EPV; c += 128) {
+          const int64_t o = ((int64_t)b * (P.Np + 1) * D + c * EPV) * ESZ;
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (P.resid) v = *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(P.resid) + o);
+          *reinterpret_cast<uint4*>(static_cast<uint8_t*>(P.out) + o) = v;
+        }
       }
     }
     const int ch8 = lane & 7, r8 = lane >> 3;                           // coalesced pattern: 8 lanes per 128-byte row segment
     // residual rows of this warp for output chunk n, coalesced (lane -> rows r8 + 4i, 16-byte chunk ch8)
-    auto load_resid = [&](int n, uint4 (&rr)[8]) {
+    // RES32: a 64-feature chunk is 256 bytes per row = two 128-byte halves (32 features each)
+    constexpr int NH = RES32 ? 2 : 1;
+    auto load_resid = [&](int n, uint4 (&rr)[8 * NH]) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = r8 + 4 * i;
-        rr[i] = make_uint4(0, 0, 0, 0);
-        if (P.resid && n < nslab && wrow0 + r < P.Np)
-          rr[i] = *reinterpret_cast<const uint4*>(P.resid + ((int64_t)b * (P.Np + 1) + 1 + wrow0 + r) * D + n * 64 + ch8 * 8);
-      }
+      for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r8 + 4 * i;
+          rr[hh * 8 + i] = make_uint4(0, 0, 0, 0);
+          if (P.resid && n < nslab && wrow0 + r < P.Np) {
+            const int64_t e = ((int64_t)b * (P.Np + 1) + 1 + wrow0 + r) * D + n * 64;
+            if constexpr (RES32) rr[hh * 8 + i] = *reinterpret_cast<const uint4*>(static_cast<const float*>(P.resid) + e + hh * 32 + ch8 * 4);
+            else rr[i] = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(P.resid) + e + ch8 * 8);
+          }
+        }
     };
-    uint4 rnext[8];
+    uint4 rnext[8 * NH];
     load_resid(g, rnext);                                              // first chunk of this warpgroup: in flight during Z
     // ---- Z phase (steps of parity g): fp32 staging -> packed bf16 at TMEM columns [64t, 64t + width/2);
     //      optional copy out for the backward, 64 features at a time through the warp staging
@@ -293,7 +306,7 @@ __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_consta
         }
       }
     }
-    // ---- projection epilogue (chunks of parity g): + bias + residual, bf16, coalesced through the warp staging
+    // ---- projection epilogue (chunks of parity g): + bias + residual, coalesced through the warp staging
     for (int n = g; n < nslab; n += 2) {
       const int buf = n & 1;
 #pragma unroll
@@ -301,7 +314,7 @@ __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_consta
         const int r = r8 + 4 * i;
         *reinterpret_cast<uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4)) = rnext[i];
       }
-      load_resid(n + 2, rnext);                                        // next chunk of this warpgroup: in flight meanwhile
+      if constexpr (!RES32) load_resid(n + 2, rnext);                  // next chunk of this warpgroup: in flight meanwhile
       __syncwarp();
       GVIT_TR(13);
       mbar_wait(&ctl->out_full[buf], (n >> 1) & 1);
@@ -312,29 +325,68 @@ __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_consta
       tmem_ld32(tl + T_OUT + buf * 64 + 32, v1);
       tc_fence_before();
       mbar_arrive(&ctl->out_free[buf]);
+      if constexpr (!RES32) {
+        __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(P.out);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const uint32_t off = lane * 128 + ((q ^ (lane & 7)) << 4);
-        const uint4 r4 = *reinterpret_cast<const uint4*>(stg + off);
-        const uint4 b4 = *reinterpret_cast<const uint4*>(&ctl->bias[n * 64 + q * 8]);
-        const float* vv = q < 4 ? &v0[8 * q] : &v1[8 * (q - 4)];
-        const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
-        uint32_t oo[4];
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t off = lane * 128 + ((q ^ (lane & 7)) << 4);
+          const uint4 r4 = *reinterpret_cast<const uint4*>(stg + off);
+          const uint4 b4 = *reinterpret_cast<const uint4*>(&ctl->bias[n * 64 + q * 8]);
+          const float* vv = q < 4 ? &v0[8 * q] : &v1[8 * (q - 4)];
+          const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+          uint32_t oo[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          oo[e] = pack2(vv[2 * e] + bf_lo(bb[e]) + bf_lo(rr[e]), vv[2 * e + 1] + bf_hi(bb[e]) + bf_hi(rr[e]));
-        *reinterpret_cast<uint4*>(stg + off) = make_uint4(oo[0], oo[1], oo[2], oo[3]);
-      }
-      __syncwarp();
+          for (int e = 0; e < 4; ++e)
+            oo[e] = pack2(vv[2 * e] + bf_lo(bb[e]) + bf_lo(rr[e]), vv[2 * e + 1] + bf_hi(bb[e]) + bf_hi(rr[e]));
+          *reinterpret_cast<uint4*>(stg + off) = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+        }
+        __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = r8 + 4 * i;
-        if (wrow0 + r < P.Np) {
-          const uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4));
-          *reinterpret_cast<uint4*>(P.out + ((int64_t)b * (P.Np + 1) + 1 + wrow0 + r) * D + n * 64 + ch8 * 8) = v4;
+        for (int i = 0; i < 8; ++i) {
+          const int r = r8 + 4 * i;
+          if (wrow0 + r < P.Np) {
+            const uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4));
+            *reinterpret_cast<uint4*>(outp + ((int64_t)b * (P.Np + 1) + 1 + wrow0 + r) * D + n * 64 + ch8 * 8) = v4;
+          }
+        }
+        __syncwarp();
+      } else {
+        float* outp = static_cast<float*>(P.out);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {                               // 32 features = 128 bytes of fp32 per row and half
+          if (hh == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = r8 + 4 * i;
+              *reinterpret_cast<uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4)) = rnext[8 + i];
+            }
+            load_resid(n + 2, rnext);                                  // both halves consumed: next chunk in flight
+            __syncwarp();
+          }
+          const float* vv = hh == 0 ? v0 : v1;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {                                // 4 features per 16-byte chunk
+            const uint32_t off = lane * 128 + ((q ^ (lane & 7)) << 4);
+            float4 r4 = *reinterpret_cast<const float4*>(stg + off);
+            const uint2 b2 = *reinterpret_cast<const uint2*>(&ctl->bias[n * 64 + hh * 32 + q * 4]);
+            // the branch value as the bf16 projection would store it, then the fp32 add (autocast semantics)
+            const uint32_t y01 = pack2(vv[4 * q] + bf_lo(b2.x), vv[4 * q + 1] + bf_hi(b2.x));
+            const uint32_t y23 = pack2(vv[4 * q + 2] + bf_lo(b2.y), vv[4 * q + 3] + bf_hi(b2.y));
+            r4.x += bf_lo(y01); r4.y += bf_hi(y01); r4.z += bf_lo(y23); r4.w += bf_hi(y23);
+            *reinterpret_cast<float4*>(stg + off) = r4;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = r8 + 4 * i;
+            if (wrow0 + r < P.Np) {
+              const uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4));
+              *reinterpret_cast<uint4*>(outp + ((int64_t)b * (P.Np + 1) + 1 + wrow0 + r) * D + n * 64 + hh * 32 + ch8 * 4) = v4;
+            }
+          }
+          __syncwarp();
         }
       }
-      __syncwarp();
     }
   }
   tc_fence_before();
@@ -342,13 +394,17 @@ __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_consta
   if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
-template <int KT>
-int launch(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const Params& P, int B, cudaStream_t st) {
-  GVIT_CHECK_CUDA(cudaFuncSetAttribute(agg3_tc_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+template <int KT, bool RES32>
+int launch2(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const Params& P, int B, cudaStream_t st) {
+  GVIT_CHECK_CUDA(cudaFuncSetAttribute(agg3_tc_kernel<KT, RES32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   dim3 grid((P.Np + 127) / 128, B);
-  agg3_tc_kernel<KT><<<grid, THREADS, SMEM_BYTES, st>>>(tm_tok, tm_w, P);
+  agg3_tc_kernel<KT, RES32><<<grid, THREADS, SMEM_BYTES, st>>>(tm_tok, tm_w, P);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
+}
+template <int KT>
+int launch(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const Params& P, int B, bool res32, cudaStream_t st) {
+  return res32 ? launch2<KT, true>(tm_tok, tm_w, P, B, st) : launch2<KT, false>(tm_tok, tm_w, P, B, st);
 }
 
 }  // namespace
@@ -360,7 +416,7 @@ bool agg3_tc_supported(int Np, int D, int k) {
 }
 
 int agg3_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, const float* vals, const void* Wg,
-                const void* bias, const void* resid, void* out, float* w_save, void* z_save, int64_t z_batch_stride,
+                const void* bias, const void* resid, int resid_dtype, void* out, float* w_save, void* z_save, int64_t z_batch_stride,
                 cudaStream_t st) {
   Params P;
   P.Np = Np; P.D = D; P.k = k;
@@ -368,8 +424,9 @@ int agg3_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, 
   GVIT_REQUIRE(B <= 65535, GVIT_ERR_SHAPE, "agg_fwd: batch %d exceeds the grid limit 65535", B);
   P.idx = idx; P.vals = vals;
   P.bias = static_cast<const __nv_bfloat16*>(bias);
-  P.resid = static_cast<const __nv_bfloat16*>(resid);
-  P.out = static_cast<__nv_bfloat16*>(out);
+  P.resid = resid;
+  P.out = out;
+  const bool res32 = resid_dtype == GVIT_F32;
   P.w_save = w_save;
   P.z_save = static_cast<__nv_bfloat16*>(z_save);
   P.zbs = z_batch_stride;
@@ -380,9 +437,9 @@ int agg3_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, 
   if (rc != GVIT_OK) return rc;
   rc = make_tmap_bf16_3d(&tm_w, Wg, D, D, 1, D, (uint64_t)D * D, 64);
   if (rc != GVIT_OK) return rc;
-  if (k <= 4) return launch<4>(tm_tok, tm_w, P, B, st);
-  if (k <= 8) return launch<8>(tm_tok, tm_w, P, B, st);
-  return launch<16>(tm_tok, tm_w, P, B, st);
+  if (k <= 4) return launch<4>(tm_tok, tm_w, P, B, res32, st);
+  if (k <= 8) return launch<8>(tm_tok, tm_w, P, B, res32, st);
+  return launch<16>(tm_tok, tm_w, P, B, res32, st);
 }
 
 }  // namespace gvit

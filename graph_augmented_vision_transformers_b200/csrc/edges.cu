@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256) dropout_bwd_kernel(const Tx* __restrict__
   for (int64_t i8 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i8 < n; i8 += (int64_t)gridDim.x * blockDim.x * 8) {
     float a[8];
     load8(dout + i8, a);
-    const uint32_t bits = mask[i8 >> 3];
+    const uint32_t bits = mask ? mask[i8 >> 3] : 0xffu;          // no mask (p == 0): a pure cast of the stream gradient
 #pragma unroll
     for (int t = 0; t < 8; ++t) a[t] = (bits >> t) & 1u ? a[t] * scale : 0.f;
     store8(dy + i8, a);

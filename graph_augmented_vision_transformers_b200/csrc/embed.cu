@@ -44,12 +44,13 @@ __global__ void __launch_bounds__(256) patchify_kernel(const Tin* __restrict__ i
 
 // x[b,0,:] = cls + pos[0];  x[b,n,:] = y[b,n,:] + bias + pos[n] (n >= 1);  then dropout(p).
 // y is the projection of the patch matrix over all 1+Np rows (row 0 of y is ignored).  cls / pos / bias are the fp32
-// (or T) parameters themselves: Tp.
-template <typename T, typename Tp>
+// (or T) parameters themselves: Tp.  To: the token stream's dtype - T, or fp32 over a bf16 projection (the fp32 residual
+// stream torch.autocast produces: cat / add with the fp32 cls_token / pos_embed promote, vit.py:207-211).
+template <typename T, typename Tp, typename To>
 __global__ void __launch_bounds__(256) embed_assemble_kernel(const T* __restrict__ y, const Tp* __restrict__ bias,
                                                              const Tp* __restrict__ cls, const Tp* __restrict__ pos, int B, int N,
                                                              int D, float p, uint64_t seed, uint64_t offset,
-                                                             const uint64_t* __restrict__ offset_dev, T* __restrict__ out,
+                                                             const uint64_t* __restrict__ offset_dev, To* __restrict__ out,
                                                              uint8_t* __restrict__ mask) {
   if (offset_dev) offset += __ldg(offset_dev);
   const float scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
@@ -102,18 +103,21 @@ int patchify(const void* img, int B, int C, int H, int W, int P, int in_dtype, i
 }
 
 int embed_assemble(const void* y, const void* bias, const void* cls, const void* pos, int B, int N, int D, float p,
-                   uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, int param_dtype, void* out, uint8_t* keep_mask,
-                   cudaStream_t st) {
+                   uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, int param_dtype, int out_dtype, void* out,
+                   uint8_t* keep_mask, cudaStream_t st) {
   using bf = __nv_bfloat16;
   const int64_t n8 = (int64_t)B * N * (D / 8);
-  if (dtype == GVIT_F32)
-    stream_launch(embed_assemble_kernel<float, float>, n8, st, static_cast<const float*>(y), static_cast<const float*>(bias), static_cast<const float*>(cls),
+  if (dtype == GVIT_BF16 && out_dtype == GVIT_F32)
+    stream_launch(embed_assemble_kernel<bf, float, float>, n8, st, static_cast<const bf*>(y), static_cast<const float*>(bias), static_cast<const float*>(cls),
+                                                                  static_cast<const float*>(pos), B, N, D, p, seed, offset, offset_dev, static_cast<float*>(out), keep_mask);
+  else if (dtype == GVIT_F32)
+    stream_launch(embed_assemble_kernel<float, float, float>, n8, st, static_cast<const float*>(y), static_cast<const float*>(bias), static_cast<const float*>(cls),
                                                               static_cast<const float*>(pos), B, N, D, p, seed, offset, offset_dev, static_cast<float*>(out), keep_mask);
   else if (param_dtype == GVIT_F32)
-    stream_launch(embed_assemble_kernel<bf, float>, n8, st, static_cast<const bf*>(y), static_cast<const float*>(bias), static_cast<const float*>(cls),
+    stream_launch(embed_assemble_kernel<bf, float, bf>, n8, st, static_cast<const bf*>(y), static_cast<const float*>(bias), static_cast<const float*>(cls),
                                                            static_cast<const float*>(pos), B, N, D, p, seed, offset, offset_dev, static_cast<bf*>(out), keep_mask);
   else
-    stream_launch(embed_assemble_kernel<bf, bf>, n8, st, static_cast<const bf*>(y), static_cast<const bf*>(bias), static_cast<const bf*>(cls),
+    stream_launch(embed_assemble_kernel<bf, bf, bf>, n8, st, static_cast<const bf*>(y), static_cast<const bf*>(bias), static_cast<const bf*>(cls),
                                                         static_cast<const bf*>(pos), B, N, D, p, seed, offset, offset_dev, static_cast<bf*>(out), keep_mask);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;

@@ -71,9 +71,10 @@ int gvit_agg_gather_fwd(const void* p, int64_t batch_stride, int64_t row_stride,
 }
 
 int gvit_agg_fwd(const void* h, int B, int Np, int D, int k, int dtype, const int32_t* idx, const float* vals,
-                 const void* Wg, const void* bias, const void* resid, void* out, float* w_save, void* z_save,
+                 const void* Wg, const void* bias, const void* resid, int resid_dtype, void* out, float* w_save, void* z_save,
                  int64_t z_batch_stride, void* stream) {
   TRY(check_dtype(dtype, "agg_fwd"));
+  TRY(check_dtype(resid_dtype, "agg_fwd"));
   GVIT_REQUIRE(h && idx && vals && Wg && out, GVIT_ERR_SHAPE, "agg_fwd: null pointer");
   GVIT_REQUIRE(B >= 1 && Np >= 1 && k >= 1 && k <= GVIT_MAX_K && k <= Np, GVIT_ERR_SHAPE, "agg_fwd: bad sizes B=%d Np=%d k=%d", B, Np, k);
   GVIT_REQUIRE(dtype == GVIT_BF16, GVIT_ERR_UNSUPPORTED,
@@ -86,7 +87,9 @@ int gvit_agg_fwd(const void* h, int B, int Np, int D, int k, int dtype, const in
                "agg_fwd: z_batch_stride=%lld must be >= Np*D and a multiple of 8", (long long)z_batch_stride);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (agg3_tc_supported(Np, D, k))
-    return agg3_fwd_tc(h, B, Np, D, k, idx, vals, Wg, bias, resid, out, w_save, z_save, z_batch_stride, st);
+    return agg3_fwd_tc(h, B, Np, D, k, idx, vals, Wg, bias, resid, resid_dtype, out, w_save, z_save, z_batch_stride, st);
+  GVIT_REQUIRE(resid_dtype == GVIT_BF16, GVIT_ERR_UNSUPPORTED,
+               "agg_fwd: an fp32 residual stream (resid / out) is fused for D <= 768 only (D=%d): add the residual on the host side", D);
   return agg_fwd_tc(h, B, Np, D, k, idx, vals, Wg, bias, resid, out, w_save, z_save, z_batch_stride, st);
 }
 
@@ -197,8 +200,9 @@ static int check_colsum_args(const char* who, int64_t n, int D, const float* col
 int gvit_dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, int y_dtype, void* dy,
                      int D, float* colsum_out, float* partial_ws, void* stream) {
   TRY(check_ln_pair(dtype, y_dtype, "dropout_bwd"));
-  GVIT_REQUIRE(dout && dy && (keep_mask || (colsum_out && p == 0.f)), GVIT_ERR_SHAPE, "dropout_bwd: null pointer");
-  GVIT_REQUIRE(n >= 8 && n % 8 == 0 && p >= 0.f && p < 1.f && (p > 0.f || colsum_out), GVIT_ERR_SHAPE, "dropout_bwd: n=%lld p=%f", (long long)n, p);
+  GVIT_REQUIRE(dout && dy && (keep_mask || p == 0.f), GVIT_ERR_SHAPE, "dropout_bwd: null pointer (keep_mask is required when p > 0)");
+  GVIT_REQUIRE(n >= 8 && n % 8 == 0 && p >= 0.f && p < 1.f && (p > 0.f || colsum_out || dtype != y_dtype), GVIT_ERR_SHAPE,
+               "dropout_bwd: n=%lld p=%f (p == 0 without column sums is only meaningful as the fp32 -> bf16 cast)", (long long)n, p);
   GVIT_REQUIRE(aligned16(dout) && aligned16(dy), GVIT_ERR_ALIGN, "dropout_bwd: 16-byte alignment required");
   TRY(check_colsum_args("dropout_bwd", n, D, colsum_out, partial_ws));
   return dropout_bwd(dout, keep_mask, n, p, dtype, y_dtype, dy, D, colsum_out, partial_ws, static_cast<cudaStream_t>(stream));
@@ -241,9 +245,10 @@ int gvit_linear_gelu_dropout_fwd(const void* x, const void* w, const void* bias,
 }
 
 int gvit_linear_dropout_residual_fwd(const void* x, const void* w, const void* bias, const void* resid, int64_t M, int N, int K, float p,
-                                     uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, void* out,
+                                     uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, int resid_dtype, void* out,
                                      uint8_t* keep_mask, void* stream) {
   TRY(check_dtype(dtype, "linear_dropout_residual_fwd"));
+  TRY(check_dtype(resid_dtype, "linear_dropout_residual_fwd"));
   GVIT_REQUIRE(x && w && resid && out, GVIT_ERR_SHAPE, "linear_dropout_residual_fwd: null pointer");
   GVIT_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || keep_mask), GVIT_ERR_SHAPE, "linear_dropout_residual_fwd: p=%f (keep_mask required when p > 0)", p);
   GVIT_REQUIRE(dtype == GVIT_BF16 && fc1_tc_supported(M, N, K), GVIT_ERR_UNSUPPORTED,
@@ -252,7 +257,8 @@ int gvit_linear_dropout_residual_fwd(const void* x, const void* w, const void* b
   GVIT_REQUIRE(aligned16(x) && aligned16(w) && aligned16(resid) && aligned16(out) && (!bias || aligned16(bias)) &&
                (!keep_mask || (reinterpret_cast<uintptr_t>(keep_mask) & 3u) == 0), GVIT_ERR_ALIGN,
                "linear_dropout_residual_fwd: tensors must be 16-byte aligned (keep_mask 4-byte)");
-  return linear_dropout_residual_fwd_tc(x, w, bias, resid, M, N, K, p, seed, offset, offset_dev, out, keep_mask, static_cast<cudaStream_t>(stream));
+  return linear_dropout_residual_fwd_tc(x, w, bias, resid, M, N, K, p, seed, offset, offset_dev, resid_dtype, out, keep_mask,
+                                        static_cast<cudaStream_t>(stream));
 }
 
 int64_t gvit_linear_gelu_dropout_bwd_ws_rows(int64_t M) { return fc2_bwd_partial_rows(M); }
@@ -283,17 +289,21 @@ int gvit_patchify(const void* img, int B, int C, int H, int W, int P, int in_dty
 }
 
 int gvit_embed_assemble(const void* y, const void* bias, const void* cls, const void* pos, int B, int N, int D, float p,
-                        uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, int param_dtype, void* out,
+                        uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, int param_dtype, int out_dtype, void* out,
                         uint8_t* keep_mask, void* stream) {
   TRY(check_dtype(dtype, "embed_assemble"));
   TRY(check_dtype(param_dtype, "embed_assemble"));
+  TRY(check_dtype(out_dtype, "embed_assemble"));
+  GVIT_REQUIRE(out_dtype == dtype || (out_dtype == GVIT_F32 && param_dtype == GVIT_F32), GVIT_ERR_DTYPE,
+               "embed_assemble: out is of y's dtype, or fp32 (fp32 residual stream) with fp32 parameters");
   GVIT_REQUIRE(y && cls && pos && out, GVIT_ERR_SHAPE, "embed_assemble: null pointer");
   GVIT_REQUIRE(param_dtype == dtype || param_dtype == GVIT_F32, GVIT_ERR_DTYPE, "embed_assemble: parameters must be fp32 or the token dtype");
   GVIT_REQUIRE(B >= 1 && N >= 2 && D >= 8 && D % 8 == 0, GVIT_ERR_SHAPE, "embed_assemble: bad sizes B=%d N=%d D=%d", B, N, D);
   GVIT_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || keep_mask), GVIT_ERR_SHAPE, "embed_assemble: p=%f (keep_mask required when p > 0)", p);
   GVIT_REQUIRE(aligned16(y) && aligned16(out) && aligned16(cls) && aligned16(pos) && (!bias || aligned16(bias)), GVIT_ERR_ALIGN,
                "embed_assemble: 16-byte alignment required");
-  return embed_assemble(y, bias, cls, pos, B, N, D, p, seed, offset, offset_dev, dtype, param_dtype, out, keep_mask, static_cast<cudaStream_t>(stream));
+  return embed_assemble(y, bias, cls, pos, B, N, D, p, seed, offset, offset_dev, dtype, param_dtype, out_dtype, out, keep_mask,
+                        static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -30,7 +30,7 @@ int knn_fwd_tc(const Tokens& p, int k, int32_t* idx, float* vals, float* rnorm, 
 bool agg_tc_supported(int Np, int D, int k);    // v2 kernel (agg_tc.cu): D up to 1024
 bool agg3_tc_supported(int Np, int D, int k);   // v3 kernel (agg3_tc.cu): whole Z tile resident in TMEM, D <= 768
 int agg3_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, const float* vals, const void* Wg,
-                const void* bias, const void* resid, void* out, float* w_save, void* z_save, int64_t z_batch_stride,
+                const void* bias, const void* resid, int resid_dtype, void* out, float* w_save, void* z_save, int64_t z_batch_stride,
                 cudaStream_t st);
 int agg_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, const float* vals, const void* Wg,
                const void* bias, const void* resid, void* out, float* w_save, void* z_save, int64_t z_batch_stride,
@@ -67,7 +67,8 @@ int fc1_gelu_dropout_fwd_tc(const void* x, const void* w, const void* bias, int6
                             uint64_t offset, const uint64_t* offset_dev, void* u, void* out, uint8_t* mask, cudaStream_t st);
 
 int linear_dropout_residual_fwd_tc(const void* x, const void* w, const void* bias, const void* resid, int64_t M, int N, int K, float p,
-                                   uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* out, uint8_t* mask, cudaStream_t st);
+                                   uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int resid_dtype, void* out, uint8_t* mask,
+                                   cudaStream_t st);
 
 int64_t fc2_bwd_partial_rows(int64_t M);
 int linear_gelu_dropout_bwd_tc(const void* dout, const void* w2, const void* u, const uint8_t* mask, int64_t M, int N, int K, float p,
@@ -76,7 +77,7 @@ int linear_gelu_dropout_bwd_tc(const void* dout, const void* w2, const void* u, 
 // ---- token prologue : embed.cu
 int patchify(const void* img, int B, int C, int H, int W, int P, int in_dtype, int out_dtype, void* out, cudaStream_t st);
 int embed_assemble(const void* y, const void* bias, const void* cls, const void* pos, int B, int N, int D, float p,
-                   uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, int param_dtype, void* out, uint8_t* keep_mask,
-                   cudaStream_t st);
+                   uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, int param_dtype, int out_dtype, void* out,
+                   uint8_t* keep_mask, cudaStream_t st);
 
 }  // namespace gvit

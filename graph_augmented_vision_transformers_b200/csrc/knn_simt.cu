@@ -1,8 +1,13 @@
 // knn_simt.cu - graph construction G1-G3 with exact fp32 FMA arithmetic.
 //
-// The fp32 parity path: every similarity is one sequential FMA chain over d = 0..D-1, in the same
-// order for every (i, j), so duplicated token rows give bit-equal similarities and the strict-">"
-// insertion below resolves them to the lowest index, exactly like the oracle's stable sort.
+// The fp32 parity path follows the STRICT specification oracle/knn_strict.c (GRAPH_SPEC_VERSION 2) operation by
+// operation, so neighbour indices AND similarities are bit-identical to it on every row:
+//   G1  ss_i = sequential FMA chain over d of p_id^2;  n_i = max(sqrt(ss_i), 1e-12);  ph_id = p_id / n_i  (IEEE division)
+//   G2  S_ij = sequential FMA chain over d = 0..D-1 of ph_id * ph_jd - the same order for every (i, j), so S is exactly
+//       symmetric and duplicated token rows give bit-equal similarities
+//   G3  strict-">" insertion while sweeping the columns in ascending order: ties resolve to the lowest index, exactly
+//       like the oracle's stable sort.
+// (Compiled without --use_fast_math: `/` and sqrtf are the correctly rounded IEEE operations.)
 // S is never written to HBM: a CTA owns 64 rows of one image, sweeps the columns in 64-wide tiles
 // and keeps a running top-k per row in shared memory.
 #include <float.h>
@@ -15,22 +20,33 @@ namespace {
 constexpr int TM = 64, TN = 64, BK = 16, PAD = 4;
 constexpr int KSTRIDE = GVIT_MAX_K + 1;  // +1: row-strided top-k lists would otherwise share a bank
 
+// ss_i of G1: ONE thread per token row, sequential FMA chain over d (the order the specification fixes)
 template <typename T>
-__global__ void __launch_bounds__(256) rownorm_kernel(const T* __restrict__ p, int64_t bs, int64_t rs, int B, int Np,
-                                                      int D, float* __restrict__ rnorm) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= B * Np) return;
-  const int b = warp / Np, i = warp % Np;
+__global__ void __launch_bounds__(128) sumsq_kernel(const T* __restrict__ p, int64_t bs, int64_t rs, int B, int Np, int D,
+                                                    float* __restrict__ ss_out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= B * Np) return;
+  const int b = r / Np, i = r % Np;
   const T* row = p + b * bs + i * rs;
   float acc = 0.f;
-  for (int d0 = lane * 8; d0 < D; d0 += 256) {
+  int d = 0;
+  for (; d + 8 <= D; d += 8) {
     float v[8];
-    load8(row + d0, v);
+    load8(row + d, v);
 #pragma unroll
     for (int t = 0; t < 8; ++t) acc = fmaf(v[t], v[t], acc);
   }
-  acc = warp_sum(acc);
-  if (lane == 0) rnorm[warp] = 1.0f / fmaxf(sqrtf(acc), 1e-12f);
+  for (; d < D; ++d) { const float v = to_f32(row[d]); acc = fmaf(v, v, acc); }
+  ss_out[r] = acc;
+}
+
+// n_i = max(sqrt(ss_i), eps) (F.normalize's clamp)
+__device__ __forceinline__ float norm_of(float ss) { return fmaxf(sqrtf(ss), 1e-12f); }
+
+// the ABI's rnorm output: 1 / n_i, written in place over ss once every similarity tile has been formed
+__global__ void __launch_bounds__(256) rnorm_finish_kernel(float* __restrict__ r, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) r[i] = 1.0f / norm_of(r[i]);
 }
 
 template <typename T>
@@ -50,7 +66,7 @@ __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, flo
 
 template <typename T>
 __global__ void __launch_bounds__(256) sim_topk_kernel(const T* __restrict__ p, int64_t bs, int64_t rs, int Np, int D,
-                                                       int k, const float* __restrict__ rnorm,
+                                                       int k, const float* __restrict__ sumsq,
                                                        int32_t* __restrict__ idx, float* __restrict__ vals) {
   __shared__ float As[BK][TM + PAD];
   __shared__ float Bs[BK][TN + PAD];
@@ -61,18 +77,22 @@ __global__ void __launch_bounds__(256) sim_topk_kernel(const T* __restrict__ p, 
   const int b = blockIdx.y, r0 = blockIdx.x * TM, tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const T* img = p + b * bs;
-  const float* rn = rnorm + (int64_t)b * Np;
+  const float* ss = sumsq + (int64_t)b * Np;
 
   if (tid < TM)
     for (int s = 0; s < k; ++s) { topv[tid][s] = -FLT_MAX; topi[tid][s] = 0x7fffffff; }
 
   const int lrow = tid >> 2, lk = (tid & 3) * 4;   // tile loader: 64 rows x 16 k, 4 elements per thread
+  const float na = r0 + lrow < Np ? norm_of(ss[r0 + lrow]) : 1.f;
   for (int c0 = 0; c0 < Np; c0 += TN) {
+    const float nb = c0 + lrow < Np ? norm_of(ss[c0 + lrow]) : 1.f;
     float acc[4][4] = {};
     for (int k0 = 0; k0 < D; k0 += BK) {
       float a[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
       if (r0 + lrow < Np && k0 + lk < D) load4<T>(img + (int64_t)(r0 + lrow) * rs + k0 + lk, a);
       if (c0 + lrow < Np && k0 + lk < D) load4<T>(img + (int64_t)(c0 + lrow) * rs + k0 + lk, bb);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { a[t] = a[t] / na; bb[t] = bb[t] / nb; }   // G1: normalise FIRST (IEEE division)
       __syncthreads();   // previous tile fully consumed
 #pragma unroll
       for (int t = 0; t < 4; ++t) { As[lk + t][lrow] = a[t]; Bs[lk + t][lrow] = bb[t]; }
@@ -90,12 +110,10 @@ __global__ void __launch_bounds__(256) sim_topk_kernel(const T* __restrict__ p, 
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int r = r0 + ty * 4 + i;
-      const float rni = r < Np ? rn[r] : 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int c = c0 + tx * 4 + j;
-        Ss[ty * 4 + i][tx * 4 + j] = c < Np ? (acc[i][j] * rni) * rn[c] : -FLT_MAX;
+        Ss[ty * 4 + i][tx * 4 + j] = c < Np ? acc[i][j] : -FLT_MAX;
       }
     }
     __syncthreads();
@@ -126,10 +144,12 @@ template <typename T>
 int launch(const Tokens& t, int k, int32_t* idx, float* vals, float* rnorm, cudaStream_t st) {
   const T* p = static_cast<const T*>(t.ptr);
   const int rows = t.B * t.Np;
-  rownorm_kernel<T><<<(rows + 7) / 8, 256, 0, st>>>(p, t.batch_stride, t.row_stride, t.B, t.Np, t.D, rnorm);
+  sumsq_kernel<T><<<(rows + 127) / 128, 128, 0, st>>>(p, t.batch_stride, t.row_stride, t.B, t.Np, t.D, rnorm);   // rnorm holds ss_i for now
   GVIT_CHECK_LAUNCH();
   dim3 grid((t.Np + TM - 1) / TM, t.B);
   sim_topk_kernel<T><<<grid, 256, 0, st>>>(p, t.batch_stride, t.row_stride, t.Np, t.D, k, rnorm, idx, vals);
+  GVIT_CHECK_LAUNCH();
+  rnorm_finish_kernel<<<(rows + 255) / 256, 256, 0, st>>>(rnorm, rows);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }

@@ -81,7 +81,10 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
-template <int MODE>
+// RES32 (MODE 1 only): the residual input and the output are fp32 - the residual stream torch.autocast keeps in fp32
+// (vit.py:207-211,117-118: cat / add with the fp32 cls_token / pos_embed promote) - while the branch value is still
+// rounded to bf16 first, exactly what `x + proj_drop(proj(o))` computes under autocast.
+template <int MODE, bool RES32 = false>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gelu_dropout_tc_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                          const __grid_constant__ CUtensorMap tm_w,
                                                                          const Params P) {
@@ -301,7 +304,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
         if constexpr (MODE == 0) {
           stage(upk);
           flush(P.u, wrow0, col0);                                     // pre-activation tile
-        } else {
+        } else if constexpr (!RES32) {
           // residual tile: coalesced global -> staging (the store pattern in reverse), then every lane reads its row
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -341,6 +344,46 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
             }
           }
           keep = ~bor;                                                 // r >= th
+        }
+        if constexpr (MODE == 1 && RES32) {
+          // fp32 stream: 16 columns (64 bytes) at a time through the same staging tile - coalesced residual load, every lane
+          // picks up its row, adds keep * scale * y, writes its row back, coalesced store
+          const float* resid32 = reinterpret_cast<const float*>(P.u);
+          float* out32 = reinterpret_cast<float*>(P.out);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int c16 = col0 + hh * 16;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = r4 + 8 * i;
+              uint4 v4 = make_uint4(0, 0, 0, 0);
+              if (wrow0 + r < P.M) v4 = *reinterpret_cast<const uint4*>(resid32 + (wrow0 + r) * P.N + c16 + ch4 * 4);
+              *reinterpret_cast<uint4*>(stg + r * 64 + ((ch4 ^ ((r >> 1) & 3)) << 4)) = v4;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4 r4v = *reinterpret_cast<const float4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4));
+              const uint32_t y01 = upk[8 * hh + 2 * q], y23 = upk[8 * hh + 2 * q + 1];
+              const int bit = 16 * hh + 4 * q;
+              r4v.x += (keep >> bit) & 1u ? bf_lo(y01) * scale : 0.f;
+              r4v.y += (keep >> (bit + 1)) & 1u ? bf_hi(y01) * scale : 0.f;
+              r4v.z += (keep >> (bit + 2)) & 1u ? bf_lo(y23) * scale : 0.f;
+              r4v.w += (keep >> (bit + 3)) & 1u ? bf_hi(y23) * scale : 0.f;
+              *reinterpret_cast<float4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = r4v;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = r4 + 8 * i;
+              if (wrow0 + r < P.M)
+                *reinterpret_cast<uint4*>(out32 + (wrow0 + r) * P.N + c16 + ch4 * 4) =
+                    *reinterpret_cast<const uint4*>(stg + r * 64 + ((ch4 ^ ((r >> 1) & 3)) << 4));
+            }
+            __syncwarp();
+          }
+          if (P.p > 0.f && row < P.M) *reinterpret_cast<uint32_t*>(P.mask + ((row * P.N + col0) >> 3)) = keep;
+          continue;
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {                                  // 8 columns per step
@@ -396,7 +439,7 @@ __global__ void __launch_bounds__(256) partial_colsum_kernel(const float* __rest
 
 bool fc1_tc_supported(int64_t M, int N, int K) { return M >= 1 && N >= BN && N % BN == 0 && K >= BK && K % BK == 0; }
 
-template <int MODE>
+template <int MODE, bool RES32 = false>
 static int fused_linear_launch(const void* x, const void* w, const void* bias, int64_t M, int N, int K, float p, uint64_t seed,
                                uint64_t offset, const uint64_t* offset_dev, void* u_or_resid, void* out, uint8_t* mask,
                                cudaStream_t st, float* partial = nullptr) {
@@ -414,7 +457,7 @@ static int fused_linear_launch(const void* x, const void* w, const void* bias, i
     P.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
     P.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
   }
-  GVIT_CHECK_CUDA(cudaFuncSetAttribute(fc1_gelu_dropout_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  GVIT_CHECK_CUDA(cudaFuncSetAttribute(fc1_gelu_dropout_tc_kernel<MODE, RES32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   const int64_t ngroups = (((M + BM - 1) / BM + CL - 1) / CL) * (N / BN);
   int max_clusters = 0;
   {
@@ -427,14 +470,14 @@ static int fused_linear_launch(const void* x, const void* w, const void* bias, i
     attr.val.clusterDim.x = CL; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, fc1_gelu_dropout_tc_kernel<MODE>, &cfg) != cudaSuccess || max_clusters < 1) {
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, fc1_gelu_dropout_tc_kernel<MODE, RES32>, &cfg) != cudaSuccess || max_clusters < 1) {
       (void)cudaGetLastError();
       max_clusters = num_sms() / CL;
     }
   }
   const int64_t want = CL * ngroups, cap = (int64_t)CL * max_clusters;
   const int grid = (int)(want < cap ? want : cap);                  // whole, co-resident clusters: a persistent grid
-  fc1_gelu_dropout_tc_kernel<MODE><<<grid, THREADS, SMEM_BYTES, st>>>(tm_x, tm_w, P);
+  fc1_gelu_dropout_tc_kernel<MODE, RES32><<<grid, THREADS, SMEM_BYTES, st>>>(tm_x, tm_w, P);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }
@@ -445,7 +488,10 @@ int fc1_gelu_dropout_fwd_tc(const void* x, const void* w, const void* bias, int6
 }
 
 int linear_dropout_residual_fwd_tc(const void* x, const void* w, const void* bias, const void* resid, int64_t M, int N, int K, float p,
-                                   uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* out, uint8_t* mask, cudaStream_t st) {
+                                   uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int resid_dtype, void* out, uint8_t* mask,
+                                   cudaStream_t st) {
+  if (resid_dtype == GVIT_F32)
+    return fused_linear_launch<1, true>(x, w, bias, M, N, K, p, seed, offset, offset_dev, const_cast<void*>(resid), out, mask, st);
   return fused_linear_launch<1>(x, w, bias, M, N, K, p, seed, offset, offset_dev, const_cast<void*>(resid), out, mask, st);
 }
 

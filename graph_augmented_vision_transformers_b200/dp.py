@@ -55,6 +55,8 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None):
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src=src, group=group)
+    from . import ops
+    ops.invalidate_shadows()       # `.data` writes do not move `_version`: the 16-bit parameter shadows are stale now
 
 
 class GradSync:

@@ -32,8 +32,9 @@ class DynamicWeightedLoss(nn.Module):
         log_neg = torch.log((1.0 - prob).clamp(min=1e-8))
         asl = -(targets * log_pos * (1.0 - prob) + (1.0 - targets) * log_neg * prob.pow(4)).mean()
         total = mix[0] * wbce + mix[1] * focal + mix[2] * asl
-        return total, {"wbce": wbce.detach(), "focal": focal.detach(), "asl": asl.detach(),
-                       "weights": mix.detach()}
+        # exactly the reference's key set (losses.py:62-66): Trainer.train_epoch appends `.item()` of every entry to lists
+        # pre-seeded with these three keys (trainer.py:129-130); the mixing weights are exposed by get_loss_weights()
+        return total, {"wbce": wbce.detach(), "focal": focal.detach(), "asl": asl.detach()}
 
     def get_loss_weights(self):
         """The current mixing weights as a numpy array (losses.py:70-76)."""

@@ -131,9 +131,16 @@ class PatchGraphLayer(nn.Module):
             raise ValueError(f"unknown graph mode {mode!r}")
         self.k, self.mode = k, mode
         self.proj = nn.Linear(dim, dim)
+        # parity instrumentation (tests): when set, every forward keeps the tokens it saw and the adjacency it built
+        self.record_graph = False
+        self.last_tokens = self.last_idx = self.last_vals = None
 
     def forward(self, h, resid=None):
         if self.mode == "knn":
+            if self.record_graph:
+                out, idx, vals = ops.patch_graph(h, self.proj.weight, self.proj.bias, self.k, resid=resid, return_graph=True)
+                self.last_tokens, self.last_idx, self.last_vals = h.detach(), idx, vals
+                return out
             return ops.patch_graph(h, self.proj.weight, self.proj.bias, self.k, resid=resid)
         y = _dense_graph(h, self.proj.weight, self.proj.bias)
         return y if resid is None else resid + y
@@ -217,8 +224,12 @@ class PatchEmbed(nn.Module):
 class VisionTransformer(nn.Module):
     def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=14, embed_dim=768, depth=12,
                  num_heads=12, mlp_ratio=4., qkv_bias=True, drop_rate=0., attn_drop_rate=0., drop_path_rate=0., *,
-                 graph_mode=None, graph_k=8, graph_every=1, fp32_residual=False):
+                 graph_mode=None, graph_k=8, graph_every=1, fp32_residual=True):
         super().__init__()
+        # Residual-stream dtype under autocast.  True (default) = torch.autocast's own semantics for the reference model:
+        # cat / add with the fp32 cls_token and pos_embed promote the stream to fp32 (vit.py:207-211) and every
+        # `x + branch` keeps it there (vit.py:117-118); branches compute in bf16.  False = opt-in bf16 stream (half the
+        # bytes on every LayerNorm / residual edge, ~2x the rounding drift - tests/test_gpu_model.py pins both).
         self.fp32_residual = fp32_residual
         self.num_classes = num_classes
         self.num_features = self.embed_dim = embed_dim
@@ -273,24 +284,24 @@ class VisionTransformer(nn.Module):
 
     def _prologue_fusable(self, x):
         pe = self.patch_embed
-        return (x.is_cuda and not self.fp32_residual and not _hooked(pe) and not _hooked(pe.proj) and not _hooked(self.pos_drop)
+        return (x.is_cuda and not _hooked(pe) and not _hooked(pe.proj) and not _hooked(self.pos_drop)
                 and tuple(x.shape[-2:]) == pe.img_size and ops.patch_embed_supported(x, pe.proj.weight))
 
     def forward_features(self, x):
         if x.is_cuda and torch.is_autocast_enabled("cuda"):
-            # one multi-tensor cast of the fp32 master parameters per step instead of one `.to()` per use
-            ops.refresh_shadows(self._parameters_for_shadow(), torch.bfloat16)
+            # one multi-tensor cast of the fp32 master parameters per forward instead of one `.to()` per use; unconditional,
+            # because `.data` writes (EMA, clamping, dist.broadcast(p.data)) change a parameter without moving `_version`
+            ops.refresh_shadows(self._parameters_for_shadow(), torch.bfloat16, force=True)
         if self._prologue_fusable(x):
             # vit.py:203-212 in three launches: patchify, projection GEMM, (bias + CLS + pos_embed + pos_drop)
             x = ops.patch_embed_tokens(x, self.patch_embed.proj.weight, self.patch_embed.proj.bias, self.cls_token,
-                                       self.pos_embed, self.pos_drop.p, self.training)
+                                       self.pos_embed, self.pos_drop.p, self.training, fp32_stream=self.fp32_residual)
             for blk in self.blocks:
                 x = blk(x)
             return self.norm(x[:, 0])
         x = self.patch_embed(x)
-        # Residual-stream dtype: by default the stream follows the compute dtype (bf16 under autocast - half the
-        # bytes on every LayerNorm / residual edge).  fp32_residual=True keeps torch.autocast's own behaviour,
-        # where cat / add promote the stream to the fp32 of cls_token and pos_embed (vit.py:207-211).
+        # fp32_residual=True keeps torch.autocast's behaviour, where cat / add promote the stream to the fp32 of
+        # cls_token and pos_embed (vit.py:207-211); False lets the stream follow the compute dtype.
         if self.fp32_residual:
             x = x.float()
         x = torch.cat((self.cls_token.expand(x.shape[0], -1, -1).to(x.dtype), x), dim=1)

@@ -64,10 +64,23 @@ def _dtype_code(t: torch.Tensor) -> int:
 
 
 def _check_cuda(*tensors):
+    """Every tensor argument on ONE CUDA device, and that device current: the C side launches on the current device's
+    stream and builds its TMA descriptors there (one process per GPU) - a model on cuda:1 under a current
+    device cuda:0 would otherwise launch against foreign pointers with no stream ordering."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("libgvit operators run on CUDA tensors only (there is no CPU fallback); "
                                f"got a tensor on {t.device}")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"libgvit operators need all tensors on one device; got {dev} and {t.device}")
+    if dev is not None and dev.index != torch.cuda.current_device():
+        raise RuntimeError(f"libgvit operators run on the CURRENT CUDA device (cuda:{torch.cuda.current_device()}); the tensors "
+                           f"are on {dev} - wrap the call in `with torch.cuda.device({dev.index}):` or torch.cuda.set_device")
 
 
 def _stream():
@@ -106,8 +119,13 @@ def invalidate_shadows() -> None:
 
 
 
-def refresh_shadows(params, dtype: torch.dtype) -> None:
-    """Bring the `dtype` shadows of `params` up to date with one multi-tensor copy (stale or missing ones only)."""
+def refresh_shadows(params, dtype: torch.dtype, force: bool = False) -> None:
+    """Bring the `dtype` shadows of `params` up to date with one multi-tensor copy.
+
+    force=False copies stale or missing shadows only, where "stale" is judged by `_version`, `data_ptr` and the epoch of
+    `invalidate_shadows` - which in-place writes through `.data` (EMA, clamping, `dist.broadcast(p.data)`) do NOT move.
+    force=True re-copies every shadow (same buffers): the model's forward uses it, so a shadow can never outlive a
+    parameter update however it was made (0.17 GB read + 0.17 GB written for ViT-B: ~60 us per forward)."""
     import weakref
     src, dst = [], []
     for prm in params:
@@ -115,7 +133,7 @@ def refresh_shadows(params, dtype: torch.dtype) -> None:
             continue
         e = _SHADOWS.get(id(prm))
         if e is not None and e[0]() is prm and e[3].dtype == dtype and e[3].shape == prm.shape:
-            if e[1] == prm._version and e[2] == prm.data_ptr() and e[4] == _SHADOW_EPOCH["n"]:
+            if not force and e[1] == prm._version and e[2] == prm.data_ptr() and e[4] == _SHADOW_EPOCH["n"]:
                 continue
             sh = e[3]
         else:
@@ -482,14 +500,15 @@ class _LinearDropoutAdd(torch.autograd.Function):
         ctx.w_dtype = weight.dtype
         weight = _shadow(weight, x.dtype)
         N, K = weight.shape
-        if (x.dtype == torch.bfloat16 and resid is not None and resid.dtype == torch.bfloat16 and K <= _FUSED_RESID_MAX_K
+        if (x.dtype == torch.bfloat16 and resid is not None and K <= _FUSED_RESID_MAX_K
                 and fused_fc1_available(N, K) and x.is_contiguous()):
-            # proj + proj_drop + residual add as ONE tcgen05 GEMM (its main loop is L2-bound, so only while K is small)
+            # proj + proj_drop + residual add as ONE tcgen05 GEMM (its main loop is L2-bound, so only while K is small);
+            # resid / out are bf16, or fp32 when the residual stream is kept in fp32 (autocast semantics)
             M = x.numel() // K
             out = torch.empty_like(resid)
             mask = torch.empty(M * N // 8, dtype=torch.uint8, device=x.device) if p > 0 else None
             _call("gvit_linear_dropout_residual_fwd", _ptr(x), _ptr(weight), _ptr(_shadow(bias, x.dtype)), _ptr(resid), M, N, K,
-                  float(p), int(seed), 0, _rng_offset_ptr(), GVIT_BF16, _ptr(out), _ptr(mask), _stream())
+                  float(p), int(seed), 0, _rng_offset_ptr(), GVIT_BF16, _dtype_code(resid), _ptr(out), _ptr(mask), _stream())
             y_dtype = x.dtype
         else:
             y = F.linear(x, weight, _shadow(bias, x.dtype))
@@ -631,10 +650,12 @@ _MLP_FUSED = {"on": os.environ.get("GVIT_MLP_FUSED", "1") != "0"}      # GVIT_ML
 
 
 def mlp_fused_available(x, w1, w2, resid) -> bool:
-    """True when the whole-Mlp node applies: bf16 compute, hidden width a multiple of 256, widths multiples of 64."""
+    """True when the whole-Mlp node applies: bf16 compute, hidden width a multiple of 256, widths multiples of 64 (the
+    residual stream may be bf16 or fp32)."""
     dt = _autocast_dtype(x)
     return (_MLP_FUSED["on"] and dt == torch.bfloat16 and x.is_cuda and w1.dim() == 2 and w2.dim() == 2
-            and w2.shape[1] == w1.shape[0] and w2.shape[0] % 8 == 0 and (resid is None or resid.dtype == torch.bfloat16)
+            and w2.shape[1] == w1.shape[0] and w2.shape[0] % 8 == 0
+            and (resid is None or resid.dtype in (torch.bfloat16, torch.float32))
             and fused_fc1_available(w1.shape[0], w1.shape[1]) and fused_fc1_available(w1.shape[0], w2.shape[0]))
 
 
@@ -685,7 +706,7 @@ class _PatchEmbedTokens(torch.autograd.Function):
     B*(1+Np) rows (the CLS slot of the patch matrix is zero), gvit_embed_assemble.  The image gets no gradient."""
 
     @staticmethod
-    def forward(ctx, img, conv_w, conv_b, cls, pos, p, seed, dt):
+    def forward(ctx, img, conv_w, conv_b, cls, pos, p, seed, dt, out_dt):
         B, C, H, W = img.shape
         D, P = conv_w.shape[0], conv_w.shape[-1]
         N, K = (H // P) * (W // P) + 1, C * P * P
@@ -698,12 +719,15 @@ class _PatchEmbedTokens(torch.autograd.Function):
             pd = prm[0].dtype
         else:
             pd = dt
+        if out_dt != dt and pd != torch.float32:
+            out_dt = dt                             # an fp32 stream over a bf16 projection needs the fp32 parameters
         b_, c_, p_ = _shadow(conv_b, pd), _shadow(cls, pd), _shadow(pos, pd)
-        out = torch.empty((B, N, D), dtype=dt, device=img.device)
+        out = torch.empty((B, N, D), dtype=out_dt, device=img.device)
         mask = torch.empty(B * N * D // 8, dtype=torch.uint8, device=img.device) if p > 0 else None
         _call("gvit_embed_assemble", _ptr(y), _ptr(b_), _ptr(c_), _ptr(p_), B, N, D, float(p), int(seed), 0,
-              _rng_offset_ptr(), _dtype_code(out), GVIT_F32 if pd == torch.float32 else GVIT_BF16, _ptr(out), _ptr(mask), st)
+              _rng_offset_ptr(), _dtype_code(y), GVIT_F32 if pd == torch.float32 else GVIT_BF16, _dtype_code(out), _ptr(out), _ptr(mask), st)
         ctx.save_for_backward(patches, mask)
+        ctx.dt = dt
         ctx.p = p
         ctx.meta = (conv_w.shape, conv_w.dtype, None if conv_b is None else conv_b.dtype, cls.dtype, pos.dtype)
         return out
@@ -715,8 +739,9 @@ class _PatchEmbedTokens(torch.autograd.Function):
         B, N, K = patches.shape
         D = dout.shape[-1]
         dout = dout.contiguous()
-        if ctx.p > 0:
-            d = torch.empty_like(dout)
+        if ctx.p > 0 or dout.dtype != ctx.dt:
+            # keep mask (and, for an fp32 stream gradient, the cast to the GEMM dtype) in one pass
+            d = torch.empty(dout.shape, dtype=ctx.dt, device=dout.device)
             _call("gvit_dropout_bwd", _ptr(dout), _ptr(mask), dout.numel(), float(ctx.p), _dtype_code(dout),
                   _dtype_code(d), _ptr(d), 0, None, None, _stream())
         else:
@@ -726,7 +751,7 @@ class _PatchEmbedTokens(torch.autograd.Function):
         dcls = dsum[0].view(1, 1, D).to(cls_dt) if ctx.needs_input_grad[3] else None
         dbias = dsum[1:].sum(0).to(b_dt) if (b_dt is not None and ctx.needs_input_grad[2]) else None
         dw = _wgrad(d.view(B * N, D), patches.view(B * N, K), w_dt).view(w_shape) if ctx.needs_input_grad[1] else None
-        return None, dw, dbias, dcls, dpos, None, None, None
+        return None, dw, dbias, dcls, dpos, None, None, None, None
 
 
 def patch_embed_supported(img: torch.Tensor, conv_w: torch.Tensor) -> bool:
@@ -735,9 +760,11 @@ def patch_embed_supported(img: torch.Tensor, conv_w: torch.Tensor) -> bool:
             and img.shape[-1] % P == 0 and img.shape[-2] % P == 0 and conv_w.shape[0] % 8 == 0)
 
 
-def patch_embed_tokens(img, conv_w, conv_b, cls_token, pos_embed, p: float, training: bool):
+def patch_embed_tokens(img, conv_w, conv_b, cls_token, pos_embed, p: float, training: bool, fp32_stream: bool = False):
     """The (B, 1+Np, D) token tensor of vit.py:203-212 from the image: patch projection (Conv2d with kernel == stride,
-    vit.py:22,34), CLS token, position embedding and pos_drop.  Runs in bf16 under autocast, else in fp32."""
+    vit.py:22,34), CLS token, position embedding and pos_drop.  Runs in bf16 under autocast, else in fp32.
+    ``fp32_stream``: under autocast emit the tokens in fp32 (bf16 projection + fp32 cls / pos: what torch.autocast's
+    promotion rules give the reference at vit.py:207-211)."""
     _check_cuda(img, conv_w, conv_b, cls_token, pos_embed)
     if not patch_embed_supported(img, conv_w):
         raise ValueError(f"patch_embed_tokens needs a square patch size that is a multiple of 8 dividing the image; got image "
@@ -748,7 +775,8 @@ def patch_embed_tokens(img, conv_w, conv_b, cls_token, pos_embed, p: float, trai
         img = img.float()
     seed = _draw_seed() if p > 0 else 0
     with torch.autocast("cuda", enabled=False):
-        return _PatchEmbedTokens.apply(img.contiguous(), conv_w, conv_b, cls_token, pos_embed, p, seed, dt)
+        return _PatchEmbedTokens.apply(img.contiguous(), conv_w, conv_b, cls_token, pos_embed, p, seed, dt,
+                                       torch.float32 if fp32_stream else dt)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -816,6 +844,11 @@ def fused_agg_available(dtype: torch.dtype, Np: int, D: int, k: int) -> bool:
     return _lib.describe_path("agg", GVIT_BF16, Np, D).startswith("agg:tcgen05")
 
 
+def fused_agg_res32_available(Np: int, D: int, k: int) -> bool:
+    """the fused aggregation kernel can add onto (and emit) an fp32 residual stream: the D <= 768 kernel only"""
+    return k <= 16 and _lib.describe_path("agg_res32", GVIT_BF16, Np, D).startswith("agg:tcgen05")
+
+
 def fused_graph_bwd_available(dtype: torch.dtype, Np: int, D: int, k: int) -> bool:
     if dtype != torch.bfloat16 or k > 16:
         return False
@@ -842,13 +875,13 @@ class _PatchGraph(torch.autograd.Function):
         _call("gvit_knn_fwd", _ptr(h, off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(vals), _ptr(rnorm), st)
         w = torch.empty((B, Np, k), dtype=torch.float32, device=h.device)
         if fused_agg_available(h.dtype, Np, D, k):
-            out = torch.empty_like(h)
+            out = torch.empty_like(h if resid is None else resid)        # an fp32 residual stream gets an fp32 result
             # z is laid out like h (zero CLS row) so that the weight / input gradients are plain GEMMs over all
             # B*(1+Np) rows of dout - slicing the CLS row off would cost a copy of dout per layer
             zf = torch.empty_like(h)
             zf[:, 0].zero_()
             _call("gvit_agg_fwd", _ptr(h), B, Np, D, k, dt, _ptr(idx), _ptr(vals), _ptr(weight), _ptr(bias),
-                  _ptr(resid), _ptr(out), _ptr(w), _ptr(zf, off), bs, st)
+                  _ptr(resid), _dtype_code(out), _ptr(out), _ptr(w), _ptr(zf, off), bs, st)
             z = zf
         else:
             z = torch.empty((B, Np, D), dtype=h.dtype, device=h.device)
@@ -875,10 +908,18 @@ class _PatchGraph(torch.autograd.Function):
         if z.shape[1] == Np + 1 and fused_graph_bwd_available(h.dtype, Np, D, k):
             # bf16: z / dz laid out like h; GEMMs over all rows (the CLS row of z is zero, the CLS row of dz is unused),
             # then both sparse stages as two per-image tensor-core GEMMs (no reverse adjacency)
-            d2 = dout.view(B * (Np + 1), D)
+            want_db = ctx.has[0] and ctx.needs_input_grad[2]
+            if dout.dtype != h.dtype:
+                # fp32 stream gradient: ONE pass casts it to the GEMM dtype and accumulates the column sums (bias gradient)
+                d2 = torch.empty((B * (Np + 1), D), dtype=h.dtype, device=h.device)
+                cs = torch.empty(D, dtype=torch.float32, device=h.device) if want_db else None
+                ws = _colsum_ws(B * (Np + 1), D, h.device) if want_db else None
+                _call("gvit_dropout_bwd", _ptr(dout), None, dout.numel(), 0.0, _dtype_code(dout), dt, _ptr(d2), D, _ptr(cs), _ptr(ws), st)
+            else:
+                d2 = dout.view(B * (Np + 1), D)
+                cs = colsum(d2) if want_db else None
             dweight = _wgrad(d2, z.view(B * (Np + 1), D), ctx.w_dtype) if ctx.needs_input_grad[1] else None
-            dbias = ((colsum(d2) - dout[:, 0].float().sum(0)).to(ctx.b_dtype)
-                     if (ctx.has[0] and ctx.needs_input_grad[2]) else None)
+            dbias = (cs - dout[:, 0].float().sum(0)).to(ctx.b_dtype) if want_db else None
             dh = None
             if ctx.needs_input_grad[0]:
                 dz = d2 @ weight                                   # (B*(1+Np), D)
@@ -922,7 +963,9 @@ def patch_graph(h: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None
         raise ValueError(f"h must be (B, 1+Np, D); got {tuple(h.shape)}")
     dt = _autocast_dtype(h)
     with torch.autocast("cuda", enabled=False):
-        fuse_resid = resid is not None and resid.dtype == dt
+        B_, N_, D_ = h.shape
+        fuse_resid = resid is not None and (resid.dtype == dt or (
+            resid.dtype == torch.float32 and dt == torch.bfloat16 and fused_agg_res32_available(N_ - 1, D_, int(k))))
         out, idx, vals = _PatchGraph.apply(h.to(dt).contiguous(), weight, bias,
                                            resid.contiguous() if fuse_resid else None, int(k))
         if resid is not None and not fuse_resid:

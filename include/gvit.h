@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GVIT_ABI_VERSION 11
+#define GVIT_ABI_VERSION 12
 #if defined(__GNUC__)
 #define GVIT_API __attribute__((visibility("default")))
 #else
@@ -89,9 +89,11 @@ GVIT_API int gvit_agg_gather_fwd(const void* p, int64_t batch_stride, int64_t ro
  * w_save ((B,Np,k) fp32) and z_save may be NULL (inference); training saves them.  z_save holds the aggregated
  * tokens z = A~ p: row i of image b at z_save[b*z_batch_stride + i*D] - pass z_full + D with stride (1+Np)*D to lay it
  * out like h (CLS row left to the caller), which lets the weight gradient run over all (B*(1+Np)) rows without a copy.
- * bf16 only (tcgen05); D % 64 == 0, D <= 1024, Np <= 1024. */
+ * bf16 only (tcgen05); D % 64 == 0, D <= 1024, Np <= 1024.  resid_dtype is the dtype of resid AND out: GVIT_BF16, or
+ * GVIT_F32 for the fp32 residual stream torch.autocast keeps (vit.py:117-118 `x + f(LN(x))` with x fp32: the branch value
+ * is rounded to bf16, the add is fp32); fp32 is fused for D <= 768 (GVIT_ERR_UNSUPPORTED otherwise). */
 GVIT_API int gvit_agg_fwd(const void* h, int B, int Np, int D, int k, int dtype, const int32_t* idx, const float* vals,
-                 const void* Wg, const void* bias, const void* resid, void* out, float* w_save, void* z_save,
+                 const void* Wg, const void* bias, const void* resid, int resid_dtype, void* out, float* w_save, void* z_save,
                  int64_t z_batch_stride, void* stream);
 
 /* Backward of G4+G5 given dz = dY Wg (the two GEMM gradients dWg, dz are plain library GEMMs on the host
@@ -177,11 +179,12 @@ GVIT_API int gvit_linear_gelu_dropout_fwd(const void* x, const void* w, const vo
                                  void* stream);
 
 /* Same GEMM with the other epilogue of the block: out = resid + dropout(x W^T + bias, p) - proj + proj_drop + the residual
- * add of vit.py:70-71,117 (and fc2 + drop + residual, vit.py:93-94,118) in one kernel.  resid / out (M,N) bf16; same
+ * add of vit.py:70-71,117 (and fc2 + drop + residual, vit.py:93-94,118) in one kernel.  resid / out (M,N) of resid_dtype
+ * (GVIT_BF16, or GVIT_F32 = the fp32 residual stream of torch.autocast: bf16 branch value added onto an fp32 x); same
  * shape limits and keep-mask convention (4-byte aligned).  Worth it while K is small (the main loop is L2-bound at
  * ~1.07 PF/s): the host side uses it for K <= 1024. */
 GVIT_API int gvit_linear_dropout_residual_fwd(const void* x, const void* w, const void* bias, const void* resid, int64_t M, int N, int K, float p,
-                                     uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, void* out,
+                                     uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, int resid_dtype, void* out,
                                      uint8_t* keep_mask, void* stream);
 
 /* Backward counterpart for the Mlp: the input gradient of fc2 fused with the backward of drop + GELU (vit.py:91-93):
@@ -203,11 +206,12 @@ GVIT_API int gvit_linear_gelu_dropout_bwd(const void* dout, const void* w2, cons
 GVIT_API int gvit_patchify(const void* img, int B, int C, int H, int W, int P, int in_dtype, int out_dtype, void* out, void* stream);
 /* out[b,0,:] = cls + pos[0];  out[b,n,:] = y[b,n,:] + bias + pos[n] for n >= 1 (row 0 of y is ignored);  then
  * dropout(p) with the keep-mask convention of gvit_dropout_residual_fwd (mask index = element index / 8).  y / out:
- * (B,N,D) of `dtype`; bias (D, nullable), cls (D), pos (N,D) of `param_dtype` (GVIT_F32 master parameters may feed a
- * bf16 stream).  The backward is gvit_dropout_bwd followed by gvit_colsum over the batch. */
+ * (B,N,D); y of `dtype`, out of `out_dtype` (= dtype, or GVIT_F32 over a bf16 y with fp32 parameters: the fp32 residual
+ * stream torch.autocast produces at vit.py:207-211); bias (D, nullable), cls (D), pos (N,D) of `param_dtype` (GVIT_F32
+ * master parameters may feed a bf16 stream).  The backward is gvit_dropout_bwd followed by gvit_colsum over the batch. */
 GVIT_API int gvit_embed_assemble(const void* y, const void* bias, const void* cls, const void* pos, int B, int N, int D, float p,
-                        uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, int param_dtype, void* out,
-                        uint8_t* keep_mask, void* stream);
+                        uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, int param_dtype, int out_dtype,
+                        void* out, uint8_t* keep_mask, void* stream);
 
 #ifdef __cplusplus
 }

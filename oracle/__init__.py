@@ -15,7 +15,11 @@ Pinning status
   restatement.
 * Graph construction / aggregation (``graph_oracle.py``): **parity unpinned** -
   the reference repository contains no graph code at all,
-  so the frozen specification of SURVEY.md section 9 is the only oracle.
+  so the frozen specification of SURVEY.md section 9 is the only oracle; ``knn_strict.c`` (plain C, built by
+  ``knn_strict.py`` with gcc) fixes its fp32 accumulation order for the bit-exact index checks.
 """
 
-GRAPH_SPEC_VERSION = 1  # bump => every golden under tests/golden/graph_* is stale
+# 1: SURVEY.md section 9 as written (fp32 accumulation order left to the GEMM library).
+# 2: + the fp32 accumulation order of G1-G3 is FIXED (oracle/knn_strict.c: sequential FMA chains, normalise first, IEEE
+#    division / sqrt) so that "neighbour indices bit-exact in fp32" is checkable on every row, not only on rows with a margin.
+GRAPH_SPEC_VERSION = 2  # bump => every golden under tests/golden/graph_* is stale

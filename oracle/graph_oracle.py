@@ -47,6 +47,17 @@ def knn_select(S: torch.Tensor, k: int):
     return idx, S.gather(-1, idx)
 
 
+def knn_select_strict(p: torch.Tensor, k: int):
+    """G1-G3 in the STRICT fp32 order of GRAPH_SPEC_VERSION 2 (``oracle/knn_strict.c``: sequential fp32 FMA chains,
+    IEEE division / sqrt, ties -> lowest index).  This is the statement "kNN neighbour indices bit-exact in fp32" is
+    checked against: returns (idx int64 (B,Np,k), vals fp32 (B,Np,k)) as torch tensors.  ``similarity`` + ``knn_select``
+    above are the same mathematics with the GEMM's (MKL's) unspecified accumulation order; the two agree on every row
+    whose decision margin exceeds fp32 round-off (tests/test_oracle_golden.py)."""
+    from . import knn_strict
+    idx, vals, _ = knn_strict.knn_strict(p.detach().float().cpu().numpy(), k)
+    return torch.from_numpy(idx.astype(np.int64)), torch.from_numpy(vals)
+
+
 def knn_f64(p: np.ndarray, k: int):
     """Float64 numpy restatement of G1-G3 for index parity at scale.
 
@@ -68,22 +79,29 @@ def knn_f64(p: np.ndarray, k: int):
     return idx.astype(np.int32), np.take_along_axis(S, idx, axis=-1), gaps.min(axis=-1)
 
 
-def graph_layer_forward(h, weight, bias, k=8, mode="knn", compute_dtype=None, return_aux=False, idx_override=None):
+def graph_layer_forward(h, weight, bias, k=8, mode="knn", compute_dtype=None, return_aux=False, idx_override=None,
+                        strict=True):
     """G0-G6 on an already layer-normed token tensor h (B, 1+Np, D).
 
     compute_dtype: None -> everything fp32.  torch.bfloat16 emulates autocast:
     G1-G4 stay fp32, G5-G6 run on operands rounded to compute_dtype (matmuls
     under autocast cast both operands; accumulation is fp32).
+    strict (knn mode, no idx_override): the neighbour INDICES come from the strict-order fp32 evaluation
+    (``knn_select_strict``, spec version 2); the similarity VALUES that carry the gradient stay torch's (autograd).
     """
     B, N, D = h.shape
     p = h[:, 1:, :]                                   # G0
     S = similarity(p)                                 # G1, G2
     cd = compute_dtype or torch.float32
     if mode == "knn":
-        idx, vals = knn_select(S, k)                  # G3
         if idx_override is not None:
             idx = idx_override.long()
-            vals = S.gather(-1, idx)
+        elif strict:
+            idx, _ = knn_select_strict(p, k)          # G3, strict fp32 order
+            idx = idx.to(h.device)
+        else:
+            idx, _ = knn_select(S, k)                 # G3, accumulation order of the library GEMM
+        vals = S.gather(-1, idx)
         w = torch.softmax(vals, dim=-1)               # G4
         pg = p.to(cd)
         bi = torch.arange(B, device=h.device)[:, None, None]
@@ -109,6 +127,9 @@ class PatchGraphLayer(nn.Module):
         super().__init__()
         self.k, self.mode = k, mode
         self.proj = nn.Linear(dim, dim)
+        # tests may pin the adjacency (e.g. to the one a device run built from ITS tokens of this layer): deep in a network
+        # a near-tie can flip on 1e-7 of input noise, and a flipped neighbour is not a small perturbation of the output
+        self.idx_override = None
 
     def forward(self, h):
-        return graph_layer_forward(h, self.proj.weight, self.proj.bias, self.k, self.mode)
+        return graph_layer_forward(h, self.proj.weight, self.proj.bias, self.k, self.mode, idx_override=self.idx_override)

@@ -61,6 +61,14 @@ def module_case(mod, x, cot, prefix=""):
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if "--graph-only" not in sys.argv:
+        reference_fixtures()
+    graph_fixtures()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+def reference_fixtures():
     ref_vit, ref_losses = _ref_modules()
     g = torch.Generator().manual_seed(0)
 
@@ -116,9 +124,12 @@ def main():
                         weight_abs_sum=wsum, img_abs_sum=float(img.double().abs().sum()),
                         n_params=sum(p.numel() for p in m.parameters()))
 
-    # 5. Graph layer - from oracle/graph_oracle.py, PARITY UNPINNED
+
+def graph_fixtures():
+    # 5. Graph layer - from oracle/graph_oracle.py, PARITY UNPINNED.  idx / vals are the STRICT fp32
+    #    evaluation (oracle/knn_strict.c, spec version 2); out / gradients come from autograd over that adjacency.
     from oracle import GRAPH_SPEC_VERSION
-    from oracle.graph_oracle import graph_layer_forward
+    from oracle.graph_oracle import graph_layer_forward, knn_select_strict
     gg = torch.Generator().manual_seed(7)
     for name, (Np, D, k, mode) in {"graph_knn_small": (20, 32, 4, "knn"), "graph_dense_small": (20, 32, 0, "dense"),
                                    "graph_knn_196": (196, 64, 8, "knn")}.items():
@@ -131,7 +142,9 @@ def main():
         d = dict(spec_version=GRAPH_SPEC_VERSION, h=_np(h), W=_np(W), b=_np(b), cot=_np(cot), out=_np(out),
                  dh=_np(h.grad), dW=_np(W.grad), db=_np(b.grad), k=k, mode=np.array(mode))
         if mode == "knn":
-            d.update(idx=_np(aux["idx"]).astype(np.int32), vals=_np(aux["vals"]))
+            si, sv = knn_select_strict(h[:, 1:], k)
+            assert torch.equal(si, aux["idx"])
+            d.update(idx=_np(si).astype(np.int32), vals=_np(sv))
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
 
     # 6. exact-tie case: duplicated rows must resolve to the lowest index
@@ -139,11 +152,20 @@ def main():
     h[0, 1 + 9] = h[0, 1 + 5]
     h[0, 1 + 17] = h[0, 1 + 5]
     h[0, 1 + 1] = h[0, 1 + 0]
-    _, aux = graph_layer_forward(h, torch.eye(16), None, 4, "knn", return_aux=True)
+    si, sv = knn_select_strict(h[:, 1:], 4)
     np.savez_compressed(os.path.join(OUT, "graph_ties.npz"), spec_version=GRAPH_SPEC_VERSION, h=_np(h),
-                        idx=_np(aux["idx"]).astype(np.int32), vals=_np(aux["vals"]), k=4)
-    for f in sorted(os.listdir(OUT)):
-        print(f, os.path.getsize(os.path.join(OUT, f)))
+                        idx=_np(si).astype(np.int32), vals=_np(sv), k=4)
+    # 7. strict adjacency at the benchmark shapes (inputs are regenerated from the seed by the tests; only idx is stored):
+    #    (2,196,768) for k in {4,8,16} and (1,576,1024) k = 8
+    d = {}
+    for tag, (B, Np, D, ks) in {"b196": (2, 196, 768, (4, 8, 16)), "l576": (1, 576, 1024, (8,))}.items():
+        hh = torch.randn(B, Np + 1, D, generator=torch.Generator().manual_seed(100 + Np))
+        d[tag + "_abs_sum"] = float(hh.double().abs().sum())
+        for k in ks:
+            si, sv = knn_select_strict(hh[:, 1:], k)
+            d[f"{tag}_k{k}_idx"] = _np(si).astype(np.int16)
+            d[f"{tag}_k{k}_vals"] = _np(sv)
+    np.savez_compressed(os.path.join(OUT, "graph_knn_strict.npz"), spec_version=GRAPH_SPEC_VERSION, **d)
 
 
 if __name__ == "__main__":

@@ -55,13 +55,13 @@ def test_validation_errors_are_loud_and_need_no_gpu():
     with pytest.raises(_lib.GvitError, match="GVIT_ERR_DTYPE"):            # bf16 stream with an fp32 branch is not a pairing
         _lib.call("gvit_layernorm_fwd", 16, 16, 16, 1, 64, 1e-5, _lib.GVIT_BF16, _lib.GVIT_F32, 16, 16, 16, None)
     with pytest.raises(_lib.GvitError, match="GVIT_ERR_UNSUPPORTED"):
-        _lib.call("gvit_agg_fwd", 16, 1, 16, 64, 4, _lib.GVIT_F32, 16, 16, 16, None, None, 16, None, None, 0, None)
+        _lib.call("gvit_agg_fwd", 16, 1, 16, 64, 4, _lib.GVIT_F32, 16, 16, 16, None, None, _lib.GVIT_F32, 16, None, None, 0, None)
     with pytest.raises(_lib.GvitError, match="GVIT_ERR_SHAPE"):            # patch size must be a multiple of 8
         _lib.call("gvit_patchify", 16, 1, 3, 224, 224, 14, _lib.GVIT_F32, _lib.GVIT_BF16, 16, None)
     with pytest.raises(_lib.GvitError, match="GVIT_ERR_DTYPE"):            # a bf16 image cannot produce fp32 patches
         _lib.call("gvit_patchify", 16, 1, 3, 224, 224, 16, _lib.GVIT_BF16, _lib.GVIT_F32, 16, None)
     with pytest.raises(_lib.GvitError, match="GVIT_ERR_SHAPE"):            # dropout without a keep-mask buffer
-        _lib.call("gvit_embed_assemble", 16, 16, 16, 16, 1, 197, 768, 0.1, 1, 0, None, _lib.GVIT_BF16, _lib.GVIT_F32, 16, None, None)
+        _lib.call("gvit_embed_assemble", 16, 16, 16, 16, 1, 197, 768, 0.1, 1, 0, None, _lib.GVIT_BF16, _lib.GVIT_F32, _lib.GVIT_BF16, 16, None, None)
     with pytest.raises(_lib.GvitError, match="GVIT_ERR_UNSUPPORTED"):      # the fused graph backward is bf16-only
         _lib.call("gvit_graph_bwd", 16, 1024, 64, 1, 16, 64, 4, _lib.GVIT_F32, 16, 16, 16, 16, 16, 1024, 16, 16, None)
 

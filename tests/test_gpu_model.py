@@ -87,6 +87,102 @@ def test_graph_vit_fp32_forward_backward_vs_oracle():
         assert rel_err(b.grad, a.grad) < 3 * TOL_F32, n
 
 
+def _pin_adjacency(o, m, img_dev, autocast):
+    """Run the device model once with graph recording on and pin the oracle's per-layer adjacency to the one the device
+    built from ITS tokens of that layer.  Deep in a network a near-tie neighbour can flip on 1e-7 of input noise, and a
+    flipped neighbour is not a small perturbation of the output; what must hold layer by layer is (a) identical inputs
+    -> identical indices (checked here for fp32 against the strict oracle, bit-exact on every row) and (b) identical
+    indices -> activations / gradients within tolerance (checked by the callers on logits and every gradient)."""
+    from oracle import knn_strict
+    for blk in m.blocks:
+        if hasattr(blk, "graph"):
+            blk.graph.record_graph = True
+    with torch.no_grad():
+        if autocast:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                m(img_dev)
+        else:
+            m(img_dev)
+    n_checked = 0
+    for bo, bm in zip(o.blocks, m.blocks):
+        if hasattr(bm, "graph"):
+            bo.graph.idx_override = bm.graph.last_idx.cpu().long()
+            if not autocast:
+                li, lv, _ = knn_strict.knn_strict(bm.graph.last_tokens[:, 1:].float().cpu().numpy(), bm.graph.k)
+                assert (bm.graph.last_idx.cpu().numpy() == li).all(), "fp32 kNN indices differ from the strict oracle"
+                assert (bm.graph.last_vals.cpu().numpy() == lv).all()
+                n_checked += 1
+            bm.graph.record_graph = False
+            bm.graph.last_tokens = bm.graph.last_idx = bm.graph.last_vals = None
+    return n_checked
+
+
+def _worst_grad_errors(o, m):
+    errs = {n: rel_err(b.grad, a.grad) for (n, a), b in zip(o.named_parameters(), m.parameters())}
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:4]
+    return errs, worst
+
+
+VITB_GRAPH = dict(img_size=224, patch_size=16, embed_dim=768, depth=12, num_heads=12, graph_mode="knn", graph_k=8)
+
+
+def test_vit_b16_graph_depth12_fp32_logits_and_every_gradient():
+    """BASELINE configs[1] model (ViT-B/16 + kNN graph block in every layer, depth 12), batch 4, fp32: logits and EVERY
+    gradient - graph.proj.*, norm_g.* included - within north_star's 1e-4, kNN indices bit-exact in all 12 layers."""
+    o, m = _pair(VITB_GRAPH, seed=42)
+    g = torch.Generator().manual_seed(1234)
+    img, tgt = torch.randn(4, 3, 224, 224, generator=g), (torch.rand(4, 14, generator=g) > 0.9).float()
+    assert _pin_adjacency(o, m, img.to(DEV), autocast=False) == 12
+    want = o(img)
+    vit_oracle.multilabel_loss(want, tgt, torch.ones(3), torch.ones(14)).backward()
+    logits = m(img.to(DEV))
+    vit_oracle.multilabel_loss(logits, tgt.to(DEV), torch.ones(3, device=DEV), torch.ones(14, device=DEV)).backward()
+    errs, worst = _worst_grad_errors(o, m)
+    print(f"\nfp32 depth-12 graph-ViT-B: logits rel err {rel_err(logits, want):.2e}; worst gradients {worst}")
+    assert rel_err(logits, want) < TOL_F32
+    assert any("graph.proj" in n for n in errs) and any("norm_g" in n for n in errs)
+    for n, e in errs.items():
+        assert e < TOL_F32, (n, e)
+
+
+@pytest.mark.parametrize("fp32_residual", [True, False])
+def test_vit_b16_graph_depth12_bf16_autocast_logits_and_every_gradient(fp32_residual):
+    """Same model under bf16 autocast (the bench's precision), per-layer adjacency pinned to the device's: logits and
+    every gradient within north_star's 2e-2 of the fp32 oracle.  fp32_residual=True is torch.autocast's own semantics
+    (the default, and what bench.py's `value` measures); False is the opt-in bf16 residual stream."""
+    o, m = _pair(VITB_GRAPH, seed=42)
+    m.fp32_residual = fp32_residual
+    g = torch.Generator().manual_seed(1234)
+    img, tgt = torch.randn(4, 3, 224, 224, generator=g), (torch.rand(4, 14, generator=g) > 0.9).float()
+    _pin_adjacency(o, m, img.to(DEV), autocast=True)
+    want = o(img)
+    vit_oracle.multilabel_loss(want, tgt, torch.ones(3), torch.ones(14)).backward()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = m(img.to(DEV))
+    vit_oracle.multilabel_loss(logits.float(), tgt.to(DEV), torch.ones(3, device=DEV), torch.ones(14, device=DEV)).backward()
+    errs, worst = _worst_grad_errors(o, m)
+    print(f"\nbf16 depth-12 graph-ViT-B (fp32_residual={fp32_residual}): logits rel err {rel_err(logits, want):.2e}; "
+          f"worst gradients {worst}")
+    assert rel_err(logits, want) < TOL_BF16
+    for n, e in errs.items():
+        assert e < TOL_BF16, (n, e)
+
+
+def test_parameter_shadows_follow_data_writes():
+    """`.data` writes do not move `_version`; an autocast forward after one must still see the new weights."""
+    _, m = _pair(seed=8)
+    img = torch.randn(2, 3, 64, 64, device=DEV)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        a = m(img)
+        for p in m.parameters():
+            p.data.mul_(1.5)                       # e.g. EMA / clamping / dist.broadcast(p.data): `_version` unchanged
+        b = m(img)
+        m2 = modules.VisionTransformer(**CFG).eval().to(DEV)
+        m2.load_state_dict(m.state_dict())
+        c = m2(img)
+    assert not torch.equal(a, b) and torch.equal(b, c)
+
+
 def test_graph_every_and_dense_variants_fp32():
     for extra in (dict(graph_every=2), dict(graph_mode="dense")):
         o, m = _pair({**CFG, **extra}, seed=3)
@@ -98,12 +194,13 @@ def test_graph_every_and_dense_variants_fp32():
 def test_graph_vit_bf16_autocast_trains():
     """bf16 autocast fwd+bwd (the bench's precision): close to the fp32 oracle, finite grads for every parameter."""
     o, m = _pair(seed=5)
-    m.train()
     g = torch.Generator().manual_seed(1)
     img, tgt = torch.randn(4, 3, 64, 64, generator=g), (torch.rand(4, 14, generator=g) > 0.7).float()
+    _pin_adjacency(o, m, img.to(DEV), autocast=True)       # near-tie neighbour swaps cannot hide (or cause) errors
+    m.train()
     with torch.autocast("cuda", dtype=torch.bfloat16):
         logits = m(img.to(DEV))
-    assert rel_err(logits, o(img)) < 5e-2                  # whole-network drift incl. possible near-tie neighbour swaps
+    assert rel_err(logits, o(img)) < TOL_BF16
     loss = vit_oracle.multilabel_loss(logits.float(), tgt.to(DEV), torch.ones(3, device=DEV), torch.ones(14, device=DEV))
     before = ops.launch_count()
     loss.backward()
@@ -112,8 +209,9 @@ def test_graph_vit_bf16_autocast_trains():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
     lo = vit_oracle.multilabel_loss(o(img), tgt, torch.ones(3), torch.ones(14))
     lo.backward()
-    worst = max(rel_err(b.grad, a.grad) for (n, a), b in zip(o.named_parameters(), m.parameters()) if "graph" not in n)
-    assert worst < 0.15, worst
+    errs, worst = _worst_grad_errors(o, m)                 # every parameter, graph.* and norm_g.* included
+    print(f"\nbf16 small graph-ViT: worst gradients {worst}")
+    assert worst[0][1] < TOL_BF16, worst
 
 
 def test_pure_bf16_model_runs():
@@ -126,13 +224,20 @@ def test_pure_bf16_model_runs():
 def test_fp32_residual_stream_option_and_hook_safe_folding():
     o, m = _pair(seed=7)
     img = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(3))
-    m.fp32_residual = True
+    assert m.fp32_residual is True                         # default = torch.autocast's own residual-stream semantics
+    _pin_adjacency(o, m, img.to(DEV), autocast=True)
     with torch.autocast("cuda", dtype=torch.bfloat16), torch.no_grad():
         a = m(img.to(DEV))
     m.fp32_residual = False
+    _pin_adjacency(o, m, img.to(DEV), autocast=True)
     with torch.autocast("cuda", dtype=torch.bfloat16), torch.no_grad():
         b = m(img.to(DEV))
-    assert rel_err(a, o(img)) < 3e-2 and rel_err(b, o(img)) < 5e-2
+    assert rel_err(b, o(img)) < TOL_BF16
+    m.fp32_residual = True
+    _pin_adjacency(o, m, img.to(DEV), autocast=True)
+    assert rel_err(a, o(img)) < TOL_BF16
+    for bo in o.blocks:
+        bo.graph.idx_override = None
     # a forward hook on blocks.1.attn (what Grad-CAM installs) must observe the attention output, not x + attention
     seen = {}
     h = m.blocks[1].attn.register_forward_hook(lambda mod, inp, out: seen.setdefault("out", out.detach()))

@@ -84,7 +84,8 @@ def test_graph_spec_frozen(name):
     assert rel_err(h.grad, g["dh"]) < 2e-5 and rel_err(W.grad, g["dW"]) < 2e-5 and rel_err(b.grad, g["db"]) < 2e-5
     assert float(out[:, 0].abs().max()) == 0.0                      # G0: CLS row untouched
     if str(g["mode"]) == "knn":
-        assert np.array_equal(aux["idx"].numpy().astype(np.int32), g["idx"])
+        assert np.array_equal(aux["idx"].numpy().astype(np.int32), g["idx"])       # strict fp32 order (spec version 2)
+        assert np.abs(aux["vals"].detach().numpy() - g["vals"]).max() < 2e-6       # torch's S vs the strict chain: round-off
         idx64, _, margin = graph_oracle.knn_f64(g["h"][:, 1:], int(g["k"]))
         sure = margin > 1e-5                                        # rows whose answer fp32 noise cannot flip
         assert sure.mean() > 0.9
@@ -104,6 +105,49 @@ def test_graph_ties_resolve_to_lowest_index():
         assert list(idx[0, r, :2]) == [0, 1]
     idx64, _, _ = graph_oracle.knn_f64(g["h"][:, 1:], int(g["k"]))
     assert list(idx64[0, 9, :3]) == [5, 9, 17]
+
+
+def test_strict_knn_known_answers():
+    """oracle/knn_strict.c on cases whose answer is known in closed form."""
+    from oracle import knn_strict
+    # orthonormal rows: S = I exactly -> self first, then ties (all zeros) in ascending column order
+    idx, vals, rn = knn_strict.knn_strict(np.eye(6, dtype=np.float32)[None] * 3.0, 3)
+    for i in range(6):
+        assert list(idx[0, i]) == [i] + [j for j in range(6) if j != i][:2]
+    assert np.array_equal(vals[0, :, 0], np.ones(6, np.float32)) and np.all(vals[0, :, 1:] == 0)
+    assert np.allclose(rn, 1 / 3.0)
+    # collinear rows: cosine exactly +-1 regardless of scale; opposite direction sorts last
+    p = np.array([[[1, 2, 2, 0], [2, 4, 4, 0], [-1, -2, -2, 0], [0, 0, 0, 5]]], dtype=np.float32)
+    idx, vals, _ = knn_strict.knn_strict(p, 4)
+    assert list(idx[0, 0]) == [0, 1, 3, 2] and list(idx[0, 1]) == [0, 1, 3, 2] and list(idx[0, 2]) == [2, 3, 0, 1]
+    assert np.allclose(vals[0, 0], [1, 1, 0, -1], atol=1e-6)
+    # zero row: norm clamps to 1e-12 (F.normalize), similarities 0, ties ascending
+    p = np.zeros((1, 3, 8), np.float32)
+    p[0, 1, 0] = 1.0
+    idx, vals, rn = knn_strict.knn_strict(p, 3)
+    assert list(idx[0, 0]) == [0, 1, 2] and np.all(vals[0, 0] == 0) and rn[0, 0] == np.float32(1e12)
+
+
+def test_strict_knn_agrees_with_torch_and_float64_where_fp32_can_tell():
+    """The strict order is one admissible fp32 evaluation of section 9: same indices as torch's GEMM-ordered fp32 and as
+    float64 on every row whose decision margin exceeds fp32 round-off; exactly symmetric; committed fixture reproduced."""
+    from oracle import knn_strict
+    g = golden("graph_knn_strict")
+    h = torch.randn(2, 197, 768, generator=torch.Generator().manual_seed(100 + 196))
+    assert abs(float(h.double().abs().sum()) - float(g["b196_abs_sum"])) < 1e-9 * float(g["b196_abs_sum"])
+    p = h[:, 1:]
+    idx, vals, _ = knn_strict.knn_strict(p.numpy(), 8)
+    assert np.array_equal(idx, g["b196_k8_idx"].astype(np.int32)) and np.array_equal(vals, g["b196_k8_vals"])
+    ti, tv = graph_oracle.knn_select(graph_oracle.similarity(p), 8)
+    idx64, _, margin = graph_oracle.knn_f64(p.numpy(), 8)
+    sure = margin > 2e-6
+    assert sure.mean() > 0.95
+    assert np.array_equal(idx[sure], idx64[sure]) and np.array_equal(ti.numpy()[sure], idx64[sure])
+    assert np.abs(vals - tv.numpy()).max() < 3e-6
+    # symmetry of the strict S: i lists j with the same bits as j lists i
+    look = {(0, i, int(j)): v for i in range(196) for j, v in zip(idx[0, i], vals[0, i])}
+    pairs = [(k, v) for k, v in look.items() if (0, k[2], k[1]) in look]
+    assert len(pairs) > 196 and all(look[(0, k[2], k[1])] == v for k, v in pairs)
 
 
 def test_dense_is_the_k_equals_np_limit():

@@ -1,11 +1,11 @@
 """Event trace of CTA 0 of a warp-specialised libgvit kernel (needs the -DGVIT_TRACE build:
-   make EXTRA=-DGVIT_TRACE OBJ_DIR=build/obj_trace LIB=graph_augmented_vision_transformers_b200/lib/libgvit_trace.so).
+   make EXTRA=-DGVIT_TRACE OBJ_DIR=build/obj_trace LIB=tools/bin/libgvit_trace.so).
 python tools/trace_kernel.py attn_bwd [--batch 256] > gpurun_out/trace_attn_bwd.txt"""
 import argparse, ctypes, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from graph_augmented_vision_transformers_b200 import _lib
-_lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), "libgvit_trace.so")
+_lib.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bin", "libgvit_trace.so")   # never next to the product library
 import bench  # noqa: E402
 
 ap = argparse.ArgumentParser()
