@@ -235,9 +235,9 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
                              2 * B * N * 4 * D * e + B * N * 4 * D // 8, 0.0, "hbm", 0),      # folded into fc1_fused for bf16
         "gelu_dropout_bwd": (lambda i: _call("gvit_gelu_dropout_bwd", _ptr(u4[(i + 1) % 2]), _ptr(u4[i % 2]), _ptr(m4), B * N * 4 * D, 0.1, dt, _ptr(o4), 4 * D, _ptr(cs_out), _ptr(cs_ws), st),
                              3 * B * N * 4 * D * e + B * N * 4 * D // 8, 0.0, "hbm", 0),      # folded into fc2_bwd_fused for bf16
-        "colsum_3072": (lambda i: _call("gvit_colsum", _ptr(u4[i % 2]), B * N, 4 * D, dt, _ptr(cs_out), _ptr(cs_ws), st),
+        "colsum_3072": (lambda i: _call("gvit_colsum", _ptr(u4[i % 2]), B * N, 4 * D, dt, 0, _ptr(cs_out), _ptr(cs_ws), st),
                         B * N * 4 * D * e, 0.0, "hbm", 12),
-        "colsum_768": (lambda i: _call("gvit_colsum", _ptr(hs[i % R]), B * N, D, dt, _ptr(cs_out), _ptr(cs_ws), st),
+        "colsum_768": (lambda i: _call("gvit_colsum", _ptr(hs[i % R]), B * N, D, dt, 0, _ptr(cs_out), _ptr(cs_ws), st),
                        B * N * D * e, 0.0, "hbm", 36),
         "layernorm_bwd_add": (lambda i: _call("gvit_layernorm_bwd", _ptr(xs[i % R]), _ptr(hs[i % R]), _ptr(gam), _ptr(mean), _ptr(rstd), B * N, D, dt, dt, _ptr(hs[(i + 1) % R]), _ptr(out), _ptr(dgb[0]), _ptr(dgb[1]), _ptr(ws), st),
                               4 * B * N * D * e, 0.0, "hbm", 36),

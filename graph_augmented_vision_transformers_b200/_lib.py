@@ -19,7 +19,7 @@ GVIT_F32, GVIT_BF16 = 0, 1
 GVIT_MAX_K = 32
 GVIT_LN_PARTIALS = 296
 GVIT_COLSUM_CHUNKS = 1024
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 STATUS_NAMES = {0: "GVIT_OK", 1: "GVIT_ERR_SHAPE", 2: "GVIT_ERR_ALIGN", 3: "GVIT_ERR_DTYPE", 4: "GVIT_ERR_CUDA",
                 5: "GVIT_ERR_UNSUPPORTED"}
@@ -55,9 +55,9 @@ SIGNATURES = {
     "gvit_attn_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp],
     "gvit_layernorm_fwd": [_vp, _vp, _vp, _i64, _i, _f, _i, _i, _vp, _vp, _vp, _vp],
     "gvit_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
-    "gvit_colsum": [_vp, _i64, _i, _i, _vp, _vp, _vp],
+    "gvit_colsum": [_vp, _i64, _i, _i, _i, _vp, _vp, _vp],
     "gvit_dropout_residual_fwd": [_vp, _vp, _i64, _f, _u64, _u64, _vp, _i, _i, _vp, _vp, _vp],
-    "gvit_dropout_bwd": [_vp, _vp, _i64, _f, _i, _i, _vp, _i, _vp, _vp, _vp],
+    "gvit_dropout_bwd": [_vp, _vp, _i64, _f, _i, _i, _vp, _i, _i, _vp, _vp, _vp],
     "gvit_gelu_dropout_fwd": [_vp, _i64, _f, _u64, _u64, _vp, _i, _vp, _vp, _vp],
     "gvit_gelu_dropout_bwd": [_vp, _vp, _vp, _i64, _f, _i, _vp, _i, _vp, _vp, _vp],
     "gvit_linear_gelu_dropout_fwd": [_vp, _vp, _vp, _i64, _i, _i, _f, _u64, _u64, _vp, _i, _vp, _vp, _vp, _vp],

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(256) gelu_dropout_bwd_kernel(const T* __restri
 // (deterministic, no atomics).  at::sum over dim 0 reached ~3.2 TB/s on these shapes.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int D, int rows_per_chunk,
-                                                             float* __restrict__ partial) {
+                                                             int skip_period, float* __restrict__ partial) {
   __shared__ float red[8][256 + 8];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + cx) * 8;
@@ -339,15 +339,18 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
 #pragma unroll
       for (int i = 0; i < 8; ++i) load8(x + (r + 8 * i) * D + col, a[i]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i) {
+        const bool on = !(skip_period && (r + 8 * i) % skip_period == 0);   // e.g. the CLS rows of a (B, 1+Np, D) tensor
 #pragma unroll
-        for (int t = 0; t < 8; ++t) acc[t] += a[i][t];
+        for (int t = 0; t < 8; ++t) acc[t] += on ? a[i][t] : 0.f;
+      }
     }
     for (; r < r1; r += 8) {
       float a[8];
       load8(x + r * D + col, a);
+      const bool on = !(skip_period && r % skip_period == 0);
 #pragma unroll
-      for (int t = 0; t < 8; ++t) acc[t] += a[t];
+      for (int t = 0; t < 8; ++t) acc[t] += on ? a[t] : 0.f;
     }
   }
 #pragma unroll
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
 template <typename Tx, typename Ty, bool GELU>
 __global__ void __launch_bounds__(256, GELU ? 4 : 2) edge_bwd_colsum_kernel(const Tx* __restrict__ dout, const Ty* __restrict__ u,
                                                               const uint8_t* __restrict__ mask, int64_t rows, int D,
-                                                              int rows_per_chunk, float p, Ty* __restrict__ dy,
+                                                              int rows_per_chunk, float p, int skip_period, Ty* __restrict__ dy,
                                                               float* __restrict__ partial) {
   __shared__ float red[8][256 + 8];
   const float scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
@@ -419,6 +422,7 @@ __global__ void __launch_bounds__(256, GELU ? 4 : 2) edge_bwd_colsum_kernel(cons
       for (int i = 0; i < RF; ++i) {
         const int64_t rr = r + 8 * i;
         if (rr < r1) {
+          const bool on = !(skip_period && rr % skip_period == 0);   // rows left out of the column sums (still written to dy)
           if (GELU) {
             GeluFor<Ty>::type::grad8(g[i], a[i], scale);
           } else {
@@ -430,7 +434,7 @@ __global__ void __launch_bounds__(256, GELU ? 4 : 2) edge_bwd_colsum_kernel(cons
             float v = (bits[i] >> t) & 1u ? g[i][t] : 0.f;
             v = to_f32(from_f32<Ty>(v));                   // the bias gradient sums the values as stored
             g[i][t] = v;
-            acc[t] += v;
+            acc[t] += on ? v : 0.f;
           }
           store8(dy + rr * D + col, g[i]);
         }
@@ -536,7 +540,7 @@ int layernorm_bwd(const void* dy, const void* x, const void* gamma, const float*
   return GVIT_OK;
 }
 
-int colsum(const void* x, int64_t rows, int D, int dtype, float* out, float* partial_ws, cudaStream_t st) {
+int colsum(const void* x, int64_t rows, int D, int dtype, int skip_period, float* out, float* partial_ws, cudaStream_t st) {
   const int colblocks = (D + 255) / 256;
   int nchunks = (6 * num_sms() + colblocks - 1) / colblocks;
   if (nchunks > GVIT_COLSUM_CHUNKS) nchunks = GVIT_COLSUM_CHUNKS;
@@ -545,9 +549,9 @@ int colsum(const void* x, int64_t rows, int D, int dtype, float* out, float* par
   nchunks = (int)((rows + rpc - 1) / rpc);
   dim3 grid(colblocks, nchunks);
   if (dtype == GVIT_F32)
-    colsum_partial_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), rows, D, rpc, partial_ws);
+    colsum_partial_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), rows, D, rpc, skip_period, partial_ws);
   else
-    colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), rows, D, rpc, partial_ws);
+    colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), rows, D, rpc, skip_period, partial_ws);
   GVIT_CHECK_LAUNCH();
   colsum_final_kernel<<<(D + 31) / 32, 256, 0, st>>>(partial_ws, nchunks, D, out);
   GVIT_CHECK_LAUNCH();
@@ -572,7 +576,7 @@ int dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, u
 }
 
 int dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, int y_dtype, void* dy,
-                int D, float* colsum_out, float* partial_ws, cudaStream_t st) {
+                int D, int skip_period, float* colsum_out, float* partial_ws, cudaStream_t st) {
   using bf = __nv_bfloat16;
   if (colsum_out) {
     int cb, nch, rpc;
@@ -580,11 +584,11 @@ int dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, 
     colsum_grid(rows, D, 6, &cb, &nch, &rpc);
     dim3 g2(cb, nch);
     if (dtype == GVIT_F32 && y_dtype == GVIT_F32)
-      edge_bwd_colsum_kernel<float, float, false><<<g2, 256, 0, st>>>(static_cast<const float*>(dout), nullptr, keep_mask, rows, D, rpc, p, static_cast<float*>(dy), partial_ws);
+      edge_bwd_colsum_kernel<float, float, false><<<g2, 256, 0, st>>>(static_cast<const float*>(dout), nullptr, keep_mask, rows, D, rpc, p, skip_period, static_cast<float*>(dy), partial_ws);
     else if (dtype == GVIT_F32)
-      edge_bwd_colsum_kernel<float, bf, false><<<g2, 256, 0, st>>>(static_cast<const float*>(dout), nullptr, keep_mask, rows, D, rpc, p, static_cast<bf*>(dy), partial_ws);
+      edge_bwd_colsum_kernel<float, bf, false><<<g2, 256, 0, st>>>(static_cast<const float*>(dout), nullptr, keep_mask, rows, D, rpc, p, skip_period, static_cast<bf*>(dy), partial_ws);
     else
-      edge_bwd_colsum_kernel<bf, bf, false><<<g2, 256, 0, st>>>(static_cast<const bf*>(dout), nullptr, keep_mask, rows, D, rpc, p, static_cast<bf*>(dy), partial_ws);
+      edge_bwd_colsum_kernel<bf, bf, false><<<g2, 256, 0, st>>>(static_cast<const bf*>(dout), nullptr, keep_mask, rows, D, rpc, p, skip_period, static_cast<bf*>(dy), partial_ws);
     GVIT_CHECK_LAUNCH();
     colsum_final_kernel<<<(D + 31) / 32, 256, 0, st>>>(partial_ws, nch, D, colsum_out);
     GVIT_CHECK_LAUNCH();
@@ -622,9 +626,9 @@ int gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, 
     colsum_grid(rows, D, 12, &cb, &nch, &rpc);               // 3 waves of 4 resident CTAs: measured best of 3..48
     dim3 g2(cb, nch);
     if (dtype == GVIT_F32)
-      edge_bwd_colsum_kernel<float, float, true><<<g2, 256, 0, st>>>(static_cast<const float*>(dout), static_cast<const float*>(u), keep_mask, rows, D, rpc, p, static_cast<float*>(du), partial_ws);
+      edge_bwd_colsum_kernel<float, float, true><<<g2, 256, 0, st>>>(static_cast<const float*>(dout), static_cast<const float*>(u), keep_mask, rows, D, rpc, p, 0, static_cast<float*>(du), partial_ws);
     else
-      edge_bwd_colsum_kernel<bf, bf, true><<<g2, 256, 0, st>>>(static_cast<const bf*>(dout), static_cast<const bf*>(u), keep_mask, rows, D, rpc, p, static_cast<bf*>(du), partial_ws);
+      edge_bwd_colsum_kernel<bf, bf, true><<<g2, 256, 0, st>>>(static_cast<const bf*>(dout), static_cast<const bf*>(u), keep_mask, rows, D, rpc, p, 0, static_cast<bf*>(du), partial_ws);
     GVIT_CHECK_LAUNCH();
     colsum_final_kernel<<<(D + 31) / 32, 256, 0, st>>>(partial_ws, nch, D, colsum_out);
     GVIT_CHECK_LAUNCH();

@@ -170,12 +170,13 @@ int gvit_layernorm_bwd(const void* dy, const void* x, const void* gamma, const f
                        static_cast<cudaStream_t>(stream));
 }
 
-int gvit_colsum(const void* x, int64_t rows, int D, int dtype, float* out, float* partial_ws, void* stream) {
+int gvit_colsum(const void* x, int64_t rows, int D, int dtype, int skip_period, float* out, float* partial_ws, void* stream) {
   TRY(check_dtype(dtype, "colsum"));
   GVIT_REQUIRE(x && out && partial_ws, GVIT_ERR_SHAPE, "colsum: null pointer");
   GVIT_REQUIRE(rows >= 1 && D >= 8 && D % 8 == 0, GVIT_ERR_SHAPE, "colsum: rows=%lld D=%d (D %% 8 == 0)", (long long)rows, D);
   GVIT_REQUIRE(aligned16(x), GVIT_ERR_ALIGN, "colsum: x must be 16-byte aligned");
-  return colsum(x, rows, D, dtype, out, partial_ws, static_cast<cudaStream_t>(stream));
+  GVIT_REQUIRE(skip_period >= 0, GVIT_ERR_SHAPE, "colsum: skip_period=%d must be >= 0", skip_period);
+  return colsum(x, rows, D, dtype, skip_period, out, partial_ws, static_cast<cudaStream_t>(stream));
 }
 
 int gvit_dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, uint64_t seed, uint64_t offset,
@@ -198,14 +199,15 @@ static int check_colsum_args(const char* who, int64_t n, int D, const float* col
 }
 
 int gvit_dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, int y_dtype, void* dy,
-                     int D, float* colsum_out, float* partial_ws, void* stream) {
+                     int D, int skip_period, float* colsum_out, float* partial_ws, void* stream) {
   TRY(check_ln_pair(dtype, y_dtype, "dropout_bwd"));
   GVIT_REQUIRE(dout && dy && (keep_mask || p == 0.f), GVIT_ERR_SHAPE, "dropout_bwd: null pointer (keep_mask is required when p > 0)");
   GVIT_REQUIRE(n >= 8 && n % 8 == 0 && p >= 0.f && p < 1.f && (p > 0.f || colsum_out || dtype != y_dtype), GVIT_ERR_SHAPE,
                "dropout_bwd: n=%lld p=%f (p == 0 without column sums is only meaningful as the fp32 -> bf16 cast)", (long long)n, p);
   GVIT_REQUIRE(aligned16(dout) && aligned16(dy), GVIT_ERR_ALIGN, "dropout_bwd: 16-byte alignment required");
   TRY(check_colsum_args("dropout_bwd", n, D, colsum_out, partial_ws));
-  return dropout_bwd(dout, keep_mask, n, p, dtype, y_dtype, dy, D, colsum_out, partial_ws, static_cast<cudaStream_t>(stream));
+  GVIT_REQUIRE(skip_period >= 0, GVIT_ERR_SHAPE, "dropout_bwd: skip_period=%d must be >= 0", skip_period);
+  return dropout_bwd(dout, keep_mask, n, p, dtype, y_dtype, dy, D, skip_period, colsum_out, partial_ws, static_cast<cudaStream_t>(stream));
 }
 
 int gvit_gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype,

@@ -50,11 +50,11 @@ int layernorm_fwd(const void* x, const void* gamma, const void* beta, int64_t ro
 int layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, int64_t rows,
                   int D, int dtype, int y_dtype, const void* dx_add, void* dx, float* dgamma, float* dbeta,
                   float* partial_ws, cudaStream_t st);
-int colsum(const void* x, int64_t rows, int D, int dtype, float* out, float* partial_ws, cudaStream_t st);
+int colsum(const void* x, int64_t rows, int D, int dtype, int skip_period, float* out, float* partial_ws, cudaStream_t st);
 int dropout_residual_fwd(const void* y, const void* resid, int64_t n, float p, uint64_t seed, uint64_t offset,
                          const uint64_t* offset_dev, int dtype, int y_dtype, void* out, uint8_t* keep_mask, cudaStream_t st);
 int dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, int y_dtype, void* dy,
-                int D, float* colsum_out, float* partial_ws, cudaStream_t st);
+                int D, int skip_period, float* colsum_out, float* partial_ws, cudaStream_t st);
 int gelu_dropout_fwd(const void* u, int64_t n, float p, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype,
                      void* out, uint8_t* keep_mask, cudaStream_t st);
 int gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, int64_t n, float p, int dtype, void* du,

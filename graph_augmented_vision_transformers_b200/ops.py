@@ -235,13 +235,14 @@ def attention_core(qkv: torch.Tensor, num_heads: int, scale: float) -> torch.Ten
 # a1 / a3: the Linear layers around the fused kernels (library GEMMs; libgvit supplies the bias gradient)
 # ------------------------------------------------------------------------------------------------
 @torch.no_grad()
-def colsum(x2: torch.Tensor) -> torch.Tensor:
-    """fp32 column sums of a contiguous (rows, D) tensor - deterministic two-pass reduction (gvit_colsum)."""
+def colsum(x2: torch.Tensor, skip_period: int = 0) -> torch.Tensor:
+    """fp32 column sums of a contiguous (rows, D) tensor - deterministic two-pass reduction (gvit_colsum).
+    ``skip_period`` > 0 leaves rows r with r % skip_period == 0 out (the CLS rows of a (B, 1+Np, D) tensor)."""
     _check_cuda(x2)
     rows, D = x2.shape
     out = torch.empty(D, dtype=torch.float32, device=x2.device)
     ws = _colsum_ws(rows, D, x2.device)
-    _call("gvit_colsum", _ptr(x2), rows, D, _dtype_code(x2), _ptr(out), _ptr(ws), _stream())
+    _call("gvit_colsum", _ptr(x2), rows, D, _dtype_code(x2), int(skip_period), _ptr(out), _ptr(ws), _stream())
     return out
 
 
@@ -416,7 +417,7 @@ class _DropoutAdd(torch.autograd.Function):
         dout = dout.contiguous()
         dy = torch.empty(dout.shape, dtype=ctx.y_dtype, device=dout.device)
         _call("gvit_dropout_bwd", _ptr(dout), _ptr(mask), dout.numel(), float(ctx.p), _dtype_code(dout),
-              _dtype_code(dy), _ptr(dy), 0, None, None, _stream())
+              _dtype_code(dy), _ptr(dy), 0, 0, None, None, _stream())
         return dy, dresid, None, None
 
 
@@ -533,7 +534,7 @@ class _LinearDropoutAdd(torch.autograd.Function):
         ws = _colsum_ws(dout.numel() // Dn, Dn, dout.device) if want_db else None
         if ctx.p > 0 or want_db:
             _call("gvit_dropout_bwd", _ptr(dout), _ptr(mask), dout.numel(), float(ctx.p), _dtype_code(dout),
-                  _dtype_code(dy), _ptr(dy), Dn, _ptr(db), _ptr(ws), _stream())
+                  _dtype_code(dy), _ptr(dy), Dn, 0, _ptr(db), _ptr(ws), _stream())
         else:
             dy = dout.to(ctx.y_dtype)
         dx, dw = _linear_grads(ctx.needs_input_grad, x, weight, dy.view(-1, Dn), ctx.w_dtype)
@@ -626,7 +627,7 @@ class _MlpFused(torch.autograd.Function):
         ws2 = _colsum_ws(M, D2, dout.device) if db2 is not None else None
         if ctx.p > 0 or db2 is not None:
             _call("gvit_dropout_bwd", _ptr(dout), _ptr(mask2), dout.numel(), float(ctx.p), _dtype_code(dout), _dtype_code(dy),
-                  _ptr(dy), D2, _ptr(db2), _ptr(ws2), st)
+                  _ptr(dy), D2, 0, _ptr(db2), _ptr(ws2), st)
         else:
             dy = dout.to(ctx.y_dtype)
         dy2 = dy.view(M, D2)
@@ -743,7 +744,7 @@ class _PatchEmbedTokens(torch.autograd.Function):
             # keep mask (and, for an fp32 stream gradient, the cast to the GEMM dtype) in one pass
             d = torch.empty(dout.shape, dtype=ctx.dt, device=dout.device)
             _call("gvit_dropout_bwd", _ptr(dout), _ptr(mask), dout.numel(), float(ctx.p), _dtype_code(dout),
-                  _dtype_code(d), _ptr(d), 0, None, None, _stream())
+                  _dtype_code(d), _ptr(d), 0, 0, None, None, _stream())
         else:
             d = dout
         dsum = colsum(d.view(B, N * D)).view(N, D)              # fp32 sum over the batch: d pos_embed
@@ -914,12 +915,14 @@ class _PatchGraph(torch.autograd.Function):
                 d2 = torch.empty((B * (Np + 1), D), dtype=h.dtype, device=h.device)
                 cs = torch.empty(D, dtype=torch.float32, device=h.device) if want_db else None
                 ws = _colsum_ws(B * (Np + 1), D, h.device) if want_db else None
-                _call("gvit_dropout_bwd", _ptr(dout), None, dout.numel(), 0.0, _dtype_code(dout), dt, _ptr(d2), D, _ptr(cs), _ptr(ws), st)
+                _call("gvit_dropout_bwd", _ptr(dout), None, dout.numel(), 0.0, _dtype_code(dout), dt, _ptr(d2), D, Np + 1, _ptr(cs), _ptr(ws), st)
             else:
                 d2 = dout.view(B * (Np + 1), D)
-                cs = colsum(d2) if want_db else None
+                cs = colsum(d2, skip_period=Np + 1) if want_db else None
+            # the column sums leave the CLS rows out (skip_period): the projection only ever saw patch rows (G0), so its bias
+            # gradient is exactly zero when they carry no gradient (the last block: the head reads the CLS token only)
             dweight = _wgrad(d2, z.view(B * (Np + 1), D), ctx.w_dtype) if ctx.needs_input_grad[1] else None
-            dbias = (cs - dout[:, 0].float().sum(0)).to(ctx.b_dtype) if want_db else None
+            dbias = cs.to(ctx.b_dtype) if want_db else None
             dh = None
             if ctx.needs_input_grad[0]:
                 dz = d2 @ weight                                   # (B*(1+Np), D)

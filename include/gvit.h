@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GVIT_ABI_VERSION 12
+#define GVIT_ABI_VERSION 13
 #if defined(__GNUC__)
 #define GVIT_API __attribute__((visibility("default")))
 #else
@@ -139,9 +139,12 @@ GVIT_API int gvit_layernorm_bwd(const void* dy, const void* x, const void* gamma
                        int64_t rows, int D, int dtype, int y_dtype, const void* dx_add, void* dx, float* dgamma,
                        float* dbeta, float* partial_ws, void* stream);
 /* Column sums out[c] = sum_r x[r*D + c] (fp32 result): the bias gradient of the nn.Linear layers of the block
- * (vit.py:50,52,83,85) from the gradient of their output.  partial_ws: GVIT_COLSUM_CHUNKS * D floats.  Deterministic. */
+ * (vit.py:50,52,83,85) from the gradient of their output.  partial_ws: GVIT_COLSUM_CHUNKS * D floats.  Deterministic.
+ * skip_period > 0 leaves the rows r with r % skip_period == 0 out of the sums - the CLS rows of a (B, 1+Np, D) token
+ * tensor with skip_period = 1+Np: the graph projection only sees patch rows (section 9 G0), so its bias gradient is the
+ * sum over patch rows and is exactly zero when they carry no gradient.  0 = every row. */
 enum { GVIT_COLSUM_CHUNKS = 1024 };
-GVIT_API int gvit_colsum(const void* x, int64_t rows, int D, int dtype, float* out, float* partial_ws, void* stream);
+GVIT_API int gvit_colsum(const void* x, int64_t rows, int D, int dtype, int skip_period, float* out, float* partial_ws, void* stream);
 
 /* out = resid + dropout(y, p) with a Philox-4x32-7 keep mask generated from (seed, offset) - the proj_drop +
  * residual edge of vit.py:71,117 (also pos_drop, vit.py:212, with resid NULL).  p == 0 degenerates to an add.
@@ -155,9 +158,10 @@ GVIT_API int gvit_dropout_residual_fwd(const void* y, const void* resid, int64_t
 /* dy = dout * keep / (1 - p);  dout has `dtype`, dy has `y_dtype`.
  * With colsum_out != NULL the same pass also writes colsum_out[c] = sum_r dy[r*D + c] (fp32, D values; the tensor is
  * read as n/D rows of D) - the bias gradient of the Linear whose output was dropped out (vit.py:70-71, 93-94);
- * partial_ws then holds GVIT_COLSUM_CHUNKS * D floats, and p == 0 (keep_mask NULL) is allowed: a cast + column sum. */
+ * partial_ws then holds GVIT_COLSUM_CHUNKS * D floats, and p == 0 (keep_mask NULL) is allowed: a cast + column sum.
+ * skip_period: as for gvit_colsum (rows left out of the column sums; dy is written for every row). */
 GVIT_API int gvit_dropout_bwd(const void* dout, const uint8_t* keep_mask, int64_t n, float p, int dtype, int y_dtype, void* dy,
-                     int D, float* colsum_out, float* partial_ws, void* stream);
+                     int D, int skip_period, float* colsum_out, float* partial_ws, void* stream);
 
 /* ---- Mlp activation edge: out = dropout(GELU(u), p), exact-erf GELU - nn.GELU + nn.Dropout at vit.py:84,92 in one
  * pass; the backward recomputes GELU' from the saved pre-activation u (no activation tensor is kept).

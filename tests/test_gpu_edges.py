@@ -106,6 +106,15 @@ def test_colsum_matches_fp64_sum(rows, D, dtype):
     assert got.dtype == torch.float32
     assert float((got.double() - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max())) + 1e-3
     assert torch.equal(got, ops.colsum(x))                  # fixed reduction order
+    if rows > 7:                                            # skip_period: rows 0, 7, 14, ... left out (CLS rows of a token tensor)
+        keep = torch.ones(rows, dtype=torch.bool, device=x.device)
+        keep[::7] = False
+        want7 = x.double()[keep].sum(0)
+        got7 = ops.colsum(x, skip_period=7)
+        assert float((got7.double() - want7).abs().max()) <= 1e-5 * float(x.double().abs().sum(0).max()) + 1e-6
+        xz = x.clone()
+        xz[keep] = 0                                        # only skipped rows carry values: the sums are EXACTLY zero
+        assert float(ops.colsum(xz, skip_period=7).abs().max()) == 0.0
 
 
 def test_linear_matches_torch_linear_forward_and_backward():

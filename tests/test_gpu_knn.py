@@ -92,9 +92,12 @@ def test_duplicated_rows_everywhere_bf16():
     assert (vals[..., 0::2] == vals[..., 1::2]).all()
 
 
+# all-row match fraction of the tcgen05 kernel against the strict fp32 oracle on the same bf16 values: MEASURED 1.00000 on
+# every shape below (profiles/r2b_knn_match.txt); the floor only leaves room for a near-tie inside the accumulation-order
+# noise on another seed.  (was 0.97 in round 1, never measured)
 # measured floor of the all-row match fraction of the tcgen05 kernel against the strict fp32 oracle on the same bf16
 # values (profiles/r2*_knn_match.txt); rows that differ are near-ties inside the accumulation-order noise
-BF16_ALL_ROW_MATCH_FLOOR = 0.97
+BF16_ALL_ROW_MATCH_FLOOR = 0.995
 
 
 @pytest.mark.parametrize("B,Np,D,k", [(3, 196, 768, 8), (2, 196, 768, 4), (2, 196, 768, 16), (1, 16, 64, 1),
@@ -115,10 +118,12 @@ def test_bf16_indices_vs_float64_oracle(B, Np, D, k):
 
 @pytest.mark.parametrize("B,Np,D,k", [(2, 196, 768, 8), (1, 50, 72, 5), (2, 576, 1024, 8), (1, 8, 8, 8)])
 def test_fp32_indices_vs_float64_oracle(B, Np, D, k):
-    """the strict fp32 result is also the mathematically right one wherever fp32 can tell (float64 cross-check)."""
+    """the strict fp32 result is also the mathematically right one wherever fp32 can tell (float64 cross-check).
+    The noise band follows the specification's sequential fp32 chain: its round-off grows with the chain length D
+    (measured max |S_fp32 - S_f64| = 2.03e-6 at D = 1024), so the band is 3e-9 * D, floored at 2e-6."""
     hc, hd = tokens(B, Np, D, seed=Np + k)
     idx, vals, _ = ops.knn_graph(hd, k)
-    check_adjacency(hc, idx, vals, k, noise=2e-6)
+    check_adjacency(hc, idx, vals, k, noise=max(2e-6, 3e-9 * D))
 
 
 def test_full_size_properties_config2():
