@@ -18,6 +18,7 @@
 //
 // Tile conventions are those of tc.cuh: [rows][64 bf16] 128B-swizzled tiles, K-major or MN-major by descriptor.
 #include <float.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 #include "tc.cuh"
@@ -391,6 +392,428 @@ __global__ void __launch_bounds__(B_THREADS, 1) graph_dp_tc_kernel(const __grid_
   if (warp == 5) tmem_dealloc(tmem, 128);
 }
 
+// =================================================================================================
+// fused persistent kernel (round 2): kernels A and B above as ONE launch, one image per CTA iteration
+// =================================================================================================
+// The split pair reads P and dZ from DRAM twice (157 + 161 MB per launch at B = 256 against 154 MB of operands: the
+// dvals kernel streams both, then the dp kernel streams both again after the first pass has been evicted by the
+// other 255 images) and launches 1.73 / 3.46 waves of one-shot CTAs.  Here a persistent CTA takes one image through
+//   phase A   G = dZ P^T over the D/64 slabs (tcgen05, fp32 G in TMEM: 2 x NT columns)
+//   extract   thread <-> row copies its G row through a private shared-memory strip 32 columns at a time and picks
+//             dw_ij = G[i, idx_ij] with k indexed reads (the split kernel compared all NT columns against all k
+//             neighbours: NT x k predicated moves per row), softmax backward -> dvals
+//   per 128-row tile of the image: build [A~^T | M3] in shared memory (as kernel B), then
+//   phase B   dp[tile, 128 features] = coef [dZ ; P] with N = 128 per instruction (two 64-feature slabs side by side as
+//             one MN-major operand; kernel B issued N = 64: 32 math cycles under ~73 cycles of operand fetch)
+// so the second and third pass over the image's P / dZ slabs (602 KB) hit L2 a few microseconds after the first, and
+// DRAM sees every operand once.  One ring of four NT x 64 slots feeds both phases; the coefficient tile doubles as
+// the extraction scratch; the output goes from TMEM to global memory directly (thread <-> row writes 128 contiguous
+// bytes: full lines, no staging tile - there is no shared memory left for one).
+constexpr int F_THREADS = 320;                 // warps 0-7 workers, warp 8 TMA producer, warp 9 MMA issuer
+constexpr int F_SLOTS = 4;
+struct __align__(8) FCtrl {
+  float rn[256];
+  int tfix[128];                               // t_j in fixed point (per-image scale), one fire-and-forget RED.ADD per edge
+  int tmax_bits[2];                            // max |dS_e S_e| of the image as float bits (double-buffered by image parity)
+  uint64_t full[F_SLOTS], empty[F_SLOTS], g_full, a_ready, coef_free, out_full[2], out_free[2];
+  uint32_t tmem_base;
+};
+struct FParams {
+  int B, Np, D, k, NT, nblk, slot_bytes;
+  uint32_t kmagic;                             // ceil(2^32 / k): e / k == __umulhi(e, kmagic) for e < 2^16
+  const int32_t* idx;
+  const float* w;
+  const float* vals;
+  float* dvals;                                // written (extract) and re-read (build) by the same CTA
+  const float* rnorm;
+  __nv_bfloat16* dp;
+  int64_t dp_bs, dp_rs;                        // batch / row stride of dp in elements
+};
+
+template <int KT>
+__global__ void __launch_bounds__(F_THREADS, 1) graph_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_dz,
+                                                                       const __grid_constant__ CUtensorMap tm_p,
+                                                                       const FParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sA = smem_raw;                                  // nblk blocks of [128][64]: coefficient tile / extraction scratch
+  if ((smem_u32(sA) & 1023u) != 0) __trap();
+  uint8_t* ring = sA + (size_t)P.nblk * TILE;              // F_SLOTS slots of [NT][64]
+  FCtrl* ctl = reinterpret_cast<FCtrl*>(ring + (size_t)F_SLOTS * P.slot_bytes);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int NT = P.NT, Np = P.Np, k = P.k;
+  const int slabs = P.D / 64;
+  const int fblocks = (slabs + 1) / 2;
+  const int mtiles = Np > 128 ? 2 : 1;
+  const int ksteps = NT / 16;
+  GVIT_TRACE_DECL
+
+  if (warp == 8 && lane == 0) {
+    prefetch_tmap(&tm_dz);
+    prefetch_tmap(&tm_p);
+    for (int s = 0; s < F_SLOTS; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&ctl->out_full[s], 1); mbar_init(&ctl->out_free[s], 256); }
+    mbar_init(&ctl->g_full, 1);
+    mbar_init(&ctl->a_ready, 256);
+    mbar_init(&ctl->coef_free, 1);
+    ctl->tmax_bits[0] = ctl->tmax_bits[1] = 0;
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc(&ctl->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
+
+  if (warp == 8) {
+    // ---------------------------------------------------------------- TMA producer
+    if (elect_one()) {
+      uint32_t pi = 0;
+      // Every pass but the last asks L2 to keep the slab (evict_last): the image's 2 x Np x D operands are re-read by this
+      // CTA a few microseconds later while 147 other CTAs stream theirs through the same L2; the last pass releases it.
+      auto load = [&](const CUtensorMap* tm, int slab, int b, uint64_t policy) {
+        const uint32_t s = pi & (F_SLOTS - 1);
+        mbar_wait(&ctl->empty[s], ((pi / F_SLOTS) & 1) ^ 1);
+        mbar_expect_tx(&ctl->full[s], (uint32_t)(NT * 128));
+        tma_load_3d_hint(ring + (size_t)s * P.slot_bytes, tm, slab * 64, 0, b, &ctl->full[s], policy);
+        ++pi;
+      };
+      for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
+        GVIT_TR(20);
+        for (int s = 0; s < slabs; ++s) { load(&tm_dz, s, b, L2_EVICT_LAST); load(&tm_p, s, b, L2_EVICT_LAST); }
+        GVIT_TR(21);
+        for (int mt = 0; mt < mtiles; ++mt) {
+          const uint64_t pol = mt + 1 < mtiles ? L2_EVICT_LAST : L2_EVICT_FIRST;
+          for (int f = 0; f < fblocks; ++f) {
+            const int nsl = slabs - 2 * f >= 2 ? 2 : 1;
+            for (int c = 0; c < nsl; ++c) load(&tm_dz, 2 * f + c, b, pol);
+            for (int c = 0; c < nsl; ++c) load(&tm_p, 2 * f + c, b, pol);
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc_g = make_idesc(128, NT, false, false);
+      const uint32_t aA = smem_u32(sA), aR = smem_u32(ring);
+      uint32_t ci = 0, na = 0, uses[2] = {0, 0}, tcount = 0;
+      auto wait_full = [&](uint32_t c) { mbar_wait(&ctl->full[c & (F_SLOTS - 1)], (c / F_SLOTS) & 1); };
+      auto slot_addr = [&](uint32_t c) { return aR + (c & (F_SLOTS - 1)) * (uint32_t)P.slot_bytes; };
+      for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
+        // the Gram accumulators overlay the output buffers: the previous image's last tiles must have been drained
+        for (int q = 0; q < 2; ++q)
+          if (uses[q] > 0) mbar_wait(&ctl->out_free[q], (uses[q] - 1) & 1);
+        tc_fence_after();
+        GVIT_TR(1);
+        for (int s = 0; s < slabs; ++s) {
+          wait_full(ci);
+          wait_full(ci + 1);
+          tc_fence_after();
+          const uint32_t aZ = slot_addr(ci), aP = slot_addr(ci + 1);
+          for (int mt = 0; mt < mtiles; ++mt)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_ss(tmem + mt * 256, make_sdesc(aZ + mt * TILE + kk * 32), make_sdesc(aP + kk * 32), idesc_g, s > 0 || kk > 0);
+          umma_commit(&ctl->empty[ci & (F_SLOTS - 1)]);
+          umma_commit(&ctl->empty[(ci + 1) & (F_SLOTS - 1)]);
+          ci += 2;
+        }
+        umma_commit(&ctl->g_full);
+        GVIT_TR(2);
+        for (int mt = 0; mt < mtiles; ++mt) {
+          mbar_wait(&ctl->a_ready, na & 1);
+          ++na;
+          tc_fence_after();
+          GVIT_TR(3);
+          for (int f = 0; f < fblocks; ++f) {
+            const int nsl = slabs - 2 * f >= 2 ? 2 : 1;
+            const uint32_t idesc_o = make_idesc(128, 64 * nsl, false, true);   // coefficients K-major, slab pair MN-major
+            const uint32_t buf = tcount & 1;
+            mbar_wait(&ctl->out_free[buf], (uses[buf] & 1) ^ 1);               // this buffer's previous tile drained
+            ++uses[buf];
+            tc_fence_after();
+            for (int half = 0; half < 2; ++half) {                             // K = [NT rows of dZ | NT rows of P]
+              GVIT_TR(5);
+              for (int c = 0; c < nsl; ++c) wait_full(ci + c);
+              tc_fence_after();
+              GVIT_TR(6);
+              const uint32_t aS = slot_addr(ci);
+              for (int kk = 0; kk < ksteps; ++kk) {
+                const int kg = half * ksteps + kk;
+                const uint64_t bdesc = nsl == 2 ? make_sdesc_lbo(aS + kk * 2048, (uint32_t)P.slot_bytes) : make_sdesc(aS + kk * 2048);
+                umma_ss(tmem + buf * 128, make_sdesc(aA + (kg >> 2) * TILE + (kg & 3) * 32), bdesc, idesc_o, half > 0 || kk > 0);
+              }
+              for (int c = 0; c < nsl; ++c) umma_commit(&ctl->empty[(ci + c) & (F_SLOTS - 1)]);
+              ci += nsl;
+            }
+            umma_commit(&ctl->out_full[buf]);
+            ++tcount;
+            GVIT_TR(4);
+          }
+          umma_commit(&ctl->coef_free);
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- workers (256 threads)
+    const int tid = threadIdx.x;
+    const int E = Np * k;
+    uint32_t it = 0, ncoef = 0, tcount = 0;
+    const int g = warp >> 2;                                           // extraction: row tile of this warp
+    const int wrow0 = g * 128 + (warp & 3) * 32;
+    float* scr = reinterpret_cast<float*>(sA) + warp * (32 * 36) + lane * 36;
+    for (int b = blockIdx.x; b < P.B; b += gridDim.x, ++it) {
+      const int32_t* idx_b = P.idx + (int64_t)b * E;
+      const float* w_b = P.w + (int64_t)b * E;
+      const float* v_b = P.vals + (int64_t)b * E;
+      float* ds_b = P.dvals + (int64_t)b * E;
+      // ---- extract: dvals of row (wrow0 + lane) ------------------------------------------------------------------
+      {
+        const int row = wrow0 + lane;
+        const bool active = g < mtiles && wrow0 < Np;                  // warp-uniform
+        const bool valid = row < Np;
+        const int64_t o = (int64_t)(valid ? row : 0) * k;
+        int nb[KT];
+        float wj[KT], dw[KT];
+        if (active) {
+#pragma unroll
+          for (int j = 0; j < KT; ++j) {
+            const bool on = valid && j < k;
+            nb[j] = on ? idx_b[o + j] : -1;
+            wj[j] = on ? w_b[o + j] : 0.f;
+            dw[j] = 0.f;
+          }
+        }
+        for (int i = tid; i < 256; i += 256) ctl->rn[i] = i < Np ? P.rnorm[(int64_t)b * Np + i] : 0.f;
+        if (ncoef > 0) mbar_wait(&ctl->coef_free, (ncoef - 1) & 1);    // the scratch is the (retired) coefficient tile
+        mbar_wait(&ctl->g_full, it & 1);
+        tc_fence_after();
+        GVIT_TR(10);
+        if (active) {
+          const uint32_t trow = tmem_lane_base(tmem, warp) + g * 256;
+          for (int c0 = 0; c0 < NT; c0 += 32) {
+            float v[32];
+            if (NT - c0 >= 32) {
+              tmem_ld32(trow + c0, v);
+            } else {                                                    // 16-column tail: do not read columns the MMA never wrote
+              float v16[16];
+              tmem_ld16(trow + c0, v16);
+#pragma unroll
+              for (int t = 0; t < 16; ++t) { v[t] = v16[t]; v[16 + t] = 0.f; }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(scr + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+#pragma unroll
+            for (int j = 0; j < KT; ++j)
+              if (nb[j] >= c0 && nb[j] < c0 + 32) dw[j] = scr[nb[j] - c0];
+          }
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < KT; ++j) s = fmaf(wj[j], dw[j], s);
+          if (valid) {
+            float m = 0.f;
+#pragma unroll
+            for (int j = 0; j < KT; ++j)
+              if (j < k) {
+                const float d = wj[j] * (dw[j] - s);
+                ds_b[o + j] = d;
+                m = fmaxf(m, fabsf(d * v_b[o + j]));
+              }
+            atomicMax(&ctl->tmax_bits[it & 1], __float_as_int(m));      // non-negative floats order like their bit patterns
+          }
+        }
+        tc_fence_before();
+        asm volatile("bar.sync 1, 256;" ::: "memory");                 // dvals visible CTA-wide, G read out, scratch free
+        if (tid == 0) ctl->tmax_bits[(it + 1) & 1] = 0;                // nobody touches the other image parity right now
+        GVIT_TR(11);
+      }
+      // fixed-point scale of t_j: every term is <= M = max |dS_e S_e| < 2^(e+1), a row sums at most 2^9 of them, so terms
+      // scaled by 2^(20-e) keep |sum| < 2^31; the sum is exact integer arithmetic: identical for every arrival order
+      float tscale, tinv;
+      {
+        const int bits = ctl->tmax_bits[it & 1];
+        const int ex = (bits >> 23) & 0xff;
+        int se = ex == 0 ? 0 : 127 + 20 - (ex - 127);
+        se = se > 254 ? 254 : se;
+        tscale = __int_as_float(se << 23);
+        tinv = se == 0 ? 0.f : __int_as_float((254 - se) << 23);
+      }
+      // ---- per row tile: coefficient tile, then the output tiles ----------------------------------------------------
+      for (int mt = 0; mt < mtiles; ++mt) {
+        const int j0 = mt * 128;
+        if (mt > 0) mbar_wait(&ctl->coef_free, (ncoef - 1) & 1);       // every MMA that read the previous tile has retired
+        ++ncoef;
+        GVIT_TR(12);
+        {
+          constexpr int EPT = 8;                                        // edges per thread: 256 * 8 = 2048 per pass
+          auto tfix_add = [&](int j, float x) { atomicAdd(&ctl->tfix[j], __float2int_rn(x * tscale)); };
+          const int jg = j0 + tid;
+          const bool valid = tid < 128 && jg < Np;
+          int ii1[8];
+          float ds1[8], vv1[8];
+          const int kk1 = min(k, 8);
+          if (valid) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int e = jg * k + min(u, k - 1);
+              ii1[u] = idx_b[e];
+              ds1[u] = ds_b[e];
+              vv1[u] = v_b[e];
+            }
+          }
+          int jj[EPT];
+#pragma unroll
+          for (int u = 0; u < EPT; ++u) {
+            const int e = u * 256 + tid;
+            jj[u] = e < E ? idx_b[e] - j0 : -1;
+          }
+          const uint4 z4 = make_uint4(0, 0, 0, 0);
+          for (int i = tid; i < P.nblk * TILE / 16; i += 256) reinterpret_cast<uint4*>(sA)[i] = z4;
+          if (tid < 128) ctl->tfix[tid] = 0;
+          float ww[EPT], dsv[EPT], vv[EPT];
+#pragma unroll
+          for (int u = 0; u < EPT; ++u) {
+            const int e = u * 256 + tid;
+            if (jj[u] >= 0 && jj[u] < 128) { ww[u] = w_b[e]; dsv[u] = ds_b[e]; vv[u] = v_b[e]; }
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          // phase 1: the row's own k entries of dS (forward edges j -> i)
+          if (valid) {
+            const float rnj = ctl->rn[jg];
+            int tacc = 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if (u < kk1) {
+                *a2_cell(sA, tid, NT + ii1[u]) = __float2bfloat16_rn(rnj * ctl->rn[ii1[u]] * ds1[u]);
+                tacc += __float2int_rn(ds1[u] * vv1[u] * tscale);
+              }
+            }
+            for (int s = 8; s < k; ++s) {                               // k > 8: the remaining own entries, one by one
+              const int e = jg * k + s;
+              const int i = idx_b[e];
+              const float ds = ds_b[e];
+              *a2_cell(sA, tid, NT + i) = __float2bfloat16_rn(rnj * ctl->rn[i] * ds);
+              tacc += __float2int_rn(ds * v_b[e] * tscale);
+            }
+            atomicAdd(&ctl->tfix[tid], tacc);
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          // phase 2: every edge i -> j of the image that lands in this tile: A~^T[j,i] = w_e, M3[j,i] += rn_j rn_i dS_e.
+          // (j,i) pairs are unique over the edges (a row's k neighbours are distinct), so the 16-bit updates do not race.
+          auto apply_edge = [&](int e, int j, float we, float ds, float v) {
+            const int i = (int)__umulhi((unsigned)e, P.kmagic);        // e / k
+            *a2_cell(sA, j, i) = __float2bfloat16_rn(we);
+            __nv_bfloat16* c = a2_cell(sA, j, NT + i);
+            *c = __float2bfloat16_rn(__bfloat162float(*c) + ctl->rn[j0 + j] * ctl->rn[i] * ds);
+            tfix_add(j, ds * v);
+          };
+#pragma unroll
+          for (int u = 0; u < EPT; ++u)
+            if (jj[u] >= 0 && jj[u] < 128) apply_edge(u * 256 + tid, jj[u], ww[u], dsv[u], vv[u]);
+          for (int e = EPT * 256 + tid; e < E; e += 256) {              // images with more than 2048 edges
+            const int j = idx_b[e] - j0;
+            if (j >= 0 && j < 128) apply_edge(e, j, w_b[e], ds_b[e], v_b[e]);
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          // phase 3: the radial term on the diagonal
+          if (valid) {
+            const float rnj = ctl->rn[jg];
+            const float t = static_cast<float>(ctl->tfix[tid]) * tinv;
+            __nv_bfloat16* c = a2_cell(sA, tid, NT + jg);
+            *c = __float2bfloat16_rn(__bfloat162float(*c) - rnj * rnj * t);
+          }
+          fence_async_smem();
+          mbar_arrive(&ctl->a_ready);
+          GVIT_TR(13);
+        }
+        // ---- output tiles of this row tile: TMEM -> bf16 -> global (warp & 3 = lane quadrant, warp >> 2 = column half) ----
+        const int orow = j0 + (warp & 3) * 32 + lane;
+        const int hsel = warp >> 2;
+        for (int f = 0; f < fblocks; ++f, ++tcount) {
+          const int nsl = slabs - 2 * f >= 2 ? 2 : 1;
+          const uint32_t buf = tcount & 1;
+          mbar_wait(&ctl->out_full[buf], (tcount >> 1) & 1);
+          tc_fence_after();
+          GVIT_TR(14);
+          const uint32_t tO = tmem_lane_base(tmem, warp) + buf * 128 + hsel * (32 * nsl);
+          float v0[32], v1[32];
+          tmem_ld32(tO, v0);
+          if (nsl == 2) tmem_ld32(tO + 32, v1);
+          tc_fence_before();
+          mbar_arrive(&ctl->out_free[buf]);
+          if (nsl == 2) {
+            // thread <-> row holds 64 features = eight 16-byte chunks.  A store instruction with one row per lane touches 32
+            // lines (16 bytes each): 2048 line-tag lookups per tile paced the whole kernel (4.5k cycles per tile against
+            // 2.4k of MMA).  An 8 x 8 chunk transpose inside each 8-lane group (three butterfly rounds, 48 shuffles) makes
+            // store s write rows 8g + s with lanes 8g .. 8g+7 covering one full 128-byte line each: 4 lines per instruction.
+            uint32_t c[8][4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              c[q][0] = pack2(v0[8 * q + 0], v0[8 * q + 1]); c[q][1] = pack2(v0[8 * q + 2], v0[8 * q + 3]);
+              c[q][2] = pack2(v0[8 * q + 4], v0[8 * q + 5]); c[q][3] = pack2(v0[8 * q + 6], v0[8 * q + 7]);
+              c[4 + q][0] = pack2(v1[8 * q + 0], v1[8 * q + 1]); c[4 + q][1] = pack2(v1[8 * q + 2], v1[8 * q + 3]);
+              c[4 + q][2] = pack2(v1[8 * q + 4], v1[8 * q + 5]); c[4 + q][3] = pack2(v1[8 * q + 6], v1[8 * q + 7]);
+            }
+#pragma unroll
+            for (int m = 1; m <= 4; m <<= 1) {
+              const bool up = (lane & m) != 0;
+#pragma unroll
+              for (int a = 0; a < 8; ++a) {
+                if (a & m) continue;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const uint32_t send = up ? c[a][e] : c[a | m][e];
+                  const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, m);
+                  if (up) c[a][e] = recv; else c[a | m][e] = recv;
+                }
+              }
+            }
+            // slot s of lane 8g + j now holds chunk j of row 8g + s
+            const int rbase = j0 + (warp & 3) * 32 + (lane & ~7);
+            __nv_bfloat16* dst = P.dp + (int64_t)b * P.dp_bs + (int64_t)rbase * P.dp_rs + f * 128 + hsel * 64 + (lane & 7) * 8;
+#pragma unroll
+            for (int s8 = 0; s8 < 8; ++s8)
+              if (rbase + s8 < Np)
+                st_global_hint(dst + (int64_t)s8 * P.dp_rs, make_uint4(c[s8][0], c[s8][1], c[s8][2], c[s8][3]), L2_EVICT_FIRST);
+          } else if (orow < Np) {                                       // single 64-feature slab (D % 128 != 0): 32 features per thread
+            __nv_bfloat16* dst = P.dp + (int64_t)b * P.dp_bs + (int64_t)orow * P.dp_rs + f * 128 + hsel * 32;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o4;
+              o4.x = pack2(v0[8 * q + 0], v0[8 * q + 1]); o4.y = pack2(v0[8 * q + 2], v0[8 * q + 3]);
+              o4.z = pack2(v0[8 * q + 4], v0[8 * q + 5]); o4.w = pack2(v0[8 * q + 6], v0[8 * q + 7]);
+              st_global_hint(dst + 8 * q, o4, L2_EVICT_FIRST);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem, 512);
+}
+
+inline size_t f_smem(int NT, int* nblk, int* slot_bytes) {
+  *nblk = (2 * NT + 63) / 64;
+  if (*nblk < 3) *nblk = 3;                                             // the extraction strips (8 x 32 x 36 floats) live in this region
+  *slot_bytes = NT * 128;
+  // phase A reads 128-row A operands out of NT-row slots: the rows past a slot's end are garbage that lands in unused Gram
+  // rows, but the bytes must exist - the last slot is followed by the control block and padding up to 128 (256) rows
+  const size_t over = (size_t)((NT > 128 ? 256 : 128) - NT) * 128;
+  return (size_t)*nblk * TILE + (size_t)F_SLOTS * *slot_bytes + (over > sizeof(FCtrl) ? over : sizeof(FCtrl));
+}
+
+template <int KT>
+int launch_fused(const CUtensorMap& tm_dz, const CUtensorMap& tm_p, const FParams& P, size_t smem, cudaStream_t st) {
+  GVIT_CHECK_CUDA(cudaFuncSetAttribute(graph_bwd_fused_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = P.B < num_sms() ? P.B : num_sms();
+  graph_bwd_fused_kernel<KT><<<grid, F_THREADS, smem, st>>>(tm_dz, tm_p, P);
+  GVIT_CHECK_LAUNCH();
+  return GVIT_OK;
+}
+
 template <int KT>
 int launch_a(const CUtensorMap& tm_dz, const CUtensorMap& tm_p, const Tokens& t, int k, int NT, const int32_t* idx,
              const float* w, float* dvals, cudaStream_t st) {
@@ -413,18 +836,31 @@ GVIT_TRACE_SETTER(gvit_debug_set_trace_graph_bwd)
 bool graph_bwd_tc_supported(int Np, int D, int k) {
   int nblk, sb;
   const int NT = (Np + 15) & ~15;
-  return Np >= 16 && Np <= 256 && D >= 64 && D % 64 == 0 && D <= 1024 && k <= 16 && b_smem(NT, &nblk, &sb) <= 227 * 1024;
+  return Np >= 16 && Np <= 256 && D >= 64 && D % 64 == 0 && D <= 1024 && k <= 16 && f_smem(NT, &nblk, &sb) <= 227 * 1024;
 }
 
 int graph_bwd_tc(const Tokens& t, int k, const int32_t* idx, const float* vals, const float* w, const float* rnorm,
                  const void* dz, int64_t dz_batch_stride, float* dvals, void* dp, cudaStream_t st) {
   const int NT = (t.Np + 15) & ~15;
-  GVIT_REQUIRE(t.B <= 65535, GVIT_ERR_SHAPE, "graph_bwd: batch %d exceeds the grid limit 65535", t.B);
-  CUtensorMap tm_dz, tm_p, tm_dp;
+  CUtensorMap tm_dz, tm_p;
   int rc = make_tmap_bf16_3d(&tm_dz, dz, t.D, t.Np, t.B, t.D, (uint64_t)dz_batch_stride, NT);
   if (rc != GVIT_OK) return rc;
   rc = make_tmap_bf16_3d(&tm_p, t.ptr, t.D, t.Np, t.B, t.row_stride, t.batch_stride, NT);
   if (rc != GVIT_OK) return rc;
+  static const bool split = getenv("GVIT_GRAPH_BWD_SPLIT") != nullptr;   // A/B switch: the round-1 two-kernel version
+  if (!split) {
+    FParams P;
+    P.B = t.B; P.Np = t.Np; P.D = t.D; P.k = k; P.NT = NT;
+    const size_t smem = f_smem(NT, &P.nblk, &P.slot_bytes);
+    P.idx = idx; P.w = w; P.vals = vals; P.dvals = dvals; P.rnorm = rnorm;
+    P.dp = static_cast<__nv_bfloat16*>(dp); P.dp_bs = t.batch_stride; P.dp_rs = t.row_stride;
+    P.kmagic = (uint32_t)((0x100000000ull + (uint64_t)k - 1) / (uint64_t)k);
+    if (k <= 4) return launch_fused<4>(tm_dz, tm_p, P, smem, st);
+    if (k <= 8) return launch_fused<8>(tm_dz, tm_p, P, smem, st);
+    return launch_fused<16>(tm_dz, tm_p, P, smem, st);
+  }
+  GVIT_REQUIRE(t.B <= 65535, GVIT_ERR_SHAPE, "graph_bwd: batch %d exceeds the grid limit 65535", t.B);
+  CUtensorMap tm_dp;
   rc = make_tmap_bf16_3d(&tm_dp, dp, t.D, t.Np, t.B, t.row_stride, t.batch_stride, 128);
   if (rc != GVIT_OK) return rc;
   if (k <= 4) rc = launch_a<4>(tm_dz, tm_p, t, k, NT, idx, w, dvals, st);

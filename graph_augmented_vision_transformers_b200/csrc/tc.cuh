@@ -80,6 +80,20 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, int
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// L2 eviction-priority hints (the encodings createpolicy.fractional.L2::evict_{first,last}.b64 with fraction 1.0 returns;
+// same constants as cute::TMA::CacheHintSm90).  evict_last keeps a tile that the SAME kernel re-reads a few microseconds
+// later resident while other CTAs stream through L2; evict_first marks data nobody re-reads.
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* m, int c0, int c1, int c2, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void st_global_hint(void* p, const uint4& v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;"
+               ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy) : "memory");
+}
 // same, delivered to the same shared-memory offset (and signalling the mbarrier at the same offset) of every CTA of the
 // cluster whose bit is set in cta_mask: ONE L2 read feeds several SMs
 __device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* m, int c0, int c1, int c2, uint64_t* bar, uint16_t cta_mask) {
