@@ -36,6 +36,19 @@ PER_GPU_BATCH = 256
 METRIC, UNIT = "graph_vit_train_images_per_sec", "images/s"
 # fwd+bwd FLOPs per image, ViT-B/16 + sparse k=8 graph block in every layer
 FLOPS_PER_IMAGE = 115.9e9
+# BASELINE configs[3]: ViT-L/16 at 384^2 (576 patch tokens) with DENSE adjacency aggregation, bf16 training; ctor kwargs
+# only (/root/reference/src/models/vit.py:125-127).  1331 GF fwd+bwd per image.
+VITL384_CFG = dict(img_size=384, patch_size=16, in_chans=3, num_classes=14, embed_dim=1024, depth=24, num_heads=16,
+                   mlp_ratio=4.0, qkv_bias=True, drop_rate=0.1, graph_mode="dense", graph_every=1)
+VITL384_BATCH, VITL384_FLOPS = 32, 1331e9
+WORKLOADS = {
+    "vitb224": (MODEL_CFG, PER_GPU_BATCH, FLOPS_PER_IMAGE,
+                "BASELINE configs[1]: ViT-B/16 + kNN graph block (196 patch tokens, k=8, every block), full training step "
+                "(fwd, loss, bwd, grad sync, clip, AdamW), bf16 autocast, 224x224"),
+    "vitl384": (VITL384_CFG, VITL384_BATCH, VITL384_FLOPS,
+                "BASELINE configs[3]: ViT-L/16 at 384x384 (576 patch tokens) + DENSE adjacency graph block in every layer, "
+                "full training step (fwd, loss, bwd, grad sync, clip, AdamW), bf16 autocast"),
+}
 
 
 def load_peaks():
@@ -265,6 +278,143 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
     return res
 
 
+def roofline_block(kernels, ms_step, peaks):
+    """`roofline` of the bench line: the dominant libgvit kernel (contract) plus what BASELINE's metric asks for - the
+    time-weighted fraction of roofline over the graph block (knn_fwd + agg_fwd + graph_bwd) and over the attention kernels,
+    each member with its own bound, achieved rate and ncu DRAM traffic (profiles/traffic.json)."""
+    traffic = {}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        traffic = json.load(open(traffic_file))
+    top = max(kernels, key=lambda n: kernels[n]["ms_per_step"])
+    kt = kernels[top]
+    roof = {"kernel": top, "bound": kt["bound"], "achieved": kt["achieved"], "peak": kt["peak"], "unit": kt["unit"],
+            "frac": kt["frac"], "traffic": traffic.get(top), "peak_source": peaks["source"] + (" (burst)" if kt["bound"] == "tensor" else ""),
+            "avg_launch_ms": kt["ms"], "share_of_step": kt["ms_per_step"] / ms_step}
+
+    def group(names):
+        members = {n: kernels[n] for n in names if n in kernels}
+        t = sum(m["ms"] for m in members.values())
+        return {"frac": sum(m["ms"] * m["frac"] for m in members.values()) / t if t > 0 else None,
+                "ms_per_layer": t, "share_of_step": sum(m["ms_per_step"] for m in members.values()) / ms_step,
+                "weighting": "time-weighted mean of the members' fractions of their own roofline",
+                "members": {n: {"bound": m["bound"], "achieved": round(m["achieved"], 1), "peak": m["peak"], "unit": m["unit"],
+                                "frac": round(m["frac"], 4), "ms": round(m["ms"], 4), "algorithmic_bytes": m["algorithmic_bytes"],
+                                "flops": m["flops"], "traffic": traffic.get(n)} for n, m in members.items()}}
+    roof["graph_block"] = group(("knn_fwd", "agg_fwd", "graph_bwd"))
+    roof["attention"] = group(("attn_fwd", "attn_bwd"))
+    return roof
+
+
+def _train_objects(dev, name, B):
+    from graph_augmented_vision_transformers_b200 import modules
+    from graph_augmented_vision_transformers_b200.losses import DynamicWeightedLoss
+    cfg = WORKLOADS[name][0]
+    torch.manual_seed(42)
+    model = modules.VisionTransformer(**cfg).to(dev).train()
+    crit = DynamicWeightedLoss(cfg["num_classes"]).to(dev)
+    opt = torch.optim.AdamW([{"params": model.parameters()}, {"params": crit.parameters(), "lr": 1e-5}], lr=1e-4,
+                            weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, fused=True, capturable=True)
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    img = torch.randn(B, 3, cfg["img_size"], cfg["img_size"], device=dev, generator=gen)
+    tgt = (torch.rand(B, 14, device=dev, generator=gen) > 0.9).float()
+    return cfg, model, crit, opt, img, tgt
+
+
+def measure_train_short(dev, name, steps, warmup, batch=None):
+    """A bounded eager-issue measurement of one workload's full training step (no CUDA graph, no e2e leg)."""
+    from graph_augmented_vision_transformers_b200 import _lib
+    _, B, flops, workload = WORKLOADS[name]
+    B = batch or B
+    cfg, model, crit, opt, img, tgt = _train_objects(dev, name, B)
+    params = list(model.parameters()) + list(crit.parameters())
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = model(img)
+        loss, _ = crit(logits, tgt)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0, foreach=True)
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        loss = step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    Np = (cfg["img_size"] // 16) ** 2
+    res = {"workload": workload, "value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "per_gpu_batch": B, "steps": steps,
+           "warmup": warmup, "step_issue": "eager", "model_tflops": B / (ms / 1e3) * flops / 1e12, "last_loss": float(loss),
+           "paths": {"graph": "dense: " + _lib.describe_path("agg_dense", _lib.GVIT_BF16, Np, cfg["embed_dim"]),
+                     "attn_fwd": _lib.describe_path("attn_fwd", _lib.GVIT_BF16, Np + 1, 64),
+                     "attn_bwd": _lib.describe_path("attn_bwd", _lib.GVIT_BF16, Np + 1, 64)}}
+    del model, crit, opt, img, tgt
+    torch.cuda.empty_cache()
+    return res
+
+
+def inference_sweep(dev, batches, ks, everys, iters):
+    """BASELINE configs[4]: inference (model.eval(), no_grad, bf16 autocast, sigmoid on the device - the call of
+    /root/reference/scripts/evaluate.py:104-115) over batch size x k x graph placement; collective-free."""
+    from graph_augmented_vision_transformers_b200 import modules
+    out = []
+    for every in everys:
+        for k in ks:
+            cfg = dict(MODEL_CFG, graph_k=k, graph_every=every, drop_rate=0.0)
+            torch.manual_seed(42)
+            model = modules.VisionTransformer(**cfg).to(dev).eval()
+            for B in batches:
+                img = torch.randn(B, 3, 224, 224, device=dev)
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                    for _ in range(2):
+                        torch.sigmoid(model(img))
+                    torch.cuda.synchronize()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    for _ in range(iters):
+                        probs = torch.sigmoid(model(img))
+                    b.record()
+                    torch.cuda.synchronize()
+                ms = a.elapsed_time(b) / iters
+                out.append({"batch": B, "k": k, "graph_every": every, "ms": round(ms, 3), "images_per_s": round(B / (ms / 1e3), 1)})
+                del img, probs
+            del model
+            torch.cuda.empty_cache()
+    return out
+
+
+def run_infer(args):
+    """`--config infer`: the full inference sweep of BASELINE configs[4] as its own JSON line (value = the best point)."""
+    from graph_augmented_vision_transformers_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if int(os.environ.get("RANK", "0")) != 0:
+        return                                               # inference is collective-free: replicas would repeat rank 0
+    _lib.load()
+    sampler = ClockSampler(dev.index)
+    sweep = inference_sweep(dev, batches=(32, 64, 128, 256, 512, 1024, 2048, 4096), ks=(4, 8, 16), everys=(1, 4),
+                            iters=max(3, args.steps))
+    clocks = sampler.stop()
+    best = max(sweep, key=lambda r: r["images_per_s"])
+    ref = next(r for r in sweep if r["batch"] == 256 and r["k"] == 8 and r["graph_every"] == 1)
+    print(json.dumps({"metric": "graph_vit_inference_images_per_sec", "value": best["images_per_s"], "unit": UNIT, "n_gpus": 1,
+                      "steps": max(3, args.steps), "warmup": 2, "ms_per_step": best["ms"], "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": "BASELINE configs[4]: ViT-B/16 + kNN graph inference sweep, batch 32-4096, k in {4,8,16}, "
+                                             "graph layer in every block vs every 4th; eval, no_grad, bf16 autocast, 224x224",
+                                 "best_point": best, "batch256_k8_every1": ref},
+                      "clocks": clocks, "sweep": sweep}), flush=True)
+
+
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
@@ -284,11 +434,14 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     _lib.load()
     peaks = load_peaks()
-    B = PER_GPU_BATCH
+    cfg, B, flops_per_image, workload = WORKLOADS[args.config]
+    if args.batch:
+        B = args.batch
+    S = cfg["img_size"]
 
     torch.manual_seed(42)                                    # the reference's seed, scripts/train.py:137
-    model = modules.VisionTransformer(**MODEL_CFG).to(dev).train()
-    crit = DynamicWeightedLoss(MODEL_CFG["num_classes"]).to(dev)
+    model = modules.VisionTransformer(**cfg).to(dev).train()
+    crit = DynamicWeightedLoss(cfg["num_classes"]).to(dev)
     dp.broadcast_parameters(model)
     dp.broadcast_parameters(crit)
     sync = dp.GradSync(model, bucket_mb=32.0, extra_params=list(crit.parameters()))
@@ -297,7 +450,7 @@ def run_ours(args):
     all_params = list(model.parameters()) + list(crit.parameters())
 
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    img_dev = torch.randn(B, 3, 224, 224, device=dev, generator=gen)
+    img_dev = torch.randn(B, 3, S, S, device=dev, generator=gen)
     tgt_dev = (torch.rand(B, 14, device=dev, generator=gen) > 0.9).float()
 
     def eager_step(img, tgt):
@@ -330,6 +483,8 @@ def run_ours(args):
     def train_step(img, tgt):
         return captured(img, tgt) if captured is not None else eager_step(img, tgt)
 
+    n_buckets = len(sync.buckets)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -361,7 +516,7 @@ def run_ours(args):
 
     # ---- end to end: every step's batch comes from pinned host memory; loss is read back ---------
     n_host = 3
-    host = [(torch.randn(B, 3, 224, 224).pin_memory(), (torch.rand(B, 14) > 0.9).float().pin_memory())
+    host = [(torch.randn(B, 3, S, S).pin_memory(), (torch.rand(B, 14) > 0.9).float().pin_memory())
             for _ in range(n_host)]
     copy_stream = torch.cuda.Stream(dev)
     slots = [(torch.empty_like(img_dev), torch.empty_like(tgt_dev)) for _ in range(2)]
@@ -414,45 +569,52 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, args.steps, finish=read_pending)
 
     # ---- roofline of the libgvit kernels, cpu baseline (rank 0, N = 1 only) -------------------------
-    roof, kernels, cpu_base = None, None, None
+    roof, kernels, cpu_base, extras = None, None, None, None
     if rank == 0:
         del slots
         torch.cuda.empty_cache()
-        kernels = kernel_rooflines(dev, B, peaks)
-        top = max(kernels, key=lambda n: kernels[n]["ms_per_step"])
-        kt = kernels[top]
-        roof = {"kernel": top, "bound": kt["bound"], "achieved": kt["achieved"], "peak": kt["peak"], "unit": kt["unit"],
-                "frac": kt["frac"], "traffic": None, "peak_source": peaks["source"] + (" (burst)" if kt["bound"] == "tensor" else ""),
-                "avg_launch_ms": kt["ms"], "share_of_step": kt["ms_per_step"] / ms_step}
-        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(traffic_file):
-            roof["traffic"] = json.load(open(traffic_file)).get(top)
-        if world == 1 and not args.no_cpu_baseline:
+        if args.config == "vitb224":
+            kernels = kernel_rooflines(dev, B, peaks)
+            roof = roofline_block(kernels, ms_step, peaks)
+        if world == 1 and not args.no_cpu_baseline and args.config == "vitb224":
             cpu_base, _, _ = time_cpu_oracle(steps=3, warmup=1, budget_s=25.0)
     barrier()
+    if rank == 0 and world == 1 and args.config == "vitb224" and not args.no_extra:
+        # BASELINE configs[3] and configs[4], bounded: the full lines are `--config vitl384` and `--config infer`
+        if captured is not None:
+            captured.release()
+            captured = None
+        del model, crit, opt, sync, img_dev, tgt_dev, host
+        torch.cuda.empty_cache()
+        extras = {"vitl384_train": measure_train_short(dev, "vitl384", steps=3, warmup=2),
+                  "infer_sweep": inference_sweep(dev, batches=(32, 256, 2048), ks=(4, 8, 16), everys=(1, 4), iters=3)}
 
     if rank == 0:
         value = B * world / (ms_step / 1e3)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "BASELINE configs[1]: ViT-B/16 + kNN graph block (196 patch tokens, k=8, every block), "
-                                       "full training step (fwd, loss, bwd, grad sync, clip, AdamW), bf16 autocast, 224x224",
-                           "step_issue": step_mode + (" (whole step replayed from one captured graph; dropout counters advance on the device)" if captured is not None else ""),
+                "config": {"workload": workload,
+                           "residual_stream": "fp32 (torch.autocast semantics: cat / add with the fp32 cls_token and pos_embed promote, "
+                                              "vit.py:207-211); branches compute in bf16",
+                           "step_issue": step_mode + (" (whole step replayed from one captured graph; dropout counters advance on the device)" if step_mode == "cuda-graph" else ""),
                            "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
                            "l2": "no flush needed: one step streams >20 GB of activations (126 MB L2); kernel micro-timings rotate >L2 input sets"},
-                "model_tflops": value * FLOPS_PER_IMAGE / 1e12,
-                "model_flops_frac_of_bf16_sustained": value * FLOPS_PER_IMAGE / 1e12 / (peaks["tf_sustained"] * world),
+                "model_tflops": value * flops_per_image / 1e12,
+                "model_flops_frac_of_bf16_sustained": value * flops_per_image / 1e12 / (peaks["tf_sustained"] * world),
                 "e2e": {"value": B * world / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
                 "kernels": {n: {k2: (round(v, 4) if isinstance(v, float) else v) for k2, v in d.items()
                                 if k2 in ("ms", "bound", "achieved", "unit", "frac", "gbs", "tflops", "ms_per_step")}
                             for n, d in (kernels or {}).items()},
-                "paths": {op: _lib.describe_path(op, _lib.GVIT_BF16, 196 if op in ("knn", "agg") else 197, 768 if op in ("knn", "agg") else 64)
+                "paths": {op: _lib.describe_path(op, _lib.GVIT_BF16, (S // 16) ** 2 + (0 if op in ("knn", "agg") else 1),
+                                                 cfg["embed_dim"] if op in ("knn", "agg") else 64)
                           for op in ("knn", "agg", "attn_fwd", "attn_bwd")},
-                "collectives_per_step": len(sync.buckets) if world > 1 else 0,
+                "collectives_per_step": n_buckets if world > 1 else 0,
                 "last_loss": losses[-1] if losses else None}
+        if extras is not None:
+            line["configs"] = extras
         print(json.dumps(line), flush=True)
     if world > 1:
         # Leave without tearing NCCL down: destroying the process group (or the interpreter's own teardown) while a captured
@@ -483,6 +645,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", choices=["vitb224", "vitl384", "infer"], default="vitb224",
+                    help="vitb224 = BASELINE configs[1]/[2] (default, the contract line); vitl384 = configs[3]; infer = configs[4] sweep")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--no-extra", action="store_true", help="skip the bounded configs[3] / configs[4] measurements of the default line")
     ap.add_argument("--eager", action="store_true", help="issue the step from Python instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -495,6 +661,8 @@ def main():
     globals()["print"] = emit                               # the two print(json.dumps(...)) calls go to the real stdout
     if args.impl == "reference":
         run_reference_arm(args, int(os.environ.get("RANK", "0")))
+    elif args.config == "infer":
+        run_infer(args)
     else:
         run_ours(args)
 
