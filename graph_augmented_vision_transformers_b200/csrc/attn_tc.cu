@@ -916,7 +916,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
 GVIT_TRACE_SETTER(gvit_debug_set_trace_attn)
 
 bool attn_fwd_tc_supported(int N, int dh) { return dh == 64 && N >= 1; }
-bool attn_bwd_tc_supported(int N, int dh) { return dh == 64 && N >= 1 && N <= 256; }
+bool attn_bwd_tc_supported(int N, int dh) { return dh == 64 && N >= 1; }   // N > 256: the two-pass kernel of attn_long_tc.cu
 
 int attn_fwd_tc(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, cudaStream_t st) {
   CUtensorMap tm;
@@ -942,6 +942,7 @@ int attn_fwd_tc(const void* qkv, int B, int N, int H, float scale, void* out, fl
 
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, int B, int N, int H, float scale,
                 float* delta_ws, void* dqkv, cudaStream_t st) {
+  if (N > 256) return attn_bwd_long_tc(qkv, out, dout, lse, B, N, H, scale, delta_ws, dqkv, st);
   CUtensorMap tm_qkv, tm_do;
   int rc = make_tmap_bf16_3d(&tm_qkv, qkv, (uint64_t)3 * H * 64, N, B, (uint64_t)3 * H * 64, (uint64_t)N * 3 * H * 64, 128);
   if (rc != GVIT_OK) return rc;

@@ -47,10 +47,12 @@ def test_fp32_core_vs_oracle(B, N, H, dh):
 
 
 @pytest.mark.parametrize("B,N,H", [(2, 197, 12), (1, 577, 16), (1, 1, 2), (3, 128, 2), (2, 129, 3), (2, 16, 1), (1, 256, 4),
-                                   (1, 257, 2), (31, 197, 12), (40, 65, 8), (27, 150, 6)])   # last three: > 148 (image, head)
-                                                                                             # items -> persistent CTAs loop
+                                   (1, 257, 2), (31, 197, 12), (40, 65, 8), (27, 150, 6),   # these three: > 148 (image, head)
+                                                                                            # items -> persistent CTAs loop
+                                   (2, 300, 3), (1, 640, 2), (1, 1025, 1), (3, 577, 16)])   # N > 256: two-pass tcgen05 backward
 def test_bf16_core_vs_oracle(B, N, H):
     assert _lib.describe_path("attn_fwd", _lib.GVIT_BF16, N, 64) == "attn_fwd:tcgen05+tma"
+    assert _lib.describe_path("attn_bwd", _lib.GVIT_BF16, N, 64) == "attn_bwd:tcgen05+tma"
     out, dqkv, want, dwant = _core_case(B, N, H, 64, torch.bfloat16, seed=N)
     assert out.dtype == torch.bfloat16
     assert rel_err(out, want) < TOL_BF16 and rel_err(dqkv, dwant) < TOL_BF16
