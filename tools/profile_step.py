@@ -13,16 +13,19 @@ from graph_augmented_vision_transformers_b200 import modules  # noqa: E402
 from graph_augmented_vision_transformers_b200.losses import DynamicWeightedLoss  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--batch", type=int, default=0)
+ap.add_argument("--config", choices=["vitb224", "vitl384"], default="vitb224")
 ap.add_argument("--rows", type=int, default=60)
 ap.add_argument("--ncu", action="store_true", help="no torch profiler: bracket one step with cudaProfilerStart/Stop for ncu --profile-from-start off")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 torch.manual_seed(42)
-model = modules.VisionTransformer(**bench.MODEL_CFG).to(dev).train()
+cfg, dbatch, _, _ = bench.WORKLOADS[args.config]
+args.batch = args.batch or dbatch
+model = modules.VisionTransformer(**cfg).to(dev).train()
 crit = DynamicWeightedLoss(14).to(dev)
 opt = torch.optim.AdamW(list(model.parameters()) + list(crit.parameters()), lr=1e-4, weight_decay=0.05, fused=True)
-img = torch.randn(args.batch, 3, 224, 224, device=dev)
+img = torch.randn(args.batch, 3, cfg["img_size"], cfg["img_size"], device=dev)
 tgt = (torch.rand(args.batch, 14, device=dev) > 0.9).float()
 params = list(model.parameters()) + list(crit.parameters())
 
