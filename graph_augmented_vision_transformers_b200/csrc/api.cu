@@ -39,7 +39,7 @@ int gvit_describe_path(const char* op, int dtype, int n_tokens, int dim, char* b
   if (!strcmp(op, "knn")) path = (bf16 && gvit::knn_tc_supported(n_tokens, dim, 8)) ? "knn:tcgen05+tma" : "knn:fp32-fma";
   else if (!strcmp(op, "agg")) path = (bf16 && (gvit::agg3_tc_supported(n_tokens, dim, 8) || gvit::agg_tc_supported(n_tokens, dim, 8))) ? "agg:tcgen05+tma" : "agg:gather-fma+library-gemm";
   else if (!strcmp(op, "agg_res32")) path = (bf16 && gvit::agg3_tc_supported(n_tokens, dim, 8)) ? "agg:tcgen05+tma fp32-stream" : "agg:host-side residual add";
-  else if (!strcmp(op, "agg_dense")) path = "agg_dense:library-bmm composition";
+  else if (!strcmp(op, "agg_dense")) path = (bf16 && n_tokens <= 1024 && dim % 64 == 0 && dim <= 1024) ? "agg_dense:tcgen05 batched GEMMs + row-wise softmax" : "agg_dense:ATen composition (fp32 parity path)";
   else if (!strcmp(op, "graph_bwd")) path = (bf16 && gvit::graph_bwd_tc_supported(n_tokens, dim, 8)) ? "graph_bwd:tcgen05+tma" : "graph_bwd:reverse-csr+gather";
   else if (!strcmp(op, "attn_fwd")) path = (bf16 && gvit::attn_fwd_tc_supported(n_tokens, dim)) ? "attn_fwd:tcgen05+tma" : "attn_fwd:fp32-fma";
   else if (!strcmp(op, "attn_bwd")) path = (bf16 && gvit::attn_bwd_tc_supported(n_tokens, dim)) ? "attn_bwd:tcgen05+tma" : "attn_bwd:fp32-fma";

@@ -119,6 +119,54 @@ int gvit_graph_bwd(const void* p, int64_t batch_stride, int64_t row_stride, int 
   return graph_bwd_tc(t, k, idx, vals, w, rnorm, dz, dz_batch_stride, dvals, dp, static_cast<cudaStream_t>(stream));
 }
 
+int gvit_bgemm(int batch, int M, int N, int nprod,
+               const void* a0, int64_t a0_rs, int64_t a0_bs, int a0_t, const void* b0, int64_t b0_rs, int64_t b0_bs, int b0_t, int K0,
+               const void* a1, int64_t a1_rs, int64_t a1_bs, int a1_t, const void* b1, int64_t b1_rs, int64_t b1_bs, int b1_t, int K1,
+               const float* row_scale, int out_dtype, void* out, int64_t out_rs, int64_t out_bs, void* stream) {
+  TRY(check_dtype(out_dtype, "bgemm"));
+  GVIT_REQUIRE(out && aligned16(out) && out_rs % 8 == 0 && out_bs % 8 == 0, GVIT_ERR_ALIGN, "bgemm: out must be 16-byte aligned with strides %% 8 == 0");
+  GVIT_REQUIRE(batch >= 1 && batch <= 65535 && M >= 1 && N >= 1, GVIT_ERR_SHAPE, "bgemm: batch=%d M=%d N=%d", batch, M, N);
+  BgemmProduct pr[2] = {{a0, a0_rs, a0_bs, a0_t, b0, b0_rs, b0_bs, b0_t, K0}, {a1, a1_rs, a1_bs, a1_t, b1, b1_rs, b1_bs, b1_t, K1}};
+  return bgemm_tc(batch, M, N, nprod, pr, row_scale, out_dtype, out, out_rs, out_bs, static_cast<cudaStream_t>(stream));
+}
+
+static int check_dense(const char* who, int B, int Np) {
+  GVIT_REQUIRE(B >= 1 && Np >= 1 && Np <= 1024, GVIT_ERR_SHAPE, "%s: B=%d Np=%d (Np <= 1024)", who, B, Np);
+  return GVIT_OK;
+}
+
+int gvit_dense_rownorm(const void* p, int64_t batch_stride, int64_t row_stride, int B, int Np, int D, float* rn, void* stream) {
+  TRY(check_dense("dense_rownorm", B, Np));
+  GVIT_REQUIRE(p && rn && D >= 8 && D % 8 == 0 && aligned16(p) && row_stride % 8 == 0 && batch_stride % 8 == 0, GVIT_ERR_SHAPE,
+               "dense_rownorm: D=%d must be a multiple of 8 with 16-byte aligned rows", D);
+  Tokens t{p, batch_stride, row_stride, B, Np, D};
+  return dense_rownorm(t, rn, static_cast<cudaStream_t>(stream));
+}
+
+int gvit_dense_softmax_fwd(const float* G, int ldg, const float* rn, int B, int Np, int ldA, void* A, void* stream) {
+  TRY(check_dense("dense_softmax_fwd", B, Np));
+  GVIT_REQUIRE(G && rn && A && ldg >= Np && ldA >= Np && ldA % 64 == 0 && ldA <= 1024, GVIT_ERR_SHAPE,
+               "dense_softmax_fwd: ldg=%d ldA=%d (>= Np, ldA %% 64 == 0)", ldg, ldA);
+  return dense_softmax_fwd(G, ldg, rn, B, Np, ldA, A, static_cast<cudaStream_t>(stream));
+}
+
+int gvit_dense_softmax_bwd(const float* dA, int ldg, const void* A, int ldA, const float* rn, int B, int Np, void* dG, void* stream) {
+  TRY(check_dense("dense_softmax_bwd", B, Np));
+  GVIT_REQUIRE(dA && A && rn && dG && ldg >= Np && ldA >= Np && ldA % 64 == 0 && ldA <= 1024, GVIT_ERR_SHAPE,
+               "dense_softmax_bwd: ldg=%d ldA=%d (>= Np, ldA %% 64 == 0)", ldg, ldA);
+  return dense_softmax_bwd(dA, ldg, A, ldA, rn, B, Np, dG, static_cast<cudaStream_t>(stream));
+}
+
+int gvit_dense_combine_bwd(const void* T, const void* V, const void* p, int64_t batch_stride, int64_t row_stride, const float* rn,
+                           int B, int Np, int D, void* dp, void* stream) {
+  TRY(check_dense("dense_combine_bwd", B, Np));
+  GVIT_REQUIRE(T && V && p && rn && dp && D >= 8 && D % 8 == 0 && D <= 1024, GVIT_ERR_SHAPE, "dense_combine_bwd: D=%d (D %% 8 == 0, D <= 1024)", D);
+  GVIT_REQUIRE(aligned16(T) && aligned16(V) && aligned16(p) && aligned16(dp) && row_stride % 8 == 0 && batch_stride % 8 == 0, GVIT_ERR_ALIGN,
+               "dense_combine_bwd: 16-byte alignment required");
+  Tokens t{p, batch_stride, row_stride, B, Np, D};
+  return dense_combine_bwd(T, V, t, rn, dp, static_cast<cudaStream_t>(stream));
+}
+
 int gvit_attn_fwd(const void* qkv, int B, int N, int H, int dh, float scale, int dtype, void* out, float* lse,
                   void* stream) {
   TRY(check_dtype(dtype, "attn_fwd"));

@@ -46,6 +46,19 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
 int attn_bwd_long_tc(const void* qkv, const void* out, const void* dout, const float* lse, int B, int N, int H,
                      float scale, float* delta_ws, void* dqkv, cudaStream_t st);   // N > 256 (attn_long_tc.cu)
 
+// ---- dense-adjacency graph layer : bgemm_tc.cu (batched tcgen05 GEMM), dense_graph.cu (row-wise stages)
+struct BgemmProduct {       // one A_p B_p term.  *_t == 0: K-major (A stored [M][K], B stored [N][K]); 1: MN-major ([K][M], [K][N])
+  const void* a; int64_t a_rs, a_bs; int a_t;
+  const void* b; int64_t b_rs, b_bs; int b_t;
+  int K;
+};
+int bgemm_tc(int batch, int M, int N, int nprod, const BgemmProduct* prods, const float* row_scale, int out_dtype, void* out,
+             int64_t out_rs, int64_t out_bs, cudaStream_t st);
+int dense_rownorm(const Tokens& t, float* rn, cudaStream_t st);
+int dense_softmax_fwd(const float* G, int ldg, const float* rn, int B, int Np, int ldA, void* A, cudaStream_t st);
+int dense_softmax_bwd(const float* dA, int ldg, const void* A, int ldA, const float* rn, int B, int Np, void* dG, cudaStream_t st);
+int dense_combine_bwd(const void* T, const void* V, const Tokens& t, const float* rn, void* dp, cudaStream_t st);
+
 // ---- edges : edges.cu
 int layernorm_fwd(const void* x, const void* gamma, const void* beta, int64_t rows, int D, float eps, int dtype,
                   int y_dtype, void* y, float* mean, float* rstd, cudaStream_t st);

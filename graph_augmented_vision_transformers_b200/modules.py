@@ -142,7 +142,10 @@ class PatchGraphLayer(nn.Module):
                 self.last_tokens, self.last_idx, self.last_vals = h.detach(), idx, vals
                 return out
             return ops.patch_graph(h, self.proj.weight, self.proj.bias, self.k, resid=resid)
-        y = _dense_graph(h, self.proj.weight, self.proj.bias)
+        if h.is_cuda and ops.dense_graph_available(ops._autocast_dtype(h), h.shape[1] - 1, h.shape[2]):
+            # bf16 compute: batched tcgen05 GEMMs + row-wise libgvit kernels (ops._DenseGraph)
+            return ops.dense_graph(h, self.proj.weight, self.proj.bias, resid=resid)
+        y = _dense_graph(h, self.proj.weight, self.proj.bias)      # fp32 parity path: the section-9 formulas through ATen
         return y if resid is None else resid + y
 
 

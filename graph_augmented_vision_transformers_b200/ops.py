@@ -954,6 +954,118 @@ class _PatchGraph(torch.autograd.Function):
         return dh, dweight, dbias, dresid, None
 
 
+# ------------------------------------------------------------------------------------------------
+# a8, dense adjacency (graph_mode='dense', BASELINE configs[3]): batched tcgen05 GEMMs + row-wise libgvit kernels
+# ------------------------------------------------------------------------------------------------
+def _bgemm(batch, M, N, prods, out, out_rs, out_bs, row_scale=None):
+    """out[b] = diag(row_scale[b]) sum_p op(A_p[b]) op(B_p[b]) through gvit_bgemm; prods = [(a_ptr, a_rs, a_bs, a_t, b_ptr, b_rs,
+    b_bs, b_t, K), ...] (one or two products)."""
+    p0 = prods[0]
+    p1 = prods[1] if len(prods) > 1 else prods[0]
+    _call("gvit_bgemm", batch, M, N, len(prods), *p0, *p1, _ptr(row_scale), _dtype_code(out), _ptr(out), out_rs, out_bs, _stream())
+
+
+def dense_graph_available(dtype: torch.dtype, Np: int, D: int) -> bool:
+    return dtype == torch.bfloat16 and _lib.describe_path("agg_dense", GVIT_BF16, Np, D).startswith("agg_dense:tcgen05")
+
+
+class _DenseGraph(torch.autograd.Function):
+    """y = cat([0, softmax(p^ p^^T) p Wg^T + b]) [+ resid] - SURVEY.md section 9 with G3 skipped (every patch token attends to
+    every patch token of its image), bf16 storage / fp32 arithmetic, every matrix product a libgvit tcgen05 GEMM:
+
+        forward   rn (G1) -> G = P P^T (fp32) -> A~ = softmax_j(G rn_i rn_j) (bf16) -> Z = A~ P -> out = resid + Z Wg^T + b
+        backward  dZ = dY Wg -> dA~ = dZ P^T -> dG = A~ (dA~ - delta) rn rn^T -> T = A~^T dZ, V = (dG + dG^T) P
+                  -> dp = T + V - rn^2 (p . V) p
+    """
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, resid):
+        ctx.w_dtype = weight.dtype
+        ctx.b_dtype = bias.dtype if bias is not None else None
+        weight, bias = _shadow(weight, h.dtype), _shadow(bias, h.dtype)
+        off, bs, rs, B, Np, D = _token_view(h)
+        st = _stream()
+        ld = (Np + 63) // 64 * 64
+        tok = _ptr(h, off)
+        rn = torch.empty((B, Np), dtype=torch.float32, device=h.device)
+        _call("gvit_dense_rownorm", tok, bs, rs, B, Np, D, _ptr(rn), st)
+        G = torch.empty((B, Np, ld), dtype=torch.float32, device=h.device)
+        _bgemm(B, Np, Np, [(tok, rs, bs, 0, tok, rs, bs, 0, D)], G, ld, Np * ld)                    # G = P P^T
+        A = torch.empty((B, Np, ld), dtype=h.dtype, device=h.device)
+        _call("gvit_dense_softmax_fwd", _ptr(G), ld, _ptr(rn), B, Np, ld, _ptr(A), st)
+        del G
+        zf = torch.empty_like(h)                                      # laid out like h: weight / input gradients run over all rows
+        zf[:, 0].zero_()
+        _bgemm(B, Np, D, [(_ptr(A), ld, Np * ld, 0, tok, rs, bs, 1, Np)], zf[:, 1:], rs, bs)        # Z = A~ P
+        M = B * (Np + 1)
+        if resid is not None and D <= _FUSED_RESID_MAX_K and fused_fc1_available(D, D):
+            out = torch.empty_like(resid)
+            _call("gvit_linear_dropout_residual_fwd", _ptr(zf), _ptr(weight), _ptr(bias), _ptr(resid), M, D, D, 0.0, 0, 0, None,
+                  GVIT_BF16, _dtype_code(resid), _ptr(out), None, st)
+            out[:, 0] = resid[:, 0]                                   # the CLS row passes through untouched (G0): no bias either
+        else:
+            out = F.linear(zf, weight, bias)
+            out[:, 0].zero_()
+            if resid is not None:
+                out = resid + out
+        ctx.save_for_backward(h, weight, rn, A, zf)
+        ctx.has = (bias is not None, resid is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, weight, rn, A, zf = ctx.saved_tensors
+        off, bs, rs, B, Np, D = _token_view(h)
+        dt, st = _dtype_code(h), _stream()
+        ld = A.shape[-1]
+        dout = dout.contiguous()
+        dresid = dout if ctx.has[1] else None
+        want_db = ctx.has[0] and ctx.needs_input_grad[2]
+        rows = B * (Np + 1)
+        if dout.dtype != h.dtype:                                     # fp32 stream gradient: one pass casts it and sums the columns
+            d2 = torch.empty((rows, D), dtype=h.dtype, device=h.device)
+            cs = torch.empty(D, dtype=torch.float32, device=h.device) if want_db else None
+            ws = _colsum_ws(rows, D, h.device) if want_db else None
+            _call("gvit_dropout_bwd", _ptr(dout), None, dout.numel(), 0.0, _dtype_code(dout), dt, _ptr(d2), D, Np + 1, _ptr(cs), _ptr(ws), st)
+        else:
+            d2 = dout.view(rows, D)
+            cs = colsum(d2, skip_period=Np + 1) if want_db else None
+        dweight = _wgrad(d2, zf.view(rows, D), ctx.w_dtype) if ctx.needs_input_grad[1] else None
+        dbias = cs.to(ctx.b_dtype) if want_db else None
+        dh = None
+        if ctx.needs_input_grad[0]:
+            tok = _ptr(h, off)
+            dz = d2 @ weight                                          # (B*(1+Np), D); its CLS rows are never read
+            dzt = _ptr(dz, off)
+            dA = torch.empty((B, Np, ld), dtype=torch.float32, device=h.device)
+            _bgemm(B, Np, Np, [(dzt, rs, bs, 0, tok, rs, bs, 0, D)], dA, ld, Np * ld)               # dA~ = dZ P^T
+            dG = torch.empty((B, Np, ld), dtype=h.dtype, device=h.device)
+            _call("gvit_dense_softmax_bwd", _ptr(dA), ld, _ptr(A), ld, _ptr(rn), B, Np, _ptr(dG), st)
+            del dA
+            V = torch.empty((B, Np, D), dtype=h.dtype, device=h.device)
+            _bgemm(B, Np, D, [(_ptr(dG), ld, Np * ld, 0, tok, rs, bs, 1, Np),                       # V = dG P + dG^T P
+                              (_ptr(dG), ld, Np * ld, 1, tok, rs, bs, 1, Np)], V, D, Np * D)
+            T = torch.empty((B, Np, D), dtype=h.dtype, device=h.device)
+            _bgemm(B, Np, D, [(_ptr(A), ld, Np * ld, 1, dzt, rs, bs, 1, Np)], T, D, Np * D)         # T = A~^T dZ
+            dh = torch.empty_like(h)
+            dh[:, 0].zero_()
+            _call("gvit_dense_combine_bwd", _ptr(T), _ptr(V), tok, bs, rs, _ptr(rn), B, Np, D, _ptr(dh, off), st)
+        return dh, dweight, dbias, dresid
+
+
+def dense_graph(h: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, resid: torch.Tensor | None = None):
+    """The dense-adjacency graph sub-layer on layer-normed tokens h (B, 1+Np, D) under bf16 autocast; returns (B, 1+Np, D) in
+    the dtype of ``resid`` (or of the compute dtype).  The CLS row is zero / ``resid``'s CLS row."""
+    _check_cuda(h, weight, bias, resid)
+    if h.dim() != 3 or h.shape[1] < 2:
+        raise ValueError(f"h must be (B, 1+Np, D); got {tuple(h.shape)}")
+    dt = _autocast_dtype(h)
+    if not dense_graph_available(dt, h.shape[1] - 1, h.shape[2]):
+        raise _lib.GvitError("dense_graph", 5, "the native dense graph layer needs bf16 compute, Np <= 1024, D % 64 == 0, D <= 1024")
+    with torch.autocast("cuda", enabled=False):
+        return _DenseGraph.apply(h.to(dt).contiguous(), weight, bias, None if resid is None else resid.contiguous())
+
+
 def patch_graph(h: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, k: int,
                 resid: torch.Tensor | None = None, return_graph: bool = False):
     """The kNN graph sub-layer on layer-normed tokens h (B, 1+Np, D): returns (B, 1+Np, D).

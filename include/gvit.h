@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GVIT_ABI_VERSION 13
+#define GVIT_ABI_VERSION 14
 #if defined(__GNUC__)
 #define GVIT_API __attribute__((visibility("default")))
 #else
@@ -112,6 +112,35 @@ GVIT_API int gvit_agg_bwd(const void* p, int64_t batch_stride, int64_t row_strid
 GVIT_API int gvit_graph_bwd(const void* p, int64_t batch_stride, int64_t row_stride, int B, int Np, int D, int k, int dtype,
                    const int32_t* idx, const float* vals, const float* w, const float* rnorm, const void* dz,
                    int64_t dz_batch_stride, float* dvals, void* dp, void* stream);
+
+/* ---- a8, dense adjacency (SURVEY section 9 with G3 skipped: `graph_mode='dense'`, BASELINE configs[3]; the ctor path is
+ * /root/reference/src/models/vit.py:125-127 with the appended keyword `graph_mode`) ------------------------------------
+ * With the adjacency dense every stage is a per-image matrix product or a row-wise pass over tensors that already live in
+ * HBM in the layer's own layouts; bf16 storage, fp32 arithmetic; Np <= 1024, D % 64 == 0, D <= 1024.
+ *
+ * gvit_bgemm: out[b] = diag(row_scale[b]) * sum_{p < nprod} op(A_p[b]) op(B_p[b]),  b < batch, nprod in {1, 2}, on tcgen05.
+ *   A_p: a_t == 0 -> stored [M rows][K] (row stride a_rs, batch stride a_bs, in elements); a_t == 1 -> stored [K rows][M].
+ *   B_p: b_t == 0 -> stored [N rows][K];                                                  b_t == 1 -> stored [K rows][N].
+ *   The contiguous extent of every operand must be padded to a multiple of 64 elements inside its row stride, and a padded
+ *   K range must hold zeros.  out: (batch, M, N) with strides out_bs / out_rs, out_dtype GVIT_BF16 or GVIT_F32; rows are
+ *   written in whole 16-byte chunks, so out_rs must cover N rounded up to 8 (bf16) / 4 (fp32) elements and the tail of the
+ *   last chunk is overwritten.  row_scale (batch * M fp32) may be NULL.  The second product's arguments are ignored when nprod == 1. */
+GVIT_API int gvit_bgemm(int batch, int M, int N, int nprod,
+               const void* a0, int64_t a0_rs, int64_t a0_bs, int a0_t, const void* b0, int64_t b0_rs, int64_t b0_bs, int b0_t, int K0,
+               const void* a1, int64_t a1_rs, int64_t a1_bs, int a1_t, const void* b1, int64_t b1_rs, int64_t b1_bs, int b1_t, int K1,
+               const float* row_scale, int out_dtype, void* out, int64_t out_rs, int64_t out_bs, void* stream);
+/* G1: rn[b,i] = 1 / max(||p[b,i,:]||, 1e-12) for the strided patch-token view p (bf16). */
+GVIT_API int gvit_dense_rownorm(const void* p, int64_t batch_stride, int64_t row_stride, int B, int Np, int D, float* rn, void* stream);
+/* G2 + G4: A~[b,i,:] = softmax_j(G[b,i,j] rn[b,i] rn[b,j]) as bf16; G fp32 (B,Np,ldg) - the Gram matrix P P^T of gvit_bgemm;
+ * A~ (B,Np,ldA), ldA % 64 == 0, the pad columns [Np, ldA) are written as zeros (a K-major gvit_bgemm operand). */
+GVIT_API int gvit_dense_softmax_fwd(const float* G, int ldg, const float* rn, int B, int Np, int ldA, void* A, void* stream);
+/* Backward of G2 + G4: dG[b,i,j] = A~_ij (dA~_ij - sum_j' dA~_ij' A~_ij') rn_i rn_j as bf16 (B,Np,ldA), pads zero. */
+GVIT_API int gvit_dense_softmax_bwd(const float* dA, int ldg, const void* A, int ldA, const float* rn, int B, int Np, void* dG,
+                           void* stream);
+/* dp[b,i,:] = T[b,i,:] + V[b,i,:] - rn_i^2 (p_i . V_i) p_i : T = A~^T dZ, V = (dG + dG^T) P, both (B,Np,D) contiguous bf16;
+ * p / dp are strided patch-token views (dp is WRITTEN).  The last term is the backward of the L2 normalisation G1. */
+GVIT_API int gvit_dense_combine_bwd(const void* T, const void* V, const void* p, int64_t batch_stride, int64_t row_stride,
+                           const float* rn, int B, int Np, int D, void* dp, void* stream);
 
 /* ---- a2: attention core, replaces /root/reference/src/models/vit.py:59-69 -------------------
  * qkv : the packed projection output of vit.py:59, (B,N,3,H,dh) contiguous - consumed in place, no

@@ -119,6 +119,78 @@ def test_dense_mode_vs_oracle():
     assert rel_err(layer(hd), want) < TOL_F32
 
 
+@pytest.mark.parametrize("batch,M,N,K,a_t,b_t,f32", [(3, 196, 196, 768, 0, 0, True), (2, 576, 1024, 576, 0, 1, False),
+                                                       (2, 576, 1024, 576, 1, 1, False), (1, 100, 64, 128, 0, 0, False),
+                                                       (2, 130, 192, 64, 1, 1, True), (5, 576, 576, 1024, 0, 0, True),
+                                                       (1, 64, 320, 192, 0, 1, False)])
+def test_bgemm_all_operand_majors_vs_torch(batch, M, N, K, a_t, b_t, f32):
+    """gvit_bgemm (tcgen05, persistent, operand majors by descriptor) against torch.bmm in fp32 on the same bf16 values;
+    operands live inside padded rows the way the layer's tensors do."""
+    from graph_augmented_vision_transformers_b200.ops import _bgemm, _ptr
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    bf = torch.bfloat16
+    pad = lambda n: (n + 63) // 64 * 64
+
+    def operand(rows, cols):                    # (batch, rows, pad(cols)) storage, zero padding
+        t = torch.zeros(batch, rows, pad(cols), device=DEV, dtype=bf)
+        t[:, :, :cols] = torch.randn(batch, rows, cols, generator=g, device=DEV).to(bf)
+        return t
+
+    A = operand(K, M) if a_t else operand(M, K)
+    Bm = operand(K, N) if b_t else operand(N, K)
+    Al = (A[:, :, :M].transpose(1, 2) if a_t else A[:, :, :K]).float()            # logical (M, K)
+    Bl = (Bm[:, :, :N] if b_t else Bm[:, :, :K].transpose(1, 2)).float()          # logical (K, N)
+    rs = torch.rand(batch, M, generator=g, device=DEV) + 0.5
+    out = torch.full((batch, M, pad(N)), 7.0, device=DEV, dtype=torch.float32 if f32 else bf)
+    _bgemm(batch, M, N, [(_ptr(A), A.shape[2], A.shape[1] * A.shape[2], a_t, _ptr(Bm), Bm.shape[2], Bm.shape[1] * Bm.shape[2], b_t, K)],
+           out, out.shape[2], out.shape[1] * out.shape[2], row_scale=rs)
+    want = torch.bmm(Al, Bl) * rs[:, :, None]
+    assert rel_err(out[:, :, :N], want) < (1e-5 if f32 else 1e-2)
+    per = 4 if f32 else 8                                                 # rows are written in whole 16-byte chunks
+    Nc = (N + per - 1) // per * per
+    assert float((out[:, :, Nc:].float() - 7.0).abs().max() if pad(N) > Nc else 0.0) == 0.0   # nothing written beyond them
+    if a_t == 0 and K == M and not f32:          # two products into one accumulator: X Y + X^T Y
+        out2 = torch.empty_like(out)
+        _bgemm(batch, M, N, [(_ptr(A), A.shape[2], A.shape[1] * A.shape[2], 0, _ptr(Bm), Bm.shape[2], Bm.shape[1] * Bm.shape[2], b_t, K),
+                             (_ptr(A), A.shape[2], A.shape[1] * A.shape[2], 1, _ptr(Bm), Bm.shape[2], Bm.shape[1] * Bm.shape[2], b_t, K)],
+               out2, out.shape[2], out.shape[1] * out.shape[2])
+        assert rel_err(out2[:, :, :N], torch.bmm(Al + Al.transpose(1, 2), Bl)) < 1e-2
+
+
+@pytest.mark.parametrize("B,Np,D", [(2, 196, 768), (1, 576, 1024), (3, 100, 64), (2, 129, 192)])
+@pytest.mark.parametrize("res32", [False, True])
+def test_dense_mode_bf16_native_forward_backward_vs_oracle(B, Np, D, res32):
+    """graph_mode='dense' under bf16 compute: batched tcgen05 GEMMs + row-wise libgvit kernels (ops._DenseGraph) against the
+    section-9 oracle with autocast semantics (G1-G4 fp32, G5-G6 on bf16), forward and every gradient."""
+    bf = torch.bfloat16
+    assert ops.dense_graph_available(bf, Np, D)
+    hc, _ = tokens(B, Np, D, seed=31, dtype=bf)
+    g = torch.Generator().manual_seed(6)
+    W = (torch.randn(D, D, generator=g) * 0.05).to(bf).float()
+    b = (torch.randn(D, generator=g) * 0.1).to(bf).float()
+    x = torch.randn(B, Np + 1, D, generator=g).to(bf).float()
+    cot = torch.randn(B, Np + 1, D, generator=g).to(bf).float()
+    h = hc.to(DEV, bf).requires_grad_(True)
+    Wd, bd = W.to(DEV, bf).requires_grad_(True), b.to(DEV, bf).requires_grad_(True)
+    xd = x.to(DEV, torch.float32 if res32 else bf).requires_grad_(True)
+    out = ops.dense_graph(h, Wd, bd, resid=xd)
+    assert out.dtype == xd.dtype
+    out.backward(cot.to(DEV, out.dtype))
+    ho, Wo, bo = hc.clone().requires_grad_(True), W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    want = graph_oracle.graph_layer_forward(ho, Wo, bo, 0, "dense", compute_dtype=bf).float()
+    want.backward(cot)
+    if res32:                                                            # fp32 stream: the branch can be isolated exactly
+        assert rel_err(out.float() - xd.detach().float(), want) < TOL_BF16
+    plain = ops.dense_graph(h.detach(), Wd.detach(), bd.detach())        # no residual: the branch itself, bf16
+    assert plain.dtype == bf and rel_err(plain, want) < TOL_BF16 and float(plain[:, 0].abs().max()) == 0.0
+    assert rel_err(out, x + want) < TOL_BF16
+    assert torch.equal(out[:, 0], xd.detach()[:, 0])                     # CLS row passes through untouched (G0)
+    assert torch.equal(xd.grad.float(), cot.to(DEV))                     # residual path: identity
+    for got, ref, n in ((h.grad, ho.grad, "dh"), (Wd.grad, Wo.grad, "dW"), (bd.grad, bo.grad, "db")):
+        assert rel_err(got, ref) < TOL_BF16, n
+    assert float(h.grad[:, 0].abs().max()) == 0.0
+
+
 def test_backward_is_deterministic_at_full_size():
     bf = torch.bfloat16
     g = torch.Generator(device=DEV).manual_seed(8)

@@ -362,7 +362,14 @@ def test_config4_vit_l_384_dense_shapes_run():
     img = torch.randn(2, 3, 384, 384, generator=torch.Generator().manual_seed(4))
     with torch.autocast("cuda", dtype=torch.bfloat16):
         logits = m(img.to(DEV))
-    assert rel_err(logits, o(img)) < 5e-2
+    assert rel_err(logits, o(img)) < TOL_BF16
+    from graph_augmented_vision_transformers_b200 import _lib
+    assert _lib.describe_path("agg_dense", _lib.GVIT_BF16, 576, 1024).startswith("agg_dense:tcgen05")
+    assert _lib.describe_path("attn_bwd", _lib.GVIT_BF16, 577, 64) == "attn_bwd:tcgen05+tma"
     logits.float().square().mean().backward()
+    o(img).square().mean().backward()
+    errs, worst = _worst_grad_errors(o, m)
+    print(f"\nconfig 4 (ViT-L/16 @ 384 dense, 2 blocks) bf16: worst gradients {worst}")
     for n, p in m.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    assert worst[0][1] < TOL_BF16, worst
