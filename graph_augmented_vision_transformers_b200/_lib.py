@@ -19,7 +19,7 @@ GVIT_F32, GVIT_BF16 = 0, 1
 GVIT_MAX_K = 32
 GVIT_LN_PARTIALS = 296
 GVIT_COLSUM_CHUNKS = 1024
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 STATUS_NAMES = {0: "GVIT_OK", 1: "GVIT_ERR_SHAPE", 2: "GVIT_ERR_ALIGN", 3: "GVIT_ERR_DTYPE", 4: "GVIT_ERR_CUDA",
                 5: "GVIT_ERR_UNSUPPORTED"}
@@ -54,6 +54,7 @@ SIGNATURES = {
     "gvit_bgemm": [_i, _i, _i, _i, _vp, _i64, _i64, _i, _vp, _i64, _i64, _i, _i, _vp, _i64, _i64, _i, _vp, _i64, _i64, _i, _i,
                    _vp, _i, _vp, _i64, _i64, _vp],
     "gvit_dense_rownorm": [_vp, _i64, _i64, _i, _i, _i, _vp, _vp],
+    "gvit_knn_select": [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp],
     "gvit_dense_softmax_fwd": [_vp, _i, _vp, _i, _i, _i, _vp, _vp],
     "gvit_dense_softmax_bwd": [_vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp],
     "gvit_dense_combine_bwd": [_vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i, _vp, _vp],

@@ -36,7 +36,8 @@ int gvit_describe_path(const char* op, int dtype, int n_tokens, int dim, char* b
   const char* path = "unsupported";
   const bool bf16 = dtype == GVIT_BF16;
   if (dtype != GVIT_F32 && dtype != GVIT_BF16) return gvit::fail(GVIT_ERR_DTYPE, "describe_path: dtype %d", dtype);
-  if (!strcmp(op, "knn")) path = (bf16 && gvit::knn_tc_supported(n_tokens, dim, 8)) ? "knn:tcgen05+tma" : "knn:fp32-fma";
+  if (!strcmp(op, "knn")) path = (bf16 && gvit::knn_tc_supported(n_tokens, dim, 8)) ? "knn:tcgen05+tma"
+                                 : (bf16 && n_tokens > 256 && n_tokens <= 1024 && dim % 64 == 0) ? "knn:tcgen05 gram + row select" : "knn:fp32-fma";
   else if (!strcmp(op, "agg")) path = (bf16 && (gvit::agg3_tc_supported(n_tokens, dim, 8) || gvit::agg_tc_supported(n_tokens, dim, 8))) ? "agg:tcgen05+tma" : "agg:gather-fma+library-gemm";
   else if (!strcmp(op, "agg_res32")) path = (bf16 && gvit::agg3_tc_supported(n_tokens, dim, 8)) ? "agg:tcgen05+tma fp32-stream" : "agg:host-side residual add";
   else if (!strcmp(op, "agg_dense")) path = (bf16 && n_tokens <= 1024 && dim % 64 == 0 && dim <= 1024) ? "agg_dense:tcgen05 batched GEMMs + row-wise softmax" : "agg_dense:ATen composition (fp32 parity path)";

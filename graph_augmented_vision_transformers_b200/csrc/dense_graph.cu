@@ -137,6 +137,46 @@ __global__ void __launch_bounds__(256) dense_combine_bwd_kernel(const bf* __rest
   }
 }
 
+// G3 for more than 256 patch tokens: per-row top-k of S_ij = (G_ij rn_i) rn_j over a materialised fp32 Gram row (gvit_bgemm),
+// one warp per row.  Lane l holds columns l, l + 32, ...; k rounds of (lane-local best, warp arg-max, winner retires).  Order:
+// larger similarity first, at equal similarity the LOWER column (section 9 G3: the stable descending sort) - the lane-local
+// scan keeps the first maximum (columns ascend with the slot) and the butterfly prefers the lower column on ties.
+__global__ void __launch_bounds__(256) knn_select_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ rn, int B, int Np,
+                                                         int k, int32_t* __restrict__ idx, float* __restrict__ vals) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= B * Np) return;
+  const int b = w / Np;
+  const float* g = G + (int64_t)w * ldg;
+  const float* rnb = rn + (int64_t)b * Np;
+  const float rni = rn[w];
+  constexpr int MAXC = 32;                                   // Np <= 1024
+  float s[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int j = c * 32 + lane;
+    s[c] = j < Np ? (g[j] * rni) * rnb[j] : -FLT_MAX;
+  }
+  uint32_t taken = 0;
+  const int64_t o = (int64_t)w * k;
+  for (int r = 0; r < k; ++r) {
+    float bv = -FLT_MAX;
+    int bj = 0x7fffffff;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const bool free_ = !((taken >> c) & 1u) && c * 32 + lane < Np;
+      if (free_ && (s[c] > bv || bj == 0x7fffffff)) { bv = s[c]; bj = c * 32 + lane; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+      if (oj != 0x7fffffff && (bj == 0x7fffffff || ov > bv || (ov == bv && oj < bj))) { bv = ov; bj = oj; }
+    }
+    if ((bj & 31) == lane) taken |= 1u << (bj >> 5);
+    if (lane == 0) { idx[o + r] = bj; vals[o + r] = bv; }
+  }
+}
+
 inline unsigned warps_grid(int64_t rows) { return (unsigned)((rows * 32 + 255) / 256); }
 
 }  // namespace
@@ -144,6 +184,12 @@ inline unsigned warps_grid(int64_t rows) { return (unsigned)((rows * 32 + 255) /
 int dense_rownorm(const Tokens& t, float* rn, cudaStream_t st) {
   dense_rownorm_kernel<<<warps_grid((int64_t)t.B * t.Np), 256, 0, st>>>(static_cast<const bf*>(t.ptr), t.batch_stride, t.row_stride, t.B,
                                                                         t.Np, t.D, rn);
+  GVIT_CHECK_LAUNCH();
+  return GVIT_OK;
+}
+
+int knn_select(const float* G, int ldg, const float* rn, int B, int Np, int k, int32_t* idx, float* vals, cudaStream_t st) {
+  knn_select_kernel<<<warps_grid((int64_t)B * Np), 256, 0, st>>>(G, ldg, rn, B, Np, k, idx, vals);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }

@@ -143,6 +143,13 @@ int gvit_dense_rownorm(const void* p, int64_t batch_stride, int64_t row_stride, 
   return dense_rownorm(t, rn, static_cast<cudaStream_t>(stream));
 }
 
+int gvit_knn_select(const float* G, int ldg, const float* rn, int B, int Np, int k, int32_t* idx, float* vals, void* stream) {
+  TRY(check_dense("knn_select", B, Np));
+  GVIT_REQUIRE(G && rn && idx && vals && ldg >= Np && k >= 1 && k <= Np && k <= GVIT_MAX_K, GVIT_ERR_SHAPE,
+               "knn_select: ldg=%d k=%d (ldg >= Np, 1 <= k <= min(Np, %d))", ldg, k, GVIT_MAX_K);
+  return knn_select(G, ldg, rn, B, Np, k, idx, vals, static_cast<cudaStream_t>(stream));
+}
+
 int gvit_dense_softmax_fwd(const float* G, int ldg, const float* rn, int B, int Np, int ldA, void* A, void* stream) {
   TRY(check_dense("dense_softmax_fwd", B, Np));
   GVIT_REQUIRE(G && rn && A && ldg >= Np && ldA >= Np && ldA % 64 == 0 && ldA <= 1024, GVIT_ERR_SHAPE,

@@ -55,6 +55,7 @@ struct BgemmProduct {       // one A_p B_p term.  *_t == 0: K-major (A stored [M
 int bgemm_tc(int batch, int M, int N, int nprod, const BgemmProduct* prods, const float* row_scale, int out_dtype, void* out,
              int64_t out_rs, int64_t out_bs, cudaStream_t st);
 int dense_rownorm(const Tokens& t, float* rn, cudaStream_t st);
+int knn_select(const float* G, int ldg, const float* rn, int B, int Np, int k, int32_t* idx, float* vals, cudaStream_t st);
 int dense_softmax_fwd(const float* G, int ldg, const float* rn, int B, int Np, int ldA, void* A, cudaStream_t st);
 int dense_softmax_bwd(const float* dA, int ldg, const void* A, int ldA, const float* rn, int B, int Np, void* dG, cudaStream_t st);
 int dense_combine_bwd(const void* T, const void* V, const Tokens& t, const float* rn, void* dp, cudaStream_t st);

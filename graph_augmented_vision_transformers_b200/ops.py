@@ -790,20 +790,35 @@ def _token_view(h: torch.Tensor):
 
 
 @torch.no_grad()
+def _knn(h: torch.Tensor, k: int):
+    """G1-G3 dispatch on a contiguous (B, 1+Np, D) tensor.  bf16 with 256 < Np <= 1024 (the 576 tokens of a 384x384 image):
+    Gram matrix on tcgen05 (gvit_bgemm, fp32) + row norms + per-row selection (gvit_knn_select); everything else is ONE
+    gvit_knn_fwd launch (tcgen05 fused GEMM + top-k up to 256 tokens, the exact-fp32-FMA kernel for fp32 / odd shapes)."""
+    off, bs, rs, B, Np, D = _token_view(h)
+    st = _stream()
+    idx = torch.empty((B, Np, k), dtype=torch.int32, device=h.device)
+    vals = torch.empty((B, Np, k), dtype=torch.float32, device=h.device)
+    rnorm = torch.empty((B, Np), dtype=torch.float32, device=h.device)
+    if h.dtype == torch.bfloat16 and _lib.describe_path("knn", GVIT_BF16, Np, D).startswith("knn:tcgen05 gram"):
+        tok = _ptr(h, off)
+        ld = (Np + 3) // 4 * 4
+        _call("gvit_dense_rownorm", tok, bs, rs, B, Np, D, _ptr(rnorm), st)
+        G = torch.empty((B, Np, ld), dtype=torch.float32, device=h.device)
+        _bgemm(B, Np, Np, [(tok, rs, bs, 0, tok, rs, bs, 0, D)], G, ld, Np * ld)
+        _call("gvit_knn_select", _ptr(G), ld, _ptr(rnorm), B, Np, int(k), _ptr(idx), _ptr(vals), st)
+    else:
+        _call("gvit_knn_fwd", _ptr(h, off), bs, rs, B, Np, D, int(k), _dtype_code(h), _ptr(idx), _ptr(vals), _ptr(rnorm), st)
+    return idx, vals, rnorm
+
+
+@torch.no_grad()
 def knn_graph(h: torch.Tensor, k: int):
     """G1-G3 over the patch tokens of h (B, 1+Np, D): returns (idx int32 (B,Np,k), vals fp32, rnorm fp32 (B,Np)).
 
     Neighbour order: descending cosine similarity, ties to the lowest index.
     """
     _check_cuda(h)
-    h = h.contiguous()
-    off, bs, rs, B, Np, D = _token_view(h)
-    idx = torch.empty((B, Np, k), dtype=torch.int32, device=h.device)
-    vals = torch.empty((B, Np, k), dtype=torch.float32, device=h.device)
-    rnorm = torch.empty((B, Np), dtype=torch.float32, device=h.device)
-    _call("gvit_knn_fwd", _ptr(h, off), bs, rs, B, Np, D, int(k), _dtype_code(h), _ptr(idx), _ptr(vals), _ptr(rnorm),
-          _stream())
-    return idx, vals, rnorm
+    return _knn(h.contiguous(), int(k))
 
 
 @torch.no_grad()
@@ -870,10 +885,7 @@ class _PatchGraph(torch.autograd.Function):
         off, bs, rs, B, Np, D = _token_view(h)
         dt = _dtype_code(h)
         st = _stream()
-        idx = torch.empty((B, Np, k), dtype=torch.int32, device=h.device)
-        vals = torch.empty((B, Np, k), dtype=torch.float32, device=h.device)
-        rnorm = torch.empty((B, Np), dtype=torch.float32, device=h.device)
-        _call("gvit_knn_fwd", _ptr(h, off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(vals), _ptr(rnorm), st)
+        idx, vals, rnorm = _knn(h, k)
         w = torch.empty((B, Np, k), dtype=torch.float32, device=h.device)
         if fused_agg_available(h.dtype, Np, D, k):
             out = torch.empty_like(h if resid is None else resid)        # an fp32 residual stream gets an fp32 result

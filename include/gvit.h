@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GVIT_ABI_VERSION 14
+#define GVIT_ABI_VERSION 15
 #if defined(__GNUC__)
 #define GVIT_API __attribute__((visibility("default")))
 #else
@@ -131,6 +131,10 @@ GVIT_API int gvit_bgemm(int batch, int M, int N, int nprod,
                const float* row_scale, int out_dtype, void* out, int64_t out_rs, int64_t out_bs, void* stream);
 /* G1: rn[b,i] = 1 / max(||p[b,i,:]||, 1e-12) for the strided patch-token view p (bf16). */
 GVIT_API int gvit_dense_rownorm(const void* p, int64_t batch_stride, int64_t row_stride, int B, int Np, int D, float* rn, void* stream);
+/* G3 for 256 < Np <= 1024 (e.g. the 576 patch tokens of a 384x384 image; gvit_knn_fwd fuses GEMM and selection up to 256
+ * tokens): per-row top-k of S_ij = (G_ij rn_i) rn_j over the materialised fp32 Gram matrix G = P P^T (gvit_bgemm) and
+ * the norms of gvit_dense_rownorm.  idx / vals as gvit_knn_fwd emits them: descending similarity, ties -> lowest index. */
+GVIT_API int gvit_knn_select(const float* G, int ldg, const float* rn, int B, int Np, int k, int32_t* idx, float* vals, void* stream);
 /* G2 + G4: A~[b,i,:] = softmax_j(G[b,i,j] rn[b,i] rn[b,j]) as bf16; G fp32 (B,Np,ldg) - the Gram matrix P P^T of gvit_bgemm;
  * A~ (B,Np,ldA), ldA % 64 == 0, the pad columns [Np, ldA) are written as zeros (a K-major gvit_bgemm operand). */
 GVIT_API int gvit_dense_softmax_fwd(const float* G, int ldg, const float* rn, int B, int Np, int ldA, void* A, void* stream);

@@ -57,12 +57,25 @@ def test_fp32_ragged_shapes_bit_exact_vs_live_strict_oracle(B, Np, D, k):
 
 
 def test_bf16_storage_fp32_arithmetic_kernel_is_bit_exact_too():
-    """bf16-stored tokens outside the tcgen05 range (Np > 256) run the same exact-FMA kernel on the bf16 values."""
-    hc, hd = tokens(1, 300, 128, seed=3, dtype=torch.bfloat16)
-    assert _lib.describe_path("knn", _lib.GVIT_BF16, 300, 128) != "knn:tcgen05+tma"
+    """bf16-stored tokens outside every tcgen05 range (D % 64 != 0) run the same exact-FMA kernel on the bf16 values."""
+    hc, hd = tokens(1, 300, 72, seed=3, dtype=torch.bfloat16)
+    assert _lib.describe_path("knn", _lib.GVIT_BF16, 300, 72) == "knn:fp32-fma"
     idx, vals, _ = ops.knn_graph(hd, 8)
     li, lv, _ = knn_strict.knn_strict(hc[:, 1:].numpy(), 8)
     assert np.array_equal(idx.cpu().numpy(), li) and np.array_equal(vals.cpu().numpy(), lv)
+
+
+def test_bf16_more_than_256_tokens_runs_on_tensor_cores():
+    """256 < Np <= 1024 (the 576 patch tokens of a 384x384 image): Gram matrix by gvit_bgemm + gvit_knn_select; exact ties
+    still resolve to the lowest index (rows 7 and 400 are duplicates)."""
+    assert _lib.describe_path("knn", _lib.GVIT_BF16, 576, 1024) == "knn:tcgen05 gram + row select"
+    hc, _ = tokens(2, 576, 256, seed=11, dtype=torch.bfloat16)
+    hc[:, 401] = hc[:, 8]                                   # patch rows 7 and 400 identical
+    idx, vals, rnorm = ops.knn_graph(hc.to(DEV, torch.bfloat16), 8)
+    idx = idx.cpu().numpy()
+    assert list(idx[0, 7, :2]) == [7, 400] and list(idx[0, 400, :2]) == [7, 400]
+    assert (idx[..., 0][:, [i for i in range(576) if i != 400]] == np.array([i for i in range(576) if i != 400])).all()
+    assert (np.diff(vals.cpu().numpy(), axis=-1) <= 0).all()
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
