@@ -44,7 +44,7 @@ VITL384_BATCH, VITL384_FLOPS = 32, 1331e9
 WORKLOADS = {
     "vitb224": (MODEL_CFG, PER_GPU_BATCH, FLOPS_PER_IMAGE,
                 "BASELINE configs[1]: ViT-B/16 + kNN graph block (196 patch tokens, k=8, every block), full training step "
-                "(fwd, loss, bwd, grad sync, clip, AdamW), bf16 autocast, 224x224"),
+                "(fwd, loss, bwd, grad sync, clip, warm-up/cosine LR, AdamW), bf16 autocast, 224x224"),
     "vitl384": (VITL384_CFG, VITL384_BATCH, VITL384_FLOPS,
                 "BASELINE configs[3]: ViT-L/16 at 384x384 (576 patch tokens) + DENSE adjacency graph block in every layer, "
                 "full training step (fwd, loss, bwd, grad sync, clip, AdamW), bf16 autocast"),
@@ -70,6 +70,13 @@ def cpu_oracle_step_fn(batch):
     lambdas = torch.ones(3, requires_grad=True)
     opt = torch.optim.AdamW([{"params": model.parameters()}, {"params": [lambdas], "lr": 1e-5}], lr=1e-4,
                             weight_decay=0.05)
+    import math
+
+    def lr_lambda(step, warm=100, total=10000):              # trainer.py:81-85
+        if step < warm:
+            return float(step) / float(max(1, warm))
+        return 0.5 * (1.0 + math.cos(math.pi * float(step - warm) / float(max(1, total - warm))))
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda)
     g = torch.Generator().manual_seed(1234)
     img = torch.randn(batch, 3, 224, 224, generator=g)
     tgt = (torch.rand(batch, 14, generator=g) > 0.9).float()
@@ -79,8 +86,9 @@ def cpu_oracle_step_fn(batch):
         opt.zero_grad(set_to_none=True)
         loss = vit_oracle.multilabel_loss(model(img), tgt, lambdas, pos_weight)
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        torch.nn.utils.clip_grad_norm_(list(model.parameters()) + [lambdas], 1.0)
         opt.step()
+        sched.step()
         return loss.item()
 
     return step
@@ -108,7 +116,7 @@ def time_cpu_oracle(steps, warmup, budget_s):
         step()
     dt = (time.perf_counter() - t0) / steps
     return dict(value=batch / dt, unit=UNIT, cores=cores, kind="port",
-                sample=f"{steps} training steps (fwd+loss+bwd+clip+AdamW) of batch {batch}, fp32, CPU oracle "
+                sample=f"{steps} training steps (fwd+loss+bwd+clip+LambdaLR+AdamW) of batch {batch}, fp32, CPU oracle "
                        f"(reference ViT restated + section-9 graph layer), torch {torch.__version__} with {cores} threads"), dt, batch
 
 
@@ -307,14 +315,14 @@ def roofline_block(kernels, ms_step, peaks):
 
 
 def _train_objects(dev, name, B):
-    from graph_augmented_vision_transformers_b200 import modules
+    from graph_augmented_vision_transformers_b200 import modules, optim
     from graph_augmented_vision_transformers_b200.losses import DynamicWeightedLoss
     cfg = WORKLOADS[name][0]
     torch.manual_seed(42)
     model = modules.VisionTransformer(**cfg).to(dev).train()
     crit = DynamicWeightedLoss(cfg["num_classes"]).to(dev)
-    opt = torch.optim.AdamW([{"params": model.parameters()}, {"params": crit.parameters(), "lr": 1e-5}], lr=1e-4,
-                            weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, fused=True, capturable=True)
+    opt = optim.FusedAdamW([{"params": model.parameters()}, {"params": crit.parameters(), "lr": 1e-5}], lr=1e-4,
+                           weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, warmup_steps=100, total_steps=10000)
     gen = torch.Generator(device=dev).manual_seed(1234)
     img = torch.randn(B, 3, cfg["img_size"], cfg["img_size"], device=dev, generator=gen)
     tgt = (torch.rand(B, 14, device=dev, generator=gen) > 0.9).float()
@@ -327,7 +335,6 @@ def measure_train_short(dev, name, steps, warmup, batch=None):
     _, B, flops, workload = WORKLOADS[name]
     B = batch or B
     cfg, model, crit, opt, img, tgt = _train_objects(dev, name, B)
-    params = list(model.parameters()) + list(crit.parameters())
 
     def step():
         opt.zero_grad(set_to_none=True)
@@ -335,8 +342,7 @@ def measure_train_short(dev, name, steps, warmup, batch=None):
             logits = model(img)
         loss, _ = crit(logits, tgt)
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(params, 1.0, foreach=True)
-        opt.step()
+        opt.step()                                           # clip + warm-up/cosine schedule + AdamW (optim.FusedAdamW)
         return loss
 
     for _ in range(warmup):
@@ -419,7 +425,7 @@ def run_infer(args):
 # our arm
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
-    from graph_augmented_vision_transformers_b200 import _lib, dp, modules, ops
+    from graph_augmented_vision_transformers_b200 import _lib, dp, modules, ops, optim
     from graph_augmented_vision_transformers_b200.losses import DynamicWeightedLoss
     from graph_augmented_vision_transformers_b200.step import CapturedTrainStep
     import torch.distributed as dist
@@ -445,9 +451,10 @@ def run_ours(args):
     dp.broadcast_parameters(model)
     dp.broadcast_parameters(crit)
     sync = dp.GradSync(model, bucket_mb=32.0, extra_params=list(crit.parameters()))
-    opt = torch.optim.AdamW([{"params": model.parameters()}, {"params": crit.parameters(), "lr": 1e-5}], lr=1e-4,
-                            weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, fused=True, capturable=True)
-    all_params = list(model.parameters()) + list(crit.parameters())
+    # the reference trainer's optimiser recipe (trainer.py:47-56,77-87,114-118): AdamW over two groups (loss weights at 0.1 x lr),
+    # linear warm-up + cosine per step, global-norm clip at 1.0 - one device-side libgvit step (optim.FusedAdamW)
+    opt = optim.FusedAdamW([{"params": model.parameters()}, {"params": crit.parameters(), "lr": 1e-5}], lr=1e-4,
+                           weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, warmup_steps=100, total_steps=10000)
 
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     img_dev = torch.randn(B, 3, S, S, device=dev, generator=gen)
@@ -460,8 +467,7 @@ def run_ours(args):
         loss, _ = crit(logits, tgt)
         loss.backward()
         sync.finish()
-        torch.nn.utils.clip_grad_norm_(all_params, 1.0, foreach=True)
-        opt.step()
+        opt.step()                                           # clip + schedule + AdamW
         return loss
 
     # The step is captured once into a CUDA graph and replayed (step.CapturedTrainStep): ~800 launches per step leave
@@ -470,7 +476,7 @@ def run_ours(args):
     if not args.eager:
         try:
             ops.reset_launch_count()
-            captured = CapturedTrainStep(model, crit, opt, max_norm=1.0, clip_params=all_params,
+            captured = CapturedTrainStep(model, crit, opt, max_norm=None,          # the clip lives inside the optimiser step
                                          grad_sync=sync if world > 1 else None, warmup=3).capture(img_dev, tgt_dev)
             per_step_launches = ops.launch_count() // 4      # 3 eager warm-up bodies + the captured one
             step_mode = "cuda-graph"

@@ -8,7 +8,7 @@ __version__ = "0.1.0"
 
 
 def __getattr__(name):
-    if name in ("ops", "modules", "dp", "step"):
+    if name in ("ops", "modules", "dp", "step", "optim", "checkpoint", "losses"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

@@ -363,4 +363,18 @@ int gvit_embed_assemble(const void* y, const void* bias, const void* cls, const 
                         static_cast<cudaStream_t>(stream));
 }
 
+int gvit_mt_chunk_elems(void) { return mt_chunk_elems(); }
+
+int gvit_mt_adamw_step(const int64_t* p, const int64_t* g, const int64_t* m, const int64_t* v, const int64_t* numel, const float* lr,
+                       const float* wd, const int32_t* chunk_tensor, const int32_t* chunk_index, int32_t* tstep, int ntensors, int nchunks,
+                       float max_norm, int64_t warmup_steps, int64_t total_steps, float beta1, float beta2, float eps, int64_t* step,
+                       float* sched, float* partial_ws, void* stream) {
+  GVIT_REQUIRE(p && g && m && v && numel && lr && wd && chunk_tensor && chunk_index && tstep && step && sched && partial_ws, GVIT_ERR_SHAPE,
+               "mt_adamw_step: null pointer");
+  GVIT_REQUIRE(ntensors >= 1 && nchunks >= 1 && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps > 0.f, GVIT_ERR_SHAPE,
+               "mt_adamw_step: nchunks=%d betas=(%f, %f) eps=%g", nchunks, beta1, beta2, eps);
+  return mt_adamw_step(p, g, m, v, numel, lr, wd, chunk_tensor, chunk_index, tstep, ntensors, nchunks, max_norm, warmup_steps, total_steps,
+                       beta1, beta2, eps, step, sched, partial_ws, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

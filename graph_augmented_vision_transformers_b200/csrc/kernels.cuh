@@ -90,6 +90,13 @@ int64_t fc2_bwd_partial_rows(int64_t M);
 int linear_gelu_dropout_bwd_tc(const void* dout, const void* w2, const void* u, const uint8_t* mask, int64_t M, int N, int K, float p,
                                void* du, float* colsum_out, float* partial_ws, cudaStream_t st);
 
+// ---- optimiser step : optim.cu
+int mt_chunk_elems();
+int mt_adamw_step(const int64_t* p, const int64_t* g, const int64_t* m, const int64_t* v, const int64_t* numel, const float* lr,
+                  const float* wd, const int32_t* chunk_tensor, const int32_t* chunk_index, int32_t* tstep, int ntensors, int nchunks,
+                  float max_norm, int64_t warmup_steps, int64_t total_steps, float beta1, float beta2, float eps, int64_t* step,
+                  float* sched, float* partial_ws, cudaStream_t st);
+
 // ---- token prologue : embed.cu
 int patchify(const void* img, int B, int C, int H, int W, int P, int in_dtype, int out_dtype, void* out, cudaStream_t st);
 int embed_assemble(const void* y, const void* bias, const void* cls, const void* pos, int B, int N, int D, float p,

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GVIT_ABI_VERSION 15
+#define GVIT_ABI_VERSION 16
 #if defined(__GNUC__)
 #define GVIT_API __attribute__((visibility("default")))
 #else
@@ -249,6 +249,25 @@ GVIT_API int gvit_patchify(const void* img, int B, int C, int H, int W, int P, i
 GVIT_API int gvit_embed_assemble(const void* y, const void* bias, const void* cls, const void* pos, int B, int N, int D, float p,
                         uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int dtype, int param_dtype, int out_dtype,
                         void* out, uint8_t* keep_mask, void* stream);
+
+/* ---- f2: the optimiser side of Trainer.train_epoch (/root/reference/src/training/trainer.py:47-56,77-87,114-118) --------------
+ * clip_grad_norm_(all params, max_norm) + LambdaLR (linear warm-up, then cosine, advanced per STEP) + AdamW over two
+ * parameter groups, as three multi-tensor launches with everything (norm, clip coefficient, schedule factor, step count)
+ * kept on the device - capturable in a CUDA graph, and the clip costs no extra pass over the gradients.
+ * Device tables, one entry per tensor (n tensors, fp32): p / g / m / v = addresses of parameter, gradient (0 = no gradient:
+ * the tensor is skipped), exp_avg, exp_avg_sq; numel; lr = its group's BASE learning rate; wd = its weight decay.
+ * chunk_tensor / chunk_index: nchunks entries, chunk c covers elements [chunk_index*E, +E) of tensor chunk_tensor with
+ * E = gvit_mt_chunk_elems().  step: device int64, completed steps (read as the scheduler epoch, then incremented).
+ * tstep: n device int32, the number of updates each tensor has received (torch.optim keeps `step` per parameter: a tensor
+ * without gradient does not advance); it drives AdamW's bias corrections.
+ * sched: 3 device floats written by the call: total gradient norm, clip coefficient, schedule factor lambda(step).
+ * max_norm <= 0 disables clipping; total_steps <= 0 keeps the learning rate constant.
+ * partial_ws: nchunks floats. */
+GVIT_API int gvit_mt_chunk_elems(void);
+GVIT_API int gvit_mt_adamw_step(const int64_t* p, const int64_t* g, const int64_t* m, const int64_t* v, const int64_t* numel,
+                       const float* lr, const float* wd, const int32_t* chunk_tensor, const int32_t* chunk_index, int32_t* tstep,
+                       int ntensors, int nchunks, float max_norm, int64_t warmup_steps, int64_t total_steps, float beta1, float beta2,
+                       float eps, int64_t* step, float* sched, float* partial_ws, void* stream);
 
 #ifdef __cplusplus
 }

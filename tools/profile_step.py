@@ -24,7 +24,9 @@ cfg, dbatch, _, _ = bench.WORKLOADS[args.config]
 args.batch = args.batch or dbatch
 model = modules.VisionTransformer(**cfg).to(dev).train()
 crit = DynamicWeightedLoss(14).to(dev)
-opt = torch.optim.AdamW(list(model.parameters()) + list(crit.parameters()), lr=1e-4, weight_decay=0.05, fused=True)
+from graph_augmented_vision_transformers_b200 import optim  # noqa: E402
+opt = optim.FusedAdamW([{"params": model.parameters()}, {"params": crit.parameters(), "lr": 1e-5}], lr=1e-4, weight_decay=0.05,
+                       max_norm=1.0, warmup_steps=100, total_steps=10000)
 img = torch.randn(args.batch, 3, cfg["img_size"], cfg["img_size"], device=dev)
 tgt = (torch.rand(args.batch, 14, device=dev) > 0.9).float()
 params = list(model.parameters()) + list(crit.parameters())
@@ -36,7 +38,6 @@ def step():
         logits = model(img)
     loss, _ = crit(logits, tgt)
     loss.backward()
-    torch.nn.utils.clip_grad_norm_(params, 1.0, foreach=True)
     opt.step()
 
 
