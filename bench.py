@@ -368,8 +368,11 @@ def measure_train_short(dev, name, steps, warmup, batch=None):
 
 def inference_sweep(dev, batches, ks, everys, iters):
     """BASELINE configs[4]: inference (model.eval(), no_grad, bf16 autocast, sigmoid on the device - the call of
-    /root/reference/scripts/evaluate.py:104-115) over batch size x k x graph placement; collective-free."""
+    /root/reference/scripts/evaluate.py:104-115) over batch size x k x graph placement; collective-free.  Each point is
+    measured issued from Python (`ms`) and replayed from a CUDA graph (`ms_graph`, step.CapturedForward: small batches are
+    launch-bound otherwise); `images_per_s` is the better of the two, `issue` says which."""
     from graph_augmented_vision_transformers_b200 import modules
+    from graph_augmented_vision_transformers_b200.step import CapturedForward
     out = []
     for every in everys:
         for k in ks:
@@ -389,8 +392,21 @@ def inference_sweep(dev, batches, ks, everys, iters):
                     b.record()
                     torch.cuda.synchronize()
                 ms = a.elapsed_time(b) / iters
-                out.append({"batch": B, "k": k, "graph_every": every, "ms": round(ms, 3), "images_per_s": round(B / (ms / 1e3), 1)})
-                del img, probs
+                cap = CapturedForward(model)
+                for _ in range(2):
+                    cap(img)
+                torch.cuda.synchronize()
+                a.record()
+                for _ in range(iters):
+                    probs = cap(img)
+                b.record()
+                torch.cuda.synchronize()
+                msg = a.elapsed_time(b) / iters
+                cap.release()
+                best = min(ms, msg)
+                out.append({"batch": B, "k": k, "graph_every": every, "ms": round(ms, 3), "ms_graph": round(msg, 3),
+                            "issue": "cuda-graph" if msg <= ms else "eager", "images_per_s": round(B / (best / 1e3), 1)})
+                del img, probs, cap
             del model
             torch.cuda.empty_cache()
     return out

@@ -267,6 +267,12 @@ __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_consta
       // an odd step's bf16 destination is the upper half of the previous (even) step's in-place staging, which the
       // OTHER warpgroup converts: wait until it has read it
       if (t & 1) mbar_wait(&ctl->conv_done[0], ((t - 1) >> 1) & 1);
+      // ... and an even step waits for the other warpgroup's previous (odd) step.  Not a data dependency - a PHASE guard:
+      // the MMA warp's step t only needs conv_done[t & 1], so warpgroup 0 could finish steps 0 AND 2 (two completions of
+      // conv_done[0]) before a delayed warpgroup 1 (it starts with the CLS-row copy and the residual prefetch, both global
+      // round trips) had begun its parity wait for step 1 - which then named a phase two completions back and never
+      // returned.  One CTA in ~10^5 hung that way (r2y: mbarrier timeout in a second-wave mt = 0 CTA at B = 128).
+      else if (t >= 2) mbar_wait(&ctl->conv_done[1], ((t - 2) >> 1) & 1);
       tc_fence_after();
       GVIT_TR(11);
       for (int h0 = 0; h0 < width; h0 += 64) {

@@ -22,7 +22,7 @@ import torch
 
 from . import ops
 
-__all__ = ["CapturedTrainStep"]
+__all__ = ["CapturedTrainStep", "CapturedForward"]
 
 
 class CapturedTrainStep:
@@ -118,3 +118,56 @@ class CapturedTrainStep:
         self.graph = None
         self.loss = None
         ops.set_rng_offset_tensor(None)
+
+
+class CapturedForward:
+    """``probs = fwd(images)`` - the inference call of /root/reference/scripts/evaluate.py:104-115 (``model.eval()``,
+    ``torch.no_grad()``, forward, sigmoid) replayed from ONE CUDA graph per batch shape.
+
+    A ViT-B + graph forward is ~330 kernel launches; at batch 32 they take ~2.5 ms on the device but ~6.4 ms to issue from
+    Python, so small-batch inference is launch-bound until the host is out of the loop.  Graphs are cached per input shape;
+    the returned tensor is a static buffer that the next call with the same shape overwrites.  Inference is collective-free,
+    so this is per-GPU state only.
+    """
+
+    def __init__(self, model, *, amp_dtype: torch.dtype | None = torch.bfloat16, activation=torch.sigmoid, warmup: int = 2):
+        self.model, self.amp_dtype, self.activation, self.warmup = model, amp_dtype, activation, max(1, int(warmup))
+        self._graphs: dict = {}
+
+    def _body(self, x):
+        if self.amp_dtype is not None:
+            with torch.autocast("cuda", dtype=self.amp_dtype):
+                y = self.model(x)
+        else:
+            y = self.model(x)
+        return self.activation(y.float()) if self.activation is not None else y
+
+    @torch.no_grad()
+    def __call__(self, images: torch.Tensor) -> torch.Tensor:
+        if not images.is_cuda:
+            raise RuntimeError("CapturedForward runs on CUDA tensors only")
+        if self.model.training:
+            raise RuntimeError("CapturedForward is the inference path: call model.eval() first (dropout would be frozen into the graph)")
+        key = (tuple(images.shape), images.dtype, images.device)
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_in = images.clone()
+            side = torch.cuda.Stream(images.device)
+            side.wait_stream(torch.cuda.current_stream(images.device))
+            with torch.cuda.stream(side):
+                for _ in range(self.warmup):
+                    self._body(static_in)
+            torch.cuda.current_stream(images.device).wait_stream(side)
+            torch.cuda.synchronize(images.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._body(static_in)
+            entry = self._graphs[key] = (graph, static_in, static_out)
+        graph, static_in, static_out = entry
+        if images.data_ptr() != static_in.data_ptr():
+            static_in.copy_(images, non_blocking=True)
+        graph.replay()
+        return static_out
+
+    def release(self):
+        self._graphs.clear()

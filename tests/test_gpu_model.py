@@ -373,3 +373,41 @@ def test_config4_vit_l_384_dense_shapes_run():
     for n, p in m.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
     assert worst[0][1] < TOL_BF16, worst
+
+
+def test_captured_forward_matches_eager_inference():
+    """step.CapturedForward (the evaluate.py:104-115 call replayed from a CUDA graph, cached per batch shape) returns exactly
+    what the eager bf16 forward returns, for two batch shapes, and refuses a model in training mode."""
+    from graph_augmented_vision_transformers_b200.step import CapturedForward
+    _, m = _pair(seed=12)
+    fwd = CapturedForward(m)
+    for B in (3, 8, 3):
+        img = torch.randn(B, 3, 64, 64, generator=torch.Generator().manual_seed(B)).to(DEV)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            want = torch.sigmoid(m(img).float())
+        assert torch.equal(fwd(img), want)
+    assert len(fwd._graphs) == 2
+    m.train()
+    with pytest.raises(RuntimeError, match="eval"):
+        fwd(img)
+
+
+def test_repeated_batch128_inference_agg3_phase_guard():
+    """Regression (r2y): at batch 128 the fused aggregation kernel launches a second wave of CTAs; an mt = 0 CTA whose
+    warpgroup 1 was delayed by its global round trips waited on a barrier phase that warpgroup 0 had already completed twice
+    and hung (~1 CTA in 10^5).  Thirty ViT-B/16 + k=4 graph forwards at that size, eager and replayed from a CUDA graph."""
+    from graph_augmented_vision_transformers_b200.step import CapturedForward
+    torch.manual_seed(42)
+    m = modules.VisionTransformer(img_size=224, patch_size=16, embed_dim=768, depth=12, num_heads=12, graph_mode="knn", graph_k=4).to(DEV).eval()
+    img = torch.randn(128, 3, 224, 224, device=DEV)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        ref = torch.sigmoid(m(img).float())
+        for _ in range(14):
+            out = torch.sigmoid(m(img).float())
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    fwd = CapturedForward(m)
+    for _ in range(15):
+        out = fwd(img)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
