@@ -334,6 +334,24 @@ int gvit_linear_gelu_dropout_bwd(const void* dout, const void* w2, const void* u
   return linear_gelu_dropout_bwd_tc(dout, w2, u, keep_mask, M, N, K, p, du, colsum_out, partial_ws, static_cast<cudaStream_t>(stream));
 }
 
+int64_t gvit_linear_gemm_ws_bytes(int64_t M, int N, int K) { return gemm2_tc_supported(M, N, K) ? gemm2_ws_bytes(M, N, K) : 0; }
+
+int gvit_linear_gemm(const void* a, int a_t, int64_t a_rs, const void* b, int b_t, int64_t b_rs, int64_t M, int N, int K,
+                     const void* bias, int out_dtype, void* out, int64_t out_rs, void* workspace, int64_t workspace_bytes,
+                     void* stream) {
+  TRY(check_dtype(out_dtype, "linear_gemm"));
+  GVIT_REQUIRE(a && b && out, GVIT_ERR_SHAPE, "linear_gemm: null pointer");
+  GVIT_REQUIRE((a_t == 0 || a_t == 1) && (b_t == 0 || b_t == 1), GVIT_ERR_SHAPE, "linear_gemm: a_t=%d b_t=%d (0 or 1)", a_t, b_t);
+  GVIT_REQUIRE(gemm2_tc_supported(M, N, K), GVIT_ERR_UNSUPPORTED, "linear_gemm: M=%lld N=%d K=%d (N %% 256 == 0 required)",
+               (long long)M, N, K);
+  GVIT_REQUIRE(M <= 0x7fffffffLL - 256 && out_rs >= N, GVIT_ERR_SHAPE, "linear_gemm: M=%lld out_rs=%lld", (long long)M, (long long)out_rs);
+  GVIT_REQUIRE(aligned16(a) && aligned16(b) && aligned16(out) && (!bias || aligned16(bias)) && a_rs % 8 == 0 && b_rs % 8 == 0 &&
+               out_rs % (out_dtype == GVIT_F32 ? 4 : 8) == 0 && (!workspace || aligned16(workspace)), GVIT_ERR_ALIGN,
+               "linear_gemm: operands / rows / workspace must be 16-byte aligned");
+  return gemm2_tc(a, a_t, a_rs, b, b_t, b_rs, M, N, K, bias, out_dtype, out, out_rs, static_cast<float*>(workspace), workspace_bytes,
+                  static_cast<cudaStream_t>(stream));
+}
+
 int gvit_patchify(const void* img, int B, int C, int H, int W, int P, int in_dtype, int out_dtype, void* out, void* stream) {
   TRY(check_dtype(in_dtype, "patchify"));
   TRY(check_dtype(out_dtype, "patchify"));

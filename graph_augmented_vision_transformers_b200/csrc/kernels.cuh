@@ -90,6 +90,12 @@ int64_t fc2_bwd_partial_rows(int64_t M);
 int linear_gelu_dropout_bwd_tc(const void* dout, const void* w2, const void* u, const uint8_t* mask, int64_t M, int N, int K, float p,
                                void* du, float* colsum_out, float* partial_ws, cudaStream_t st);
 
+// ---- 2-SM Linear GEMM : gemm2_tc.cu
+bool gemm2_tc_supported(int64_t M, int N, int K);
+int64_t gemm2_ws_bytes(int64_t M, int N, int K);
+int gemm2_tc(const void* a, int a_t, int64_t a_rs, const void* b, int b_t, int64_t b_rs, int64_t M, int N, int K, const void* bias,
+             int out_dtype, void* out, int64_t out_rs, float* ws, int64_t ws_bytes, cudaStream_t st);
+
 // ---- optimiser step : optim.cu
 int mt_chunk_elems();
 int mt_adamw_step(const int64_t* p, const int64_t* g, const int64_t* m, const int64_t* v, const int64_t* numel, const float* lr,

@@ -167,6 +167,56 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- cta_group::2 : one tcgen05.mma spans the two CTAs of a cluster pair (M = 256).  Each CTA stages ITS 128 rows of A and
+// ITS half of B's N extent at the same shared-memory offsets; the leader (cluster rank 0) issues the instruction and the
+// hardware reads both shared memories, so a CTA fills and feeds only HALF of B per tile.  Both CTAs allocate / free TMEM
+// with the .cta_group::2 forms (same warp id, same slot address); barriers living in the leader are reached from the peer
+// through a mapa-translated shared::cluster address. ----
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_smem_addr), "r"(rank));
+  return r;
+}
+// remote (or local) arrival on an mbarrier given by its shared::cluster address
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// tile load into THIS CTA's shared memory whose completion bytes are counted on the mbarrier at `bar_cluster_addr`
+// (the leader's full barrier of the stage)
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* m, int c0, int c1, int c2, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* slot_in_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_ss_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(static_cast<uint32_t>(accumulate))
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_2sm(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(static_cast<uint32_t>(accumulate))
+      : "memory");
+}
+// arrives (once all previously issued pair MMAs have completed) on the mbarrier at this shared-memory offset in every CTA
+// of cta_mask
+__device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
 // ---- tcgen05.ld : warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); thread t gets lane base+t ----
 // commit that arrives on the mbarrier at the same shared-memory offset in every CTA of the cluster selected by cta_mask
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {

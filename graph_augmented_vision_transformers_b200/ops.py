@@ -161,10 +161,62 @@ def _shadow(prm, dtype: torch.dtype):
     return t.to(dtype).contiguous()
 
 
+# ------------------------------------------------------------------------------------------------
+# a1 / f1: the dense GEMMs of every nn.Linear - forward, input gradient, weight gradient - through gvit_linear_gemm (one
+# persistent 2-SM tcgen05 kernel, csrc/gemm2_tc.cu) whenever the operands are bf16 with an output width that is a multiple
+# of 256; the exact-fp32 parity path and the 14-logit head (vit.py:176) stay torch matmuls.
+# ------------------------------------------------------------------------------------------------
+_GEMM2 = {"on": os.environ.get("GVIT_GEMM2", "1") != "0"}             # GVIT_GEMM2=0: library GEMMs (A/B switch)
+
+
+def _gemm2_operand(t: torch.Tensor) -> bool:
+    return (t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 8 == 0 and t.stride(0) >= t.shape[1]
+            and t.data_ptr() % 16 == 0)
+
+
+def _gemm2(a, a_t, b, b_t, M, N, K, bias, out):
+    ws_bytes = 0
+    ws = None
+    if out.dtype == torch.float32:
+        ws_bytes = int(_lib.load().gvit_linear_gemm_ws_bytes(M, N, K))
+        if ws_bytes:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=out.device)
+    _call("gvit_linear_gemm", _ptr(a), a_t, a.stride(0), _ptr(b), b_t, b.stride(0), M, N, K, _ptr(bias),
+          GVIT_F32 if out.dtype == torch.float32 else GVIT_BF16, _ptr(out), out.stride(0), _ptr(ws), ws_bytes, _stream())
+    return out
+
+
+def _mm_nt(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None) -> torch.Tensor:
+    """``F.linear(x, w, bias)``: y = x w^T + bias over the last dimension of x (w is (N, K))."""
+    N, K = w.shape
+    if (_GEMM2["on"] and x.is_cuda and x.dtype == torch.bfloat16 and N % 256 == 0 and K % 64 == 0 and x.is_contiguous()
+            and _gemm2_operand(w) and (bias is None or (bias.dtype == torch.bfloat16 and bias.is_contiguous() and bias.data_ptr() % 16 == 0))):
+        x2 = x.view(-1, K)
+        if _gemm2_operand(x2):
+            y = torch.empty(x.shape[:-1] + (N,), dtype=torch.bfloat16, device=x.device)
+            _gemm2(x2, 0, w, 0, x2.shape[0], N, K, bias, y.view(-1, N))
+            return y
+    return F.linear(x, w, bias)
+
+
+def _mm_nn(dy2: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """``dy2 @ w``: the input gradient of a Linear, w (N, K) read as stored (an MN-major B operand, no transpose copy)."""
+    N, K = w.shape
+    if _GEMM2["on"] and dy2.is_cuda and K % 256 == 0 and N % 64 == 0 and _gemm2_operand(dy2) and _gemm2_operand(w):
+        dx = torch.empty((dy2.shape[0], K), dtype=torch.bfloat16, device=dy2.device)
+        return _gemm2(dy2, 0, w, 1, dy2.shape[0], K, N, None, dx)
+    return dy2 @ w
+
+
 def _wgrad(dy2: torch.Tensor, x2: torch.Tensor, master_dtype: torch.dtype) -> torch.Tensor:
     """dW = dy2^T x2 in the MASTER parameter's dtype: an fp32 master over 16-bit operands gets the GEMM's fp32
-    accumulator written out as is (no bf16 rounding of the gradient, no cast kernel afterwards)."""
+    accumulator written out as is (no bf16 rounding of the gradient, no cast kernel afterwards).  Both operands are read
+    as stored (MN-major); the reduction over all rows is split into pieces added in a fixed order (deterministic)."""
     if master_dtype == torch.float32 and dy2.dtype != torch.float32:
+        N, K = dy2.shape[1], x2.shape[1]
+        if _GEMM2["on"] and dy2.is_cuda and K % 256 == 0 and N % 64 == 0 and _gemm2_operand(dy2) and _gemm2_operand(x2):
+            dw = torch.empty((N, K), dtype=torch.float32, device=dy2.device)
+            return _gemm2(dy2, 1, x2, 1, N, K, dy2.shape[0], None, dw)
         return torch.mm(dy2.t(), x2, out_dtype=torch.float32)
     return (dy2.t() @ x2).to(master_dtype)
 
@@ -257,7 +309,7 @@ class _Linear(torch.autograd.Function):
         ctx.has_bias = bias is not None
         ctx.bias_dtype = bias.dtype if bias is not None else None
         ctx.w_dtype = weight.dtype
-        return F.linear(x, w, _shadow(bias, x.dtype))
+        return _mm_nt(x, w, _shadow(bias, x.dtype))
 
     @staticmethod
     def backward(ctx, dy):
@@ -265,7 +317,7 @@ class _Linear(torch.autograd.Function):
         dy2 = dy.reshape(-1, dy.shape[-1])
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
-        dx = (dy2 @ weight).view(x.shape) if ctx.needs_input_grad[0] else None
+        dx = _mm_nn(dy2, weight).view(x.shape) if ctx.needs_input_grad[0] else None
         dw = _wgrad(dy2, x.reshape(-1, x.shape[-1]), ctx.w_dtype) if ctx.needs_input_grad[1] else None
         db = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -485,7 +537,7 @@ def gelu_dropout(u: torch.Tensor, p: float, training: bool) -> torch.Tensor:
 # Linear + edge, as one autograd node each: the edge's backward kernel also yields the Linear's bias gradient
 # ------------------------------------------------------------------------------------------------
 def _linear_grads(ctx_needs, x, weight, dy2, w_dtype):
-    dx = (dy2 @ weight).view(x.shape) if ctx_needs[0] else None
+    dx = _mm_nn(dy2, weight).view(x.shape) if ctx_needs[0] else None
     dw = _wgrad(dy2, x.reshape(-1, x.shape[-1]), w_dtype) if ctx_needs[1] else None
     return dx, dw
 
@@ -512,7 +564,7 @@ class _LinearDropoutAdd(torch.autograd.Function):
                   float(p), int(seed), 0, _rng_offset_ptr(), GVIT_BF16, _dtype_code(resid), _ptr(out), _ptr(mask), _stream())
             y_dtype = x.dtype
         else:
-            y = F.linear(x, weight, _shadow(bias, x.dtype))
+            y = _mm_nt(x, weight, _shadow(bias, x.dtype))
             n = y.numel()
             out = torch.empty_like(y if resid is None else resid)
             mask = torch.empty(n // 8, dtype=torch.uint8, device=y.device) if p > 0 else None
@@ -560,7 +612,7 @@ class _LinearGeluDropout(torch.autograd.Function):
             _call("gvit_linear_gelu_dropout_fwd", _ptr(x), _ptr(weight), _ptr(_shadow(bias, x.dtype)), M, N, K, float(p),
                   int(seed), 0, _rng_offset_ptr(), GVIT_BF16, _ptr(u), _ptr(out), _ptr(mask), _stream())
         else:
-            u = F.linear(x, weight, _shadow(bias, x.dtype))
+            u = _mm_nt(x, weight, _shadow(bias, x.dtype))
             n = u.numel()
             out = torch.empty_like(u)
             mask = torch.empty(n // 8, dtype=torch.uint8, device=u.device) if p > 0 else None
@@ -602,7 +654,7 @@ class _MlpFused(torch.autograd.Function):
         mask1 = torch.empty(M * Nh // 8, dtype=torch.uint8, device=x.device) if p > 0 else None
         _call("gvit_linear_gelu_dropout_fwd", _ptr(x), _ptr(w1s), _ptr(_shadow(b1, x.dtype)), M, Nh, K, float(p), int(seed1), 0,
               _rng_offset_ptr(), GVIT_BF16, _ptr(u), _ptr(h), _ptr(mask1), st)
-        y = F.linear(h, w2s, _shadow(b2, x.dtype))
+        y = _mm_nt(h, w2s, _shadow(b2, x.dtype))
         n = y.numel()
         out = torch.empty_like(y if resid is None else resid)
         mask2 = torch.empty(n // 8, dtype=torch.uint8, device=x.device) if p > 0 else None
@@ -640,7 +692,7 @@ class _MlpFused(torch.autograd.Function):
         _call("gvit_linear_gelu_dropout_bwd", _ptr(dy2), _ptr(w2s), _ptr(u), _ptr(mask1), M, Nh, D2, float(ctx.p), GVIT_BF16,
               _ptr(du), _ptr(db1), _ptr(part), st)
         du2 = du.view(M, Nh)
-        dx = (du2 @ w1s).view(x.shape) if ctx.needs_input_grad[0] else None
+        dx = _mm_nn(du2, w1s).view(x.shape) if ctx.needs_input_grad[0] else None
         dw1 = _wgrad(du2, x.reshape(M, K), w1_dt) if ctx.needs_input_grad[1] else None
         return (dx, dw1, (db1.to(b1_dt) if b1_dt is not None and ctx.needs_input_grad[2] else None), dw2,
                 (db2.to(b2_dt) if db2 is not None and ctx.needs_input_grad[4] else None),
@@ -714,7 +766,7 @@ class _PatchEmbedTokens(torch.autograd.Function):
         st = _stream()
         patches = torch.empty((B, N, K), dtype=dt, device=img.device)
         _call("gvit_patchify", _ptr(img), B, C, H, W, P, _dtype_code(img), _dtype_code(patches), _ptr(patches), st)
-        y = F.linear(patches.view(B * N, K), _shadow(conv_w, dt).view(D, K))
+        y = _mm_nt(patches.view(B * N, K), _shadow(conv_w, dt).view(D, K))
         prm = [cls, pos] + ([conv_b] if conv_b is not None else [])
         if all(t.dtype == torch.float32 for t in prm) or all(t.dtype == dt for t in prm):
             pd = prm[0].dtype
@@ -937,7 +989,7 @@ class _PatchGraph(torch.autograd.Function):
             dbias = cs.to(ctx.b_dtype) if want_db else None
             dh = None
             if ctx.needs_input_grad[0]:
-                dz = d2 @ weight                                   # (B*(1+Np), D)
+                dz = _mm_nn(d2, weight)                            # (B*(1+Np), D)
                 dvals = torch.empty((B, Np, k), dtype=torch.float32, device=h.device)
                 dh = torch.empty_like(h)
                 dh[:, 0].zero_()
@@ -1016,7 +1068,7 @@ class _DenseGraph(torch.autograd.Function):
                   GVIT_BF16, _dtype_code(resid), _ptr(out), None, st)
             out[:, 0] = resid[:, 0]                                   # the CLS row passes through untouched (G0): no bias either
         else:
-            out = F.linear(zf, weight, bias)
+            out = _mm_nt(zf, weight, bias)
             out[:, 0].zero_()
             if resid is not None:
                 out = resid + out
@@ -1047,7 +1099,7 @@ class _DenseGraph(torch.autograd.Function):
         dh = None
         if ctx.needs_input_grad[0]:
             tok = _ptr(h, off)
-            dz = d2 @ weight                                          # (B*(1+Np), D); its CLS rows are never read
+            dz = _mm_nn(d2, weight)                                       # (B*(1+Np), D); its CLS rows are never read
             dzt = _ptr(dz, off)
             dA = torch.empty((B, Np, ld), dtype=torch.float32, device=h.device)
             _bgemm(B, Np, Np, [(dzt, rs, bs, 0, tok, rs, bs, 0, D)], dA, ld, Np * ld)               # dA~ = dZ P^T

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GVIT_ABI_VERSION 16
+#define GVIT_ABI_VERSION 17
 #if defined(__GNUC__)
 #define GVIT_API __attribute__((visibility("default")))
 #else
@@ -232,6 +232,23 @@ GVIT_API int gvit_linear_dropout_residual_fwd(const void* x, const void* w, cons
 GVIT_API int64_t gvit_linear_gelu_dropout_bwd_ws_rows(int64_t M);
 GVIT_API int gvit_linear_gelu_dropout_bwd(const void* dout, const void* w2, const void* u, const uint8_t* keep_mask, int64_t M, int N, int K,
                                  float p, int dtype, void* du, float* colsum_out, float* partial_ws, void* stream);
+
+/* ---- a1 / f1: the Linear GEMMs themselves (vit.py:59 qkv, :93 fc2, :28 patch projection, and the autograd of every
+ * nn.Linear of the block): out (M,N) = op(a) op(b) [+ bias] as ONE persistent 2-SM tcgen05 kernel - 256 x 256 tiles per
+ * CTA pair (`tcgen05.mma.cta_group::2`), each CTA staging its 128 rows of a and its half of the tile's b columns.
+ *   forward          y  = x W^T + b :  a = x (M,K),   a_t 0;  b = W (N,K),  b_t 0;  out bf16
+ *   input gradient   dx = dy W      :  a = dy (M,K'), a_t 0;  b = W (K',N), b_t 1;  out bf16          (K' = out features)
+ *   weight gradient  dW = dy^T x    :  a = dy (K,M),  a_t 1;  b = x (K,N),  b_t 1;  out fp32          (K = all rows)
+ * *_t == 0: the operand is stored [rows][K] (K contiguous); 1: stored [K][rows] (rows contiguous); *_rs = its row stride
+ * in elements.  Operands bf16, bias (N) bf16 or NULL (bf16 output only), N % 256 == 0, 16-byte aligned rows.
+ * An fp32 product with fewer 256 x 256 tiles than CTA pairs (the weight gradient) is split along K when `workspace` holds
+ * gvit_linear_gemm_ws_bytes(M,N,K) bytes: the pieces of a tile leave fp32 partial tiles in the workspace and a second small
+ * kernel adds them in a FIXED order (deterministic).  workspace may be NULL (whole tiles per pair, fewer SMs busy); it
+ * must not be shared by launches that may run concurrently. */
+GVIT_API int64_t gvit_linear_gemm_ws_bytes(int64_t M, int N, int K);
+GVIT_API int gvit_linear_gemm(const void* a, int a_t, int64_t a_rs, const void* b, int b_t, int64_t b_rs, int64_t M, int N, int K,
+                     const void* bias, int out_dtype, void* out, int64_t out_rs, void* workspace, int64_t workspace_bytes,
+                     void* stream);
 
 /* ---- f4: token prologue, replaces PatchEmbed (/root/reference/src/models/vit.py:25-36) and the CLS / pos_embed /
  * pos_drop lines vit.py:207-212.  A kernel == stride convolution is a GEMM over non-overlapping patches:

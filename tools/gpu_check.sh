@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 summary=gpurun_out/check_summary.txt
 : > "$summary"
-for f in tests/test_gpu_edges.py tests/test_gpu_knn.py tests/test_gpu_graph.py tests/test_gpu_attention.py tests/test_gpu_model.py; do
+for f in tests/test_gpu_*.py; do
   name=$(basename "$f" .py)
   timeout 420 python -m pytest "$f" -q -m gpu -x --no-header -p no:cacheprovider > "gpurun_out/$name.log" 2>&1
   rc=$?
