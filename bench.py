@@ -263,6 +263,37 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
         "layernorm_bwd_add": (lambda i: _call("gvit_layernorm_bwd", _ptr(xs[i % R]), _ptr(hs[i % R]), _ptr(gam), _ptr(mean), _ptr(rstd), B * N, D, dt, dt, _ptr(hs[(i + 1) % R]), _ptr(out), _ptr(dgb[0]), _ptr(dgb[1]), _ptr(ws), st),
                               4 * B * N * D * e, 0.0, "hbm", 36),
     }
+    # ---- gemm2_tc_kernel (gvit_linear_gemm): the eleven library-free Linear GEMMs of one block, launched back to back the way a
+    # training step issues them: qkv fwd / dgrad / wgrad, proj dgrad / wgrad, fc1 dgrad / wgrad, fc2 fwd / wgrad, graph
+    # projection dgrad / wgrad (the other four products run inside the fused-epilogue kernels above).  "per launch" = the mean
+    # over these eleven launches, algorithmic FLOPs = 2 M N K of each.
+    M = B * N
+    Wqkv = torch.randn(3 * D, D, device=dev, dtype=bf, generator=g) * 0.03
+    bqkv = torch.zeros(3 * D, device=dev, dtype=bf)
+    y3 = torch.empty(M, 3 * D, device=dev, dtype=bf)
+    dW3, dW1, dW4, dW4t = (torch.empty(a, b_, device=dev) for a, b_ in ((3 * D, D), (D, D), (4 * D, D), (D, 4 * D)))
+    gws = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+
+    def gemm(a, a_t, b_, b_t, m_, n_, k_, bias_, o):
+        _call("gvit_linear_gemm", _ptr(a), a_t, a.stride(0), _ptr(b_), b_t, b_.stride(0), m_, n_, k_, _ptr(bias_),
+              0 if o.dtype == torch.float32 else 1, _ptr(o), o.stride(0), _ptr(gws), gws.numel(), st)
+
+    def block_gemms(i):
+        x2, d2, q2, u2, o2 = hs[i % R].view(M, D), xs[i % R].view(M, D), qkvs[i % 2].view(M, 3 * D), u4[i % 2].view(M, 4 * D), out.view(M, D)
+        gemm(x2, 0, Wqkv, 0, M, 3 * D, D, bqkv, y3)            # qkv forward
+        gemm(q2, 0, Wqkv, 1, M, D, 3 * D, None, o2)            # qkv input gradient
+        gemm(q2, 1, x2, 1, 3 * D, D, M, None, dW3)             # qkv weight gradient
+        gemm(d2, 0, W, 1, M, D, D, None, o2)                   # proj input gradient
+        gemm(d2, 1, x2, 1, D, D, M, None, dW1)                 # proj weight gradient
+        gemm(u2, 0, W1, 1, M, D, 4 * D, None, o2)              # fc1 input gradient
+        gemm(u2, 1, x2, 1, 4 * D, D, M, None, dW4)             # fc1 weight gradient
+        gemm(u2, 0, W2, 0, M, D, 4 * D, bias, o2)              # fc2 forward
+        gemm(d2, 1, u2, 1, D, 4 * D, M, None, dW4t)            # fc2 weight gradient
+        gemm(d2, 0, W, 1, M, D, D, None, o2)                   # graph projection input gradient
+        gemm(d2, 1, x2, 1, D, D, M, None, dW1)                 # graph projection weight gradient
+    n_gemm = 11
+    gemm_flops = 2.0 * M * D * D * (3 * 3 + 2 + 2 * 4 + 2 * 4 + 2)
+    cases["linear_gemm"] = (block_gemms, (M * D * e * 30 + M * 3 * D * e * 3), gemm_flops, "tensor", 12)
     _call("gvit_layernorm_fwd", _ptr(hs[0]), _ptr(gam), _ptr(bet), B * N, D, 1e-5, dt, dt, _ptr(out), _ptr(mean), _ptr(rstd), st)
     res = {}
     for name, (fn, nbytes, flops, bound, per_step) in cases.items():
@@ -283,6 +314,9 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
             ach, peak, unit = tfs, peaks["tf_burst"], "TFLOP/s"
         res[name] = dict(ms=ms, bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak, gbs=gbs, tflops=tfs,
                          algorithmic_bytes=nbytes, flops=flops, launches_per_step=per_step, ms_per_step=ms * per_step)
+        if name == "linear_gemm":                              # per LAUNCH of gemm2_tc_kernel: the mean over the block's eleven
+            res[name].update(ms=ms / n_gemm, flops=flops / n_gemm, algorithmic_bytes=nbytes // n_gemm, launches_per_step=per_step * n_gemm,
+                             launches_timed=n_gemm, note="mean over the 11 Linear GEMMs of one block (incl. the split-K reduce of the weight gradients)")
     return res
 
 

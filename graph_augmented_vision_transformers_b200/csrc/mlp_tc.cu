@@ -19,19 +19,20 @@
 // double-buffered in TMEM, so the MMAs of tile i+1 overlap bias + GELU + dropout + the two stores of tile i, and the
 // pre-activation never makes the extra HBM round trip.
 //
-// Tiles: BM x BN x BK = 128 x 256 x 64, both operands K-major ([rows][64 bf16] 128B-swizzled TMA boxes), 4-stage ring
-// (48 KB per stage).  One tcgen05.mma is 128 x 256 x 16: 12 KB of shared-memory operands per 128 tensor cycles.
+// Tiles: 256 x 256 per CTA PAIR, K in 64-deep slabs: `tcgen05.mma.cta_group::2` (M = 256, N = 256, K = 16) issued by the
+// leader CTA of a 2-CTA cluster.  Each CTA stages its own 128 rows of x and its own 128 of the tile's 256 W rows (16 + 16 KB
+// per stage, six stages); completion bytes of both CTAs land on the leader's full barrier, ring slots and accumulators are
+// released to both CTAs by multicast tcgen05.commit - the same main loop as gemm2_tc.cu.  Each CTA's 128 x 256 fp32 half of
+// the accumulator is double-buffered in its own TMEM (2 x 256 columns).
+// History: un-paired 128 x 256 tiles ran the main loop at 1.07 PF/s (48 KB of operands per stage per CTA through L2 ->
+// shared memory); W multicast across a 2-CTA cluster cut the L2 side to 32 KB but not the shared-memory fill (0.29 ms for
+// fc1 at B = 256); pairing the MMA itself halves both.
 // Tile order: consecutive tile ids share the x row block (the 12 column tiles of one row block run on neighbouring
-// CTAs at the same time, so x is read from HBM once and from L2 eleven times); W (4.7 MB) stays L2-resident.
-// Measured on B200: the main loop alone runs at 1.07 PF/s - the L2 -> SM operand traffic of un-clustered 128 x 256
-// tiles (96 B/clk/SM at full tensor rate, ~43 B/clk/SM available chip-wide) is its bound - and the epilogue is ~30
-// instructions per element, so SIXTEEN epilogue warps (4 per scheduler) are needed to keep it off the critical path:
-// with eight, the kernel ran at the speed of GEMM + separate elementwise pass.
-// Clusters of CL = 2 CTAs work on consecutive row blocks of the same column tile: each CTA fetches 1/CL of the W tile
-// and TMA-multicasts it to the whole cluster, so the L2 -> SM traffic drops from 48 to 32 KB per stage (a ring slot is
-// refilled once EVERY CTA has released it: the MMA warps commit to the empty barrier of all CTAs of the cluster).
+// pairs at the same time, so x is read from HBM once and from L2 eleven times); W (4.7 MB) stays L2-resident.
+// The epilogue is ~30 instructions per element, so SIXTEEN epilogue warps (4 per scheduler) are needed to keep it off
+// the critical path: with eight, the kernel ran at the speed of GEMM + separate elementwise pass.
 // Warp roles: 0-15 epilogue (warpgroup g = warp / 4 owns accumulator columns [64g, 64g + 64), thread <-> row = TMEM lane),
-// 16 TMA producer, 17 MMA issuer.
+// 16 TMA producer, 17 MMA issuer (leader CTA only).
 #include "gelu.cuh"
 #include "kernels.cuh"
 #include "philox.cuh"
@@ -43,11 +44,9 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int STAGES = 4;
-constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
-// CTAs per cluster: CL row blocks share one W tile (each fetches 1/CL of it).  Measured: 2 -> 275 us; 4 -> 490 us, because
-// only ~34 four-CTA clusters are co-resident on the 148 SMs (GPC granularity), so a 37-cluster persistent grid ran in two
-// waves.  The grid is sized from cudaOccupancyMaxActiveClusters for that reason.
+constexpr int STAGES = 6;
+constexpr int A_BYTES = BM * 128, B_BYTES = (BN / 2) * 128, STAGE_BYTES = A_BYTES + B_BYTES;   // per CTA: own rows, own half of W
+// CTAs per cluster = the MMA pair.  The grid is sized from cudaOccupancyMaxActiveClusters (whole co-resident pairs).
 constexpr int CL = 2;
 constexpr int EPI_WARPS = 16;
 constexpr int WSTAGE = 2 * 1024;            // per-warp staging ([32 rows][64 B]) for coalesced global stores
@@ -104,11 +103,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
   if (warp == EPI_WARPS && lane == 0) {
     prefetch_tmap(&tm_x);
     prefetch_tmap(&tm_w);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], CL); }   // empty: every CTA's MMA warp
-    for (int s = 0; s < 2; ++s) { mbar_init(&ctl->acc_full[s], 1); mbar_init(&ctl->acc_free[s], EPI_WARPS * 32); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&ctl->acc_full[s], 1); mbar_init(&ctl->acc_free[s], CL * EPI_WARPS); }   // leader's: one arrival per epilogue warp of the pair
     fence_mbar_init();
   }
-  if (warp == EPI_WARPS + 1) tmem_alloc(&ctl->tmem_base, 512);
+  if (warp == EPI_WARPS + 1) tmem_alloc_2sm(&ctl->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                                      // the peer's barriers exist before anything is multicast to it
@@ -123,32 +122,29 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
         const int mp = pr / nN, n = pr - mp * nN, m = CL * mp + rank;
         for (int kb = 0; kb < nK; ++kb, ++it) {
           const int s = it % STAGES;
-          mbar_wait(&ctl->empty[s], ((it / STAGES) & 1) ^ 1);            // released by EVERY CTA of the cluster
-          mbar_expect_tx(&ctl->full[s], (uint32_t)STAGE_BYTES);          // own x tile + own W slice + the peers' W slices
-          tma_load_3d(ring + (size_t)s * STAGE_BYTES, &tm_x, kb * BK, m * BM, 0, &ctl->full[s]);             // rows >= M: zeros
-          if constexpr (MODE != 2) {                                     // W (N, K): K-major, one box of BN / CL rows
-            tma_load_3d_mc(ring + (size_t)s * STAGE_BYTES + A_BYTES + rank * (B_BYTES / CL), &tm_w, kb * BK, n * BN + rank * (BN / CL), 0,
-                           &ctl->full[s], (uint16_t)((1u << CL) - 1));
+          mbar_wait(&ctl->empty[s], ((it / STAGES) & 1) ^ 1);            // released by the leader's multicast commit
+          const uint32_t fullL = mapa_u32(smem_u32(&ctl->full[s]), 0);
+          if (rank == 0) mbar_expect_tx(&ctl->full[s], (uint32_t)(CL * STAGE_BYTES));   // both CTAs' tiles
+          tma_load_3d_2sm(ring + (size_t)s * STAGE_BYTES, &tm_x, kb * BK, m * BM, 0, fullL);                 // rows >= M: zeros
+          if constexpr (MODE != 2) {                                     // W (N, K): K-major, this CTA's BN / 2 rows of the tile
+            tma_load_3d_2sm(ring + (size_t)s * STAGE_BYTES + A_BYTES, &tm_w, kb * BK, n * BN + rank * (BN / CL), 0, fullL);
           } else {                                                       // W2 (K, N): MN-major, [64 k][64 n] atoms of 8 KB
 #pragma unroll
-            for (int j = 0; j < 4 / CL; ++j) {
-              const int atom = rank * (4 / CL) + j;
-              tma_load_3d_mc(ring + (size_t)s * STAGE_BYTES + A_BYTES + atom * 8192, &tm_w, n * BN + atom * 64, kb * BK, 0, &ctl->full[s],
-                             (uint16_t)((1u << CL) - 1));
-            }
+            for (int j = 0; j < 2; ++j)
+              tma_load_3d_2sm(ring + (size_t)s * STAGE_BYTES + A_BYTES + j * 8192, &tm_w, n * BN + rank * (BN / CL) + j * 64, kb * BK, 0, fullL);
           }
         }
       }
     }
   } else if (warp == EPI_WARPS + 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc(BM, BN, false, MODE == 2);
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc = make_idesc(CL * BM, BN, false, MODE == 2);
       const uint32_t aR = smem_u32(ring);
       int it = 0, tc = 0;
       for (int pr = cid; pr < npairs; pr += ncl, ++tc) {
         const int buf = tc & 1;
-        if (tc >= 2) {                              // the epilogue has drained this accumulator buffer (use tc/2 - 1)
+        if (tc >= 2) {                              // both CTAs' epilogues have drained this accumulator buffer (use tc/2 - 1)
           mbar_wait(&ctl->acc_free[buf], ((tc >> 1) - 1) & 1);
           tc_fence_after();
         }
@@ -159,11 +155,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
           const uint32_t aA = aR + s * STAGE_BYTES, aB = aA + A_BYTES;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_ss(tmem + buf * BN, make_sdesc(aA + kk * 32),
-                    MODE == 2 ? make_sdesc_lbo(aB + kk * 2048, 8192) : make_sdesc(aB + kk * 32), idesc, kb > 0 || kk > 0);
-          umma_commit_mc(&ctl->empty[s], (uint16_t)((1u << CL) - 1));  // slot s of EVERY CTA is written by the next refill
+            umma_ss_2sm(tmem + buf * BN, make_sdesc(aA + kk * 32),
+                        MODE == 2 ? make_sdesc_lbo(aB + kk * 2048, 8192) : make_sdesc(aB + kk * 32), idesc, kb > 0 || kk > 0);
+          umma_commit_2sm_mc(&ctl->empty[s], (uint16_t)((1u << CL) - 1));  // slot s of BOTH CTAs may be refilled
         }
-        umma_commit(&ctl->acc_full[buf]);
+        umma_commit_2sm_mc(&ctl->acc_full[buf], (uint16_t)((1u << CL) - 1));
       }
     }
   } else {
@@ -229,9 +225,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
         }
         float v[32];
         tmem_ld32(tl + buf * BN + h * 32, v);
-        if (h == 1) {                                                  // this thread's accumulator row has been read
+        if (h == 1) {                                                  // this warp's accumulator rows have been read
           tc_fence_before();
-          mbar_arrive(&ctl->acc_free[buf]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&ctl->acc_free[buf]), 0));
         }
         __syncwarp();
         if constexpr (MODE == 2) {
@@ -414,7 +411,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                                      // no CTA leaves while its peer may still multicast into it
-  if (warp == EPI_WARPS + 1) tmem_dealloc(tmem, 512);
+  if (warp == EPI_WARPS + 1) tmem_dealloc_2sm(tmem, 512);
 }
 
 // out[c] = sum over the partial rows, fixed order (32 columns x 8 row lanes per CTA, then lanes 0..7): deterministic
@@ -447,7 +444,7 @@ static int fused_linear_launch(const void* x, const void* w, const void* bias, i
   int rc = make_tmap_bf16_3d(&tm_x, x, (uint64_t)K, (uint64_t)M, 1, (uint64_t)K, (uint64_t)M * K, BM);
   if (rc != GVIT_OK) return rc;
   if (MODE != 2)
-    rc = make_tmap_bf16_3d(&tm_w, w, (uint64_t)K, (uint64_t)N, 1, (uint64_t)K, (uint64_t)N * K, BN / CL);   // one CTA's slice of the tile
+    rc = make_tmap_bf16_3d(&tm_w, w, (uint64_t)K, (uint64_t)N, 1, (uint64_t)K, (uint64_t)N * K, BN / CL);   // one CTA's half of the tile
   else
     rc = make_tmap_bf16_3d(&tm_w, w, (uint64_t)N, (uint64_t)K, 1, (uint64_t)N, (uint64_t)N * K, 64);        // W2 (K, N): [64 k][64 n] atoms
   if (rc != GVIT_OK) return rc;
