@@ -1,0 +1,492 @@
+// agg4_tc.cu - fused aggregation G4+G5+G6 + residual for bf16, D <= 768, as a 2-SM kernel: ONE CTA PAIR PER IMAGE
+// (north_star: "gather / normalise, then a tcgen05 GEMM with TMA-staged tiles that keeps A.X in shared
+// memory or TMEM with no HBM round-trip").
+//
+//   out[b,1+i,:] = resid[b,1+i,:] + ( sum_j softmax_k(vals)_ij * p[b, idx_ij, :] ) Wg^T + bias
+//
+// agg3_tc.cu gave each 128-row tile of an image its own CTA, so both CTAs of an image streamed ALL token slabs (301 KB) and
+// ALL of Wg (1.18 MB) through L2 -> shared memory: 1.48 MB per 128 rows, and the measured W stream arrived at ~25-30
+// B/clk/SM with the tensor pipe 48 % busy.  Here the two row tiles of an image are the two halves of `cta_group::2` MMAs
+// (M = 256): every B operand - token slab or W piece - is split between the pair, each CTA stages HALF of it, so the
+// operand bytes per CTA and per image halve (0.74 MB).  The pair is persistent (images b = pair, pair + pairs, ...), the
+// producer runs ahead into the next image while the epilogue of the current one drains.
+//
+// Per image (rank r = 0 / 1 owns token rows [128 r, 128 r + 128) = its TMEM lanes, its A~ tile, its output rows):
+//   A~ tile    : 128 x NT dense bf16 adjacency rows in shared memory (zeroed, then each row's k softmax weights scattered).
+//   Z phase    : Z = A~ . P, 128 features per step: MMA M = 256, N = 128, K = tokens; rank r stages the 64-feature token
+//                slab 2 t + r (MN-major B).  fp32 result in a TMEM staging area, converted IN TENSOR MEMORY to packed bf16:
+//                the whole aggregated tile Z [128 x D] of a CTA ends up in TMEM columns [0, D/2) (training streams a copy
+//                out for the weight gradient).
+//   projection : per 64-feature output chunk OUT = Z . W_chunk^T, A from TMEM (TS form), rank r stages W rows
+//                [64 n + 32 r, + 32) in pieces of up to 512 reduction columns; fp32 chunk double-buffered in TMEM so that
+//                bias + residual + store of chunk n overlap the MMAs of chunk n + 1.
+// TMEM (512 columns per CTA): Z bf16 [0, D/2) | Z fp32 staging: step t even -> [64 t, 64 t + 128) (in place), odd ->
+//                [384, 512) | OUT chunk buffers [384, 448), [448, 512).
+// Shared memory per CTA: A~ (4 x 16 KB) | ring of 4 x 32 KB slots | 8 x 4 KB per-warp staging.
+// Warp roles: 0-3 row warpgroup 0, 4-7 row warpgroup 1 (thread <-> token row = TMEM lane; warpgroup g owns the Z steps and
+// output chunks of parity g), 8 TMA producer (both CTAs), 9 MMA issuer (leader) and TMEM owner.
+// Barriers.  In the leader, arrived at by both CTAs: full[slot] (TMA bytes), a_ready, conv_done[parity], out_free[buf].
+// In each CTA, released by multicast tcgen05.commit: empty[slot], a_free, zs_full[parity], out_full[buf]; local:
+// conv_loc[parity] (the two warpgroups of a CTA hand the in-place staging columns to each other).  Every waiter counts the
+// completions it has consumed and waits for them one by one, so no barrier can run two phases ahead of a waiter.
+#include <float.h>
+
+#include "kernels.cuh"
+#include "tc.cuh"
+
+namespace gvit {
+namespace {
+
+using namespace tc;
+
+constexpr int THREADS = 320;
+constexpr int TILE = 128 * 128;             // [128 rows][64 bf16]
+constexpr int A_BYTES = 4 * TILE;           // A~ [128][256] as four 64-column blocks
+constexpr int SLOT = 32 * 1024;             // ring slot: one token slab [<=256][64] or one W piece (<= 8 boxes of [32][64])
+constexpr int NSLOT = 4;
+constexpr int WSTAGE = 4 * 1024;            // per-warp staging ([32 rows][128 B]) for coalesced global access
+constexpr int T_OUT = 384;                  // first OUT chunk buffer / odd Z staging
+
+struct __align__(8) Ctrl {
+  uint64_t full[NSLOT], empty[NSLOT], a_ready, a_free, zs_full[2], conv_done[2], conv_loc[2], out_full[2], out_free[2];
+  uint32_t tmem_base;
+  __align__(16) __nv_bfloat16 bias[768];
+};
+constexpr size_t SMEM_BYTES = A_BYTES + NSLOT * SLOT + 8 * WSTAGE + sizeof(Ctrl);
+
+struct Params {
+  int B, Np, D, k, NT;
+  const int32_t* idx;
+  const float* vals;
+  const __nv_bfloat16* bias;
+  const void* resid;                        // bf16, or fp32 when the kernel is instantiated with RES32 (fp32 residual stream)
+  void* out;                                // same type as resid
+  float* w_save;
+  __nv_bfloat16* z_save;
+  int64_t zbs;                              // batch stride of z_save in elements (rows are D apart)
+};
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+// consume completions of `bar` until `seen` reaches `need` (one parity wait per completion: never skips a phase)
+__device__ __forceinline__ void wait_upto(uint64_t* bar, uint32_t& seen, uint32_t need) {
+  while (seen < need) { mbar_wait(bar, seen & 1); ++seen; }
+}
+
+template <int KT, bool RES32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_kernel(const __grid_constant__ CUtensorMap tm_tok,
+                                                                                       const __grid_constant__ CUtensorMap tm_w, const Params P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sA = smem_raw;
+  if ((smem_u32(sA) & 1023u) != 0) __trap();
+  uint8_t* sRing = sA + A_BYTES;
+  uint8_t* sStg = sRing + NSLOT * SLOT;
+  Ctrl* ctl = reinterpret_cast<Ctrl*>(sStg + 8 * WSTAGE);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const int D = P.D, NT = P.NT;
+  const int nchunk = D / 64;                // 64-feature output chunks
+  const int nstep = D / 128;                // Z steps of 128 features (64 per CTA)
+  const int npiece = (D + 511) / 512;       // W pieces of (up to) 512 reduction columns per output chunk
+
+  if (warp == 8 && lane == 0) {
+    prefetch_tmap(&tm_tok);
+    prefetch_tmap(&tm_w);
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&ctl->zs_full[s], 1);
+      mbar_init(&ctl->conv_done[s], 8);     // 4 warps of the owning warpgroup in each CTA
+      mbar_init(&ctl->conv_loc[s], 4);
+      mbar_init(&ctl->out_full[s], 1);
+      mbar_init(&ctl->out_free[s], 8);
+    }
+    mbar_init(&ctl->a_ready, 8);            // warpgroup 0 of each CTA
+    mbar_init(&ctl->a_free, 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc_2sm(&ctl->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (elect_one()) {
+      uint32_t c = 0;                                                  // ring fill counter
+      for (int b = cid; b < P.B; b += ncl) {
+        for (int t = 0; t < nstep; ++t, ++c) {                         // this CTA's 64-feature token slab of step t
+          const uint32_t sl = c % NSLOT;
+          mbar_wait(&ctl->empty[sl], ((c / NSLOT) & 1) ^ 1);
+          if (rank == 0) mbar_expect_tx(&ctl->full[sl], (uint32_t)(2 * NT * 128));
+          tma_load_3d_2sm(sRing + sl * SLOT, &tm_tok, (2 * t + rank) * 64, 0, b, mapa_u32(smem_u32(&ctl->full[sl]), 0));
+        }
+        for (int n = 0; n < nchunk; ++n) {                             // W rows [64 n + 32 rank, + 32), pieces of <= 512 columns
+          for (int p = 0; p < npiece; ++p, ++c) {
+            const uint32_t sl = c % NSLOT;
+            const int nbox = min(8, (D - p * 512) / 64);
+            mbar_wait(&ctl->empty[sl], ((c / NSLOT) & 1) ^ 1);
+            if (rank == 0) mbar_expect_tx(&ctl->full[sl], (uint32_t)(2 * nbox * 4096));
+            const uint32_t fullL = mapa_u32(smem_u32(&ctl->full[sl]), 0);
+            for (int j = 0; j < nbox; ++j)
+              tma_load_3d_2sm(sRing + sl * SLOT + j * 4096, &tm_w, p * 512 + j * 64, n * 64 + rank * 32, 0, fullL);
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0 && elect_one()) {
+      const uint32_t aA = smem_u32(sA), aR = smem_u32(sRing);
+      const uint32_t idesc_z = make_idesc(256, 128, false, true);      // A~ K-major, token slabs MN-major
+      const uint32_t idesc_w = make_idesc(256, 64, false, false);      // Z from TMEM, W piece K-major
+      uint32_t c = 0;                                                  // ring consume counter
+      uint32_t a_seen = 0, conv_seen[2] = {0, 0}, conv_iss[2] = {0, 0}, free_seen[2] = {0, 0}, out_iss[2] = {0, 0};
+      for (int b = cid; b < P.B; b += ncl) {
+        wait_upto(&ctl->a_ready, a_seen, a_seen + 1);                  // both CTAs' adjacency tiles are built
+        tc_fence_after();
+        for (int t = 0; t < nstep; ++t) {                              // ---- Z phase
+          const int par = t & 1;
+          const uint32_t stg = par ? T_OUT : 64 * t;
+          wait_upto(&ctl->conv_done[par], conv_seen[par], conv_iss[par]);            // earlier steps of this parity converted
+          if (par) {                                                   // odd staging = the OUT buffers of the previous image
+            wait_upto(&ctl->out_free[0], free_seen[0], out_iss[0]);
+            wait_upto(&ctl->out_free[1], free_seen[1], out_iss[1]);
+          }
+          const uint32_t sl = c % NSLOT;
+          mbar_wait(&ctl->full[sl], (c / NSLOT) & 1);
+          tc_fence_after();
+          const uint32_t aTok = aR + sl * SLOT;
+          for (int ks = 0; ks < NT / 16; ++ks)
+            umma_ss_2sm(tmem + stg, make_sdesc(aA + (ks >> 2) * TILE + (ks & 3) * 32), make_sdesc(aTok + ks * 2048), idesc_z, ks > 0);
+          umma_commit_2sm_mc(&ctl->zs_full[par], 3);
+          umma_commit_2sm_mc(&ctl->empty[sl], 3);
+          ++conv_iss[par];
+          ++c;
+        }
+        umma_commit_2sm_mc(&ctl->a_free, 3);                           // the A~ tiles may be rebuilt for the next image
+        wait_upto(&ctl->conv_done[0], conv_seen[0], conv_iss[0]);      // every Z step is packed bf16 in TMEM
+        wait_upto(&ctl->conv_done[1], conv_seen[1], conv_iss[1]);
+        tc_fence_after();
+        for (int n = 0; n < nchunk; ++n) {                             // ---- projection
+          const int buf = n & 1;
+          wait_upto(&ctl->out_free[buf], free_seen[buf], out_iss[buf]);
+          tc_fence_after();
+          for (int p = 0; p < npiece; ++p, ++c) {
+            const uint32_t sl = c % NSLOT;
+            const int nbox = min(8, (D - p * 512) / 64);
+            mbar_wait(&ctl->full[sl], (c / NSLOT) & 1);
+            tc_fence_after();
+            const uint32_t aW = aR + sl * SLOT;
+            for (int j = 0; j < nbox; ++j)
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_ts_2sm(tmem + T_OUT + buf * 64, tmem + (p * 512 + j * 64 + kk * 16) / 2, make_sdesc(aW + j * 4096 + kk * 32),
+                            idesc_w, p > 0 || j > 0 || kk > 0);
+            umma_commit_2sm_mc(&ctl->empty[sl], 3);
+          }
+          umma_commit_2sm_mc(&ctl->out_full[buf], 3);
+          ++out_iss[buf];
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ row warpgroups (both CTAs)
+    const int g = warp >> 2;                                           // warpgroup: parity of the steps / chunks it owns
+    const int row = threadIdx.x & 127;                                 // == TMEM lane
+    const int rowg = rank * 128 + row;                                 // token row inside the image
+    const bool valid = rowg < P.Np;
+    uint8_t* stg = sStg + warp * WSTAGE;                               // this warp's private staging (4 KB)
+    const int wrow0 = rank * 128 + (warp & 3) * 32;                    // first token row of this warp
+    const uint32_t tl = tmem_lane_base(tmem, warp);
+    const int ch8 = lane & 7, r8 = lane >> 3;                          // coalesced pattern: 8 lanes per 128-byte row segment
+    const uint32_t a_readyL = mapa_u32(smem_u32(&ctl->a_ready), 0);
+    const uint32_t conv_doneL = mapa_u32(smem_u32(&ctl->conv_done[g]), 0);      // this warpgroup's parity, in the leader
+    const uint32_t out_freeL = mapa_u32(smem_u32(&ctl->out_free[g]), 0);
+    uint32_t afree_seen = 0, zs_seen = 0, loc_seen = 0, loc_done_other = 0, full_seen = 0;
+    // zs_seen / full_seen: completions of zs_full[g] / out_full[g] consumed; loc_seen: completions of the OTHER warpgroup's
+    // conv_loc consumed; loc_done_other: how many steps the other warpgroup has had to convert before my next step
+    {
+      const uint4 z4 = make_uint4(0, 0, 0, 0);
+      for (int i = threadIdx.x; i < 768 / 8; i += 256)
+        reinterpret_cast<uint4*>(ctl->bias)[i] = (P.bias && i < D / 8) ? reinterpret_cast<const uint4*>(P.bias)[i] : z4;
+    }
+    constexpr int NH = RES32 ? 2 : 1;
+    for (int b = cid, iter = 0; b < P.B; b += ncl, ++iter) {
+      // residual rows of this warp for output chunk n, coalesced (lane -> rows r8 + 4i, 16-byte chunk ch8)
+      // RES32: a 64-feature chunk is 256 bytes per row = two 128-byte halves (32 features each)
+      auto load_resid = [&](int n, uint4 (&rr)[8 * NH]) {
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = r8 + 4 * i;
+            rr[hh * 8 + i] = make_uint4(0, 0, 0, 0);
+            if (P.resid && n < nchunk && wrow0 + r < P.Np) {
+              const int64_t e = ((int64_t)b * (P.Np + 1) + 1 + wrow0 + r) * D + n * 64;
+              if constexpr (RES32) rr[hh * 8 + i] = *reinterpret_cast<const uint4*>(static_cast<const float*>(P.resid) + e + hh * 32 + ch8 * 4);
+              else rr[i] = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(P.resid) + e + ch8 * 8);
+            }
+          }
+      };
+      // ---- G4 + adjacency tile: zero A~, then scatter each row's k softmax weights (bf16) at its neighbour columns
+      if (iter > 0) wait_upto(&ctl->a_free, afree_seen, (uint32_t)iter);           // the previous image's Z MMAs have read A~
+      {
+        const uint4 z4 = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < A_BYTES / 16; i += 256) reinterpret_cast<uint4*>(sA)[i] = z4;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (g == 0) {
+          if (valid) {
+            float w[KT];
+            int nb[KT];
+            float mx = -FLT_MAX, sum = 0.f;
+            const int64_t o = ((int64_t)b * P.Np + rowg) * P.k;
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+              const bool on = j < P.k;
+              nb[j] = on ? P.idx[o + j] : 0;
+              w[j] = on ? P.vals[o + j] : -FLT_MAX;
+              mx = fmaxf(mx, w[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < KT; ++j) { w[j] = j < P.k ? expf(w[j] - mx) : 0.f; sum += w[j]; }
+            const float inv = 1.0f / sum;
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+              if (j < P.k) {
+                const float wj = w[j] * inv;
+                if (P.w_save) P.w_save[o + j] = wj;
+                const int cidx = nb[j];
+                *reinterpret_cast<__nv_bfloat16*>(sA + (cidx >> 6) * TILE + swz128(row, cidx & 63) + (cidx & 7) * 2) = __float2bfloat16_rn(wj);
+              }
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(a_readyL);
+        } else if (rank == 0) {
+          // CLS row: out[b,0,:] = resid[b,0,:] (the graph leaves CLS untouched, section 9 G0), 16 bytes per thread and trip
+          constexpr int EPV = RES32 ? 4 : 8;                             // elements per 16-byte vector
+          constexpr int ESZ = RES32 ? 4 : 2;
+          for (int c = row; c < D / EPV; c += 128) {
+            const int64_t o = ((int64_t)b * (P.Np + 1) * D + c * EPV) * ESZ;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (P.resid) v = *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(P.resid) + o);
+            *reinterpret_cast<uint4*>(static_cast<uint8_t*>(P.out) + o) = v;
+          }
+        }
+      }
+      uint4 rnext[8 * NH];
+      load_resid(g, rnext);                                              // first chunk of this warpgroup: in flight during Z
+      // ---- Z phase (steps of parity g): fp32 staging -> packed bf16 at TMEM columns [64t, 64t + 64);
+      //      optional copy out for the backward, 64 features at a time through the warp staging
+      for (int t = 0; t < nstep; ++t) {
+        if ((t & 1) != g) { ++loc_done_other; continue; }                // the other warpgroup's step
+        const uint32_t src = tl + ((t & 1) ? T_OUT : 64 * t), dst = tl + 64 * t;
+        mbar_wait(&ctl->zs_full[g], zs_seen & 1);
+        ++zs_seen;
+        // the two warpgroups convert strictly in step order: an odd step's bf16 destination is the upper half of the
+        // previous (even) step's in-place staging, and taking every completion of the other's barrier in turn keeps the
+        // parity waits from ever naming a phase two completions back
+        wait_upto(&ctl->conv_loc[g ^ 1], loc_seen, loc_done_other);
+        tc_fence_after();
+        for (int h0 = 0; h0 < 128; h0 += 64) {
+#pragma unroll
+          for (int cc = 0; cc < 64; cc += 32) {
+            const int c0 = h0 + cc;
+            float v[32];
+            tmem_ld32(src + c0, v);
+            uint32_t pk[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) pk[e] = pack2(v[2 * e], v[2 * e + 1]);
+            tmem_st16(dst + (c0 >> 1), pk);                             // in place for even t: columns already read
+            if (P.z_save) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(stg + lane * 128 + ((((cc >> 3) + q) ^ (lane & 7)) << 4)) =
+                    make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            }
+          }
+          if (h0 == 64) {                                                // whole step converted: release it
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(&ctl->conv_loc[g]);
+              mbar_arrive_cluster(conv_doneL);
+            }
+          }
+          if (P.z_save) {                                                // coalesced: 4 whole 128-byte row segments per instr
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = r8 + 4 * i;
+              if (wrow0 + r < P.Np) {
+                const uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4));
+                *reinterpret_cast<uint4*>(P.z_save + (int64_t)b * P.zbs + (int64_t)(wrow0 + r) * D + t * 128 + h0 + ch8 * 8) = v4;
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+      // ---- projection epilogue (chunks of parity g): + bias + residual, coalesced through the warp staging
+      for (int n = g; n < nchunk; n += 2) {
+        const int buf = n & 1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r8 + 4 * i;
+          *reinterpret_cast<uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4)) = rnext[i];
+        }
+        if constexpr (!RES32) load_resid(n + 2, rnext);                  // next chunk of this warpgroup: in flight meanwhile
+        __syncwarp();
+        mbar_wait(&ctl->out_full[buf], full_seen & 1);
+        ++full_seen;
+        tc_fence_after();
+        float v0[32], v1[32];
+        tmem_ld32(tl + T_OUT + buf * 64, v0);
+        tmem_ld32(tl + T_OUT + buf * 64 + 32, v1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(out_freeL);                   // buf == g
+        if constexpr (!RES32) {
+          __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(P.out);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t off = lane * 128 + ((q ^ (lane & 7)) << 4);
+            const uint4 r4 = *reinterpret_cast<const uint4*>(stg + off);
+            const uint4 b4 = *reinterpret_cast<const uint4*>(&ctl->bias[n * 64 + q * 8]);
+            const float* vv = q < 4 ? &v0[8 * q] : &v1[8 * (q - 4)];
+            const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+            uint32_t oo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              oo[e] = pack2(vv[2 * e] + bf_lo(bb[e]) + bf_lo(rr[e]), vv[2 * e + 1] + bf_hi(bb[e]) + bf_hi(rr[e]));
+            *reinterpret_cast<uint4*>(stg + off) = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = r8 + 4 * i;
+            if (wrow0 + r < P.Np) {
+              const uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4));
+              *reinterpret_cast<uint4*>(outp + ((int64_t)b * (P.Np + 1) + 1 + wrow0 + r) * D + n * 64 + ch8 * 8) = v4;
+            }
+          }
+          __syncwarp();
+        } else {
+          float* outp = static_cast<float*>(P.out);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {                               // 32 features = 128 bytes of fp32 per row and half
+            if (hh == 1) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = r8 + 4 * i;
+                *reinterpret_cast<uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4)) = rnext[8 + i];
+              }
+              load_resid(n + 2, rnext);                                  // both halves consumed: next chunk in flight
+              __syncwarp();
+            }
+            const float* vv = hh == 0 ? v0 : v1;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {                                // 4 features per 16-byte chunk
+              const uint32_t off = lane * 128 + ((q ^ (lane & 7)) << 4);
+              float4 r4 = *reinterpret_cast<const float4*>(stg + off);
+              const uint2 b2 = *reinterpret_cast<const uint2*>(&ctl->bias[n * 64 + hh * 32 + q * 4]);
+              // the branch value as the bf16 projection would store it, then the fp32 add (autocast semantics)
+              const uint32_t y01 = pack2(vv[4 * q] + bf_lo(b2.x), vv[4 * q + 1] + bf_hi(b2.x));
+              const uint32_t y23 = pack2(vv[4 * q + 2] + bf_lo(b2.y), vv[4 * q + 3] + bf_hi(b2.y));
+              r4.x += bf_lo(y01); r4.y += bf_hi(y01); r4.z += bf_lo(y23); r4.w += bf_hi(y23);
+              *reinterpret_cast<float4*>(stg + off) = r4;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = r8 + 4 * i;
+              if (wrow0 + r < P.Np) {
+                const uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4));
+                *reinterpret_cast<uint4*>(outp + ((int64_t)b * (P.Np + 1) + 1 + wrow0 + r) * D + n * 64 + hh * 32 + ch8 * 4) = v4;
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 9) tmem_dealloc_2sm(tmem, 512);
+}
+
+template <int KT, bool RES32>
+int launch2(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const Params& P, cudaStream_t st) {
+  GVIT_CHECK_CUDA(cudaFuncSetAttribute(agg4_tc_kernel<KT, RES32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  int pairs = 0;
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((num_sms() / 2) * 2);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&pairs, agg4_tc_kernel<KT, RES32>, &cfg) != cudaSuccess || pairs < 1) {
+      (void)cudaGetLastError();
+      pairs = num_sms() / 2;
+    }
+  }
+  const int grid = 2 * (P.B < pairs ? P.B : pairs);
+  agg4_tc_kernel<KT, RES32><<<grid, THREADS, SMEM_BYTES, st>>>(tm_tok, tm_w, P);
+  GVIT_CHECK_LAUNCH();
+  return GVIT_OK;
+}
+template <int KT>
+int launch(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const Params& P, bool res32, cudaStream_t st) {
+  return res32 ? launch2<KT, true>(tm_tok, tm_w, P, st) : launch2<KT, false>(tm_tok, tm_w, P, st);
+}
+
+}  // namespace
+
+bool agg4_tc_supported(int Np, int D, int k) {
+  return Np >= 16 && Np <= 256 && D >= 128 && D % 128 == 0 && D <= 768 && k <= 16;
+}
+
+int agg4_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, const float* vals, const void* Wg,
+                const void* bias, const void* resid, int resid_dtype, void* out, float* w_save, void* z_save, int64_t z_batch_stride,
+                cudaStream_t st) {
+  Params P;
+  P.B = B; P.Np = Np; P.D = D; P.k = k;
+  P.NT = (Np + 15) & ~15;
+  P.idx = idx; P.vals = vals;
+  P.bias = static_cast<const __nv_bfloat16*>(bias);
+  P.resid = resid;
+  P.out = out;
+  const bool res32 = resid_dtype == GVIT_F32;
+  P.w_save = w_save;
+  P.z_save = static_cast<__nv_bfloat16*>(z_save);
+  P.zbs = z_batch_stride;
+
+  CUtensorMap tm_tok, tm_w;
+  const __nv_bfloat16* tok = static_cast<const __nv_bfloat16*>(h) + D;   // skip the CLS row (section 9, G0)
+  int rc = make_tmap_bf16_3d(&tm_tok, tok, D, Np, B, D, (uint64_t)(Np + 1) * D, P.NT);
+  if (rc != GVIT_OK) return rc;
+  rc = make_tmap_bf16_3d(&tm_w, Wg, D, D, 1, D, (uint64_t)D * D, 32);
+  if (rc != GVIT_OK) return rc;
+  if (k <= 4) return launch<4>(tm_tok, tm_w, P, res32, st);
+  if (k <= 8) return launch<8>(tm_tok, tm_w, P, res32, st);
+  return launch<16>(tm_tok, tm_w, P, res32, st);
+}
+
+}  // namespace gvit

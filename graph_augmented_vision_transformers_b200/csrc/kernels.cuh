@@ -32,6 +32,10 @@ bool agg3_tc_supported(int Np, int D, int k);   // v3 kernel (agg3_tc.cu): whole
 int agg3_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, const float* vals, const void* Wg,
                 const void* bias, const void* resid, int resid_dtype, void* out, float* w_save, void* z_save, int64_t z_batch_stride,
                 cudaStream_t st);
+bool agg4_tc_supported(int Np, int D, int k);   // v4 kernel (agg4_tc.cu): one CTA pair per image (cta_group::2), D % 128 == 0, D <= 768
+int agg4_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, const float* vals, const void* Wg,
+                const void* bias, const void* resid, int resid_dtype, void* out, float* w_save, void* z_save, int64_t z_batch_stride,
+                cudaStream_t st);
 int agg_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, const float* vals, const void* Wg,
                const void* bias, const void* resid, void* out, float* w_save, void* z_save, int64_t z_batch_stride,
                cudaStream_t st);

@@ -177,9 +177,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_smem_addr, uint32_t ra
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_smem_addr), "r"(rank));
   return r;
 }
-// remote (or local) arrival on an mbarrier given by its shared::cluster address
+// remote (or local) arrival on an mbarrier given by its shared::cluster address.  Default semantics (.release at CTA scope):
+// the arrivals here order tensor-memory reads (tcgen05.fence::before_thread_sync precedes them), not generic-proxy data
+// another CTA will read - `.release.cluster` compiled to MEMBAR.ALL.CTA + ERRBAR per arrival, 13 % of the fused fc1
+// kernel's stall samples (profiles/r4d_ncu_fc1_2sm.txt).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // tile load into THIS CTA's shared memory whose completion bytes are counted on the mbarrier at `bar_cluster_addr`
 // (the leader's full barrier of the stage)

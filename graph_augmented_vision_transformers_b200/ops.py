@@ -555,7 +555,7 @@ class _LinearDropoutAdd(torch.autograd.Function):
         N, K = weight.shape
         if (x.dtype == torch.bfloat16 and resid is not None and K <= _FUSED_RESID_MAX_K
                 and fused_fc1_available(N, K) and x.is_contiguous()):
-            # proj + proj_drop + residual add as ONE tcgen05 GEMM (its main loop is L2-bound, so only while K is small);
+            # proj + proj_drop + residual add as ONE tcgen05 GEMM;
             # resid / out are bf16, or fp32 when the residual stream is kept in fp32 (autocast semantics)
             M = x.numel() // K
             out = torch.empty_like(resid)
@@ -654,14 +654,24 @@ class _MlpFused(torch.autograd.Function):
         mask1 = torch.empty(M * Nh // 8, dtype=torch.uint8, device=x.device) if p > 0 else None
         _call("gvit_linear_gelu_dropout_fwd", _ptr(x), _ptr(w1s), _ptr(_shadow(b1, x.dtype)), M, Nh, K, float(p), int(seed1), 0,
               _rng_offset_ptr(), GVIT_BF16, _ptr(u), _ptr(h), _ptr(mask1), st)
-        y = _mm_nt(h, w2s, _shadow(b2, x.dtype))
-        n = y.numel()
-        out = torch.empty_like(y if resid is None else resid)
-        mask2 = torch.empty(n // 8, dtype=torch.uint8, device=x.device) if p > 0 else None
-        _call("gvit_dropout_residual_fwd", _ptr(y), _ptr(resid), n, float(p), int(seed2), 0, _rng_offset_ptr(), _dtype_code(out),
-              _dtype_code(y), _ptr(out), _ptr(mask2), st)
+        D2 = w2s.shape[0]
+        if resid is not None and Nh <= _FUSED_RESID_MAX_K and fused_fc1_available(D2, Nh):
+            # fc2 + drop + residual add (vit.py:93-94,118) as ONE tcgen05 GEMM: bias, keep mask and the add run in its epilogue
+            out = torch.empty_like(resid)
+            mask2 = torch.empty(M * D2 // 8, dtype=torch.uint8, device=x.device) if p > 0 else None
+            _call("gvit_linear_dropout_residual_fwd", _ptr(h), _ptr(w2s), _ptr(_shadow(b2, x.dtype)), _ptr(resid), M, D2, Nh, float(p),
+                  int(seed2), 0, _rng_offset_ptr(), GVIT_BF16, _dtype_code(resid), _ptr(out), _ptr(mask2), st)
+            y_dtype = x.dtype
+        else:
+            y = _mm_nt(h, w2s, _shadow(b2, x.dtype))
+            n = y.numel()
+            out = torch.empty_like(y if resid is None else resid)
+            mask2 = torch.empty(n // 8, dtype=torch.uint8, device=x.device) if p > 0 else None
+            _call("gvit_dropout_residual_fwd", _ptr(y), _ptr(resid), n, float(p), int(seed2), 0, _rng_offset_ptr(), _dtype_code(out),
+                  _dtype_code(y), _ptr(out), _ptr(mask2), st)
+            y_dtype = y.dtype
         ctx.save_for_backward(x, w1s, w2s, u, h, mask1, mask2)
-        ctx.p, ctx.has_resid, ctx.y_dtype = p, resid is not None, y.dtype
+        ctx.p, ctx.has_resid, ctx.y_dtype = p, resid is not None, y_dtype
         return out
 
     @staticmethod
@@ -899,7 +909,8 @@ def agg_gather(h: torch.Tensor, idx: torch.Tensor, vals: torch.Tensor):
 
 
 _FC1_ENABLED = {"on": True}
-_FUSED_RESID_MAX_K = 1024        # Linear + dropout + residual goes through the fused GEMM up to this reduction length
+_FUSED_RESID_MAX_K = int(os.environ.get("GVIT_FUSED_RESID_MAX_K", "8192"))   # Linear + dropout + residual goes through the fused GEMM up to
+# this reduction length (1024 while its main loop was L2-bound; the 2-SM main loop runs K = 3072 / 4096 at GEMM speed)
 
 
 def fused_fc1_available(N: int, K: int) -> bool:
