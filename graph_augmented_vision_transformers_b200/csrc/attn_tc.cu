@@ -18,6 +18,7 @@
 //
 // Warp roles: 0-3 softmax / epilogue, 4 TMA producer, 5 MMA issuer (+ TMEM allocation).
 #include <float.h>
+#include <stdlib.h>
 
 #include "gelu.cuh"
 #include "kernels.cuh"
@@ -933,6 +934,9 @@ int attn_fwd_tc(const void* qkv, int B, int N, int H, float scale, void* out, fl
     GVIT_CHECK_LAUNCH();
     return GVIT_OK;
   }
+  // N > 256: the persistent key-block kernel (attn_fwd_long_tc.cu); GVIT_ATTN_FWD_LONG_V1=1 keeps the first kernel (A/B switch)
+  static const bool v1 = getenv("GVIT_ATTN_FWD_LONG_V1") != nullptr;
+  if (!v1) return attn_fwd_long_tc(qkv, B, N, H, scale, out, lse, st);
   GVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));
   dim3 grid((N + 127) / 128, H, B);
   attn_fwd_tc_kernel<<<grid, THREADS, FWD_SMEM, st>>>(tm, N, H, scale, static_cast<__nv_bfloat16*>(out), lse);

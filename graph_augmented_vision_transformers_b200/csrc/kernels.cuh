@@ -47,6 +47,7 @@ bool attn_bwd_tc_supported(int N, int dh);
 int attn_fwd_tc(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, cudaStream_t st);
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, int B, int N, int H,
                 float scale, float* delta_ws, void* dqkv, cudaStream_t st);
+int attn_fwd_long_tc(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, cudaStream_t st);   // N > 256 (attn_fwd_long_tc.cu)
 int attn_bwd_long_tc(const void* qkv, const void* out, const void* dout, const float* lse, int B, int N, int H,
                      float scale, float* delta_ws, void* dqkv, cudaStream_t st);   // N > 256 (attn_long_tc.cu)
 
