@@ -92,7 +92,9 @@ def test_attn_drop_is_refused_loudly():
         ops.attention_core(torch.randn(1, 4, 3 * 48, device=DEV), 1, 1.0)      # head dim 48
 
 
-@pytest.mark.parametrize("N,boost_from,boost", [(197, 100, 60.0), (197, 33, 25.0), (256, 200, 200.0), (150, 64, 8.0)])
+@pytest.mark.parametrize("N,boost_from,boost", [(197, 100, 60.0), (197, 33, 25.0), (256, 200, 200.0), (150, 64, 8.0),
+                                                (577, 300, 60.0), (513, 420, 200.0), (300, 290, 25.0)])   # N > 256: the online-softmax
+                                                # rescale of the key-block kernel (running max jumps in a LATER block)
 def test_bf16_large_logits_late_keys(N, boost_from, boost):
     """Softmax range stress: keys from `boost_from` on are scaled so that the row maxima sit far (tens to hundreds of nats)
     above the scores of the first keys, in some heads and not in others; forward, saved log-sum-exp (through the
