@@ -246,11 +246,11 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
                           2 * B * N * D * e, 0.0, "hbm", 36),
         "layernorm_bwd": (lambda i: _call("gvit_layernorm_bwd", _ptr(xs[i % R]), _ptr(hs[i % R]), _ptr(gam), _ptr(mean), _ptr(rstd), B * N, D, dt, dt, None, _ptr(out), _ptr(dgb[0]), _ptr(dgb[1]), _ptr(ws), st),
                           3 * B * N * D * e, 0.0, "hbm", 1),
-        "fc1_fused": (lambda i: _call("gvit_linear_gelu_dropout_fwd", _ptr(hs[i % R]), _ptr(W1), _ptr(b1), B * N, 4 * D, D, 0.1, 1234, 0, None, dt, _ptr(u4[i % 2]), _ptr(o4), _ptr(m4), st),
+        "fc1_fused": (lambda i: _call("gvit_linear_gelu_dropout_fwd", _ptr(hs[i % R]), _ptr(W1), _ptr(b1), B * N, 4 * D, D, 0.1, 1234, 0, None, dt, 1, _ptr(u4[i % 2]), _ptr(o4), None, st),
                       B * N * D * e + 4 * D * D * e + 2 * B * N * 4 * D * e + B * N * 4 * D // 8, 2.0 * B * N * D * 4 * D, "tensor", 12),
         "proj_fused": (lambda i: _call("gvit_linear_dropout_residual_fwd", _ptr(hs[i % R]), _ptr(W), _ptr(bias), _ptr(xs[i % R]), B * N, D, D, 0.1, 1234, 0, None, dt, dt, _ptr(out), _ptr(m1), st),
                        3 * B * N * D * e + D * D * e + B * N * D // 8, 2.0 * B * N * D * D, "hbm", 12),
-        "fc2_bwd_fused": (lambda i: _call("gvit_linear_gelu_dropout_bwd", _ptr(hs[i % R]), _ptr(W2), _ptr(u4[i % 2]), _ptr(m4), B * N, 4 * D, D, 0.1, dt, _ptr(o4), _ptr(cs_out), _ptr(part4), st),
+        "fc2_bwd_fused": (lambda i: _call("gvit_linear_gelu_dropout_bwd", _ptr(hs[i % R]), _ptr(W2), _ptr(u4[i % 2]), None, B * N, 4 * D, D, 0.1, dt, 1, _ptr(o4), _ptr(cs_out), _ptr(part4), st),
                           B * N * D * e + 4 * D * D * e + 2 * B * N * 4 * D * e + B * N * 4 * D // 8, 2.0 * B * N * D * 4 * D, "tensor", 12),
         "gelu_dropout_fwd": (lambda i: _call("gvit_gelu_dropout_fwd", _ptr(u4[i % 2]), B * N * 4 * D, 0.1, 1234, 0, None, dt, _ptr(o4), _ptr(m4), st),
                              2 * B * N * 4 * D * e + B * N * 4 * D // 8, 0.0, "hbm", 0),      # folded into fc1_fused for bf16

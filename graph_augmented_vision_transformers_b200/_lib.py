@@ -19,7 +19,7 @@ GVIT_F32, GVIT_BF16 = 0, 1
 GVIT_MAX_K = 32
 GVIT_LN_PARTIALS = 296
 GVIT_COLSUM_CHUNKS = 1024
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 STATUS_NAMES = {0: "GVIT_OK", 1: "GVIT_ERR_SHAPE", 2: "GVIT_ERR_ALIGN", 3: "GVIT_ERR_DTYPE", 4: "GVIT_ERR_CUDA",
                 5: "GVIT_ERR_UNSUPPORTED"}
@@ -67,10 +67,10 @@ SIGNATURES = {
     "gvit_dropout_bwd": [_vp, _vp, _i64, _f, _i, _i, _vp, _i, _i, _vp, _vp, _vp],
     "gvit_gelu_dropout_fwd": [_vp, _i64, _f, _u64, _u64, _vp, _i, _vp, _vp, _vp],
     "gvit_gelu_dropout_bwd": [_vp, _vp, _vp, _i64, _f, _i, _vp, _i, _vp, _vp, _vp],
-    "gvit_linear_gelu_dropout_fwd": [_vp, _vp, _vp, _i64, _i, _i, _f, _u64, _u64, _vp, _i, _vp, _vp, _vp, _vp],
+    "gvit_linear_gelu_dropout_fwd": [_vp, _vp, _vp, _i64, _i, _i, _f, _u64, _u64, _vp, _i, _i, _vp, _vp, _vp, _vp],
     "gvit_linear_dropout_residual_fwd": [_vp, _vp, _vp, _vp, _i64, _i, _i, _f, _u64, _u64, _vp, _i, _i, _vp, _vp, _vp],
     "gvit_linear_gelu_dropout_bwd_ws_rows": [_i64],
-    "gvit_linear_gelu_dropout_bwd": [_vp, _vp, _vp, _vp, _i64, _i, _i, _f, _i, _vp, _vp, _vp, _vp],
+    "gvit_linear_gelu_dropout_bwd": [_vp, _vp, _vp, _vp, _i64, _i, _i, _f, _i, _i, _vp, _vp, _vp, _vp],
     "gvit_linear_gemm_ws_bytes": [_i64, _i, _i],
     "gvit_linear_gemm": [_vp, _i, _i64, _vp, _i, _i64, _i64, _i, _i, _vp, _i, _vp, _i64, _vp, _i64, _vp],
     "gvit_mt_chunk_elems": [],

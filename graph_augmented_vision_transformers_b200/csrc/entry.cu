@@ -294,18 +294,22 @@ int gvit_gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_m
 }
 
 int gvit_linear_gelu_dropout_fwd(const void* x, const void* w, const void* bias, int64_t M, int N, int K, float p, uint64_t seed,
-                                 uint64_t offset, const uint64_t* offset_dev, int dtype, void* u, void* out, uint8_t* keep_mask,
-                                 void* stream) {
+                                 uint64_t offset, const uint64_t* offset_dev, int dtype, int save_mode, void* u, void* out,
+                                 uint8_t* keep_mask, void* stream) {
   TRY(check_dtype(dtype, "linear_gelu_dropout_fwd"));
-  GVIT_REQUIRE(x && w && u && out, GVIT_ERR_SHAPE, "linear_gelu_dropout_fwd: null pointer");
-  GVIT_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || keep_mask), GVIT_ERR_SHAPE, "linear_gelu_dropout_fwd: p=%f (keep_mask required when p > 0)", p);
+  GVIT_REQUIRE(x && w && out, GVIT_ERR_SHAPE, "linear_gelu_dropout_fwd: null pointer");
+  GVIT_REQUIRE(save_mode == 0 || save_mode == 1, GVIT_ERR_SHAPE, "linear_gelu_dropout_fwd: save_mode=%d (0: pre-activation, 1: backward factor)", save_mode);
+  // the keep mask is what the backward of save_mode 0 needs; the factor of save_mode 1 already contains it, and u == NULL saves nothing
+  GVIT_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || keep_mask || save_mode == 1 || !u), GVIT_ERR_SHAPE,
+               "linear_gelu_dropout_fwd: p=%f (keep_mask required when p > 0 and the pre-activation is saved)", p);
   GVIT_REQUIRE(dtype == GVIT_BF16 && fc1_tc_supported(M, N, K), GVIT_ERR_UNSUPPORTED,
                "linear_gelu_dropout_fwd: the fused kernel is bf16-only with N %% 256 == 0 and K %% 64 == 0 (M=%lld N=%d K=%d); "
                "compose a library GEMM with gvit_gelu_dropout_fwd instead", (long long)M, N, K);
-  GVIT_REQUIRE(aligned16(x) && aligned16(w) && aligned16(u) && aligned16(out) && (!bias || aligned16(bias)) &&
+  GVIT_REQUIRE(aligned16(x) && aligned16(w) && (!u || aligned16(u)) && aligned16(out) && (!bias || aligned16(bias)) &&
                (!keep_mask || (reinterpret_cast<uintptr_t>(keep_mask) & 7u) == 0), GVIT_ERR_ALIGN,
                "linear_gelu_dropout_fwd: tensors must be 16-byte aligned (keep_mask 8-byte)");
-  return fc1_gelu_dropout_fwd_tc(x, w, bias, M, N, K, p, seed, offset, offset_dev, u, out, keep_mask, static_cast<cudaStream_t>(stream));
+  return fc1_gelu_dropout_fwd_tc(x, w, bias, M, N, K, p, seed, offset, offset_dev, save_mode, u, out, keep_mask,
+                                 static_cast<cudaStream_t>(stream));
 }
 
 int gvit_linear_dropout_residual_fwd(const void* x, const void* w, const void* bias, const void* resid, int64_t M, int N, int K, float p,
@@ -328,17 +332,20 @@ int gvit_linear_dropout_residual_fwd(const void* x, const void* w, const void* b
 int64_t gvit_linear_gelu_dropout_bwd_ws_rows(int64_t M) { return fc2_bwd_partial_rows(M); }
 
 int gvit_linear_gelu_dropout_bwd(const void* dout, const void* w2, const void* u, const uint8_t* keep_mask, int64_t M, int N, int K,
-                                 float p, int dtype, void* du, float* colsum_out, float* partial_ws, void* stream) {
+                                 float p, int dtype, int saved_mode, void* du, float* colsum_out, float* partial_ws, void* stream) {
   TRY(check_dtype(dtype, "linear_gelu_dropout_bwd"));
   GVIT_REQUIRE(dout && w2 && u && du && colsum_out && partial_ws, GVIT_ERR_SHAPE, "linear_gelu_dropout_bwd: null pointer");
-  GVIT_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || keep_mask), GVIT_ERR_SHAPE, "linear_gelu_dropout_bwd: p=%f (keep_mask required when p > 0)", p);
+  GVIT_REQUIRE(saved_mode == 0 || saved_mode == 1, GVIT_ERR_SHAPE, "linear_gelu_dropout_bwd: saved_mode=%d (0: pre-activation, 1: backward factor)", saved_mode);
+  GVIT_REQUIRE(p >= 0.f && p < 1.f && (p == 0.f || keep_mask || saved_mode == 1), GVIT_ERR_SHAPE,
+               "linear_gelu_dropout_bwd: p=%f (keep_mask required when p > 0 and u is the pre-activation)", p);
   GVIT_REQUIRE(dtype == GVIT_BF16 && fc1_tc_supported(M, N, K), GVIT_ERR_UNSUPPORTED,
                "linear_gelu_dropout_bwd: the fused kernel is bf16-only with N %% 256 == 0 and K %% 64 == 0 (M=%lld N=%d K=%d); "
                "compose a library GEMM with gvit_gelu_dropout_bwd instead", (long long)M, N, K);
   GVIT_REQUIRE(aligned16(dout) && aligned16(w2) && aligned16(u) && aligned16(du) && aligned16(partial_ws) &&
                (!keep_mask || (reinterpret_cast<uintptr_t>(keep_mask) & 3u) == 0), GVIT_ERR_ALIGN,
                "linear_gelu_dropout_bwd: tensors must be 16-byte aligned (keep_mask 4-byte)");
-  return linear_gelu_dropout_bwd_tc(dout, w2, u, keep_mask, M, N, K, p, du, colsum_out, partial_ws, static_cast<cudaStream_t>(stream));
+  return linear_gelu_dropout_bwd_tc(dout, w2, u, keep_mask, M, N, K, p, saved_mode, du, colsum_out, partial_ws,
+                                    static_cast<cudaStream_t>(stream));
 }
 
 int64_t gvit_linear_gemm_ws_bytes(int64_t M, int N, int K) { return gemm2_tc_supported(M, N, K) ? gemm2_ws_bytes(M, N, K) : 0; }

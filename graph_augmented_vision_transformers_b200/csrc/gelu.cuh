@@ -34,6 +34,10 @@ template <> struct Gelu<true> {
 #pragma unroll
     for (int t = 0; t < 8; ++t) g[t] = g[t] * mul * grad(u[t]);
   }
+  static __device__ __forceinline__ void fwd_grad8(float (&a)[8], float (&d)[8], float mul) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { d[t] = mul * grad(a[t]); a[t] = fwd(a[t]) * mul; }
+  }
 };
 template <> struct Gelu<false> {
   // returns Phi(u) and e = exp(-u^2/2); MUFU.RCP / MUFU.EX2 approximations (1 ulp-ish, far below bf16 resolution):
@@ -93,6 +97,20 @@ template <> struct Gelu<false> {
       const f32x2 c = cdf2(u[t], u[t + 1], mul, e);
       const f32x2 d = fma2(mul2(pk2(u[t], u[t + 1]), pk2(k, k)), e, c);     // mul * (Phi + u phi)
       up2(mul2(pk2(g[t], g[t + 1]), d), g[t], g[t + 1]);
+    }
+  }
+  // a[t] = mul * gelu(a[t]) and d[t] = mul * gelu'(a[t]) from ONE evaluation of Phi and exp(-u^2/2): two packed instructions
+  // more than fwd8.  The fused fc1 GEMM stores d (times the keep bit) instead of the pre-activation, so that the backward
+  // GEMM's epilogue is a single multiply (mlp_tc.cu, `factor` mode).
+  static __device__ __forceinline__ void fwd_grad8(float (&a)[8], float (&d)[8], float mul) {
+    const float k = 0.3989422804014327f * mul;
+#pragma unroll
+    for (int t = 0; t < 8; t += 2) {
+      f32x2 e;
+      const f32x2 u = pk2(a[t], a[t + 1]);
+      const f32x2 c = cdf2(a[t], a[t + 1], mul, e);
+      up2(fma2(mul2(u, pk2(k, k)), e, c), d[t], d[t + 1]);
+      up2(mul2(u, c), a[t], a[t + 1]);
     }
   }
 };

@@ -85,7 +85,7 @@ int gelu_dropout_bwd(const void* dout, const void* u, const uint8_t* keep_mask, 
 // ---- fused fc1 : mlp_tc.cu
 bool fc1_tc_supported(int64_t M, int N, int K);
 int fc1_gelu_dropout_fwd_tc(const void* x, const void* w, const void* bias, int64_t M, int N, int K, float p, uint64_t seed,
-                            uint64_t offset, const uint64_t* offset_dev, void* u, void* out, uint8_t* mask, cudaStream_t st);
+                            uint64_t offset, const uint64_t* offset_dev, int save_mode, void* u, void* out, uint8_t* mask, cudaStream_t st);
 
 int linear_dropout_residual_fwd_tc(const void* x, const void* w, const void* bias, const void* resid, int64_t M, int N, int K, float p,
                                    uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int resid_dtype, void* out, uint8_t* mask,
@@ -93,7 +93,7 @@ int linear_dropout_residual_fwd_tc(const void* x, const void* w, const void* bia
 
 int64_t fc2_bwd_partial_rows(int64_t M);
 int linear_gelu_dropout_bwd_tc(const void* dout, const void* w2, const void* u, const uint8_t* mask, int64_t M, int N, int K, float p,
-                               void* du, float* colsum_out, float* partial_ws, cudaStream_t st);
+                               int saved_mode, void* du, float* colsum_out, float* partial_ws, cudaStream_t st);
 
 // ---- 2-SM Linear GEMM : gemm2_tc.cu
 bool gemm2_tc_supported(int64_t M, int N, int K);

@@ -70,6 +70,8 @@ struct Params {
   __nv_bfloat16* out;
   uint8_t* mask;
   float* partial;                             // MODE 2: (ceil(M/128) * 4, N) fp32 column partial sums of du
+  int factor;                                 // MODE 0: store keep * gelu'(u) / (1 - p) in `u` instead of the pre-activation (u may
+                                              // be NULL: inference, nothing saved).  MODE 2: `u` holds that factor (mask unused)
   uint32_t rk[2 * GVIT_PHILOX_ROUNDS];        // Philox round keys, precomputed on the host: constant-bank operands, no
 };                                            // per-call key schedule in the epilogue
 
@@ -208,6 +210,22 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
       const int buf = tc & 1;
       const int64_t wrow0 = (int64_t)m * BM + (warp & 3) * 32;         // first row of this warp
       const int64_t row = wrow0 + lane;
+      // MODE 2: the saved tile (pre-activation or backward factor) of this warp's rows is the one global read of the
+      // epilogue; it is fetched one 32-column half ahead - the first before the accumulator wait - so that its latency
+      // lies under the MMAs / the previous half instead of in front of every half
+      uint4 pre[4];
+      auto prefetch_saved = [&](int h) {
+        if constexpr (MODE == 2) {
+          const int c0 = n * BN + g * 64 + h * 32;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = r4 + 8 * i;
+            pre[i] = make_uint4(0, 0, 0, 0);
+            if (wrow0 + r < P.M) pre[i] = *reinterpret_cast<const uint4*>(P.u + (wrow0 + r) * P.N + c0 + ch4 * 8);
+          }
+        }
+      };
+      prefetch_saved(0);
       mbar_wait(&ctl->acc_full[buf], (tc >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -235,14 +253,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
           // ---- du = dh * keep / (1 - p) * gelu'(u); column sums of du over this warp's 32 rows
           uint32_t uu[16];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {                                // u tile: coalesced global -> staging -> own row
+          for (int i = 0; i < 4; ++i) {                                // saved tile: coalesced global (prefetched) -> staging -> own row
             const int r = r4 + 8 * i;
-            uint4 v4 = make_uint4(0, 0, 0, 0);
-            if (wrow0 + r < P.M) v4 = *reinterpret_cast<const uint4*>(P.u + (wrow0 + r) * P.N + col0 + ch4 * 8);
-            *reinterpret_cast<uint4*>(stg + r * 64 + ((ch4 ^ ((r >> 1) & 3)) << 4)) = v4;
+            *reinterpret_cast<uint4*>(stg + r * 64 + ((ch4 ^ ((r >> 1) & 3)) << 4)) = pre[i];
           }
+          if (h == 0) prefetch_saved(1);
           uint32_t keep = 0xffffffffu;
-          if (P.p > 0.f && row < P.M) keep = *reinterpret_cast<const uint32_t*>(P.mask + ((row * P.N + col0) >> 3));
+          if (!P.factor && P.p > 0.f && row < P.M) keep = *reinterpret_cast<const uint32_t*>(P.mask + ((row * P.N + col0) >> 3));
           __syncwarp();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -259,9 +276,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
               uq[2 * e] = bf_lo(uu[4 * q + e]); uq[2 * e + 1] = bf_hi(uu[4 * q + e]);
               gq[2 * e] = v[8 * q + 2 * e]; gq[2 * e + 1] = v[8 * q + 2 * e + 1];
             }
-            Gelu<false>::grad8(gq, uq, scale);
+            if (P.factor) {                                            // the forward saved keep * gelu'(u) / (1 - p): one multiply
 #pragma unroll
-            for (int t = 0; t < 8; ++t) gq[t] = (keep >> (8 * q + t)) & 1u ? gq[t] : 0.f;
+              for (int t = 0; t < 8; ++t) gq[t] *= uq[t];
+            } else {
+              Gelu<false>::grad8(gq, uq, scale);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) gq[t] = (keep >> (8 * q + t)) & 1u ? gq[t] : 0.f;
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) dpk[4 * q + e] = pack2(gq[2 * e], gq[2 * e + 1]);
           }
@@ -299,8 +321,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
         __syncwarp();                                                  // bias reads done: the staging area is free again
         uint32_t rres[16];                                             // MODE 1: this row's 32 residual values (bf16 pairs)
         if constexpr (MODE == 0) {
-          stage(upk);
-          flush(P.u, wrow0, col0);                                     // pre-activation tile
+          if (!P.factor && P.u != nullptr) {
+            stage(upk);
+            flush(P.u, wrow0, col0);                                   // pre-activation tile
+          }
         } else if constexpr (!RES32) {
           // residual tile: coalesced global -> staging (the store pattern in reverse), then every lane reads its row
 #pragma unroll
@@ -382,15 +406,29 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
           if (P.p > 0.f && row < P.M) *reinterpret_cast<uint32_t*>(P.mask + ((row * P.N + col0) >> 3)) = keep;
           continue;
         }
+        uint32_t fpk[16];                                              // MODE 0, factor mode: keep * gelu'(u) / (1 - p), 32 bf16
 #pragma unroll
         for (int q = 0; q < 4; ++q) {                                  // 8 columns per step
           float a[8];
 #pragma unroll
           for (int e = 0; e < 4; ++e) { a[2 * e] = bf_lo(upk[4 * q + e]); a[2 * e + 1] = bf_hi(upk[4 * q + e]); }
           if constexpr (MODE == 0) {
-            Gelu<false>::fwd8(a, scale);                               // GELU of the stored value, dropout scale folded in
+            if (P.factor && P.u != nullptr) {                          // value and backward factor from one evaluation
+              float dg[8];
+              Gelu<false>::fwd_grad8(a, dg, scale);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) a[t] = (keep >> (8 * q + t)) & 1u ? a[t] : 0.f;
+              for (int t = 0; t < 8; ++t) {
+                const bool kp = (keep >> (8 * q + t)) & 1u;
+                a[t] = kp ? a[t] : 0.f;
+                dg[t] = kp ? dg[t] : 0.f;
+              }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) fpk[4 * q + e] = pack2(dg[2 * e], dg[2 * e + 1]);
+            } else {
+              Gelu<false>::fwd8(a, scale);                             // GELU of the stored value, dropout scale folded in
+#pragma unroll
+              for (int t = 0; t < 8; ++t) a[t] = (keep >> (8 * q + t)) & 1u ? a[t] : 0.f;
+            }
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {                              // resid + keep * scale * y (y as a bf16 GEMM would store it)
@@ -404,7 +442,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
         }
         stage(upk);
         flush(P.out, wrow0, col0);                                     // activation tile
-        if (P.p > 0.f && row < P.M) *reinterpret_cast<uint32_t*>(P.mask + ((row * P.N + col0) >> 3)) = keep;
+        if constexpr (MODE == 0) {
+          if (P.factor && P.u != nullptr) {
+            stage(fpk);
+            flush(P.u, wrow0, col0);                                   // backward factor tile (instead of the pre-activation)
+          }
+        }
+        if (P.p > 0.f && P.mask != nullptr && row < P.M) *reinterpret_cast<uint32_t*>(P.mask + ((row * P.N + col0) >> 3)) = keep;
       }
     }
   }
@@ -439,7 +483,7 @@ bool fc1_tc_supported(int64_t M, int N, int K) { return M >= 1 && N >= BN && N %
 template <int MODE, bool RES32 = false>
 static int fused_linear_launch(const void* x, const void* w, const void* bias, int64_t M, int N, int K, float p, uint64_t seed,
                                uint64_t offset, const uint64_t* offset_dev, void* u_or_resid, void* out, uint8_t* mask,
-                               cudaStream_t st, float* partial = nullptr) {
+                               cudaStream_t st, float* partial = nullptr, int factor = 0) {
   CUtensorMap tm_x, tm_w;
   int rc = make_tmap_bf16_3d(&tm_x, x, (uint64_t)K, (uint64_t)M, 1, (uint64_t)K, (uint64_t)M * K, BM);
   if (rc != GVIT_OK) return rc;
@@ -449,7 +493,7 @@ static int fused_linear_launch(const void* x, const void* w, const void* bias, i
     rc = make_tmap_bf16_3d(&tm_w, w, (uint64_t)N, (uint64_t)K, 1, (uint64_t)N, (uint64_t)N * K, 64);        // W2 (K, N): [64 k][64 n] atoms
   if (rc != GVIT_OK) return rc;
   Params P{M, N, K, p, seed, offset, offset_dev, static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(u_or_resid),
-           static_cast<__nv_bfloat16*>(out), mask, partial, {}};
+           static_cast<__nv_bfloat16*>(out), mask, partial, factor, {}};
   for (int r = 0; r < GVIT_PHILOX_ROUNDS; ++r) {
     P.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
     P.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
@@ -480,8 +524,8 @@ static int fused_linear_launch(const void* x, const void* w, const void* bias, i
 }
 
 int fc1_gelu_dropout_fwd_tc(const void* x, const void* w, const void* bias, int64_t M, int N, int K, float p, uint64_t seed,
-                            uint64_t offset, const uint64_t* offset_dev, void* u, void* out, uint8_t* mask, cudaStream_t st) {
-  return fused_linear_launch<0>(x, w, bias, M, N, K, p, seed, offset, offset_dev, u, out, mask, st);
+                            uint64_t offset, const uint64_t* offset_dev, int save_mode, void* u, void* out, uint8_t* mask, cudaStream_t st) {
+  return fused_linear_launch<0>(x, w, bias, M, N, K, p, seed, offset, offset_dev, u, out, mask, st, nullptr, save_mode);
 }
 
 int linear_dropout_residual_fwd_tc(const void* x, const void* w, const void* bias, const void* resid, int64_t M, int N, int K, float p,
@@ -496,9 +540,9 @@ int linear_dropout_residual_fwd_tc(const void* x, const void* w, const void* bia
 int64_t fc2_bwd_partial_rows(int64_t M) { return (((M + BM - 1) / BM + CL - 1) / CL) * CL * 4; }
 
 int linear_gelu_dropout_bwd_tc(const void* dout, const void* w2, const void* u, const uint8_t* mask, int64_t M, int N, int K, float p,
-                               void* du, float* colsum_out, float* partial_ws, cudaStream_t st) {
+                               int saved_mode, void* du, float* colsum_out, float* partial_ws, cudaStream_t st) {
   int rc = fused_linear_launch<2>(dout, w2, nullptr, M, N, K, p, 0, 0, nullptr, const_cast<void*>(u), du, const_cast<uint8_t*>(mask), st,
-                                  partial_ws);
+                                  partial_ws, saved_mode);
   if (rc != GVIT_OK) return rc;
   partial_colsum_kernel<<<(N + 31) / 32, 256, 0, st>>>(partial_ws, (int)fc2_bwd_partial_rows(M), N, colsum_out);
   GVIT_CHECK_LAUNCH();

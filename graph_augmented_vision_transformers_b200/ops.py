@@ -610,7 +610,7 @@ class _LinearGeluDropout(torch.autograd.Function):
             out = torch.empty_like(u)
             mask = torch.empty(M * N // 8, dtype=torch.uint8, device=x.device) if p > 0 else None
             _call("gvit_linear_gelu_dropout_fwd", _ptr(x), _ptr(weight), _ptr(_shadow(bias, x.dtype)), M, N, K, float(p),
-                  int(seed), 0, _rng_offset_ptr(), GVIT_BF16, _ptr(u), _ptr(out), _ptr(mask), _stream())
+                  int(seed), 0, _rng_offset_ptr(), GVIT_BF16, 0, _ptr(u), _ptr(out), _ptr(mask), _stream())
         else:
             u = _mm_nt(x, weight, _shadow(bias, x.dtype))
             n = u.numel()
@@ -640,7 +640,7 @@ class _MlpFused(torch.autograd.Function):
     """out = resid + dropout(fc2(dropout(gelu(fc1(x)))))  - the whole Mlp branch of vit.py:88-94,118 as one autograd node, so
     that the backward can run fc2's input-gradient GEMM fused with the GELU / dropout backward and fc1's bias gradient
     (gvit_linear_gelu_dropout_bwd): the (M, 4D) gradient of the hidden activation never makes an HBM round trip.
-    Forward: fused fc1 GEMM (gvit_linear_gelu_dropout_fwd), library fc2 GEMM, gvit_dropout_residual_fwd."""
+    Forward: fused fc1 GEMM (gvit_linear_gelu_dropout_fwd, saving the backward factor), fused fc2 + drop + residual GEMM."""
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, resid, p, seed1, seed2):
@@ -649,11 +649,17 @@ class _MlpFused(torch.autograd.Function):
         Nh, K = w1s.shape
         M = x.numel() // K
         st = _stream()
-        u = torch.empty(x.shape[:-1] + (Nh,), dtype=x.dtype, device=x.device)
-        h = torch.empty_like(u)
-        mask1 = torch.empty(M * Nh // 8, dtype=torch.uint8, device=x.device) if p > 0 else None
+        # what the backward needs of fc1 + GELU + drop is the FACTOR keep * gelu'(u) / (1 - p): the fused kernel writes it in
+        # place of the pre-activation (no keep mask), so that the backward GEMM's epilogue is one multiply; nothing at all
+        # is saved when no gradient is wanted (inference: one (M, 4D) store less per layer)
+        want_grad = any(ctx.needs_input_grad[:5])
+        mode = 1 if _MLP_FACTOR["on"] else 0
+        h = torch.empty(x.shape[:-1] + (Nh,), dtype=x.dtype, device=x.device)
+        u = torch.empty_like(h) if want_grad else None
+        mask1 = torch.empty(M * Nh // 8, dtype=torch.uint8, device=x.device) if (p > 0 and want_grad and mode == 0) else None
         _call("gvit_linear_gelu_dropout_fwd", _ptr(x), _ptr(w1s), _ptr(_shadow(b1, x.dtype)), M, Nh, K, float(p), int(seed1), 0,
-              _rng_offset_ptr(), GVIT_BF16, _ptr(u), _ptr(h), _ptr(mask1), st)
+              _rng_offset_ptr(), GVIT_BF16, mode, _ptr(u), _ptr(h), _ptr(mask1), st)
+        ctx.mode = mode
         D2 = w2s.shape[0]
         if resid is not None and Nh <= _FUSED_RESID_MAX_K and fused_fc1_available(D2, Nh):
             # fc2 + drop + residual add (vit.py:93-94,118) as ONE tcgen05 GEMM: bias, keep mask and the add run in its epilogue
@@ -699,7 +705,7 @@ class _MlpFused(torch.autograd.Function):
         db1 = torch.empty(Nh, dtype=torch.float32, device=dout.device)
         rows = _lib.load().gvit_linear_gelu_dropout_bwd_ws_rows(M)
         part = torch.empty(rows * Nh, dtype=torch.float32, device=dout.device)
-        _call("gvit_linear_gelu_dropout_bwd", _ptr(dy2), _ptr(w2s), _ptr(u), _ptr(mask1), M, Nh, D2, float(ctx.p), GVIT_BF16,
+        _call("gvit_linear_gelu_dropout_bwd", _ptr(dy2), _ptr(w2s), _ptr(u), _ptr(mask1), M, Nh, D2, float(ctx.p), GVIT_BF16, ctx.mode,
               _ptr(du), _ptr(db1), _ptr(part), st)
         du2 = du.view(M, Nh)
         dx = _mm_nn(du2, w1s).view(x.shape) if ctx.needs_input_grad[0] else None
@@ -709,6 +715,7 @@ class _MlpFused(torch.autograd.Function):
                 (dout if ctx.has_resid else None), None, None, None)
 
 
+_MLP_FACTOR = {"on": os.environ.get("GVIT_MLP_FACTOR", "1") != "0"}   # GVIT_MLP_FACTOR=0: save the pre-activation + keep mask (A/B switch)
 _MLP_FUSED = {"on": os.environ.get("GVIT_MLP_FUSED", "1") != "0"}      # GVIT_MLP_FUSED=0: two-op composition (A/B switch)
 
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GVIT_ABI_VERSION 17
+#define GVIT_ABI_VERSION 18
 #if defined(__GNUC__)
 #define GVIT_API __attribute__((visibility("default")))
 #else
@@ -211,9 +211,13 @@ GVIT_API int gvit_gelu_dropout_bwd(const void* dout, const void* u, const uint8_
  * x (M,K) and w (N,K) row-major bf16 (w is nn.Linear's weight), bias (N) bf16 or NULL, u / out (M,N) bf16,
  * keep_mask M*N/8 bytes (8-byte aligned; NULL when p == 0).  bf16 only, N % 256 == 0, K % 64 == 0: other shapes return
  * GVIT_ERR_UNSUPPORTED (compose a library GEMM with gvit_gelu_dropout_fwd); gvit_describe_path("fc1", dtype, N, K) tells. */
+/* save_mode selects what the backward gets: 0 = the pre-activation u and the keep mask (what gvit_gelu_dropout_bwd and
+ * gvit_linear_gelu_dropout_bwd(saved_mode 0) consume); 1 = `u` receives the BACKWARD FACTOR keep * gelu'(u) / (1 - p)
+ * (bf16) instead, computed from the same Phi(u) / exp(-u^2/2) evaluation as the activation - the backward GEMM's epilogue
+ * is then one multiply (keep_mask may be NULL).  u == NULL saves nothing (inference). */
 GVIT_API int gvit_linear_gelu_dropout_fwd(const void* x, const void* w, const void* bias, int64_t M, int N, int K, float p, uint64_t seed,
-                                 uint64_t offset, const uint64_t* offset_dev, int dtype, void* u, void* out, uint8_t* keep_mask,
-                                 void* stream);
+                                 uint64_t offset, const uint64_t* offset_dev, int dtype, int save_mode, void* u, void* out,
+                                 uint8_t* keep_mask, void* stream);
 
 /* Same GEMM with the other epilogue of the block: out = resid + dropout(x W^T + bias, p) - proj + proj_drop + the residual
  * add of vit.py:70-71,117 (and fc2 + drop + residual, vit.py:93-94,118) in one kernel.  resid / out (M,N) of resid_dtype
@@ -231,7 +235,9 @@ GVIT_API int gvit_linear_dropout_residual_fwd(const void* x, const void* w, cons
  * partial_ws: gvit_linear_gelu_dropout_bwd_ws_rows(M) * N floats.  bf16 only, N % 256 == 0, K % 64 == 0. */
 GVIT_API int64_t gvit_linear_gelu_dropout_bwd_ws_rows(int64_t M);
 GVIT_API int gvit_linear_gelu_dropout_bwd(const void* dout, const void* w2, const void* u, const uint8_t* keep_mask, int64_t M, int N, int K,
-                                 float p, int dtype, void* du, float* colsum_out, float* partial_ws, void* stream);
+                                 float p, int dtype, int saved_mode, void* du, float* colsum_out, float* partial_ws, void* stream);
+/* saved_mode 1: `u` is the backward factor written by gvit_linear_gelu_dropout_fwd(save_mode 1) and du = (dout W2) * u;
+ * keep_mask is not read. */
 
 /* ---- a1 / f1: the Linear GEMMs themselves (vit.py:59 qkv, :93 fc2, :28 patch projection, and the autograd of every
  * nn.Linear of the block): out (M,N) = op(a) op(b) [+ bias] as ONE persistent 2-SM tcgen05 kernel - 256 x 256 tiles per

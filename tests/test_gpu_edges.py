@@ -348,7 +348,7 @@ def test_fused_fc2_dgrad_gelu_backward_kernel(M, N, K, p):
     db = torch.empty(N, device=DEV)
     rows = _lib.load().gvit_linear_gelu_dropout_bwd_ws_rows(M)
     part = torch.empty(rows * N, device=DEV)
-    _call("gvit_linear_gelu_dropout_bwd", _ptr(dy), _ptr(w2), _ptr(u), _ptr(mask), M, N, K, float(p), GVIT_BF16, _ptr(du), _ptr(db),
+    _call("gvit_linear_gelu_dropout_bwd", _ptr(dy), _ptr(w2), _ptr(u), _ptr(mask), M, N, K, float(p), GVIT_BF16, 0, _ptr(du), _ptr(db),
           _ptr(part), _stream())
     dh = dy @ w2                                                               # (M, N) bf16, what the unfused path stores
     du_ref = torch.empty_like(du)
@@ -362,9 +362,50 @@ def test_fused_fc2_dgrad_gelu_backward_kernel(M, N, K, p):
     assert rel_err(db, du.float().sum(0)) < 1e-4                               # the bias gradient sums the values as stored
     assert rel_err(db, db_ref) < TOL_BF16
     db2 = torch.empty(N, device=DEV)
-    _call("gvit_linear_gelu_dropout_bwd", _ptr(dy), _ptr(w2), _ptr(u), _ptr(mask), M, N, K, float(p), GVIT_BF16, _ptr(du_ref), _ptr(db2),
+    _call("gvit_linear_gelu_dropout_bwd", _ptr(dy), _ptr(w2), _ptr(u), _ptr(mask), M, N, K, float(p), GVIT_BF16, 0, _ptr(du_ref), _ptr(db2),
           _ptr(part), _stream())
     assert torch.equal(db, db2) and torch.equal(du, du_ref)                    # deterministic
+
+
+@pytest.mark.parametrize("M,N,K,p", [(4 * 197, 3072, 768, 0.1), (130, 256, 64, 0.25), (300, 512, 128, 0.0)])
+def test_fused_fc1_saved_backward_factor(M, N, K, p):
+    """f1 - save_mode 1 of gvit_linear_gelu_dropout_fwd: `u` receives keep * gelu'(u) / (1 - p) instead of the pre-activation
+    (same activation output, same keep decisions as save_mode 0), and gvit_linear_gelu_dropout_bwd(saved_mode 1) - one
+    multiply in its epilogue - gives the gradient of the save_mode 0 pair; u == NULL saves nothing."""
+    from graph_augmented_vision_transformers_b200 import _lib
+    from graph_augmented_vision_transformers_b200.ops import _call, _ptr, _stream, GVIT_BF16
+    g = torch.Generator(device=DEV).manual_seed(M + N + 11)
+    x = torch.randn(M, K, generator=g, device=DEV).bfloat16()
+    w = (torch.randn(N, K, generator=g, device=DEV) * K ** -0.5).bfloat16()
+    b = torch.randn(N, generator=g, device=DEV).bfloat16()
+    u0, o0, f1, o1, o2 = (torch.empty(M, N, device=DEV, dtype=torch.bfloat16) for _ in range(5))
+    mask = torch.empty(M * N // 8, dtype=torch.uint8, device=DEV) if p > 0 else None
+    st = _stream()
+    _call("gvit_linear_gelu_dropout_fwd", _ptr(x), _ptr(w), _ptr(b), M, N, K, float(p), 77, 0, None, GVIT_BF16, 0, _ptr(u0), _ptr(o0), _ptr(mask), st)
+    _call("gvit_linear_gelu_dropout_fwd", _ptr(x), _ptr(w), _ptr(b), M, N, K, float(p), 77, 0, None, GVIT_BF16, 1, _ptr(f1), _ptr(o1), None, st)
+    _call("gvit_linear_gelu_dropout_fwd", _ptr(x), _ptr(w), _ptr(b), M, N, K, float(p), 77, 0, None, GVIT_BF16, 1, None, _ptr(o2), None, st)
+    assert torch.equal(o0, o1) and torch.equal(o0, o2)                         # the activation does not depend on what is saved
+    uf = u0.float()
+    gprime = 0.5 * (1 + torch.erf(uf / 2 ** 0.5)) + uf * torch.exp(-0.5 * uf * uf) / (2 * torch.pi) ** 0.5
+    if p > 0:
+        bits = torch.from_numpy(__import__("numpy").unpackbits(mask.cpu().numpy(), bitorder="little")).to(DEV).view(M, N).float()
+    else:
+        bits = torch.ones(M, N, device=DEV)
+    want = gprime * bits / (1 - p)
+    assert rel_err(f1, want) < TOL_BF16 / 2
+    assert ((f1 == 0) == (want.bfloat16() == 0)).float().mean() > 0.999
+    # backward: (dy W2) * factor against the save_mode 0 kernel on (u, mask)
+    dy = torch.randn(M, K, generator=g, device=DEV).bfloat16()
+    w2 = (torch.randn(K, N, generator=g, device=DEV) * K ** -0.5).bfloat16()
+    rows = _lib.load().gvit_linear_gelu_dropout_bwd_ws_rows(M)
+    part = torch.empty(rows * N, device=DEV)
+    du0, du1 = torch.empty_like(u0), torch.empty_like(u0)
+    db0, db1 = torch.empty(N, device=DEV), torch.empty(N, device=DEV)
+    _call("gvit_linear_gelu_dropout_bwd", _ptr(dy), _ptr(w2), _ptr(u0), _ptr(mask), M, N, K, float(p), GVIT_BF16, 0, _ptr(du0), _ptr(db0), _ptr(part), st)
+    _call("gvit_linear_gelu_dropout_bwd", _ptr(dy), _ptr(w2), _ptr(f1), None, M, N, K, float(p), GVIT_BF16, 1, _ptr(du1), _ptr(db1), _ptr(part), st)
+    assert rel_err(du1, du0) < TOL_BF16                                        # the factor is rounded to bf16 once more
+    assert float((du1.float() - du0.float()).abs().mean() / du0.float().abs().mean()) < 6e-3
+    assert rel_err(db1, du1.float().sum(0)) < 1e-4 and rel_err(db1, db0) < TOL_BF16
 
 
 @pytest.mark.parametrize("p", [0.0, 0.2])
