@@ -8,10 +8,8 @@
 // A [128][64] bf16 tile (128-byte rows, 128B swizzle) is used K-major for Q and K (K = head dim) and
 // MN-major for V (K = keys), so no transpose is ever materialised.
 //
-// Forward (one CTA per 128-query tile x head x image, 2 CTAs/SM):
-//   for each 128-key block j:  S_j = Q K_j^T  (tcgen05.mma -> TMEM cols [0,128))
-//     softmax warps (thread <-> query row = TMEM lane): row max, p = exp2(s*c - m), bf16 P_j -> smem
-//     O_j = P_j V_j (tcgen05.mma -> TMEM cols [128,192)), folded into fp32 registers with the online rescale.
+// Forward: N <= 256 below (attn_fwd_tc2_kernel: a whole head per work item, no online rescale); N > 256 in
+//   attn_fwd_long_tc.cu (key blocks + online softmax).
 // Backward (one CTA per head x image, N <= 256), key-major so every transposed product is a plain
 //   K-major/MN-major operand:  S^T = K Q^T, dP^T = V dO^T  -> threads form P^T, dS^T (and dS, transposed
 //   through shared memory) -> dV += P^T dO, dK += dS^T Q, dQ += dS K, all accumulated in TMEM.
@@ -31,7 +29,6 @@ using namespace tc;
 
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 constexpr int TILE_BYTES = 128 * 128;   // [128 rows][64 bf16]
-constexpr int THREADS = 192;
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -55,43 +52,6 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
-// write 32 consecutive bf16 (columns c0..c0+31 of row `row`) of a K-major operand made of [128][64] blocks
-__device__ __forceinline__ void store_row32(uint8_t* tile, int row, int c0, const float (&p)[32]) {
-  uint8_t* blk = tile + (c0 >> 6) * TILE_BYTES;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 w;
-    w.x = pack_bf16(p[8 * q + 0], p[8 * q + 1]);
-    w.y = pack_bf16(p[8 * q + 2], p[8 * q + 3]);
-    w.z = pack_bf16(p[8 * q + 4], p[8 * q + 5]);
-    w.w = pack_bf16(p[8 * q + 6], p[8 * q + 7]);
-    *reinterpret_cast<uint4*>(blk + swz128(row, (c0 & 63) + 8 * q)) = w;
-  }
-}
-__device__ __forceinline__ void store_out64(__nv_bfloat16* dst, const float (&o)[64], float mul) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    uint4 w;
-    w.x = pack_bf16(o[8 * q + 0] * mul, o[8 * q + 1] * mul);
-    w.y = pack_bf16(o[8 * q + 2] * mul, o[8 * q + 3] * mul);
-    w.z = pack_bf16(o[8 * q + 4] * mul, o[8 * q + 5] * mul);
-    w.w = pack_bf16(o[8 * q + 6] * mul, o[8 * q + 7] * mul);
-    *reinterpret_cast<uint4*>(dst + 8 * q) = w;
-  }
-}
-
-__device__ __forceinline__ void store_out32(__nv_bfloat16* dst, const float (&o)[32], float mul) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 w;
-    w.x = pack_bf16(o[8 * q + 0] * mul, o[8 * q + 1] * mul);
-    w.y = pack_bf16(o[8 * q + 2] * mul, o[8 * q + 3] * mul);
-    w.z = pack_bf16(o[8 * q + 4] * mul, o[8 * q + 5] * mul);
-    w.w = pack_bf16(o[8 * q + 6] * mul, o[8 * q + 7] * mul);
-    *reinterpret_cast<uint4*>(dst + 8 * q) = w;
-  }
-}
-
 // 64 fp32 -> bf16 into row `row` of a swizzled [128][64] staging tile (the layout a SWIZZLE_128B TMA store reads)
 __device__ __forceinline__ void stage_out64(uint8_t* tile, int row, const float (&a)[32], const float (&b)[32], float mul) {
 #pragma unroll
@@ -108,148 +68,6 @@ __device__ __forceinline__ void stage_out64(uint8_t* tile, int row, const float 
     w.w = pack_bf16(b[8 * q + 6] * mul, b[8 * q + 7] * mul);
     *reinterpret_cast<uint4*>(tile + swz128(row, 32 + 8 * q)) = w;
   }
-}
-
-// =================================================================================================
-// forward
-// =================================================================================================
-struct __align__(8) FwdCtrl {
-  uint64_t q_full, kv_full[2], kv_empty[2], s_full, p_full, o_full;
-  uint32_t tmem_base;
-};
-constexpr size_t FWD_SMEM = 1024 + 7 * TILE_BYTES + sizeof(FwdCtrl);   // Q, K x2, V x2, P x2 (two 64-key blocks)
-
-__global__ void __launch_bounds__(THREADS, 2) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, int N,
-                                                                 int H, float scale, __nv_bfloat16* __restrict__ out,
-                                                                 float* __restrict__ lse) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];   // no static __shared__ in these kernels: base is 1024-aligned
-  uint8_t* sm = smem_raw;   // NOT rounded through an integer: that made every access a generic LD/ST instead of LDS/STS
-  if ((smem_u32(sm) & 1023u) != 0) __trap();
-  uint8_t* sQ = sm;
-  uint8_t* sK = sm + TILE_BYTES;          // 2 stages
-  uint8_t* sV = sm + 3 * TILE_BYTES;      // 2 stages
-  uint8_t* sP = sm + 5 * TILE_BYTES;      // [128 rows][128 keys] as two 64-key blocks
-  FwdCtrl* ctl = reinterpret_cast<FwdCtrl*>(sm + 7 * TILE_BYTES);
-
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role id
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int nblk = (N + 127) / 128;
-
-  if (warp == 4 && lane == 0) {
-    prefetch_tmap(&tm_qkv);
-    mbar_init(&ctl->q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&ctl->kv_full[s], 1); mbar_init(&ctl->kv_empty[s], 1); }
-    mbar_init(&ctl->s_full, 1);
-    mbar_init(&ctl->p_full, 128);
-    mbar_init(&ctl->o_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == 5) tmem_alloc(&ctl->tmem_base, 256);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
-  const uint32_t tS = tmem, tO = tmem + 128;
-
-  if (warp == 4) {
-    if (elect_one()) {   // ONE elected thread runs the whole role loop (see tc.cuh)
-      mbar_expect_tx(&ctl->q_full, TILE_BYTES);
-      tma_load_3d(sQ, &tm_qkv, h * 64, q0, b, &ctl->q_full);
-      for (int j = 0; j < nblk; ++j) {
-        const int s = j & 1;
-        mbar_wait(&ctl->kv_empty[s], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&ctl->kv_full[s], 2 * TILE_BYTES);
-        tma_load_3d(sK + s * TILE_BYTES, &tm_qkv, (H + h) * 64, j * 128, b, &ctl->kv_full[s]);
-        tma_load_3d(sV + s * TILE_BYTES, &tm_qkv, (2 * H + h) * 64, j * 128, b, &ctl->kv_full[s]);
-      }
-    }
-  } else if (warp == 5) {
-    if (elect_one()) {   // ONE elected thread runs the whole role loop (see tc.cuh)
-      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
-      auto issue_s = [&](int j) {
-        const int s = j & 1;
-        const int nj = (min(128, N - j * 128) + 15) & ~15;
-        mbar_wait(&ctl->kv_full[s], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t aK = smem_u32(sK + s * TILE_BYTES);
-        const uint32_t idesc = make_idesc(128, nj, false, false);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) umma_ss(tS, make_sdesc(aQ + kk * 32), make_sdesc(aK + kk * 32), idesc, kk > 0);
-        umma_commit(&ctl->s_full);
-      };
-      mbar_wait(&ctl->q_full, 0);
-      issue_s(0);
-      for (int j = 0; j < nblk; ++j) {
-        const int s = j & 1;
-        const int nj = (min(128, N - j * 128) + 15) & ~15;
-        mbar_wait(&ctl->p_full, j & 1);      // P_j in smem; S_j and O_{j-1} fully read by the softmax warps
-        tc_fence_after();
-        if (j + 1 < nblk) issue_s(j + 1);    // next scores overlap this block's P.V
-        const uint32_t aV = smem_u32(sV + s * TILE_BYTES);
-        const uint32_t idesc = make_idesc(128, 64, false, true);
-        for (int ks = 0; ks < nj / 16; ++ks)
-          umma_ss(tO, make_sdesc(aP + (ks >> 2) * TILE_BYTES + (ks & 3) * 32), make_sdesc(aV + ks * 2048), idesc, ks > 0);
-        umma_commit(&ctl->o_full);
-        umma_commit(&ctl->kv_empty[s]);
-      }
-    }
-  } else {
-    const int r = warp * 32 + lane;                 // query row inside the tile == TMEM lane
-    const uint32_t lS = tmem_lane_base(tS, warp), lO = tmem_lane_base(tO, warp);
-    const float sl2 = scale * LOG2E;
-    float m_run = -1e30f, l_run = 0.f;
-    float o[64];
-#pragma unroll
-    for (int d = 0; d < 64; ++d) o[d] = 0.f;
-    for (int j = 0; j < nblk; ++j) {
-      const int len = min(128, N - j * 128);
-      const int nj = (len + 15) & ~15;
-      mbar_wait(&ctl->s_full, j & 1);
-      tc_fence_after();
-      float mx = -1e30f;
-      for (int c0 = 0; c0 < nj; c0 += 32) {
-        float v[32];
-        tmem_ld32(lS + c0, v);
-#pragma unroll
-        for (int t = 0; t < 32; ++t) mx = (c0 + t < len) ? fmaxf(mx, v[t]) : mx;
-      }
-      const float m_new = fmaxf(m_run, mx * sl2);
-      float l_blk = 0.f;
-      for (int c0 = 0; c0 < nj; c0 += 32) {
-        float v[32];
-        tmem_ld32(lS + c0, v);
-#pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          v[t] = (c0 + t < len) ? ex2(fmaf(v[t], sl2, -m_new)) : 0.f;
-          l_blk += v[t];
-        }
-        store_row32(sP, r, c0, v);
-      }
-      fence_async_smem();
-      tc_fence_before();
-      mbar_arrive(&ctl->p_full);
-      const float corr = ex2(m_run - m_new);
-      l_run = l_run * corr + l_blk;
-      m_run = m_new;
-      mbar_wait(&ctl->o_full, j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int hlf = 0; hlf < 2; ++hlf) {
-        float v[32];
-        tmem_ld32(lO + hlf * 32, v);
-#pragma unroll
-        for (int t = 0; t < 32; ++t) o[hlf * 32 + t] = fmaf(o[hlf * 32 + t], corr, v[t]);
-      }
-    }
-    const int q = q0 + r;
-    if (q < N) {
-      store_out64(out + (((int64_t)b * N + q) * H + h) * 64, o, 1.0f / l_run);
-      lse[((int64_t)b * H + h) * N + q] = (m_run + log2f(l_run)) * LN2;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, 256);
 }
 
 // =================================================================================================
@@ -934,14 +752,7 @@ int attn_fwd_tc(const void* qkv, int B, int N, int H, float scale, void* out, fl
     GVIT_CHECK_LAUNCH();
     return GVIT_OK;
   }
-  // N > 256: the persistent key-block kernel (attn_fwd_long_tc.cu); GVIT_ATTN_FWD_LONG_V1=1 keeps the first kernel (A/B switch)
-  static const bool v1 = getenv("GVIT_ATTN_FWD_LONG_V1") != nullptr;
-  if (!v1) return attn_fwd_long_tc(qkv, B, N, H, scale, out, lse, st);
-  GVIT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));
-  dim3 grid((N + 127) / 128, H, B);
-  attn_fwd_tc_kernel<<<grid, THREADS, FWD_SMEM, st>>>(tm, N, H, scale, static_cast<__nv_bfloat16*>(out), lse);
-  GVIT_CHECK_LAUNCH();
-  return GVIT_OK;
+  return attn_fwd_long_tc(qkv, B, N, H, scale, out, lse, st);   // N > 256: the persistent key-block kernel (attn_fwd_long_tc.cu)
 }
 
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, int B, int N, int H, float scale,

@@ -841,6 +841,10 @@ bool graph_bwd_tc_supported(int Np, int D, int k) {
 
 int graph_bwd_tc(const Tokens& t, int k, const int32_t* idx, const float* vals, const float* w, const float* rnorm,
                  const void* dz, int64_t dz_batch_stride, float* dvals, void* dp, cudaStream_t st) {
+  // 128 < Np <= 256: one CTA pair per image (graph_bwd_pair_tc.cu); GVIT_GRAPH_BWD_NOPAIR=1 keeps the one-CTA kernel (A/B switch)
+  static const bool nopair = getenv("GVIT_GRAPH_BWD_NOPAIR") != nullptr;
+  if (!nopair && graph_bwd_pair_supported(t.Np, t.D, k))
+    return graph_bwd_pair_tc(t, k, idx, vals, w, rnorm, dz, dz_batch_stride, dvals, dp, st);
   const int NT = (t.Np + 15) & ~15;
   CUtensorMap tm_dz, tm_p;
   int rc = make_tmap_bf16_3d(&tm_dz, dz, t.D, t.Np, t.B, t.D, (uint64_t)dz_batch_stride, NT);

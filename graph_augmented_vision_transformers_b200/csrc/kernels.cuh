@@ -42,6 +42,9 @@ int agg_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, c
 bool graph_bwd_tc_supported(int Np, int D, int k);
 int graph_bwd_tc(const Tokens& p, int k, const int32_t* idx, const float* vals, const float* w, const float* rnorm,
                  const void* dz, int64_t dz_batch_stride, float* dvals, void* dp, cudaStream_t st);
+bool graph_bwd_pair_supported(int Np, int D, int k);   // one CTA pair per image (graph_bwd_pair_tc.cu): 128 < Np <= 256, D % 128 == 0
+int graph_bwd_pair_tc(const Tokens& p, int k, const int32_t* idx, const float* vals, const float* w, const float* rnorm,
+                      const void* dz, int64_t dz_batch_stride, float* dvals, void* dp, cudaStream_t st);
 bool attn_fwd_tc_supported(int N, int dh);
 bool attn_bwd_tc_supported(int N, int dh);
 int attn_fwd_tc(const void* qkv, int B, int N, int H, float scale, void* out, float* lse, cudaStream_t st);
