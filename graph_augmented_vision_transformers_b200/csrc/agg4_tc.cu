@@ -48,7 +48,7 @@ constexpr int WSTAGE = 4 * 1024;            // per-warp staging ([32 rows][128 B
 constexpr int T_OUT = 384;                  // first OUT chunk buffer / odd Z staging
 
 struct __align__(8) Ctrl {
-  uint64_t full[NSLOT], empty[NSLOT], a_ready, a_free, zs_full[2], conv_done[2], conv_loc[2], out_full[2], out_free[2];
+  uint64_t full[NSLOT], empty[NSLOT], a_ready, a_free, zs_full[2], conv_done[2], conv_loc[2], out_full, out_free;
   uint32_t tmem_base;
   __align__(16) __nv_bfloat16 bias[768];
 };
@@ -89,12 +89,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
   Ctrl* ctl = reinterpret_cast<Ctrl*>(sStg + 8 * WSTAGE);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  GVIT_TRACE_DECL
   const int rank = (int)cluster_ctarank();
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
   const int D = P.D, NT = P.NT;
-  const int nchunk = D / 64;                // 64-feature output chunks
+  const int nchunk = D / 128;               // 128-feature output chunks (64 W rows per CTA)
   const int nstep = D / 128;                // Z steps of 128 features (64 per CTA)
-  const int npiece = (D + 511) / 512;       // W pieces of (up to) 512 reduction columns per output chunk
+  const int npiece = (D + 255) / 256;       // W pieces of (up to) 256 reduction columns per output chunk: 4 boxes of [64][64]
 
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tm_tok);
@@ -104,9 +105,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
       mbar_init(&ctl->zs_full[s], 1);
       mbar_init(&ctl->conv_done[s], 8);     // 4 warps of the owning warpgroup in each CTA
       mbar_init(&ctl->conv_loc[s], 4);
-      mbar_init(&ctl->out_full[s], 1);
-      mbar_init(&ctl->out_free[s], 8);
     }
+    mbar_init(&ctl->out_full, 1);
+    mbar_init(&ctl->out_free, 16);          // leader's: the 8 row warps of each CTA have read the chunk out of TMEM
     mbar_init(&ctl->a_ready, 8);            // warpgroup 0 of each CTA
     mbar_init(&ctl->a_free, 1);
     fence_mbar_init();
@@ -129,15 +130,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
           if (rank == 0) mbar_expect_tx(&ctl->full[sl], (uint32_t)(2 * NT * 128));
           tma_load_3d_2sm(sRing + sl * SLOT, &tm_tok, (2 * t + rank) * 64, 0, b, mapa_u32(smem_u32(&ctl->full[sl]), 0));
         }
-        for (int n = 0; n < nchunk; ++n) {                             // W rows [64 n + 32 rank, + 32), pieces of <= 512 columns
+        for (int n = 0; n < nchunk; ++n) {                             // W rows [128 n + 64 rank, + 64), pieces of <= 256 columns
           for (int p = 0; p < npiece; ++p, ++c) {
             const uint32_t sl = c % NSLOT;
-            const int nbox = min(8, (D - p * 512) / 64);
+            const int nbox = min(4, (D - p * 256) / 64);
             mbar_wait(&ctl->empty[sl], ((c / NSLOT) & 1) ^ 1);
-            if (rank == 0) mbar_expect_tx(&ctl->full[sl], (uint32_t)(2 * nbox * 4096));
+            if (rank == 0) mbar_expect_tx(&ctl->full[sl], (uint32_t)(2 * nbox * 8192));
             const uint32_t fullL = mapa_u32(smem_u32(&ctl->full[sl]), 0);
             for (int j = 0; j < nbox; ++j)
-              tma_load_3d_2sm(sRing + sl * SLOT + j * 4096, &tm_w, p * 512 + j * 64, n * 64 + rank * 32, 0, fullL);
+              tma_load_3d_2sm(sRing + sl * SLOT + j * 8192, &tm_w, p * 256 + j * 64, n * 128 + rank * 64, 0, fullL);
           }
         }
       }
@@ -147,23 +148,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
     if (rank == 0 && elect_one()) {
       const uint32_t aA = smem_u32(sA), aR = smem_u32(sRing);
       const uint32_t idesc_z = make_idesc(256, 128, false, true);      // A~ K-major, token slabs MN-major
-      const uint32_t idesc_w = make_idesc(256, 64, false, false);      // Z from TMEM, W piece K-major
+      const uint32_t idesc_w = make_idesc(256, 128, false, false);     // Z from TMEM, W piece K-major (64 rows per CTA)
       uint32_t c = 0;                                                  // ring consume counter
-      uint32_t a_seen = 0, conv_seen[2] = {0, 0}, conv_iss[2] = {0, 0}, free_seen[2] = {0, 0}, out_iss[2] = {0, 0};
+      uint32_t a_seen = 0, conv_seen[2] = {0, 0}, conv_iss[2] = {0, 0}, free_seen = 0, out_iss = 0;
       for (int b = cid; b < P.B; b += ncl) {
         wait_upto(&ctl->a_ready, a_seen, a_seen + 1);                  // both CTAs' adjacency tiles are built
         tc_fence_after();
+        GVIT_TR(1);
         for (int t = 0; t < nstep; ++t) {                              // ---- Z phase
           const int par = t & 1;
           const uint32_t stg = par ? T_OUT : 64 * t;
           wait_upto(&ctl->conv_done[par], conv_seen[par], conv_iss[par]);            // earlier steps of this parity converted
           if (par) {                                                   // odd staging = the OUT buffers of the previous image
-            wait_upto(&ctl->out_free[0], free_seen[0], out_iss[0]);
-            wait_upto(&ctl->out_free[1], free_seen[1], out_iss[1]);
+            wait_upto(&ctl->out_free, free_seen, out_iss);
           }
           const uint32_t sl = c % NSLOT;
+          GVIT_TR(2);
           mbar_wait(&ctl->full[sl], (c / NSLOT) & 1);
           tc_fence_after();
+          GVIT_TR(3);
           const uint32_t aTok = aR + sl * SLOT;
           for (int ks = 0; ks < NT / 16; ++ks)
             umma_ss_2sm(tmem + stg, make_sdesc(aA + (ks >> 2) * TILE + (ks & 3) * 32), make_sdesc(aTok + ks * 2048), idesc_z, ks > 0);
@@ -176,25 +179,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
         wait_upto(&ctl->conv_done[0], conv_seen[0], conv_iss[0]);      // every Z step is packed bf16 in TMEM
         wait_upto(&ctl->conv_done[1], conv_seen[1], conv_iss[1]);
         tc_fence_after();
-        for (int n = 0; n < nchunk; ++n) {                             // ---- projection
-          const int buf = n & 1;
-          wait_upto(&ctl->out_free[buf], free_seen[buf], out_iss[buf]);
+        GVIT_TR(4);
+        for (int n = 0; n < nchunk; ++n) {                             // ---- projection: N = 128 per instruction (a 2-SM MMA
+          wait_upto(&ctl->out_free, free_seen, out_iss);               // takes ~80 cycles whatever its N: 64-wide chunks ran at 40 %)
           tc_fence_after();
+          GVIT_TR(5);
           for (int p = 0; p < npiece; ++p, ++c) {
             const uint32_t sl = c % NSLOT;
-            const int nbox = min(8, (D - p * 512) / 64);
+            const int nbox = min(4, (D - p * 256) / 64);
             mbar_wait(&ctl->full[sl], (c / NSLOT) & 1);
             tc_fence_after();
+            GVIT_TR(6);
             const uint32_t aW = aR + sl * SLOT;
             for (int j = 0; j < nbox; ++j)
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                umma_ts_2sm(tmem + T_OUT + buf * 64, tmem + (p * 512 + j * 64 + kk * 16) / 2, make_sdesc(aW + j * 4096 + kk * 32),
-                            idesc_w, p > 0 || j > 0 || kk > 0);
+                umma_ts_2sm(tmem + T_OUT, tmem + (p * 256 + j * 64 + kk * 16) / 2, make_sdesc(aW + j * 8192 + kk * 32), idesc_w,
+                            p > 0 || j > 0 || kk > 0);
             umma_commit_2sm_mc(&ctl->empty[sl], 3);
           }
-          umma_commit_2sm_mc(&ctl->out_full[buf], 3);
-          ++out_iss[buf];
+          umma_commit_2sm_mc(&ctl->out_full, 3);
+          GVIT_TR(7);
+          ++out_iss;
         }
       }
     }
@@ -210,7 +216,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
     const int ch8 = lane & 7, r8 = lane >> 3;                          // coalesced pattern: 8 lanes per 128-byte row segment
     const uint32_t a_readyL = mapa_u32(smem_u32(&ctl->a_ready), 0);
     const uint32_t conv_doneL = mapa_u32(smem_u32(&ctl->conv_done[g]), 0);      // this warpgroup's parity, in the leader
-    const uint32_t out_freeL = mapa_u32(smem_u32(&ctl->out_free[g]), 0);
+    const uint32_t out_freeL = mapa_u32(smem_u32(&ctl->out_free), 0);
     uint32_t afree_seen = 0, zs_seen = 0, loc_seen = 0, loc_done_other = 0, full_seen = 0;
     // zs_seen / full_seen: completions of zs_full[g] / out_full[g] consumed; loc_seen: completions of the OTHER warpgroup's
     // conv_loc consumed; loc_done_other: how many steps the other warpgroup has had to convert before my next step
@@ -230,7 +236,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
           for (int i = 0; i < 8; ++i) {
             const int r = r8 + 4 * i;
             rr[hh * 8 + i] = make_uint4(0, 0, 0, 0);
-            if (P.resid && n < nchunk && wrow0 + r < P.Np) {
+            if (P.resid && n < D / 64 && wrow0 + r < P.Np) {
               const int64_t e = ((int64_t)b * (P.Np + 1) + 1 + wrow0 + r) * D + n * 64;
               if constexpr (RES32) rr[hh * 8 + i] = *reinterpret_cast<const uint4*>(static_cast<const float*>(P.resid) + e + hh * 32 + ch8 * 4);
               else rr[i] = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(P.resid) + e + ch8 * 8);
@@ -238,7 +244,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
           }
       };
       // ---- G4 + adjacency tile: zero A~, then scatter each row's k softmax weights (bf16) at its neighbour columns
+      GVIT_TR(10);
       if (iter > 0) wait_upto(&ctl->a_free, afree_seen, (uint32_t)iter);           // the previous image's Z MMAs have read A~
+      GVIT_TR(11);
       {
         const uint4 z4 = make_uint4(0, 0, 0, 0);
         for (int i = threadIdx.x; i < A_BYTES / 16; i += 256) reinterpret_cast<uint4*>(sA)[i] = z4;
@@ -272,6 +280,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(a_readyL);
+          GVIT_TR(12);
         } else if (rank == 0) {
           // CLS row: out[b,0,:] = resid[b,0,:] (the graph leaves CLS untouched, section 9 G0), 16 bytes per thread and trip
           constexpr int EPV = RES32 ? 4 : 8;                             // elements per 16-byte vector
@@ -291,13 +300,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
       for (int t = 0; t < nstep; ++t) {
         if ((t & 1) != g) { ++loc_done_other; continue; }                // the other warpgroup's step
         const uint32_t src = tl + ((t & 1) ? T_OUT : 64 * t), dst = tl + 64 * t;
+        GVIT_TR(13);
         mbar_wait(&ctl->zs_full[g], zs_seen & 1);
+        GVIT_TR(14);
         ++zs_seen;
         // the two warpgroups convert strictly in step order: an odd step's bf16 destination is the upper half of the
         // previous (even) step's in-place staging, and taking every completion of the other's barrier in turn keeps the
         // parity waits from ever naming a phase two completions back
         wait_upto(&ctl->conv_loc[g ^ 1], loc_seen, loc_done_other);
         tc_fence_after();
+        GVIT_TR(15);
         for (int h0 = 0; h0 < 128; h0 += 64) {
 #pragma unroll
           for (int cc = 0; cc < 64; cc += 32) {
@@ -323,6 +335,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
               mbar_arrive(&ctl->conv_loc[g]);
               mbar_arrive_cluster(conv_doneL);
             }
+            GVIT_TR(16);
           }
           if (P.z_save) {                                                // coalesced: 4 whole 128-byte row segments per instr
             __syncwarp();
@@ -339,8 +352,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
         }
       }
       // ---- projection epilogue (chunks of parity g): + bias + residual, coalesced through the warp staging
-      for (int n = g; n < nchunk; n += 2) {
-        const int buf = n & 1;
+      // (warpgroup g takes the 64-feature half g of every 128-feature chunk: 64-feature index n = 2 * chunk + g)
+      for (int n = g; n < D / 64; n += 2) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = r8 + 4 * i;
@@ -348,15 +361,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
         }
         if constexpr (!RES32) load_resid(n + 2, rnext);                  // next chunk of this warpgroup: in flight meanwhile
         __syncwarp();
-        mbar_wait(&ctl->out_full[buf], full_seen & 1);
+        GVIT_TR(17);
+        mbar_wait(&ctl->out_full, full_seen & 1);
+        GVIT_TR(18);
         ++full_seen;
         tc_fence_after();
         float v0[32], v1[32];
-        tmem_ld32(tl + T_OUT + buf * 64, v0);
-        tmem_ld32(tl + T_OUT + buf * 64 + 32, v1);
+        tmem_ld32(tl + T_OUT + g * 64, v0);
+        tmem_ld32(tl + T_OUT + g * 64 + 32, v1);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(out_freeL);                   // buf == g
+        if (lane == 0) mbar_arrive_cluster(out_freeL);
+        GVIT_TR(19);
         if constexpr (!RES32) {
           __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(P.out);
 #pragma unroll
@@ -459,6 +475,8 @@ int launch(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const Params& P, 
 
 }  // namespace
 
+GVIT_TRACE_SETTER(gvit_debug_set_trace_agg4)
+
 bool agg4_tc_supported(int Np, int D, int k) {
   return Np >= 16 && Np <= 256 && D >= 128 && D % 128 == 0 && D <= 768 && k <= 16;
 }
@@ -482,7 +500,7 @@ int agg4_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, 
   const __nv_bfloat16* tok = static_cast<const __nv_bfloat16*>(h) + D;   // skip the CLS row (section 9, G0)
   int rc = make_tmap_bf16_3d(&tm_tok, tok, D, Np, B, D, (uint64_t)(Np + 1) * D, P.NT);
   if (rc != GVIT_OK) return rc;
-  rc = make_tmap_bf16_3d(&tm_w, Wg, D, D, 1, D, (uint64_t)D * D, 32);
+  rc = make_tmap_bf16_3d(&tm_w, Wg, D, D, 1, D, (uint64_t)D * D, 64);
   if (rc != GVIT_OK) return rc;
   if (k <= 4) return launch<4>(tm_tok, tm_w, P, res32, st);
   if (k <= 8) return launch<8>(tm_tok, tm_w, P, res32, st);

@@ -88,10 +88,11 @@ int gvit_agg_fwd(const void* h, int B, int Np, int D, int k, int dtype, const in
   GVIT_REQUIRE(!z_save || (z_batch_stride >= (int64_t)Np * D && z_batch_stride % 8 == 0), GVIT_ERR_ALIGN,
                "agg_fwd: z_batch_stride=%lld must be >= Np*D and a multiple of 8", (long long)z_batch_stride);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // GVIT_AGG_PAIR=1: one CTA pair per image with cta_group::2 MMAs (agg4_tc.cu).  Correct, and measured SLOWER than agg3
-  // (0.1425 vs 0.1192 ms at B = 256, profiles/README.md): kept as the A/B evidence for that design, off by default.
-  static const bool use_pair = getenv("GVIT_AGG_PAIR") != nullptr;
-  if (use_pair && agg4_tc_supported(Np, D, k))
+  // Default for D <= 768: one CTA pair per image with cta_group::2 MMAs (agg4_tc.cu): with the projection issued as N = 128
+  // instructions it measured 0.107 ms against 0.119 ms for the one-CTA-per-row-tile kernel (agg3) at B = 256 on the same box
+  // (profiles/README.md).  GVIT_AGG_NOPAIR=1 selects agg3 (A/B switch).
+  static const bool use_pair = getenv("GVIT_AGG_NOPAIR") == nullptr;
+  if (use_pair && Np > 128 && agg4_tc_supported(Np, D, k))                  // one row tile: a pair would idle its second CTA
     return agg4_fwd_tc(h, B, Np, D, k, idx, vals, Wg, bias, resid, resid_dtype, out, w_save, z_save, z_batch_stride, st);
   if (agg3_tc_supported(Np, D, k))
     return agg3_fwd_tc(h, B, Np, D, k, idx, vals, Wg, bias, resid, resid_dtype, out, w_save, z_save, z_batch_stride, st);

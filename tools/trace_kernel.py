@@ -16,7 +16,7 @@ args = ap.parse_args()
 dev = torch.device("cuda", 0)
 lib = _lib.load()
 setter = {"attn_bwd": "gvit_debug_set_trace_attn", "attn_fwd": "gvit_debug_set_trace_attn",
-          "agg_fwd": "gvit_debug_set_trace_agg", "knn_fwd": "gvit_debug_set_trace_knn", "graph_bwd": "gvit_debug_set_trace_graph_bwd_pair"}[args.name]
+          "agg_fwd": "gvit_debug_set_trace_agg" if os.environ.get("GVIT_AGG_NOPAIR") else "gvit_debug_set_trace_agg4", "knn_fwd": "gvit_debug_set_trace_knn", "graph_bwd": "gvit_debug_set_trace_graph_bwd_pair"}[args.name]
 fn = getattr(lib, setter); fn.argtypes = [ctypes.c_void_p, ctypes.c_uint]; fn.restype = ctypes.c_int
 per_warp = 4096
 buf = torch.zeros(16 * per_warp, dtype=torch.int64, device=dev)
