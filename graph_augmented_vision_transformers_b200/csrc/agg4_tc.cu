@@ -48,7 +48,7 @@ constexpr int WSTAGE = 4 * 1024;            // per-warp staging ([32 rows][128 B
 constexpr int T_OUT = 384;                  // first OUT chunk buffer / odd Z staging
 
 struct __align__(8) Ctrl {
-  uint64_t full[NSLOT], empty[NSLOT], a_ready, a_free, zs_full[2], conv_done[2], conv_loc[2], out_full, out_free;
+  uint64_t full[NSLOT], empty[NSLOT], a_ready, a_free, zs_full[2], conv_done[2], out_full, out_free;
   uint32_t tmem_base;
   __align__(16) __nv_bfloat16 bias[768];
 };
@@ -103,8 +103,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&ctl->zs_full[s], 1);
-      mbar_init(&ctl->conv_done[s], 8);     // 4 warps of the owning warpgroup in each CTA
-      mbar_init(&ctl->conv_loc[s], 4);
+      mbar_init(&ctl->conv_done[s], 16);    // the 8 row warps of each CTA
     }
     mbar_init(&ctl->out_full, 1);
     mbar_init(&ctl->out_free, 16);          // leader's: the 8 row warps of each CTA have read the chunk out of TMEM
@@ -150,7 +149,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
       const uint32_t idesc_z = make_idesc(256, 128, false, true);      // A~ K-major, token slabs MN-major
       const uint32_t idesc_w = make_idesc(256, 128, false, false);     // Z from TMEM, W piece K-major (64 rows per CTA)
       uint32_t c = 0;                                                  // ring consume counter
-      uint32_t a_seen = 0, conv_seen[2] = {0, 0}, conv_iss[2] = {0, 0}, free_seen = 0, out_iss = 0;
+      uint32_t a_seen = 0, conv_seen0 = 0, conv_seen1 = 0, conv_iss0 = 0, conv_iss1 = 0, free_seen = 0, out_iss = 0;
       for (int b = cid; b < P.B; b += ncl) {
         wait_upto(&ctl->a_ready, a_seen, a_seen + 1);                  // both CTAs' adjacency tiles are built
         tc_fence_after();
@@ -158,9 +157,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
         for (int t = 0; t < nstep; ++t) {                              // ---- Z phase
           const int par = t & 1;
           const uint32_t stg = par ? T_OUT : 64 * t;
-          wait_upto(&ctl->conv_done[par], conv_seen[par], conv_iss[par]);            // earlier steps of this parity converted
-          if (par) {                                                   // odd staging = the OUT buffers of the previous image
+          if (par) {                                                   // earlier steps of this parity converted; odd staging =
+            wait_upto(&ctl->conv_done[1], conv_seen1, conv_iss1);      // the OUT buffer of the previous image
             wait_upto(&ctl->out_free, free_seen, out_iss);
+          } else {
+            wait_upto(&ctl->conv_done[0], conv_seen0, conv_iss0);
           }
           const uint32_t sl = c % NSLOT;
           GVIT_TR(2);
@@ -172,12 +173,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
             umma_ss_2sm(tmem + stg, make_sdesc(aA + (ks >> 2) * TILE + (ks & 3) * 32), make_sdesc(aTok + ks * 2048), idesc_z, ks > 0);
           umma_commit_2sm_mc(&ctl->zs_full[par], 3);
           umma_commit_2sm_mc(&ctl->empty[sl], 3);
-          ++conv_iss[par];
+          if (par) ++conv_iss1; else ++conv_iss0;
           ++c;
         }
         umma_commit_2sm_mc(&ctl->a_free, 3);                           // the A~ tiles may be rebuilt for the next image
-        wait_upto(&ctl->conv_done[0], conv_seen[0], conv_iss[0]);      // every Z step is packed bf16 in TMEM
-        wait_upto(&ctl->conv_done[1], conv_seen[1], conv_iss[1]);
+        wait_upto(&ctl->conv_done[0], conv_seen0, conv_iss0);          // every Z step is packed bf16 in TMEM
+        wait_upto(&ctl->conv_done[1], conv_seen1, conv_iss1);
         tc_fence_after();
         GVIT_TR(4);
         for (int n = 0; n < nchunk; ++n) {                             // ---- projection: N = 128 per instruction (a 2-SM MMA
@@ -215,17 +216,68 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
     const uint32_t tl = tmem_lane_base(tmem, warp);
     const int ch8 = lane & 7, r8 = lane >> 3;                          // coalesced pattern: 8 lanes per 128-byte row segment
     const uint32_t a_readyL = mapa_u32(smem_u32(&ctl->a_ready), 0);
-    const uint32_t conv_doneL = mapa_u32(smem_u32(&ctl->conv_done[g]), 0);      // this warpgroup's parity, in the leader
+    const uint32_t conv_doneL0 = mapa_u32(smem_u32(&ctl->conv_done[0]), 0), conv_doneL1 = mapa_u32(smem_u32(&ctl->conv_done[1]), 0);   // in the leader
     const uint32_t out_freeL = mapa_u32(smem_u32(&ctl->out_free), 0);
-    uint32_t afree_seen = 0, zs_seen = 0, loc_seen = 0, loc_done_other = 0, full_seen = 0;
-    // zs_seen / full_seen: completions of zs_full[g] / out_full[g] consumed; loc_seen: completions of the OTHER warpgroup's
-    // conv_loc consumed; loc_done_other: how many steps the other warpgroup has had to convert before my next step
+    uint32_t afree_seen = 0, zs_seen0 = 0, zs_seen1 = 0, full_seen = 0;        // completions consumed of a_free / zs_full[parity] / out_full
     {
       const uint4 z4 = make_uint4(0, 0, 0, 0);
       for (int i = threadIdx.x; i < 768 / 8; i += 256)
         reinterpret_cast<uint4*>(ctl->bias)[i] = (P.bias && i < D / 8) ? reinterpret_cast<const uint4*>(P.bias)[i] : z4;
     }
     constexpr int NH = RES32 ? 2 : 1;
+    // ---- G4 + adjacency tile of image bb (the it-th of this pair): zero A~, then scatter each row's k softmax weights (bf16)
+    //      at its neighbour columns.  Runs in the slot where the row warps would otherwise wait for the first projection
+    //      chunk of the PREVIOUS image, so the MMA issuer finds a_ready complete when it gets to the next image.
+    auto build_adj = [&](int bb, int it) {
+      GVIT_TR(10);
+      if (it > 0) wait_upto(&ctl->a_free, afree_seen, (uint32_t)it);     // the previous image's Z MMAs have read A~
+      GVIT_TR(11);
+      const uint4 z4 = make_uint4(0, 0, 0, 0);
+      for (int i = threadIdx.x; i < A_BYTES / 16; i += 256) reinterpret_cast<uint4*>(sA)[i] = z4;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (g == 0) {
+        if (valid) {
+          float w[KT];
+          int nb[KT];
+          float mx = -FLT_MAX, sum = 0.f;
+          const int64_t o = ((int64_t)bb * P.Np + rowg) * P.k;
+#pragma unroll
+          for (int j = 0; j < KT; ++j) {
+            const bool on = j < P.k;
+            nb[j] = on ? P.idx[o + j] : 0;
+            w[j] = on ? P.vals[o + j] : -FLT_MAX;
+            mx = fmaxf(mx, w[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < KT; ++j) { w[j] = j < P.k ? expf(w[j] - mx) : 0.f; sum += w[j]; }
+          const float inv = 1.0f / sum;
+#pragma unroll
+          for (int j = 0; j < KT; ++j) {
+            if (j < P.k) {
+              const float wj = w[j] * inv;
+              if (P.w_save) P.w_save[o + j] = wj;
+              const int cidx = nb[j];
+              *reinterpret_cast<__nv_bfloat16*>(sA + (cidx >> 6) * TILE + swz128(row, cidx & 63) + (cidx & 7) * 2) = __float2bfloat16_rn(wj);
+            }
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(a_readyL);
+        GVIT_TR(12);
+      } else if (rank == 0) {
+        // CLS row: out[bb,0,:] = resid[bb,0,:] (the graph leaves CLS untouched, section 9 G0), 16 bytes per thread and trip
+        constexpr int EPV = RES32 ? 4 : 8;                               // elements per 16-byte vector
+        constexpr int ESZ = RES32 ? 4 : 2;
+        for (int c = row; c < D / EPV; c += 128) {
+          const int64_t o = ((int64_t)bb * (P.Np + 1) * D + c * EPV) * ESZ;
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (P.resid) v = *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(P.resid) + o);
+          *reinterpret_cast<uint4*>(static_cast<uint8_t*>(P.out) + o) = v;
+        }
+      }
+    };
+    if (cid < P.B) build_adj(cid, 0);
     for (int b = cid, iter = 0; b < P.B; b += ncl, ++iter) {
       // residual rows of this warp for output chunk n, coalesced (lane -> rows r8 + 4i, 16-byte chunk ch8)
       // RES32: a 64-feature chunk is 256 bytes per row = two 128-byte halves (32 features each)
@@ -243,114 +295,65 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
             }
           }
       };
-      // ---- G4 + adjacency tile: zero A~, then scatter each row's k softmax weights (bf16) at its neighbour columns
-      GVIT_TR(10);
-      if (iter > 0) wait_upto(&ctl->a_free, afree_seen, (uint32_t)iter);           // the previous image's Z MMAs have read A~
-      GVIT_TR(11);
-      {
-        const uint4 z4 = make_uint4(0, 0, 0, 0);
-        for (int i = threadIdx.x; i < A_BYTES / 16; i += 256) reinterpret_cast<uint4*>(sA)[i] = z4;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (g == 0) {
-          if (valid) {
-            float w[KT];
-            int nb[KT];
-            float mx = -FLT_MAX, sum = 0.f;
-            const int64_t o = ((int64_t)b * P.Np + rowg) * P.k;
-#pragma unroll
-            for (int j = 0; j < KT; ++j) {
-              const bool on = j < P.k;
-              nb[j] = on ? P.idx[o + j] : 0;
-              w[j] = on ? P.vals[o + j] : -FLT_MAX;
-              mx = fmaxf(mx, w[j]);
-            }
-#pragma unroll
-            for (int j = 0; j < KT; ++j) { w[j] = j < P.k ? expf(w[j] - mx) : 0.f; sum += w[j]; }
-            const float inv = 1.0f / sum;
-#pragma unroll
-            for (int j = 0; j < KT; ++j) {
-              if (j < P.k) {
-                const float wj = w[j] * inv;
-                if (P.w_save) P.w_save[o + j] = wj;
-                const int cidx = nb[j];
-                *reinterpret_cast<__nv_bfloat16*>(sA + (cidx >> 6) * TILE + swz128(row, cidx & 63) + (cidx & 7) * 2) = __float2bfloat16_rn(wj);
-              }
-            }
-          }
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(a_readyL);
-          GVIT_TR(12);
-        } else if (rank == 0) {
-          // CLS row: out[b,0,:] = resid[b,0,:] (the graph leaves CLS untouched, section 9 G0), 16 bytes per thread and trip
-          constexpr int EPV = RES32 ? 4 : 8;                             // elements per 16-byte vector
-          constexpr int ESZ = RES32 ? 4 : 2;
-          for (int c = row; c < D / EPV; c += 128) {
-            const int64_t o = ((int64_t)b * (P.Np + 1) * D + c * EPV) * ESZ;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (P.resid) v = *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(P.resid) + o);
-            *reinterpret_cast<uint4*>(static_cast<uint8_t*>(P.out) + o) = v;
-          }
-        }
-      }
       uint4 rnext[8 * NH];
       load_resid(g, rnext);                                              // first chunk of this warpgroup: in flight during Z
-      // ---- Z phase (steps of parity g): fp32 staging -> packed bf16 at TMEM columns [64t, 64t + 64);
-      //      optional copy out for the backward, 64 features at a time through the warp staging
+      // ---- Z phase: BOTH warpgroups convert every step, warpgroup g the 64 staging columns [64 g, 64 g + 64) -> packed bf16
+      //      at TMEM columns [64 t + 32 g, + 32), so a step's conversion takes half as long and overlaps the next step's MMAs;
+      //      optional copy out for the backward (64 features per warpgroup and step) through the warp staging.
+      //      Even steps convert in place: warpgroup 1 writes columns that warpgroup 0 reads, and the next (odd) step's
+      //      destination is the upper half of this staging area, so the two warps that share a TMEM lane quarter meet at a
+      //      64-thread named barrier between their loads and their stores.
       for (int t = 0; t < nstep; ++t) {
-        if ((t & 1) != g) { ++loc_done_other; continue; }                // the other warpgroup's step
-        const uint32_t src = tl + ((t & 1) ? T_OUT : 64 * t), dst = tl + 64 * t;
+        const int par = t & 1;
+        const uint32_t src = tl + (par ? T_OUT : 64 * t) + 64 * g, dst = tl + 64 * t + 32 * g;
         GVIT_TR(13);
-        mbar_wait(&ctl->zs_full[g], zs_seen & 1);
+        mbar_wait(&ctl->zs_full[par], (par ? zs_seen1 : zs_seen0) & 1);
         GVIT_TR(14);
-        ++zs_seen;
-        // the two warpgroups convert strictly in step order: an odd step's bf16 destination is the upper half of the
-        // previous (even) step's in-place staging, and taking every completion of the other's barrier in turn keeps the
-        // parity waits from ever naming a phase two completions back
-        wait_upto(&ctl->conv_loc[g ^ 1], loc_seen, loc_done_other);
+        if (par) ++zs_seen1; else ++zs_seen0;
         tc_fence_after();
+        uint32_t pk0[16], pk1[16];
+        {
+          float v[32];
+          tmem_ld32(src, v);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pk0[e] = pack2(v[2 * e], v[2 * e + 1]);
+          tmem_ld32(src + 32, v);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pk1[e] = pack2(v[2 * e], v[2 * e + 1]);
+        }
+        if (!par) {
+          tc_fence_before();
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + (warp & 3)) : "memory");
+          tc_fence_after();
+        }
         GVIT_TR(15);
-        for (int h0 = 0; h0 < 128; h0 += 64) {
+        tmem_st16(dst, pk0);
+        tmem_st16(dst + 16, pk1);
+        if (P.z_save) {
 #pragma unroll
-          for (int cc = 0; cc < 64; cc += 32) {
-            const int c0 = h0 + cc;
-            float v[32];
-            tmem_ld32(src + c0, v);
-            uint32_t pk[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) pk[e] = pack2(v[2 * e], v[2 * e + 1]);
-            tmem_st16(dst + (c0 >> 1), pk);                             // in place for even t: columns already read
-            if (P.z_save) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<uint4*>(stg + lane * 128 + ((((cc >> 3) + q) ^ (lane & 7)) << 4)) =
-                    make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-            }
-          }
-          if (h0 == 64) {                                                // whole step converted: release it
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              mbar_arrive(&ctl->conv_loc[g]);
-              mbar_arrive_cluster(conv_doneL);
-            }
-            GVIT_TR(16);
-          }
-          if (P.z_save) {                                                // coalesced: 4 whole 128-byte row segments per instr
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = r8 + 4 * i;
-              if (wrow0 + r < P.Np) {
-                const uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4));
-                *reinterpret_cast<uint4*>(P.z_save + (int64_t)b * P.zbs + (int64_t)(wrow0 + r) * D + t * 128 + h0 + ch8 * 8) = v4;
-              }
-            }
-            __syncwarp();
+          for (int q = 0; q < 4; ++q) {
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(pk0[4 * q], pk0[4 * q + 1], pk0[4 * q + 2], pk0[4 * q + 3]);
+            *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + q) ^ (lane & 7)) << 4)) = make_uint4(pk1[4 * q], pk1[4 * q + 1], pk1[4 * q + 2], pk1[4 * q + 3]);
           }
         }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(par ? conv_doneL1 : conv_doneL0);
+        GVIT_TR(16);
+        if (P.z_save) {                                                  // coalesced: 4 whole 128-byte row segments per instr
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = r8 + 4 * i;
+            if (wrow0 + r < P.Np) {
+              const uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4));
+              *reinterpret_cast<uint4*>(P.z_save + (int64_t)b * P.zbs + (int64_t)(wrow0 + r) * D + t * 128 + g * 64 + ch8 * 8) = v4;
+            }
+          }
+          __syncwarp();
+        }
       }
+      if (b + ncl < P.B) build_adj(b + ncl, iter + 1);                   // next image's adjacency tile, under this image's projection
       // ---- projection epilogue (chunks of parity g): + bias + residual, coalesced through the warp staging
       // (warpgroup g takes the 64-feature half g of every 128-feature chunk: 64-feature index n = 2 * chunk + g)
       for (int n = g; n < D / 64; n += 2) {
