@@ -56,6 +56,7 @@ constexpr size_t SMEM_BYTES = A_BYTES + NSLOT * SLOT + 8 * WSTAGE + sizeof(Ctrl)
 
 struct Params {
   int B, Np, D, k, NT;
+  int kvec;                                 // k == KT and idx / vals / w_save 16-byte aligned: whole adjacency rows by vector access
   const int32_t* idx;
   const float* vals;
   const __nv_bfloat16* bias;
@@ -80,7 +81,9 @@ __device__ __forceinline__ void wait_upto(uint64_t* bar, uint32_t& seen, uint32_
 
 template <int KT, bool RES32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_kernel(const __grid_constant__ CUtensorMap tm_tok,
-                                                                                       const __grid_constant__ CUtensorMap tm_w, const Params P) {
+                                                                                       const __grid_constant__ CUtensorMap tm_w,
+                                                                                       const __grid_constant__ CUtensorMap tm_z,
+                                                                                       const __grid_constant__ CUtensorMap tm_out, const Params P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sA = smem_raw;
   if ((smem_u32(sA) & 1023u) != 0) __trap();
@@ -100,6 +103,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tm_tok);
     prefetch_tmap(&tm_w);
+    prefetch_tmap(&tm_z);
+    prefetch_tmap(&tm_out);
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&ctl->zs_full[s], 1);
@@ -235,19 +240,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
       const uint4 z4 = make_uint4(0, 0, 0, 0);
       for (int i = threadIdx.x; i < A_BYTES / 16; i += 256) reinterpret_cast<uint4*>(sA)[i] = z4;
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      GVIT_TR(20);
       if (g == 0) {
         if (valid) {
           float w[KT];
           int nb[KT];
           float mx = -FLT_MAX, sum = 0.f;
           const int64_t o = ((int64_t)bb * P.Np + rowg) * P.k;
+          if (P.kvec) {                                                  // whole rows of 16 / 32 / 64 bytes: vector loads
 #pragma unroll
-          for (int j = 0; j < KT; ++j) {
-            const bool on = j < P.k;
-            nb[j] = on ? P.idx[o + j] : 0;
-            w[j] = on ? P.vals[o + j] : -FLT_MAX;
-            mx = fmaxf(mx, w[j]);
+            for (int j = 0; j < KT; j += 4) {
+              const int4 i4 = *reinterpret_cast<const int4*>(P.idx + o + j);
+              const float4 v4 = *reinterpret_cast<const float4*>(P.vals + o + j);
+              nb[j] = i4.x; nb[j + 1] = i4.y; nb[j + 2] = i4.z; nb[j + 3] = i4.w;
+              w[j] = v4.x; w[j + 1] = v4.y; w[j + 2] = v4.z; w[j + 3] = v4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+              const bool on = j < P.k;
+              nb[j] = on ? P.idx[o + j] : 0;
+              w[j] = on ? P.vals[o + j] : -FLT_MAX;
+            }
           }
+#pragma unroll
+          for (int j = 0; j < KT; ++j) mx = fmaxf(mx, w[j]);
+          GVIT_TR(21);
 #pragma unroll
           for (int j = 0; j < KT; ++j) { w[j] = j < P.k ? expf(w[j] - mx) : 0.f; sum += w[j]; }
           const float inv = 1.0f / sum;
@@ -255,10 +273,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
           for (int j = 0; j < KT; ++j) {
             if (j < P.k) {
               const float wj = w[j] * inv;
-              if (P.w_save) P.w_save[o + j] = wj;
+              w[j] = wj;
+              if (P.w_save && !P.kvec) P.w_save[o + j] = wj;
               const int cidx = nb[j];
               *reinterpret_cast<__nv_bfloat16*>(sA + (cidx >> 6) * TILE + swz128(row, cidx & 63) + (cidx & 7) * 2) = __float2bfloat16_rn(wj);
             }
+          }
+          if (P.w_save && P.kvec) {
+#pragma unroll
+            for (int j = 0; j < KT; j += 4) *reinterpret_cast<float4*>(P.w_save + o + j) = make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
           }
         }
         fence_async_smem();
@@ -296,7 +319,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
           }
       };
       uint4 rnext[8 * NH];
-      load_resid(g, rnext);                                              // first chunk of this warpgroup: in flight during Z
       // ---- Z phase: BOTH warpgroups convert every step, warpgroup g the 64 staging columns [64 g, 64 g + 64) -> packed bf16
       //      at TMEM columns [64 t + 32 g, + 32), so a step's conversion takes half as long and overlaps the next step's MMAs;
       //      optional copy out for the backward (64 features per warpgroup and step) through the warp staging.
@@ -329,7 +351,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
         GVIT_TR(15);
         tmem_st16(dst, pk0);
         tmem_st16(dst + 16, pk1);
-        if (P.z_save) {
+        if (P.z_save) {                                                  // [32 rows][64 features] of this warp -> staging -> one TMA tile
+          if (lane == 0) tma_store_wait_read();                          // store (asynchronous: the warp's own LSU queue stays free)
+          __syncwarp();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(pk0[4 * q], pk0[4 * q + 1], pk0[4 * q + 2], pk0[4 * q + 3]);
@@ -341,22 +365,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(par ? conv_doneL1 : conv_doneL0);
         GVIT_TR(16);
-        if (P.z_save) {                                                  // coalesced: 4 whole 128-byte row segments per instr
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = r8 + 4 * i;
-            if (wrow0 + r < P.Np) {
-              const uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4));
-              *reinterpret_cast<uint4*>(P.z_save + (int64_t)b * P.zbs + (int64_t)(wrow0 + r) * D + t * 128 + g * 64 + ch8 * 8) = v4;
-            }
-          }
+        if (P.z_save) {
+          fence_async_smem();
           __syncwarp();
+          if (lane == 0 && wrow0 < P.Np) {                               // rows >= Np are clipped by the TMA unit
+            tma_store_3d(&tm_z, stg, t * 128 + g * 64, wrow0, b);
+            tma_store_commit();
+          }
         }
       }
+      load_resid(g, rnext);                                              // first chunk of this warpgroup: in flight during the build
       if (b + ncl < P.B) build_adj(b + ncl, iter + 1);                   // next image's adjacency tile, under this image's projection
       // ---- projection epilogue (chunks of parity g): + bias + residual, coalesced through the warp staging
       // (warpgroup g takes the 64-feature half g of every 128-feature chunk: 64-feature index n = 2 * chunk + g)
       for (int n = g; n < D / 64; n += 2) {
+        if (lane == 0) tma_store_wait_read();                            // the staging tile's previous TMA store has read it
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = r8 + 4 * i;
@@ -377,7 +401,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
         if (lane == 0) mbar_arrive_cluster(out_freeL);
         GVIT_TR(19);
         if constexpr (!RES32) {
-          __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(P.out);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const uint32_t off = lane * 128 + ((q ^ (lane & 7)) << 4);
@@ -391,21 +414,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
               oo[e] = pack2(vv[2 * e] + bf_lo(bb[e]) + bf_lo(rr[e]), vv[2 * e + 1] + bf_hi(bb[e]) + bf_hi(rr[e]));
             *reinterpret_cast<uint4*>(stg + off) = make_uint4(oo[0], oo[1], oo[2], oo[3]);
           }
+          fence_async_smem();
           __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = r8 + 4 * i;
-            if (wrow0 + r < P.Np) {
-              const uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4));
-              *reinterpret_cast<uint4*>(outp + ((int64_t)b * (P.Np + 1) + 1 + wrow0 + r) * D + n * 64 + ch8 * 8) = v4;
-            }
+          if (lane == 0 && wrow0 < P.Np) {                               // tm_out starts at token row 1: the CLS row is skipped
+            tma_store_3d(&tm_out, stg, n * 64, wrow0, b);
+            tma_store_commit();
           }
-          __syncwarp();
         } else {
-          float* outp = static_cast<float*>(P.out);
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {                               // 32 features = 128 bytes of fp32 per row and half
             if (hh == 1) {
+              if (lane == 0) tma_store_wait_read();
+              __syncwarp();
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const int r = r8 + 4 * i;
@@ -426,21 +446,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
               r4.x += bf_lo(y01); r4.y += bf_hi(y01); r4.z += bf_lo(y23); r4.w += bf_hi(y23);
               *reinterpret_cast<float4*>(stg + off) = r4;
             }
+            fence_async_smem();
             __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = r8 + 4 * i;
-              if (wrow0 + r < P.Np) {
-                const uint4 v4 = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4));
-                *reinterpret_cast<uint4*>(outp + ((int64_t)b * (P.Np + 1) + 1 + wrow0 + r) * D + n * 64 + hh * 32 + ch8 * 4) = v4;
-              }
+            if (lane == 0 && wrow0 < P.Np) {
+              tma_store_3d(&tm_out, stg, n * 64 + hh * 32, wrow0, b);
+              tma_store_commit();
             }
-            __syncwarp();
           }
         }
       }
     }
   }
+  if (warp < 8 && lane == 0) tma_store_wait_all();                       // every tile store of this warp has landed
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -448,7 +465,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
 }
 
 template <int KT, bool RES32>
-int launch2(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const Params& P, cudaStream_t st) {
+int launch2(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const CUtensorMap& tm_z, const CUtensorMap& tm_out, const Params& P,
+            cudaStream_t st) {
   GVIT_CHECK_CUDA(cudaFuncSetAttribute(agg4_tc_kernel<KT, RES32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   int pairs = 0;
   {
@@ -466,14 +484,19 @@ int launch2(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const Params& P,
       pairs = num_sms() / 2;
     }
   }
+  if (const char* e = getenv("GVIT_AGG_MAXPAIRS")) {                     // experiment switch: fewer pairs -> is the kernel bound per SM or chip-wide?
+    const int m = atoi(e);
+    if (m >= 1 && m < pairs) pairs = m;
+  }
   const int grid = 2 * (P.B < pairs ? P.B : pairs);
-  agg4_tc_kernel<KT, RES32><<<grid, THREADS, SMEM_BYTES, st>>>(tm_tok, tm_w, P);
+  agg4_tc_kernel<KT, RES32><<<grid, THREADS, SMEM_BYTES, st>>>(tm_tok, tm_w, tm_z, tm_out, P);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }
 template <int KT>
-int launch(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const Params& P, bool res32, cudaStream_t st) {
-  return res32 ? launch2<KT, true>(tm_tok, tm_w, P, st) : launch2<KT, false>(tm_tok, tm_w, P, st);
+int launch(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const CUtensorMap& tm_z, const CUtensorMap& tm_out, const Params& P, bool res32,
+           cudaStream_t st) {
+  return res32 ? launch2<KT, true>(tm_tok, tm_w, tm_z, tm_out, P, st) : launch2<KT, false>(tm_tok, tm_w, tm_z, tm_out, P, st);
 }
 
 }  // namespace
@@ -496,18 +519,30 @@ int agg4_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, 
   P.out = out;
   const bool res32 = resid_dtype == GVIT_F32;
   P.w_save = w_save;
+  P.kvec = (k == 4 || k == 8 || k == 16) && aligned16(idx) && aligned16(vals) && (!w_save || aligned16(w_save));
   P.z_save = static_cast<__nv_bfloat16*>(z_save);
   P.zbs = z_batch_stride;
 
-  CUtensorMap tm_tok, tm_w;
+  CUtensorMap tm_tok, tm_w, tm_z, tm_out;
   const __nv_bfloat16* tok = static_cast<const __nv_bfloat16*>(h) + D;   // skip the CLS row (section 9, G0)
   int rc = make_tmap_bf16_3d(&tm_tok, tok, D, Np, B, D, (uint64_t)(Np + 1) * D, P.NT);
   if (rc != GVIT_OK) return rc;
   rc = make_tmap_bf16_3d(&tm_w, Wg, D, D, 1, D, (uint64_t)D * D, 64);
   if (rc != GVIT_OK) return rc;
-  if (k <= 4) return launch<4>(tm_tok, tm_w, P, res32, st);
-  if (k <= 8) return launch<8>(tm_tok, tm_w, P, res32, st);
-  return launch<16>(tm_tok, tm_w, P, res32, st);
+  // output / saved-Z tiles of [32 rows][128 bytes] leave through TMA stores: out starts at token row 1 (the CLS row is copied
+  // by ordinary stores), rows >= Np of a warp's tile are clipped by the TMA unit
+  if (res32) rc = make_tmap_f32_3d(&tm_out, static_cast<float*>(out) + D, D, Np, B, D, (uint64_t)(Np + 1) * D, 32);
+  else rc = make_tmap_bf16_3d(&tm_out, static_cast<__nv_bfloat16*>(out) + D, D, Np, B, D, (uint64_t)(Np + 1) * D, 32);
+  if (rc != GVIT_OK) return rc;
+  if (z_save) {
+    rc = make_tmap_bf16_3d(&tm_z, z_save, D, Np, B, D, (uint64_t)z_batch_stride, 32);
+    if (rc != GVIT_OK) return rc;
+  } else {
+    tm_z = tm_out;                                                       // never dereferenced
+  }
+  if (k <= 4) return launch<4>(tm_tok, tm_w, tm_z, tm_out, P, res32, st);
+  if (k <= 8) return launch<8>(tm_tok, tm_w, tm_z, tm_out, P, res32, st);
+  return launch<16>(tm_tok, tm_w, tm_z, tm_out, P, res32, st);
 }
 
 }  // namespace gvit

@@ -134,6 +134,8 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // the committed stores have finished READING shared memory (the buffer may be reused)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// the committed stores are complete (before the CTA exits)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- tcgen05: TMEM allocation (one full warp executes these) ----
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {
@@ -337,5 +339,8 @@ __device__ __forceinline__ void trace_event(int id, unsigned int& cursor) {
 // ------------------------------------------------------------------------------------------------
 int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batch,
                       uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows);
+// same for an fp32 tensor: box {32, box_rows, 1} (128-byte rows, 128-byte swizzle)
+int make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batch,
+                     uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows);
 
 }  // namespace gvit
