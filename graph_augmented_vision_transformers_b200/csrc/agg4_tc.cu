@@ -79,6 +79,29 @@ __device__ __forceinline__ void wait_upto(uint64_t* bar, uint32_t& seen, uint32_
   while (seen < need) { mbar_wait(bar, seen & 1); ++seen; }
 }
 
+// Work items of a pair.  Full rounds: image cid + it * ncl, every output chunk.  The images left over after the full rounds
+// (r = B mod ncl) would occupy r of the ncl pairs for a whole round; when 2 r <= ncl each of them is split between two pairs -
+// both run the Z phase, each projects one half of the 128-feature output chunks (a half item costs ~0.63 of an image), and
+// only the first half ("primary") writes the saved weights, the saved Z tile and the CLS row.
+struct Item { int b, c0, c1; bool primary; };
+__device__ __forceinline__ bool get_item(int it, int cid, int ncl, int B, int nchunk, Item& I) {
+  const int R = B / ncl, r = B - R * ncl;
+  I.c0 = 0; I.c1 = nchunk; I.primary = true;
+  if (it < R) { I.b = cid + it * ncl; return true; }
+  if (it > R || r == 0) return false;
+  if (2 * r <= ncl && (nchunk & 1) == 0) {
+    if (cid >= 2 * r) return false;
+    I.b = R * ncl + (cid >> 1);
+    I.primary = (cid & 1) == 0;
+    I.c0 = (cid & 1) * (nchunk >> 1);
+    I.c1 = I.c0 + (nchunk >> 1);
+    return true;
+  }
+  if (cid >= r) return false;
+  I.b = R * ncl + cid;
+  return true;
+}
+
 template <int KT, bool RES32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_kernel(const __grid_constant__ CUtensorMap tm_tok,
                                                                                        const __grid_constant__ CUtensorMap tm_w,
@@ -127,14 +150,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     if (elect_one()) {
       uint32_t c = 0;                                                  // ring fill counter
-      for (int b = cid; b < P.B; b += ncl) {
+      Item I;
+      for (int it = 0; get_item(it, cid, ncl, P.B, nchunk, I); ++it) {
+        const int b = I.b;
         for (int t = 0; t < nstep; ++t, ++c) {                         // this CTA's 64-feature token slab of step t
           const uint32_t sl = c % NSLOT;
           mbar_wait(&ctl->empty[sl], ((c / NSLOT) & 1) ^ 1);
           if (rank == 0) mbar_expect_tx(&ctl->full[sl], (uint32_t)(2 * NT * 128));
           tma_load_3d_2sm(sRing + sl * SLOT, &tm_tok, (2 * t + rank) * 64, 0, b, mapa_u32(smem_u32(&ctl->full[sl]), 0));
         }
-        for (int n = 0; n < nchunk; ++n) {                             // W rows [128 n + 64 rank, + 64), pieces of <= 256 columns
+        for (int n = I.c0; n < I.c1; ++n) {                            // W rows [128 n + 64 rank, + 64), pieces of <= 256 columns
           for (int p = 0; p < npiece; ++p, ++c) {
             const uint32_t sl = c % NSLOT;
             const int nbox = min(4, (D - p * 256) / 64);
@@ -155,7 +180,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
       const uint32_t idesc_w = make_idesc(256, 128, false, false);     // Z from TMEM, W piece K-major (64 rows per CTA)
       uint32_t c = 0;                                                  // ring consume counter
       uint32_t a_seen = 0, conv_seen0 = 0, conv_seen1 = 0, conv_iss0 = 0, conv_iss1 = 0, free_seen = 0, out_iss = 0;
-      for (int b = cid; b < P.B; b += ncl) {
+      Item I;
+      for (int it = 0; get_item(it, cid, ncl, P.B, nchunk, I); ++it) {
         wait_upto(&ctl->a_ready, a_seen, a_seen + 1);                  // both CTAs' adjacency tiles are built
         tc_fence_after();
         GVIT_TR(1);
@@ -186,7 +212,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
         wait_upto(&ctl->conv_done[1], conv_seen1, conv_iss1);
         tc_fence_after();
         GVIT_TR(4);
-        for (int n = 0; n < nchunk; ++n) {                             // ---- projection: N = 128 per instruction (a 2-SM MMA
+        for (int n = I.c0; n < I.c1; ++n) {                            // ---- projection: N = 128 per instruction (a 2-SM MMA
           wait_upto(&ctl->out_free, free_seen, out_iss);               // takes ~80 cycles whatever its N: 64-wide chunks ran at 40 %)
           tc_fence_after();
           GVIT_TR(5);
@@ -233,7 +259,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
     // ---- G4 + adjacency tile of image bb (the it-th of this pair): zero A~, then scatter each row's k softmax weights (bf16)
     //      at its neighbour columns.  Runs in the slot where the row warps would otherwise wait for the first projection
     //      chunk of the PREVIOUS image, so the MMA issuer finds a_ready complete when it gets to the next image.
-    auto build_adj = [&](int bb, int it) {
+    auto build_adj = [&](int bb, int it, bool primary) {
       GVIT_TR(10);
       if (it > 0) wait_upto(&ctl->a_free, afree_seen, (uint32_t)it);     // the previous image's Z MMAs have read A~
       GVIT_TR(11);
@@ -274,12 +300,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
             if (j < P.k) {
               const float wj = w[j] * inv;
               w[j] = wj;
-              if (P.w_save && !P.kvec) P.w_save[o + j] = wj;
+              if (P.w_save && primary && !P.kvec) P.w_save[o + j] = wj;
               const int cidx = nb[j];
               *reinterpret_cast<__nv_bfloat16*>(sA + (cidx >> 6) * TILE + swz128(row, cidx & 63) + (cidx & 7) * 2) = __float2bfloat16_rn(wj);
             }
           }
-          if (P.w_save && P.kvec) {
+          if (P.w_save && primary && P.kvec) {
 #pragma unroll
             for (int j = 0; j < KT; j += 4) *reinterpret_cast<float4*>(P.w_save + o + j) = make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
           }
@@ -288,7 +314,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(a_readyL);
         GVIT_TR(12);
-      } else if (rank == 0) {
+      } else if (rank == 0 && primary) {
         // CLS row: out[bb,0,:] = resid[bb,0,:] (the graph leaves CLS untouched, section 9 G0), 16 bytes per thread and trip
         constexpr int EPV = RES32 ? 4 : 8;                               // elements per 16-byte vector
         constexpr int ESZ = RES32 ? 4 : 2;
@@ -300,8 +326,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
         }
       }
     };
-    if (cid < P.B) build_adj(cid, 0);
-    for (int b = cid, iter = 0; b < P.B; b += ncl, ++iter) {
+    Item I, Inext;
+    if (get_item(0, cid, ncl, P.B, nchunk, I)) build_adj(I.b, 0, I.primary);
+    for (int iter = 0; get_item(iter, cid, ncl, P.B, nchunk, I); ++iter) {
+      const int b = I.b;
+      const bool zsave = P.z_save != nullptr && I.primary;
       // residual rows of this warp for output chunk n, coalesced (lane -> rows r8 + 4i, 16-byte chunk ch8)
       // RES32: a 64-feature chunk is 256 bytes per row = two 128-byte halves (32 features each)
       auto load_resid = [&](int n, uint4 (&rr)[8 * NH]) {
@@ -311,7 +340,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
           for (int i = 0; i < 8; ++i) {
             const int r = r8 + 4 * i;
             rr[hh * 8 + i] = make_uint4(0, 0, 0, 0);
-            if (P.resid && n < D / 64 && wrow0 + r < P.Np) {
+            if (P.resid && n < 2 * I.c1 && wrow0 + r < P.Np) {
               const int64_t e = ((int64_t)b * (P.Np + 1) + 1 + wrow0 + r) * D + n * 64;
               if constexpr (RES32) rr[hh * 8 + i] = *reinterpret_cast<const uint4*>(static_cast<const float*>(P.resid) + e + hh * 32 + ch8 * 4);
               else rr[i] = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(P.resid) + e + ch8 * 8);
@@ -351,7 +380,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
         GVIT_TR(15);
         tmem_st16(dst, pk0);
         tmem_st16(dst + 16, pk1);
-        if (P.z_save) {                                                  // [32 rows][64 features] of this warp -> staging -> one TMA tile
+        if (zsave) {                                                     // [32 rows][64 features] of this warp -> staging -> one TMA tile
           if (lane == 0) tma_store_wait_read();                          // store (asynchronous: the warp's own LSU queue stays free)
           __syncwarp();
 #pragma unroll
@@ -365,7 +394,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(par ? conv_doneL1 : conv_doneL0);
         GVIT_TR(16);
-        if (P.z_save) {
+        if (zsave) {
           fence_async_smem();
           __syncwarp();
           if (lane == 0 && wrow0 < P.Np) {                               // rows >= Np are clipped by the TMA unit
@@ -374,18 +403,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
           }
         }
       }
-      load_resid(g, rnext);                                              // first chunk of this warpgroup: in flight during the build
-      if (b + ncl < P.B) build_adj(b + ncl, iter + 1);                   // next image's adjacency tile, under this image's projection
+      load_resid(2 * I.c0 + g, rnext);                                   // first chunk of this warpgroup: in flight during the build
+      if (get_item(iter + 1, cid, ncl, P.B, nchunk, Inext)) build_adj(Inext.b, iter + 1, Inext.primary);   // next adjacency tile, under this projection
       // ---- projection epilogue (chunks of parity g): + bias + residual, coalesced through the warp staging
       // (warpgroup g takes the 64-feature half g of every 128-feature chunk: 64-feature index n = 2 * chunk + g)
-      for (int n = g; n < D / 64; n += 2) {
+      for (int n = 2 * I.c0 + g; n < 2 * I.c1; n += 2) {
+        GVIT_TR(22);
         if (lane == 0) tma_store_wait_read();                            // the staging tile's previous TMA store has read it
         __syncwarp();
+        GVIT_TR(23);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = r8 + 4 * i;
           *reinterpret_cast<uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4)) = rnext[i];
         }
+        GVIT_TR(24);
         if constexpr (!RES32) load_resid(n + 2, rnext);                  // next chunk of this warpgroup: in flight meanwhile
         __syncwarp();
         GVIT_TR(17);
@@ -488,7 +520,9 @@ int launch2(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const CUtensorMa
     const int m = atoi(e);
     if (m >= 1 && m < pairs) pairs = m;
   }
-  const int grid = 2 * (P.B < pairs ? P.B : pairs);
+  // fewer images than pairs: two pairs per image when they fit (get_item splits the output chunks between them)
+  const int used = P.B >= pairs ? pairs : (2 * P.B <= pairs && (P.D / 128) % 2 == 0 ? 2 * P.B : P.B);
+  const int grid = 2 * used;
   agg4_tc_kernel<KT, RES32><<<grid, THREADS, SMEM_BYTES, st>>>(tm_tok, tm_w, tm_z, tm_out, P);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;

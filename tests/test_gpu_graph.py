@@ -99,6 +99,39 @@ def test_bf16_fused_residual_epilogue():
     assert mixed.dtype == torch.float32 and rel_err(mixed, x32 + plain.float()) < 1e-6
 
 
+@pytest.mark.parametrize("B", [1, 37, 75, 80, 120])
+@pytest.mark.parametrize("res32", [False, True])
+def test_bf16_aggregation_work_items_are_batch_invariant(B, res32):
+    """The CTA-pair aggregation kernel schedules whole images in full rounds and splits the left-over images' output chunks
+    between two pairs (agg4_tc.cu get_item): every image must come out bit-identical to the same image run in a batch of one
+    or two, whatever round / half it landed in - output, CLS row, and the saved tiles the backward reads."""
+    bf = torch.bfloat16
+    Np, D, k = 196, 768, 8
+    hc, hd = tokens(B, Np, D, seed=40 + B, dtype=bf)
+    g = torch.Generator().manual_seed(6)
+    W = (torch.randn(D, D, generator=g) * 0.05).to(DEV, bf)
+    b = (torch.randn(D, generator=g) * 0.1).to(DEV, bf)
+    x = torch.randn(B, Np + 1, D, generator=g).to(DEV, torch.float32 if res32 else bf)
+    cot = torch.randn(B, Np + 1, D, generator=g).to(DEV, x.dtype)
+
+    def run(h, xr, c):
+        h = h.clone().requires_grad_(True)
+        if res32:
+            with torch.autocast("cuda", dtype=bf):
+                out = ops.patch_graph(h.float(), W.float(), b.float(), k, resid=xr)
+        else:
+            out = ops.patch_graph(h, W, b, k, resid=xr)
+        out.backward(c)
+        return out.detach(), h.grad
+
+    out, dh = run(hd, x, cot)
+    for lo in sorted({0, B // 2, max(B - 2, 0)}):
+        hi = min(lo + 2, B)
+        o2, d2 = run(hd[lo:hi], x[lo:hi], cot[lo:hi])
+        assert torch.equal(out[lo:hi], o2), (lo, "out")
+        assert torch.equal(dh[lo:hi], d2), (lo, "dh")
+
+
 def test_graph_reverse_is_the_transposed_adjacency():
     _, hd = tokens(3, 196, 64, seed=9)
     idx, _, _ = ops.knn_graph(hd, 8)
