@@ -218,7 +218,8 @@ __global__ void __launch_bounds__(THREADS, 1) agg3_tc_kernel(const __grid_consta
               const float wj = w[j] * inv;
               if (P.w_save) P.w_save[o + j] = wj;
               const int cidx = nb[j];
-              *reinterpret_cast<__nv_bfloat16*>(sA + (cidx >> 6) * TILE + swz128(row, cidx & 63) + (cidx & 7) * 2) = __float2bfloat16_rn(wj);
+              if (nb_ok(cidx, P.Np))
+                *reinterpret_cast<__nv_bfloat16*>(sA + (cidx >> 6) * TILE + swz128(row, cidx & 63) + (cidx & 7) * 2) = __float2bfloat16_rn(wj);
             }
           }
         }

@@ -302,7 +302,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
               w[j] = wj;
               if (P.w_save && primary && !P.kvec) P.w_save[o + j] = wj;
               const int cidx = nb[j];
-              *reinterpret_cast<__nv_bfloat16*>(sA + (cidx >> 6) * TILE + swz128(row, cidx & 63) + (cidx & 7) * 2) = __float2bfloat16_rn(wj);
+              if (nb_ok(cidx, P.Np))
+                *reinterpret_cast<__nv_bfloat16*>(sA + (cidx >> 6) * TILE + swz128(row, cidx & 63) + (cidx & 7) * 2) = __float2bfloat16_rn(wj);
             }
           }
           if (P.w_save && primary && P.kvec) {

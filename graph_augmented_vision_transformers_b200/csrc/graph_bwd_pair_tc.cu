@@ -367,7 +367,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             if (u < kk1) {
-              *a2_cell(sA, tid, NT + ii1[u]) = __float2bfloat16_rn(rnj * ctl->rn[ii1[u]] * ds1[u]);
+              if (nb_ok(ii1[u], Np)) *a2_cell(sA, tid, NT + ii1[u]) = __float2bfloat16_rn(rnj * ctl->rn[ii1[u]] * ds1[u]);
               tacc += __float2int_rn(ds1[u] * vv1[u] * tscale);
             }
           }
@@ -375,7 +375,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
             const int e = jg * k + s;
             const int i = idx_b[e];
             const float ds = __ldcg(ds_b + e);
-            *a2_cell(sA, tid, NT + i) = __float2bfloat16_rn(rnj * ctl->rn[i] * ds);
+            if (nb_ok(i, Np)) *a2_cell(sA, tid, NT + i) = __float2bfloat16_rn(rnj * ctl->rn[i] * ds);
             tacc += __float2int_rn(ds * v_b[e] * tscale);
           }
           atomicAdd(&ctl->tfix[tid], tacc);

@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) graph_dp_tc_kernel(const __grid_
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           if (u < kk1) {
-            *a2_cell(sA, tid, NT + ii1[u]) = __float2bfloat16_rn(rnj * ctl->rn[ii1[u]] * ds1[u]);
+            if (nb_ok(ii1[u], P.Np)) *a2_cell(sA, tid, NT + ii1[u]) = __float2bfloat16_rn(rnj * ctl->rn[ii1[u]] * ds1[u]);
             tacc += __float2ll_rn(ds1[u] * vv1[u] * FIX_SCALE);
           }
         }
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) graph_dp_tc_kernel(const __grid_
           const int e = jg * P.k + s;
           const int i = idx_b[e];
           const float ds = ds_b[e];
-          *a2_cell(sA, tid, NT + i) = __float2bfloat16_rn(rnj * ctl->rn[i] * ds);
+          if (nb_ok(i, P.Np)) *a2_cell(sA, tid, NT + i) = __float2bfloat16_rn(rnj * ctl->rn[i] * ds);
           tacc += __float2ll_rn(ds * v_b[e] * FIX_SCALE);
         }
         tfix_add(tid, tacc);
@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) graph_bwd_fused_kernel(const __g
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               if (u < kk1) {
-                *a2_cell(sA, tid, NT + ii1[u]) = __float2bfloat16_rn(rnj * ctl->rn[ii1[u]] * ds1[u]);
+                if (nb_ok(ii1[u], Np)) *a2_cell(sA, tid, NT + ii1[u]) = __float2bfloat16_rn(rnj * ctl->rn[ii1[u]] * ds1[u]);
                 tacc += __float2int_rn(ds1[u] * vv1[u] * tscale);
               }
             }
@@ -693,7 +693,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) graph_bwd_fused_kernel(const __g
               const int e = jg * k + s;
               const int i = idx_b[e];
               const float ds = ds_b[e];
-              *a2_cell(sA, tid, NT + i) = __float2bfloat16_rn(rnj * ctl->rn[i] * ds);
+              if (nb_ok(i, Np)) *a2_cell(sA, tid, NT + i) = __float2bfloat16_rn(rnj * ctl->rn[i] * ds);
               tacc += __float2int_rn(ds * v_b[e] * tscale);
             }
             atomicAdd(&ctl->tfix[tid], tacc);

@@ -299,6 +299,20 @@ __device__ __forceinline__ uint32_t swz128(int row, int col) {
   return static_cast<uint32_t>(row) * 128u + ((((static_cast<uint32_t>(col) >> 3) ^ (static_cast<uint32_t>(row) & 7u)) << 4));
 }
 
+// ---- neighbour indices from an adjacency list ----
+// In range by contract (gvit_knn_fwd writes them), but the lists are caller-supplied pointers at the C ABI: an out-of-range
+// value must never become a shared-memory scatter.  Product builds skip such an edge; -DGVIT_DEBUG_BOUNDS builds trap with a message.
+__device__ __forceinline__ bool nb_ok(int i, int n) {
+  const bool ok = static_cast<unsigned>(i) < static_cast<unsigned>(n);
+#ifdef GVIT_DEBUG_BOUNDS
+  if (!ok) {
+    printf("gvit: neighbour index %d outside [0, %d) (block %d thread %d)\n", i, n, blockIdx.x, threadIdx.x);
+    __trap();
+  }
+#endif
+  return ok;
+}
+
 // ---- optional event trace (builds with -DGVIT_TRACE only; see tools/trace_kernel.py) ----
 // CTA 0 records (warp, event id, clock64) tuples into a global buffer set by gvit_debug_set_trace(); used to see
 // where the warp-specialised pipelines wait.  Compiled out of the product library.

@@ -132,6 +132,40 @@ def test_bf16_aggregation_work_items_are_batch_invariant(B, res32):
         assert torch.equal(dh[lo:hi], d2), (lo, "dh")
 
 
+def test_bf16_aggregation_skips_out_of_range_neighbours():
+    """The adjacency lists are caller-supplied pointers at the C ABI: an index outside [0, Np) must not become a shared-memory
+    scatter.  The product build drops such an edge (a -DGVIT_DEBUG_BOUNDS build traps with a message): every other row of the
+    image, and every other image, comes out exactly as with the clean list."""
+    from graph_augmented_vision_transformers_b200.ops import _call, _dtype_code, _ptr, _stream
+    bf = torch.bfloat16
+    B, Np, D, k = 3, 196, 768, 8
+    _, hd = tokens(B, Np, D, seed=9, dtype=bf)
+    g = torch.Generator().manual_seed(8)
+    W = (torch.randn(D, D, generator=g) * 0.05).to(DEV, bf)
+    b = (torch.randn(D, generator=g) * 0.1).to(DEV, bf)
+    idx, vals, _ = ops.knn_graph(hd, k)
+
+    def run(ix):
+        out = torch.empty_like(hd)
+        w = torch.empty(B, Np, k, device=DEV)
+        z = torch.empty(B, Np, D, device=DEV, dtype=bf)
+        _call("gvit_agg_fwd", _ptr(hd), B, Np, D, k, _dtype_code(hd), _ptr(ix), _ptr(vals), _ptr(W), _ptr(b), None, _dtype_code(hd),
+              _ptr(out), _ptr(w), _ptr(z), Np * D, _stream())
+        torch.cuda.synchronize()
+        return out
+
+    clean = run(idx)
+    bad = idx.clone()
+    bad[1, 7, 3] = 1_000_000
+    bad[1, 150, 0] = -5
+    got = run(bad)
+    keep = torch.ones(B, Np + 1, dtype=torch.bool, device=DEV)
+    keep[1, 1 + 7] = False
+    keep[1, 1 + 150] = False
+    assert torch.equal(got[keep], clean[keep])
+    assert torch.isfinite(got.float()).all()
+
+
 def test_graph_reverse_is_the_transposed_adjacency():
     _, hd = tokens(3, 196, 64, seed=9)
     idx, _, _ = ops.knn_graph(hd, 8)
