@@ -302,15 +302,22 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
         for i in range(3):
             fn(i)
         torch.cuda.synchronize()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-        # The host needs ~20 us per call (ctypes + two tensor-map encodes + launch): for a 30 us kernel an event pair recorded
-        # on an idle stream would time the host, not the kernel.  A ~1.5 ms spin kernel goes first, the host queues every
-        # iteration behind it, and the event pairs then bracket back-to-back kernel executions only.
-        torch.cuda._sleep(3_000_000)
-        for i, (a, b) in enumerate(evs):
-            a.record(); fn(i); b.record()
-        torch.cuda.synchronize()
-        ms = statistics.median(a.elapsed_time(b) for a, b in evs)
+        # ONE event pair around `iters` back-to-back launches (rotating input sets), three such groups, median of the group
+        # means.  An event pair around a SINGLE launch measures 6.5 us for an empty 148-CTA kernel on B200 against 2.6 us per
+        # launch back to back (tools/launch_overhead.cu): ~4 us of event overhead that a stream or a captured graph never pays
+        # and that is 5-15 % of these 25-100 us kernels.  The host needs ~20 us per call (ctypes + tensor-map encodes), so a
+        # ~1.5 ms spin kernel goes first and the host queues the whole group behind it: the GPU never waits for the host.
+        groups = []
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(3_000_000)
+            a.record()
+            for i in range(iters):
+                fn(i)
+            b.record()
+            torch.cuda.synchronize()
+            groups.append(a.elapsed_time(b) / iters)
+        ms = statistics.median(groups)
         gbs, tfs = nbytes / ms / 1e6, flops / ms / 1e9
         if bound == "hbm":
             ach, peak, unit = gbs, peaks["hbm"], "GB/s"

@@ -1,34 +1,40 @@
-// agg4_tc.cu - fused aggregation G4+G5+G6 + residual for bf16, D <= 768, as a 2-SM kernel: ONE CTA PAIR PER IMAGE
-// (north_star: "gather / normalise, then a tcgen05 GEMM with TMA-staged tiles that keeps A.X in shared
-// memory or TMEM with no HBM round-trip").
+// agg4_tc.cu - fused aggregation G4+G5+G6 + residual for bf16, 128 < Np <= 256, D <= 768, as a 2-SM kernel: ONE CTA PAIR PER
+// IMAGE (north_star: "gather / normalise, then a tcgen05 GEMM with TMA-staged tiles that keeps A.X in
+// shared memory or TMEM with no HBM round-trip").
 //
 //   out[b,1+i,:] = resid[b,1+i,:] + ( sum_j softmax_k(vals)_ij * p[b, idx_ij, :] ) Wg^T + bias
 //
-// agg3_tc.cu gave each 128-row tile of an image its own CTA, so both CTAs of an image streamed ALL token slabs (301 KB) and
-// ALL of Wg (1.18 MB) through L2 -> shared memory: 1.48 MB per 128 rows, and the measured W stream arrived at ~25-30
-// B/clk/SM with the tensor pipe 48 % busy.  Here the two row tiles of an image are the two halves of `cta_group::2` MMAs
-// (M = 256): every B operand - token slab or W piece - is split between the pair, each CTA stages HALF of it, so the
-// operand bytes per CTA and per image halve (0.74 MB).  The pair is persistent (images b = pair, pair + pairs, ...), the
-// producer runs ahead into the next image while the epilogue of the current one drains.
+// agg3_tc.cu gives each 128-row tile of an image its own CTA, so both CTAs of an image stream ALL token slabs (301 KB) and
+// ALL of Wg (1.18 MB) through L2 -> shared memory.  Here the two row tiles of an image are the two halves of `cta_group::2`
+// MMAs (M = 256): every B operand - token slab or W piece - is split between the pair, each CTA stages HALF of it, so the
+// operand bytes per CTA and per image halve (0.74 MB).  The pair is persistent over its work items (get_item below: whole
+// images in full rounds; the images left over after the last full round are split between two pairs, half of the output
+// chunks each).
 //
-// Per image (rank r = 0 / 1 owns token rows [128 r, 128 r + 128) = its TMEM lanes, its A~ tile, its output rows):
-//   A~ tile    : 128 x NT dense bf16 adjacency rows in shared memory (zeroed, then each row's k softmax weights scattered).
+// Per item (rank r = 0 / 1 owns token rows [128 r, 128 r + 128) = its TMEM lanes, its A~ tile, its output rows):
+//   A~ tile    : 128 x NT dense bf16 adjacency rows in shared memory (zeroed, then each row's k softmax weights scattered);
+//                the tile of item n + 1 is built while item n's projection runs (the row warps would otherwise wait there).
 //   Z phase    : Z = A~ . P, 128 features per step: MMA M = 256, N = 128, K = tokens; rank r stages the 64-feature token
-//                slab 2 t + r (MN-major B).  fp32 result in a TMEM staging area, converted IN TENSOR MEMORY to packed bf16:
-//                the whole aggregated tile Z [128 x D] of a CTA ends up in TMEM columns [0, D/2) (training streams a copy
-//                out for the weight gradient).
-//   projection : per 64-feature output chunk OUT = Z . W_chunk^T, A from TMEM (TS form), rank r stages W rows
-//                [64 n + 32 r, + 32) in pieces of up to 512 reduction columns; fp32 chunk double-buffered in TMEM so that
-//                bias + residual + store of chunk n overlap the MMAs of chunk n + 1.
+//                slab 2 t + r (MN-major B).  fp32 result in a TMEM staging area, converted IN TENSOR MEMORY to packed bf16
+//                by BOTH row warpgroups (64 staging columns each), so a step's conversion overlaps the next step's MMAs:
+//                the whole aggregated tile Z [128 x D] of a CTA ends up in TMEM columns [0, D/2) (training also sends each
+//                [32 rows x 64 features] piece out through a TMA store for the weight gradient).
+//   projection : per 128-feature output chunk OUT = Z . W_chunk^T, A from TMEM (TS form), N = 128 per instruction (a 2-SM
+//                MMA takes ~75-80 cycles whatever its N: 64-wide chunks ran the tensor pipe at 40 %); rank r stages W rows
+//                [128 n + 64 r, + 64) in pieces of 256 reduction columns.  ONE fp32 chunk buffer: TMEM is full, so the MMAs of
+//                chunk n + 1 wait until both warpgroups have read chunk n (~1.8k of the ~5.6k cycles per chunk: the bound of
+//                this design, see profiles/README.md).  Epilogue: warpgroup g takes the 64-feature half g of the chunk:
+//                + bias + residual in the warp's staging tile, then one TMA store per [32 rows x 128 bytes].
 // TMEM (512 columns per CTA): Z bf16 [0, D/2) | Z fp32 staging: step t even -> [64 t, 64 t + 128) (in place), odd ->
-//                [384, 512) | OUT chunk buffers [384, 448), [448, 512).
+//                [384, 512) | OUT chunk buffer [384, 512).
 // Shared memory per CTA: A~ (4 x 16 KB) | ring of 4 x 32 KB slots | 8 x 4 KB per-warp staging.
-// Warp roles: 0-3 row warpgroup 0, 4-7 row warpgroup 1 (thread <-> token row = TMEM lane; warpgroup g owns the Z steps and
-// output chunks of parity g), 8 TMA producer (both CTAs), 9 MMA issuer (leader) and TMEM owner.
-// Barriers.  In the leader, arrived at by both CTAs: full[slot] (TMA bytes), a_ready, conv_done[parity], out_free[buf].
-// In each CTA, released by multicast tcgen05.commit: empty[slot], a_free, zs_full[parity], out_full[buf]; local:
-// conv_loc[parity] (the two warpgroups of a CTA hand the in-place staging columns to each other).  Every waiter counts the
-// completions it has consumed and waits for them one by one, so no barrier can run two phases ahead of a waiter.
+// Warp roles: 0-3 row warpgroup 0, 4-7 row warpgroup 1 (thread <-> token row = TMEM lane), 8 TMA producer (both CTAs),
+// 9 MMA issuer (leader) and TMEM owner.
+// Barriers.  In the leader, arrived at by both CTAs: full[slot] (TMA bytes), a_ready, conv_done[step parity], out_free.
+// In each CTA, released by multicast tcgen05.commit: empty[slot], a_free, zs_full[step parity], out_full.  The two warps
+// that share a TMEM lane quarter meet at a 64-thread named barrier inside every in-place conversion.  Every waiter counts
+// the completions it has consumed and waits for them one by one, so no barrier can run two phases ahead of a waiter.
+// Measured at B = 256, Np = 196, D = 768, k = 8 (training: w and Z saved): 0.0906 ms against 0.1210 ms for agg3 on the same box.
 #include <float.h>
 
 #include "kernels.cuh"
@@ -116,6 +122,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   GVIT_TRACE_DECL
+  GVIT_SPAN(0);
   const int rank = (int)cluster_ctarank();
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
   const int D = P.D, NT = P.NT;
@@ -494,6 +501,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
+  GVIT_SPAN(1);
   if (warp == 9) tmem_dealloc_2sm(tmem, 512);
 }
 

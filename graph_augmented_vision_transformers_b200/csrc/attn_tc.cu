@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) attn_fwd_tc2_kernel(const __gri
   const int MT = (N + 127) >> 7;                 // 128-row query tiles (1 or 2) == 128-row key/value tiles
   const int NT = (N + 15) & ~15;                 // key extent of the MMAs
   GVIT_TRACE_DECL
+  GVIT_SPAN(0);
 
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tm_qkv);
@@ -263,6 +264,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) attn_fwd_tc2_kernel(const __gri
   }
   tc_fence_before();
   __syncthreads();
+  GVIT_SPAN(1);
   if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
@@ -411,6 +413,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform role id
   const int T = (N + 127) / 128;           // tiles along queries == tiles along keys (1 or 2)
   GVIT_TRACE_DECL
+  GVIT_SPAN(0);
 
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tm_qkv);
@@ -727,6 +730,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) attn_bwd_tc_kernel(const __grid
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // outstanding TMA stores of this thread (no-op for most)
   tc_fence_before();
   __syncthreads();
+  GVIT_SPAN(1);
   if (warp == 9) tmem_dealloc(tmem, 512);
 }
 

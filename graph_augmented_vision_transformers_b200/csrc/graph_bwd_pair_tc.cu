@@ -106,6 +106,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
   const int fblocks = P.D / 128;
   const int ksteps = NT / 16;
   GVIT_TRACE_DECL
+  GVIT_SPAN(0);
 
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tm_dzA); prefetch_tmap(&tm_pB); prefetch_tmap(&tm_dzF); prefetch_tmap(&tm_pF);
@@ -465,6 +466,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
+  GVIT_SPAN(1);
   if (warp == 9) tmem_dealloc_2sm(tmem, 512);
 }
 

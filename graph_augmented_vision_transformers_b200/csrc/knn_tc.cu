@@ -312,6 +312,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) knn_pair
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
   const int slabs = D / 64, NH = NT / 2;                   // NH tokens of the N extent per CTA
   GVIT_TRACE_DECL
+  GVIT_SPAN(0);
 
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -437,6 +438,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) knn_pair
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
+  GVIT_SPAN(1);
   if (warp == 9) tmem_dealloc_2sm(tmem, TMEM_COLS);
 }
 

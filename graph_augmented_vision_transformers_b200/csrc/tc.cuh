@@ -331,6 +331,15 @@ __device__ __forceinline__ void trace_event(int id, unsigned int& cursor) {
     ++cursor;
   }
 }
+// every CTA's begin (0) / end (1) in %globaltimer nanoseconds, behind the 16 event regions: launch skew, imbalance, tail
+__device__ __forceinline__ void span_mark(int which) {
+  if (threadIdx.x == 0 && g_trace_buf != nullptr && blockIdx.x < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_trace_buf[16 * g_trace_cap + 2 * blockIdx.x + which] = t;
+  }
+}
+#define GVIT_SPAN(which) ::gvit::tc::span_mark(which)
 #define GVIT_TRACE_DECL unsigned int gvit_trc = 0;
 #define GVIT_TR(id) ::gvit::tc::trace_event(id, gvit_trc)
 #define GVIT_TRACE_SETTER(NAME)                                                                   \
@@ -342,6 +351,7 @@ __device__ __forceinline__ void trace_event(int id, unsigned int& cursor) {
   }
 #else
 #define GVIT_TR(id) ((void)0)
+#define GVIT_SPAN(which) ((void)0)
 #define GVIT_TRACE_DECL
 #define GVIT_TRACE_SETTER(NAME)
 #endif

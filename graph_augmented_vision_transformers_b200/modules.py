@@ -19,6 +19,8 @@ from __future__ import annotations
 
 import logging
 
+import warnings
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -71,13 +73,30 @@ class Attention(nn.Module):
     def forward(self, x, resid=None):
         """``resid`` (used by Block) folds the residual add of vit.py:117 into the proj_drop kernel."""
         if self.training and self.attn_drop.p > 0:
-            # 0 in every configuration the reference ships (vit.py:127; scripts/train.py never sets it)
-            raise NotImplementedError("attn_drop > 0 is not implemented by the fused attention kernel")
-        o = ops.attention_core(_linear(self.qkv, x), self.num_heads, self.scale)
+            # Dropout on the attention probabilities (vit.py:66).  0 in every configuration the reference ships (vit.py:127;
+            # scripts/train.py never sets it), and the fused kernels keep no (B,H,N,N) tensor to drop from: this one case runs
+            # the reference's own op sequence (vit.py:60-69) on the GPU - said once, loudly, so it never passes for the fused path.
+            o = self._attention_with_prob_dropout(_linear(self.qkv, x))
+        else:
+            o = ops.attention_core(_linear(self.qkv, x), self.num_heads, self.scale)
         if _hooked(self.proj) or _hooked(self.proj_drop):
             return ops.dropout_add(self.proj(o), resid, self.proj_drop.p, self.training)
         # proj + proj_drop + residual as one node: the dropout backward pass also yields proj's bias gradient
         return ops.linear_dropout_add(o, self.proj.weight, self.proj.bias, resid, self.proj_drop.p, self.training)
+
+
+    _warned_attn_drop = False
+
+    def _attention_with_prob_dropout(self, qkv):
+        if not Attention._warned_attn_drop:
+            Attention._warned_attn_drop = True
+            warnings.warn("attn_drop > 0 in training: attention runs as the composed softmax(q k^T) -> dropout -> @ v "
+                          "(vit.py:60-69) on the GPU, not through the fused tcgen05 attention kernels", RuntimeWarning, stacklevel=3)
+        B, N, C3 = qkv.shape
+        q, k, v = qkv.reshape(B, N, 3, self.num_heads, C3 // (3 * self.num_heads)).permute(2, 0, 3, 1, 4)   # vit.py:59-61
+        attn = (q @ k.transpose(-2, -1)) * self.scale                                                       # vit.py:64
+        attn = self.attn_drop(attn.softmax(dim=-1))                                                         # vit.py:65-66
+        return (attn @ v).transpose(1, 2).reshape(B, N, C3 // 3)                                            # vit.py:69
 
 
 class Mlp(nn.Module):

@@ -84,10 +84,37 @@ def test_softmax_rows_sum_to_one_at_full_size():
     assert (ops.attention_core(qkv2.view(B, N, -1), H, 0.125).float() - 2).abs().max() < 2e-2
 
 
-def test_attn_drop_is_refused_loudly():
-    m = modules.Attention(64, num_heads=1, attn_drop=0.1).to(DEV).train()
-    with pytest.raises(NotImplementedError):
-        m(torch.randn(1, 4, 64, device=DEV))
+def test_attn_drop_runs_the_reference_op_sequence_and_says_so():
+    """attn_drop > 0 (vit.py:66; 0 in every shipped configuration): the fused kernels keep no (B,H,N,N) tensor, so training
+    with it runs the reference's op sequence on the GPU - with a RuntimeWarning; eval mode stays on the fused kernel."""
+    torch.manual_seed(0)
+    m = modules.Attention(128, num_heads=2, qkv_bias=True, attn_drop=0.25).to(DEV)
+    x = torch.randn(3, 50, 128, device=DEV)
+    modules.Attention._warned_attn_drop = False
+    m.train()
+    with pytest.warns(RuntimeWarning, match="attn_drop"):
+        torch.manual_seed(7)
+        y1 = m(x)
+    torch.manual_seed(7)
+    y2 = m(x)
+    assert torch.equal(y1, y2)                                  # same seed, same mask
+    # the same mask through the plain reference formula (vit.py:59-71)
+    torch.manual_seed(7)
+    B, N, C = x.shape
+    qkv = m.qkv(x).reshape(B, N, 3, 2, C // 2).permute(2, 0, 3, 1, 4)
+    attn = torch.nn.functional.dropout(((qkv[0] @ qkv[1].transpose(-2, -1)) * m.scale).softmax(dim=-1), 0.25, True)
+    want = m.proj((attn @ qkv[2]).transpose(1, 2).reshape(B, N, C))
+    assert rel_err(y1, want) < TOL_F32
+    xg = x.clone().requires_grad_(True)
+    m(xg).square().sum().backward()
+    assert torch.isfinite(xg.grad).all() and all(torch.isfinite(p.grad).all() for p in m.parameters())
+    m.eval()
+    m2 = modules.Attention(128, num_heads=2, qkv_bias=True, attn_drop=0.0).to(DEV).eval()
+    m2.load_state_dict(m.state_dict())
+    assert torch.equal(m(x), m2(x))                             # no dropout in eval: the fused kernel either way
+
+
+def test_unsupported_head_dim_is_refused_loudly():
     with pytest.raises(_lib.GvitError, match="GVIT_ERR_UNSUPPORTED"):
         ops.attention_core(torch.randn(1, 4, 3 * 48, device=DEV), 1, 1.0)      # head dim 48
 
