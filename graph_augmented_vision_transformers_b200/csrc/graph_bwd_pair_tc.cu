@@ -78,6 +78,7 @@ struct __align__(8) QCtrl {
 };
 struct QParams {
   int B, Np, D, k, NT, nblk, slot_bytes;
+  int kvec;                                    // k in {4, 8, 16} == KT and idx / w / vals / dvals 16-byte aligned: whole rows by vector access
   uint32_t kmagic;                             // ceil(2^32 / k): e / k == __umulhi(e, kmagic) for e < 2^16
   const int32_t* idx;
   const float* w;
@@ -249,22 +250,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
       const float* w_b = P.w + (int64_t)b * E;
       const float* v_b = P.vals + (int64_t)b * E;
       float* ds_b = P.dvals + (int64_t)b * E;
+      // thread tid < 128 owns row j0 + tid in the extraction AND in the build: its neighbour list, similarities and dS entries
+      // stay in registers across the two; the edge-parallel build operands that do not depend on the peer (jj, ww, vv) are
+      // fetched, and the coefficient tile is zeroed, while the dvals handshake with the peer CTA is in flight
+      constexpr int EPT = 8;                                          // edges per thread: 256 * 8 = 2048 per pass
+      int nb[KT], jj[EPT];
+      float vj[KT], dsown[KT], ww[EPT], vv[EPT];
       // ---- extract: dvals of row (wrow0 + lane), warps 0-3 --------------------------------------------------------
       {
         const int row = wrow0 + lane;
         const bool active = warp < 4 && wrow0 < Np;                    // warp-uniform
         const bool valid = row < Np;
         const int64_t o = (int64_t)(valid ? row : 0) * k;
-        int nb[KT];
-        float wj[KT], dw[KT];
-        if (active) {
+        float wj[KT], dw[KT];                                          // vj: the row's similarities, for the fixed-point scale below -
+        if (active) {                                                  // loaded here so that the latency hides behind the Gram product
+          if (P.kvec && valid) {
 #pragma unroll
-          for (int j = 0; j < KT; ++j) {
-            const bool on = valid && j < k;
-            nb[j] = on ? idx_b[o + j] : -1;
-            wj[j] = on ? w_b[o + j] : 0.f;
-            dw[j] = 0.f;
+            for (int j = 0; j < KT; j += 4) {
+              const int4 i4 = *reinterpret_cast<const int4*>(idx_b + o + j);
+              const float4 w4 = *reinterpret_cast<const float4*>(w_b + o + j);
+              const float4 v4 = *reinterpret_cast<const float4*>(v_b + o + j);
+              nb[j] = i4.x; nb[j + 1] = i4.y; nb[j + 2] = i4.z; nb[j + 3] = i4.w;
+              wj[j] = w4.x; wj[j + 1] = w4.y; wj[j + 2] = w4.z; wj[j + 3] = w4.w;
+              vj[j] = v4.x; vj[j + 1] = v4.y; vj[j + 2] = v4.z; vj[j + 3] = v4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+              const bool on = valid && j < k;
+              nb[j] = on ? idx_b[o + j] : -1;
+              wj[j] = on ? w_b[o + j] : 0.f;
+              vj[j] = on ? v_b[o + j] : 0.f;
+            }
           }
+#pragma unroll
+          for (int j = 0; j < KT; ++j) dw[j] = 0.f;
         }
         for (int i = tid; i < 256; i += 256) ctl->rn[i] = i < Np ? P.rnorm[(int64_t)b * Np + i] : 0.f;
         if (it > 0) mbar_wait(&ctl->coef_free, (it - 1) & 1);          // the scratch is the (retired) coefficient tile
@@ -289,28 +309,54 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
             for (int j = 0; j < KT; ++j)
               if (nb[j] >= c0 && nb[j] < c0 + 32) dw[j] = scr[nb[j] - c0];
           }
+          GVIT_TR(20);
           float s = 0.f;
 #pragma unroll
           for (int j = 0; j < KT; ++j) s = fmaf(wj[j], dw[j], s);
           if (valid) {
             float m = 0.f;
+            float (&d)[KT] = dsown;
 #pragma unroll
-            for (int j = 0; j < KT; ++j)
-              if (j < k) {
-                const float d = wj[j] * (dw[j] - s);
-                ds_b[o + j] = d;
-                m = fmaxf(m, fabsf(d * v_b[o + j]));
-              }
+            for (int j = 0; j < KT; ++j) {
+              d[j] = j < k ? wj[j] * (dw[j] - s) : 0.f;
+              m = fmaxf(m, fabsf(d[j] * vj[j]));
+            }
+            if (P.kvec) {
+#pragma unroll
+              for (int j = 0; j < KT; j += 4) *reinterpret_cast<float4*>(ds_b + o + j) = make_float4(d[j], d[j + 1], d[j + 2], d[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < KT; ++j)
+                if (j < k) ds_b[o + j] = d[j];
+            }
             atomicMax(&ctl->tmax_own[it & 1], __float_as_int(m));       // non-negative floats order like their bit patterns
           }
         }
+        GVIT_TR(21);
         tc_fence_before();
         __threadfence();                                               // this CTA's dvals rows: visible to the peer
         asm volatile("bar.sync 1, 256;" ::: "memory");                 // G read out, scratch free, tmax_own final
+        GVIT_TR(22);
         if (tid == 0) {
           st_cluster_u32(mapa_u32(smem_u32(&ctl->tmax_peer[it & 1]), rank ^ 1), (uint32_t)ctl->tmax_own[it & 1]);
           mbar_arrive_release_cluster(peer_bar);                        // "my rows of dvals and my maximum are published"
           ctl->tmax_own[(it + 1) & 1] = 0;                              // nobody touches the other image parity right now
+        }
+        // while the handshake is in flight: everything of the build that does not need the peer's dvals
+#pragma unroll
+        for (int u = 0; u < EPT; ++u) {
+          const int e = u * 256 + tid;
+          jj[u] = e < E ? idx_b[e] - j0 : -1;
+        }
+        {
+          const uint4 z4 = make_uint4(0, 0, 0, 0);
+          for (int i = tid; i < P.nblk * TILE / 16; i += 256) reinterpret_cast<uint4*>(sA)[i] = z4;   // scratch is free (barrier above)
+          if (tid < 128) ctl->tfix[tid] = 0;
+        }
+#pragma unroll
+        for (int u = 0; u < EPT; ++u) {
+          const int e = u * 256 + tid;
+          if (jj[u] >= 0 && jj[u] < 128) { ww[u] = w_b[e]; vv[u] = v_b[e]; }
         }
         mbar_wait_acquire_cluster(&ctl->peer, it & 1);                 // ... and so are the peer's
         GVIT_TR(11);
@@ -329,59 +375,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
       // ---- this CTA's coefficient tile [A~^T | M3] (rows j0 .. j0+127), from the edges of the WHOLE image ----------------
       GVIT_TR(12);
       {
-        constexpr int EPT = 8;                                        // edges per thread: 256 * 8 = 2048 per pass
         auto tfix_add = [&](int j, float x) { atomicAdd(&ctl->tfix[j], __float2int_rn(x * tscale)); };
         const int jg = j0 + tid;
         const bool valid = tid < 128 && jg < Np;
-        int ii1[8];
-        float ds1[8], vv1[8];
-        const int kk1 = min(k, 8);
-        if (valid) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int e = jg * k + min(u, k - 1);
-            ii1[u] = idx_b[e];
-            ds1[u] = __ldcg(ds_b + e);
-            vv1[u] = v_b[e];
-          }
-        }
-        int jj[EPT];
+        float dsv[EPT];
 #pragma unroll
         for (int u = 0; u < EPT; ++u) {
           const int e = u * 256 + tid;
-          jj[u] = e < E ? idx_b[e] - j0 : -1;
-        }
-        const uint4 z4 = make_uint4(0, 0, 0, 0);
-        for (int i = tid; i < P.nblk * TILE / 16; i += 256) reinterpret_cast<uint4*>(sA)[i] = z4;
-        if (tid < 128) ctl->tfix[tid] = 0;
-        float ww[EPT], dsv[EPT], vv[EPT];
-#pragma unroll
-        for (int u = 0; u < EPT; ++u) {
-          const int e = u * 256 + tid;
-          if (jj[u] >= 0 && jj[u] < 128) { ww[u] = w_b[e]; dsv[u] = __ldcg(ds_b + e); vv[u] = v_b[e]; }
+          if (jj[u] >= 0 && jj[u] < 128) dsv[u] = __ldcg(ds_b + e);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        GVIT_TR(23);
         // phase 1: the row's own k entries of dS (forward edges j -> i)
         if (valid) {
           const float rnj = ctl->rn[jg];
           int tacc = 0;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            if (u < kk1) {
-              if (nb_ok(ii1[u], Np)) *a2_cell(sA, tid, NT + ii1[u]) = __float2bfloat16_rn(rnj * ctl->rn[ii1[u]] * ds1[u]);
-              tacc += __float2int_rn(ds1[u] * vv1[u] * tscale);
+          for (int u = 0; u < KT; ++u) {
+            if (u < k) {
+              if (nb_ok(nb[u], Np)) *a2_cell(sA, tid, NT + nb[u]) = __float2bfloat16_rn(rnj * ctl->rn[nb[u]] * dsown[u]);
+              tacc += __float2int_rn(dsown[u] * vj[u] * tscale);
             }
-          }
-          for (int s = 8; s < k; ++s) {                               // k > 8: the remaining own entries, one by one
-            const int e = jg * k + s;
-            const int i = idx_b[e];
-            const float ds = __ldcg(ds_b + e);
-            if (nb_ok(i, Np)) *a2_cell(sA, tid, NT + i) = __float2bfloat16_rn(rnj * ctl->rn[i] * ds);
-            tacc += __float2int_rn(ds * v_b[e] * tscale);
           }
           atomicAdd(&ctl->tfix[tid], tacc);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        GVIT_TR(24);
         // phase 2: every edge i -> j of the image that lands in this tile: A~^T[j,i] = w_e, M3[j,i] += rn_j rn_i dS_e.
         // (j,i) pairs are unique over the edges (a row's k neighbours are distinct), so the 16-bit updates do not race.
         auto apply_edge = [&](int e, int j, float we, float ds, float v) {
@@ -399,6 +418,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
           if (j >= 0 && j < 128) apply_edge(e, j, w_b[e], __ldcg(ds_b + e), v_b[e]);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        GVIT_TR(25);
         // phase 3: the radial term on the diagonal
         if (valid) {
           const float rnj = ctl->rn[jg];
@@ -530,6 +550,7 @@ int graph_bwd_pair_tc(const Tokens& t, int k, const int32_t* idx, const float* v
   P.idx = idx; P.w = w; P.vals = vals; P.dvals = dvals; P.rnorm = rnorm;
   P.dp = static_cast<__nv_bfloat16*>(dp); P.dp_bs = t.batch_stride; P.dp_rs = t.row_stride;
   P.kmagic = (uint32_t)((0x100000000ull + (uint64_t)k - 1) / (uint64_t)k);
+  P.kvec = (k == 4 || k == 8 || k == 16) && aligned16(idx) && aligned16(w) && aligned16(vals) && aligned16(dvals);
   if (k <= 4) return launch_pair<4>(tm, P, smem, st);
   if (k <= 8) return launch_pair<8>(tm, P, smem, st);
   return launch_pair<16>(tm, P, smem, st);
