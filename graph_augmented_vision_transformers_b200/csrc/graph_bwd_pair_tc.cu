@@ -10,15 +10,21 @@
 // rows - and every B operand is split between the two CTAs: phase A stages half of P's tokens, phase B half of each
 // 128-feature chunk (one 64-feature slab of dZ and one of P).  Both row tiles are served by the SAME pass over the slabs
 // (M = 256), so a CTA streams 0.35 + 0.32 MB per image instead of 1.9 MB.
-// Measured (profiles/r4n_*): 0.1018 ms against 0.1131 ms for the one-CTA kernel at B = 256 (same box).  Both of its GEMM phases
+// Measured (profiles/r4n_*): 0.1018 ms against 0.1131 ms for the one-CTA kernel at B = 256 (same box); 0.0923 ms after r5.  Both of its GEMM phases
 // now run at the chip-wide rate at which L2 delivers UNIQUE operand bytes (~6.5 TB/s: phase A 12-14k cycles per image while
 // all pairs stream, 6.7k once the others have finished; phase B 2.0-2.2k cycles per chunk against 1.7k of tensor time), and
 // the extraction / build in between (11-12k cycles per image) streams nothing.  Starting the odd pairs 12k / 20k / 28k cycles
 // late so that the phases interleave chip-wide changed nothing (0.1007 / 0.1048 / 0.1108 ms).
 //
-// Cross-CTA data: the coefficient tile of a row tile needs dvals (dS) of ALL rows of the image - the peer's rows come
-// through global memory (dvals is an output anyway), ordered by a release / acquire mbarrier handshake at cluster scope,
-// which also carries the peer's max |dS S| for the fixed-point scale of the radial term.
+// Cross-CTA data: the coefficient tile of a row tile needs dvals (dS) of ALL rows of the image.  For k <= 8 (the image's
+// 256 x k values fit behind the control block) every row thread sends its k values straight into the peer's shared memory
+// with `st.async ... mbarrier::complete_tx::bytes`, the peer's max |dS S| (fixed-point scale of the radial term) follows the
+// same way, and the receiving CTA's one arrival is its own expect_tx of those bytes: no fence, no global round trip
+// (r5: 0.0964 -> 0.0923 ms; the same exchange as st.shared::cluster + one mbarrier.arrive.release.cluster made the
+// arriving thread wait ~6k cycles behind the CTA's global dvals stores).  Larger k: through global memory (dvals is an
+// output anyway) behind a release / acquire mbarrier handshake at cluster scope.  The row thread keeps its neighbour list,
+// similarities and dS entries in registers from the extraction into the build; the peer-independent build operands are
+// fetched and the tile is zeroed while the exchange is in flight (r5: 0.1016 -> 0.0964 ms).
 // TMEM per CTA: G [0, NT) | output chunk buffers [256, 384), [384, 512).  Shared memory: coefficient tile (nblk x 16 KB,
 // doubles as the extraction scratch) | ring of four NT x 64 slots.
 // Warp roles: 0-7 workers (extract: warps 0-3, thread <-> row; build and output: all), 8 TMA producer (both CTAs), 9 MMA
@@ -65,6 +71,17 @@ __device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_
     }
   }
 }
+// asynchronous stores into the peer CTA's shared memory that count their bytes on the peer's mbarrier: the data is visible to
+// whoever observes that barrier's phase complete - no release fence on the sending side (an mbarrier.arrive.release.cluster
+// behind 128 threads' global dvals stores cost the arriving thread ~6k cycles)
+__device__ __forceinline__ void st_async_b32(uint32_t dst_cluster, uint32_t v, uint32_t mbar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst_cluster), "r"(v), "r"(mbar_cluster) : "memory");
+}
+__device__ __forceinline__ void st_async_f32x4(uint32_t dst_cluster, float4 v, uint32_t mbar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(dst_cluster), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)),
+                 "r"(mbar_cluster) : "memory");
+}
 __device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
   asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
 }
@@ -78,6 +95,8 @@ struct __align__(8) QCtrl {
 };
 struct QParams {
   int B, Np, D, k, NT, nblk, slot_bytes;
+  int dsx;                                     // the image's dvals (256 x k fp32) fit behind QCtrl: the pair exchanges them through
+                                               // distributed shared memory instead of global memory + __threadfence
   int kvec;                                    // k in {4, 8, 16} == KT and idx / w / vals / dvals 16-byte aligned: whole rows by vector access
   uint32_t kmagic;                             // ceil(2^32 / k): e / k == __umulhi(e, kmagic) for e < 2^16
   const int32_t* idx;
@@ -98,6 +117,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
   if ((smem_u32(sA) & 1023u) != 0) __trap();
   uint8_t* ring = sA + (size_t)P.nblk * TILE;              // Q_SLOTS slots of [NT][64]
   QCtrl* ctl = reinterpret_cast<QCtrl*>(ring + (size_t)Q_SLOTS * P.slot_bytes);
+  float* ds_img = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ctl + 1) + 15) & ~static_cast<uintptr_t>(15));   // P.dsx: dS of every edge of the image, [256 rows][k], both CTAs hold a copy
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -329,17 +349,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
               for (int j = 0; j < KT; ++j)
                 if (j < k) ds_b[o + j] = d[j];
             }
+            if (P.dsx) {                                               // my rows into my own copy and into the peer's
+              const uint32_t peer_ds = mapa_u32(smem_u32(ds_img + o), rank ^ 1);
+              if (P.kvec) {
+#pragma unroll
+                for (int j = 0; j < KT; j += 4) {
+                  const float4 d4 = make_float4(d[j], d[j + 1], d[j + 2], d[j + 3]);
+                  *reinterpret_cast<float4*>(ds_img + o + j) = d4;
+                  st_async_f32x4(peer_ds + 4 * j, d4, peer_bar);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < KT; ++j)
+                  if (j < k) { ds_img[o + j] = d[j]; st_async_b32(peer_ds + 4 * j, __float_as_uint(d[j]), peer_bar); }
+              }
+            }
             atomicMax(&ctl->tmax_own[it & 1], __float_as_int(m));       // non-negative floats order like their bit patterns
           }
         }
         GVIT_TR(21);
         tc_fence_before();
-        __threadfence();                                               // this CTA's dvals rows: visible to the peer
+        if (!P.dsx) __threadfence();                                   // this CTA's dvals rows in global memory: visible to the peer
         asm volatile("bar.sync 1, 256;" ::: "memory");                 // G read out, scratch free, tmax_own final
         GVIT_TR(22);
         if (tid == 0) {
-          st_cluster_u32(mapa_u32(smem_u32(&ctl->tmax_peer[it & 1]), rank ^ 1), (uint32_t)ctl->tmax_own[it & 1]);
-          mbar_arrive_release_cluster(peer_bar);                        // "my rows of dvals and my maximum are published"
+          if (P.dsx) {
+            // my maximum follows my rows as one more counted store; the one arrival of MY barrier's phase is my own expect_tx
+            // of everything the peer sends: its valid rows x k dS values + its maximum
+            st_async_b32(mapa_u32(smem_u32(&ctl->tmax_peer[it & 1]), rank ^ 1), (uint32_t)ctl->tmax_own[it & 1], peer_bar);
+            const int peer_rows = rank == 0 ? Np - 128 : 128;           // the pair kernel runs for 128 < Np <= 256 only
+            mbar_expect_tx(&ctl->peer, (uint32_t)(peer_rows * k * 4 + 4));
+          } else {
+            st_cluster_u32(mapa_u32(smem_u32(&ctl->tmax_peer[it & 1]), rank ^ 1), (uint32_t)ctl->tmax_own[it & 1]);
+            mbar_arrive_release_cluster(peer_bar);                      // "my rows of dvals and my maximum are published"
+          }
           ctl->tmax_own[(it + 1) & 1] = 0;                              // nobody touches the other image parity right now
         }
         // while the handshake is in flight: everything of the build that does not need the peer's dvals
@@ -358,7 +401,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
           const int e = u * 256 + tid;
           if (jj[u] >= 0 && jj[u] < 128) { ww[u] = w_b[e]; vv[u] = v_b[e]; }
         }
-        mbar_wait_acquire_cluster(&ctl->peer, it & 1);                 // ... and so are the peer's
+        if (P.dsx) mbar_wait(&ctl->peer, it & 1);                      // the peer's rows and maximum have landed in my shared memory
+        else mbar_wait_acquire_cluster(&ctl->peer, it & 1);            // ... the peer's rows are published in global memory
         GVIT_TR(11);
       }
       // fixed-point scale of t_j: every term is <= M = max |dS_e S_e| < 2^(e+1), a row sums at most 2^9 of them, so terms
@@ -382,7 +426,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
 #pragma unroll
         for (int u = 0; u < EPT; ++u) {
           const int e = u * 256 + tid;
-          if (jj[u] >= 0 && jj[u] < 128) dsv[u] = __ldcg(ds_b + e);
+          if (jj[u] >= 0 && jj[u] < 128) dsv[u] = P.dsx ? ds_img[e] : __ldcg(ds_b + e);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         GVIT_TR(23);
@@ -415,7 +459,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
           if (jj[u] >= 0 && jj[u] < 128) apply_edge(u * 256 + tid, jj[u], ww[u], dsv[u], vv[u]);
         for (int e = EPT * 256 + tid; e < E; e += 256) {              // images with more than 2048 edges
           const int j = idx_b[e] - j0;
-          if (j >= 0 && j < 128) apply_edge(e, j, w_b[e], __ldcg(ds_b + e), v_b[e]);
+          if (j >= 0 && j < 128) apply_edge(e, j, w_b[e], P.dsx ? ds_img[e] : __ldcg(ds_b + e), v_b[e]);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         GVIT_TR(25);
@@ -546,7 +590,9 @@ int graph_bwd_pair_tc(const Tokens& t, int k, const int32_t* idx, const float* v
   if (rc != GVIT_OK) return rc;
   QParams P;
   P.B = t.B; P.Np = t.Np; P.D = t.D; P.k = k; P.NT = NT;
-  const size_t smem = q_smem(NT, &P.nblk, &P.slot_bytes);
+  size_t smem = q_smem(NT, &P.nblk, &P.slot_bytes);
+  P.dsx = smem + (size_t)256 * k * 4 + 16 <= 227 * 1024;
+  if (P.dsx) smem += (size_t)256 * k * 4 + 16;
   P.idx = idx; P.w = w; P.vals = vals; P.dvals = dvals; P.rnorm = rnorm;
   P.dp = static_cast<__nv_bfloat16*>(dp); P.dp_bs = t.batch_stride; P.dp_rs = t.row_stride;
   P.kmagic = (uint32_t)((0x100000000ull + (uint64_t)k - 1) / (uint64_t)k);
