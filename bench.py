@@ -208,6 +208,8 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
     idxs = [ops.knn_graph(h, k) for h in hs]
     w = torch.empty(B, Np, k, device=dev); z = torch.empty(B, Np, D, device=dev, dtype=bf)
     out = torch.empty(B, N, D, device=dev, dtype=bf)
+    xs32 = [torch.randn(B, N, D, device=dev, generator=g) for _ in range(2)]
+    out32 = torch.empty(B, N, D, device=dev)
     rev = [ops.graph_reverse(i[0]) for i in idxs]
     dvals = torch.empty(B, Np, k, device=dev)
     ao = torch.empty(B, N, D, device=dev, dtype=bf); lse = torch.empty(B, H, N, device=dev)
@@ -228,8 +230,13 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
         # name: (launch fn(i), algorithmic bytes, flops, bound, launches per training step)
         "knn_fwd": (lambda i: _call("gvit_knn_fwd", _ptr(hs[i % R], off), bs, rs, B, Np, D, k, dt, _ptr(idx), _ptr(vals), _ptr(rnorm), st),
                     tok + B * Np * k * 8, 2.0 * B * Np * Np * D, "hbm", 12),
-        "agg_fwd": (lambda i: _call("gvit_agg_fwd", _ptr(hs[i % R]), B, Np, D, k, dt, _ptr(idxs[i % R][0]), _ptr(idxs[i % R][1]), _ptr(W), _ptr(bias), _ptr(xs[i % R]), dt, _ptr(out), _ptr(w), _ptr(z), Np * D, st),
-                    3 * tok + B * Np * k * 8, 2.0 * B * Np * D * (k + D), "tensor", 12),
+        # agg_fwd = the instantiation the training step runs: fp32 residual stream in, fp32 stream out (5 x tok bytes; at that
+        # traffic the HBM roofline is the tighter one: 388.6 MB / 6.55 TB/s = 59 us against 36 us of tensor time)
+        "agg_fwd": (lambda i: _call("gvit_agg_fwd", _ptr(hs[i % R]), B, Np, D, k, dt, _ptr(idxs[i % R][0]), _ptr(idxs[i % R][1]), _ptr(W), _ptr(bias), _ptr(xs32[i % 2]), 0, _ptr(out32), _ptr(w), _ptr(z), Np * D, st),
+                    5 * tok + B * Np * k * 8, 2.0 * B * Np * D * (k + D), "auto", 12),
+        # the same kernel on a bf16 residual stream (fp32_residual=False, inference in bf16): 3 x tok bytes, tensor and HBM floors equal
+        "agg_fwd_bf16_stream": (lambda i: _call("gvit_agg_fwd", _ptr(hs[i % R]), B, Np, D, k, dt, _ptr(idxs[i % R][0]), _ptr(idxs[i % R][1]), _ptr(W), _ptr(bias), _ptr(xs[i % R]), dt, _ptr(out), _ptr(w), _ptr(z), Np * D, st),
+                                3 * tok + B * Np * k * 8, 2.0 * B * Np * D * (k + D), "tensor", 0),
         "attn_fwd": (lambda i: _call("gvit_attn_fwd", _ptr(qkvs[i % 2]), B, N, H, 64, 0.125, dt, _ptr(ao), _ptr(lse), st),
                      4 * B * N * D * e + 4 * B * H * N, 4.0 * B * N * N * D, "hbm", 12),
         "attn_bwd": (lambda i: _call("gvit_attn_bwd", _ptr(qkvs[i % 2]), _ptr(ao), _ptr(xs[i % R]), _ptr(lse), B, N, H, 64, 0.125, dt, _ptr(delta), _ptr(dqkv), st),
@@ -319,6 +326,8 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
             groups.append(a.elapsed_time(b) / iters)
         ms = statistics.median(groups)
         gbs, tfs = nbytes / ms / 1e6, flops / ms / 1e9
+        if bound == "auto":                                  # whichever roofline gives the longer floor at these bytes / FLOPs
+            bound = "hbm" if nbytes / (peaks["hbm"] * 1e9) >= flops / (peaks["tf_burst"] * 1e12) else "tensor"
         if bound == "hbm":
             ach, peak, unit = gbs, peaks["hbm"], "GB/s"
         else:

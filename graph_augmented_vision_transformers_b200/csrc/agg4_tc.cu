@@ -341,9 +341,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
       const bool zsave = P.z_save != nullptr && I.primary;
       // residual rows of this warp for output chunk n, coalesced (lane -> rows r8 + 4i, 16-byte chunk ch8)
       // RES32: a 64-feature chunk is 256 bytes per row = two 128-byte halves (32 features each)
-      auto load_resid = [&](int n, uint4 (&rr)[8 * NH]) {
+      // (RES32: one half at a time - 16 outstanding 16-byte loads per thread stalled the issuing warp for thousands of cycles
+      //  behind the L1 miss queue when the memory system was busy, 8 at two different points of the chunk do not)
+      auto load_resid = [&](int n, uint4 (&rr)[8 * NH], int h0, int h1) {
 #pragma unroll
-        for (int hh = 0; hh < NH; ++hh)
+        for (int hh = 0; hh < NH; ++hh) {
+          if (hh < h0 || hh >= h1) continue;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = r8 + 4 * i;
@@ -354,6 +357,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
               else rr[i] = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(P.resid) + e + ch8 * 8);
             }
           }
+        }
       };
       uint4 rnext[8 * NH];
       // ---- Z phase: BOTH warpgroups convert every step, warpgroup g the 64 staging columns [64 g, 64 g + 64) -> packed bf16
@@ -411,8 +415,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
           }
         }
       }
-      load_resid(2 * I.c0 + g, rnext);                                   // first chunk of this warpgroup: in flight during the build
+      load_resid(2 * I.c0 + g, rnext, 0, 1);                             // first chunk of this warpgroup: in flight during the build
       if (get_item(iter + 1, cid, ncl, P.B, nchunk, Inext)) build_adj(Inext.b, iter + 1, Inext.primary);   // next adjacency tile, under this projection
+      if constexpr (RES32) load_resid(2 * I.c0 + g, rnext, 1, 2);
       // ---- projection epilogue (chunks of parity g): + bias + residual, coalesced through the warp staging
       // (warpgroup g takes the 64-feature half g of every 128-feature chunk: 64-feature index n = 2 * chunk + g)
       for (int n = 2 * I.c0 + g; n < 2 * I.c1; n += 2) {
@@ -426,7 +431,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
           *reinterpret_cast<uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4)) = rnext[i];
         }
         GVIT_TR(24);
-        if constexpr (!RES32) load_resid(n + 2, rnext);                  // next chunk of this warpgroup: in flight meanwhile
+        load_resid(n + 2, rnext, 0, 1);                                  // next chunk of this warpgroup (its first half): in flight meanwhile
         __syncwarp();
         GVIT_TR(17);
         mbar_wait(&ctl->out_full, full_seen & 1);
@@ -471,7 +476,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
                 const int r = r8 + 4 * i;
                 *reinterpret_cast<uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4)) = rnext[8 + i];
               }
-              load_resid(n + 2, rnext);                                  // both halves consumed: next chunk in flight
+              load_resid(n + 2, rnext, 1, 2);                            // second half of the next chunk
               __syncwarp();
             }
             const float* vv = hh == 0 ? v0 : v1;
@@ -525,10 +530,9 @@ int launch2(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const CUtensorMa
       pairs = num_sms() / 2;
     }
   }
-  if (const char* e = getenv("GVIT_AGG_MAXPAIRS")) {                     // experiment switch: fewer pairs -> is the kernel bound per SM or chip-wide?
-    const int m = atoi(e);
-    if (m >= 1 && m < pairs) pairs = m;
-  }
+  // experiment switch (profiles/r5b_batch_sweep.txt): fewer pairs -> is the kernel bound per SM or chip-wide?
+  static const int max_pairs = [] { const char* e = getenv("GVIT_AGG_MAXPAIRS"); return e ? atoi(e) : 0; }();
+  if (max_pairs >= 1 && max_pairs < pairs) pairs = max_pairs;
   // fewer images than pairs: two pairs per image when they fit (get_item splits the output chunks between them)
   const int used = P.B >= pairs ? pairs : (2 * P.B <= pairs && (P.D / 128) % 2 == 0 ? 2 * P.B : P.B);
   const int grid = 2 * used;

@@ -51,3 +51,15 @@ gaps.sort()
 n = len(gaps)
 print(f"{len(ev)} kernels, span {span:.3f} ms, summed kernel time {busy:.3f} ms, idle {span - busy:.3f} ms ({100 * (span - busy) / span:.1f} %)")
 print(f"gap between consecutive kernels (us): median {gaps[n // 2]:.2f}, p90 {gaps[int(n * 0.9)]:.2f}, max {gaps[-1]:.2f}, sum {sum(gaps) / 1e3:.3f} ms")
+
+# ---- three replays back to back: what separates one replay's last kernel from the next replay's first (steady state) ----
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(3):
+        cap(img, tgt)
+    torch.cuda.synchronize()
+ev = sorted(((e.time_range.start, e.time_range.end, e.name) for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA),
+            key=lambda t: t[0])
+gaps = sorted(((ev[i + 1][0] - ev[i][1], i) for i in range(len(ev) - 1)), reverse=True)[:4]
+print(f"three replays back to back: {len(ev)} device events, total span {(ev[-1][1] - ev[0][0]) / 1e3:.3f} ms")
+for g, i in gaps:
+    print(f"  gap {g:9.2f} us after [{ev[i][2][:60]}] before [{ev[i + 1][2][:60]}] (event {i + 1} of {len(ev)})")

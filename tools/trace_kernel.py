@@ -41,6 +41,9 @@ for t, warp, eid in ev[: args.max]:
 # per-CTA spans (globaltimer ns) of the LAST traced launch: launch skew, imbalance, tail
 live = [(int(b), int(e)) for b, e in span if b != 0 and e != 0]
 if live:
+    t00 = min(b for b, _ in live)
+    late = sorted(((int(e) - t00, i) for i, (b, e) in enumerate(span) if b != 0 and e != 0), reverse=True)[:12]
+    print("# latest CTAs (end ns, blockIdx.x): " + ", ".join(f"{t}:{i}" for t, i in late))
     t0 = min(b for b, _ in live)
     ends = sorted(e - t0 for _, e in live)
     begins = sorted(b - t0 for b, _ in live)
