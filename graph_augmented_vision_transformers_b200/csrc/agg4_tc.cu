@@ -48,20 +48,23 @@ using namespace tc;
 constexpr int THREADS = 320;
 constexpr int TILE = 128 * 128;             // [128 rows][64 bf16]
 constexpr int A_BYTES = 4 * TILE;           // A~ [128][256] as four 64-column blocks
-constexpr int SLOT = 32 * 1024;             // ring slot: one token slab [<=256][64] or one W piece (<= 8 boxes of [32][64])
-constexpr int NSLOT = 4;
-constexpr int WSTAGE = 4 * 1024;            // per-warp staging ([32 rows][128 B]) for coalesced global access
+constexpr int SLOT = 16 * 1024;             // ring slot: HALF a token slab ([<=128 tokens][64]) or one W piece (2 boxes of [64][64])
+constexpr int NSLOT = 6;
+constexpr int WSTAGE = 4 * 1024;            // staging tile ([32 rows][128 B]): residual in (TMA load), result out (TMA store)
+constexpr int NSTG = 2;                     // two staging tiles per row warp: one loading / storing while the other is worked on
 constexpr int T_OUT = 384;                  // first OUT chunk buffer / odd Z staging
 
 struct __align__(8) Ctrl {
   uint64_t full[NSLOT], empty[NSLOT], a_ready, a_free, zs_full[2], conv_done[2], out_full, out_free;
+  uint64_t rbar[8][NSTG];                   // per row warp and staging tile: the residual tile has landed
   uint32_t tmem_base;
   __align__(16) __nv_bfloat16 bias[768];
 };
-constexpr size_t SMEM_BYTES = A_BYTES + NSLOT * SLOT + 8 * WSTAGE + sizeof(Ctrl);
+constexpr size_t SMEM_BYTES = A_BYTES + NSLOT * SLOT + 8 * NSTG * WSTAGE + sizeof(Ctrl);
 
 struct Params {
   int B, Np, D, k, NT;
+  int R0;                                   // tokens in the first half-slab: a multiple of 16, the second holds NT - R0 (<= R0)
   int kvec;                                 // k == KT and idx / vals / w_save 16-byte aligned: whole adjacency rows by vector access
   const int32_t* idx;
   const float* vals;
@@ -79,6 +82,8 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+__device__ __forceinline__ int wrow0_of(int rank, int warp) { return rank * 128 + (warp & 3) * 32; }
 
 // consume completions of `bar` until `seen` reaches `need` (one parity wait per completion: never skips a phase)
 __device__ __forceinline__ void wait_upto(uint64_t* bar, uint32_t& seen, uint32_t need) {
@@ -112,13 +117,14 @@ template <int KT, bool RES32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_kernel(const __grid_constant__ CUtensorMap tm_tok,
                                                                                        const __grid_constant__ CUtensorMap tm_w,
                                                                                        const __grid_constant__ CUtensorMap tm_z,
-                                                                                       const __grid_constant__ CUtensorMap tm_out, const Params P) {
+                                                                                       const __grid_constant__ CUtensorMap tm_out,
+                                                                                       const __grid_constant__ CUtensorMap tm_res, const Params P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sA = smem_raw;
   if ((smem_u32(sA) & 1023u) != 0) __trap();
   uint8_t* sRing = sA + A_BYTES;
   uint8_t* sStg = sRing + NSLOT * SLOT;
-  Ctrl* ctl = reinterpret_cast<Ctrl*>(sStg + 8 * WSTAGE);
+  Ctrl* ctl = reinterpret_cast<Ctrl*>(sStg + 8 * NSTG * WSTAGE);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   GVIT_TRACE_DECL
@@ -128,13 +134,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
   const int D = P.D, NT = P.NT;
   const int nchunk = D / 128;               // 128-feature output chunks (64 W rows per CTA)
   const int nstep = D / 128;                // Z steps of 128 features (64 per CTA)
-  const int npiece = (D + 255) / 256;       // W pieces of (up to) 256 reduction columns per output chunk: 4 boxes of [64][64]
+  const int npiece = D / 128;               // W pieces of 128 reduction columns per output chunk: 2 boxes of [64][64]
 
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tm_tok);
     prefetch_tmap(&tm_w);
     prefetch_tmap(&tm_z);
     prefetch_tmap(&tm_out);
+    prefetch_tmap(&tm_res);
+    for (int w8 = 0; w8 < 8; ++w8)
+      for (int s = 0; s < NSTG; ++s) mbar_init(&ctl->rbar[w8][s], 1);
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&ctl->zs_full[s], 1);
@@ -160,21 +169,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
       Item I;
       for (int it = 0; get_item(it, cid, ncl, P.B, nchunk, I); ++it) {
         const int b = I.b;
-        for (int t = 0; t < nstep; ++t, ++c) {                         // this CTA's 64-feature token slab of step t
-          const uint32_t sl = c % NSLOT;
-          mbar_wait(&ctl->empty[sl], ((c / NSLOT) & 1) ^ 1);
-          if (rank == 0) mbar_expect_tx(&ctl->full[sl], (uint32_t)(2 * NT * 128));
-          tma_load_3d_2sm(sRing + sl * SLOT, &tm_tok, (2 * t + rank) * 64, 0, b, mapa_u32(smem_u32(&ctl->full[sl]), 0));
+        for (int t = 0; t < nstep; ++t) {                              // this CTA's 64-feature token slab of step t, as two
+          for (int hf = 0; hf < 2; ++hf, ++c) {                        // half-slabs of R0 tokens (rows >= Np arrive as zeros)
+            const uint32_t sl = c % NSLOT;
+            mbar_wait(&ctl->empty[sl], ((c / NSLOT) & 1) ^ 1);
+            if (rank == 0) mbar_expect_tx(&ctl->full[sl], (uint32_t)(2 * P.R0 * 128));
+            tma_load_3d_2sm(sRing + sl * SLOT, &tm_tok, (2 * t + rank) * 64, hf * P.R0, b, mapa_u32(smem_u32(&ctl->full[sl]), 0));
+          }
         }
-        for (int n = I.c0; n < I.c1; ++n) {                            // W rows [128 n + 64 rank, + 64), pieces of <= 256 columns
+        for (int n = I.c0; n < I.c1; ++n) {                            // W rows [128 n + 64 rank, + 64), pieces of 128 columns
           for (int p = 0; p < npiece; ++p, ++c) {
             const uint32_t sl = c % NSLOT;
-            const int nbox = min(4, (D - p * 256) / 64);
             mbar_wait(&ctl->empty[sl], ((c / NSLOT) & 1) ^ 1);
-            if (rank == 0) mbar_expect_tx(&ctl->full[sl], (uint32_t)(2 * nbox * 8192));
+            if (rank == 0) mbar_expect_tx(&ctl->full[sl], (uint32_t)(2 * 2 * 8192));
             const uint32_t fullL = mapa_u32(smem_u32(&ctl->full[sl]), 0);
-            for (int j = 0; j < nbox; ++j)
-              tma_load_3d_2sm(sRing + sl * SLOT + j * 8192, &tm_w, p * 256 + j * 64, n * 128 + rank * 64, 0, fullL);
+            for (int j = 0; j < 2; ++j)
+              tma_load_3d_2sm(sRing + sl * SLOT + j * 8192, &tm_w, p * 128 + j * 64, n * 128 + rank * 64, 0, fullL);
           }
         }
       }
@@ -201,18 +211,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
           } else {
             wait_upto(&ctl->conv_done[0], conv_seen0, conv_iss0);
           }
-          const uint32_t sl = c % NSLOT;
+          const uint32_t sl0 = c % NSLOT, sl1 = (c + 1) % NSLOT;
           GVIT_TR(2);
-          mbar_wait(&ctl->full[sl], (c / NSLOT) & 1);
+          mbar_wait(&ctl->full[sl0], (c / NSLOT) & 1);
+          mbar_wait(&ctl->full[sl1], ((c + 1) / NSLOT) & 1);
           tc_fence_after();
           GVIT_TR(3);
-          const uint32_t aTok = aR + sl * SLOT;
+          const uint32_t aTok0 = aR + sl0 * SLOT, aTok1 = aR + sl1 * SLOT;
+          const int K0 = P.R0 / 16;
           for (int ks = 0; ks < NT / 16; ++ks)
-            umma_ss_2sm(tmem + stg, make_sdesc(aA + (ks >> 2) * TILE + (ks & 3) * 32), make_sdesc(aTok + ks * 2048), idesc_z, ks > 0);
+            umma_ss_2sm(tmem + stg, make_sdesc(aA + (ks >> 2) * TILE + (ks & 3) * 32),
+                        make_sdesc(ks < K0 ? aTok0 + ks * 2048 : aTok1 + (ks - K0) * 2048), idesc_z, ks > 0);
           umma_commit_2sm_mc(&ctl->zs_full[par], 3);
-          umma_commit_2sm_mc(&ctl->empty[sl], 3);
+          umma_commit_2sm_mc(&ctl->empty[sl0], 3);
+          umma_commit_2sm_mc(&ctl->empty[sl1], 3);
           if (par) ++conv_iss1; else ++conv_iss0;
-          ++c;
+          c += 2;
         }
         umma_commit_2sm_mc(&ctl->a_free, 3);                           // the A~ tiles may be rebuilt for the next image
         wait_upto(&ctl->conv_done[0], conv_seen0, conv_iss0);          // every Z step is packed bf16 in TMEM
@@ -225,15 +239,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
           GVIT_TR(5);
           for (int p = 0; p < npiece; ++p, ++c) {
             const uint32_t sl = c % NSLOT;
-            const int nbox = min(4, (D - p * 256) / 64);
             mbar_wait(&ctl->full[sl], (c / NSLOT) & 1);
             tc_fence_after();
             GVIT_TR(6);
             const uint32_t aW = aR + sl * SLOT;
-            for (int j = 0; j < nbox; ++j)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                umma_ts_2sm(tmem + T_OUT, tmem + (p * 256 + j * 64 + kk * 16) / 2, make_sdesc(aW + j * 8192 + kk * 32), idesc_w,
+                umma_ts_2sm(tmem + T_OUT, tmem + (p * 128 + j * 64 + kk * 16) / 2, make_sdesc(aW + j * 8192 + kk * 32), idesc_w,
                             p > 0 || j > 0 || kk > 0);
             umma_commit_2sm_mc(&ctl->empty[sl], 3);
           }
@@ -249,10 +263,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
     const int row = threadIdx.x & 127;                                 // == TMEM lane
     const int rowg = rank * 128 + row;                                 // token row inside the image
     const bool valid = rowg < P.Np;
-    uint8_t* stg = sStg + warp * WSTAGE;                               // this warp's private staging (4 KB)
+    uint8_t* stg0 = sStg + warp * (NSTG * WSTAGE);                     // this warp's two private staging tiles (4 KB each)
+    const bool wact = wrow0_of(rank, warp) < P.Np;                     // warp-uniform: the warp owns at least one token row
+    uint32_t rph0 = 0, rph1 = 0;                                       // residual-tile arrivals consumed per staging tile
     const int wrow0 = rank * 128 + (warp & 3) * 32;                    // first token row of this warp
     const uint32_t tl = tmem_lane_base(tmem, warp);
-    const int ch8 = lane & 7, r8 = lane >> 3;                          // coalesced pattern: 8 lanes per 128-byte row segment
     const uint32_t a_readyL = mapa_u32(smem_u32(&ctl->a_ready), 0);
     const uint32_t conv_doneL0 = mapa_u32(smem_u32(&ctl->conv_done[0]), 0), conv_doneL1 = mapa_u32(smem_u32(&ctl->conv_done[1]), 0);   // in the leader
     const uint32_t out_freeL = mapa_u32(smem_u32(&ctl->out_free), 0);
@@ -262,7 +277,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
       for (int i = threadIdx.x; i < 768 / 8; i += 256)
         reinterpret_cast<uint4*>(ctl->bias)[i] = (P.bias && i < D / 8) ? reinterpret_cast<const uint4*>(P.bias)[i] : z4;
     }
-    constexpr int NH = RES32 ? 2 : 1;
     // ---- G4 + adjacency tile of image bb (the it-th of this pair): zero A~, then scatter each row's k softmax weights (bf16)
     //      at its neighbour columns.  Runs in the slot where the row warps would otherwise wait for the first projection
     //      chunk of the PREVIOUS image, so the MMA issuer finds a_ready complete when it gets to the next image.
@@ -339,27 +353,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
     for (int iter = 0; get_item(iter, cid, ncl, P.B, nchunk, I); ++iter) {
       const int b = I.b;
       const bool zsave = P.z_save != nullptr && I.primary;
-      // residual rows of this warp for output chunk n, coalesced (lane -> rows r8 + 4i, 16-byte chunk ch8)
-      // RES32: a 64-feature chunk is 256 bytes per row = two 128-byte halves (32 features each)
-      // (RES32: one half at a time - 16 outstanding 16-byte loads per thread stalled the issuing warp for thousands of cycles
-      //  behind the L1 miss queue when the memory system was busy, 8 at two different points of the chunk do not)
-      auto load_resid = [&](int n, uint4 (&rr)[8 * NH], int h0, int h1) {
-#pragma unroll
-        for (int hh = 0; hh < NH; ++hh) {
-          if (hh < h0 || hh >= h1) continue;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = r8 + 4 * i;
-            rr[hh * 8 + i] = make_uint4(0, 0, 0, 0);
-            if (P.resid && n < 2 * I.c1 && wrow0 + r < P.Np) {
-              const int64_t e = ((int64_t)b * (P.Np + 1) + 1 + wrow0 + r) * D + n * 64;
-              if constexpr (RES32) rr[hh * 8 + i] = *reinterpret_cast<const uint4*>(static_cast<const float*>(P.resid) + e + hh * 32 + ch8 * 4);
-              else rr[i] = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(P.resid) + e + ch8 * 8);
-            }
-          }
-        }
-      };
-      uint4 rnext[8 * NH];
       // ---- Z phase: BOTH warpgroups convert every step, warpgroup g the 64 staging columns [64 g, 64 g + 64) -> packed bf16
       //      at TMEM columns [64 t + 32 g, + 32), so a step's conversion takes half as long and overlaps the next step's MMAs;
       //      optional copy out for the backward (64 features per warpgroup and step) through the warp staging.
@@ -392,13 +385,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
         GVIT_TR(15);
         tmem_st16(dst, pk0);
         tmem_st16(dst + 16, pk1);
+        uint8_t* stgz = stg0 + par * WSTAGE;                             // steps alternate between the two staging tiles
         if (zsave) {                                                     // [32 rows][64 features] of this warp -> staging -> one TMA tile
-          if (lane == 0) tma_store_wait_read();                          // store (asynchronous: the warp's own LSU queue stays free)
+          if (lane == 0) {                                               // store (asynchronous); this tile's previous store (two steps
+            if (t < 2) tma_store_wait_read();                            // back, or the previous item's last ones) has read it - the
+            else tma_store_wait_read1();                                 // other tile's may still be pending
+          }
           __syncwarp();
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(pk0[4 * q], pk0[4 * q + 1], pk0[4 * q + 2], pk0[4 * q + 3]);
-            *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + q) ^ (lane & 7)) << 4)) = make_uint4(pk1[4 * q], pk1[4 * q + 1], pk1[4 * q + 2], pk1[4 * q + 3]);
+            *reinterpret_cast<uint4*>(stgz + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(pk0[4 * q], pk0[4 * q + 1], pk0[4 * q + 2], pk0[4 * q + 3]);
+            *reinterpret_cast<uint4*>(stgz + lane * 128 + (((4 + q) ^ (lane & 7)) << 4)) = make_uint4(pk1[4 * q], pk1[4 * q + 1], pk1[4 * q + 2], pk1[4 * q + 3]);
           }
         }
         tmem_st_wait();
@@ -410,46 +407,63 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
           fence_async_smem();
           __syncwarp();
           if (lane == 0 && wrow0 < P.Np) {                               // rows >= Np are clipped by the TMA unit
-            tma_store_3d(&tm_z, stg, t * 128 + g * 64, wrow0, b);
+            tma_store_3d(&tm_z, stgz, t * 128 + g * 64, wrow0, b);
             tma_store_commit();
           }
         }
       }
-      load_resid(2 * I.c0 + g, rnext, 0, 1);                             // first chunk of this warpgroup: in flight during the build
+      // ---- projection epilogue.  Unit = one [32 rows x 128 bytes] tile of this warp: the 64-feature half g of a chunk on a
+      //      bf16 stream, one 32-feature half of it on the fp32 stream.  Units alternate between the two staging tiles: while
+      //      unit u is worked on in tile u & 1 (residual tile landed by TMA -> + branch value + bias in place -> TMA store), the
+      //      residual tile of unit u + 1 is already loading into the other one.
+      constexpr int UPC = RES32 ? 2 : 1;                                 // units per chunk
+      const int nunit = (I.c1 - I.c0) * UPC;                             // this warpgroup's units of the item
+      const bool has_res = P.resid != nullptr;
+      auto load_unit = [&](int u, int tile) {                            // lane 0 only
+        if (u < nunit && has_res && wact) {
+          const int n = 2 * I.c0 + g + 2 * (u / UPC);                    // 64-feature index
+          uint64_t* bar = &ctl->rbar[warp][tile];
+          mbar_expect_tx(bar, (uint32_t)WSTAGE);
+          tma_load_3d(stg0 + tile * WSTAGE, &tm_res, n * 64 + (RES32 ? (u & 1) * 32 : 0), wrow0, b, bar);
+        }
+      };
+      if (lane == 0) { tma_store_wait_read(); load_unit(0, 0); }         // first residual tile: in flight during the build
+      __syncwarp();
       if (get_item(iter + 1, cid, ncl, P.B, nchunk, Inext)) build_adj(Inext.b, iter + 1, Inext.primary);   // next adjacency tile, under this projection
-      if constexpr (RES32) load_resid(2 * I.c0 + g, rnext, 1, 2);
-      // ---- projection epilogue (chunks of parity g): + bias + residual, coalesced through the warp staging
-      // (warpgroup g takes the 64-feature half g of every 128-feature chunk: 64-feature index n = 2 * chunk + g)
-      for (int n = 2 * I.c0 + g; n < 2 * I.c1; n += 2) {
+      float v0[32], v1[32];
+      for (int u = 0; u < nunit; ++u) {
+        const int tile = u & 1;
+        const int n = 2 * I.c0 + g + 2 * (u / UPC);
+        uint8_t* stg = stg0 + tile * WSTAGE;
         GVIT_TR(22);
-        if (lane == 0) tma_store_wait_read();                            // the staging tile's previous TMA store has read it
+        if (lane == 0) { tma_store_wait_read(); load_unit(u + 1, tile ^ 1); }   // the other tile's store has read it: refill it
         __syncwarp();
         GVIT_TR(23);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r8 + 4 * i;
-          *reinterpret_cast<uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4)) = rnext[i];
+        if (!RES32 || (u & 1) == 0) {                                    // a new chunk: take it out of TMEM and hand the buffer back
+          GVIT_TR(17);
+          mbar_wait(&ctl->out_full, full_seen & 1);
+          GVIT_TR(18);
+          ++full_seen;
+          tc_fence_after();
+          tmem_ld32(tl + T_OUT + g * 64, v0);
+          tmem_ld32(tl + T_OUT + g * 64 + 32, v1);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(out_freeL);
+          GVIT_TR(19);
+        }
+        if (!wact) continue;                                             // no token rows: nothing to add, nothing to store
+        if (has_res) {
+          mbar_wait(&ctl->rbar[warp][tile], (tile ? rph1 : rph0) & 1);   // the residual tile has landed
+          if (tile) ++rph1; else ++rph0;
         }
         GVIT_TR(24);
-        load_resid(n + 2, rnext, 0, 1);                                  // next chunk of this warpgroup (its first half): in flight meanwhile
-        __syncwarp();
-        GVIT_TR(17);
-        mbar_wait(&ctl->out_full, full_seen & 1);
-        GVIT_TR(18);
-        ++full_seen;
-        tc_fence_after();
-        float v0[32], v1[32];
-        tmem_ld32(tl + T_OUT + g * 64, v0);
-        tmem_ld32(tl + T_OUT + g * 64 + 32, v1);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(out_freeL);
-        GVIT_TR(19);
         if constexpr (!RES32) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const uint32_t off = lane * 128 + ((q ^ (lane & 7)) << 4);
-            const uint4 r4 = *reinterpret_cast<const uint4*>(stg + off);
+            uint4 r4 = make_uint4(0, 0, 0, 0);
+            if (has_res) r4 = *reinterpret_cast<const uint4*>(stg + off);
             const uint4 b4 = *reinterpret_cast<const uint4*>(&ctl->bias[n * 64 + q * 8]);
             const float* vv = q < 4 ? &v0[8 * q] : &v1[8 * (q - 4)];
             const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
@@ -459,45 +473,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
               oo[e] = pack2(vv[2 * e] + bf_lo(bb[e]) + bf_lo(rr[e]), vv[2 * e + 1] + bf_hi(bb[e]) + bf_hi(rr[e]));
             *reinterpret_cast<uint4*>(stg + off) = make_uint4(oo[0], oo[1], oo[2], oo[3]);
           }
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0 && wrow0 < P.Np) {                               // tm_out starts at token row 1: the CLS row is skipped
-            tma_store_3d(&tm_out, stg, n * 64, wrow0, b);
-            tma_store_commit();
-          }
         } else {
+          const int hh = u & 1;                                          // 32 features = 128 bytes of fp32 per row and half
+          const float* vv = hh == 0 ? v0 : v1;
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {                               // 32 features = 128 bytes of fp32 per row and half
-            if (hh == 1) {
-              if (lane == 0) tma_store_wait_read();
-              __syncwarp();
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int r = r8 + 4 * i;
-                *reinterpret_cast<uint4*>(stg + r * 128 + ((ch8 ^ (r & 7)) << 4)) = rnext[8 + i];
-              }
-              load_resid(n + 2, rnext, 1, 2);                            // second half of the next chunk
-              __syncwarp();
-            }
-            const float* vv = hh == 0 ? v0 : v1;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {                                // 4 features per 16-byte chunk
-              const uint32_t off = lane * 128 + ((q ^ (lane & 7)) << 4);
-              float4 r4 = *reinterpret_cast<const float4*>(stg + off);
-              const uint2 b2 = *reinterpret_cast<const uint2*>(&ctl->bias[n * 64 + hh * 32 + q * 4]);
-              // the branch value as the bf16 projection would store it, then the fp32 add (autocast semantics)
-              const uint32_t y01 = pack2(vv[4 * q] + bf_lo(b2.x), vv[4 * q + 1] + bf_hi(b2.x));
-              const uint32_t y23 = pack2(vv[4 * q + 2] + bf_lo(b2.y), vv[4 * q + 3] + bf_hi(b2.y));
-              r4.x += bf_lo(y01); r4.y += bf_hi(y01); r4.z += bf_lo(y23); r4.w += bf_hi(y23);
-              *reinterpret_cast<float4*>(stg + off) = r4;
-            }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0 && wrow0 < P.Np) {
-              tma_store_3d(&tm_out, stg, n * 64 + hh * 32, wrow0, b);
-              tma_store_commit();
-            }
+          for (int q = 0; q < 8; ++q) {                                  // 4 features per 16-byte chunk
+            const uint32_t off = lane * 128 + ((q ^ (lane & 7)) << 4);
+            float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_res) r4 = *reinterpret_cast<const float4*>(stg + off);
+            const uint2 b2 = *reinterpret_cast<const uint2*>(&ctl->bias[n * 64 + hh * 32 + q * 4]);
+            // the branch value as the bf16 projection would store it, then the fp32 add (autocast semantics)
+            const uint32_t y01 = pack2(vv[4 * q] + bf_lo(b2.x), vv[4 * q + 1] + bf_hi(b2.x));
+            const uint32_t y23 = pack2(vv[4 * q + 2] + bf_lo(b2.y), vv[4 * q + 3] + bf_hi(b2.y));
+            r4.x += bf_lo(y01); r4.y += bf_hi(y01); r4.z += bf_lo(y23); r4.w += bf_hi(y23);
+            *reinterpret_cast<float4*>(stg + off) = r4;
           }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {                                                 // tm_out starts at token row 1: the CLS row is skipped
+          tma_store_3d(&tm_out, stg, n * 64 + (RES32 ? (u & 1) * 32 : 0), wrow0, b);
+          tma_store_commit();
         }
       }
     }
@@ -511,8 +507,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
 }
 
 template <int KT, bool RES32>
-int launch2(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const CUtensorMap& tm_z, const CUtensorMap& tm_out, const Params& P,
-            cudaStream_t st) {
+int launch2(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const CUtensorMap& tm_z, const CUtensorMap& tm_out,
+            const CUtensorMap& tm_res, const Params& P, cudaStream_t st) {
   GVIT_CHECK_CUDA(cudaFuncSetAttribute(agg4_tc_kernel<KT, RES32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   int pairs = 0;
   {
@@ -536,14 +532,14 @@ int launch2(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const CUtensorMa
   // fewer images than pairs: two pairs per image when they fit (get_item splits the output chunks between them)
   const int used = P.B >= pairs ? pairs : (2 * P.B <= pairs && (P.D / 128) % 2 == 0 ? 2 * P.B : P.B);
   const int grid = 2 * used;
-  agg4_tc_kernel<KT, RES32><<<grid, THREADS, SMEM_BYTES, st>>>(tm_tok, tm_w, tm_z, tm_out, P);
+  agg4_tc_kernel<KT, RES32><<<grid, THREADS, SMEM_BYTES, st>>>(tm_tok, tm_w, tm_z, tm_out, tm_res, P);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }
 template <int KT>
-int launch(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const CUtensorMap& tm_z, const CUtensorMap& tm_out, const Params& P, bool res32,
-           cudaStream_t st) {
-  return res32 ? launch2<KT, true>(tm_tok, tm_w, tm_z, tm_out, P, st) : launch2<KT, false>(tm_tok, tm_w, tm_z, tm_out, P, st);
+int launch(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const CUtensorMap& tm_z, const CUtensorMap& tm_out, const CUtensorMap& tm_res,
+           const Params& P, bool res32, cudaStream_t st) {
+  return res32 ? launch2<KT, true>(tm_tok, tm_w, tm_z, tm_out, tm_res, P, st) : launch2<KT, false>(tm_tok, tm_w, tm_z, tm_out, tm_res, P, st);
 }
 
 }  // namespace
@@ -551,7 +547,7 @@ int launch(const CUtensorMap& tm_tok, const CUtensorMap& tm_w, const CUtensorMap
 GVIT_TRACE_SETTER(gvit_debug_set_trace_agg4)
 
 bool agg4_tc_supported(int Np, int D, int k) {
-  return Np >= 16 && Np <= 256 && D >= 128 && D % 128 == 0 && D <= 768 && k <= 16;
+  return Np > 128 && Np <= 256 && D >= 128 && D % 128 == 0 && D <= 768 && k <= 16;   // two row tiles; both half-slabs non-empty
 }
 
 int agg4_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, const float* vals, const void* Wg,
@@ -560,6 +556,7 @@ int agg4_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, 
   Params P;
   P.B = B; P.Np = Np; P.D = D; P.k = k;
   P.NT = (Np + 15) & ~15;
+  P.R0 = ((P.NT + 31) / 32) * 16;                                      // 144 <= NT <= 256: 80 <= R0 <= 128 tokens, NT - R0 in [64, R0]
   P.idx = idx; P.vals = vals;
   P.bias = static_cast<const __nv_bfloat16*>(bias);
   P.resid = resid;
@@ -570,9 +567,9 @@ int agg4_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, 
   P.z_save = static_cast<__nv_bfloat16*>(z_save);
   P.zbs = z_batch_stride;
 
-  CUtensorMap tm_tok, tm_w, tm_z, tm_out;
+  CUtensorMap tm_tok, tm_w, tm_z, tm_out, tm_res;
   const __nv_bfloat16* tok = static_cast<const __nv_bfloat16*>(h) + D;   // skip the CLS row (section 9, G0)
-  int rc = make_tmap_bf16_3d(&tm_tok, tok, D, Np, B, D, (uint64_t)(Np + 1) * D, P.NT);
+  int rc = make_tmap_bf16_3d(&tm_tok, tok, D, Np, B, D, (uint64_t)(Np + 1) * D, P.R0);   // half-slab boxes
   if (rc != GVIT_OK) return rc;
   rc = make_tmap_bf16_3d(&tm_w, Wg, D, D, 1, D, (uint64_t)D * D, 64);
   if (rc != GVIT_OK) return rc;
@@ -587,9 +584,16 @@ int agg4_fwd_tc(const void* h, int B, int Np, int D, int k, const int32_t* idx, 
   } else {
     tm_z = tm_out;                                                       // never dereferenced
   }
-  if (k <= 4) return launch<4>(tm_tok, tm_w, tm_z, tm_out, P, res32, st);
-  if (k <= 8) return launch<8>(tm_tok, tm_w, tm_z, tm_out, P, res32, st);
-  return launch<16>(tm_tok, tm_w, tm_z, tm_out, P, res32, st);
+  if (resid) {                                                         // residual tiles arrive through TMA loads (token row 1 onwards)
+    if (res32) rc = make_tmap_f32_3d(&tm_res, static_cast<const float*>(resid) + D, D, Np, B, D, (uint64_t)(Np + 1) * D, 32);
+    else rc = make_tmap_bf16_3d(&tm_res, static_cast<const __nv_bfloat16*>(resid) + D, D, Np, B, D, (uint64_t)(Np + 1) * D, 32);
+    if (rc != GVIT_OK) return rc;
+  } else {
+    tm_res = tm_out;                                                     // never dereferenced
+  }
+  if (k <= 4) return launch<4>(tm_tok, tm_w, tm_z, tm_out, tm_res, P, res32, st);
+  if (k <= 8) return launch<8>(tm_tok, tm_w, tm_z, tm_out, tm_res, P, res32, st);
+  return launch<16>(tm_tok, tm_w, tm_z, tm_out, tm_res, P, res32, st);
 }
 
 }  // namespace gvit
