@@ -15,26 +15,29 @@
 //   A~ tile    : 128 x NT dense bf16 adjacency rows in shared memory (zeroed, then each row's k softmax weights scattered);
 //                the tile of item n + 1 is built while item n's projection runs (the row warps would otherwise wait there).
 //   Z phase    : Z = A~ . P, 128 features per step: MMA M = 256, N = 128, K = tokens; rank r stages the 64-feature token
-//                slab 2 t + r (MN-major B).  fp32 result in a TMEM staging area, converted IN TENSOR MEMORY to packed bf16
+//                slab 2 t + r (MN-major B) as two half-slabs of R0 and NT - R0 tokens, one 16 KB ring slot each.  fp32 result in a TMEM staging area, converted IN TENSOR MEMORY to packed bf16
 //                by BOTH row warpgroups (64 staging columns each), so a step's conversion overlaps the next step's MMAs:
 //                the whole aggregated tile Z [128 x D] of a CTA ends up in TMEM columns [0, D/2) (training also sends each
 //                [32 rows x 64 features] piece out through a TMA store for the weight gradient).
 //   projection : per 128-feature output chunk OUT = Z . W_chunk^T, A from TMEM (TS form), N = 128 per instruction (a 2-SM
 //                MMA takes ~75-80 cycles whatever its N: 64-wide chunks ran the tensor pipe at 40 %); rank r stages W rows
-//                [128 n + 64 r, + 64) in pieces of 256 reduction columns.  ONE fp32 chunk buffer: TMEM is full, so the MMAs of
-//                chunk n + 1 wait until both warpgroups have read chunk n (~1.8k of the ~5.6k cycles per chunk: the bound of
-//                this design, see profiles/README.md).  Epilogue: warpgroup g takes the 64-feature half g of the chunk:
-//                + bias + residual in the warp's staging tile, then one TMA store per [32 rows x 128 bytes].
+//                [128 n + 64 r, + 64) in pieces of 128 reduction columns (16 KB).  ONE fp32 chunk buffer: TMEM is full, so the
+//                MMAs of chunk n + 1 wait until both warpgroups have read chunk n (~1.8k of the ~5.3k cycles per chunk: the
+//                bound of this design, see profiles/README.md).  Epilogue: warpgroup g takes the 64-feature half g of the
+//                chunk in units of [32 rows x 128 bytes] (one per chunk on a bf16 stream, two on the fp32 stream); every row
+//                warp owns two staging tiles used in turn: the unit's residual tile lands by TMA load while the previous unit
+//                is worked on, bias + branch value are added in place, one TMA store sends the tile out.
 // TMEM (512 columns per CTA): Z bf16 [0, D/2) | Z fp32 staging: step t even -> [64 t, 64 t + 128) (in place), odd ->
 //                [384, 512) | OUT chunk buffer [384, 512).
-// Shared memory per CTA: A~ (4 x 16 KB) | ring of 4 x 32 KB slots | 8 x 4 KB per-warp staging.
+// Shared memory per CTA: A~ (4 x 16 KB) | ring of 6 x 16 KB slots | 8 warps x 2 x 4 KB staging tiles.
 // Warp roles: 0-3 row warpgroup 0, 4-7 row warpgroup 1 (thread <-> token row = TMEM lane), 8 TMA producer (both CTAs),
 // 9 MMA issuer (leader) and TMEM owner.
 // Barriers.  In the leader, arrived at by both CTAs: full[slot] (TMA bytes), a_ready, conv_done[step parity], out_free.
 // In each CTA, released by multicast tcgen05.commit: empty[slot], a_free, zs_full[step parity], out_full.  The two warps
 // that share a TMEM lane quarter meet at a 64-thread named barrier inside every in-place conversion.  Every waiter counts
 // the completions it has consumed and waits for them one by one, so no barrier can run two phases ahead of a waiter.
-// Measured at B = 256, Np = 196, D = 768, k = 8 (training: w and Z saved): 0.0906 ms against 0.1210 ms for agg3 on the same box.
+// Measured at B = 256, Np = 196, D = 768, k = 8 (training: w and Z saved), same box: fp32 residual stream 0.1037 ms against
+// 0.1401 ms for agg3; bf16 stream 0.089-0.091 ms against 0.1210 ms.
 #include <float.h>
 
 #include "kernels.cuh"
