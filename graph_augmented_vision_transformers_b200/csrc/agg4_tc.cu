@@ -93,29 +93,6 @@ __device__ __forceinline__ void wait_upto(uint64_t* bar, uint32_t& seen, uint32_
   while (seen < need) { mbar_wait(bar, seen & 1); ++seen; }
 }
 
-// Work items of a pair.  Full rounds: image cid + it * ncl, every output chunk.  The images left over after the full rounds
-// (r = B mod ncl) would occupy r of the ncl pairs for a whole round; when 2 r <= ncl each of them is split between two pairs -
-// both run the Z phase, each projects one half of the 128-feature output chunks (a half item costs ~0.63 of an image), and
-// only the first half ("primary") writes the saved weights, the saved Z tile and the CLS row.
-struct Item { int b, c0, c1; bool primary; };
-__device__ __forceinline__ bool get_item(int it, int cid, int ncl, int B, int nchunk, Item& I) {
-  const int R = B / ncl, r = B - R * ncl;
-  I.c0 = 0; I.c1 = nchunk; I.primary = true;
-  if (it < R) { I.b = cid + it * ncl; return true; }
-  if (it > R || r == 0) return false;
-  if (2 * r <= ncl && (nchunk & 1) == 0) {
-    if (cid >= 2 * r) return false;
-    I.b = R * ncl + (cid >> 1);
-    I.primary = (cid & 1) == 0;
-    I.c0 = (cid & 1) * (nchunk >> 1);
-    I.c1 = I.c0 + (nchunk >> 1);
-    return true;
-  }
-  if (cid >= r) return false;
-  I.b = R * ncl + cid;
-  return true;
-}
-
 template <int KT, bool RES32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_kernel(const __grid_constant__ CUtensorMap tm_tok,
                                                                                        const __grid_constant__ CUtensorMap tm_w,

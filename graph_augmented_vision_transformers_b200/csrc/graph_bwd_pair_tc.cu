@@ -174,7 +174,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
           tma_prefetch_3d(&tm_pB, s * 64, rank * NH, b);
         }
       };
-      for (int b = cid; b < P.B; b += ncl) {
+      Item I, Inext;
+      for (int itp = 0; get_item(itp, cid, ncl, P.B, fblocks, I); ++itp) {
+        const int b = I.b;
         // every ring slot of the previous image's phase B consumed (its last commit also retires the MMAs that read the
         // coefficient tile)
         for (int q = 0; q < Q_SLOTS; ++q)
@@ -187,13 +189,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
           tma_load_3d_2sm(aslot(j), &tm_dzA, s * 64, rank * 128, b, fullL);
           tma_load_3d_2sm(aslot(j) + 128 * 128, &tm_pB, s * 64, rank * NH, b, fullL);
         }
-        if (b + ncl < P.B) prefetch_a(b + ncl);
+        if (get_item(itp + 1, cid, ncl, P.B, fblocks, Inext)) prefetch_a(Inext.b);
         // every phase-A slot consumed before the ring geometry of phase B is written
         for (uint32_t q = 0; q < (uint32_t)Q_ASLOTS && q < pa; ++q) {
           const uint32_t last = pa - 1 - ((pa - 1 - q) % Q_ASLOTS + Q_ASLOTS) % Q_ASLOTS;   // last load index that used slot q
           mbar_wait(&ctl->emptyA[q], (last / Q_ASLOTS) & 1);
         }
-        for (int f = 0; f < fblocks; ++f) {                                   // phase B: own 64 features of the chunk, all tokens
+        for (int f = I.c0; f < I.c1; ++f) {                                   // phase B: own 64 features of the chunk, all tokens
           cntB[pi & (Q_SLOTS - 1)]++;
           load(&tm_dzF, (2 * f + rank) * 64, 0, b, 2u * (uint32_t)NT * 128u);
           cntB[pi & (Q_SLOTS - 1)]++;
@@ -212,7 +214,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
       auto slot_addr = [&](uint32_t c) { return aR + (c & (Q_SLOTS - 1)) * (uint32_t)P.slot_bytes; };
       uint32_t ca = 0;                                                        // phase-A slab counter
       const uint32_t aC = smem_u32(sA);
-      for (int b = cid; b < P.B; b += ncl) {
+      Item I;
+      for (int itm = 0; get_item(itm, cid, ncl, P.B, fblocks, I); ++itm) {
         GVIT_TR(1);
         for (int s = 0; s < slabs; ++s, ++ca) {                               // G = dZ P^T (the previous image's G was read out
           const uint32_t j = ca % Q_ASLOTS;                                    // before its a_ready, i.e. before its phase B)
@@ -230,7 +233,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
         ++na;
         tc_fence_after();
         GVIT_TR(3);
-        for (int f = 0; f < fblocks; ++f) {
+        for (int f = I.c0; f < I.c1; ++f) {
           const uint32_t buf = tcount & 1;
           mbar_wait(&ctl->out_free[buf], (uses[buf] & 1) ^ 1);                 // this buffer's previous chunk drained by both CTAs
           ++uses[buf];
@@ -265,7 +268,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
     const uint32_t a_readyL = mapa_u32(smem_u32(&ctl->a_ready), 0);
     const uint32_t out_freeL0 = mapa_u32(smem_u32(&ctl->out_free[0]), 0), out_freeL1 = mapa_u32(smem_u32(&ctl->out_free[1]), 0);
     const uint32_t peer_bar = mapa_u32(smem_u32(&ctl->peer), rank ^ 1);
-    for (int b = cid; b < P.B; b += ncl, ++it) {
+    Item I;
+    for (; get_item((int)it, cid, ncl, P.B, fblocks, I); ++it) {
+      const int b = I.b;
       const int32_t* idx_b = P.idx + (int64_t)b * E;
       const float* w_b = P.w + (int64_t)b * E;
       const float* v_b = P.vals + (int64_t)b * E;
@@ -341,10 +346,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
               d[j] = j < k ? wj[j] * (dw[j] - s) : 0.f;
               m = fmaxf(m, fabsf(d[j] * vj[j]));
             }
-            if (P.kvec) {
+            // dvals is an output: written once per image (the pair that holds the other half of a split image computes the same
+            // values); without the shared-memory exchange it is also how the two CTAs of a pair see each other's rows
+            if (P.kvec && (I.primary || !P.dsx)) {
 #pragma unroll
               for (int j = 0; j < KT; j += 4) *reinterpret_cast<float4*>(ds_b + o + j) = make_float4(d[j], d[j + 1], d[j + 2], d[j + 3]);
-            } else {
+            } else if (I.primary || !P.dsx) {
 #pragma unroll
               for (int j = 0; j < KT; ++j)
                 if (j < k) ds_b[o + j] = d[j];
@@ -477,7 +484,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1) graph_
       }
       // ---- output chunks of this row tile: TMEM -> bf16 -> global (warp & 3 = lane quadrant, warp >> 2 = 64-feature half) ----
       const int hsel = warp >> 2;
-      for (int f = 0; f < fblocks; ++f, ++tcount) {
+      for (int f = I.c0; f < I.c1; ++f, ++tcount) {
         const uint32_t buf = tcount & 1;
         mbar_wait(&ctl->out_full[buf], (tcount >> 1) & 1);
         tc_fence_after();
@@ -560,7 +567,9 @@ int launch_pair(const CUtensorMap (&tm)[4], const QParams& P, size_t smem, cudaS
       pairs = num_sms() / 2;
     }
   }
-  const int grid = 2 * (P.B < pairs ? P.B : pairs);
+  // fewer images than pairs: two pairs per image when they fit (get_item splits the output chunks between them)
+  const int used = P.B >= pairs ? pairs : (2 * P.B <= pairs && (P.D / 128) % 2 == 0 ? 2 * P.B : P.B);
+  const int grid = 2 * used;
   graph_bwd_pair_kernel<KT><<<grid, Q_THREADS, smem, st>>>(tm[0], tm[1], tm[2], tm[3], P);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;

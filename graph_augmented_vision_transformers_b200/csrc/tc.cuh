@@ -301,6 +301,30 @@ __device__ __forceinline__ uint32_t swz128(int row, int col) {
   return static_cast<uint32_t>(row) * 128u + ((((static_cast<uint32_t>(col) >> 3) ^ (static_cast<uint32_t>(row) & 7u)) << 4));
 }
 
+// ---- work items of a persistent CTA pair (agg4_tc.cu, graph_bwd_pair_tc.cu) ----
+// Full rounds: image cid + it * ncl, every output chunk.  The images left over after the full rounds
+// (r = B mod ncl) would occupy r of the ncl pairs for a whole round; when 2 r <= ncl each of them is split between two pairs -
+// both run the per-image phases (Z phase / Gram product, extraction, build), each takes one half of the 128-feature output
+// chunks, and only the first half ("primary") writes the per-image side outputs (saved weights, saved Z, CLS row, dvals).
+struct Item { int b, c0, c1; bool primary; };
+__device__ __forceinline__ bool get_item(int it, int cid, int ncl, int B, int nchunk, Item& I) {
+  const int R = B / ncl, r = B - R * ncl;
+  I.c0 = 0; I.c1 = nchunk; I.primary = true;
+  if (it < R) { I.b = cid + it * ncl; return true; }
+  if (it > R || r == 0) return false;
+  if (2 * r <= ncl && (nchunk & 1) == 0) {
+    if (cid >= 2 * r) return false;
+    I.b = R * ncl + (cid >> 1);
+    I.primary = (cid & 1) == 0;
+    I.c0 = (cid & 1) * (nchunk >> 1);
+    I.c1 = I.c0 + (nchunk >> 1);
+    return true;
+  }
+  if (cid >= r) return false;
+  I.b = R * ncl + cid;
+  return true;
+}
+
 // ---- neighbour indices from an adjacency list ----
 // In range by contract (gvit_knn_fwd writes them), but the lists are caller-supplied pointers at the C ABI: an out-of-range
 // value must never become a shared-memory scatter.  Product builds skip such an edge; -DGVIT_DEBUG_BOUNDS builds trap with a message.
