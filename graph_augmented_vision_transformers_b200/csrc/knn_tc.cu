@@ -313,6 +313,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) knn_pair
   const int slabs = D / 64, NH = NT / 2;                   // NH tokens of the N extent per CTA
   GVIT_TRACE_DECL
   GVIT_SPAN(0);
+  GVIT_TR(30);
 
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -331,6 +332,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) knn_pair
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
+  GVIT_TR(33);
 
   if (warp == 8) {
     if (elect_one()) {
@@ -435,9 +437,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) knn_pair
       }
     }
   }
+  GVIT_TR(31);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
+  GVIT_TR(32);
   GVIT_SPAN(1);
   if (warp == 9) tmem_dealloc_2sm(tmem, TMEM_COLS);
 }
