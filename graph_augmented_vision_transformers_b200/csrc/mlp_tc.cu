@@ -54,9 +54,20 @@ constexpr int THREADS = (EPI_WARPS + 2) * 32;
 
 struct __align__(8) Ctrl {
   uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_free[2];
+  uint64_t rbar[EPI_WARPS];                   // fp32-stream MODE 1: this warp's residual tile has landed (TMA load)
   uint32_t tmem_base;
 };
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_WARPS * WSTAGE + sizeof(Ctrl);
+// Shared-memory layout per instantiation.  The fp32-stream Linear + dropout + residual (MODE 1, RES32) moves its residual / output
+// tiles by TMA as [32 rows][32 fp32] = 4 KB per epilogue warp (whole 128-byte lines; no registers, no LSU round trips), paid for
+// with one ring stage (5 instead of 6) and a separate 128-byte bias row per warp (the tile is the TMA target).
+template <int MODE, bool RES32>
+struct Lay {
+  static constexpr bool T32 = MODE == 1 && RES32;
+  static constexpr int NST = T32 ? 5 : STAGES;
+  static constexpr int WS = T32 ? 4096 : WSTAGE;
+  static constexpr int BIAS = T32 ? EPI_WARPS * 128 : 0;
+  static constexpr size_t SMEM = (size_t)NST * STAGE_BYTES + EPI_WARPS * WS + BIAS + sizeof(Ctrl);
+};
 
 struct Params {
   int64_t M;
@@ -88,12 +99,15 @@ __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 
 template <int MODE, bool RES32 = false>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gelu_dropout_tc_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                          const __grid_constant__ CUtensorMap tm_w,
+                                                                         const __grid_constant__ CUtensorMap tm_res,
+                                                                         const __grid_constant__ CUtensorMap tm_o32,
                                                                          const Params P) {
+  using L = Lay<MODE, RES32>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* ring = smem_raw;
   if ((smem_u32(ring) & 1023u) != 0) __trap();
-  uint8_t* sStg = ring + (size_t)STAGES * STAGE_BYTES;
-  Ctrl* ctl = reinterpret_cast<Ctrl*>(sStg + EPI_WARPS * WSTAGE);
+  uint8_t* sStg = ring + (size_t)L::NST * STAGE_BYTES;
+  Ctrl* ctl = reinterpret_cast<Ctrl*>(sStg + EPI_WARPS * L::WS + L::BIAS);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int nM = (int)((P.M + BM - 1) / BM), nN = P.N / BN, nK = P.K / BK;
@@ -105,7 +119,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
   if (warp == EPI_WARPS && lane == 0) {
     prefetch_tmap(&tm_x);
     prefetch_tmap(&tm_w);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
+    for (int s = 0; s < L::NST; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], 1); }
+    for (int w8 = 0; w8 < EPI_WARPS; ++w8) mbar_init(&ctl->rbar[w8], 1);
+    if (L::T32) { prefetch_tmap(&tm_res); prefetch_tmap(&tm_o32); }
     for (int s = 0; s < 2; ++s) { mbar_init(&ctl->acc_full[s], 1); mbar_init(&ctl->acc_free[s], CL * EPI_WARPS); }   // leader's: one arrival per epilogue warp of the pair
     fence_mbar_init();
   }
@@ -123,8 +139,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
       for (int pr = cid; pr < npairs; pr += ncl) {
         const int mp = pr / nN, n = pr - mp * nN, m = CL * mp + rank;
         for (int kb = 0; kb < nK; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&ctl->empty[s], ((it / STAGES) & 1) ^ 1);            // released by the leader's multicast commit
+          const int s = it % L::NST;
+          mbar_wait(&ctl->empty[s], ((it / L::NST) & 1) ^ 1);            // released by the leader's multicast commit
           const uint32_t fullL = mapa_u32(smem_u32(&ctl->full[s]), 0);
           if (rank == 0) mbar_expect_tx(&ctl->full[s], (uint32_t)(CL * STAGE_BYTES));   // both CTAs' tiles
           tma_load_3d_2sm(ring + (size_t)s * STAGE_BYTES, &tm_x, kb * BK, m * BM, 0, fullL);                 // rows >= M: zeros
@@ -151,8 +167,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
           tc_fence_after();
         }
         for (int kb = 0; kb < nK; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&ctl->full[s], (it / STAGES) & 1);
+          const int s = it % L::NST;
+          mbar_wait(&ctl->full[s], (it / L::NST) & 1);
           tc_fence_after();
           const uint32_t aA = aR + s * STAGE_BYTES, aB = aA + A_BYTES;
 #pragma unroll
@@ -167,7 +183,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int g = warp >> 2;                                           // accumulator column quarter
-    uint8_t* stg = sStg + warp * WSTAGE;
+    uint8_t* stg = sStg + warp * L::WS;
+    uint32_t rph = 0;                                                  // T32: residual-tile arrivals consumed
     const uint32_t tl = tmem_lane_base(tmem, warp) + g * 64;
     const int ch4 = lane & 3, r4 = lane >> 2;                          // coalesced pattern: 4 lanes per 64-byte row segment
     const float scale = P.p > 0.f ? 1.0f / (1.0f - P.p) : 1.0f;
@@ -228,13 +245,28 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
         }
       };
       prefetch_saved(0);
+      // T32: the residual tile [32 rows][32 fp32] of the NEXT 32-column half is requested as soon as the staging tile's previous
+      // store has been read - here before the accumulator wait, below behind the previous half's store
+      auto request_resid = [&](int h) {
+        if constexpr (L::T32) {
+          if (lane == 0) {
+            tma_store_wait_read();
+            if (wrow0 < P.M) {
+              mbar_expect_tx(&ctl->rbar[warp], 4096u);
+              tma_load_3d(stg, &tm_res, n * BN + g * 64 + h * 32, (int)wrow0, 0, &ctl->rbar[warp]);
+            }
+          }
+          __syncwarp();
+        }
+      };
+      request_resid(0);
       mbar_wait(&ctl->acc_full[buf], (tc >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {                                    // 32 columns at a time
         const int col0 = n * BN + g * 64 + h * 32;
         // bias of these 32 columns as fp32 in the (idle) staging area: every lane then reads it with broadcast LDS.128
-        float* sbias = reinterpret_cast<float*>(stg);
+        float* sbias = L::T32 ? reinterpret_cast<float*>(sStg + EPI_WARPS * L::WS + warp * 128) : reinterpret_cast<float*>(stg);
         if (MODE != 2 && lane < 8) {
           float4 bf4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (P.bias) {
@@ -368,42 +400,31 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
           keep = ~bor;                                                 // r >= th
         }
         if constexpr (MODE == 1 && RES32) {
-          // fp32 stream: 16 columns (64 bytes) at a time through the same staging tile - coalesced residual load, every lane
-          // picks up its row, adds keep * scale * y, writes its row back, coalesced store
-          const float* resid32 = reinterpret_cast<const float*>(P.u);
-          float* out32 = reinterpret_cast<float*>(P.out);
+          // fp32 stream: the residual tile of these 32 columns has landed in the staging tile by TMA (128-byte swizzle: 16-byte
+          // chunk q of row r at q ^ (r & 7)); every lane adds keep * scale * y to its row in place, one TMA store sends it out
+          if (wrow0 < P.M) {
+            mbar_wait(&ctl->rbar[warp], rph & 1);
+            ++rph;
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int c16 = col0 + hh * 16;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = r4 + 8 * i;
-              uint4 v4 = make_uint4(0, 0, 0, 0);
-              if (wrow0 + r < P.M) v4 = *reinterpret_cast<const uint4*>(resid32 + (wrow0 + r) * P.N + c16 + ch4 * 4);
-              *reinterpret_cast<uint4*>(stg + r * 64 + ((ch4 ^ ((r >> 1) & 3)) << 4)) = v4;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float4 r4v = *reinterpret_cast<const float4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4));
-              const uint32_t y01 = upk[8 * hh + 2 * q], y23 = upk[8 * hh + 2 * q + 1];
-              const int bit = 16 * hh + 4 * q;
+            for (int q = 0; q < 8; ++q) {
+              const uint32_t o = lane * 128 + ((q ^ (lane & 7)) << 4);
+              float4 r4v = *reinterpret_cast<const float4*>(stg + o);
+              const uint32_t y01 = upk[2 * q], y23 = upk[2 * q + 1];
+              const int bit = 4 * q;
               r4v.x += (keep >> bit) & 1u ? bf_lo(y01) * scale : 0.f;
               r4v.y += (keep >> (bit + 1)) & 1u ? bf_hi(y01) * scale : 0.f;
               r4v.z += (keep >> (bit + 2)) & 1u ? bf_lo(y23) * scale : 0.f;
               r4v.w += (keep >> (bit + 3)) & 1u ? bf_hi(y23) * scale : 0.f;
-              *reinterpret_cast<float4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = r4v;
+              *reinterpret_cast<float4*>(stg + o) = r4v;
             }
+            fence_async_smem();
             __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = r4 + 8 * i;
-              if (wrow0 + r < P.M)
-                *reinterpret_cast<uint4*>(out32 + (wrow0 + r) * P.N + c16 + ch4 * 4) =
-                    *reinterpret_cast<const uint4*>(stg + r * 64 + ((ch4 ^ ((r >> 1) & 3)) << 4));
+            if (lane == 0) {
+              tma_store_3d(&tm_o32, stg, col0, (int)wrow0, 0);         // rows >= M are clipped by the TMA unit
+              tma_store_commit();
             }
-            __syncwarp();
           }
+          if (h == 0) request_resid(1);                                // waits for that store's read, then refills the tile
           if (P.p > 0.f && row < P.M) *reinterpret_cast<uint32_t*>(P.mask + ((row * P.N + col0) >> 3)) = keep;
           continue;
         }
@@ -453,6 +474,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
       }
     }
   }
+  if (L::T32 && warp < EPI_WARPS && lane == 0) tma_store_wait_all();   // every output tile of this warp has landed
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                                      // no CTA leaves while its peer may still multicast into it
@@ -485,7 +507,8 @@ template <int MODE, bool RES32 = false>
 static int fused_linear_launch(const void* x, const void* w, const void* bias, int64_t M, int N, int K, float p, uint64_t seed,
                                uint64_t offset, const uint64_t* offset_dev, void* u_or_resid, void* out, uint8_t* mask,
                                cudaStream_t st, float* partial = nullptr, int factor = 0) {
-  CUtensorMap tm_x, tm_w;
+  using L = Lay<MODE, RES32>;
+  CUtensorMap tm_x, tm_w, tm_res, tm_o32;
   int rc = make_tmap_bf16_3d(&tm_x, x, (uint64_t)K, (uint64_t)M, 1, (uint64_t)K, (uint64_t)M * K, BM);
   if (rc != GVIT_OK) return rc;
   if (MODE != 2)
@@ -493,20 +516,28 @@ static int fused_linear_launch(const void* x, const void* w, const void* bias, i
   else
     rc = make_tmap_bf16_3d(&tm_w, w, (uint64_t)N, (uint64_t)K, 1, (uint64_t)N, (uint64_t)N * K, 64);        // W2 (K, N): [64 k][64 n] atoms
   if (rc != GVIT_OK) return rc;
+  if (L::T32) {                                                       // residual in / stream out as [32 rows][32 fp32] TMA tiles
+    rc = make_tmap_f32_3d(&tm_res, u_or_resid, (uint64_t)N, (uint64_t)M, 1, (uint64_t)N, (uint64_t)M * N, 32);
+    if (rc != GVIT_OK) return rc;
+    rc = make_tmap_f32_3d(&tm_o32, out, (uint64_t)N, (uint64_t)M, 1, (uint64_t)N, (uint64_t)M * N, 32);
+    if (rc != GVIT_OK) return rc;
+  } else {
+    tm_res = tm_x; tm_o32 = tm_x;                                      // never dereferenced
+  }
   Params P{M, N, K, p, seed, offset, offset_dev, static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(u_or_resid),
            static_cast<__nv_bfloat16*>(out), mask, partial, factor, {}};
   for (int r = 0; r < GVIT_PHILOX_ROUNDS; ++r) {
     P.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
     P.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
   }
-  GVIT_CHECK_CUDA(cudaFuncSetAttribute(fc1_gelu_dropout_tc_kernel<MODE, RES32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  GVIT_CHECK_CUDA(cudaFuncSetAttribute(fc1_gelu_dropout_tc_kernel<MODE, RES32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
   const int64_t ngroups = (((M + BM - 1) / BM + CL - 1) / CL) * (N / BN);
   int max_clusters = 0;
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((num_sms() / CL) * CL);
     cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.dynamicSmemBytes = L::SMEM;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = CL; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
@@ -519,7 +550,7 @@ static int fused_linear_launch(const void* x, const void* w, const void* bias, i
   }
   const int64_t want = CL * ngroups, cap = (int64_t)CL * max_clusters;
   const int grid = (int)(want < cap ? want : cap);                  // whole, co-resident clusters: a persistent grid
-  fc1_gelu_dropout_tc_kernel<MODE, RES32><<<grid, THREADS, SMEM_BYTES, st>>>(tm_x, tm_w, P);
+  fc1_gelu_dropout_tc_kernel<MODE, RES32><<<grid, THREADS, L::SMEM, st>>>(tm_x, tm_w, tm_res, tm_o32, P);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }
