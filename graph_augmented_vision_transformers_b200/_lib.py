@@ -12,7 +12,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgvit.so")
+# GVIT_LIB=<path>: load another build of the library (same ABI version) - same-box A/B runs of bench.py / the tools
+LIB_PATH = os.environ.get("GVIT_LIB") or os.path.join(_HERE, "lib", "libgvit.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "gvit.h")
 
 GVIT_F32, GVIT_BF16 = 0, 1
