@@ -258,6 +258,9 @@ def kernel_rooflines(dev, B, peaks, iters=10, only=None):
         # proj + proj_drop + residual as the step runs it: fp32 residual stream in and out (fc2 + drop + residual is the same kernel at K = 4 D)
         "proj_fused": (lambda i: _call("gvit_linear_dropout_residual_fwd", _ptr(hs[i % R]), _ptr(W), _ptr(bias), _ptr(xs32[i % 2]), B * N, D, D, 0.1, 1234, 0, None, dt, 0, _ptr(out32), _ptr(m1), st),
                        B * N * D * e + 2 * B * N * D * 4 + D * D * e + B * N * D // 8, 2.0 * B * N * D * D, "auto", 12),
+        # fc2 + drop + residual: the same kernel at K = 4 D (tensor-bound)
+        "fc2_fused": (lambda i: _call("gvit_linear_dropout_residual_fwd", _ptr(u4[i % 2]), _ptr(W2), _ptr(bias), _ptr(xs32[i % 2]), B * N, D, 4 * D, 0.1, 1234, 0, None, dt, 0, _ptr(out32), _ptr(m1), st),
+                      B * N * 4 * D * e + 2 * B * N * D * 4 + 4 * D * D * e + B * N * D // 8, 2.0 * B * N * D * 4 * D, "auto", 12),
         "proj_fused_bf16_stream": (lambda i: _call("gvit_linear_dropout_residual_fwd", _ptr(hs[i % R]), _ptr(W), _ptr(bias), _ptr(xs[i % R]), B * N, D, D, 0.1, 1234, 0, None, dt, dt, _ptr(out), _ptr(m1), st),
                                    3 * B * N * D * e + D * D * e + B * N * D // 8, 2.0 * B * N * D * D, "hbm", 0),
         "fc2_bwd_fused": (lambda i: _call("gvit_linear_gelu_dropout_bwd", _ptr(hs[i % R]), _ptr(W2), _ptr(u4[i % 2]), None, B * N, 4 * D, D, 0.1, dt, 1, _ptr(o4), _ptr(cs_out), _ptr(part4), st),
