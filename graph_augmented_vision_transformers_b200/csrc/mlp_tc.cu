@@ -60,9 +60,11 @@ struct __align__(8) Ctrl {
 // Shared-memory layout per instantiation.  The fp32-stream Linear + dropout + residual (MODE 1, RES32) moves its residual / output
 // tiles by TMA as [32 rows][32 fp32] = 4 KB per epilogue warp (whole 128-byte lines; no registers, no LSU round trips), paid for
 // with one ring stage (5 instead of 6) and a separate 128-byte bias row per warp (the tile is the TMA target).
-template <int MODE, bool RES32>
+// TILES = false keeps the register-staged fp32 epilogue and all six stages: the K = 4 D product (fc2) is tensor-bound, its epilogue is
+// hidden, and the sixth stage is worth 2.5 % there (0.1910 vs 0.1958 ms).
+template <int MODE, bool RES32, bool TILES>
 struct Lay {
-  static constexpr bool T32 = MODE == 1 && RES32;
+  static constexpr bool T32 = MODE == 1 && RES32 && TILES;
   static constexpr int NST = T32 ? 5 : STAGES;
   static constexpr int WS = T32 ? 4096 : WSTAGE;
   static constexpr int BIAS = T32 ? EPI_WARPS * 128 : 0;
@@ -96,13 +98,13 @@ __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 
 // RES32 (MODE 1 only): the residual input and the output are fp32 - the residual stream torch.autocast keeps in fp32
 // (vit.py:207-211,117-118: cat / add with the fp32 cls_token / pos_embed promote) - while the branch value is still
 // rounded to bf16 first, exactly what `x + proj_drop(proj(o))` computes under autocast.
-template <int MODE, bool RES32 = false>
+template <int MODE, bool RES32 = false, bool TILES = false>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gelu_dropout_tc_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                          const __grid_constant__ CUtensorMap tm_w,
                                                                          const __grid_constant__ CUtensorMap tm_res,
                                                                          const __grid_constant__ CUtensorMap tm_o32,
                                                                          const Params P) {
-  using L = Lay<MODE, RES32>;
+  using L = Lay<MODE, RES32, TILES>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* ring = smem_raw;
   if ((smem_u32(ring) & 1023u) != 0) __trap();
@@ -399,7 +401,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
           }
           keep = ~bor;                                                 // r >= th
         }
-        if constexpr (MODE == 1 && RES32) {
+        if constexpr (L::T32) {
           // fp32 stream: the residual tile of these 32 columns has landed in the staging tile by TMA (128-byte swizzle: 16-byte
           // chunk q of row r at q ^ (r & 7)); every lane adds keep * scale * y to its row in place, one TMA store sends it out
           if (wrow0 < P.M) {
@@ -425,6 +427,46 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) fc1_gel
             }
           }
           if (h == 0) request_resid(1);                                // waits for that store's read, then refills the tile
+          if (P.p > 0.f && row < P.M) *reinterpret_cast<uint32_t*>(P.mask + ((row * P.N + col0) >> 3)) = keep;
+          continue;
+        }
+        if constexpr (MODE == 1 && RES32 && !TILES) {
+          // fp32 stream: 16 columns (64 bytes) at a time through the same staging tile - coalesced residual load, every lane
+          // picks up its row, adds keep * scale * y, writes its row back, coalesced store
+          const float* resid32 = reinterpret_cast<const float*>(P.u);
+          float* out32 = reinterpret_cast<float*>(P.out);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int c16 = col0 + hh * 16;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = r4 + 8 * i;
+              uint4 v4 = make_uint4(0, 0, 0, 0);
+              if (wrow0 + r < P.M) v4 = *reinterpret_cast<const uint4*>(resid32 + (wrow0 + r) * P.N + c16 + ch4 * 4);
+              *reinterpret_cast<uint4*>(stg + r * 64 + ((ch4 ^ ((r >> 1) & 3)) << 4)) = v4;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4 r4v = *reinterpret_cast<const float4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4));
+              const uint32_t y01 = upk[8 * hh + 2 * q], y23 = upk[8 * hh + 2 * q + 1];
+              const int bit = 16 * hh + 4 * q;
+              r4v.x += (keep >> bit) & 1u ? bf_lo(y01) * scale : 0.f;
+              r4v.y += (keep >> (bit + 1)) & 1u ? bf_hi(y01) * scale : 0.f;
+              r4v.z += (keep >> (bit + 2)) & 1u ? bf_lo(y23) * scale : 0.f;
+              r4v.w += (keep >> (bit + 3)) & 1u ? bf_hi(y23) * scale : 0.f;
+              *reinterpret_cast<float4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = r4v;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = r4 + 8 * i;
+              if (wrow0 + r < P.M)
+                *reinterpret_cast<uint4*>(out32 + (wrow0 + r) * P.N + c16 + ch4 * 4) =
+                    *reinterpret_cast<const uint4*>(stg + r * 64 + ((ch4 ^ ((r >> 1) & 3)) << 4));
+            }
+            __syncwarp();
+          }
           if (P.p > 0.f && row < P.M) *reinterpret_cast<uint32_t*>(P.mask + ((row * P.N + col0) >> 3)) = keep;
           continue;
         }
@@ -503,11 +545,11 @@ __global__ void __launch_bounds__(256) partial_colsum_kernel(const float* __rest
 
 bool fc1_tc_supported(int64_t M, int N, int K) { return M >= 1 && N >= BN && N % BN == 0 && K >= BK && K % BK == 0; }
 
-template <int MODE, bool RES32 = false>
+template <int MODE, bool RES32 = false, bool TILES = false>
 static int fused_linear_launch(const void* x, const void* w, const void* bias, int64_t M, int N, int K, float p, uint64_t seed,
                                uint64_t offset, const uint64_t* offset_dev, void* u_or_resid, void* out, uint8_t* mask,
                                cudaStream_t st, float* partial = nullptr, int factor = 0) {
-  using L = Lay<MODE, RES32>;
+  using L = Lay<MODE, RES32, TILES>;
   CUtensorMap tm_x, tm_w, tm_res, tm_o32;
   int rc = make_tmap_bf16_3d(&tm_x, x, (uint64_t)K, (uint64_t)M, 1, (uint64_t)K, (uint64_t)M * K, BM);
   if (rc != GVIT_OK) return rc;
@@ -530,7 +572,7 @@ static int fused_linear_launch(const void* x, const void* w, const void* bias, i
     P.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
     P.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
   }
-  GVIT_CHECK_CUDA(cudaFuncSetAttribute(fc1_gelu_dropout_tc_kernel<MODE, RES32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
+  GVIT_CHECK_CUDA(cudaFuncSetAttribute(fc1_gelu_dropout_tc_kernel<MODE, RES32, TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM));
   const int64_t ngroups = (((M + BM - 1) / BM + CL - 1) / CL) * (N / BN);
   int max_clusters = 0;
   {
@@ -543,14 +585,14 @@ static int fused_linear_launch(const void* x, const void* w, const void* bias, i
     attr.val.clusterDim.x = CL; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, fc1_gelu_dropout_tc_kernel<MODE, RES32>, &cfg) != cudaSuccess || max_clusters < 1) {
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, fc1_gelu_dropout_tc_kernel<MODE, RES32, TILES>, &cfg) != cudaSuccess || max_clusters < 1) {
       (void)cudaGetLastError();
       max_clusters = num_sms() / CL;
     }
   }
   const int64_t want = CL * ngroups, cap = (int64_t)CL * max_clusters;
   const int grid = (int)(want < cap ? want : cap);                  // whole, co-resident clusters: a persistent grid
-  fc1_gelu_dropout_tc_kernel<MODE, RES32><<<grid, THREADS, L::SMEM, st>>>(tm_x, tm_w, tm_res, tm_o32, P);
+  fc1_gelu_dropout_tc_kernel<MODE, RES32, TILES><<<grid, THREADS, L::SMEM, st>>>(tm_x, tm_w, tm_res, tm_o32, P);
   GVIT_CHECK_LAUNCH();
   return GVIT_OK;
 }
@@ -563,8 +605,11 @@ int fc1_gelu_dropout_fwd_tc(const void* x, const void* w, const void* bias, int6
 int linear_dropout_residual_fwd_tc(const void* x, const void* w, const void* bias, const void* resid, int64_t M, int N, int K, float p,
                                    uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int resid_dtype, void* out, uint8_t* mask,
                                    cudaStream_t st) {
-  if (resid_dtype == GVIT_F32)
-    return fused_linear_launch<1, true>(x, w, bias, M, N, K, p, seed, offset, offset_dev, const_cast<void*>(resid), out, mask, st);
+  if (resid_dtype == GVIT_F32) {
+    // HBM-bound products (K up to 2 D): TMA tiles for the fp32 residual / output; tensor-bound ones keep the sixth ring stage
+    if (K <= 1536) return fused_linear_launch<1, true, true>(x, w, bias, M, N, K, p, seed, offset, offset_dev, const_cast<void*>(resid), out, mask, st);
+    return fused_linear_launch<1, true, false>(x, w, bias, M, N, K, p, seed, offset, offset_dev, const_cast<void*>(resid), out, mask, st);
+  }
   return fused_linear_launch<1>(x, w, bias, M, N, K, p, seed, offset, offset_dev, const_cast<void*>(resid), out, mask, st);
 }
 
