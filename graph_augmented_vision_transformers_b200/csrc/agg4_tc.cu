@@ -349,13 +349,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
         tc_fence_after();
         uint32_t pk0[16], pk1[16];
         {
-          float v[32];
-          tmem_ld32(src, v);
+          float va[32], vb[32];
+          tmem_ld32x2(src, src + 32, va, vb);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) pk0[e] = pack2(v[2 * e], v[2 * e + 1]);
-          tmem_ld32(src + 32, v);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) pk1[e] = pack2(v[2 * e], v[2 * e + 1]);
+          for (int e = 0; e < 16; ++e) { pk0[e] = pack2(va[2 * e], va[2 * e + 1]); pk1[e] = pack2(vb[2 * e], vb[2 * e + 1]); }
         }
         if (!par) {
           tc_fence_before();
@@ -425,8 +422,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) agg4_tc_
           GVIT_TR(18);
           ++full_seen;
           tc_fence_after();
-          tmem_ld32(tl + T_OUT + g * 64, v0);
-          tmem_ld32(tl + T_OUT + g * 64 + 32, v1);
+          tmem_ld32x2(tl + T_OUT + g * 64, tl + T_OUT + g * 64 + 32, v0, v1);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(out_freeL);
